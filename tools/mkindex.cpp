@@ -1,0 +1,383 @@
+// spumoni_mkindex -- FIXTURE TOOL: synthetic references / reads and a stand-in for `spumoni build`.
+//
+// Not part of the query hot path and never linked into libspumoni_b200.so.  The reference builds
+// its index by shelling out to Big-BWT / pfp_thresholds (/root/reference/src/spumoni.cpp:442-545)
+// which do not exist in this image, so this tool produces the same artefacts directly:
+//   <prefix>.fa                      forward + "_rev_comp" records  (refbuilder.cpp:349-379)
+//   <prefix>.fa.bwt.heads/.bwt.len   run heads / 5-byte run lengths (ms_rle_string.hpp:246-247)
+//   <prefix>.fa.thr_pos              5-byte thresholds per run      (thresholds_ds.hpp:405-423)
+//   <prefix>.fa.ssa/.esa             5+5-byte (pos, SA) samples     (compute_ms_pml.cpp:428-436)
+//   <prefix>.fa.thrbv.spumoni        pml_pointers::serialize        (compute_ms_pml.cpp:192-213)
+//   <prefix>.fa.thrbv.ms             ms_pointers::serialize         (compute_ms_pml.cpp:517-542)
+//   *.pmlnulldb / *.msnulldb         EmpNullDatabase::serialize     (emp_null_database.cpp:82-102)
+// Threshold definition (MONI): for consecutive c-runs ending at e and starting at s, the leftmost
+// t in (e, s] minimising LCP[t]; 0 for the first run of a character.
+#include <algorithm>
+#include <cctype>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "sais.hpp"
+#include "sdsl_writer.hpp"
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static void die(const std::string& m) {
+    std::fprintf(stderr, "spumoni_mkindex: %s\n", m.c_str());
+    std::exit(1);
+}
+
+struct Rng {  // splitmix64: deterministic across platforms
+    uint64_t s;
+    explicit Rng(uint64_t seed) : s(seed) {}
+    inline uint64_t next() {
+        uint64_t z = (s += 0x9E3779B97F4A7C15ULL);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+    inline double unif() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+    inline uint64_t below(uint64_t n) { return (uint64_t)(((__uint128_t)next() * n) >> 64); }
+};
+static const char ACGT[4] = {'A', 'C', 'G', 'T'};
+
+typedef std::map<std::string, std::string> Args;
+static Args parse_args(int argc, char** argv, int from) {
+    Args a;
+    for (int i = from; i < argc; i++) {
+        std::string k = argv[i];
+        if (k.rfind("--", 0) != 0) die("unexpected argument " + k);
+        k = k.substr(2);
+        if (i + 1 < argc && std::string(argv[i + 1]).rfind("--", 0) != 0) a[k] = argv[++i];
+        else a[k] = "1";
+    }
+    return a;
+}
+static std::string get(const Args& a, const std::string& k, const std::string& d = "") {
+    auto it = a.find(k);
+    return it == a.end() ? d : it->second;
+}
+static bool has(const Args& a, const std::string& k) { return a.count(k) > 0; }
+
+// ---------------------------------------------------------------- FASTA
+struct Fasta {
+    std::vector<std::string> names, seqs;
+};
+static Fasta read_fasta(const std::string& path) {
+    std::ifstream in(path);
+    if (!in) die("cannot open " + path);
+    Fasta f;
+    std::string line;
+    while (std::getline(in, line)) {
+        while (!line.empty() && std::isspace((unsigned char)line.back())) line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            size_t e = line.find_first_of(" \t", 1);
+            f.names.push_back(line.substr(1, e == std::string::npos ? std::string::npos : e - 1));
+            f.seqs.emplace_back();
+        } else {
+            if (f.seqs.empty()) die("FASTA does not start with '>'");
+            f.seqs.back() += line;
+        }
+    }
+    return f;
+}
+static std::string revcomp(const std::string& s) {  // complement table of refbuilder.cpp:22-31 on ACGTN etc.
+    static unsigned char tab[256];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 256; i++) tab[i] = (unsigned char)i;
+        const char* from = "ABCDGHKMNRSTVWXYabcdghkmnrstvwxy";
+        const char* to = "TVGHCDMKNYSABWXRtvghcdmknysabwxr";
+        for (int i = 0; from[i]; i++) tab[(unsigned char)from[i]] = (unsigned char)to[i];
+        tab['U'] = 'A'; tab['u'] = 'a';
+        init = true;
+    }
+    std::string r(s.size(), 0);
+    for (size_t i = 0; i < s.size(); i++) r[i] = (char)tab[(unsigned char)s[s.size() - 1 - i]];
+    return r;
+}
+
+// ---------------------------------------------------------------- genome
+static int cmd_genome(const Args& a) {
+    std::string kind = get(a, "kind", "iid"), out = get(a, "out");
+    uint64_t len = std::stoull(get(a, "len", "1000000"));
+    uint64_t haps = std::stoull(get(a, "haps", "1"));
+    double snp = std::stod(get(a, "snp", "0.001")), indel = std::stod(get(a, "indel", "0.0001"));
+    Rng rng(std::stoull(get(a, "seed", "1")));
+    if (out.empty()) die("genome: --out required");
+    std::ofstream o(out);
+    if (kind == "iid") {
+        std::string s(len, 'A');
+        for (auto& c : s) c = ACGT[rng.next() & 3];
+        o << ">seq0\n" << s << "\n";
+    } else if (kind == "pangenome") {
+        uint64_t al = len / haps;
+        std::string anc(al, 'A');
+        for (auto& c : anc) c = ACGT[rng.next() & 3];
+        for (uint64_t h = 0; h < haps; h++) {
+            std::string s;
+            s.reserve(al + al / 100);
+            for (uint64_t i = 0; i < al; i++) {
+                double r = rng.unif();
+                if (r < snp) {
+                    char c;
+                    do c = ACGT[rng.next() & 3]; while (c == anc[i]);
+                    s.push_back(c);
+                } else if (r < snp + indel) {
+                    uint64_t l = 1 + rng.below(5);
+                    if (rng.next() & 1) { for (uint64_t k = 0; k < l; k++) s.push_back(ACGT[rng.next() & 3]); s.push_back(anc[i]); }
+                    else i += l - 1;  // deletion of l bases
+                } else
+                    s.push_back(anc[i]);
+            }
+            o << ">hap" << h << "\n" << s << "\n";
+        }
+    } else
+        die("genome: unknown --kind " + kind);
+    return 0;
+}
+
+// ---------------------------------------------------------------- build
+static void put5(std::ofstream& o, uint64_t v) { o.write((const char*)&v, 5); }
+
+template <typename Idx>
+static void build_rlbwt(const std::vector<uint8_t>& T /* with terminator 0 at end */, sdslw::RlbwtParts& P, bool verbose) {
+    const uint64_t n = T.size();
+    double t0 = now_s();
+    std::vector<Idx> SA(n);
+    suffix_array_sais<Idx>(T.data(), SA.data(), (Idx)n);
+    if (verbose) std::fprintf(stderr, "[mkindex] suffix array: %.2f s\n", now_s() - t0);
+    t0 = now_s();
+    // PLCP via the Phi algorithm (chunk-parallel), then LCP in SA order
+    std::vector<Idx> plcp(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) plcp[(size_t)SA[i]] = i ? SA[i - 1] : (Idx)-1;  // phi
+    {
+        int nt = 1;
+#ifdef _OPENMP
+        nt = omp_get_max_threads();
+#endif
+        int nchunks = nt * 16;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < nchunks; c++) {
+            uint64_t lo = n * (uint64_t)c / nchunks, hi = n * (uint64_t)(c + 1) / nchunks;
+            uint64_t h = 0;
+            for (uint64_t i = lo; i < hi; i++) {
+                Idx j = plcp[i];
+                if (j < 0) { plcp[i] = 0; h = 0; continue; }
+                while (i + h < n && (uint64_t)j + h < n && T[i + h] == T[(uint64_t)j + h]) h++;
+                plcp[i] = (Idx)h;
+                if (h) h--;
+            }
+        }
+    }
+    std::vector<Idx> lcp(n);
+    std::vector<uint8_t> bwt(n);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        lcp[i] = plcp[(size_t)SA[i]];
+        bwt[i] = SA[i] ? T[(size_t)SA[i] - 1] : T[n - 1];
+    }
+    std::vector<Idx>().swap(plcp);
+    if (verbose) std::fprintf(stderr, "[mkindex] lcp+bwt: %.2f s\n", now_s() - t0);
+    t0 = now_s();
+    // runs, thresholds, samples
+    P.n = n;
+    bool present[256] = {false};
+    for (uint64_t i = 0; i < n; i++) present[bwt[i]] = true;
+    std::vector<int> syms;
+    for (int c = 0; c < 256; c++) if (present[c]) syms.push_back(c);
+    const uint64_t INF = ~0ULL;
+    uint64_t minl[256], minp[256];
+    bool seen[256] = {false};
+    for (int c = 0; c < 256; c++) { minl[c] = INF; minp[c] = 0; }
+    uint64_t i = 0;
+    while (i < n) {
+        uint8_t c = bwt[i];
+        uint64_t j = i;
+        // position i: update all symbols with lcp[i], then read off c's threshold
+        {
+            uint64_t l = (uint64_t)lcp[i];
+            for (int s : syms) if (l < minl[s]) { minl[s] = l; minp[s] = i; }
+        }
+        uint64_t thr = seen[c] ? minp[c] : 0;
+        j = i + 1;
+        while (j < n && bwt[j] == c) {
+            uint64_t l = (uint64_t)lcp[j];
+            for (int s : syms) if (l < minl[s]) { minl[s] = l; minp[s] = j; }
+            j++;
+        }
+        P.heads.push_back(c);
+        P.lens.push_back(j - i);
+        P.thr.push_back(thr);
+        P.ssa.push_back((uint64_t)SA[i]);
+        P.esa.push_back((uint64_t)SA[j - 1]);
+        seen[c] = true;
+        minl[c] = INF;  // range for the next c-run starts after position j-1
+        i = j;
+    }
+    if (verbose)
+        std::fprintf(stderr, "[mkindex] runs/thresholds: %.2f s  (n=%llu r=%llu n/r=%.2f)\n", now_s() - t0,
+                     (unsigned long long)n, (unsigned long long)P.heads.size(), (double)n / P.heads.size());
+}
+
+static int cmd_build(const Args& a) {
+    std::string input = get(a, "input"), prefix = get(a, "prefix");
+    if (input.empty() || prefix.empty()) die("build: --input and --prefix required");
+    bool use_rc = !has(a, "no-revcomp"), verbose = has(a, "verbose");
+    bool want_pml = has(a, "pml") || !has(a, "ms"), want_ms = has(a, "ms");
+    bool keep = has(a, "keep");
+    Fasta f = read_fasta(input);
+    std::string ref = prefix + ".fa";
+    std::vector<uint8_t> T;
+    {
+        std::ofstream o(ref);
+        if (!o) die("cannot write " + ref);
+        for (size_t k = 0; k < f.seqs.size(); k++) {
+            std::string s = f.seqs[k];
+            for (auto& c : s) c = (char)std::toupper((unsigned char)c);
+            o << '>' << f.names[k] << '\n' << s << '\n';
+            T.insert(T.end(), s.begin(), s.end());
+            if (use_rc) {
+                std::string r = revcomp(s);
+                o << '>' << f.names[k] << "_rev_comp" << '\n' << r << '\n';
+                T.insert(T.end(), r.begin(), r.end());
+            }
+        }
+    }
+    for (auto c : T) if (c <= 1) die("input contains bytes <= 0x01");
+    T.push_back(0);
+    sdslw::RlbwtParts P;
+    if (T.size() < (1ULL << 31)) build_rlbwt<int32_t>(T, P, verbose);
+    else build_rlbwt<int64_t>(T, P, verbose);
+    double t0 = now_s();
+    if (keep) {
+        std::ofstream h(ref + ".bwt.heads"), l(ref + ".bwt.len"), t(ref + ".thr_pos"), s(ref + ".ssa"), e(ref + ".esa");
+        uint64_t pos = 0;
+        for (size_t k = 0; k < P.heads.size(); k++) {
+            h.put((char)P.heads[k]);
+            put5(l, P.lens[k]);
+            put5(t, P.thr[k]);
+            put5(s, pos); put5(s, P.ssa[k]);
+            pos += P.lens[k];
+            put5(e, pos - 1); put5(e, P.esa[k]);
+        }
+    }
+    if (want_pml) {
+        std::ofstream o(ref + ".thrbv.spumoni", std::ios::binary);
+        sdslw::write_pml_index(o, P);
+    }
+    if (want_ms) {
+        std::ofstream o(ref + ".thrbv.ms", std::ios::binary);
+        sdslw::write_ms_index(o, P);
+    }
+    if (verbose) std::fprintf(stderr, "[mkindex] serialise: %.2f s\n", now_s() - t0);
+    std::printf("{\"n\": %llu, \"r\": %llu}\n", (unsigned long long)P.n, (unsigned long long)P.heads.size());
+    return 0;
+}
+
+// ---------------------------------------------------------------- reads
+static int cmd_reads(const Args& a) {
+    std::string ref = get(a, "ref"), out = get(a, "out"), bin = get(a, "bin");
+    if (ref.empty() || (out.empty() && bin.empty())) die("reads: --ref and --out/--bin required");
+    uint64_t N = std::stoull(get(a, "n", "1000")), L = std::stoull(get(a, "len", "150"));
+    uint64_t Lmax = std::stoull(get(a, "len-max", "0"));  // if set: lengths uniform in [len, len-max]
+    double sub = std::stod(get(a, "sub", "0.01")), ins = std::stod(get(a, "ins", "0")), del = std::stod(get(a, "del", "0"));
+    double neg = std::stod(get(a, "neg-frac", "0.5"));
+    uint64_t seed = std::stoull(get(a, "seed", "2"));
+    Fasta f = read_fasta(ref);
+    std::string T;
+    for (auto& s : f.seqs) T += s;
+    if (T.size() < 2) die("reads: reference too short");
+    std::vector<uint64_t> off(N + 1, 0);
+    {
+        for (uint64_t r = 0; r < N; r++) {
+            uint64_t len = L;
+            if (Lmax > L) { Rng g(seed * 0x100000001B3ULL + r * 2 + 1); len = L + g.below(Lmax - L + 1); }
+            off[r + 1] = off[r] + len;
+        }
+    }
+    std::vector<uint8_t> buf(off[N]);
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < (int64_t)N; r++) {
+        Rng g((seed << 32) ^ (uint64_t)r * 0x9E3779B97F4A7C15ULL);
+        uint64_t len = off[r + 1] - off[r];
+        uint8_t* o = buf.data() + off[r];
+        if (g.unif() < neg) {
+            for (uint64_t k = 0; k < len; k++) o[k] = ACGT[g.next() & 3];
+        } else {
+            uint64_t p = g.below(T.size());
+            uint64_t k = 0;
+            while (k < len) {
+                if (p >= T.size()) p = 0;
+                double x = g.unif();
+                if (x < ins) o[k++] = ACGT[g.next() & 3];
+                else if (x < ins + del) p++;
+                else if (x < ins + del + sub) {
+                    char c;
+                    do c = ACGT[g.next() & 3]; while (c == T[p]);
+                    o[k++] = (uint8_t)c; p++;
+                } else o[k++] = (uint8_t)T[p++];
+            }
+        }
+    }
+    if (!out.empty()) {
+        std::ofstream o(out, std::ios::binary);
+        std::string line;
+        for (uint64_t r = 0; r < N; r++) {
+            line = ">read_" + std::to_string(r) + "\n";
+            o.write(line.data(), (std::streamsize)line.size());
+            o.write((const char*)buf.data() + off[r], (std::streamsize)(off[r + 1] - off[r]));
+            o.put('\n');
+        }
+    }
+    if (!bin.empty()) {
+        std::ofstream o(bin, std::ios::binary), q(bin + ".off", std::ios::binary);
+        o.write((const char*)buf.data(), (std::streamsize)buf.size());
+        q.write((const char*)off.data(), (std::streamsize)(off.size() * 8));
+    }
+    std::printf("{\"reads\": %llu, \"bases\": %llu}\n", (unsigned long long)N, (unsigned long long)off[N]);
+    return 0;
+}
+
+// ---------------------------------------------------------------- nulldb
+static int cmd_nulldb(const Args& a) {
+    std::string stats = get(a, "stats"), out = get(a, "out");
+    if (stats.empty() || out.empty()) die("nulldb: --stats (u64 LE binary) and --out required");
+    std::ifstream in(stats, std::ios::binary | std::ios::ate);
+    if (!in) die("cannot open " + stats);
+    size_t bytes = (size_t)in.tellg();
+    in.seekg(0);
+    std::vector<uint64_t> v(bytes / 8);
+    in.read((char*)v.data(), (std::streamsize)(v.size() * 8));
+    std::ofstream o(out, std::ios::binary);
+    sdslw::write_null_db(o, v, std::stod(get(a, "ks-thr", "0.0")));
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 2) die("usage: spumoni_mkindex genome|build|reads|nulldb [--key value ...]");
+    std::string cmd = argv[1];
+    Args a = parse_args(argc, argv, 2);
+#ifdef _OPENMP
+    if (has(a, "threads")) omp_set_num_threads(std::stoi(get(a, "threads")));
+#endif
+    if (cmd == "genome") return cmd_genome(a);
+    if (cmd == "build") return cmd_build(a);
+    if (cmd == "reads") return cmd_reads(a);
+    if (cmd == "nulldb") return cmd_nulldb(a);
+    die("unknown command " + cmd);
+    return 1;
+}

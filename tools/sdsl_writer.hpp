@@ -1,0 +1,429 @@
+// Writers for the on-disk structures `spumoni build` serialises.
+//
+// FIXTURE CODE (not on the query hot path): no reference binary exists in this image, so test and
+// benchmark indexes are produced here in the reference's own byte format.  The layouts below
+// restate, from the published sdsl-lite v2.1.1 / maxrossi91 r-index sources (NOT present under
+// /root/reference -- "parity unpinned"), what these calls write:
+//   pml_pointers::serialize   /root/reference/src/compute_ms_pml.cpp:192-213
+//   ms_pointers::serialize    /root/reference/src/compute_ms_pml.cpp:517-542
+//   my_serialize(vector)      /root/reference/include/common.hpp:458-465
+//   thr_bv::serialize         /root/reference/include/thresholds_ds.hpp:502-512
+//   EmpNullDatabase::serialize /root/reference/src/emp_null_database.cpp:82-102
+//   ri::rle_string / ri::sparse_sd_vector / ri::huff_string ::serialize   (third party)
+//   sdsl::int_vector / sd_vector / select_support_mcl / rank_support_v / wt_huff (third party)
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <ostream>
+#include <queue>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace sdslw {
+
+inline uint32_t hi(uint64_t x) { return x ? 63 - __builtin_clzll(x) : 0; }  // sdsl::bits::hi
+
+inline void put_u64(std::ostream& o, uint64_t v) { o.write((const char*)&v, 8); }
+inline void put_u16(std::ostream& o, uint16_t v) { o.write((const char*)&v, 2); }
+inline void put_u8(std::ostream& o, uint8_t v) { o.write((const char*)&v, 1); }
+inline void put_f64(std::ostream& o, double v) { o.write((const char*)&v, 8); }
+
+// sdsl::int_vector<0> (width stored) / bit_vector / int_vector<64> (width implied)
+struct IntVec {
+    uint64_t bit_size = 0;
+    uint8_t width = 64;
+    std::vector<uint64_t> w;
+    IntVec() {}
+    IntVec(uint64_t n, uint8_t width_) : bit_size(n * width_), width(width_), w((n * width_ + 63) / 64, 0) {}
+    uint64_t size() const { return width ? bit_size / width : 0; }
+    bool empty() const { return bit_size == 0; }
+    inline void set(uint64_t i, uint64_t v) {
+        uint64_t b = i * width;
+        uint32_t off = b & 63;
+        uint64_t mask = width == 64 ? ~0ULL : ((1ULL << width) - 1);
+        v &= mask;
+        w[b >> 6] = (w[b >> 6] & ~(mask << off)) | (v << off);
+        if (off + width > 64) {
+            uint32_t done = 64 - off;
+            w[(b >> 6) + 1] = (w[(b >> 6) + 1] & ~(mask >> done)) | (v >> done);
+        }
+    }
+    inline uint64_t get(uint64_t i) const {
+        uint64_t b = i * width;
+        uint32_t off = b & 63;
+        uint64_t mask = width == 64 ? ~0ULL : ((1ULL << width) - 1);
+        uint64_t v = w[b >> 6] >> off;
+        if (off + width > 64) v |= w[(b >> 6) + 1] << (64 - off);
+        return v & mask;
+    }
+    inline bool bit(uint64_t i) const { return (w[i >> 6] >> (i & 63)) & 1; }
+    inline void set_bit(uint64_t i) { w[i >> 6] |= 1ULL << (i & 63); }
+    void write(std::ostream& o, bool with_width) const {
+        put_u64(o, bit_size);
+        if (with_width) put_u8(o, width);
+        o.write((const char*)w.data(), (std::streamsize)(w.size() * 8));
+    }
+};
+inline IntVec make_bitvec(uint64_t nbits) {
+    IntVec v;
+    v.bit_size = nbits;
+    v.width = 1;
+    v.w.assign((nbits + 63) / 64, 0);
+    return v;
+}
+
+// sdsl::select_support_mcl<t_b,1>::init_slow + serialize
+inline void write_select_mcl(std::ostream& o, const IntVec& bv, bool ones) {
+    const uint64_t SB = 4096;
+    uint64_t capacity = ((bv.bit_size + 63) >> 6) << 6;
+    uint64_t logn = hi(capacity) + 1, logn4 = logn * logn * logn * logn;
+    uint64_t arg_cnt = 0;
+    for (uint64_t i = 0; i < bv.w.size(); i++) arg_cnt += __builtin_popcountll(bv.w[i]);
+    if (!ones) arg_cnt = bv.bit_size - arg_cnt;
+    put_u64(o, arg_cnt);
+    if (!arg_cnt) return;
+    uint64_t sb = (arg_cnt + SB - 1) / SB;
+    IntVec superblock(sb, (uint8_t)logn);
+    std::vector<IntVec> mini(sb), lng(sb);
+    bool any_long = false;
+    std::vector<uint64_t> argpos(SB);
+    uint64_t cnt = 0, sb_cnt = 0;
+    for (uint64_t i = 0; i < bv.bit_size; i++) {
+        if (bv.bit(i) != ones) continue;
+        argpos[cnt % SB] = i;
+        ++cnt;
+        if (cnt % SB == 0 || cnt == arg_cnt) {
+            superblock.set(sb_cnt, argpos[0]);
+            uint64_t last = (cnt - 1) % SB;
+            uint64_t pos_diff = argpos[last] - argpos[0];
+            if (pos_diff > logn4) {
+                any_long = true;
+                lng[sb_cnt] = IntVec(SB, (uint8_t)(hi(argpos[last]) + 1));
+                for (uint64_t j = 0; j <= last; j++) lng[sb_cnt].set(j, argpos[j]);
+            } else {
+                mini[sb_cnt] = IntVec(64, (uint8_t)(hi(pos_diff) + 1));
+                for (uint64_t j = 0; j <= last; j += 64) mini[sb_cnt].set(j / 64, argpos[j] - argpos[0]);
+            }
+            ++sb_cnt;
+        }
+    }
+    superblock.write(o, true);
+    IntVec mini_or_long = make_bitvec(any_long ? sb : 0);
+    if (any_long)
+        for (uint64_t i = 0; i < sb; i++)
+            if (!mini[i].empty()) mini_or_long.set_bit(i);
+    mini_or_long.write(o, false);
+    for (uint64_t i = 0; i < sb; i++) {
+        if (any_long && !mini_or_long.bit(i)) lng[i].write(o, true);
+        else mini[i].write(o, true);
+    }
+}
+
+// sdsl::rank_support_v<1,1> over bv: one int_vector<64>
+inline IntVec build_rank_v(const IntVec& bv) {
+    uint64_t capacity = ((bv.bit_size + 63) >> 6) << 6;
+    uint64_t nblk = ((capacity >> 9) + 1) << 1;
+    IntVec bb(nblk, 64);
+    uint64_t words = capacity >> 6;
+    uint64_t j = 0, sum = words ? (uint64_t)__builtin_popcountll(bv.w[0]) : 0, second = 0, i;
+    for (i = 1; i < words; ++i) {
+        if (!(i & 7)) {
+            j += 2;
+            bb.w[j - 1] = second;
+            bb.w[j] = bb.w[j - 2] + sum;
+            second = sum = 0;
+        } else {
+            second |= sum << (63 - 9 * (i & 7));
+        }
+        sum += (uint64_t)__builtin_popcountll(bv.w[i]);
+    }
+    if (i & 7) {
+        second |= sum << (63 - 9 * (i & 7));
+        bb.w[j + 1] = second;
+    } else {
+        j += 2;
+        bb.w[j - 1] = second;
+        bb.w[j] = bb.w[j - 2] + sum;
+        bb.w[j + 1] = 0;
+    }
+    return bb;
+}
+
+// ri::sparse_sd_vector(onset positions, universe) -> u, n, [sdsl::sd_vector<>]
+inline void write_sparse_sd(std::ostream& o, const std::vector<uint64_t>& onset, uint64_t universe) {
+    uint64_t u = universe, m = onset.size();
+    put_u64(o, u);
+    put_u64(o, m);
+    if (u == 0) return;
+    // sdsl::sd_vector_builder(n=u, m)
+    uint32_t logm = hi(m) + 1, logn = hi(u) + 1;
+    if (logm == logn) --logm;
+    uint8_t wl = (uint8_t)(logn - logm);
+    IntVec low(m, wl);
+    IntVec high = make_bitvec(m + (1ULL << logm));
+    uint64_t last_high = 0, highpos = 0;
+    for (uint64_t k = 0; k < m; k++) {
+        uint64_t i = onset[k];
+        if (i >= u || (k && i <= onset[k - 1])) throw std::runtime_error("sparse_sd: onset not increasing/in range");
+        uint64_t cur_high = i >> wl;
+        highpos += cur_high - last_high;
+        last_high = cur_high;
+        low.set(k, i);
+        high.set_bit(highpos++);
+    }
+    put_u64(o, u);  // sd_vector::m_size
+    put_u8(o, wl);
+    low.write(o, true);
+    high.write(o, false);
+    write_select_mcl(o, high, true);
+    write_select_mcl(o, high, false);
+}
+
+// ri::huff_string == sdsl::wt_huff<> over the run heads
+inline void write_wt_huff(std::ostream& o, const std::vector<uint8_t>& s) {
+    const uint16_t UNDEF = 0xFFFF;
+    struct Node { uint64_t bv_pos, bv_pos_rank; uint16_t parent, child[2]; };
+    uint64_t size = s.size();
+    std::vector<uint64_t> C(256, 0);
+    for (uint8_t c : s) C[c]++;
+    uint64_t sigma = 0;
+    for (auto f : C) sigma += f > 0;
+    // huff_shape::construct_tree
+    std::vector<Node> tmp;
+    typedef std::pair<uint64_t, uint64_t> P;
+    std::priority_queue<P, std::vector<P>, std::greater<P>> pq;
+    for (uint32_t c = 0; c < 256; c++)
+        if (C[c] > 0) {
+            pq.push(P(C[c], tmp.size()));
+            tmp.push_back(Node{C[c], c, UNDEF, {UNDEF, UNDEF}});
+        }
+    while (pq.size() > 1) {
+        P v1 = pq.top(); pq.pop();
+        P v2 = pq.top(); pq.pop();
+        tmp[v1.second].parent = (uint16_t)tmp.size();
+        tmp[v2.second].parent = (uint16_t)tmp.size();
+        pq.push(P(v1.first + v2.first, tmp.size()));
+        tmp.push_back(Node{v1.first + v2.first, 0, UNDEF, {(uint16_t)v1.second, (uint16_t)v2.second}});
+    }
+    // _byte_tree (BFS order)
+    std::vector<Node> nodes(tmp.size());
+    uint64_t bv_size = 0;
+    if (!tmp.empty()) {
+        nodes[0] = tmp.back();
+        size_t node_cnt = 1;
+        uint16_t last_parent = UNDEF;
+        std::deque<uint16_t> q;
+        q.push_back(0);
+        while (!q.empty()) {
+            uint16_t idx = q.front();
+            q.pop_front();
+            uint64_t frq = nodes[idx].bv_pos;
+            nodes[idx].bv_pos = bv_size;
+            if (nodes[idx].child[0] != UNDEF) bv_size += frq;
+            if (idx > 0) {
+                if (last_parent != nodes[idx].parent) nodes[nodes[idx].parent].child[0] = idx;
+                else nodes[nodes[idx].parent].child[1] = idx;
+                last_parent = nodes[idx].parent;
+            }
+            if (nodes[idx].child[0] != UNDEF) {
+                for (int k = 0; k <= 1; k++) {
+                    nodes[node_cnt] = tmp[nodes[idx].child[k]];
+                    nodes[node_cnt].parent = idx;
+                    q.push_back((uint16_t)node_cnt);
+                    nodes[idx].child[k] = (uint16_t)node_cnt++;
+                }
+            }
+        }
+    }
+    std::vector<uint16_t> c_to_leaf(256, UNDEF);
+    for (size_t v = 0; v < nodes.size(); v++)
+        if (nodes[v].child[0] == UNDEF) c_to_leaf[(uint8_t)nodes[v].bv_pos_rank] = (uint16_t)v;
+    std::vector<uint64_t> path(256, 0);
+    for (uint32_t c = 0, prev_c = 0; c < 256; c++) {
+        if (c_to_leaf[c] != UNDEF) {
+            uint16_t v = c_to_leaf[c];
+            uint64_t pw = 0, pl = 0;
+            while (v != 0) {
+                pw <<= 1;
+                if (nodes[nodes[v].parent].child[1] == v) pw |= 1ULL;
+                ++pl;
+                v = nodes[v].parent;
+            }
+            path[c] = pw | (pl << 56);
+            prev_c = c;
+        } else {
+            path[c] = prev_c;
+        }
+    }
+    // bit sequence
+    IntVec bv = make_bitvec(bv_size);
+    std::vector<uint64_t> node_pos(nodes.size());
+    for (size_t v = 0; v < nodes.size(); v++) node_pos[v] = nodes[v].bv_pos;
+    for (uint8_t c : s) {
+        uint64_t p = path[c];
+        uint32_t pl = (uint32_t)(p >> 56);
+        uint16_t v = 0;
+        for (uint32_t l = 0; l < pl; l++, p >>= 1) {
+            if (p & 1) bv.set_bit(node_pos[v]);
+            node_pos[v]++;
+            v = nodes[v].child[p & 1];
+        }
+    }
+    IntVec rk = build_rank_v(bv);
+    // init_node_ranks: inner nodes get rank1(bv_pos)
+    {
+        std::vector<uint64_t> pref(bv.w.size() + 1, 0);
+        for (size_t i = 0; i < bv.w.size(); i++) pref[i + 1] = pref[i] + __builtin_popcountll(bv.w[i]);
+        for (auto& nd : nodes)
+            if (nd.child[0] != UNDEF) {
+                uint64_t p = nd.bv_pos;
+                uint64_t r = pref[p >> 6];
+                if (p & 63) r += __builtin_popcountll(bv.w[p >> 6] & ((1ULL << (p & 63)) - 1));
+                nd.bv_pos_rank = r;
+            }
+    }
+    put_u64(o, size);
+    put_u64(o, sigma);
+    bv.write(o, false);
+    rk.write(o, false);
+    write_select_mcl(o, bv, true);
+    write_select_mcl(o, bv, false);
+    put_u64(o, nodes.size());
+    for (auto& nd : nodes) {
+        put_u64(o, nd.bv_pos);
+        put_u64(o, nd.bv_pos_rank);
+        put_u16(o, nd.parent);
+        put_u16(o, nd.child[0]);
+        put_u16(o, nd.child[1]);
+    }
+    for (int c = 0; c < 256; c++) put_u16(o, c_to_leaf[c]);
+    for (int c = 0; c < 256; c++) put_u64(o, path[c]);
+}
+
+// ms_rle_string<sparse_sd_vector, huff_string>(heads, lengths, B=2) + ri::rle_string::serialize
+// (constructor semantics: /root/reference/include/ms_rle_string.hpp:217-288)
+inline void write_rle_string(std::ostream& o, const std::vector<uint8_t>& heads_in,
+                             const std::vector<uint64_t>& lens, uint64_t B = 2) {
+    std::vector<uint8_t> heads(heads_in);
+    uint64_t R = heads.size(), n = 0;
+    std::vector<std::vector<uint64_t>> per_letter(256);
+    std::vector<uint64_t> per_letter_n(256, 0), runs_onset;
+    for (uint64_t i = 0; i < R; i++) {
+        if (heads[i] <= 1) heads[i] = 1;
+        uint8_t c = heads[i];
+        if (i % B == B - 1) runs_onset.push_back(n + lens[i] - 1);
+        per_letter_n[c] += lens[i];
+        per_letter[c].push_back(per_letter_n[c] - 1);
+        n += lens[i];
+    }
+    put_u64(o, n);
+    put_u64(o, R);
+    put_u64(o, B);
+    if (n == 0) return;
+    write_sparse_sd(o, runs_onset, n);
+    for (int c = 0; c < 256; c++) write_sparse_sd(o, per_letter[c], per_letter_n[c]);
+    write_wt_huff(o, heads);
+}
+
+// thr_bv(filename, bwt) + serialize (/root/reference/include/thresholds_ds.hpp:384-440, :502-512)
+inline void write_thr_bv(std::ostream& o, const std::vector<uint8_t>& heads, const std::vector<uint64_t>& thr,
+                         uint64_t n) {
+    std::vector<std::vector<uint64_t>> per(256);
+    std::vector<uint64_t> uni(256, 0);
+    for (size_t i = 0; i < heads.size(); i++) {
+        uint8_t c = heads[i] <= 1 ? 1 : heads[i];
+        if (thr[i] > 0) per[c].push_back(thr[i]);
+        uni[c] = n;
+    }
+    for (int c = 0; c < 256; c++) write_sparse_sd(o, per[c], uni[c]);
+}
+
+// int_vector<>(r, 0, bitsize(n)) of SA samples (/root/reference/src/compute_ms_pml.cpp:404-439)
+inline void write_samples(std::ostream& o, const std::vector<uint64_t>& vals, uint64_t n) {
+    uint8_t log_n = (uint8_t)(hi(n) + 1);  // bitsize(n)
+    IntVec v(vals.size(), log_n);
+    for (size_t i = 0; i < vals.size(); i++) v.set(i, vals[i]);
+    v.write(o, true);
+}
+
+// build_F_ (/root/reference/src/compute_ms_pml.cpp:119-147); returns terminator_position
+inline uint64_t build_F(const std::vector<uint8_t>& heads, const std::vector<uint64_t>& lens,
+                        std::vector<uint64_t>& F) {
+    F.assign(256, 0);
+    uint64_t term = 0;
+    for (size_t i = 0; i < heads.size(); i++) {
+        if (heads[i] > 1) F[heads[i]] += lens[i];
+        else { F[1] += lens[i]; term = i; }
+    }
+    for (int i = 255; i > 0; --i) F[i] = F[i - 1];
+    F[0] = 0;
+    for (int i = 1; i < 256; ++i) F[i] += F[i - 1];
+    return term;
+}
+
+struct RlbwtParts {
+    uint64_t n = 0;
+    std::vector<uint8_t> heads;       // raw (terminator may be 0x00)
+    std::vector<uint64_t> lens;
+    std::vector<uint64_t> thr;        // BWT positions, 0 for first run of a char
+    std::vector<uint64_t> ssa, esa;   // SA values at run start / end (as .ssa/.esa second column)
+};
+
+inline void write_pml_index(std::ostream& o, const RlbwtParts& p) {
+    std::vector<uint64_t> F;
+    uint64_t term = build_F(p.heads, p.lens, F);
+    put_u64(o, term);
+    put_u64(o, 256);
+    for (int i = 0; i < 256; i++) put_u64(o, F[i]);
+    write_rle_string(o, p.heads, p.lens);
+    write_thr_bv(o, p.heads, p.thr, p.n);
+}
+
+inline void write_ms_index(std::ostream& o, const RlbwtParts& p) {
+    std::vector<uint64_t> F;
+    uint64_t term = build_F(p.heads, p.lens, F);
+    put_u64(o, term);
+    put_u64(o, 256);
+    for (int i = 0; i < 256; i++) put_u64(o, F[i]);
+    write_rle_string(o, p.heads, p.lens);
+    std::vector<uint64_t> sl(p.esa.size()), ss(p.ssa.size());
+    for (size_t i = 0; i < sl.size(); i++) sl[i] = p.esa[i] ? p.esa[i] - 1 : p.n - 1;
+    for (size_t i = 0; i < ss.size(); i++) ss[i] = p.ssa[i] ? p.ssa[i] - 1 : p.n - 1;
+    write_samples(o, sl, p.n);
+    write_thr_bv(o, p.heads, p.thr, p.n);
+    write_samples(o, ss, p.n);
+}
+
+// EmpNullDatabase ctor arithmetic + serialize (/root/reference/src/emp_null_database.cpp:41-102)
+inline void write_null_db(std::ostream& o, const std::vector<uint64_t>& stats, double ks_stat_threshold) {
+    uint64_t mx = 0;
+    double sum = 0;
+    for (auto v : stats) { if (v > mx) mx = v; sum += (double)v; }
+    int width = 1;
+    if (mx > 1) {
+        // max(ceil(log2(max)), 1) -- exact integer form of the reference's floating-point expression
+        int c = (int)hi(mx);
+        if ((1ULL << c) != mx) c++;
+        width = c < 1 ? 1 : c;
+    }
+    IntVec v(stats.size(), (uint8_t)width);
+    for (size_t i = 0; i < stats.size(); i++) v.set(i, stats[i]);
+    std::vector<uint64_t> sorted(stats);
+    std::sort(sorted.begin(), sorted.end());
+    uint64_t largest = 0, cur = sorted.empty() ? 0 : sorted[0], occ = 0;
+    for (auto x : sorted) {
+        if (x == cur) occ++;
+        else { if (occ >= 5) largest = cur; cur = x; occ = 1; }
+    }
+    if (occ >= 5) largest = cur;
+    put_u64(o, stats.size());
+    put_f64(o, ks_stat_threshold);
+    put_f64(o, stats.empty() ? 0.0 : sum / (double)stats.size());
+    put_f64(o, (double)largest);
+    v.write(o, true);
+}
+
+}  // namespace sdslw
