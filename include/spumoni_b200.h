@@ -1,0 +1,152 @@
+/*
+ * spumoni_b200.h -- C ABI of the B200-native MS/PML hot path.
+ *
+ * This is the drop-in boundary for SPUMONI's per-read query path.  The reference exposes no
+ * FFI; the in-process seam these entry points replace is
+ *     pml_t::matching_statistics(const char*, size_t, std::vector<size_t>&)
+ *         /root/reference/src/compute_ms_pml.cpp:730-732
+ *     ms_t::matching_statistics(const char*, size_t, std::vector<size_t>&, std::vector<size_t>&)
+ *         /root/reference/src/compute_ms_pml.cpp:795-812
+ * which the reference calls once per read from N OpenMP threads (:936-938, :1124-1126).  A GPU
+ * cannot be fed per read, so the ABI is batch-granular: reads are passed concatenated, one byte
+ * per base, with an offsets array (CSR style).  Each entry point cites the reference interface it
+ * replaces.  INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this boundary;
+ *   - every function returns 0 on success and a non-zero spb_status on failure; the library
+ *     never calls exit() (the reference's FATAL_* macros do, spumoni_main.hpp:28-33) -- the
+ *     message is available from spb_last_error() (thread-local);
+ *   - the caller owns all input/output buffers; index objects are owned by the library;
+ *   - "ref_file" is the path the reference passes around internally: "<prefix>.fa"
+ *     (spumoni.cpp:744-747); the index is "<ref_file>.thrbv.spumoni" / "<ref_file>.thrbv.ms"
+ *     (compute_ms_pml.cpp:215-217, :544-546), exactly as written by `spumoni build`;
+ *   - the CUDA path is the only path: without a usable GPU the query calls fail loudly.
+ */
+#ifndef SPUMONI_B200_H
+#define SPUMONI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPB_ABI_VERSION 1
+#define SPB_QUERY_TOUPPER 1u
+
+typedef enum {
+    SPB_OK = 0,
+    SPB_ERR_IO = 1,        /* file missing / unreadable */
+    SPB_ERR_FORMAT = 2,    /* on-disk structure failed validation */
+    SPB_ERR_ARG = 3,       /* bad argument */
+    SPB_ERR_CUDA = 4,      /* CUDA runtime error (message has the cudaError string) */
+    SPB_ERR_NO_DEVICE = 5, /* index not resident on a GPU / no GPU present */
+    SPB_ERR_LIMIT = 6      /* size outside supported range (n >= 2^40-2, r >= 2^32-64, read >= 2^32) */
+} spb_status;
+
+typedef enum { SPB_MODE_PML = 0, SPB_MODE_MS = 1 } spb_mode;
+
+typedef struct spb_index spb_index; /* opaque: pml_t / ms_t equivalent */
+
+/* Per-read result of the bin-max classifier (compute_ms_pml.cpp:969-995 / :1150-1176).
+ * nbins = above + below; status FOUND iff above/(above+below) > 0.5; avg = sum_max / nbins. */
+typedef struct {
+    uint64_t sum_max; /* sum of per-bin maxima              (sum_max_bin_values) */
+    uint32_t above;   /* bins with max >= max_value_thr     (bins_above)         */
+    uint32_t below;   /* bins with max <  max_value_thr     (bins_below)         */
+} spb_bin_stats;
+
+typedef struct {
+    uint32_t bin_width;      /* -w; 0 disables classification (stats may then be NULL) */
+    uint32_t lanes_per_read; /* 0 = library default; else one of 4, 8, 16, 32 (tuning knob) */
+    uint64_t max_value_thr;  /* see spb_max_value_threshold */
+    uint32_t flags;          /* SPB_QUERY_TOUPPER: apply ::toupper to read bytes on the device (compute_ms_pml.cpp:916-917) */
+    uint32_t reserved[3];
+} spb_query_opts;
+
+/* EmpNullDatabase (emp_null_database.hpp:16-33); values are not kept, only the scalars */
+typedef struct {
+    uint64_t num_values;
+    double ks_stat_threshold;
+    double mean_null_stat;
+    double percentile_value;
+} spb_nulldb;
+
+const char* spb_last_error(void);
+int spb_abi_version(void);
+
+/* ---- index lifetime ------------------------------------------------------------------ */
+
+/* pml_t::pml_t(filename, ...) compute_ms_pml.cpp:700-721 -> pml_pointers::load :222-229
+ * ms_t::ms_t(filename, ...)   compute_ms_pml.cpp:755-786 -> ms_pointers::load  :551-562
+ * Parses the reference's on-disk index (host only, no GPU needed) and flattens it into the
+ * device layout.  MS mode takes the text from <ref_file> itself (the FASTA written by
+ * `spumoni build`) instead of <ref_file>.slp -- see DESIGN.md. */
+int spb_index_open(const char* ref_file, int mode, spb_index** out);
+
+/* get_bwt_stats() compute_ms_pml.cpp:171-173 / :484-486 */
+int spb_index_stats(const spb_index* idx, uint64_t* n, uint64_t* r);
+
+/* The flat image: one contiguous, position-independent blob (header + tables).  Multi-GPU
+ * loaders broadcast these bytes (NCCL) instead of re-parsing the file on every rank. */
+int spb_index_flat(const spb_index* idx, const void** host_blob, uint64_t* bytes);
+int spb_index_from_flat(const void* host_blob, uint64_t bytes, spb_index** out);
+/* Header-only variant for ranks that receive the image directly into device memory: the first
+ * spb_flat_header_bytes() bytes of the image describe it completely; pair with
+ * spb_index_attach_device. */
+uint64_t spb_flat_header_bytes(void);
+int spb_index_from_header(const void* header, uint64_t bytes, spb_index** out);
+
+/* Make the index resident on `device`: library-owned allocation + H2D copy ... */
+int spb_index_to_device(spb_index* idx, int device);
+/* ... or adopt caller-owned device memory that already holds the flat image (e.g. the
+ * receive buffer of an ncclBroadcast).  The memory must stay valid until spb_index_close. */
+int spb_index_attach_device(spb_index* idx, int device, const void* dev_blob, uint64_t bytes);
+
+void spb_index_close(spb_index* idx);
+
+/* ---- queries ------------------------------------------------------------------------- */
+/* Reads: `reads` holds n_reads reads back to back, one byte per base (already upper-cased or
+ * not: the kernels apply ::toupper as compute_ms_pml.cpp:916-917 does when `toupper` != 0 in
+ * the *_host calls; device calls take bytes verbatim); read i is reads[offsets[i] .. offsets[i+1]).
+ * Outputs are indexed like the input: lengths[offsets[i] + j] is position j of read i. */
+
+/* pml_t::matching_statistics compute_ms_pml.cpp:730-732 -> pml_pointers::_query :237-286,
+ * plus (optional) the bin-max classifier :969-995.  Host buffers; H2D + kernel + D2H inside;
+ * returns when the outputs are complete.  Pinned host memory (spb_host_alloc) makes the
+ * copies asynchronous and overlapped. */
+int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                       uint32_t* lengths, spb_bin_stats* stats, const spb_query_opts* opts);
+
+/* ms_t::matching_statistics compute_ms_pml.cpp:795-812 -> ms_pointers::_query :570-623 */
+int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                      uint32_t* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts);
+
+/* Same, on buffers already resident on the index's device; asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*; NULL = default stream).  d_reads must be 256-byte aligned
+ * and readable up to the next multiple of 256 bytes past offsets[n_reads]. */
+int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                         uint32_t* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream);
+int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                        uint32_t* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
+                        const spb_query_opts* opts, void* cuda_stream);
+
+/* ---- classification helpers ---------------------------------------------------------- */
+/* EmpNullDatabase::load emp_null_database.cpp:104-110 */
+int spb_nulldb_load(const char* path, spb_nulldb* out);
+/* max_value_thr derivation compute_ms_pml.cpp:871-875 (PML) / :1061-1063 (MS) */
+uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dna_letters, int use_promotions);
+
+/* ---- utilities ----------------------------------------------------------------------- */
+int spb_host_alloc(void** p, size_t bytes); /* pinned host memory */
+void spb_host_free(void* p);
+int spb_device_count(void);
+/* number of kernels this library has launched in the calling process (bench `gpu_launches`) */
+uint64_t spb_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPUMONI_B200_H */

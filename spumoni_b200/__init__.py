@@ -1,0 +1,289 @@
+"""spumoni_b200 -- B200-native MS/PML hot path of SPUMONI, host-side mirror in Python.
+
+The product is ``lib/libspumoni_b200.so`` (hand-written sm_100a CUDA behind the C ABI declared in
+``include/spumoni_b200.h``).  This module is a thin ctypes mirror of that ABI shaped like the
+reference's own objects (``pml_t`` / ``ms_t`` with ``matching_statistics`` and
+``get_bwt_stats``, /root/reference/src/compute_ms_pml.cpp:694-838) so that tests read like
+reference call sites.  There is no CPU fallback: if the shared library is missing, importing
+the bindings raises; if no GPU is present, queries raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+__all__ = ["pml_t", "ms_t", "Index", "EmpNullDatabase", "SpumoniError", "load_library", "build_library",
+           "max_value_threshold", "kernel_launches", "device_count", "BinStats", "QueryOpts", "LIB_PATH", "CLI_PATH"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libspumoni_b200.so")
+CLI_PATH = os.path.join(_HERE, "bin", "spumoni")
+MODE_PML, MODE_MS = 0, 1
+QUERY_TOUPPER = 1
+
+BinStats = np.dtype([("sum_max", np.uint64), ("above", np.uint32), ("below", np.uint32)])
+
+
+class QueryOpts(ctypes.Structure):
+    _fields_ = [("bin_width", ctypes.c_uint32), ("lanes_per_read", ctypes.c_uint32),
+                ("max_value_thr", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 3)]
+
+
+class _NullDb(ctypes.Structure):
+    _fields_ = [("num_values", ctypes.c_uint64), ("ks_stat_threshold", ctypes.c_double),
+                ("mean_null_stat", ctypes.c_double), ("percentile_value", ctypes.c_double)]
+
+
+class SpumoniError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"spumoni_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib: Optional[ctypes.CDLL] = None
+
+
+def build_library(force: bool = False) -> None:
+    """Compile libspumoni_b200.so + the `spumoni` CLI for sm_100a (nvcc; no GPU needed)."""
+    args = ["make", "-C", os.path.join(_HERE, "csrc"), "-s"]
+    if force:
+        args.append("-B")
+    subprocess.check_call(args)
+
+
+def load_library() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(spumoni_b200 has no fallback path)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, u64, i32, cp = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_char_p
+    L.spb_last_error.restype = cp
+    L.spb_abi_version.restype = i32
+    L.spb_index_open.argtypes = [cp, i32, ctypes.POINTER(vp)]
+    L.spb_index_stats.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
+    L.spb_index_flat.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
+    L.spb_index_from_flat.argtypes = [vp, u64, ctypes.POINTER(vp)]
+    L.spb_flat_header_bytes.restype = u64
+    L.spb_index_from_header.argtypes = [vp, u64, ctypes.POINTER(vp)]
+    L.spb_index_to_device.argtypes = [vp, i32]
+    L.spb_index_attach_device.argtypes = [vp, i32, vp, u64]
+    L.spb_index_close.argtypes = [vp]
+    L.spb_index_close.restype = None
+    L.spb_pml_query_host.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(QueryOpts)]
+    L.spb_ms_query_host.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts)]
+    L.spb_pml_query_device.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(QueryOpts), vp]
+    L.spb_ms_query_device.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts), vp]
+    L.spb_nulldb_load.argtypes = [cp, ctypes.POINTER(_NullDb)]
+    L.spb_max_value_threshold.argtypes = [ctypes.c_double, i32, i32, i32]
+    L.spb_max_value_threshold.restype = u64
+    L.spb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
+    L.spb_host_free.argtypes = [vp]
+    L.spb_host_free.restype = None
+    L.spb_device_count.restype = i32
+    L.spb_kernel_launches.restype = u64
+    _lib = L
+    return L
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise SpumoniError(rc, load_library().spb_last_error().decode(errors="replace"))
+
+
+def max_value_threshold(percentile_value: float, is_pml: bool, use_dna_letters=False, use_promotions=False) -> int:
+    """compute_ms_pml.cpp:871-875 (PML) / :1061-1063 (MS)."""
+    return int(load_library().spb_max_value_threshold(percentile_value, int(is_pml), int(use_dna_letters),
+                                                      int(use_promotions)))
+
+
+def flat_header_bytes() -> int:
+    return int(load_library().spb_flat_header_bytes())
+
+
+def kernel_launches() -> int:
+    return int(load_library().spb_kernel_launches())
+
+
+def device_count() -> int:
+    return int(load_library().spb_device_count())
+
+
+class EmpNullDatabase:
+    """EmpNullDatabase::load (emp_null_database.cpp:104-110)."""
+
+    def __init__(self):
+        self.num_values = 0
+        self.ks_stat_threshold = 0.0
+        self.mean_null_stat = 0.0
+        self.percentile_value = 0.0
+
+    def load(self, path: str) -> "EmpNullDatabase":
+        db = _NullDb()
+        _check(load_library().spb_nulldb_load(path.encode(), ctypes.byref(db)))
+        self.num_values, self.ks_stat_threshold = db.num_values, db.ks_stat_threshold
+        self.mean_null_stat, self.percentile_value = db.mean_null_stat, db.percentile_value
+        return self
+
+
+def pack_reads(reads) -> Tuple[np.ndarray, np.ndarray]:
+    """list of bytes -> (concatenated uint8 array, uint64 offsets[n+1])."""
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    if len(reads):
+        off[1:] = np.cumsum([len(r) for r in reads], dtype=np.uint64)
+    buf = np.frombuffer(b"".join(reads), dtype=np.uint8).copy() if len(reads) else np.zeros(0, dtype=np.uint8)
+    return buf, off
+
+
+class _OwnedArray(np.ndarray):
+    _owner = None
+
+
+class Index:
+    """Owning handle on a flat index (``spb_index``)."""
+
+    def __init__(self, handle: int, mode: int):
+        self._h = ctypes.c_void_p(handle)
+        self.mode = mode
+        self._keepalive = None
+
+    # ---- construction
+    @classmethod
+    def open(cls, ref_file: str, mode: int) -> "Index":
+        h = ctypes.c_void_p()
+        _check(load_library().spb_index_open(ref_file.encode(), mode, ctypes.byref(h)))
+        return cls(h.value, mode)
+
+    @classmethod
+    def from_flat(cls, blob: np.ndarray) -> "Index":
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        _check(load_library().spb_index_from_flat(blob.ctypes.data, blob.nbytes, ctypes.byref(h)))
+        mode = int(np.frombuffer(blob[12:16].tobytes(), dtype=np.uint32)[0])
+        return cls(h.value, mode)
+
+    @classmethod
+    def from_header(cls, header: np.ndarray) -> "Index":
+        """Header-only index (no host image); pair with attach_device."""
+        header = np.ascontiguousarray(header, dtype=np.uint8)
+        h = ctypes.c_void_p()
+        _check(load_library().spb_index_from_header(header.ctypes.data, header.nbytes, ctypes.byref(h)))
+        mode = int(np.frombuffer(header[12:16].tobytes(), dtype=np.uint32)[0])
+        return cls(h.value, mode)
+
+    def close(self) -> None:
+        if self._h:
+            load_library().spb_index_close(self._h)
+            self._h = ctypes.c_void_p()
+            self._keepalive = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- reference-shaped accessors
+    def get_bwt_stats(self) -> Tuple[int, int]:
+        n, r = ctypes.c_uint64(), ctypes.c_uint64()
+        _check(load_library().spb_index_stats(self._h, ctypes.byref(n), ctypes.byref(r)))
+        return n.value, r.value
+
+    def flat(self) -> np.ndarray:
+        """The flat image as a read-only uint8 view (valid while the index is open)."""
+        p, b = ctypes.c_void_p(), ctypes.c_uint64()
+        _check(load_library().spb_index_flat(self._h, ctypes.byref(p), ctypes.byref(b)))
+        arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint8)), shape=(b.value,))
+        arr.flags.writeable = False
+        view = arr.view(_OwnedArray)
+        view._owner = self  # the blob lives inside the index: keep it alive with the view
+        return view
+
+    # ---- residency
+    def to_device(self, device: int = 0) -> "Index":
+        _check(load_library().spb_index_to_device(self._h, device))
+        return self
+
+    def attach_device(self, device: int, dev_tensor) -> "Index":
+        """Adopt a torch uint8 CUDA tensor already holding the flat image (e.g. after a broadcast)."""
+        _check(load_library().spb_index_attach_device(self._h, device, dev_tensor.data_ptr(), dev_tensor.numel()))
+        self._keepalive = dev_tensor
+        return self
+
+    # ---- queries (host buffers)
+    def _opts(self, bin_width=0, max_value_thr=0, lanes=0, toupper=False) -> QueryOpts:
+        o = QueryOpts()
+        o.bin_width, o.lanes_per_read, o.max_value_thr = bin_width, lanes, max_value_thr
+        o.flags = QUERY_TOUPPER if toupper else 0
+        return o
+
+    def query_host(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0,
+                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None):
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        total = int(offsets[-1]) if n >= 0 and len(offsets) else 0
+        L = out_lengths if out_lengths is not None else np.zeros(total, dtype=np.uint32)
+        S = None
+        if bin_width:
+            S = out_stats if out_stats is not None else np.zeros(n, dtype=BinStats)
+        o = self._opts(bin_width, max_value_thr, lanes, toupper)
+        lib = load_library()
+        if self.mode == MODE_MS:
+            P = out_pointers if out_pointers is not None else np.zeros(total, dtype=np.uint64)
+            _check(lib.spb_ms_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
+                                         P.ctypes.data, S.ctypes.data if S is not None else None, ctypes.byref(o)))
+            return L, P, S
+        _check(lib.spb_pml_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
+                                      S.ctypes.data if S is not None else None, ctypes.byref(o)))
+        return L, None, S
+
+    # ---- queries (torch CUDA tensors, asynchronous on `stream`)
+    def query_device(self, d_reads, d_offsets, n_reads: int, d_lengths, d_pointers=None, d_stats=None, bin_width=0,
+                     max_value_thr=0, lanes=0, toupper=False, stream: int = 0) -> None:
+        o = self._opts(bin_width, max_value_thr, lanes, toupper)
+        lib = load_library()
+        sp = d_stats.data_ptr() if d_stats is not None else None
+        if self.mode == MODE_MS:
+            _check(lib.spb_ms_query_device(self._h, d_reads.data_ptr(), d_offsets.data_ptr(), n_reads,
+                                           d_lengths.data_ptr(), d_pointers.data_ptr(), sp, ctypes.byref(o), stream))
+        else:
+            _check(lib.spb_pml_query_device(self._h, d_reads.data_ptr(), d_offsets.data_ptr(), n_reads,
+                                            d_lengths.data_ptr(), sp, ctypes.byref(o), stream))
+
+
+class pml_t(Index):
+    """pml_t (compute_ms_pml.cpp:694-746): loads <ref_file>.thrbv.spumoni."""
+
+    def __init__(self, filename: str, device: Optional[int] = 0):
+        idx = Index.open(filename, MODE_PML)
+        super().__init__(idx._h.value, MODE_PML)
+        idx._h = ctypes.c_void_p()
+        if device is not None:
+            self.to_device(device)
+
+    def matching_statistics(self, read: bytes, **kw) -> np.ndarray:
+        buf, off = pack_reads([read])
+        return self.query_host(buf, off, **kw)[0]
+
+
+class ms_t(Index):
+    """ms_t (compute_ms_pml.cpp:748-838): loads <ref_file>.thrbv.ms; text from <ref_file>."""
+
+    def __init__(self, filename: str, device: Optional[int] = 0):
+        idx = Index.open(filename, MODE_MS)
+        super().__init__(idx._h.value, MODE_MS)
+        idx._h = ctypes.c_void_p()
+        if device is not None:
+            self.to_device(device)
+
+    def matching_statistics(self, read: bytes, **kw) -> Tuple[np.ndarray, np.ndarray]:
+        buf, off = pack_reads([read])
+        L, P, _ = self.query_host(buf, off, **kw)
+        return L, P

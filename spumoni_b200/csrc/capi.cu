@@ -1,0 +1,374 @@
+// C ABI of libspumoni_b200.so (declared in include/spumoni_b200.h).
+//
+// Host plumbing only: index lifetime, device residency, batch pipelining (H2D / kernel / D2H on
+// rotating streams) and error translation.  All per-base work happens in kernels.cu.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/spumoni_b200.h"
+#include "flat_index.h"
+#include "index_host.h"
+#include "kernels.h"
+
+namespace {
+
+thread_local std::string g_error;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_error = msg;
+    return code;
+}
+#define SPB_CUDA(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess)                                                                           \
+            return fail(SPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+constexpr int kSlots = 3;                         // pipeline depth of the host entry points
+constexpr uint64_t kChunkBases = 32ull << 20;     // bases per pipelined sub-batch
+constexpr int kCounters = 64;
+constexpr int kDefaultLanes = 8;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_reads = nullptr;
+    uint64_t* d_offsets = nullptr;
+    uint32_t* d_lengths = nullptr;
+    uint64_t* d_pointers = nullptr;
+    spb_bin_stats* d_stats = nullptr;
+    uint64_t* h_offsets = nullptr;  // pinned staging for chunk-local offsets
+    uint64_t cap_bases = 0, cap_reads = 0;
+    bool cap_ms = false;
+};
+
+}  // namespace
+
+struct spb_index {
+    int mode = 0;
+    SpbFlatHeader hdr;
+    std::vector<uint8_t> host_blob;
+    int device = -1;
+    const uint8_t* dev_blob = nullptr;
+    bool own_dev = false;
+    int num_sms = 0;
+    unsigned long long* d_counters = nullptr;
+    uint32_t counter_next = 0;
+    Slot slots[kSlots];
+};
+
+namespace {
+
+int ensure_device_state(spb_index* idx) {
+    if (idx->device < 0 || !idx->dev_blob) return fail(SPB_ERR_NO_DEVICE, "index is not resident on a GPU (call spb_index_to_device)");
+    SPB_CUDA(cudaSetDevice(idx->device));
+    if (!idx->d_counters) {
+        SPB_CUDA(cudaMalloc(&idx->d_counters, kCounters * sizeof(unsigned long long)));
+        SPB_CUDA(cudaDeviceGetAttribute(&idx->num_sms, cudaDevAttrMultiProcessorCount, idx->device));
+    }
+    return SPB_OK;
+}
+
+void free_slot(Slot& s) {
+    if (s.d_reads) cudaFree(s.d_reads);
+    if (s.d_offsets) cudaFree(s.d_offsets);
+    if (s.d_lengths) cudaFree(s.d_lengths);
+    if (s.d_pointers) cudaFree(s.d_pointers);
+    if (s.d_stats) cudaFree(s.d_stats);
+    if (s.h_offsets) cudaFreeHost(s.h_offsets);
+    s.d_reads = nullptr; s.d_offsets = nullptr; s.d_lengths = nullptr; s.d_pointers = nullptr; s.d_stats = nullptr;
+    s.h_offsets = nullptr;
+    s.cap_bases = s.cap_reads = 0;
+}
+
+int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms) {
+    if (!s.stream) SPB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    if (bases <= s.cap_bases && reads <= s.cap_reads && (!ms || s.cap_ms)) return SPB_OK;
+    SPB_CUDA(cudaStreamSynchronize(s.stream));
+    const uint64_t nb = bases > s.cap_bases ? bases : s.cap_bases, nr = reads > s.cap_reads ? reads : s.cap_reads;
+    cudaStream_t keep = s.stream;
+    free_slot(s);
+    s.stream = keep;
+    SPB_CUDA(cudaMalloc(&s.d_reads, nb + 512));
+    SPB_CUDA(cudaMalloc(&s.d_offsets, (nr + 1) * sizeof(uint64_t)));
+    SPB_CUDA(cudaMalloc(&s.d_lengths, (nb + 64) * sizeof(uint32_t)));
+    SPB_CUDA(cudaMalloc(&s.d_stats, (nr + 1) * sizeof(spb_bin_stats)));
+    if (ms) SPB_CUDA(cudaMalloc(&s.d_pointers, (nb + 64) * sizeof(uint64_t)));
+    SPB_CUDA(cudaMallocHost(&s.h_offsets, (nr + 1) * sizeof(uint64_t)));
+    s.cap_bases = nb; s.cap_reads = nr; s.cap_ms = ms;
+    return SPB_OK;
+}
+
+int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                 uint32_t* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats, const spb_query_opts* opts,
+                 cudaStream_t stream) {
+    if (n_reads == 0) return SPB_OK;
+    if ((ms ? 1 : 0) != idx->mode) return fail(SPB_ERR_ARG, ms ? "MS query on a PML index" : "PML query on an MS index");
+    if (!d_reads || !d_offsets || !d_lengths || (ms && !d_pointers)) return fail(SPB_ERR_ARG, "null device buffer");
+    if (((uintptr_t)d_reads & 255u) != 0) return fail(SPB_ERR_ARG, "d_reads must be 256-byte aligned");
+    int lanes = opts && opts->lanes_per_read ? (int)opts->lanes_per_read : kDefaultLanes;
+    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SPB_ERR_ARG, "lanes_per_read must be 4, 8, 16 or 32");
+    const SpbFlatHeader& h = idx->hdr;
+    spb::WalkParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.runs = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_runs);
+    p.blocks = idx->dev_blob + h.off_blocks;
+    p.crec = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_crec);
+    p.csamp = ms ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_csamp) : nullptr;
+    p.text = ms ? idx->dev_blob + h.off_text : nullptr;
+    p.chartab = reinterpret_cast<const SpbCharTab*>(idx->dev_blob + offsetof(SpbFlatHeader, chartab));
+    p.n = h.n; p.R = h.R; p.n_text = h.n_text; p.last_run_sample = h.last_run_sample;
+    p.blk_stride = h.blk_stride;
+    p.flags = (opts && (opts->flags & SPB_QUERY_TOUPPER)) ? SPB_FLAG_TOUPPER : 0;
+    p.reads = d_reads; p.offsets = d_offsets; p.n_reads = n_reads;
+    p.lengths = d_lengths; p.pointers = d_pointers;
+    p.bin_width = (opts && d_stats) ? opts->bin_width : 0;
+    p.stats = p.bin_width ? d_stats : nullptr;
+    p.max_value_thr = opts ? opts->max_value_thr : 0;
+    p.work_counter = idx->d_counters + (idx->counter_next++ % kCounters);
+    SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), stream));
+    SPB_CUDA(spb::launch_walk(p, ms, lanes, idx->num_sms, stream));
+    g_launches.fetch_add(1);
+    return SPB_OK;
+}
+
+int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+               uint32_t* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
+    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    if (n_reads == 0) return SPB_OK;
+    if (!reads || !offsets || !lengths || (ms && !pointers)) return fail(SPB_ERR_ARG, "null host buffer");
+    int rc = ensure_device_state(idx);
+    if (rc) return rc;
+    const bool want_stats = stats && opts && opts->bin_width;
+    uint64_t r0 = 0;
+    int chunk = 0;
+    while (r0 < n_reads) {
+        // sub-batch [r0, r1): at least one read, up to kChunkBases bases
+        uint64_t r1 = r0 + 1;
+        while (r1 < n_reads && offsets[r1 + 1] - offsets[r0] <= kChunkBases) r1++;
+        const uint64_t b0 = offsets[r0], nb = offsets[r1] - b0, nr = r1 - r0;
+        if (offsets[r1] < b0) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
+        Slot& s = idx->slots[chunk % kSlots];
+        rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), ms);
+        if (rc) return rc;
+        SPB_CUDA(cudaStreamSynchronize(s.stream));  // previous use of this slot (incl. its h_offsets) is done
+        for (uint64_t i = 0; i <= nr; i++) {
+            const uint64_t o = offsets[r0 + i];
+            if (o < b0 || (i && o < offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
+            if (i && o - offsets[r0 + i - 1] > 0xFFFFFFFFull) return fail(SPB_ERR_LIMIT, "read longer than 2^32-1 bases");
+            s.h_offsets[i] = o - b0;
+        }
+        SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
+        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, s.d_stats, opts, s.stream);
+        if (rc) return rc;
+        if (nb) SPB_CUDA(cudaMemcpyAsync(lengths + b0, s.d_lengths, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (ms && nb) SPB_CUDA(cudaMemcpyAsync(pointers + b0, s.d_pointers, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
+        r0 = r1;
+        chunk++;
+    }
+    for (int i = 0; i < kSlots; i++)
+        if (idx->slots[i].stream) SPB_CUDA(cudaStreamSynchronize(idx->slots[i].stream));
+    return SPB_OK;
+}
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        return f();
+    } catch (spb::IoError& e) {
+        return fail(SPB_ERR_IO, e.what());
+    } catch (spb::LimitError& e) {
+        return fail(SPB_ERR_LIMIT, e.what());
+    } catch (std::bad_alloc&) {
+        return fail(SPB_ERR_LIMIT, "out of host memory");
+    } catch (std::exception& e) {
+        return fail(SPB_ERR_FORMAT, e.what());
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* spb_last_error(void) { return g_error.c_str(); }
+int spb_abi_version(void) { return SPB_ABI_VERSION; }
+
+int spb_index_open(const char* ref_file, int mode, spb_index** out) {
+    if (!ref_file || !out || (mode != SPB_MODE_PML && mode != SPB_MODE_MS)) return fail(SPB_ERR_ARG, "spb_index_open: bad argument");
+    *out = nullptr;
+    return guarded([&]() -> int {
+        const bool ms = mode == SPB_MODE_MS;
+        const std::string ref(ref_file);
+        spb::DecodedIndex d = spb::parse_index_file(ref + (ms ? ".thrbv.ms" : ".thrbv.spumoni"), ms);
+        std::string text;
+        if (ms) text = spb::load_reference_text(ref);
+        std::unique_ptr<spb_index> idx(new spb_index());
+        idx->mode = mode;
+        idx->host_blob = spb::build_flat_image(d, ms, text);
+        std::memcpy(&idx->hdr, idx->host_blob.data(), sizeof(SpbFlatHeader));
+        *out = idx.release();
+        return SPB_OK;
+    });
+}
+
+int spb_index_stats(const spb_index* idx, uint64_t* n, uint64_t* r) {
+    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    if (n) *n = idx->hdr.n;
+    if (r) *r = idx->hdr.R;
+    return SPB_OK;
+}
+
+int spb_index_flat(const spb_index* idx, const void** host_blob, uint64_t* bytes) {
+    if (!idx || !host_blob || !bytes) return fail(SPB_ERR_ARG, "spb_index_flat: bad argument");
+    if (idx->host_blob.empty()) return fail(SPB_ERR_ARG, "this index holds no host copy of the flat image");
+    *host_blob = idx->host_blob.data();
+    *bytes = idx->host_blob.size();
+    return SPB_OK;
+}
+
+int spb_index_from_flat(const void* host_blob, uint64_t bytes, spb_index** out) {
+    if (!host_blob || !out) return fail(SPB_ERR_ARG, "spb_index_from_flat: bad argument");
+    *out = nullptr;
+    return guarded([&]() -> int {
+        spb::validate_flat_image(host_blob, bytes);
+        std::unique_ptr<spb_index> idx(new spb_index());
+        std::memcpy(&idx->hdr, host_blob, sizeof(SpbFlatHeader));
+        idx->mode = (int)idx->hdr.mode;
+        idx->host_blob.assign((const uint8_t*)host_blob, (const uint8_t*)host_blob + bytes);
+        *out = idx.release();
+        return SPB_OK;
+    });
+}
+
+uint64_t spb_flat_header_bytes(void) { return sizeof(SpbFlatHeader); }
+
+int spb_index_from_header(const void* header, uint64_t bytes, spb_index** out) {
+    if (!header || !out) return fail(SPB_ERR_ARG, "spb_index_from_header: bad argument");
+    *out = nullptr;
+    if (bytes < sizeof(SpbFlatHeader)) return fail(SPB_ERR_ARG, "header shorter than spb_flat_header_bytes()");
+    SpbFlatHeader h;
+    std::memcpy(&h, header, sizeof(h));
+    if (h.magic != SPB_FLAT_MAGIC || h.version != SPB_FLAT_VERSION) return fail(SPB_ERR_FORMAT, "not a spumoni_b200 flat image (magic/version)");
+    spb_index* idx = new spb_index();
+    idx->hdr = h;
+    idx->mode = (int)h.mode;
+    *out = idx;
+    return SPB_OK;
+}
+
+int spb_index_to_device(spb_index* idx, int device) {
+    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    if (idx->host_blob.empty()) return fail(SPB_ERR_ARG, "no host image to upload");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(SPB_ERR_NO_DEVICE, "no CUDA device available; spumoni_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(SPB_ERR_ARG, "device ordinal out of range");
+    SPB_CUDA(cudaSetDevice(device));
+    if (idx->own_dev && idx->dev_blob) cudaFree((void*)idx->dev_blob);
+    void* p = nullptr;
+    SPB_CUDA(cudaMalloc(&p, idx->host_blob.size()));
+    SPB_CUDA(cudaMemcpy(p, idx->host_blob.data(), idx->host_blob.size(), cudaMemcpyHostToDevice));
+    idx->dev_blob = (const uint8_t*)p;
+    idx->own_dev = true;
+    idx->device = device;
+    return ensure_device_state(idx);
+}
+
+int spb_index_attach_device(spb_index* idx, int device, const void* dev_blob, uint64_t bytes) {
+    if (!idx || !dev_blob) return fail(SPB_ERR_ARG, "spb_index_attach_device: bad argument");
+    if (bytes != idx->hdr.total_bytes) return fail(SPB_ERR_ARG, "device image size does not match the index");
+    if (((uintptr_t)dev_blob & 255u) != 0) return fail(SPB_ERR_ARG, "device image must be 256-byte aligned");
+    SPB_CUDA(cudaSetDevice(device));
+    SpbFlatHeader chk;
+    SPB_CUDA(cudaMemcpy(&chk, dev_blob, sizeof(chk), cudaMemcpyDeviceToHost));
+    if (chk.magic != SPB_FLAT_MAGIC || chk.total_bytes != idx->hdr.total_bytes || chk.n != idx->hdr.n || chk.R != idx->hdr.R)
+        return fail(SPB_ERR_FORMAT, "device memory does not hold this index's flat image");
+    if (idx->own_dev && idx->dev_blob) cudaFree((void*)idx->dev_blob);
+    idx->dev_blob = (const uint8_t*)dev_blob;
+    idx->own_dev = false;
+    idx->device = device;
+    return ensure_device_state(idx);
+}
+
+void spb_index_close(spb_index* idx) {
+    if (!idx) return;
+    if (idx->device >= 0) {
+        cudaSetDevice(idx->device);
+        for (int i = 0; i < kSlots; i++) {
+            if (idx->slots[i].stream) cudaStreamSynchronize(idx->slots[i].stream);
+            free_slot(idx->slots[i]);
+            if (idx->slots[i].stream) cudaStreamDestroy(idx->slots[i].stream);
+        }
+        if (idx->d_counters) cudaFree(idx->d_counters);
+        if (idx->own_dev && idx->dev_blob) cudaFree((void*)idx->dev_blob);
+    }
+    delete idx;
+}
+
+int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                       uint32_t* lengths, spb_bin_stats* stats, const spb_query_opts* opts) {
+    return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, stats, opts);
+}
+int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                      uint32_t* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
+    return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, stats, opts);
+}
+int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                         uint32_t* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream) {
+    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    int rc = ensure_device_state(idx);
+    if (rc) return rc;
+    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_stats, opts, (cudaStream_t)cuda_stream);
+}
+int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                        uint32_t* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
+                        const spb_query_opts* opts, void* cuda_stream) {
+    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    int rc = ensure_device_state(idx);
+    if (rc) return rc;
+    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_stats, opts, (cudaStream_t)cuda_stream);
+}
+
+int spb_nulldb_load(const char* path, spb_nulldb* out) {
+    if (!path || !out) return fail(SPB_ERR_ARG, "spb_nulldb_load: bad argument");
+    return guarded([&]() -> int {
+        spb::NullDb db = spb::load_null_db(path);
+        out->num_values = db.num_values;
+        out->ks_stat_threshold = db.ks_stat_threshold;
+        out->mean_null_stat = db.mean_null_stat;
+        out->percentile_value = db.percentile_value;
+        return SPB_OK;
+    });
+}
+
+uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dna_letters, int use_promotions) {
+    uint64_t thr = (uint64_t)(percentile_value > 3.0 ? percentile_value : 3.0);
+    if (use_dna_letters) thr++;
+    else if (is_pml && !use_promotions) thr += 4;
+    return thr;
+}
+
+int spb_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(SPB_ERR_ARG, "spb_host_alloc: null");
+    SPB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return SPB_OK;
+}
+void spb_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+int spb_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) return 0;
+    return count;
+}
+uint64_t spb_kernel_launches(void) { return g_launches.load(); }
+
+}  // extern "C"

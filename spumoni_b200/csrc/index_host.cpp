@@ -1,0 +1,534 @@
+// Host side of the index: parse the reference's on-disk structures and flatten them.
+//
+// Reads, byte for byte, what `spumoni build` writes:
+//   pml_pointers::serialize / load   /root/reference/src/compute_ms_pml.cpp:192-213, :222-229
+//   ms_pointers::serialize / load    /root/reference/src/compute_ms_pml.cpp:517-542, :551-562
+//   my_serialize / my_load (F)       /root/reference/include/common.hpp:458-465, :487-495
+//   thr_bv::serialize / load         /root/reference/include/thresholds_ds.hpp:502-523
+//   EmpNullDatabase::load            /root/reference/src/emp_null_database.cpp:104-110
+// and the third-party containers inside them (ri::rle_string, ri::sparse_sd_vector,
+// ri::huff_string = sdsl::wt_huff<>, sdsl::sd_vector<>, sdsl::int_vector<>).
+// Nothing is queried in succinct form: every structure is decoded ONCE into plain arrays
+// (heads / run lengths / thresholds / samples), cross-validated against the redundant
+// information in the file, and re-encoded into the flat device image of flat_index.h.
+#include "index_host.h"
+
+#include <algorithm>
+#include <cctype>
+#include <cstring>
+#include <fstream>
+#include <stdexcept>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace spb {
+
+namespace {
+
+struct FormatError : std::runtime_error {
+    explicit FormatError(const std::string& m) : std::runtime_error(m) {}
+};
+
+class ByteReader {
+public:
+    ByteReader(const uint8_t* b, size_t n) : cur_(b), end_(b + n) {}
+    uint64_t u64() { return scalar<uint64_t>(); }
+    uint16_t u16() { return scalar<uint16_t>(); }
+    uint8_t u8() { return scalar<uint8_t>(); }
+    double f64() { return scalar<double>(); }
+    const uint8_t* bytes(size_t n) {
+        if ((size_t)(end_ - cur_) < n) throw FormatError("unexpected end of index file");
+        const uint8_t* p = cur_;
+        cur_ += n;
+        return p;
+    }
+    bool at_end() const { return cur_ == end_; }
+    size_t remaining() const { return (size_t)(end_ - cur_); }
+private:
+    template <typename T> T scalar() {
+        T v;
+        std::memcpy(&v, bytes(sizeof(T)), sizeof(T));
+        return v;
+    }
+    const uint8_t* cur_;
+    const uint8_t* end_;
+};
+
+// sdsl::int_vector<w>: bit length, [width byte if w == 0], ceil(bits/64) words
+struct PackedInts {
+    uint64_t bits = 0;
+    uint32_t width = 0;
+    std::vector<uint64_t> words;
+    uint64_t count() const { return width ? bits / width : 0; }
+    uint64_t at(uint64_t i) const {
+        const uint64_t b = i * width;
+        const uint32_t sh = (uint32_t)(b & 63);
+        uint64_t v = words[b >> 6] >> sh;
+        if (sh + width > 64) v |= words[(b >> 6) + 1] << (64 - sh);
+        return width >= 64 ? v : v & ((uint64_t(1) << width) - 1);
+    }
+    bool bit(uint64_t i) const { return (words[i >> 6] >> (i & 63)) & 1u; }
+};
+
+PackedInts read_packed(ByteReader& in, uint32_t fixed_width) {
+    PackedInts v;
+    v.bits = in.u64();
+    v.width = fixed_width ? fixed_width : in.u8();
+    if (v.width == 0 || v.width > 64) throw FormatError("int_vector with invalid width");
+    const uint64_t nwords = (v.bits + 63) / 64;
+    if (nwords > in.remaining() / 8) throw FormatError("int_vector longer than file");
+    const uint8_t* src = in.bytes((size_t)nwords * 8);
+    v.words.resize((size_t)nwords + 1, 0);
+    std::memcpy(v.words.data(), src, (size_t)nwords * 8);
+    return v;
+}
+
+// sdsl::select_support_mcl: only its extent matters (it is an accelerator, not data)
+void skip_select_support(ByteReader& in) {
+    const uint64_t args = in.u64();
+    if (args == 0) return;
+    read_packed(in, 0);  // superblock
+    read_packed(in, 1);  // mini_or_long
+    const uint64_t superblocks = (args + 4095) >> 12;
+    for (uint64_t i = 0; i < superblocks; i++) read_packed(in, 0);
+}
+
+// ri::sparse_sd_vector -> sorted positions of the set bits
+struct SparseBits {
+    uint64_t universe = 0;
+    std::vector<uint64_t> ones;
+};
+SparseBits read_sparse_bits(ByteReader& in) {
+    SparseBits s;
+    s.universe = in.u64();
+    const uint64_t declared = in.u64();
+    if (s.universe == 0) {
+        if (declared) throw FormatError("sparse_sd_vector: ones in an empty universe");
+        return s;
+    }
+    const uint64_t size = in.u64();
+    const uint32_t wl = in.u8();
+    PackedInts low = read_packed(in, 0);
+    PackedInts high = read_packed(in, 1);
+    skip_select_support(in);
+    skip_select_support(in);
+    if (size != s.universe) throw FormatError("sparse_sd_vector: size != universe");
+    if (declared && low.width != wl) throw FormatError("sparse_sd_vector: low width != wl");
+    s.ones.reserve((size_t)declared);
+    // Elias-Fano: the i-th set bit of `high` at index b encodes bucket b - i
+    uint64_t seen = 0;
+    const uint64_t hw = (high.bits + 63) / 64;
+    for (uint64_t w = 0; w < hw; w++) {
+        uint64_t word = high.words[w];
+        while (word) {
+            const uint32_t t = (uint32_t)__builtin_ctzll(word);
+            word &= word - 1;
+            const uint64_t b = w * 64 + t;
+            if (b >= high.bits) break;
+            if (seen >= low.count()) throw FormatError("sparse_sd_vector: more high bits than low entries");
+            const uint64_t v = ((b - seen) << wl) | low.at(seen);
+            if (v >= s.universe || (!s.ones.empty() && v <= s.ones.back()))
+                throw FormatError("sparse_sd_vector: positions not increasing / out of universe");
+            s.ones.push_back(v);
+            seen++;
+        }
+    }
+    if (seen != declared) throw FormatError("sparse_sd_vector: declared count != decoded count");
+    return s;
+}
+
+// ri::huff_string (sdsl::wt_huff<>) -> the plain byte string
+std::vector<uint8_t> read_wavelet_string(ByteReader& in) {
+    const uint64_t size = in.u64();
+    const uint64_t sigma = in.u64();
+    PackedInts bv = read_packed(in, 1);
+    read_packed(in, 64);  // rank_support_v blocks
+    skip_select_support(in);
+    skip_select_support(in);
+    const uint64_t nnodes = in.u64();
+    if (nnodes > 1024) throw FormatError("wt_huff: implausible node count");
+    struct Node { uint64_t bv_pos, bv_pos_rank; uint16_t parent, child0, child1; };
+    std::vector<Node> nodes((size_t)nnodes);
+    for (auto& nd : nodes) {
+        nd.bv_pos = in.u64();
+        nd.bv_pos_rank = in.u64();
+        nd.parent = in.u16();
+        nd.child0 = in.u16();
+        nd.child1 = in.u16();
+    }
+    uint16_t c_to_leaf[256];
+    for (int i = 0; i < 256; i++) c_to_leaf[i] = in.u16();
+    in.bytes(256 * 8);  // m_path (derivable from the tree)
+    const uint16_t UNDEF = 0xFFFF;
+    std::vector<int> leaf_symbol((size_t)nnodes, -1);
+    uint64_t leaves = 0;
+    for (int c = 0; c < 256; c++)
+        if (c_to_leaf[c] != UNDEF) {
+            if (c_to_leaf[c] >= nnodes || nodes[c_to_leaf[c]].child0 != UNDEF) throw FormatError("wt_huff: bad c_to_leaf");
+            leaf_symbol[c_to_leaf[c]] = c;
+            leaves++;
+        }
+    if (leaves != sigma) throw FormatError("wt_huff: sigma != number of leaves");
+    std::vector<uint8_t> out((size_t)size);
+    if (size == 0) return out;
+    if (nnodes == 0) throw FormatError("wt_huff: empty tree for non-empty string");
+    // rank directory: ones before each 64-bit word
+    const uint64_t nwords = (bv.bits + 63) / 64;
+    std::vector<uint64_t> before((size_t)nwords + 1, 0);
+    for (uint64_t w = 0; w < nwords; w++) before[w + 1] = before[w] + (uint64_t)__builtin_popcountll(bv.words[w]);
+    auto rank1 = [&](uint64_t i) {
+        uint64_t r = before[i >> 6];
+        if (i & 63) r += (uint64_t)__builtin_popcountll(bv.words[i >> 6] & ((uint64_t(1) << (i & 63)) - 1));
+        return r;
+    };
+    std::vector<uint64_t> node_rank((size_t)nnodes, 0), node_len((size_t)nnodes, 0);
+    for (size_t v = 0; v < nodes.size(); v++)
+        if (nodes[v].child0 != UNDEF) {
+            if (nodes[v].bv_pos > bv.bits) throw FormatError("wt_huff: node outside bit vector");
+            node_rank[v] = rank1(nodes[v].bv_pos);
+        }
+    bool bad = false;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)size; i++) {
+        uint32_t v = 0;
+        uint64_t idx = (uint64_t)i;
+        int guard = 0;
+        while (nodes[v].child0 != UNDEF) {
+            const uint64_t at = nodes[v].bv_pos + idx;
+            if (at >= bv.bits || ++guard > 300) { bad = true; break; }
+            const uint64_t ones = rank1(at) - node_rank[v];
+            if (bv.bit(at)) { idx = ones; v = nodes[v].child1; }
+            else { idx -= ones; v = nodes[v].child0; }
+            if (v >= nodes.size()) { bad = true; break; }
+        }
+        if (bad) continue;
+        if (leaf_symbol[v] < 0) { bad = true; continue; }
+        out[(size_t)i] = (uint8_t)leaf_symbol[v];
+    }
+    if (bad) throw FormatError("wt_huff: inconsistent tree / bit vector");
+    return out;
+}
+
+std::vector<uint8_t> slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary | std::ios::ate);
+    if (!f) throw IoError("cannot open " + path);
+    const std::streamoff sz = f.tellg();
+    f.seekg(0);
+    std::vector<uint8_t> b((size_t)sz);
+    if (sz && !f.read((char*)b.data(), sz)) throw IoError("cannot read " + path);
+    return b;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+DecodedIndex parse_index_file(const std::string& path, bool ms) {
+    std::vector<uint8_t> buf = slurp(path);
+    ByteReader in(buf.data(), buf.size());
+    DecodedIndex d;
+    try {
+        d.terminator_position = in.u64();
+        const uint64_t fsize = in.u64();
+        if (fsize != 256) throw FormatError("F does not have 256 entries");
+        d.F.resize(256);
+        for (auto& f : d.F) f = in.u64();
+        // ri::rle_string
+        d.n = in.u64();
+        d.R = in.u64();
+        const uint64_t B = in.u64();
+        if (d.n == 0 || d.R == 0 || B == 0) throw FormatError("empty BWT");
+        SparseBits runs = read_sparse_bits(in);
+        std::vector<SparseBits> per_letter(256);
+        for (int c = 0; c < 256; c++) per_letter[c] = read_sparse_bits(in);
+        d.heads = read_wavelet_string(in);
+        if (d.heads.size() != d.R) throw FormatError("run_heads.size() != R");
+        // run lengths: the j-th c-run ends at c-local index per_letter[c].ones[j]
+        d.lens.resize((size_t)d.R);
+        std::vector<uint64_t> ord(256, 0);
+        uint64_t total = 0;
+        for (uint64_t k = 0; k < d.R; k++) {
+            const uint8_t c = d.heads[(size_t)k];
+            const SparseBits& s = per_letter[c];
+            const uint64_t j = ord[c]++;
+            if (j >= s.ones.size()) throw FormatError("more runs of a letter than runs_per_letter bits");
+            const uint64_t len = j ? s.ones[(size_t)j] - s.ones[(size_t)j - 1] : s.ones[0] + 1;
+            d.lens[(size_t)k] = len;
+            total += len;
+        }
+        if (total != d.n) throw FormatError("sum of run lengths != n");
+        for (int c = 0; c < 256; c++) {
+            if (ord[c] != per_letter[c].ones.size()) throw FormatError("runs_per_letter has unused bits");
+            if (per_letter[c].ones.size() && per_letter[c].ones.back() + 1 != per_letter[c].universe)
+                throw FormatError("runs_per_letter universe != letter count");
+        }
+        {   // `runs` marks the last position of every B-th run (ms_rle_string.hpp:255-256)
+            if (runs.universe != d.n) throw FormatError("runs bit vector universe != n");
+            uint64_t pos = 0, t = 0;
+            for (uint64_t k = 0; k < d.R; k++) {
+                pos += d.lens[(size_t)k];
+                if (k % B == B - 1) {
+                    if (t >= runs.ones.size() || runs.ones[(size_t)t] != pos - 1) throw FormatError("runs bit vector disagrees with run lengths");
+                    t++;
+                }
+            }
+            if (t != runs.ones.size()) throw FormatError("runs bit vector has extra bits");
+        }
+        {   // F must equal build_F_ of the decoded runs (compute_ms_pml.cpp:119-147)
+            std::vector<uint64_t> cnt(256, 0), F(256, 0);
+            for (uint64_t k = 0; k < d.R; k++) cnt[d.heads[(size_t)k]] += d.lens[(size_t)k];
+            uint64_t acc = 0;
+            for (int c = 0; c < 256; c++) { F[c] = acc; acc += cnt[c]; }
+            if (F != d.F) throw FormatError("F array disagrees with the run-length BWT");
+        }
+        if (ms) {
+            PackedInts sl = read_packed(in, 0);
+            if (sl.count() != d.R) throw FormatError("samples_last has != R entries");
+            d.samples_last.resize((size_t)d.R);
+            for (uint64_t k = 0; k < d.R; k++) d.samples_last[(size_t)k] = sl.at(k);
+        }
+        // thr_bv: thresholds of the j-th c-run (j >= 1) is the (j-1)-th bit of thresholds_per_letter[c]
+        {
+            std::vector<SparseBits> thr(256);
+            for (int c = 0; c < 256; c++) thr[c] = read_sparse_bits(in);
+            d.thr.assign((size_t)d.R, 0);
+            std::vector<uint64_t> o(256, 0);
+            for (uint64_t k = 0; k < d.R; k++) {
+                const uint8_t c = d.heads[(size_t)k];
+                const uint64_t j = o[c]++;
+                if (j == 0) continue;
+                if (j - 1 >= thr[c].ones.size()) throw FormatError("fewer thresholds than runs for a letter");
+                d.thr[(size_t)k] = thr[c].ones[(size_t)j - 1];
+            }
+            for (int c = 0; c < 256; c++) {
+                const uint64_t want = o[c] ? o[c] - 1 : 0;
+                if (thr[c].ones.size() != want) throw FormatError("threshold count != runs-1 for a letter");
+            }
+        }
+        if (ms) {
+            PackedInts ss = read_packed(in, 0);
+            if (ss.count() != d.R) throw FormatError("samples_start has != R entries");
+            d.samples_start.resize((size_t)d.R);
+            for (uint64_t k = 0; k < d.R; k++) d.samples_start[(size_t)k] = ss.at(k);
+        }
+        if (!in.at_end()) throw FormatError("trailing bytes after the index");
+    } catch (FormatError& e) {
+        throw FormatError(path + ": " + e.what());
+    }
+    return d;
+}
+
+std::string load_reference_text(const std::string& fasta_path) {
+    std::ifstream f(fasta_path);
+    if (!f) throw IoError("cannot open " + fasta_path);
+    std::string text, line;
+    while (std::getline(f, line)) {
+        if (!line.empty() && line[0] == '>') continue;
+        while (!line.empty() && std::isspace((unsigned char)line.back())) line.pop_back();
+        text += line;
+    }
+    return text;
+}
+
+NullDb load_null_db(const std::string& path) {
+    std::vector<uint8_t> buf = slurp(path);
+    ByteReader in(buf.data(), buf.size());
+    NullDb db;
+    try {
+        db.num_values = in.u64();
+        db.ks_stat_threshold = in.f64();
+        db.mean_null_stat = in.f64();
+        db.percentile_value = in.f64();
+        PackedInts v = read_packed(in, 0);
+        if (v.count() != db.num_values) throw FormatError("null_stats length != num_values");
+    } catch (FormatError& e) {
+        throw FormatError(path + ": " + e.what());
+    }
+    return db;
+}
+
+// ------------------------------------------------------------------------------------------
+static inline uint32_t pack_hi(uint64_t a, int shift) { return (uint32_t)((a >> 32) & 0xFF) << shift; }
+
+std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std::string& text) {
+    const uint64_t n = d.n, R = d.R;
+    if (n >= SPB_POS_MAX - 1) throw LimitError("BWT length >= 2^40-2 is not supported");
+    if (R >= 0xFFFFFFFFull - SPB_RUN_PAD) throw LimitError("more than 2^32-64 runs are not supported");
+    if (ms && text.size() + 1 != n) throw FormatError("reference text length + 1 != BWT length (is <prefix>.fa the indexed text?)");
+
+    // per-run tables
+    std::vector<uint64_t> start((size_t)R + 1), lf((size_t)R);
+    std::vector<uint64_t> numC(256, 0);
+    std::vector<uint32_t> numRunsC(256, 0);
+    {
+        uint64_t pos = 0;
+        for (uint64_t k = 0; k < R; k++) {
+            start[(size_t)k] = pos;
+            const uint8_t c = d.heads[(size_t)k];
+            lf[(size_t)k] = d.F[c] + numC[c];
+            numC[c] += d.lens[(size_t)k];
+            numRunsC[c]++;
+            pos += d.lens[(size_t)k];
+        }
+        start[(size_t)R] = n;
+    }
+    auto run_of = [&](uint64_t p) -> uint64_t {  // run containing BWT position p (R if p == n)
+        return (uint64_t)(std::upper_bound(start.begin(), start.end(), p) - start.begin()) - 1;
+    };
+    std::vector<uint32_t> dest((size_t)R);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)R; k++) dest[(size_t)k] = (uint32_t)run_of(lf[(size_t)k]);
+
+    // compact alphabet
+    uint32_t sigma = 0;
+    uint32_t cidx[256];
+    for (int c = 0; c < 256; c++) cidx[c] = numRunsC[c] ? sigma++ : 0xFFFFFFFFu;
+    const uint32_t sigma_pad = (uint32_t)align_up(sigma ? sigma : 1, 8);
+    const uint32_t blk_stride = 32 + 4 * sigma_pad;
+    const uint32_t num_blocks = (uint32_t)((R + 31) / 32 + 1);
+    uint64_t num_crec = 0;
+    uint32_t crec_base[256];
+    for (int c = 0; c < 256; c++) {
+        crec_base[c] = (uint32_t)num_crec;
+        if (numRunsC[c]) num_crec += (uint64_t)numRunsC[c] + 1;
+    }
+    if (num_crec >= 0xFFFFFFFFull) throw LimitError("per-character record table exceeds 2^32 entries");
+
+    // layout
+    SpbFlatHeader h;
+    std::memset(&h, 0, sizeof(h));
+    h.magic = SPB_FLAT_MAGIC;
+    h.version = SPB_FLAT_VERSION;
+    h.mode = ms ? 1 : 0;
+    h.n = n;
+    h.R = R;
+    h.n_text = ms ? text.size() : 0;
+    h.last_run_sample = ms ? (d.samples_last[(size_t)R - 1] + 1) % n : 0;
+    h.sigma = sigma;
+    h.sigma_pad = sigma_pad;
+    h.blk_stride = blk_stride;
+    h.num_blocks = num_blocks;
+    h.num_crec = num_crec;
+    h.terminator_position = d.terminator_position;
+    size_t off = align_up(sizeof(SpbFlatHeader), 256);
+    h.off_runs = off;
+    off = align_up(off + ((size_t)R + SPB_RUN_PAD) * sizeof(SpbRunRec), 256);
+    h.off_blocks = off;
+    off = align_up(off + (size_t)num_blocks * blk_stride, 256);
+    h.off_crec = off;
+    off = align_up(off + ((size_t)num_crec + 1) * sizeof(SpbCharRec), 256);
+    if (ms) {
+        h.off_csamp = off;
+        off = align_up(off + ((size_t)num_crec + 1) * sizeof(SpbCharSamp), 256);
+        h.off_text = off;
+        off = align_up(off + text.size() + 64, 256);
+    }
+    h.total_bytes = off;
+    for (int c = 0; c < 256; c++) {
+        h.F[c] = d.F[c];
+        SpbCharTab& t = h.chartab[c];
+        if (numRunsC[c]) {
+            t.crec_base = crec_base[c];
+            t.num_runs = numRunsC[c];
+            t.dest_f = 0;
+            t.cidx = cidx[c];
+        } else {
+            t.crec_base = (uint32_t)(d.F[c] & 0xFFFFFFFFu);
+            t.num_runs = (uint32_t)(d.F[c] >> 32);
+            t.dest_f = (uint32_t)run_of(d.F[c]);
+            t.cidx = 0xFFFFFFFFu;
+        }
+    }
+
+    std::vector<uint8_t> blob(h.total_bytes, 0);
+    std::memcpy(blob.data(), &h, sizeof(h));
+    SpbRunRec* runs = reinterpret_cast<SpbRunRec*>(blob.data() + h.off_runs);
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)R; k++) {
+        SpbRunRec r;
+        r.x = (uint32_t)start[(size_t)k];
+        r.y = (uint32_t)lf[(size_t)k];
+        r.z = dest[(size_t)k];
+        r.w = (uint32_t)d.heads[(size_t)k] | pack_hi(start[(size_t)k], 8) | pack_hi(lf[(size_t)k], 16);
+        runs[k] = r;
+    }
+    for (uint64_t k = R; k < R + SPB_RUN_PAD; k++) {
+        const uint64_t s = k == R ? n : SPB_POS_MAX;
+        SpbRunRec r;
+        r.x = (uint32_t)s;
+        r.y = 0;
+        r.z = (uint32_t)R;
+        r.w = pack_hi(s, 8);  // head 0: never equals a present character
+        runs[k] = r;
+    }
+    // block headers
+    {
+        std::vector<uint32_t> cnt(sigma_pad, 0);
+        for (uint32_t b = 0; b < num_blocks; b++) {
+            uint8_t* hdr = blob.data() + h.off_blocks + (size_t)b * blk_stride;
+            std::memcpy(hdr + 32, cnt.data(), 4 * (size_t)sigma_pad);
+            for (uint32_t t = 0; t < 32; t++) {
+                const uint64_t k = (uint64_t)b * 32 + t;
+                if (k < R) {
+                    hdr[t] = d.heads[(size_t)k];
+                    cnt[cidx[d.heads[(size_t)k]]]++;
+                }
+            }
+        }
+    }
+    // per-character records (+ samples)
+    {
+        SpbCharRec* crec = reinterpret_cast<SpbCharRec*>(blob.data() + h.off_crec);
+        SpbCharSamp* csamp = ms ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_csamp) : nullptr;
+        std::vector<uint32_t> o(256, 0);
+        std::vector<uint64_t> prev_sl(256, 0);
+        for (uint64_t k = 0; k < R; k++) {
+            const uint8_t c = d.heads[(size_t)k];
+            const size_t at = (size_t)crec_base[c] + o[c]++;
+            const uint64_t thr = d.thr[(size_t)k];
+            if (thr > n) throw FormatError("threshold beyond the BWT");
+            SpbCharRec r;
+            r.x = (uint32_t)thr;
+            r.y = (uint32_t)lf[(size_t)k];
+            r.z = dest[(size_t)k];
+            r.w = pack_hi(thr, 0) | pack_hi(lf[(size_t)k], 8);
+            crec[at] = r;
+            if (ms) {
+                csamp[at].ss = d.samples_start[(size_t)k];
+                csamp[at].sl = prev_sl[c];
+                prev_sl[c] = d.samples_last[(size_t)k];
+            }
+        }
+        for (int c = 0; c < 256; c++) {
+            if (!numRunsC[c]) continue;
+            const size_t at = (size_t)crec_base[c] + numRunsC[c];
+            const uint64_t end = d.F[c] + numC[c];
+            SpbCharRec r;
+            r.x = (uint32_t)(n + 1);
+            r.y = (uint32_t)end;
+            r.z = (uint32_t)run_of(end);
+            r.w = pack_hi(n + 1, 0) | pack_hi(end, 8);
+            crec[at] = r;
+            if (ms) {
+                csamp[at].ss = 0;
+                csamp[at].sl = prev_sl[c];
+            }
+        }
+    }
+    if (ms) std::memcpy(blob.data() + h.off_text, text.data(), text.size());
+    return blob;
+}
+
+void validate_flat_image(const void* blob, uint64_t bytes) {
+    if (bytes < sizeof(SpbFlatHeader)) throw FormatError("flat image smaller than its header");
+    SpbFlatHeader h;
+    std::memcpy(&h, blob, sizeof(h));
+    if (h.magic != SPB_FLAT_MAGIC || h.version != SPB_FLAT_VERSION) throw FormatError("not a spumoni_b200 flat image (magic/version)");
+    if (h.total_bytes != bytes) throw FormatError("flat image size mismatch");
+    if (h.off_runs + (h.R + SPB_RUN_PAD) * sizeof(SpbRunRec) > bytes || h.off_crec + (h.num_crec + 1) * sizeof(SpbCharRec) > bytes)
+        throw FormatError("flat image tables exceed the blob");
+}
+
+}  // namespace spb

@@ -1,0 +1,36 @@
+// Host-side index handling: on-disk format -> decoded arrays -> flat device image.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "flat_index.h"
+
+namespace spb {
+
+struct IoError : std::runtime_error { explicit IoError(const std::string& m) : std::runtime_error(m) {} };
+struct LimitError : std::runtime_error { explicit LimitError(const std::string& m) : std::runtime_error(m) {} };
+
+// pml_pointers / ms_pointers after decoding every succinct component into plain arrays
+struct DecodedIndex {
+    uint64_t n = 0, R = 0, terminator_position = 0;
+    std::vector<uint64_t> F;              // 256 entries
+    std::vector<uint8_t> heads;           // R run heads (bytes <= 1 already stored as 1)
+    std::vector<uint64_t> lens;           // R run lengths
+    std::vector<uint64_t> thr;            // R thresholds (BWT positions; 0 for the first run of a letter)
+    std::vector<uint64_t> samples_start;  // MS: R text positions
+    std::vector<uint64_t> samples_last;   // MS: R text positions
+};
+
+struct NullDb {
+    uint64_t num_values = 0;
+    double ks_stat_threshold = 0, mean_null_stat = 0, percentile_value = 0;
+};
+
+DecodedIndex parse_index_file(const std::string& path, bool ms);
+std::string load_reference_text(const std::string& fasta_path);
+NullDb load_null_db(const std::string& path);
+std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std::string& text);
+void validate_flat_image(const void* blob, uint64_t bytes);
+
+}  // namespace spb

@@ -1,0 +1,352 @@
+// `spumoni run` -- drop-in command line for the query side of SPUMONI, on top of the C ABI.
+//
+// Keeps the reference's process seam:
+//   flags / validation      /root/reference/src/spumoni.cpp:163-206, include/spumoni_main.hpp:233-330
+//   run_main                /root/reference/src/spumoni.cpp:733-755
+//   run_spumoni_main        /root/reference/src/compute_ms_pml.cpp:1305-1342   (PML)
+//   run_spumoni_ms_main     /root/reference/src/compute_ms_pml.cpp:1344-1382   (MS)
+//   classify_reads_pml/_ms  /root/reference/src/compute_ms_pml.cpp:845-1034, :1036-1217
+//   BatchLoader             /root/reference/src/batch_loader.cpp:26-131 (FASTA path, id quirk :104-106)
+// Output files (<reads>.pseudo_lengths | .lengths + .pointers | .report) are byte-identical to the
+// reference's single-thread output.  Everything per-base runs on the GPU through
+// libspumoni_b200.so; this file only parses FASTA, batches reads, and formats results.
+// Not supported (outside SURVEY section 8): minimizer digestion (-m/-a, needs bonsai) and the
+// document array (-d).
+#include <getopt.h>
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../../include/spumoni_b200.h"
+
+#define SPUMONI_VERSION "2.0.9"  // version of the reference this CLI mirrors (spumoni_main.hpp:24)
+
+static void fatal_warning(const std::string& m) { std::fprintf(stderr, "Warning: %s\n\n", m.c_str()); std::exit(1); }
+static void fatal_error(const std::string& m) { std::fprintf(stderr, "\n\033[31mError: \033[0m%s\n\n", m.c_str()); std::exit(1); }
+static void force_log(const char* func, const std::string& m) { std::fprintf(stderr, "\033[32m[%s] \033[0m%s\n", func, m.c_str()); }
+static void status_log(const char* func, const std::string& m) { std::fprintf(stderr, "\033[32m[%s] \033[0m%s ... ", func, m.c_str()); }
+static void done_log(double sec) { std::fprintf(stderr, "done.  (%.3f sec)\n", sec); }
+static double now_s() { return std::chrono::duration<double>(std::chrono::system_clock::now().time_since_epoch()).count(); }
+static bool is_file(const std::string& p) { struct stat st; return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode); }
+static bool ends_with(const std::string& s, const std::string& suf) { return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0; }
+static void spb_or_die(int rc) { if (rc) fatal_error(spb_last_error()); }
+
+struct RunOptions {  // SpumoniRunOptions, spumoni_main.hpp:233-249
+    std::string ref_file, pattern_file;
+    bool ms_requested = false, pml_requested = false;
+    size_t threads = 1;
+    bool use_doc = false, write_report = false, min_digest = true, use_promotions = false, use_dna_letters = false,
+         is_general_text = false;
+    size_t k = 4, w = 11, bin_size = 150;
+};
+
+static int run_usage() {
+    std::fprintf(stderr, "spumoni run - Uses a spumoni index to compute MS/PML of patterns w.r.t. a reference.\n");
+    std::fprintf(stderr, "Usage: spumoni run [options]\n\n");
+    std::fprintf(stderr, "Options:\n\tGeneral options:\n");
+    std::fprintf(stderr, "\t%-35sprints this usage message\n", "-h, --help");
+    std::fprintf(stderr, "\t%-25s%-10snumber of helper threads (default: 1)\n\n", "-t, --threads", "[INT]");
+    std::fprintf(stderr, "\tInput/output options:\n");
+    std::fprintf(stderr, "\t%-25s%-10soutput prefix used for index\n", "-r, --ref", "[FILE]");
+    std::fprintf(stderr, "\t%-25s%-10spath to patterns file that will be used.\n", "-p, --pattern", "[FILE]");
+    std::fprintf(stderr, "\t%-25s%-10suse index to compute MSs\n", "-M, --MS", "");
+    std::fprintf(stderr, "\t%-25s%-10suse index to compute PMLs\n", "-P, --PML", "");
+    std::fprintf(stderr, "\t%-25s%-10spattern file is general text (default: FASTA)\n", "-g, --general", "");
+    std::fprintf(stderr, "\t%-25s%-10suse document array to get assignments\n", "-d, --doc-array", "");
+    std::fprintf(stderr, "\t%-25s%-10swrite out the classifications in a report file\n", "-c, --classify", "");
+    std::fprintf(stderr, "\t%-25s%-10ssize of region in bp for classification (default: 150)\n\n", "-w, --window", "[INT]");
+    std::fprintf(stderr, "\tMinimizer options:\n");
+    std::fprintf(stderr, "\t%-25s%-10sturn off minimizer digestion of reads (default: on)\n", "-n, --no-digest", "");
+    std::fprintf(stderr, "\t%-25s%-10suse alphabet-promoted minimizers\n", "-m, --minimizer-alphabet", "");
+    std::fprintf(stderr, "\t%-25s%-10suse DNA-letter based minimizers\n", "-a, --dna-minimizer", "");
+    std::fprintf(stderr, "\t%-25s%-10ssmall window size (k) for finding minimizers (default: 4)\n", "-K, --small-window", "[INT]");
+    std::fprintf(stderr, "\t%-25s%-10slarge window size (w) for finding minimizers (default: 11)\n\n", "-W, --large-window", "[INT]");
+    return 0;
+}
+
+static void parse_run_options(int argc, char** argv, RunOptions* o) {
+    static struct option long_options[] = {
+        {"help", no_argument, NULL, 'h'},          {"threads", required_argument, NULL, 't'},
+        {"ref", required_argument, NULL, 'r'},     {"pattern", required_argument, NULL, 'p'},
+        {"MS", no_argument, NULL, 'M'},            {"PML", no_argument, NULL, 'P'},
+        {"general-text", no_argument, NULL, 'g'},  {"doc-array", no_argument, NULL, 'd'},
+        {"classify", no_argument, NULL, 'c'},      {"window", required_argument, NULL, 'w'},
+        {"no-digest", no_argument, NULL, 'n'},     {"minimizer-alphabet", no_argument, NULL, 'm'},
+        {"dna-minimizer", no_argument, NULL, 't'}, {"small-window", required_argument, NULL, 'K'},
+        {"large-window", required_argument, NULL, 'W'}, {0, 0, 0, 0}};
+    int long_index = 0;
+    for (int c; (c = getopt_long(argc, argv, "hr:p:MPt:dcnmaK:W:w:g", long_options, &long_index)) >= 0;) {
+        switch (c) {
+            case 'h': run_usage(); std::exit(1);
+            case 'r': o->ref_file.assign(optarg); break;
+            case 'p': o->pattern_file.assign(optarg); break;
+            case 'M': o->ms_requested = true; break;
+            case 'P': o->pml_requested = true; break;
+            case 'c': o->write_report = true; break;
+            case 'm': o->use_promotions = true; break;
+            case 'a': o->use_dna_letters = true; break;
+            case 'n': o->min_digest = false; break;
+            case 'K': o->k = std::max(std::atoi(optarg), 1); break;
+            case 'W': o->w = std::max(std::atoi(optarg), 1); break;
+            case 'w': o->bin_size = std::max(std::atoi(optarg), 1); break;
+            case 'g': o->is_general_text = true; break;
+            case 't': o->threads = std::max(std::atoi(optarg), 1); break;
+            case 'd': o->use_doc = true; break;
+            default: run_usage(); std::exit(1);
+        }
+    }
+}
+
+static void validate(const RunOptions& o, bool ms) {  // SpumoniRunOptions::validate, spumoni_main.hpp:267-329
+    if (o.ref_file == "" || o.pattern_file == "") fatal_warning("Both a reference file (-r) and pattern file (-p) must be provided.");
+    if (o.ms_requested == o.pml_requested) fatal_warning("An output type with -M or -P must be specified, only one can be used at a time.");
+    const std::string ext = o.use_promotions ? ".bin" : ".fa";
+    if (!is_file(o.ref_file + ext)) fatal_error("The following path is not valid: " + o.ref_file + ext + " (remember to only specify output prefix)");
+    if (!is_file(o.pattern_file)) fatal_error("The following path is not valid: " + o.pattern_file);
+    if (!o.is_general_text && !ends_with(o.pattern_file, ".fa") && !ends_with(o.pattern_file, ".fasta") && !ends_with(o.pattern_file, ".fna"))
+        fatal_error("The pattern file provided does not appear to be a FASTA\n       file, please convert to FASTA and re-run.");
+    if (o.is_general_text && o.min_digest) fatal_warning("For general-text querying, minimizer digestion must be turned off with -n.");
+    if (o.is_general_text && o.threads > 1) fatal_warning("For general-text querying, multi-threading is not available.");
+    if (o.is_general_text && o.write_report) fatal_warning("For general-text querying, classification is not available.");
+    if (o.use_doc) fatal_warning("the document array (-d) is not supported by spumoni_b200.");
+    if (!is_file(o.ref_file + ext + (ms ? ".thrbv.ms" : ".thrbv.spumoni")))
+        fatal_warning("The index required for this computation is not available, please use spumoni build.");
+    if (o.k > 4) fatal_warning("small window size (k) cannot be larger than 4 characters.");
+    if (o.w < o.k) fatal_warning("large window size (w) should be larger than the small window size (k)");
+    if (o.min_digest) {
+        if (o.use_promotions && o.use_dna_letters) fatal_error("Only one type of minimizer can be specified from either -m or -a.");
+        if (!o.use_promotions && !o.use_dna_letters) fatal_error("A minimizer type must be specified using -m or -a.");
+        fatal_error("minimizer digestion (-m/-a) is not supported by spumoni_b200; build and query with -n.");
+    } else if (o.use_promotions || o.use_dna_letters)
+        fatal_error("A minimizer type should not be specified if intending not to use minimizer digestion.");
+    if (o.bin_size < 50 || o.bin_size > 400) fatal_warning("the bin size used is not optimal. Re-run using a value between 50 and 400.");
+}
+
+// ---------------------------------------------------------------------------------- input
+struct ReadBatch {
+    std::vector<std::string> ids;
+    std::vector<uint64_t> offsets{0};
+    std::vector<uint8_t> bases;
+    void clear() { ids.clear(); offsets.assign(1, 0); bases.clear(); }
+};
+
+class FastaSource {  // sequential equivalent of BatchLoader::loadBatch + grabNextRead (FASTA)
+public:
+    explicit FastaSource(const std::string& path) : in_(path.c_str()) {
+        if (!in_.good()) return;
+        int pk = in_.peek();
+        if (pk == EOF) { done_ = true; return; }
+        if (pk != '>') fatal_error("unrecognized input query file type - expects FASTA or FASTQ.");
+        if (!std::getline(in_, line_)) done_ = true;
+    }
+    // appends one record; false at end of input
+    bool next(ReadBatch& b) {
+        if (done_ || line_.empty()) return false;  // an empty header line ends the input (batch_loader.cpp:87)
+        if (line_[0] != '>') fatal_error(std::string("Incorrect FASTA entry, it should start with '>' but found ") + line_[0]);
+        if (line_.size() <= 2) fatal_error("header line is missing an id. invalid query cannot be processed.");
+        size_t idl = line_.find_first_of(" \t\r", 1);
+        idl = (idl == std::string::npos) ? line_.size() : idl;
+        b.ids.push_back(line_.substr(1, idl));  // keeps the delimiter (batch_loader.cpp:104-106)
+        const size_t before = b.bases.size();
+        for (;;) {
+            if (!std::getline(in_, line_)) { done_ = true; break; }
+            if (!line_.empty() && line_[0] == '>') break;
+            size_t e = line_.size();
+            while (e > 0 && std::isspace((unsigned char)line_[e - 1])) e--;
+            b.bases.insert(b.bases.end(), line_.begin(), line_.begin() + e);
+        }
+        if (b.bases.size() == before) {  // compute_ms_pml.cpp:926-931
+            std::cout << "\n\n";
+            fatal_warning(b.ids.back() + " was empty after digestion, commonly due to reads consisting of mostly non-ACGT "
+                          "characters. Please remove read or run SPUMONI without minimizer digestion.");
+        }
+        b.offsets.push_back(b.bases.size());
+        return true;
+    }
+private:
+    std::ifstream in_;
+    std::string line_;
+    bool done_ = false;
+};
+
+// ---------------------------------------------------------------------------------- output
+static inline char* put_uint(char* p, uint64_t v) {
+    char tmp[24];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+
+template <typename T>
+static void format_values(const ReadBatch& b, const T* vals, int threads, std::vector<std::string>& out) {
+    const size_t nr = b.ids.size();
+    out.resize(nr);
+#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    for (int64_t r = 0; r < (int64_t)nr; r++) {
+        const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1];
+        std::string& s = out[r];
+        s.resize(b.ids[r].size() + 3 + (hi - lo) * 21);
+        char* p = &s[0];
+        *p++ = '>';
+        std::memcpy(p, b.ids[r].data(), b.ids[r].size());
+        p += b.ids[r].size();
+        *p++ = '\n';
+        for (uint64_t i = lo; i < hi; i++) { p = put_uint(p, (uint64_t)vals[i]); *p++ = ' '; }
+        *p++ = '\n';
+        s.resize((size_t)(p - &s[0]));
+    }
+}
+
+static void write_all(std::ofstream& f, const std::vector<std::string>& parts) {
+    for (const auto& s : parts) f.write(s.data(), (std::streamsize)s.size());
+}
+
+static void report_header(std::ofstream& f, size_t thr) {  // compute_ms_pml.cpp:877-886
+    f.precision(4);
+    f << std::setw(30) << std::left << "read id:" << std::setw(15) << std::left << "status:" << std::setw(19) << std::left
+      << "avg max-value (thr=" << std::setw(2) << std::left << thr << std::setw(5) << std::left << "):" << std::setw(12)
+      << std::left << "above thr:" << std::setw(12) << std::left << "below thr:" << std::endl;
+}
+static void report_row(std::ofstream& f, const std::string& id, const spb_bin_stats& s) {  // :1012-1020
+    const size_t nbins = (size_t)s.above + s.below;
+    const bool found = (s.above / (s.above + s.below + 0.0) > 0.50);
+    f.precision(3);
+    f << std::setw(30) << std::left << id << std::setw(15) << std::left << (found ? "FOUND" : "NOT_PRESENT") << std::setw(26)
+      << std::left << (s.sum_max + 0.0) / nbins << std::setw(12) << std::left << (size_t)s.above << std::setw(12) << std::left
+      << (size_t)s.below << std::endl;
+}
+
+// ---------------------------------------------------------------------------------- driver
+struct Outputs {
+    std::ofstream lengths, pointers, report;
+};
+
+static void process_batch(spb_index* idx, bool ms, const RunOptions& o, const spb_query_opts& qo, ReadBatch& b, Outputs& out,
+                          std::vector<uint32_t>& L, std::vector<uint64_t>& P, std::vector<spb_bin_stats>& S) {
+    const size_t nr = b.ids.size();
+    if (!nr) return;
+    L.resize(b.bases.size());
+    if (ms) P.resize(b.bases.size());
+    if (o.write_report) S.resize(nr);
+    if (ms) spb_or_die(spb_ms_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), P.data(), o.write_report ? S.data() : nullptr, &qo));
+    else spb_or_die(spb_pml_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), o.write_report ? S.data() : nullptr, &qo));
+    std::vector<std::string> parts;
+    format_values(b, L.data(), (int)o.threads, parts);
+    write_all(out.lengths, parts);
+    if (ms) {
+        format_values(b, P.data(), (int)o.threads, parts);
+        write_all(out.pointers, parts);
+    }
+    if (o.write_report)
+        for (size_t r = 0; r < nr; r++) report_row(out.report, b.ids[r], S[r]);
+}
+
+static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
+    Outputs out;
+    out.lengths.open(o.pattern_file + (ms ? ".lengths" : ".pseudo_lengths"));
+    if (ms) out.pointers.open(o.pattern_file + ".pointers");
+    spb_query_opts qo;
+    std::memset(&qo, 0, sizeof(qo));
+    qo.flags = o.is_general_text ? 0 : SPB_QUERY_TOUPPER;  // general text is used verbatim (:1219-1297)
+    if (!o.is_general_text) {
+        // the reference loads the null database unconditionally (:864-869) but only uses it with -c
+        spb_nulldb db;
+        std::memset(&db, 0, sizeof(db));
+        const std::string dbp = o.ref_file + (ms ? ".msnulldb" : ".pmlnulldb");
+        if (is_file(dbp)) spb_or_die(spb_nulldb_load(dbp.c_str(), &db));
+        else if (o.write_report) fatal_error("The following path is not valid: " + dbp);
+        qo.max_value_thr = spb_max_value_threshold(db.percentile_value, ms ? 0 : 1, o.use_dna_letters, o.use_promotions);
+        if (o.write_report) {
+            out.report.open(o.pattern_file + ".report", std::ofstream::out);
+            qo.bin_width = (uint32_t)o.bin_size;
+            report_header(out.report, qo.max_value_thr);
+        }
+    }
+    const uint64_t kBatchBases = 256ull << 20;
+    ReadBatch b;
+    std::vector<uint32_t> L;
+    std::vector<uint64_t> P;
+    std::vector<spb_bin_stats> S;
+    size_t num_reads = 0;
+    if (!o.is_general_text) {
+        FastaSource src(o.pattern_file);
+        while (src.next(b)) {
+            num_reads++;
+            if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S); b.clear(); }
+        }
+    } else {  // classify_general_reads_*: reads are separated by 0x01, ids are read_<i>
+        std::ifstream fd(o.pattern_file, std::ifstream::in | std::ifstream::binary);
+        char ch = (char)fd.get();
+        while (fd.good()) {
+            if (ch == '\x01') {
+                b.ids.push_back("read_" + std::to_string(num_reads));
+                b.offsets.push_back(b.bases.size());
+                num_reads++;
+                if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S); b.clear(); }
+            } else
+                b.bases.push_back((uint8_t)ch);
+            ch = (char)fd.get();
+        }
+        b.bases.resize(b.offsets.back());  // bytes after the last separator are never queried
+    }
+    process_batch(idx, ms, o, qo, b, out, L, P, S);
+    return num_reads;
+}
+
+static int run_main(int argc, char** argv) {
+    if (argc == 1) return run_usage();
+    RunOptions o;
+    parse_run_options(argc, argv, &o);
+    const bool ms = o.ms_requested && !o.pml_requested;
+    validate(o, ms);
+    o.ref_file += o.use_promotions ? ".bin" : ".fa";
+    const char* tag = ms ? "compute_ms" : "compute_pml";
+
+    status_log(ms ? "ms_construct" : "pml_construct", ms ? "loading the MS index" : "loading the PML index");
+    double t0 = now_s();
+    spb_index* idx = nullptr;
+    spb_or_die(spb_index_open(o.ref_file.c_str(), ms ? SPB_MODE_MS : SPB_MODE_PML, &idx));
+    int dev = 0;
+    if (const char* e = std::getenv("SPUMONI_B200_DEVICE")) dev = std::atoi(e);
+    spb_or_die(spb_index_to_device(idx, dev));
+    done_log(now_s() - t0);
+    std::cout << std::endl;
+    force_log(tag, "input reads will be used directly, no minimizer digestion");
+
+    t0 = now_s();
+    status_log(tag, ms ? "processing the reads" : "processing the patterns");
+    size_t num_reads = classify_reads(idx, ms, o);
+    done_log(now_s() - t0);
+    force_log(tag, "finished processing " + std::to_string(num_reads) + " reads. results are saved in *." + (ms ? "lengths" : "pseudo_lengths") + " file.");
+    std::cout << std::endl;
+    spb_index_close(idx);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    std::fprintf(stderr, "\n\033[1m\033[31mSPUMONI version: %s \033[0m(spumoni_b200 query engine)\n\n", SPUMONI_VERSION);
+    if (argc > 1) {
+        if (std::strcmp(argv[1], "run") == 0) return run_main(argc - 1, argv + 1);
+        if (std::strcmp(argv[1], "build") == 0) {
+            std::fprintf(stderr, "spumoni_b200 provides the `run` sub-command only; build indexes with the reference's `spumoni build`.\n");
+            return 1;
+        }
+    }
+    std::fprintf(stderr, "SPUMONI has different sub-commands to run which can used as follows:\nUsage: spumoni <command> [options]\n\n");
+    std::fprintf(stderr, "Commands:\n\trun\tcomputes MSs or PMLs for patterns against already built SPUMONI index.\n\n");
+    return 1;
+}

@@ -1,0 +1,112 @@
+"""CPU: the product's host side (on-disk parse -> flat image) against the oracle, without a GPU.
+
+The flat image is walked by tests/flat_emulator.py (a Python transcription of the kernel's step)."""
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import spumoni_b200 as sp
+from conftest import MKINDEX, build_index
+from flat_emulator import FlatImage
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")
+
+
+def test_flat_image_matches_golden_vectors(tmp_path):
+    for ci, case in enumerate(json.load(open(GOLDEN))["cases"]):
+        ref = build_index(str(tmp_path / f"c{ci}"), text=case["text"].encode("latin1"))
+        pml, ms = sp.Index.open(ref, sp.MODE_PML), sp.Index.open(ref, sp.MODE_MS)
+        assert pml.get_bwt_stats() == (case["n"], case["r"]) == ms.get_bwt_stats()
+        fp, fm = FlatImage(pml.flat()), FlatImage(ms.flat())
+        for rd in case["reads"]:
+            read = rd["read"].encode("latin1")
+            assert fp.walk(read)[0] == rd["pml"]
+            _, ptr = fm.walk(read)
+            assert [str(x) for x in ptr] == rd["ms_pointers"]
+            assert fm.ms_lengths(read, ptr) == rd["ms_lengths"]
+
+
+def test_flat_image_vs_oracle_random(tmp_path):
+    rng = random.Random(17)
+    for trial in range(12):
+        n = rng.randint(50, 4000)
+        alpha = rng.choice(["ACGT", "ACGTN", "ACGT\xe9"])
+        if rng.random() < 0.4:  # repetitive: long runs, windows that overflow
+            unit = "".join(rng.choice(alpha) for _ in range(rng.randint(2, 30)))
+            text = "".join(unit if rng.random() < 0.93 else rng.choice(alpha) for _ in range(n // len(unit) + 1))
+        else:
+            text = "".join(rng.choice(alpha) for _ in range(n))
+        tb = text.encode("latin1")
+        ref = build_index(str(tmp_path / f"t{trial}"), text=tb, revcomp=(alpha == "ACGT" and trial % 2 == 0))
+        po, mo = oracle.OracleIndex(ref, "pml"), oracle.OracleIndex(ref, "ms")
+        fp, fm = FlatImage(sp.Index.open(ref, 0).flat()), FlatImage(sp.Index.open(ref, 1).flat())
+        for _ in range(8):
+            ln = rng.randint(1, 150)
+            read = bytes(rng.choice(b"ACGTNY\xe9") for _ in range(ln)) if rng.random() < 0.4 else (tb[rng.randint(0, max(0, len(tb) - ln)):][:ln] or b"A")
+            assert fp.walk(read)[0] == po.matching_statistics(read).tolist()
+            L, P = mo.matching_statistics(read)
+            _, ptr = fm.walk(read)
+            assert ptr == P.tolist() and fm.ms_lengths(read, ptr) == L.tolist()
+
+
+def test_flat_roundtrip_and_header(small_index):
+    idx = sp.Index.open(small_index["ref"], sp.MODE_PML)
+    blob = np.array(idx.flat(), copy=True)
+    again = sp.Index.from_flat(blob)
+    assert again.get_bwt_stats() == idx.get_bwt_stats()
+    assert np.array_equal(again.flat(), blob)
+    hdr = sp.Index.from_header(blob[: sp.flat_header_bytes()])
+    assert hdr.get_bwt_stats() == idx.get_bwt_stats()
+    with pytest.raises(sp.SpumoniError):
+        hdr.flat()  # header-only index carries no host image
+    with pytest.raises(sp.SpumoniError):
+        sp.Index.from_flat(blob[:-8])
+
+
+def test_corrupt_and_missing_files_fail_loudly(small_index, tmp_path):
+    with pytest.raises(sp.SpumoniError) as e:
+        sp.Index.open(str(tmp_path / "nope.fa"), sp.MODE_PML)
+    assert e.value.code == 1  # SPB_ERR_IO
+    src = small_index["ref"] + ".thrbv.spumoni"
+    data = open(src, "rb").read()
+    bad = str(tmp_path / "bad.fa")
+    open(bad + ".thrbv.spumoni", "wb").write(data[: len(data) // 2])  # truncated
+    with pytest.raises(sp.SpumoniError) as e:
+        sp.Index.open(bad, sp.MODE_PML)
+    assert e.value.code == 2  # SPB_ERR_FORMAT
+    open(bad + ".thrbv.spumoni", "wb").write(data + b"\0" * 8)  # must be consumed exactly to EOF
+    with pytest.raises(sp.SpumoniError):
+        sp.Index.open(bad, sp.MODE_PML)
+    corrupt = bytearray(data)
+    corrupt[8 + 8 + 65 * 8] ^= 0x10  # F['A']
+    open(bad + ".thrbv.spumoni", "wb").write(bytes(corrupt))
+    with pytest.raises(sp.SpumoniError):
+        sp.Index.open(bad, sp.MODE_PML)
+
+
+def test_ms_index_requires_matching_text(small_index, tmp_path):
+    ref = str(tmp_path / "x.fa")
+    open(ref, "w").write(">s\nACGT\n")
+    open(ref + ".thrbv.ms", "wb").write(open(small_index["ref"] + ".thrbv.ms", "rb").read())
+    with pytest.raises(sp.SpumoniError):
+        sp.Index.open(ref, sp.MODE_MS)
+
+
+def test_nulldb_roundtrip(tmp_path):
+    vals = np.array([3, 3, 3, 3, 3, 9, 9, 9, 9, 9, 9, 11, 11, 2, 0, 16], dtype=np.uint64)
+    vals.tofile(str(tmp_path / "s.bin"))
+    out = str(tmp_path / "x.pmlnulldb")
+    subprocess.check_call([MKINDEX, "nulldb", "--stats", str(tmp_path / "s.bin"), "--out", out, "--ks-thr", "0.25"])
+    db = sp.EmpNullDatabase().load(out)
+    assert db.num_values == 16 and db.percentile_value == 9.0 and db.ks_stat_threshold == 0.25
+    assert abs(db.mean_null_stat - float(vals.mean())) < 1e-12
+    assert oracle.nulldb_percentile(out) == 9.0
+    assert sp.max_value_threshold(db.percentile_value, True) == 13
+    assert sp.max_value_threshold(1.0, False) == 3
+    raw = open(out, "rb").read()  # width = max(ceil(log2(16)),1) = 4 bits (reference quirk: 16 itself does not fit)
+    assert raw[32 + 8] == 4

@@ -1,0 +1,233 @@
+"""GPU: parity of the CUDA path (through the C ABI) with the oracle. Run with `-m gpu` on a B200."""
+import json
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import spumoni_b200 as sp
+from oracle import naive
+from conftest import MKINDEX, build_index, load_bin_reads
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")
+LANES = [4, 8, 16, 32]
+
+
+def oracle_batch(ref, mode, buf, off):
+    idx = oracle.OracleIndex(ref, mode)
+    _, L, P = idx.query_batch(buf, off, threads=os.cpu_count() or 1)
+    return L, P
+
+
+@pytest.mark.parametrize("lanes", LANES)
+def test_golden_vectors(tmp_path, lanes):
+    for ci, case in enumerate(json.load(open(GOLDEN))["cases"]):
+        ref = build_index(str(tmp_path / f"c{ci}"), text=case["text"].encode("latin1"))
+        pml, ms = sp.pml_t(ref), sp.ms_t(ref)
+        assert pml.get_bwt_stats() == (case["n"], case["r"])
+        reads = [rd["read"].encode("latin1") for rd in case["reads"]]
+        buf, off = sp.pack_reads(reads)
+        L, _, _ = pml.query_host(buf, off, lanes=lanes)
+        Lm, Pm, _ = ms.query_host(buf, off, lanes=lanes)
+        for i, rd in enumerate(case["reads"]):
+            a, b = int(off[i]), int(off[i + 1])
+            assert L[a:b].tolist() == rd["pml"]
+            assert [str(x) for x in Pm[a:b].tolist()] == rd["ms_pointers"]
+            assert Lm[a:b].tolist() == rd["ms_lengths"]
+            # reference-shaped single-read call
+            assert pml.matching_statistics(reads[i], lanes=lanes).tolist() == rd["pml"]
+
+
+@pytest.mark.parametrize("lanes", LANES)
+def test_small_index_all_reads(small_index, lanes):
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    L, _, _ = sp.pml_t(small_index["ref"]).query_host(buf, off, lanes=lanes)
+    assert np.array_equal(L.astype(np.uint64), Lo)
+    Lo, Po = oracle_batch(small_index["ref"], "ms", buf, off)
+    L, P, _ = sp.ms_t(small_index["ref"]).query_host(buf, off, lanes=lanes)
+    assert np.array_equal(P, Po)
+    assert np.array_equal(L.astype(np.uint64), Lo)
+
+
+def test_edge_cases(small_index):
+    ref = small_index["ref"]
+    pml, ms = sp.pml_t(ref), sp.ms_t(ref)
+    # empty batch
+    L, _, _ = pml.query_host(np.zeros(0, np.uint8), np.zeros(1, np.uint64))
+    assert L.size == 0
+    # single bases, absent characters, bytes >= 0x80, NUL, the terminator byte, empty reads inside a batch
+    reads = [b"A", b"N", b"\xe9", b"\x00", b"\x01", b"", b"ACGT" * 30, b"", b"NNNNACGTNNNN", b"ACG\xffT\x80ACGTACGTA", b"Y" * 40,
+             b"ACGTTGCA" * 200 + b"N" + b"TTGACCA" * 150]
+    buf, off = sp.pack_reads(reads)
+    po, mo = oracle.OracleIndex(ref, "pml"), oracle.OracleIndex(ref, "ms")
+    for lanes in LANES:
+        L, _, _ = pml.query_host(buf, off, lanes=lanes)
+        Lm, Pm, _ = ms.query_host(buf, off, lanes=lanes)
+        for i, r in enumerate(reads):
+            a, b = int(off[i]), int(off[i + 1])
+            if not r:
+                continue
+            assert L[a:b].tolist() == po.matching_statistics(r).tolist(), (lanes, r[:20])
+            lo, p_o = mo.matching_statistics(r)
+            assert Pm[a:b].tolist() == p_o.tolist() and Lm[a:b].tolist() == lo.tolist(), (lanes, r[:20])
+
+
+def test_toupper_flag(small_index):
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    pml = sp.pml_t(small_index["ref"])
+    lower = np.where((buf >= 65) & (buf <= 90), buf + 32, buf).astype(np.uint8)
+    L0, _, _ = pml.query_host(buf, off)
+    L1, _, _ = pml.query_host(lower, off, toupper=True)
+    L2, _, _ = pml.query_host(lower, off, toupper=False)
+    assert np.array_equal(L0, L1) and not np.array_equal(L0, L2)
+
+
+def test_window_overflow_fallback(tmp_path):
+    """Long BWT runs whose LF image spans hundreds of runs: exercises locate_run's binary search."""
+    rng = random.Random(5)
+    w = "ACGTACGTTTGACAGGATTACA"
+    text = "".join(rng.choice("ACT") + "G" + w + "".join(rng.choice("ACGT") for _ in range(rng.randint(3, 9))) for _ in range(600))
+    ref = build_index(str(tmp_path), text=text.encode())
+    reads = []
+    for _ in range(200):
+        s = rng.randint(0, len(text) - 80)
+        reads.append(text[s:s + rng.randint(30, 80)].encode())
+    reads += [("C" + "G" + w).encode(), ("TG" + w + "A").encode(), (w * 3).encode()]
+    buf, off = sp.pack_reads(reads)
+    Lo, _ = oracle_batch(ref, "pml", buf, off)
+    Lmo, Pmo = oracle_batch(ref, "ms", buf, off)
+    for lanes in LANES:
+        L, _, _ = sp.pml_t(ref).query_host(buf, off, lanes=lanes)
+        assert np.array_equal(L.astype(np.uint64), Lo)
+        Lm, Pm, _ = sp.ms_t(ref).query_host(buf, off, lanes=lanes)
+        assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
+
+
+@pytest.mark.parametrize("mode", ["pml", "ms"])
+def test_classifier_stats(small_index, mode):
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    idx = sp.pml_t(small_index["ref"]) if mode == "pml" else sp.ms_t(small_index["ref"])
+    for bw, thr in ((50, 7), (150, 13), (400, 3)):
+        L, _, S = idx.query_host(buf, off, bin_width=bw, max_value_thr=thr)
+        for r in range(len(off) - 1):
+            found, summ, above, below, nb = naive.classify_bins(L[int(off[r]):int(off[r + 1])].tolist(), bw, thr)
+            assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)
+
+
+def test_multi_chunk_pipeline_and_ragged_lengths(small_index):
+    """> 32 Mi bases forces several pipelined sub-batches; expected output tiles the oracle's."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    reps = (40 << 20) // len(buf) + 1
+    big = np.tile(buf, reps)
+    lens = np.diff(off)
+    big_off = np.concatenate([[0], np.cumsum(np.tile(lens, reps))]).astype(np.uint64)
+    L, _, _ = sp.pml_t(small_index["ref"]).query_host(big, big_off)
+    assert L.size == len(buf) * reps
+    assert np.array_equal(L.reshape(reps, -1).astype(np.uint64), np.broadcast_to(Lo, (reps, len(buf))))
+
+
+def test_device_api_with_torch_tensors(small_index):
+    import torch
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    idx = sp.pml_t(small_index["ref"])
+    dev = torch.device("cuda", 0)
+    d_reads = torch.zeros(len(buf) + 512, dtype=torch.uint8, device=dev)
+    d_reads[: len(buf)] = torch.from_numpy(buf).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_len = torch.zeros(len(buf), dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        idx.query_device(d_reads, d_off, len(off) - 1, d_len, stream=s.cuda_stream)
+    s.synchronize()
+    assert np.array_equal(d_len.cpu().numpy().astype(np.uint64), Lo)
+    with pytest.raises(sp.SpumoniError):  # alignment contract
+        idx.query_device(d_reads[16:], d_off, len(off) - 1, d_len)
+    assert sp.kernel_launches() > 0
+
+
+def test_attach_device_from_broadcast_buffer(small_index):
+    import torch
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    base = sp.Index.open(small_index["ref"], sp.MODE_PML)
+    blob = np.array(base.flat(), copy=True)
+    dev_blob = torch.from_numpy(blob).to("cuda:0")
+    idx = sp.Index.from_header(blob[: sp.flat_header_bytes()]).attach_device(0, dev_blob)
+    L, _, _ = idx.query_host(buf, off)
+    L2, _, _ = base.to_device(0).query_host(buf, off)
+    assert np.array_equal(L, L2)
+
+
+@pytest.mark.parametrize("flags", [["-P"], ["-P", "-c"], ["-M"], ["-M", "-c", "-w", "100"]])
+def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
+    ref = small_index["ref"]
+    for ext in (".pmlnulldb", ".msnulldb"):
+        stats = (np.arange(1, 200, dtype=np.uint64) * 7) % 11
+        stats.tofile(str(tmp_path / "stats.bin"))
+        subprocess.check_call([MKINDEX, "nulldb", "--stats", str(tmp_path / "stats.bin"), "--out", ref + ext])
+    qa, qb = str(tmp_path / "a.fa"), str(tmp_path / "b.fa")
+    body = open(small_index["reads_fa"]).read()
+    body = body.replace(">read_3\n", ">read_3 with description\n").replace(">read_5\n", ">read_5\tx\n")
+    body = body.replace("ACGT", "acgt", 5)
+    open(qa, "w").write(body)
+    open(qb, "w").write(body)
+    ms = "-M" in flags
+    bw = int(flags[flags.index("-w") + 1]) if "-w" in flags else 150
+    oracle.run(ref, qa, "ms" if ms else "pml", report="-c" in flags, bin_width=bw, threads=1)
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", ref[:-3], "-p", qb, "-n"] + flags, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    exts = [".lengths", ".pointers"] if ms else [".pseudo_lengths"]
+    if "-c" in flags:
+        exts.append(".report")
+    for e in exts:
+        assert open(qa + e, "rb").read() == open(qb + e, "rb").read(), e
+    assert "finished processing 300 reads" in r.stderr
+
+
+def test_cli_empty_read_aborts_like_reference(small_index, tmp_path):
+    q = str(tmp_path / "q.fa")
+    open(q, "w").write(">a\nACGT\n>b\n>c\nACGT\n")
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", small_index["ref"][:-3], "-p", q, "-P", "-n"], capture_output=True, text=True)
+    assert r.returncode == 1 and "was empty after digestion" in r.stderr
+
+
+def test_cli_general_text(small_index, tmp_path):
+    q = str(tmp_path / "q.txt")
+    open(q, "wb").write(b"ACGTACGTAGGT\x01acgtNNACGT\x01TTTT\x01tail-without-separator")
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", small_index["ref"][:-3], "-p", q, "-P", "-n", "-g"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    po = oracle.OracleIndex(small_index["ref"], "pml")
+    exp = b""
+    for i, rd in enumerate([b"ACGTACGTAGGT", b"acgtNNACGT", b"TTTT"]):
+        exp += b">read_%d\n" % i + b"".join(b"%d " % v for v in po.matching_statistics(rd).tolist()) + b"\n"
+    assert open(q + ".pseudo_lengths", "rb").read() == exp
+
+
+def test_medium_scale_properties(tmp_path):
+    """2 Mb pangenome, 20k x 500 bp reads: full comparison with the (multi-threaded) oracle plus
+    size-independent properties (PML <= MS, X[i] <= X[i+1]+1, pointers in range when no char is absent)."""
+    d = str(tmp_path)
+    from conftest import mkindex
+    mkindex("genome", "--kind", "pangenome", "--len", 2000000, "--haps", 10, "--snp", 0.002, "--indel", 0.0002, "--seed", 21, "--out", d + "/raw.fa")
+    ref = build_index(d, fasta=d + "/raw.fa", revcomp=True)
+    mkindex("reads", "--ref", ref, "--n", 20000, "--len", 500, "--sub", 0.06, "--ins", 0.02, "--del", 0.02, "--neg-frac", 0.1, "--seed", 22, "--bin", d + "/r.bin")
+    buf, off = load_bin_reads(d + "/r.bin")
+    Lp, _, _ = sp.pml_t(ref).query_host(buf, off)
+    Lm, Pm, _ = sp.ms_t(ref).query_host(buf, off)
+    n = sp.Index.open(ref, 0).get_bwt_stats()[0]
+    assert np.all(Lp <= Lm)
+    inner = np.ones(len(buf), dtype=bool)
+    inner[(off[1:] - 1).astype(np.int64)] = False  # last position of each read has no successor
+    assert np.all(Lm[:-1][inner[:-1]] <= Lm[1:][inner[:-1]] + 1)
+    assert np.all(Lp[:-1][inner[:-1]] <= Lp[1:][inner[:-1]] + 1)
+    assert np.all(Pm < n)
+    Lo, _ = oracle_batch(ref, "pml", buf, off)
+    assert np.array_equal(Lp.astype(np.uint64), Lo)
+    Lmo, Pmo = oracle_batch(ref, "ms", buf, off)
+    assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
