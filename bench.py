@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- PML-mode classification throughput (bases/sec) of the B200 hot path.
+
+Workload (BASELINE.json configs[1]): PML on a 100 Mb pangenome index (20 x 5 Mb haplotypes, 0.1 % SNPs,
+0.01 % indels, + reverse complement, n ~ 2e8), 1 M synthetic 1 kb ONT-like reads (6 % sub, 2 % ins, 2 % del,
+10 % negatives) per GPU.  A "step" is one pass of the hot path over the rank's 1 M reads (1e9 bases).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
+  python bench.py --impl reference [--gpus N] ...              the CPU path (oracle port), all host threads
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
+"""
+from __future__ import annotations
+
+import argparse
+import hashlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+MKINDEX = os.path.join(ROOT, "tools", "bin", "spumoni_mkindex")
+
+BYTES_PER_BASE_PML = 69  # 1 B read + 4 B length + 2 x 32 B index sectors
+METRIC = "bases/sec PML-mode classification"
+
+WORKLOADS = {
+    # name: (genome args, reads per rank, read length, read args)
+    "c2": dict(genome=["--kind", "pangenome", "--len", "100000000", "--haps", "20", "--snp", "0.001", "--indel", "0.0001", "--seed", "3"],
+               n_reads=1_000_000, read_len=1000, reads=["--sub", "0.06", "--ins", "0.02", "--del", "0.02", "--neg-frac", "0.1"],
+               desc="PML, 100 Mb pangenome index (20x5 Mb, +revcomp), 1 M x 1 kb ONT-like reads per GPU"),
+    # development-size stand-in (NOT a bench line): SPB_BENCH_WORKLOAD=dev
+    "dev": dict(genome=["--kind", "pangenome", "--len", "4000000", "--haps", "8", "--snp", "0.001", "--indel", "0.0001", "--seed", "3"],
+                n_reads=50_000, read_len=1000, reads=["--sub", "0.06", "--ins", "0.02", "--del", "0.02", "--neg-frac", "0.1"],
+                desc="DEV ONLY: PML, 4 Mb pangenome index, 50 k x 1 kb reads per GPU"),
+}
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def cache_dir(name: str) -> str:
+    w = WORKLOADS[name]
+    key = hashlib.sha1(json.dumps([w["genome"], "fixture-v1"]).encode()).hexdigest()[:12]
+    base = os.environ.get("SPUMONI_B200_CACHE", "/tmp/spumoni_b200_cache")
+    d = os.path.join(base, f"{name}_{key}")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def ensure_index(name: str) -> str:
+    """Untimed setup: synthetic reference + `spumoni build` stand-in (tools/). Returns ref_file (<prefix>.fa)."""
+    d = cache_dir(name)
+    ref = os.path.join(d, "idx.fa")
+    if os.path.exists(ref + ".thrbv.spumoni") and os.path.exists(os.path.join(d, "ok")):
+        return ref
+    t0 = time.time()
+    subprocess.check_call([MKINDEX, "genome", "--out", os.path.join(d, "raw.fa")] + WORKLOADS[name]["genome"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--pml"], stdout=subprocess.DEVNULL)
+    os.remove(os.path.join(d, "raw.fa"))
+    open(os.path.join(d, "ok"), "w").write("ok")
+    log(f"built index {name} in {time.time() - t0:.1f} s")
+    return ref
+
+
+def ensure_reads(name: str, ref: str, seed: int):
+    w = WORKLOADS[name]
+    path = os.path.join(cache_dir(name), f"reads_{w['n_reads']}_{w['read_len']}_s{seed}.bin")
+    if not (os.path.exists(path) and os.path.exists(path + ".off")):
+        tmp = path + f".tmp{os.getpid()}"
+        subprocess.check_call([MKINDEX, "reads", "--ref", ref, "--n", str(w["n_reads"]), "--len", str(w["read_len"]), "--seed", str(seed),
+                               "--bin", tmp] + w["reads"], stdout=subprocess.DEVNULL)
+        os.replace(tmp + ".off", path + ".off")
+        os.replace(tmp, path)
+    return np.fromfile(path, dtype=np.uint8), np.fromfile(path + ".off", dtype=np.uint64)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_reference(args, name):
+    """Reference arm: the CPU path (oracle port of compute_ms_pml.cpp:237-286) on all host threads.
+    Each step is a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    ref = ensure_index(name)
+    buf, off = ensure_reads(name, ref, seed=4)
+    cores = os.cpu_count() or 1
+    w = WORKLOADS[name]
+    sample_reads = min(len(off) - 1, max(200, 1000 * cores * 1000 // w["read_len"]))
+    idx = oracle.OracleIndex(ref, "pml")
+    sb, so = buf[: int(off[sample_reads])], off[: sample_reads + 1]
+    for _ in range(args.warmup):
+        idx.query_batch(sb[: int(so[max(1, sample_reads // 10)])], so[: max(1, sample_reads // 10) + 1], threads=cores, want_output=False)
+    secs = []
+    for _ in range(args.steps):
+        s, _, _ = idx.query_batch(sb, so, threads=cores, want_output=False)
+        secs.append(s)
+    total = sum(secs)
+    value = int(so[-1]) * args.steps / total
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+           "config": {"workload": w["desc"], "sample": f"first {sample_reads} reads ({int(so[-1])} bases) per step"},
+           "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
+                            "sample": f"first {sample_reads} reads of the workload, {args.steps} steps, in-memory, OpenMP dynamic over reads"},
+           "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per read (tuning; 0 = library default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    name = os.environ.get("SPB_BENCH_WORKLOAD", "c2")
+    w = WORKLOADS[name]
+    if not os.path.exists(MKINDEX):
+        import __graft_entry__
+        __graft_entry__.build()
+    if args.impl == "reference":
+        return run_reference(args, name)
+
+    import torch
+    import torch.distributed as dist
+
+    import spumoni_b200 as sp
+    from spumoni_b200.distributed import broadcast_index
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; spumoni_b200 has no CPU path to measure")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- untimed setup: index (rank 0 builds + parses, NCCL broadcast), reads per rank
+    if rank == 0:
+        ref = ensure_index(name)
+    barrier()
+    ref = os.path.join(cache_dir(name), "idx.fa")
+    t0 = time.time()
+    if world > 1:
+        idx = broadcast_index(sp.Index.open(ref, sp.MODE_PML) if rank == 0 else None, device=local, src=0)
+    else:
+        idx = sp.Index.open(ref, sp.MODE_PML).to_device(local)
+    n, r = idx.get_bwt_stats()
+    log(f"rank {rank}: index resident (n={n}, r={r}) in {time.time() - t0:.1f} s")
+    buf, off = ensure_reads(name, ref, seed=4 + rank)
+    n_reads, n_bases = len(off) - 1, int(off[-1])
+
+    h_reads = torch.from_numpy(buf).pin_memory()
+    h_off = torch.from_numpy(off.astype(np.int64)).pin_memory()
+    h_len = torch.empty(n_bases, dtype=torch.int32).pin_memory()
+    d_reads = torch.zeros(n_bases + 512, dtype=torch.uint8, device=dev)
+    d_reads[:n_bases].copy_(h_reads)
+    d_off = h_off.to(dev)
+    d_len = torch.zeros(n_bases, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device():
+        idx.query_device(d_reads, d_off, n_reads, d_len, lanes=args.lanes, stream=stream.cuda_stream)
+
+    np_reads, np_off = h_reads.numpy(), h_off.numpy().view(np.uint64)
+    np_len = h_len.numpy().view(np.uint32)
+
+    def step_host():
+        idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len)
+
+    # ---------------- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sp.kernel_launches()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step_device()
+        evs[i + 1].record(stream)
+    barrier()
+    launches = sp.kernel_launches() - launches0
+    kern_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    total_ms = evs[0].elapsed_time(evs[-1])
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = n_bases * world * args.steps / (total_ms_max / 1e3)
+
+    # ---------------- end-to-end through the host-buffer C ABI (H2D + kernel + D2H inside the timed region)
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = n_bases * world * args.steps / float(t.item())
+    same = bool(np.array_equal(np_len, d_len.cpu().numpy().view(np.uint32)))
+
+    # ---------------- parity spot check + CPU baseline (rank 0, N=1)
+    cpu_baseline, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        cores = os.cpu_count() or 1
+        sample_reads = min(n_reads, max(200, 2500 * cores * 1000 // w["read_len"]))
+        o = oracle.OracleIndex(ref, "pml")
+        sec, Lo, _ = o.query_batch(buf[: int(off[sample_reads])], off[: sample_reads + 1], threads=cores)
+        sb = int(off[sample_reads])
+        mism = int(np.count_nonzero(Lo != np_len[:sb].astype(np.uint64)))
+        parity = {"reads_checked": sample_reads, "bases_checked": sb, "mismatches": mism, "host_equals_device_path": same}
+        cpu_baseline = {"value": sb / sec, "unit": "bases/s", "cores": cores, "kind": "port",
+                        "sample": f"first {sample_reads} reads ({sb} bases) of the same workload, in-memory, OpenMP over reads"}
+        if mism or not same:
+            raise SystemExit(f"bench.py: PARITY FAILURE vs oracle: {parity}")
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        kavg_ms = sum(kern_ms) / len(kern_ms)
+        achieved = BYTES_PER_BASE_PML * n_bases / (kavg_ms / 1e3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64", "data": "synthetic",
+            "config": {"workload": w["desc"], "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
+                       "lanes_per_read": args.lanes or 8, "l2": "inputs (1 GB reads + 4 GB lengths per step) larger than L2; no explicit flush",
+                       "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1), "d2h_bytes_per_step": 4 * n_bases},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "spb_walk_kernel<G,false>", "kernel_ms": kavg_ms,
+                         "bytes_per_base": BYTES_PER_BASE_PML, "peak_source": peak_src},
+            "cpu_baseline": cpu_baseline, "parity": parity,
+        }
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                out["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

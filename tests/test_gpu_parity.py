@@ -192,7 +192,7 @@ def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
 
 def test_cli_empty_read_aborts_like_reference(small_index, tmp_path):
     q = str(tmp_path / "q.fa")
-    open(q, "w").write(">a\nACGT\n>b\n>c\nACGT\n")
+    open(q, "w").write(">r_a\nACGT\n>r_b\n>r_c\nACGT\n")
     r = subprocess.run([sp.CLI_PATH, "run", "-r", small_index["ref"][:-3], "-p", q, "-P", "-n"], capture_output=True, text=True)
     assert r.returncode == 1 and "was empty after digestion" in r.stderr
 
