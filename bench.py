@@ -304,13 +304,13 @@ def main():
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
-                       "lanes_per_read": args.lanes or 8, "l2": "inputs (1 GB reads + 4 GB lengths per step) larger than L2; no explicit flush",
+                       "lanes_per_read": args.lanes or 1, "l2": "inputs (1 GB reads + 4 GB lengths per step) larger than L2; no explicit flush",
                        "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1), "d2h_bytes_per_step": 4 * n_bases},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spb_walk_kernel<G,false>", "kernel_ms": kavg_ms,
+                         "traffic": None, "kernel": "spb_pml_fast_kernel<false>" if (args.lanes or 1) == 1 else "spb_walk_kernel<G,false>", "kernel_ms": kavg_ms,
                          "bytes_per_base": BYTES_PER_BASE_PML, "peak_source": peak_src},
             "cpu_baseline": cpu_baseline, "parity": parity,
         }

@@ -60,7 +60,7 @@ typedef struct {
 
 typedef struct {
     uint32_t bin_width;      /* -w; 0 disables classification (stats may then be NULL) */
-    uint32_t lanes_per_read; /* 0 = library default; else one of 4, 8, 16, 32 (tuning knob) */
+    uint32_t lanes_per_read; /* 0 = library default (1 for PML, 4 for MS); 1 = thread-per-read fast path (PML), 4/8/16/32 = cooperative */
     uint64_t max_value_thr;  /* see spb_max_value_threshold */
     uint32_t flags;          /* SPB_QUERY_TOUPPER: apply ::toupper to read bytes on the device (compute_ms_pml.cpp:916-917) */
     uint32_t reserved[3];

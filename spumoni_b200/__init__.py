@@ -20,7 +20,8 @@ __all__ = ["pml_t", "ms_t", "Index", "EmpNullDatabase", "SpumoniError", "load_li
            "max_value_threshold", "kernel_launches", "device_count", "BinStats", "QueryOpts", "LIB_PATH", "CLI_PATH"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libspumoni_b200.so")
+LIB_PATH = os.environ.get("SPUMONI_B200_LIB") or os.path.join(_HERE, "lib", "libspumoni_b200.so")
+SATTEST_LIB_PATH = os.path.join(_HERE, "lib", "libspumoni_b200_sattest.so")  # test-only build, see csrc/Makefile
 CLI_PATH = os.path.join(_HERE, "bin", "spumoni")
 MODE_PML, MODE_MS = 0, 1
 QUERY_TOUPPER = 1

@@ -35,7 +35,7 @@ int fail(int code, const std::string& msg) {
 constexpr int kSlots = 3;                         // pipeline depth of the host entry points
 constexpr uint64_t kChunkBases = 32ull << 20;     // bases per pipelined sub-batch
 constexpr int kCounters = 64;
-constexpr int kDefaultLanes = 8;
+constexpr int kDefaultLanes = 4;  // cooperative kernel (MS, or PML without fast symbols)
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -113,9 +113,11 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     if ((ms ? 1 : 0) != idx->mode) return fail(SPB_ERR_ARG, ms ? "MS query on a PML index" : "PML query on an MS index");
     if (!d_reads || !d_offsets || !d_lengths || (ms && !d_pointers)) return fail(SPB_ERR_ARG, "null device buffer");
     if (((uintptr_t)d_reads & 255u) != 0) return fail(SPB_ERR_ARG, "d_reads must be 256-byte aligned");
-    int lanes = opts && opts->lanes_per_read ? (int)opts->lanes_per_read : kDefaultLanes;
-    if (lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SPB_ERR_ARG, "lanes_per_read must be 4, 8, 16 or 32");
     const SpbFlatHeader& h = idx->hdr;
+    const bool has_fast = !ms && h.num_fast > 0 && h.off_fast != 0;
+    int lanes = opts && opts->lanes_per_read ? (int)opts->lanes_per_read : (has_fast ? 1 : kDefaultLanes);
+    if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SPB_ERR_ARG, "lanes_per_read must be 1, 4, 8, 16 or 32");
+    if (lanes == 1 && !has_fast) return fail(SPB_ERR_ARG, "lanes_per_read = 1 needs a PML index with fast symbols");
     spb::WalkParams p;
     std::memset(&p, 0, sizeof(p));
     p.runs = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_runs);
@@ -132,6 +134,10 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.bin_width = (opts && d_stats) ? opts->bin_width : 0;
     p.stats = p.bin_width ? d_stats : nullptr;
     p.max_value_thr = opts ? opts->max_value_thr : 0;
+    p.rows = has_fast ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_fast) : nullptr;
+    p.rl = has_fast ? reinterpret_cast<const uint32_t*>(idx->dev_blob + h.off_rl) : nullptr;
+    p.init_off = h.init_off;
+    p.init_h = h.init_h;
     p.work_counter = idx->d_counters + (idx->counter_next++ % kCounters);
     SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), stream));
     SPB_CUDA(spb::launch_walk(p, ms, lanes, idx->num_sms, stream));

@@ -425,6 +425,31 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         h.off_text = off;
         off = align_up(off + text.size() + 64, 256);
     }
+    // fast symbols: up to four most frequent run heads with 1 < byte < 0x80 (bytes >= 0x80 never
+    // "match" in the reference, App. C-1; the terminator never occurs in a read that matters)
+    uint32_t fid[256];
+    for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
+    uint32_t num_fast = 0;
+    if (!ms) {
+        std::vector<int> cand;
+        for (int c = 2; c < 0x80; c++) if (numRunsC[c]) cand.push_back(c);
+        std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return numRunsC[a] > numRunsC[b]; });
+        if (cand.size() > 4) cand.resize(4);
+        std::sort(cand.begin(), cand.end());
+        for (int c : cand) { h.fast_sym[num_fast] = (uint32_t)c; fid[c] = num_fast++; }
+        for (uint64_t k = 0; k < R; k++)
+            if (d.lens[(size_t)k] >= 0xFFFFFFFFull) num_fast = 0;  // 32-bit in-run offsets would overflow: generic path only
+        if (!num_fast) for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
+    }
+    h.num_fast = num_fast;
+    if (num_fast) {
+        h.off_fast = off;
+        off = align_up(off + (size_t)R * 64, 256);
+        h.off_rl = off;
+        off = align_up(off + ((size_t)R + 16) * 4, 256);
+        h.init_off = (uint32_t)(d.lens[(size_t)R - 1] - 1);
+        h.init_h = fid[d.heads[(size_t)R - 1]];
+    }
     h.total_bytes = off;
     for (int c = 0; c < 256; c++) {
         h.F[c] = d.F[c];
@@ -432,7 +457,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         if (numRunsC[c]) {
             t.crec_base = crec_base[c];
             t.num_runs = numRunsC[c];
-            t.dest_f = 0;
+            t.dest_f = fid[c];
             t.cidx = cidx[c];
         } else {
             t.crec_base = (uint32_t)(d.F[c] & 0xFFFFFFFFu);
@@ -518,6 +543,75 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         }
     }
     if (ms) std::memcpy(blob.data() + h.off_text, text.data(), text.size());
+    if (num_fast) {
+        SpbFastRec* rows = reinterpret_cast<SpbFastRec*>(blob.data() + h.off_fast);
+        uint32_t* rl = reinterpret_cast<uint32_t*>(blob.data() + h.off_rl);
+        auto sat26 = [](uint64_t v) { return (uint32_t)(v >= SPB_FAST_SAT ? SPB_FAST_SAT : v); };
+        auto hid = [&](uint64_t k) -> uint32_t { return k < R ? fid[d.heads[(size_t)k]] : SPB_SYM_SLOW; };
+        // runs of every fast symbol in BWT order (the j-th c-run), and #c-runs before each run
+        std::vector<std::vector<uint32_t>> cruns(num_fast);
+        for (uint64_t k = 0; k < R; k++) {
+            const uint32_t f = fid[d.heads[(size_t)k]];
+            if (f < SPB_SYM_SLOW) cruns[f].push_back((uint32_t)k);
+        }
+        std::vector<uint32_t> before((size_t)R * num_fast);
+        {
+            uint32_t cnt[4] = {0, 0, 0, 0};
+            for (uint64_t k = 0; k < R; k++) {
+                for (uint32_t s = 0; s < num_fast; s++) before[(size_t)k * num_fast + s] = cnt[s];
+                const uint32_t f = fid[d.heads[(size_t)k]];
+                if (f < SPB_SYM_SLOW) cnt[f]++;
+            }
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t kk = 0; kk < (int64_t)R; kk++) {
+            const uint64_t k = (uint64_t)kk;
+            const uint32_t hk = fid[d.heads[(size_t)k]];
+            const uint64_t len_k = d.lens[(size_t)k];
+            rl[k] = (uint32_t)(len_k >= SPB_RL_SAT ? SPB_RL_SAT : len_k) | (hk << 29);
+            if (hk >= SPB_SYM_SLOW) continue;  // row unused: steps from this run take the generic path
+            SpbFastRec* row = rows + (size_t)k * 4;
+            {   // match record
+                const uint64_t de = dest[(size_t)k];
+                SpbFastRec a;
+                a.x = (uint32_t)(start[(size_t)de + 1] - lf[(size_t)k]);
+                a.y = (uint32_t)de;
+                a.z = (uint32_t)(lf[(size_t)k] - start[(size_t)de]);
+                const uint64_t len1 = de + 1 < R ? d.lens[(size_t)de + 1] : 0;
+                a.w = sat26(len1) | (hid(de) << 26) | (hid(de + 1) << 29);
+                row[0] = a;
+            }
+            for (uint32_t s = 0; s < num_fast; s++) {
+                if (s == hk) continue;
+                const int c = (int)h.fast_sym[s];
+                const uint32_t j = before[(size_t)k * num_fast + s];
+                uint64_t thr, lfj;
+                if (j < numRunsC[c]) {
+                    const uint32_t k2 = cruns[s][j];
+                    thr = d.thr[k2];
+                    lfj = lf[k2];
+                } else {
+                    thr = n + 1;
+                    lfj = d.F[c] + numC[c];
+                }
+                SpbFastRec jr;
+                const uint64_t st = start[(size_t)k];
+                jr.x = thr <= st ? 0u : (uint32_t)std::min<uint64_t>(thr - st, len_k);
+                const uint64_t kA = run_of(lfj);  // R if lfj == n
+                const uint64_t offA = kA < R ? lfj - start[(size_t)kA] : 0;
+                uint64_t kB = kA, offB = 0;
+                if (lfj > 0) {
+                    if (offA > 0) { kB = kA; offB = offA - 1; }
+                    else { kB = kA - 1; offB = d.lens[(size_t)kB] - 1; }
+                }
+                jr.y = (uint32_t)kA;
+                jr.z = sat26(offA) | (hid(kA) << 26) | ((kB != kA ? 1u : 0u) << 29);
+                jr.w = sat26(offB) | (hid(kB) << 26);
+                row[1 + s - (s > hk ? 1 : 0)] = jr;
+            }
+        }
+        for (uint64_t k = R; k < R + 16; k++) rl[k] = SPB_RL_SAT | (SPB_SYM_SLOW << 29);
+    }
     return blob;
 }
 

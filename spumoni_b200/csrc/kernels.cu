@@ -20,6 +20,10 @@
 #include "flat_index.h"
 #include "kernels.h"
 
+#ifndef SPB_FAST_MINB
+#define SPB_FAST_MINB 10  /* 128-thread CTAs per SM the fast kernel is compiled for (register cap 48) */
+#endif
+
 namespace spb {
 
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
@@ -308,6 +312,259 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
     }
 }
 
+
+// ==========================================================================================
+// PML fast path: one thread per read, one 16-byte gather per backward-search step.
+//
+// Every lane is a small state machine that issues exactly one vector load per loop iteration
+// (a transition record in STEP mode, four run lengths in SCAN mode), so the 32 independent
+// pointer chases of a warp stay in lock step at the load and their latencies overlap instead of
+// serialising behind divergent branches.  Lanes drift apart in read position, pull their next
+// read from the work counter on their own, and only the rare symbols (absent characters, runs
+// headed by a non-fast symbol, saturated fields) leave the lock step for the generic code.
+// ==========================================================================================
+#define SPB_FAST_THREADS 128
+
+struct ThreadLoc { uint32_t k; uint4 rec; };
+
+// thread-level predecessor search over the generic run records (slow path only)
+__device__ __noinline__ ThreadLoc locate_thread(const uint4* __restrict__ runs, uint64_t R, uint64_t target, uint64_t w0) {
+    uint64_t lo = w0;
+    uint4 cur = ldg_nc16(runs + lo);
+    // gallop, then bisect: start[lo] <= target < start[hi]
+    uint64_t step = 1, hi = lo + 1;
+    for (;;) {
+        if (hi > R + 1) { hi = R + 1; break; }
+        uint4 t = ldg_nc16(runs + hi);
+        if (rec_start(t) > target) break;
+        lo = hi; cur = t;
+        hi = lo + step;
+        step <<= 1;
+    }
+    while (hi - lo > 1) {
+        uint64_t mid = (lo + hi) >> 1;
+        uint4 t = ldg_nc16(runs + mid);
+        if (rec_start(t) <= target) { lo = mid; cur = t; } else hi = mid;
+    }
+    ThreadLoc out;
+    out.k = (uint32_t)lo;
+    out.rec = cur;
+    return out;
+}
+
+// One reference step in absolute coordinates (same statements as spb_walk_kernel's body) for a
+// single thread.  In: state (k, off), byte c.  Out: new (k, off), returns the new PML length.
+struct SlowOut { uint32_t k, off, length; };
+__device__ __noinline__ SlowOut slow_step(const uint4* __restrict__ runs, const uint8_t* __restrict__ blocks,
+                                          const uint4* __restrict__ crec, uint32_t blk_stride, uint64_t R, uint64_t n,
+                                          const uint4 ct, uint32_t c, uint32_t k, uint32_t off, uint32_t length) {
+    const uint4 krec = ldg_nc16(runs + k);
+    const uint64_t pos = (k < R) ? rec_start(krec) + off : n;
+    uint64_t npos, w0;
+    if (ct.w == 0xFFFFFFFFu) {
+        length = 0;
+        npos = (uint64_t)ct.x | ((uint64_t)ct.y << 32);
+        w0 = ct.z;
+    } else if (k < R && rec_head(krec) == c && c < 0x80u) {
+        length++;
+        npos = rec_lf(krec) + off;
+        w0 = krec.z;
+    } else {
+        const uint32_t j = (k < R) ? crun_ordinal(blocks, blk_stride, k, c, ct.w) : ct.y;
+        const uint4 cr = ldg_nc16(crec + (size_t)ct.x + j);
+        const bool down = pos < crec_thr(cr);
+        const bool same = (k < R) && rec_head(krec) == c;
+        length = 0;
+        const uint64_t lf = crec_lf(cr);
+        npos = down ? lf - 1 : (same ? lf + off : lf);
+        w0 = (down && cr.z > 0) ? cr.z - 1 : cr.z;
+    }
+    SlowOut o;
+    o.length = length;
+    if (npos >= n) {
+        o.k = (uint32_t)R;
+        o.off = 0;
+    } else {
+        ThreadLoc L = locate_thread(runs, R, npos, w0);
+        o.k = L.k;
+        o.off = (uint32_t)(npos - rec_start(L.rec));
+    }
+    return o;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(SPB_FAST_THREADS, SPB_FAST_MINB) spb_pml_fast_kernel(const WalkParams p) {
+    __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
+    for (int i = threadIdx.x; i < 256; i += SPB_FAST_THREADS) {
+        const SpbCharTab t = p.chartab[i];
+        s_fid[i] = (uint8_t)(t.cidx == 0xFFFFFFFFu ? 5u : t.dest_f);
+    }
+    __syncthreads();
+
+    const uint4* __restrict__ rows = p.rows;
+    const uint32_t R32 = (uint32_t)p.R;
+    const bool upper = (p.flags & SPB_FLAG_TOUPPER) != 0;
+    const bool do_stats = STATS && p.bin_width != 0 && p.stats != nullptr;
+
+    // lane state
+    bool have = false;
+    unsigned long long r = 0;
+    uint64_t base = 0, end = 0, gi = 0, chunk = 0;
+    uint32_t k = 0, off = 0, h = 0, length = 0;
+    uint32_t mode = 0, sk = 0, rem = 0;  // mode 0 = STEP, 1 = SCAN
+    uint32_t ob0 = 0, ob1 = 0, ob2 = 0, ob3 = 0;
+    // classifier
+    uint64_t bin_lb = 0, sum_max = 0;
+    uint32_t bin_max = 0, above = 0, below = 0;
+
+    for (;;) {
+        if (!have) {  // ---- pull the next read (rare, divergent)
+            r = atomicAdd(p.work_counter, 1ULL);
+            if (r >= p.n_reads) break;
+            base = p.offsets[r];
+            const uint64_t m = p.offsets[r + 1] - base;
+            if (m == 0) {
+                if (do_stats) { spb_bin_stats z; z.sum_max = 0; z.above = 0; z.below = 0; p.stats[r] = z; }
+                continue;
+            }
+            end = base + m;
+            gi = end - 1;
+            k = R32 - 1; off = p.init_off; h = p.init_h; length = 0; mode = 0;
+            chunk = *reinterpret_cast<const uint64_t*>(p.reads + (gi & ~7ull));
+            have = true;
+            if (STATS && do_stats) {
+                const uint64_t bw = p.bin_width;
+                const uint64_t nbins = m / bw > 0 ? m / bw : 1;
+                bin_lb = base + (nbins - 1) * bw;  // in global index coordinates
+                bin_max = 0; above = 0; below = 0; sum_max = 0;
+            }
+        }
+
+        // ---- address generation: one gather per lane per iteration
+        const uint4* addr = rows;
+        uint32_t c = 0, s = 0;
+        bool is_match = false, slow = false;
+        if (mode == 0) {
+            c = (uint32_t)(chunk >> ((gi & 7) * 8)) & 0xFFu;
+            if (upper && c >= 'a' && c <= 'z') c -= 32;
+            s = s_fid[c];
+            if (s < SPB_SYM_SLOW && h < SPB_SYM_SLOW) {
+                is_match = (s == h);
+                addr = rows + (size_t)k * 4 + (is_match ? 0u : 1u + s - (s > h ? 1u : 0u));
+            } else
+                slow = true;
+        } else
+            addr = reinterpret_cast<const uint4*>(p.rl + (sk & ~3u));
+
+        bool emit = false;
+        if (!slow) {
+            const uint4 rec = ldg_nc16(addr);
+            if (mode == 0) {
+                emit = true;
+                const bool lt = off < rec.x;
+                if (is_match) {
+                    length++;
+                    if (lt) {
+                        k = rec.y; off += rec.z; h = (rec.w >> 26) & 7u;
+                    } else {
+                        const uint32_t r2 = off - rec.x, len1 = rec.w & 0x3FFFFFFu;
+                        if (r2 < len1) { k = rec.y + 1; off = r2; h = rec.w >> 29; }
+                        else if (len1 == SPB_FAST_SAT) { length--; slow = true; emit = false; }  // length of run dest+1 unknown
+                        else { mode = 1; sk = rec.y + 2; rem = r2 - len1; }
+                    }
+                } else {
+                    uint32_t nk, noff, nh;
+                    if (!lt) { nk = rec.y; noff = rec.z & 0x3FFFFFFu; nh = (rec.z >> 26) & 7u; }
+                    else { nk = rec.y - ((rec.z >> 29) & 1u); noff = rec.w & 0x3FFFFFFu; nh = (rec.w >> 26) & 7u; }
+                    if (noff == SPB_FAST_SAT) { slow = true; emit = false; }  // offset did not fit: redo in absolute coordinates
+                    else { length = 0; k = nk; off = noff; h = nh; }
+                }
+            } else {
+                // SCAN: rec = lengths of runs (sk & ~3) .. +3; walk forward until rem falls inside a run
+                const uint32_t w4[4] = {rec.x, rec.y, rec.z, rec.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (mode == 1 && (uint32_t)i >= (sk & 3u)) {
+                        const uint32_t len = w4[i] & 0x1FFFFFFFu;
+                        if (len == SPB_RL_SAT) {  // unknown length: finish with an absolute search
+                            const uint4 sr = ldg_nc16(p.runs + sk);
+                            ThreadLoc L = locate_thread(p.runs, p.R, rec_start(sr) + rem, sk);
+                            k = L.k; off = (uint32_t)(rec_start(sr) + rem - rec_start(L.rec));
+                            h = s_fid[rec_head(L.rec)]; if (h > SPB_SYM_SLOW) h = SPB_SYM_SLOW;
+                            mode = 0;
+                        } else if (rem < len) { k = sk; off = rem; h = w4[i] >> 29; mode = 0; }
+                        else { rem -= len; sk++; }
+                    }
+                }
+            }
+        }
+        if (slow) {  // ---- generic step in absolute coordinates (absent / rare symbols, non-fast run heads, saturation)
+            const uint4 ct = reinterpret_cast<const uint4*>(p.chartab)[c];
+            const SlowOut so = slow_step(p.runs, p.blocks, p.crec, p.blk_stride, p.R, p.n, ct, c, k, off, length);
+            k = so.k; off = so.off; length = so.length;
+            if (k < R32) {
+                const uint4 kr = ldg_nc16(p.runs + k);
+                h = s_fid[rec_head(kr)];
+                if (h > SPB_SYM_SLOW) h = SPB_SYM_SLOW;
+            } else h = SPB_SYM_SLOW;
+            emit = true;
+        }
+
+        if (emit) {
+            // buffer four lengths and store them as one 16-byte word when the group is complete
+            const uint32_t slot = (uint32_t)gi & 3u;
+            if (slot == 0) ob0 = length; else if (slot == 1) ob1 = length; else if (slot == 2) ob2 = length; else ob3 = length;
+            const bool last = (gi == base);
+            if (slot == 0 || last) {
+                const uint64_t g = gi & ~3ull;  // entries g+slot .. g+3 below `end` were produced by this read
+                uint32_t* dst = p.lengths + g;
+                if (slot == 0 && g + 3 < end) {
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(ob0, ob1, ob2, ob3);
+                } else {
+                    if (slot == 0) dst[0] = ob0;
+                    if (slot <= 1 && g + 1 < end) dst[1] = ob1;
+                    if (slot <= 2 && g + 2 < end) dst[2] = ob2;
+                    if (g + 3 < end) dst[3] = ob3;
+                }
+            }
+            if (STATS && do_stats) {
+                if (gi < bin_lb) {
+                    if (bin_max >= p.max_value_thr) above++; else below++;
+                    sum_max += bin_max;
+                    bin_max = 0;
+                    bin_lb -= p.bin_width;
+                }
+                bin_max = length > bin_max ? length : bin_max;
+            }
+            if (last) {
+                if (STATS && do_stats) {
+                    if (bin_max >= p.max_value_thr) above++; else below++;
+                    sum_max += bin_max;
+                    spb_bin_stats st; st.sum_max = sum_max; st.above = above; st.below = below;
+                    p.stats[r] = st;
+                }
+                have = false;
+            } else {
+                --gi;
+                if ((gi & 7ull) == 7ull) chunk = *reinterpret_cast<const uint64_t*>(p.reads + (gi & ~7ull));
+            }
+        }
+    }
+}
+
+template <bool STATS>
+static cudaError_t launch_fast(const WalkParams& p, int num_sms, cudaStream_t stream) {
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spb_pml_fast_kernel<STATS>, SPB_FAST_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) occ = 1;
+    unsigned long long need = (p.n_reads + SPB_FAST_THREADS - 1) / SPB_FAST_THREADS;
+    unsigned long long grid = (unsigned long long)num_sms * occ;
+    if (need < grid) grid = need ? need : 1;
+    spb_pml_fast_kernel<STATS><<<(unsigned)grid, SPB_FAST_THREADS, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 template <int G, bool MS>
 static cudaError_t launch_t(const WalkParams& p, int num_sms, cudaStream_t stream) {
     int occ = 0;
@@ -323,6 +580,10 @@ static cudaError_t launch_t(const WalkParams& p, int num_sms, cudaStream_t strea
 }
 
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream) {
+    if (lanes == 1) {
+        if (ms || !p.rows) return cudaErrorInvalidValue;
+        return (p.bin_width && p.stats) ? launch_fast<true>(p, num_sms, stream) : launch_fast<false>(p, num_sms, stream);
+    }
     switch (lanes) {
         case 4: return ms ? launch_t<4, true>(p, num_sms, stream) : launch_t<4, false>(p, num_sms, stream);
         case 8: return ms ? launch_t<8, true>(p, num_sms, stream) : launch_t<8, false>(p, num_sms, stream);

@@ -31,8 +31,13 @@ struct WalkParams {
     uint32_t bin_width;
     uint64_t max_value_thr;
     unsigned long long* work_counter;  // zeroed before launch
+    // PML fast path (thread per read); rows == nullptr when the index has no fast symbols
+    const uint4* rows;
+    const uint32_t* rl;
+    uint32_t init_off, init_h;
 };
 
+// lanes: 4/8/16/32 = cooperative walk kernel (PML or MS); 1 = PML fast path (thread per read)
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream);
 
 }  // namespace spb

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQ"  # up to terminator_position
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQIII4II"  # up to pad0 (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -20,7 +20,9 @@ class FlatImage:
         self.b = b
         (self.magic, self.version, self.mode, self.n, self.R, self.n_text, self.last_run_sample, self.sigma,
          self.sigma_pad, self.blk_stride, self.num_blocks, self.num_crec, self.off_runs, self.off_blocks,
-         self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position) = struct.unpack_from(HDR_FMT, b, 0)
+         self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position, self.off_fast,
+         self.off_rl, self.num_fast, self.init_off, self.init_h, fs0, fs1, fs2, fs3, _pad) = struct.unpack_from(HDR_FMT, b, 0)
+        self.fast_sym = [fs0, fs1, fs2, fs3]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -29,6 +31,9 @@ class FlatImage:
         nrec = self.R + 64
         self.runs = np.frombuffer(b, dtype=np.uint32, count=4 * nrec, offset=self.off_runs).reshape(nrec, 4)
         self.crec = np.frombuffer(b, dtype=np.uint32, count=4 * (self.num_crec + 1), offset=self.off_crec).reshape(-1, 4)
+        if self.num_fast:
+            self.rows = np.frombuffer(b, dtype=np.uint32, count=16 * self.R, offset=self.off_fast).reshape(self.R, 4, 4)
+            self.rl = np.frombuffer(b, dtype=np.uint32, count=self.R + 16, offset=self.off_rl)
         if self.mode == 1:
             self.csamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.num_crec + 1), offset=self.off_csamp).reshape(-1, 2)
             self.text = b[self.off_text:self.off_text + self.n_text]
@@ -109,3 +114,94 @@ class FlatImage:
             out[i] = l
             l = l - 1 if l else 0
         return out
+
+
+    # ---- PML fast path (spb_pml_fast_kernel), including its fall-backs; sat26/sat29 let a test lower the
+    # saturation limits the way the SPB_FAST_SAT / SPB_RL_SAT test build does
+    def slow_step(self, k, off, c, length):
+        n, R = self.n, self.R
+        kr = self.run(k)
+        pos = kr["start"] + off if k < R else n
+        ct = self.chartab[c]
+        if ct[3] == 0xFFFFFFFF:
+            length = 0
+            npos, w0 = ct[0] | (ct[1] << 32), ct[2]
+        elif k < R and kr["head"] == c and c < 0x80:
+            length += 1
+            npos, w0 = kr["lf"] + off, kr["dest"]
+        else:
+            j = self.crun_ordinal(k, c, ct[3]) if k < R else ct[1]
+            x, y, z, w = (int(v) for v in self.crec[ct[0] + j])
+            thr, lf = x | ((w & 0xFF) << 32), y | (((w >> 8) & 0xFF) << 32)
+            down = pos < thr
+            same = k < R and kr["head"] == c
+            length = 0
+            npos = lf - 1 if down else (lf + off if same else lf)
+            w0 = z - 1 if (down and z > 0) else z
+        if npos >= n:
+            return R, 0, length
+        k2 = self.locate(npos, w0)
+        return k2, npos - self.run(k2)["start"], length
+
+    def fid(self, c):
+        ct = self.chartab[c]
+        return 5 if ct[3] == 0xFFFFFFFF else ct[2]
+
+    def walk_fast(self, read: bytes, sat26=0x3FFFFFF, sat29=0x1FFFFFFF):
+        assert self.num_fast and self.mode == 0
+        m, R = len(read), self.R
+        k, off, h, length = R - 1, self.init_off, self.init_h, 0
+        out = [0] * m
+        stats = {"fast": 0, "scan_iters": 0, "slow": 0}
+        for gi in range(m - 1, -1, -1):
+            c = read[gi]
+            s = self.fid(c)
+            slow = not (s < 4 and h < 4)
+            if not slow:
+                match = s == h
+                x, y, z, w = (int(v) for v in self.rows[k][0 if match else 1 + s - (1 if s > h else 0)])
+                lt = off < x
+                if match:
+                    if lt:
+                        k, off, h, length = y, off + z, (w >> 26) & 7, length + 1
+                    else:
+                        r2, len1 = off - x, w & 0x3FFFFFF
+                        if r2 < len1:
+                            k, off, h, length = y + 1, r2, w >> 29, length + 1
+                        elif len1 == sat26:
+                            slow = True
+                        else:
+                            length += 1
+                            sk, rem = y + 2, r2 - len1
+                            while True:
+                                stats["scan_iters"] += 1
+                                wv = int(self.rl[sk])
+                                ln = wv & 0x1FFFFFFF
+                                if ln == sat29:
+                                    st = self.run(sk)["start"] + rem
+                                    k = self.locate(st, sk)
+                                    off = st - self.run(k)["start"]
+                                    h = min(self.fid(self.run(k)["head"]), 4)
+                                    break
+                                if rem < ln:
+                                    k, off, h = sk, rem, wv >> 29
+                                    break
+                                rem -= ln
+                                sk += 1
+                else:
+                    if not lt:
+                        nk, noff, nh = y, z & 0x3FFFFFF, (z >> 26) & 7
+                    else:
+                        nk, noff, nh = y - ((z >> 29) & 1), w & 0x3FFFFFF, (w >> 26) & 7
+                    if noff == sat26:
+                        slow = True
+                    else:
+                        k, off, h, length = nk, noff, nh, 0
+                if not slow:
+                    stats["fast"] += 1
+            if slow:
+                stats["slow"] += 1
+                k, off, length = self.slow_step(k, off, c, length)
+                h = min(self.fid(self.run(k)["head"]), 4) if k < R else 4
+            out[gi] = length
+        return out, stats

@@ -26,6 +26,8 @@ def test_flat_image_matches_golden_vectors(tmp_path):
         for rd in case["reads"]:
             read = rd["read"].encode("latin1")
             assert fp.walk(read)[0] == rd["pml"]
+            if fp.num_fast:
+                assert fp.walk_fast(read)[0] == rd["pml"]
             _, ptr = fm.walk(read)
             assert [str(x) for x in ptr] == rd["ms_pointers"]
             assert fm.ms_lengths(read, ptr) == rd["ms_lengths"]
@@ -48,7 +50,9 @@ def test_flat_image_vs_oracle_random(tmp_path):
         for _ in range(8):
             ln = rng.randint(1, 150)
             read = bytes(rng.choice(b"ACGTNY\xe9") for _ in range(ln)) if rng.random() < 0.4 else (tb[rng.randint(0, max(0, len(tb) - ln)):][:ln] or b"A")
-            assert fp.walk(read)[0] == po.matching_statistics(read).tolist()
+            want = po.matching_statistics(read).tolist()
+            assert fp.walk(read)[0] == want
+            assert fp.walk_fast(read)[0] == want
             L, P = mo.matching_statistics(read)
             _, ptr = fm.walk(read)
             assert ptr == P.tolist() and fm.ms_lengths(read, ptr) == L.tolist()
@@ -110,3 +114,36 @@ def test_nulldb_roundtrip(tmp_path):
     assert sp.max_value_threshold(1.0, False) == 3
     raw = open(out, "rb").read()  # width = max(ceil(log2(16)),1) = 4 bits (reference quirk: 16 itself does not fit)
     assert raw[32 + 8] == 4
+
+
+def test_fast_path_saturation_fallbacks_host_side(tmp_path):
+    """The sattest build stores every offset/length >= 7 (resp. 15) as 'saturated'; walking its flat image
+    with the same limits must still reproduce the oracle (exercises the slow/absolute fall-backs)."""
+    import subprocess, sys, textwrap
+    rng = random.Random(23)
+    unit = "ACGTTGCAAGGCTTAACCGGT"
+    text = "".join(unit if rng.random() < 0.9 else rng.choice("ACGT") for _ in range(120)) + "A" * 40 + "".join(rng.choice("ACGTN") for _ in range(300))
+    ref = build_index(str(tmp_path), text=text.encode())
+    out = str(tmp_path / "flat.npy")
+    code = textwrap.dedent(f"""
+        import numpy as np, spumoni_b200 as sp
+        np.save({out!r}, np.array(sp.Index.open({ref!r}, 0).flat(), copy=True))
+    """)
+    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    subprocess.check_call([sys.executable, "-c", code], env=env)
+    img = FlatImage(np.load(out))
+    po = oracle.OracleIndex(ref, "pml")
+    tb = text.encode()
+    used_slow = used_scan = 0
+    for _ in range(40):
+        ln = rng.randint(5, 200)
+        s0 = rng.randint(0, len(tb) - ln)
+        read = bytearray(tb[s0:s0 + ln])
+        for i in range(len(read)):
+            if rng.random() < 0.05:
+                read[i] = rng.choice(b"ACGTN")
+        got, st = img.walk_fast(bytes(read), sat26=7, sat29=15)
+        assert got == po.matching_statistics(bytes(read)).tolist()
+        used_slow += st["slow"]
+        used_scan += st["scan_iters"]
+    assert used_slow > 0 and used_scan > 0

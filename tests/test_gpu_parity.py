@@ -14,7 +14,11 @@ from conftest import MKINDEX, build_index, load_bin_reads
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")
-LANES = [4, 8, 16, 32]
+LANES = [1, 4, 8, 16, 32]  # 1 = thread-per-read PML fast path; MS has no 1-lane kernel
+
+
+def ms_lanes(lanes):
+    return 0 if lanes == 1 else lanes
 
 
 def oracle_batch(ref, mode, buf, off):
@@ -32,7 +36,7 @@ def test_golden_vectors(tmp_path, lanes):
         reads = [rd["read"].encode("latin1") for rd in case["reads"]]
         buf, off = sp.pack_reads(reads)
         L, _, _ = pml.query_host(buf, off, lanes=lanes)
-        Lm, Pm, _ = ms.query_host(buf, off, lanes=lanes)
+        Lm, Pm, _ = ms.query_host(buf, off, lanes=ms_lanes(lanes))
         for i, rd in enumerate(case["reads"]):
             a, b = int(off[i]), int(off[i + 1])
             assert L[a:b].tolist() == rd["pml"]
@@ -49,7 +53,7 @@ def test_small_index_all_reads(small_index, lanes):
     L, _, _ = sp.pml_t(small_index["ref"]).query_host(buf, off, lanes=lanes)
     assert np.array_equal(L.astype(np.uint64), Lo)
     Lo, Po = oracle_batch(small_index["ref"], "ms", buf, off)
-    L, P, _ = sp.ms_t(small_index["ref"]).query_host(buf, off, lanes=lanes)
+    L, P, _ = sp.ms_t(small_index["ref"]).query_host(buf, off, lanes=ms_lanes(lanes))
     assert np.array_equal(P, Po)
     assert np.array_equal(L.astype(np.uint64), Lo)
 
@@ -67,7 +71,7 @@ def test_edge_cases(small_index):
     po, mo = oracle.OracleIndex(ref, "pml"), oracle.OracleIndex(ref, "ms")
     for lanes in LANES:
         L, _, _ = pml.query_host(buf, off, lanes=lanes)
-        Lm, Pm, _ = ms.query_host(buf, off, lanes=lanes)
+        Lm, Pm, _ = ms.query_host(buf, off, lanes=ms_lanes(lanes))
         for i, r in enumerate(reads):
             a, b = int(off[i]), int(off[i + 1])
             if not r:
@@ -104,7 +108,7 @@ def test_window_overflow_fallback(tmp_path):
     for lanes in LANES:
         L, _, _ = sp.pml_t(ref).query_host(buf, off, lanes=lanes)
         assert np.array_equal(L.astype(np.uint64), Lo)
-        Lm, Pm, _ = sp.ms_t(ref).query_host(buf, off, lanes=lanes)
+        Lm, Pm, _ = sp.ms_t(ref).query_host(buf, off, lanes=ms_lanes(lanes))
         assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
 
 
@@ -113,10 +117,11 @@ def test_classifier_stats(small_index, mode):
     buf, off = load_bin_reads(small_index["reads_bin"])
     idx = sp.pml_t(small_index["ref"]) if mode == "pml" else sp.ms_t(small_index["ref"])
     for bw, thr in ((50, 7), (150, 13), (400, 3)):
-        L, _, S = idx.query_host(buf, off, bin_width=bw, max_value_thr=thr)
-        for r in range(len(off) - 1):
-            found, summ, above, below, nb = naive.classify_bins(L[int(off[r]):int(off[r + 1])].tolist(), bw, thr)
-            assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)
+        for lanes in ([1, 8] if mode == "pml" else [4]):
+            L, _, S = idx.query_host(buf, off, bin_width=bw, max_value_thr=thr, lanes=lanes)
+            for r in range(len(off) - 1):
+                found, summ, above, below, nb = naive.classify_bins(L[int(off[r]):int(off[r + 1])].tolist(), bw, thr)
+                assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)
 
 
 def test_multi_chunk_pipeline_and_ragged_lengths(small_index):
@@ -231,3 +236,21 @@ def test_medium_scale_properties(tmp_path):
     assert np.array_equal(Lp.astype(np.uint64), Lo)
     Lmo, Pmo = oracle_batch(ref, "ms", buf, off)
     assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
+
+
+def test_fast_path_saturation_fallbacks_on_gpu(small_index, tmp_path):
+    """Same inputs through the test-only library build whose 26/29-bit fields saturate at 7/15: every
+    fall-back of the thread-per-read kernel (slow step, absolute scan) runs and must stay bit-exact."""
+    import sys, textwrap
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    out = str(tmp_path / "L.npy")
+    code = textwrap.dedent(f"""
+        import numpy as np, spumoni_b200 as sp
+        buf = np.fromfile({small_index["reads_bin"]!r}, dtype=np.uint8); off = np.fromfile({small_index["reads_bin"] + ".off"!r}, dtype=np.uint64)
+        L, _, S = sp.pml_t({small_index["ref"]!r}).query_host(buf, off, lanes=1, bin_width=150, max_value_thr=9)
+        np.save({out!r}, L)
+    """)
+    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    subprocess.check_call([sys.executable, "-c", code], env=env)
+    assert np.array_equal(np.load(out).astype(np.uint64), Lo)
