@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -72,6 +73,13 @@ int ensure_device_state(spb_index* idx) {
     if (!idx->d_counters) {
         SPB_CUDA(cudaMalloc(&idx->d_counters, kCounters * sizeof(unsigned long long)));
         SPB_CUDA(cudaDeviceGetAttribute(&idx->num_sms, cudaDevAttrMultiProcessorCount, idx->device));
+        // Every backward-search step is one random 16/32-byte gather; the default L2 fill granularity
+        // drags whole 128-byte lines out of HBM for each of them (ncu: 128 B of DRAM traffic per
+        // step).  Ask for sector-sized fills.  SPUMONI_B200_L2_FETCH=0 keeps the device default.
+        size_t gran = 32;
+        if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) gran = (size_t)std::atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);  // a hint: failure is not an error
+        cudaGetLastError();
     }
     return SPB_OK;
 }
