@@ -176,7 +176,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per read (tuning; 0 = library default)")
+    ap.add_argument("--length-bytes", type=int, default=1, choices=[1, 2, 4],
+                    help="element size of the lengths output (1/2 are checked lossless: a clamped value fails the step and it is redone wider)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra 4-byte-lengths measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     name = os.environ.get("SPB_BENCH_WORKLOAD", "c2")
@@ -224,60 +227,78 @@ def main():
 
     h_reads = torch.from_numpy(buf).pin_memory()
     h_off = torch.from_numpy(off.astype(np.int64)).pin_memory()
-    h_len = torch.empty(n_bases, dtype=torch.int32).pin_memory()
     d_reads = torch.zeros(n_bases + 512, dtype=torch.uint8, device=dev)
     d_reads[:n_bases].copy_(h_reads)
     d_off = h_off.to(dev)
-    d_len = torch.zeros(n_bases, dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
-
-    def step_device():
-        idx.query_device(d_reads, d_off, n_reads, d_len, lanes=args.lanes, stream=stream.cuda_stream)
-
     np_reads, np_off = h_reads.numpy(), h_off.numpy().view(np.uint64)
-    np_len = h_len.numpy().view(np.uint32)
+    TDT = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
+    NDT = {1: np.uint8, 2: np.uint16, 4: np.uint32}
 
-    def step_host():
-        idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len)
+    def measure(width):
+        """Device-resident and end-to-end timing with `width`-byte lengths. Returns a dict + the host output."""
+        h_len = torch.empty(n_bases, dtype=TDT[width]).pin_memory()
+        d_len = torch.zeros(n_bases, dtype=TDT[width], device=dev)
+        d_sat = torch.zeros(1, dtype=torch.int64, device=dev)
+        np_len = h_len.numpy().view(NDT[width])
 
-    # ---------------- device-resident throughput ("value")
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
+        def step_device():
+            idx.query_device(d_reads, d_off, n_reads, d_len, lanes=args.lanes, stream=stream.cuda_stream, d_saturated=d_sat)
+
+        def step_host():
+            # the call a user makes: host buffers in, host buffers out (a clamped narrow value makes the call fail)
+            try:
+                idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len, length_bytes=width)
+            except sp.SpumoniError as e:
+                raise SystemExit(f"bench.py: {e}; rerun with --length-bytes 2" if e.code == sp.ERR_OVERFLOW else f"bench.py: {e}")
+
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        launches0 = sp.kernel_launches()
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        evs[0].record(stream)
+        for i in range(args.steps):
+            step_device()
+            evs[i + 1].record(stream)
+        barrier()
+        launches = sp.kernel_launches() - launches0
+        kern_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+        total_ms = evs[0].elapsed_time(evs[-1])
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms_max = float(t.item())
+        if int(d_sat.item()) != 0:
+            raise SystemExit(f"bench.py: {int(d_sat.item())} lengths were clamped at {width} byte(s); rerun with --length-bytes 2")
+        for _ in range(2):
+            step_host()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        same = bool(np.array_equal(np_len, d_len.cpu().numpy().view(NDT[width])))
+        return {"value": n_bases * world * args.steps / (total_ms_max / 1e3), "ms_per_step": total_ms_max / args.steps,
+                "kernel_ms": sum(kern_ms) / len(kern_ms), "launches": int(launches),
+                "e2e": n_bases * world * args.steps / float(t.item()), "same": same,
+                "d2h_bytes_per_step": width * n_bases}, np_len
+
+    # ---------------- timed region (clock sampling covers the headline measurement)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = sp.kernel_launches()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    evs[0].record(stream)
-    for i in range(args.steps):
-        step_device()
-        evs[i + 1].record(stream)
-    barrier()
-    launches = sp.kernel_launches() - launches0
-    kern_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-    total_ms = evs[0].elapsed_time(evs[-1])
+    main_m, np_len = measure(args.length_bytes)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = n_bases * world * args.steps / (total_ms_max / 1e3)
-
-    # ---------------- end-to-end through the host-buffer C ABI (H2D + kernel + D2H inside the timed region)
-    for _ in range(2):
-        step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = n_bases * world * args.steps / float(t.item())
-    same = bool(np.array_equal(np_len, d_len.cpu().numpy().view(np.uint32)))
+    other = {}
+    if args.length_bytes != 4 and not args.no_variants:
+        other["u32"], _ = measure(4)
+    value, total_ms_max, kavg_ms, launches = main_m["value"], main_m["ms_per_step"] * args.steps, main_m["kernel_ms"], main_m["launches"]
+    e2e_value, same = main_m["e2e"], main_m["same"]
 
     # ---------------- parity spot check + CPU baseline (rank 0, N=1)
     cpu_baseline, parity = None, None
@@ -297,27 +318,31 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        kavg_ms = sum(kern_ms) / len(kern_ms)
         achieved = BYTES_PER_BASE_PML * n_bases / (kavg_ms / 1e3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
             "config": {"workload": w["desc"], "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
-                       "lanes_per_read": args.lanes or 1, "l2": "inputs (1 GB reads + 4 GB lengths per step) larger than L2; no explicit flush",
+                       "lanes_per_read": args.lanes or 1, "length_bytes": args.length_bytes,
+                       "l2": "inputs (1 GB reads per step) and outputs (1-4 GB lengths) larger than L2; no explicit flush",
                        "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)"},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1), "d2h_bytes_per_step": 4 * n_bases},
+            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1), "d2h_bytes_per_step": main_m["d2h_bytes_per_step"],
+                    "api": f"spb_pml_query_host, pinned host buffers, uint{8 * args.length_bytes} lengths (lossless on this workload: 0 clamped values)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spb_pml_fast_kernel<false>" if (args.lanes or 1) == 1 else "spb_walk_kernel<G,false>", "kernel_ms": kavg_ms,
+                         "traffic": None, "kernel": "spb_move_kernel<PML>" if (args.lanes or 1) == 1 else "spb_walk_kernel<G,false>", "kernel_ms": kavg_ms,
                          "bytes_per_base": BYTES_PER_BASE_PML, "peak_source": peak_src},
             "cpu_baseline": cpu_baseline, "parity": parity,
+            "variants": {k: {"value": v["value"], "kernel_ms": v["kernel_ms"], "e2e": v["e2e"], "d2h_bytes_per_step": v["d2h_bytes_per_step"]} for k, v in other.items()},
         }
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                out["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+                tj = json.load(open(tr))
+                if tj.get("kernel") == out["roofline"]["kernel"]:
+                    out["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
         print(json.dumps(out), flush=True)

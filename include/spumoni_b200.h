@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define SPB_ABI_VERSION 1
+#define SPB_ABI_VERSION 2
 #define SPB_QUERY_TOUPPER 1u
 
 typedef enum {
@@ -43,7 +43,9 @@ typedef enum {
     SPB_ERR_ARG = 3,       /* bad argument */
     SPB_ERR_CUDA = 4,      /* CUDA runtime error (message has the cudaError string) */
     SPB_ERR_NO_DEVICE = 5, /* index not resident on a GPU / no GPU present */
-    SPB_ERR_LIMIT = 6      /* size outside supported range (n >= 2^40-2, r >= 2^32-64, read >= 2^32) */
+    SPB_ERR_LIMIT = 6,     /* size outside supported range (n >= 2^40-2, r >= 2^32-64, read >= 2^32) */
+    SPB_ERR_OVERFLOW = 7   /* narrow (1/2-byte) length output clamped at least one value; outputs are otherwise complete:
+                              repeat the call with a wider length_bytes */
 } spb_status;
 
 typedef enum { SPB_MODE_PML = 0, SPB_MODE_MS = 1 } spb_mode;
@@ -60,10 +62,15 @@ typedef struct {
 
 typedef struct {
     uint32_t bin_width;      /* -w; 0 disables classification (stats may then be NULL) */
-    uint32_t lanes_per_read; /* 0 = library default (1 for PML, 4 for MS); 1 = thread-per-read fast path (PML), 4/8/16/32 = cooperative */
+    uint32_t lanes_per_read; /* 0 = library default; 1 = thread-per-read kernels over the move rows (needs an index whose
+                                frequent run heads are < 0x80, e.g. DNA), 4/8/16/32 = cooperative generic kernel */
     uint64_t max_value_thr;  /* see spb_max_value_threshold */
     uint32_t flags;          /* SPB_QUERY_TOUPPER: apply ::toupper to read bytes on the device (compute_ms_pml.cpp:916-917) */
-    uint32_t reserved[3];
+    uint32_t length_bytes;   /* element size of the `lengths` output: 0 or 4 = uint32_t, 2 = uint16_t, 1 = uint8_t.  A PML/MS
+                                length never exceeds the read length, so 2 is lossless for reads < 65536 bases.  Values that do
+                                not fit are clamped to the maximum and counted (lanes_per_read 1 only). */
+    uint64_t* saturated;     /* optional.  *_host calls: host pointer, receives the number of clamped values (the call then
+                                returns SPB_ERR_OVERFLOW).  *_device calls: device pointer, incremented by the kernels. */
 } spb_query_opts;
 
 /* EmpNullDatabase (emp_null_database.hpp:16-33); values are not kept, only the scalars */
@@ -118,19 +125,20 @@ void spb_index_close(spb_index* idx);
  * returns when the outputs are complete.  Pinned host memory (spb_host_alloc) makes the
  * copies asynchronous and overlapped. */
 int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-                       uint32_t* lengths, spb_bin_stats* stats, const spb_query_opts* opts);
+                       void* lengths /* uint32_t[], or uint16_t[] / uint8_t[] per opts->length_bytes */, spb_bin_stats* stats,
+                       const spb_query_opts* opts);
 
 /* ms_t::matching_statistics compute_ms_pml.cpp:795-812 -> ms_pointers::_query :570-623 */
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-                      uint32_t* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts);
+                      void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts);
 
 /* Same, on buffers already resident on the index's device; asynchronous on `cuda_stream`
  * (a cudaStream_t passed as void*; NULL = default stream).  d_reads must be 256-byte aligned
- * and readable up to the next multiple of 256 bytes past offsets[n_reads]. */
+ * and readable up to the next multiple of 256 bytes past offsets[n_reads]; d_lengths must be 16-byte aligned. */
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                         uint32_t* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream);
+                         void* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream);
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                        uint32_t* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
+                        void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
                         const spb_query_opts* opts, void* cuda_stream);
 
 /* ---- classification helpers ---------------------------------------------------------- */

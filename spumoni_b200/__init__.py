@@ -25,13 +25,16 @@ SATTEST_LIB_PATH = os.path.join(_HERE, "lib", "libspumoni_b200_sattest.so")  # t
 CLI_PATH = os.path.join(_HERE, "bin", "spumoni")
 MODE_PML, MODE_MS = 0, 1
 QUERY_TOUPPER = 1
+ERR_OVERFLOW = 7
+_LEN_DTYPES = {4: np.uint32, 2: np.uint16, 1: np.uint8}
 
 BinStats = np.dtype([("sum_max", np.uint64), ("above", np.uint32), ("below", np.uint32)])
 
 
 class QueryOpts(ctypes.Structure):
     _fields_ = [("bin_width", ctypes.c_uint32), ("lanes_per_read", ctypes.c_uint32),
-                ("max_value_thr", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("reserved", ctypes.c_uint32 * 3)]
+                ("max_value_thr", ctypes.c_uint64), ("flags", ctypes.c_uint32), ("length_bytes", ctypes.c_uint32),
+                ("saturated", ctypes.c_void_p)]
 
 
 class _NullDb(ctypes.Structure):
@@ -93,9 +96,11 @@ def load_library() -> ctypes.CDLL:
     return L
 
 
-def _check(rc: int) -> None:
+def _check(rc: int, saturated=None) -> None:
     if rc != 0:
-        raise SpumoniError(rc, load_library().spb_last_error().decode(errors="replace"))
+        e = SpumoniError(rc, load_library().spb_last_error().decode(errors="replace"))
+        e.saturated = int(saturated.value) if saturated is not None else 0
+        raise e
 
 
 def max_value_threshold(percentile_value: float, is_pml: bool, use_dna_letters=False, use_promotions=False) -> int:
@@ -218,37 +223,47 @@ class Index:
         return self
 
     # ---- queries (host buffers)
-    def _opts(self, bin_width=0, max_value_thr=0, lanes=0, toupper=False) -> QueryOpts:
+    def _opts(self, bin_width=0, max_value_thr=0, lanes=0, toupper=False, length_bytes=4, saturated=None) -> QueryOpts:
         o = QueryOpts()
         o.bin_width, o.lanes_per_read, o.max_value_thr = bin_width, lanes, max_value_thr
         o.flags = QUERY_TOUPPER if toupper else 0
+        o.length_bytes = length_bytes
+        o.saturated = saturated
         return o
 
     def query_host(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0,
-                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None):
+                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None, length_bytes=4):
+        """length_bytes 4/2/1 selects uint32/uint16/uint8 lengths; if a value does not fit, SpumoniError with
+        code ERR_OVERFLOW is raised (``.saturated`` = number of clamped values) and the caller retries wider."""
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         total = int(offsets[-1]) if n >= 0 and len(offsets) else 0
-        L = out_lengths if out_lengths is not None else np.zeros(total, dtype=np.uint32)
+        L = out_lengths if out_lengths is not None else np.zeros(total, dtype=_LEN_DTYPES[length_bytes])
+        assert L.dtype.itemsize == length_bytes and L.size >= total
         S = None
         if bin_width:
             S = out_stats if out_stats is not None else np.zeros(n, dtype=BinStats)
-        o = self._opts(bin_width, max_value_thr, lanes, toupper)
+        sat = ctypes.c_uint64(0)
+        o = self._opts(bin_width, max_value_thr, lanes, toupper, length_bytes, ctypes.addressof(sat))
+        self.last_saturated = sat  # keeps the counter alive for the duration of the call
         lib = load_library()
         if self.mode == MODE_MS:
             P = out_pointers if out_pointers is not None else np.zeros(total, dtype=np.uint64)
             _check(lib.spb_ms_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
-                                         P.ctypes.data, S.ctypes.data if S is not None else None, ctypes.byref(o)))
+                                         P.ctypes.data, S.ctypes.data if S is not None else None, ctypes.byref(o)), sat)
             return L, P, S
         _check(lib.spb_pml_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
-                                      S.ctypes.data if S is not None else None, ctypes.byref(o)))
+                                      S.ctypes.data if S is not None else None, ctypes.byref(o)), sat)
         return L, None, S
 
     # ---- queries (torch CUDA tensors, asynchronous on `stream`)
     def query_device(self, d_reads, d_offsets, n_reads: int, d_lengths, d_pointers=None, d_stats=None, bin_width=0,
-                     max_value_thr=0, lanes=0, toupper=False, stream: int = 0) -> None:
-        o = self._opts(bin_width, max_value_thr, lanes, toupper)
+                     max_value_thr=0, lanes=0, toupper=False, stream: int = 0, d_saturated=None) -> None:
+        """d_lengths: int32/int16/uint8 CUDA tensor (its element size selects the output width);
+        d_saturated: optional 1-element int64 CUDA tensor incremented by the number of clamped values."""
+        o = self._opts(bin_width, max_value_thr, lanes, toupper, d_lengths.element_size(),
+                       d_saturated.data_ptr() if d_saturated is not None else None)
         lib = load_library()
         sp = d_stats.data_ptr() if d_stats is not None else None
         if self.mode == MODE_MS:

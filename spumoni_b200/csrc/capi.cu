@@ -35,8 +35,8 @@ int fail(int code, const std::string& msg) {
 
 constexpr int kSlots = 3;                         // pipeline depth of the host entry points
 constexpr uint64_t kChunkBases = 32ull << 20;     // bases per pipelined sub-batch
-constexpr int kCounters = 64;
-constexpr int kDefaultLanes = 4;  // cooperative kernel (MS, or PML without fast symbols)
+constexpr int kCounters = 64;     // pairs of work counters, rotated per launch
+constexpr int kDefaultLanes = 4;  // cooperative kernel (indexes without fast symbols)
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -46,6 +46,9 @@ struct Slot {
     uint64_t* d_pointers = nullptr;
     spb_bin_stats* d_stats = nullptr;
     uint64_t* h_offsets = nullptr;  // pinned staging for chunk-local offsets
+    unsigned long long* d_sat = nullptr;  // clamped-value counter of the launch in flight
+    unsigned long long* h_sat = nullptr;  // pinned copy
+    bool sat_pending = false;
     uint64_t cap_bases = 0, cap_reads = 0;
     bool cap_ms = false;
 };
@@ -62,6 +65,7 @@ struct spb_index {
     int num_sms = 0;
     unsigned long long* d_counters = nullptr;
     uint32_t counter_next = 0;
+    uint32_t row_ld = 0;
     Slot slots[kSlots];
 };
 
@@ -80,6 +84,7 @@ int ensure_device_state(spb_index* idx) {
         if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) gran = (size_t)std::atoi(e);
         if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);  // a hint: failure is not an error
         cudaGetLastError();
+        if (const char* e = std::getenv("SPUMONI_B200_ROW_LD")) idx->row_ld = (uint32_t)std::atoi(e);  // development knob
     }
     return SPB_OK;
 }
@@ -91,6 +96,9 @@ void free_slot(Slot& s) {
     if (s.d_pointers) cudaFree(s.d_pointers);
     if (s.d_stats) cudaFree(s.d_stats);
     if (s.h_offsets) cudaFreeHost(s.h_offsets);
+    if (s.d_sat) cudaFree(s.d_sat);
+    if (s.h_sat) cudaFreeHost(s.h_sat);
+    s.d_sat = nullptr; s.h_sat = nullptr; s.sat_pending = false;
     s.d_reads = nullptr; s.d_offsets = nullptr; s.d_lengths = nullptr; s.d_pointers = nullptr; s.d_stats = nullptr;
     s.h_offsets = nullptr;
     s.cap_bases = s.cap_reads = 0;
@@ -110,22 +118,33 @@ int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms) {
     SPB_CUDA(cudaMalloc(&s.d_stats, (nr + 1) * sizeof(spb_bin_stats)));
     if (ms) SPB_CUDA(cudaMalloc(&s.d_pointers, (nb + 64) * sizeof(uint64_t)));
     SPB_CUDA(cudaMallocHost(&s.h_offsets, (nr + 1) * sizeof(uint64_t)));
+    SPB_CUDA(cudaMalloc(&s.d_sat, sizeof(unsigned long long)));
+    SPB_CUDA(cudaMallocHost(&s.h_sat, sizeof(unsigned long long)));
     s.cap_bases = nb; s.cap_reads = nr; s.cap_ms = ms;
     return SPB_OK;
 }
 
+int length_bytes_of(const spb_query_opts* opts) {
+    const uint32_t w = opts ? opts->length_bytes : 0;
+    return w == 0 ? 4 : (int)w;
+}
+
 int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                 uint32_t* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats, const spb_query_opts* opts,
-                 cudaStream_t stream) {
+                 void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats, const spb_query_opts* opts,
+                 unsigned long long* d_saturated, cudaStream_t stream) {
     if (n_reads == 0) return SPB_OK;
     if ((ms ? 1 : 0) != idx->mode) return fail(SPB_ERR_ARG, ms ? "MS query on a PML index" : "PML query on an MS index");
     if (!d_reads || !d_offsets || !d_lengths || (ms && !d_pointers)) return fail(SPB_ERR_ARG, "null device buffer");
     if (((uintptr_t)d_reads & 255u) != 0) return fail(SPB_ERR_ARG, "d_reads must be 256-byte aligned");
+    if (((uintptr_t)d_lengths & 15u) != 0 || ((uintptr_t)d_pointers & 15u) != 0) return fail(SPB_ERR_ARG, "d_lengths / d_pointers must be 16-byte aligned");
     const SpbFlatHeader& h = idx->hdr;
-    const bool has_fast = !ms && h.num_fast > 0 && h.off_fast != 0;
+    const bool has_fast = h.num_fast > 0 && h.off_mrows != 0 && (!ms || h.off_msamp != 0);
     int lanes = opts && opts->lanes_per_read ? (int)opts->lanes_per_read : (has_fast ? 1 : kDefaultLanes);
     if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SPB_ERR_ARG, "lanes_per_read must be 1, 4, 8, 16 or 32");
-    if (lanes == 1 && !has_fast) return fail(SPB_ERR_ARG, "lanes_per_read = 1 needs a PML index with fast symbols");
+    if (lanes == 1 && !has_fast) return fail(SPB_ERR_ARG, "lanes_per_read = 1 needs an index with fast symbols (frequent run heads < 0x80)");
+    const int width = length_bytes_of(opts);
+    if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
+    if (width != 4 && lanes != 1) return fail(SPB_ERR_ARG, "narrow length output needs lanes_per_read = 1");
     spb::WalkParams p;
     std::memset(&p, 0, sizeof(p));
     p.runs = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_runs);
@@ -142,25 +161,32 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.bin_width = (opts && d_stats) ? opts->bin_width : 0;
     p.stats = p.bin_width ? d_stats : nullptr;
     p.max_value_thr = opts ? opts->max_value_thr : 0;
-    p.rows = has_fast ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_fast) : nullptr;
-    p.rl = has_fast ? reinterpret_cast<const uint32_t*>(idx->dev_blob + h.off_rl) : nullptr;
-    p.init_off = h.init_off;
-    p.init_h = h.init_h;
-    p.work_counter = idx->d_counters + (idx->counter_next++ % kCounters);
-    SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, sizeof(unsigned long long), stream));
-    SPB_CUDA(spb::launch_walk(p, ms, lanes, idx->num_sms, stream));
-    g_launches.fetch_add(1);
+    p.rows = has_fast ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_mrows) : nullptr;
+    p.msamp = (has_fast && ms) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_msamp) : nullptr;
+    for (int i = 0; i < 4; i++) { p.mv_end_k[i] = h.mv_end_k[i]; p.mv_end_off[i] = h.mv_end_off[i]; p.mv_end_sl[i] = h.mv_end_sl[i]; }
+    p.out_width = (uint32_t)width;
+    p.row_ld = idx->row_ld;
+    p.saturated = d_saturated;
+    p.work_counter = idx->d_counters + 2 * (idx->counter_next++ % (kCounters / 2));
+    SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, 2 * sizeof(unsigned long long), stream));
+    int launched = 0;
+    SPB_CUDA(spb::launch_walk(p, ms, lanes, idx->num_sms, stream, &launched));
+    g_launches.fetch_add((uint64_t)launched);
     return SPB_OK;
 }
 
 int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-               uint32_t* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
+               void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
+    if (opts && opts->saturated) *opts->saturated = 0;
     if (n_reads == 0) return SPB_OK;
     if (!reads || !offsets || !lengths || (ms && !pointers)) return fail(SPB_ERR_ARG, "null host buffer");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
     const bool want_stats = stats && opts && opts->bin_width;
+    const int width = length_bytes_of(opts);
+    if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
+    uint64_t total_sat = 0;
     uint64_t r0 = 0;
     int chunk = 0;
     while (r0 < n_reads) {
@@ -172,7 +198,8 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         Slot& s = idx->slots[chunk % kSlots];
         rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), ms);
         if (rc) return rc;
-        SPB_CUDA(cudaStreamSynchronize(s.stream));  // previous use of this slot (incl. its h_offsets) is done
+        SPB_CUDA(cudaStreamSynchronize(s.stream));  // previous use of this slot (incl. its pinned staging) is done
+        if (s.sat_pending) { total_sat += *s.h_sat; s.sat_pending = false; }
         for (uint64_t i = 0; i <= nr; i++) {
             const uint64_t o = offsets[r0 + i];
             if (o < b0 || (i && o < offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
@@ -181,16 +208,27 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         }
         SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
         if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
-        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, s.d_stats, opts, s.stream);
+        if (width != 4) SPB_CUDA(cudaMemsetAsync(s.d_sat, 0, sizeof(unsigned long long), s.stream));
+        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, s.d_stats, opts, width != 4 ? s.d_sat : nullptr, s.stream);
         if (rc) return rc;
-        if (nb) SPB_CUDA(cudaMemcpyAsync(lengths + b0, s.d_lengths, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)lengths + b0 * (uint64_t)width, s.d_lengths, nb * (uint64_t)width, cudaMemcpyDeviceToHost, s.stream));
         if (ms && nb) SPB_CUDA(cudaMemcpyAsync(pointers + b0, s.d_pointers, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
         if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
+        if (width != 4) {
+            SPB_CUDA(cudaMemcpyAsync(s.h_sat, s.d_sat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+            s.sat_pending = true;
+        }
         r0 = r1;
         chunk++;
     }
-    for (int i = 0; i < kSlots; i++)
-        if (idx->slots[i].stream) SPB_CUDA(cudaStreamSynchronize(idx->slots[i].stream));
+    for (int i = 0; i < kSlots; i++) {
+        Slot& s = idx->slots[i];
+        if (!s.stream) continue;
+        SPB_CUDA(cudaStreamSynchronize(s.stream));
+        if (s.sat_pending) { total_sat += *s.h_sat; s.sat_pending = false; }
+    }
+    if (opts && opts->saturated) *opts->saturated = total_sat;
+    if (total_sat) return fail(SPB_ERR_OVERFLOW, std::to_string(total_sat) + " length value(s) exceed the " + std::to_string(width) + "-byte output and were clamped; repeat with a wider length_bytes");
     return SPB_OK;
 }
 
@@ -328,27 +366,29 @@ void spb_index_close(spb_index* idx) {
 }
 
 int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-                       uint32_t* lengths, spb_bin_stats* stats, const spb_query_opts* opts) {
+                       void* lengths, spb_bin_stats* stats, const spb_query_opts* opts) {
     return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, stats, opts);
 }
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-                      uint32_t* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
+                      void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
     return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, stats, opts);
 }
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                         uint32_t* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream) {
+                         void* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_stats, opts, (cudaStream_t)cuda_stream);
+    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_stats, opts,
+                        opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
 }
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                        uint32_t* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
+                        void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
                         const spb_query_opts* opts, void* cuda_stream) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_stats, opts, (cudaStream_t)cuda_stream);
+    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_stats, opts,
+                        opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
 }
 
 int spb_nulldb_load(const char* path, spb_nulldb* out) {

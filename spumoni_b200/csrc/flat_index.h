@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define SPB_FLAT_MAGIC 0x3030324250535F42ULL /* "B_SPB200" */
-#define SPB_FLAT_VERSION 3u
+#define SPB_FLAT_VERSION 4u
 #define SPB_RUN_PAD 64u  /* sentinel + padding run records past R (start = 2^40-1) */
 #define SPB_POS_MAX 0xFFFFFFFFFFULL
 
@@ -51,34 +51,47 @@ struct SpbCharTab {      // per byte value c; 16 bytes
     uint32_t cidx;       // compact symbol index (0..sigma-1)   | absent: 0xFFFFFFFF
 };
 
-// ---- PML fast path (thread-per-read kernel) --------------------------------------------------
-// Up to four "fast" symbols (the most frequent run heads below 0x80: A,C,G,T for DNA) get a fully
-// resolved transition table so that one backward-search step is ONE 16-byte gather.  The state of a
-// read is (k, off, h): run index, offset inside the run, fast id of the run's head (SPB_SYM_SLOW if
-// the head is not a fast symbol).  Row k (64 bytes) = { SpbFastMatch, SpbFastJump[3] }; the jump
-// slot of fast symbol s in a run whose head has fast id h is  s - (s > h).
+// ---- move rows (thread-per-read kernel, PML and MS) -------------------------------------------
+// Up to four "fast" symbols (the most frequent run heads below 0x80: A,C,G,T for DNA) are walked over
+// a table of 16-byte rows, one per BWT run, that is the ONLY index memory a regular step touches.  The
+// state of a read is (k, off): run index and offset inside the run; no absolute BWT position is carried.
 //
-//   SpbFastMatch (c == head[k]):   pos' = lf[k] + off lies in run dest, dest+1, or further
-//     x = dlen   = start[dest+1] - lf[k]        off <  dlen        -> (dest,   off + delta, hd)
-//     y = dest                                   off - dlen < len1  -> (dest+1, off - dlen,  hd1)
-//     z = delta  = lf[k] - start[dest]           otherwise          -> scan forward from dest+2 (SpbRunLen)
-//     w = len1 (26 bits, saturating) | hd << 26 | hd1 << 29
-//   SpbFastJump (c != head[k], c the slot's symbol; j = #c-runs before k, (thr, lf) = crec[c][j]):
-//     x = thr_rel = clamp(thr - start[k], 0, len[k])     down = off < thr_rel   (<=> pos < thr)
-//     y = kA      run containing lf                        !down -> (kA, offA, hA)
-//     z = offA (26) | hA << 26 | flagB << 29               down  -> (kA - flagB, offB, hB)   (position lf - 1)
-//     w = offB (26) | hB << 26
-//   offsets/lengths that do not fit 26 bits are stored as SPB_FAST_SAT and send the step down the
-//   generic (absolute position) path.
-// SpbRunLen[k] = len[k] (29 bits, saturating) | fast id of head[k] << 29, one word per run (+ padding).
+//   x = dest                      run containing lf[k]  (lf[k] = LF of the run's first character)
+//   y = len   (20) | thr0 << 20   run length                       | threshold code of jump slot 0
+//   z = delta (20) | thr1 << 20   lf[k] - start[dest]              | threshold code of jump slot 1
+//   w = thr2 (12) | dist0 << 12 | dist1 << 17 | dist2 << 22 | fid << 27 | slow << 30
+//
+//   match  (c == head[k])         (k, off) -> (dest, off + delta); the next row load normalises the state
+//                                 by walking forward while off >= len (the LF image of a run can span
+//                                 several runs; neighbours share the 128-byte line just fetched).
+//   jump   (c != head[k]); the jump slot of fast symbol s in a run whose head has fast id h is s - (s > h):
+//          thr code v: 0 never down | 1..SPB_MV_THR_MAX: down iff off < v  (v = thr - start[k]) |
+//                      SPB_MV_THR_SLOW: use the generic step | SPB_MV_THR_ALWAYS: always down
+//          dist d    : the next run headed by c is k2 = k + d (1..SPB_MV_DIST_FAR-1); 0 = there is none
+//                      (state SpbFlatHeader::mv_end[s], always down); SPB_MV_DIST_FAR = too far, generic step
+//          up   -> (dest[k2], delta[k2])                  first position of the next c-run, then LF
+//          down -> that position - 1: (dest[k2], delta[k2] - 1), or (dest[k2] - 1, SPB_MV_OFF_LAST) when
+//                  delta[k2] == 0     (last position of the previous c-run, then LF)
+//   slow = 1: len or delta does not fit its field, or the head is not a fast symbol, or k == R (pos == n):
+//          every step through this row is done by the generic absolute-position code.
+// MS adds one 16-byte SpbCharSamp per row k2: ss = samples_start[k2], sl = samples_last[previous run with
+// the same head] -- the two values a jump through k2 can assign to the SA sample.
 #define SPB_SYM_SLOW 4u
-#ifndef SPB_FAST_SAT
-#define SPB_FAST_SAT 0x3FFFFFFu  /* 26-bit fields; the test build lowers these to exercise the fallbacks */
+#ifndef SPB_MV_LEN_BITS
+#define SPB_MV_LEN_BITS 20      /* the test build lowers these limits to exercise the fall-backs */
 #endif
-#ifndef SPB_RL_SAT
-#define SPB_RL_SAT 0x1FFFFFFFu   /* 29-bit run length */
+#ifndef SPB_MV_THR_MAX
+#define SPB_MV_THR_MAX 0xFFDu
 #endif
-struct SpbFastRec { uint32_t x, y, z, w; };
+#ifndef SPB_MV_DIST_FAR
+#define SPB_MV_DIST_FAR 31u
+#endif
+#define SPB_MV_LEN_MASK ((1u << SPB_MV_LEN_BITS) - 1u)
+#define SPB_MV_THR_SLOW 0xFFEu
+#define SPB_MV_THR_ALWAYS 0xFFFu
+#define SPB_MV_OFF_LAST 0xFFFFFFFFu
+#define SPB_MV_ROW_PAD 16u
+struct SpbMoveRow { uint32_t x, y, z, w; };
 
 struct SpbFlatHeader {
     uint64_t magic;
@@ -93,12 +106,13 @@ struct SpbFlatHeader {
     uint64_t off_runs, off_blocks, off_crec, off_csamp, off_text;  // byte offsets from blob start
     uint64_t total_bytes;
     uint64_t terminator_position;
-    uint64_t off_fast, off_rl;   // fast rows (R * 64 bytes) and SpbRunLen words; 0 if no fast symbols
+    uint64_t off_mrows, off_msamp;  // move rows ((R + SPB_MV_ROW_PAD) * 16 bytes) and, MS only, per-row samples; 0 if no fast symbols
     uint32_t num_fast;           // number of fast symbols (0..4)
-    uint32_t init_off;           // state of the empty string: k = R-1, off = len[R-1]-1, h = init_h
-    uint32_t init_h;
     uint32_t fast_sym[4];        // byte value of each fast id
-    uint32_t pad0;
+    uint32_t mv_end_k[4];        // state of BWT position F[c] + numC[c] - 1 per fast symbol (jump target when no later c-run exists)
+    uint32_t mv_end_off[4];
+    uint32_t pad0[3];
+    uint64_t mv_end_sl[4];       // MS: samples_last of the last c-run
     uint64_t F[256];
     SpbCharTab chartab[256];
 };

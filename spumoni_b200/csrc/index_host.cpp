@@ -430,7 +430,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     uint32_t fid[256];
     for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
     uint32_t num_fast = 0;
-    if (!ms) {
+    {
         std::vector<int> cand;
         for (int c = 2; c < 0x80; c++) if (numRunsC[c]) cand.push_back(c);
         std::stable_sort(cand.begin(), cand.end(), [&](int a, int b) { return numRunsC[a] > numRunsC[b]; });
@@ -438,17 +438,17 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         std::sort(cand.begin(), cand.end());
         for (int c : cand) { h.fast_sym[num_fast] = (uint32_t)c; fid[c] = num_fast++; }
         for (uint64_t k = 0; k < R; k++)
-            if (d.lens[(size_t)k] >= 0xFFFFFFFFull) num_fast = 0;  // 32-bit in-run offsets would overflow: generic path only
+            if (d.lens[(size_t)k] >= 0xFFFFFFFEull) num_fast = 0;  // 32-bit in-run offsets would overflow: generic kernels only
         if (!num_fast) for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
     }
     h.num_fast = num_fast;
     if (num_fast) {
-        h.off_fast = off;
-        off = align_up(off + (size_t)R * 64, 256);
-        h.off_rl = off;
-        off = align_up(off + ((size_t)R + 16) * 4, 256);
-        h.init_off = (uint32_t)(d.lens[(size_t)R - 1] - 1);
-        h.init_h = fid[d.heads[(size_t)R - 1]];
+        h.off_mrows = off;
+        off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow), 256);
+        if (ms) {
+            h.off_msamp = off;
+            off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbCharSamp), 256);
+        }
     }
     h.total_bytes = off;
     for (int c = 0; c < 256; c++) {
@@ -544,73 +544,76 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     }
     if (ms) std::memcpy(blob.data() + h.off_text, text.data(), text.size());
     if (num_fast) {
-        SpbFastRec* rows = reinterpret_cast<SpbFastRec*>(blob.data() + h.off_fast);
-        uint32_t* rl = reinterpret_cast<uint32_t*>(blob.data() + h.off_rl);
-        auto sat26 = [](uint64_t v) { return (uint32_t)(v >= SPB_FAST_SAT ? SPB_FAST_SAT : v); };
-        auto hid = [&](uint64_t k) -> uint32_t { return k < R ? fid[d.heads[(size_t)k]] : SPB_SYM_SLOW; };
-        // runs of every fast symbol in BWT order (the j-th c-run), and #c-runs before each run
-        std::vector<std::vector<uint32_t>> cruns(num_fast);
-        for (uint64_t k = 0; k < R; k++) {
-            const uint32_t f = fid[d.heads[(size_t)k]];
-            if (f < SPB_SYM_SLOW) cruns[f].push_back((uint32_t)k);
-        }
-        std::vector<uint32_t> before((size_t)R * num_fast);
+        SpbMoveRow* rows = reinterpret_cast<SpbMoveRow*>(blob.data() + h.off_mrows);
+        SpbCharSamp* msamp = ms ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
+        SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
+        // next run (strictly after k) headed by each fast symbol, by a backward sweep
+        std::vector<uint32_t> nxt((size_t)R * num_fast);
         {
-            uint32_t cnt[4] = {0, 0, 0, 0};
-            for (uint64_t k = 0; k < R; k++) {
-                for (uint32_t s = 0; s < num_fast; s++) before[(size_t)k * num_fast + s] = cnt[s];
+            uint32_t cur[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+            for (uint64_t k = R; k-- > 0;) {
+                for (uint32_t s = 0; s < num_fast; s++) nxt[(size_t)k * num_fast + s] = cur[s];
                 const uint32_t f = fid[d.heads[(size_t)k]];
-                if (f < SPB_SYM_SLOW) cnt[f]++;
+                if (f < SPB_SYM_SLOW) cur[f] = (uint32_t)k;
             }
         }
 #pragma omp parallel for schedule(static)
         for (int64_t kk = 0; kk < (int64_t)R; kk++) {
             const uint64_t k = (uint64_t)kk;
             const uint32_t hk = fid[d.heads[(size_t)k]];
-            const uint64_t len_k = d.lens[(size_t)k];
-            rl[k] = (uint32_t)(len_k >= SPB_RL_SAT ? SPB_RL_SAT : len_k) | (hk << 29);
-            if (hk >= SPB_SYM_SLOW) continue;  // row unused: steps from this run take the generic path
-            SpbFastRec* row = rows + (size_t)k * 4;
-            {   // match record
-                const uint64_t de = dest[(size_t)k];
-                SpbFastRec a;
-                a.x = (uint32_t)(start[(size_t)de + 1] - lf[(size_t)k]);
-                a.y = (uint32_t)de;
-                a.z = (uint32_t)(lf[(size_t)k] - start[(size_t)de]);
-                const uint64_t len1 = de + 1 < R ? d.lens[(size_t)de + 1] : 0;
-                a.w = sat26(len1) | (hid(de) << 26) | (hid(de + 1) << 29);
-                row[0] = a;
-            }
-            for (uint32_t s = 0; s < num_fast; s++) {
-                if (s == hk) continue;
-                const int c = (int)h.fast_sym[s];
-                const uint32_t j = before[(size_t)k * num_fast + s];
-                uint64_t thr, lfj;
-                if (j < numRunsC[c]) {
-                    const uint32_t k2 = cruns[s][j];
-                    thr = d.thr[k2];
-                    lfj = lf[k2];
-                } else {
-                    thr = n + 1;
-                    lfj = d.F[c] + numC[c];
+            const uint64_t len_k = d.lens[(size_t)k], st = start[(size_t)k];
+            const uint64_t de = dest[(size_t)k], delta = lf[(size_t)k] - start[(size_t)de];
+            bool slow = hk >= SPB_SYM_SLOW || len_k > SPB_MV_LEN_MASK || delta > SPB_MV_LEN_MASK;
+            uint32_t thr3[3] = {0, 0, 0}, dist3[3] = {0, 0, 0};
+            if (hk < SPB_SYM_SLOW) {
+                for (uint32_t s = 0; s < num_fast; s++) {
+                    if (s == hk) continue;
+                    const uint32_t slot = s - (s > hk ? 1u : 0u);
+                    const uint32_t k2 = nxt[(size_t)k * num_fast + s];
+                    if (k2 == 0xFFFFFFFFu) {  // no later c-run: thr = n+1 (App. C-6), the jump always goes down
+                        thr3[slot] = SPB_MV_THR_ALWAYS;
+                        dist3[slot] = 0;
+                        continue;
+                    }
+                    const uint64_t thr = d.thr[k2];
+                    if (thr <= st) thr3[slot] = 0;
+                    else if (thr >= st + len_k) thr3[slot] = SPB_MV_THR_ALWAYS;
+                    else thr3[slot] = (thr - st) <= SPB_MV_THR_MAX ? (uint32_t)(thr - st) : SPB_MV_THR_SLOW;
+                    const uint64_t dd = (uint64_t)k2 - k;
+                    dist3[slot] = dd < SPB_MV_DIST_FAR ? (uint32_t)dd : SPB_MV_DIST_FAR;
                 }
-                SpbFastRec jr;
-                const uint64_t st = start[(size_t)k];
-                jr.x = thr <= st ? 0u : (uint32_t)std::min<uint64_t>(thr - st, len_k);
-                const uint64_t kA = run_of(lfj);  // R if lfj == n
-                const uint64_t offA = kA < R ? lfj - start[(size_t)kA] : 0;
-                uint64_t kB = kA, offB = 0;
-                if (lfj > 0) {
-                    if (offA > 0) { kB = kA; offB = offA - 1; }
-                    else { kB = kA - 1; offB = d.lens[(size_t)kB] - 1; }
-                }
-                jr.y = (uint32_t)kA;
-                jr.z = sat26(offA) | (hid(kA) << 26) | ((kB != kA ? 1u : 0u) << 29);
-                jr.w = sat26(offB) | (hid(kB) << 26);
-                row[1 + s - (s > hk ? 1 : 0)] = jr;
             }
+            SpbMoveRow r;
+            r.x = (uint32_t)de;
+            r.y = (uint32_t)(len_k > SPB_MV_LEN_MASK ? SPB_MV_LEN_MASK : len_k) | (thr3[0] << 20);
+            r.z = (uint32_t)(delta > SPB_MV_LEN_MASK ? SPB_MV_LEN_MASK : delta) | (thr3[1] << 20);
+            r.w = thr3[2] | (dist3[0] << 12) | (dist3[1] << 17) | (dist3[2] << 22) | ((hk > SPB_SYM_SLOW ? SPB_SYM_SLOW : hk) << 27) |
+                  ((slow ? 1u : 0u) << 30);
+            rows[k] = r;
         }
-        for (uint64_t k = R; k < R + 16; k++) rl[k] = SPB_RL_SAT | (SPB_SYM_SLOW << 29);
+        for (uint64_t k = R; k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
+            SpbMoveRow r;
+            r.x = (uint32_t)R; r.y = 1; r.z = 0;
+            r.w = (SPB_SYM_SLOW << 27) | (1u << 30);
+            rows[k] = r;
+        }
+        if (ms) {
+            std::vector<uint64_t> prev_sl(256, 0);
+            for (uint64_t k = 0; k < R; k++) {
+                const uint8_t c = d.heads[(size_t)k];
+                msamp[k].ss = d.samples_start[(size_t)k];
+                msamp[k].sl = prev_sl[c];
+                prev_sl[c] = d.samples_last[(size_t)k];
+            }
+            for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_sl[s] = prev_sl[h.fast_sym[s]];
+        }
+        for (uint32_t s = 0; s < num_fast; s++) {
+            const int c = (int)h.fast_sym[s];
+            const uint64_t p = d.F[c] + numC[c] - 1;  // numC[c] >= 1
+            const uint64_t kp = run_of(p);
+            hd->mv_end_k[s] = (uint32_t)kp;
+            hd->mv_end_off[s] = (uint32_t)std::min<uint64_t>(p - start[(size_t)kp], 0xFFFFFFFEull);
+        }
     }
     return blob;
 }

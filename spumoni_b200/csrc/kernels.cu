@@ -20,10 +20,6 @@
 #include "flat_index.h"
 #include "kernels.h"
 
-#ifndef SPB_FAST_MINB
-#define SPB_FAST_MINB 10  /* 128-thread CTAs per SM the fast kernel is compiled for (register cap 48) */
-#endif
-
 namespace spb {
 
 __device__ __forceinline__ uint4 ldg_nc16(const void* p) {
@@ -224,7 +220,7 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
                 if ((int)(gi & (G - 1)) == gl) out32 = length;
                 if ((gi & (G - 1)) == 0 || pidx == 0) {
                     const uint64_t idx = (gi & ~(uint64_t)(G - 1)) + gl;
-                    if (idx >= gi && idx < base + m) p.lengths[idx] = out32;
+                    if (idx >= gi && idx < base + m) reinterpret_cast<uint32_t*>(p.lengths)[idx] = out32;
                 }
                 if (do_stats) {
                     if (pidx < bin_lb) {  // left the bin [bin_lb, ...): close it
@@ -287,7 +283,7 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
                 if ((int)(gi & (G - 1)) == gl) out32 = (uint32_t)l;
                 if ((gi & (G - 1)) == (uint64_t)(G - 1) || i == m - 1) {
                     const uint64_t idx = (gi & ~(uint64_t)(G - 1)) + gl;
-                    if (idx <= gi && idx >= base) p.lengths[idx] = out32;
+                    if (idx <= gi && idx >= base) reinterpret_cast<uint32_t*>(p.lengths)[idx] = out32;
                 }
                 if (do_stats) {
                     if (i >= bin_ub && bins_closed + 1 < nbins) {
@@ -314,20 +310,33 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
 
 
 // ==========================================================================================
-// PML fast path: one thread per read, one 16-byte gather per backward-search step.
+// Thread-per-read kernels over the move rows (flat_index.h): PML and the MS pointer walk.
 //
-// Every lane is a small state machine that issues exactly one vector load per loop iteration
-// (a transition record in STEP mode, four run lengths in SCAN mode), so the 32 independent
-// pointer chases of a warp stay in lock step at the load and their latencies overlap instead of
-// serialising behind divergent branches.  Lanes drift apart in read position, pull their next
-// read from the work counter on their own, and only the rare symbols (absent characters, runs
-// headed by a non-fast symbol, saturated fields) leave the lock step for the generic code.
+// Every lane is a small state machine that issues exactly ONE 16-byte row load per loop iteration:
+//   STEP : row[k]  -> normalise (off >= len: walk to the next row), then match or decide the jump
+//   JUMP2: row[k2] -> the next run headed by the read character; its (dest, delta) is the landing state
+// so the 32 independent pointer chases of a warp stay in lock step at the load and their latencies
+// overlap.  The only random access of a step is row[k]; k2 and the normalisation walk touch the
+// neighbouring rows of the 128-byte line that access just brought in.  Lanes pull their next read from
+// an atomic work counter; rare cases (non-fast symbols, saturated fields, far jump targets, pos == n)
+// take the generic absolute-position step.
 // ==========================================================================================
-#define SPB_FAST_THREADS 128
+#define SPB_MV_THREADS 128
+#ifndef SPB_MV_MINB
+#define SPB_MV_MINB 10  /* 128-thread CTAs per SM (register cap 48) */
+#endif
+
+template <int LD>
+__device__ __forceinline__ uint4 ld_row(const uint4* p) {
+    uint4 r;
+    if (LD == 0) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
 
 struct ThreadLoc { uint32_t k; uint4 rec; };
 
-// thread-level predecessor search over the generic run records (slow path only)
+// thread-level predecessor search over the generic run records (generic step only)
 __device__ __noinline__ ThreadLoc locate_thread(const uint4* __restrict__ runs, uint64_t R, uint64_t target, uint64_t w0) {
     uint64_t lo = w0;
     uint4 cur = ldg_nc16(runs + lo);
@@ -352,70 +361,133 @@ __device__ __noinline__ ThreadLoc locate_thread(const uint4* __restrict__ runs, 
     return out;
 }
 
-// One reference step in absolute coordinates (same statements as spb_walk_kernel's body) for a
-// single thread.  In: state (k, off), byte c.  Out: new (k, off), returns the new PML length.
-struct SlowOut { uint32_t k, off, length; };
-__device__ __noinline__ SlowOut slow_step(const uint4* __restrict__ runs, const uint8_t* __restrict__ blocks,
-                                          const uint4* __restrict__ crec, uint32_t blk_stride, uint64_t R, uint64_t n,
-                                          const uint4 ct, uint32_t c, uint32_t k, uint32_t off, uint32_t length) {
-    const uint4 krec = ldg_nc16(runs + k);
-    const uint64_t pos = (k < R) ? rec_start(krec) + off : n;
+// One reference step in absolute coordinates (same statements as spb_walk_kernel's body) for a single
+// thread.  In: state (k, off) -- off may be un-normalised (>= len[k]) or SPB_MV_OFF_LAST --, byte c.
+// Out: the normalised new state; PML length / MS sample updated in place.
+struct SlowOut { uint32_t k, off; };
+template <bool MS>
+__device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint32_t k, uint32_t off, uint32_t& length, uint64_t& sample) {
+    const uint4* __restrict__ runs = p.runs;
+    const uint64_t R = p.R, n = p.n;
+    const uint4 ct = reinterpret_cast<const uint4*>(p.chartab)[c];
+    uint64_t pos = n;
+    uint4 krec = ldg_nc16(runs + (k < R ? k : R));
+    if (k < R) {
+        if (off == SPB_MV_OFF_LAST) pos = rec_start(ldg_nc16(runs + k + 1)) - 1;
+        else {
+            pos = rec_start(krec) + off;
+            const ThreadLoc L = locate_thread(runs, R, pos, k);  // un-normalised offsets: find the true run
+            k = L.k; krec = L.rec;
+        }
+    } else k = (uint32_t)R;
     uint64_t npos, w0;
     if (ct.w == 0xFFFFFFFFu) {
         length = 0;
+        if (MS) sample = 0;
         npos = (uint64_t)ct.x | ((uint64_t)ct.y << 32);
         w0 = ct.z;
     } else if (k < R && rec_head(krec) == c && c < 0x80u) {
         length++;
-        npos = rec_lf(krec) + off;
+        if (MS) sample--;
+        npos = rec_lf(krec) + (pos - rec_start(krec));
         w0 = krec.z;
     } else {
-        const uint32_t j = (k < R) ? crun_ordinal(blocks, blk_stride, k, c, ct.w) : ct.y;
-        const uint4 cr = ldg_nc16(crec + (size_t)ct.x + j);
+        const uint32_t j = (k < R) ? crun_ordinal(p.blocks, p.blk_stride, k, c, ct.w) : ct.y;
+        const uint4 cr = ldg_nc16(p.crec + (size_t)ct.x + j);
         const bool down = pos < crec_thr(cr);
         const bool same = (k < R) && rec_head(krec) == c;
         length = 0;
+        if (MS) {
+            const uint4 cs = ldg_nc16(p.csamp + (size_t)ct.x + j);
+            if (j < ct.y) sample = (uint64_t)cs.x | ((uint64_t)cs.y << 32);
+            if (down) sample = (uint64_t)cs.z | ((uint64_t)cs.w << 32);
+        }
         const uint64_t lf = crec_lf(cr);
-        npos = down ? lf - 1 : (same ? lf + off : lf);
+        npos = down ? lf - 1 : (same ? lf + (pos - rec_start(krec)) : lf);
         w0 = (down && cr.z > 0) ? cr.z - 1 : cr.z;
     }
     SlowOut o;
-    o.length = length;
     if (npos >= n) {
         o.k = (uint32_t)R;
         o.off = 0;
     } else {
-        ThreadLoc L = locate_thread(runs, R, npos, w0);
+        const ThreadLoc L = locate_thread(runs, R, npos, w0);
         o.k = L.k;
         o.off = (uint32_t)(npos - rec_start(L.rec));
     }
     return o;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(SPB_FAST_THREADS, SPB_FAST_MINB) spb_pml_fast_kernel(const WalkParams p) {
+// 16-byte output word holding 16/OW values of OW bytes each (lengths as u8 / u16 / u32)
+template <int OW>
+struct OutWord {
+    static constexpr uint32_t VPW = 16 / OW;
+    static constexpr uint32_t VMAX = OW == 4 ? 0xFFFFFFFFu : (OW == 2 ? 0xFFFFu : 0xFFu);
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+    __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
+    __device__ __forceinline__ void put(uint32_t slot, uint32_t v) {
+        const uint32_t word = (slot * OW) >> 2, sh = ((slot * OW) & 3u) * 8u;
+        const uint32_t bits = OW == 4 ? v : (v << sh);
+        if (word == 0) w0 |= bits; else if (word == 1) w1 |= bits; else if (word == 2) w2 |= bits; else w3 |= bits;
+    }
+    __device__ __forceinline__ uint32_t get(uint32_t slot) const {
+        const uint32_t word = (slot * OW) >> 2, sh = ((slot * OW) & 3u) * 8u;
+        const uint32_t w = word == 0 ? w0 : (word == 1 ? w1 : (word == 2 ? w2 : w3));
+        return OW == 4 ? w : ((w >> sh) & VMAX);
+    }
+};
+template <int OW>
+__device__ __forceinline__ void store_val(void* base, uint64_t idx, uint32_t v) {
+    if (OW == 4) reinterpret_cast<uint32_t*>(base)[idx] = v;
+    else if (OW == 2) reinterpret_cast<uint16_t*>(base)[idx] = (uint16_t)v;
+    else reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)v;
+}
+// Flush the word of group g (values g .. g+VPW-1); only entries in [lo, hi) were produced by this read.
+template <int OW>
+__device__ __forceinline__ void flush_word(void* out, const OutWord<OW>& b, uint64_t g, uint64_t lo, uint64_t hi) {
+    constexpr uint32_t VPW = OutWord<OW>::VPW;
+    if (lo <= g && g + VPW <= hi) {
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<uint8_t*>(out) + g * OW), "r"(b.w0), "r"(b.w1), "r"(b.w2), "r"(b.w3) : "memory");
+    } else {
+#pragma unroll 1
+        for (uint32_t t = 0; t < VPW; t++)
+            if (g + t >= lo && g + t < hi) store_val<OW>(out, g + t, b.get(t));
+    }
+}
+
+struct BinState {
+    uint64_t bound = 0, sum_max = 0;
+    uint32_t bin_max = 0, above = 0, below = 0;
+};
+
+template <bool MS, bool STATS, int OW, int LD>
+__global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
-    for (int i = threadIdx.x; i < 256; i += SPB_FAST_THREADS) {
+    __shared__ uint32_t s_end_k[4], s_end_off[4];
+    __shared__ uint64_t s_end_sl[4];
+    for (int i = threadIdx.x; i < 256; i += SPB_MV_THREADS) {
         const SpbCharTab t = p.chartab[i];
         s_fid[i] = (uint8_t)(t.cidx == 0xFFFFFFFFu ? 5u : t.dest_f);
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (threadIdx.x == i) { s_end_k[i] = p.mv_end_k[i]; s_end_off[i] = p.mv_end_off[i]; s_end_sl[i] = p.mv_end_sl[i]; }
     __syncthreads();
 
     const uint4* __restrict__ rows = p.rows;
     const uint32_t R32 = (uint32_t)p.R;
     const bool upper = (p.flags & SPB_FLAG_TOUPPER) != 0;
-    const bool do_stats = STATS && p.bin_width != 0 && p.stats != nullptr;
+    const bool do_stats = !MS && STATS && p.bin_width != 0 && p.stats != nullptr;
 
     // lane state
-    bool have = false;
+    bool have = false, down = false;
     unsigned long long r = 0;
     uint64_t base = 0, end = 0, gi = 0, chunk = 0;
-    uint32_t k = 0, off = 0, h = 0, length = 0;
-    uint32_t mode = 0, sk = 0, rem = 0;  // mode 0 = STEP, 1 = SCAN
-    uint32_t ob0 = 0, ob1 = 0, ob2 = 0, ob3 = 0;
-    // classifier
-    uint64_t bin_lb = 0, sum_max = 0;
-    uint32_t bin_max = 0, above = 0, below = 0;
+    uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2
+    uint64_t sample = 0, pbuf = 0;
+    uint32_t nsat = 0;
+    OutWord<OW> ob;
+    BinState bs;
 
     for (;;) {
         if (!have) {  // ---- pull the next read (rare, divergent)
@@ -429,118 +501,110 @@ __global__ void __launch_bounds__(SPB_FAST_THREADS, SPB_FAST_MINB) spb_pml_fast_
             }
             end = base + m;
             gi = end - 1;
-            k = R32 - 1; off = p.init_off; h = p.init_h; length = 0; mode = 0;
+            k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0; mode = 0;  // empty string: pos = n-1
+            if (MS) sample = p.last_run_sample;
             chunk = *reinterpret_cast<const uint64_t*>(p.reads + (gi & ~7ull));
+            ob.clear();
             have = true;
-            if (STATS && do_stats) {
+            if (do_stats) {
                 const uint64_t bw = p.bin_width;
                 const uint64_t nbins = m / bw > 0 ? m / bw : 1;
-                bin_lb = base + (nbins - 1) * bw;  // in global index coordinates
-                bin_max = 0; above = 0; below = 0; sum_max = 0;
+                bs.bound = base + (nbins - 1) * bw;  // lower bound of the open bin, in global index coordinates
+                bs.bin_max = 0; bs.above = 0; bs.below = 0; bs.sum_max = 0;
             }
         }
 
-        // ---- address generation: one gather per lane per iteration
-        const uint4* addr = rows;
-        uint32_t c = 0, s = 0;
-        bool is_match = false, slow = false;
+        // ---- one row load per lane per iteration
+        const uint4 rec = ld_row<LD>(rows + (mode ? k2 : k));
+        uint32_t c = (uint32_t)(chunk >> ((gi & 7) * 8)) & 0xFFu;
+        if (upper && c >= 'a' && c <= 'z') c -= 32;
+        bool slow = false, emit = false;
         if (mode == 0) {
-            c = (uint32_t)(chunk >> ((gi & 7) * 8)) & 0xFFu;
-            if (upper && c >= 'a' && c <= 'z') c -= 32;
-            s = s_fid[c];
-            if (s < SPB_SYM_SLOW && h < SPB_SYM_SLOW) {
-                is_match = (s == h);
-                addr = rows + (size_t)k * 4 + (is_match ? 0u : 1u + s - (s > h ? 1u : 0u));
-            } else
-                slow = true;
-        } else
-            addr = reinterpret_cast<const uint4*>(p.rl + (sk & ~3u));
-
-        bool emit = false;
-        if (!slow) {
-            const uint4 rec = ldg_nc16(addr);
-            if (mode == 0) {
-                emit = true;
-                const bool lt = off < rec.x;
-                if (is_match) {
+            if ((rec.w >> 30) & 1u) slow = true;
+            else {
+                const uint32_t len = rec.y & SPB_MV_LEN_MASK;
+                if (off == SPB_MV_OFF_LAST) off = len - 1;
+                if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
+                const uint32_t h = (rec.w >> 27) & 7u, s = s_fid[c];
+                if (s >= SPB_SYM_SLOW) slow = true;
+                else if (s == h) {  // bwt[pos] == c (:250 / :582)
                     length++;
-                    if (lt) {
-                        k = rec.y; off += rec.z; h = (rec.w >> 26) & 7u;
+                    if (MS) sample--;
+                    off += rec.z & SPB_MV_LEN_MASK;
+                    k = rec.x;
+                    emit = true;
+                } else {  // threshold jump (:251-279 / :583-616)
+                    const uint32_t slot = s - (s > h ? 1u : 0u);
+                    const uint32_t v = slot == 0 ? (rec.y >> 20) : (slot == 1 ? (rec.z >> 20) : (rec.w & 0xFFFu));
+                    const uint32_t d = (rec.w >> (12u + 5u * slot)) & 31u;
+                    if (v == SPB_MV_THR_SLOW || d == SPB_MV_DIST_FAR) slow = true;
+                    else if (d == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
+                        k = s_end_k[s]; off = s_end_off[s];
+                        length = 0;
+                        if (MS) sample = s_end_sl[s];
+                        emit = true;
                     } else {
-                        const uint32_t r2 = off - rec.x, len1 = rec.w & 0x3FFFFFFu;
-                        if (r2 < len1) { k = rec.y + 1; off = r2; h = rec.w >> 29; }
-                        else if (len1 == SPB_FAST_SAT) { length--; slow = true; emit = false; }  // length of run dest+1 unknown
-                        else { mode = 1; sk = rec.y + 2; rem = r2 - len1; }
-                    }
-                } else {
-                    uint32_t nk, noff, nh;
-                    if (!lt) { nk = rec.y; noff = rec.z & 0x3FFFFFFu; nh = (rec.z >> 26) & 7u; }
-                    else { nk = rec.y - ((rec.z >> 29) & 1u); noff = rec.w & 0x3FFFFFFu; nh = (rec.w >> 26) & 7u; }
-                    if (noff == SPB_FAST_SAT) { slow = true; emit = false; }  // offset did not fit: redo in absolute coordinates
-                    else { length = 0; k = nk; off = noff; h = nh; }
-                }
-            } else {
-                // SCAN: rec = lengths of runs (sk & ~3) .. +3; walk forward until rem falls inside a run
-                const uint32_t w4[4] = {rec.x, rec.y, rec.z, rec.w};
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (mode == 1 && (uint32_t)i >= (sk & 3u)) {
-                        const uint32_t len = w4[i] & 0x1FFFFFFFu;
-                        if (len == SPB_RL_SAT) {  // unknown length: finish with an absolute search
-                            const uint4 sr = ldg_nc16(p.runs + sk);
-                            ThreadLoc L = locate_thread(p.runs, p.R, rec_start(sr) + rem, sk);
-                            k = L.k; off = (uint32_t)(rec_start(sr) + rem - rec_start(L.rec));
-                            h = s_fid[rec_head(L.rec)]; if (h > SPB_SYM_SLOW) h = SPB_SYM_SLOW;
-                            mode = 0;
-                        } else if (rem < len) { k = sk; off = rem; h = w4[i] >> 29; mode = 0; }
-                        else { rem -= len; sk++; }
+                        down = (v == SPB_MV_THR_ALWAYS) || (off < v);
+                        k2 = k + d;
+                        mode = 1;
                     }
                 }
             }
+        } else {
+            mode = 0;
+            if ((rec.w >> 30) & 1u) slow = true;  // landing state not encodable: redo the step from (k, off)
+            else {
+                const uint32_t d2 = rec.z & SPB_MV_LEN_MASK;
+                if (MS) {
+                    const uint4 sm = ldg_nc16(p.msamp + k2);
+                    sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                }
+                if (!down) { k = rec.x; off = d2; }
+                else if (d2) { k = rec.x; off = d2 - 1; }
+                else { k = rec.x - 1; off = SPB_MV_OFF_LAST; }
+                length = 0;
+                emit = true;
+            }
         }
-        if (slow) {  // ---- generic step in absolute coordinates (absent / rare symbols, non-fast run heads, saturation)
-            const uint4 ct = reinterpret_cast<const uint4*>(p.chartab)[c];
-            const SlowOut so = slow_step(p.runs, p.blocks, p.crec, p.blk_stride, p.R, p.n, ct, c, k, off, length);
-            k = so.k; off = so.off; length = so.length;
-            if (k < R32) {
-                const uint4 kr = ldg_nc16(p.runs + k);
-                h = s_fid[rec_head(kr)];
-                if (h > SPB_SYM_SLOW) h = SPB_SYM_SLOW;
-            } else h = SPB_SYM_SLOW;
+        if (slow) {  // ---- generic step in absolute coordinates
+            const SlowOut so = slow_step<MS>(p, c, k, off, length, sample);
+            k = so.k; off = so.off;
             emit = true;
         }
 
         if (emit) {
-            // buffer four lengths and store them as one 16-byte word when the group is complete
-            const uint32_t slot = (uint32_t)gi & 3u;
-            if (slot == 0) ob0 = length; else if (slot == 1) ob1 = length; else if (slot == 2) ob2 = length; else ob3 = length;
             const bool last = (gi == base);
-            if (slot == 0 || last) {
-                const uint64_t g = gi & ~3ull;  // entries g+slot .. g+3 below `end` were produced by this read
-                uint32_t* dst = p.lengths + g;
-                if (slot == 0 && g + 3 < end) {
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(ob0, ob1, ob2, ob3);
-                } else {
-                    if (slot == 0) dst[0] = ob0;
-                    if (slot <= 1 && g + 1 < end) dst[1] = ob1;
-                    if (slot <= 2 && g + 2 < end) dst[2] = ob2;
-                    if (g + 3 < end) dst[3] = ob3;
+            if (MS) {
+                if (gi & 1ull) {
+                    if (last) p.pointers[gi] = sample; else pbuf = sample;
+                } else if (gi + 1 < end) {
+                    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p.pointers + gi), "l"(sample), "l"(pbuf) : "memory");
+                } else p.pointers[gi] = sample;
+            } else {
+                constexpr uint32_t VPW = OutWord<OW>::VPW;
+                const uint32_t slot = (uint32_t)gi & (VPW - 1);
+                uint32_t v = length;
+                if (OW < 4 && v > OutWord<OW>::VMAX) { v = OutWord<OW>::VMAX; nsat++; }
+                ob.put(slot, v);
+                if (slot == 0 || last) {
+                    flush_word<OW>(p.lengths, ob, gi & ~(uint64_t)(VPW - 1), gi, end);
+                    ob.clear();
                 }
-            }
-            if (STATS && do_stats) {
-                if (gi < bin_lb) {
-                    if (bin_max >= p.max_value_thr) above++; else below++;
-                    sum_max += bin_max;
-                    bin_max = 0;
-                    bin_lb -= p.bin_width;
+                if (do_stats) {
+                    if (gi < bs.bound) {  // left the bin [bound, ...): close it
+                        if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;
+                        bs.sum_max += bs.bin_max;
+                        bs.bin_max = 0;
+                        bs.bound -= p.bin_width;
+                    }
+                    bs.bin_max = length > bs.bin_max ? length : bs.bin_max;
                 }
-                bin_max = length > bin_max ? length : bin_max;
             }
             if (last) {
-                if (STATS && do_stats) {
-                    if (bin_max >= p.max_value_thr) above++; else below++;
-                    sum_max += bin_max;
-                    spb_bin_stats st; st.sum_max = sum_max; st.above = above; st.below = below;
+                if (do_stats) {
+                    if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;
+                    bs.sum_max += bs.bin_max;
+                    spb_bin_stats st; st.sum_max = bs.sum_max; st.above = bs.above; st.below = bs.below;
                     p.stats[r] = st;
                 }
                 have = false;
@@ -550,19 +614,127 @@ __global__ void __launch_bounds__(SPB_FAST_THREADS, SPB_FAST_MINB) spb_pml_fast_
             }
         }
     }
+    if (OW < 4 && nsat && p.saturated) atomicAdd(p.saturated, (unsigned long long)nsat);
 }
 
-template <bool STATS>
-static cudaError_t launch_fast(const WalkParams& p, int num_sms, cudaStream_t stream) {
+// MS pointers -> lengths (ms_t::matching_statistics, compute_ms_pml.cpp:795-812) + bin-max classifier
+// (:1150-1176); one thread per read, left to right, carrying l.  Each iteration either compares one
+// more character (read vs text at pointer + l) or emits one length.
+template <bool STATS, int OW>
+__global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const WalkParams p) {
+    const bool upper = (p.flags & SPB_FLAG_TOUPPER) != 0;
+    const bool do_stats = STATS && p.bin_width != 0 && p.stats != nullptr;
+    const uint64_t n_text = p.n_text;
+    bool have = false, ext = false;
+    unsigned long long r = 0;
+    uint64_t base = 0, m = 0, i = 0, l = 0, ptr = 0, prev = 0, nbins = 1, bins_closed = 0;
+    uint32_t nsat = 0;
+    OutWord<OW> ob;
+    BinState bs;
+    for (;;) {
+        if (!have) {
+            r = atomicAdd(p.work_counter + 1, 1ULL);
+            if (r >= p.n_reads) break;
+            base = p.offsets[r];
+            m = p.offsets[r + 1] - base;
+            if (m == 0) {
+                if (do_stats) { spb_bin_stats z; z.sum_max = 0; z.above = 0; z.below = 0; p.stats[r] = z; }
+                continue;
+            }
+            i = 0; l = 0; prev = 0;
+            ptr = p.pointers[base];
+            ext = true;
+            ob.clear();
+            have = true;
+            if (do_stats) {
+                const uint64_t bw = p.bin_width;
+                nbins = m / bw > 0 ? m / bw : 1;
+                bs.bound = bw;  // exclusive upper bound of the open bin (read coordinates)
+                bins_closed = 0;
+                bs.bin_max = 0; bs.above = 0; bs.below = 0; bs.sum_max = 0;
+            }
+        }
+        if (ext) {
+            const uint64_t tp = ptr + l;  // wraps like size_t (App. C-4)
+            bool ok = (i + l < m) && (tp < n_text);
+            if (ok) {
+                uint32_t rc = p.reads[base + i + l];
+                if (upper && rc >= 'a' && rc <= 'z') rc -= 32;
+                ok = rc == (uint32_t)p.text[tp];
+            }
+            if (ok) { l++; continue; }
+            ext = false;
+        }
+        // ---- emit lengths[i] = l
+        {
+            constexpr uint32_t VPW = OutWord<OW>::VPW;
+            const uint64_t gidx = base + i;
+            const uint32_t slot = (uint32_t)gidx & (VPW - 1);
+            uint32_t v = (uint32_t)l;
+            if (OW < 4 && v > OutWord<OW>::VMAX) { v = OutWord<OW>::VMAX; nsat++; }
+            ob.put(slot, v);
+            if (slot == VPW - 1 || i == m - 1) {
+                flush_word<OW>(p.lengths, ob, gidx & ~(uint64_t)(VPW - 1), base, gidx + 1);
+                ob.clear();
+            }
+            if (do_stats) {
+                if (i >= bs.bound && bins_closed + 1 < nbins) {
+                    if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;
+                    bs.sum_max += bs.bin_max;
+                    bs.bin_max = 0;
+                    bs.bound += p.bin_width;
+                    bins_closed++;
+                }
+                bs.bin_max = (uint32_t)l > bs.bin_max ? (uint32_t)l : bs.bin_max;
+            }
+        }
+        l = l ? l - 1 : 0;
+        prev = ptr;
+        if (++i == m) {
+            if (do_stats) {
+                if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;
+                bs.sum_max += bs.bin_max;
+                spb_bin_stats st; st.sum_max = bs.sum_max; st.above = bs.above; st.below = bs.below;
+                p.stats[r] = st;
+            }
+            have = false;
+        } else {
+            ptr = p.pointers[base + i];
+            ext = ptr != prev + 1;
+        }
+    }
+    if (OW < 4 && nsat && p.saturated) atomicAdd(p.saturated, (unsigned long long)nsat);
+}
+
+template <typename K>
+static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms, cudaStream_t stream) {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spb_pml_fast_kernel<STATS>, SPB_FAST_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SPB_MV_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
-    unsigned long long need = (p.n_reads + SPB_FAST_THREADS - 1) / SPB_FAST_THREADS;
+    // persistent grid: a whole number of CTAs per SM; reads are pulled from the work counter
+    unsigned long long need = (p.n_reads + SPB_MV_THREADS - 1) / SPB_MV_THREADS;
     unsigned long long grid = (unsigned long long)num_sms * occ;
     if (need < grid) grid = need ? need : 1;
-    spb_pml_fast_kernel<STATS><<<(unsigned)grid, SPB_FAST_THREADS, 0, stream>>>(p);
+    kernel<<<(unsigned)grid, SPB_MV_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <bool STATS, int LD>
+static cudaError_t launch_move_pml(const WalkParams& p, int num_sms, cudaStream_t stream) {
+    switch (p.out_width) {
+        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD>, p, num_sms, stream);
+        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD>, p, num_sms, stream);
+        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD>, p, num_sms, stream);
+    }
+}
+template <bool STATS>
+static cudaError_t launch_ms_lengths(const WalkParams& p, int num_sms, cudaStream_t stream) {
+    switch (p.out_width) {
+        case 1: return launch_persistent(spb_ms_lengths_kernel<STATS, 1>, p, num_sms, stream);
+        case 2: return launch_persistent(spb_ms_lengths_kernel<STATS, 2>, p, num_sms, stream);
+        default: return launch_persistent(spb_ms_lengths_kernel<STATS, 4>, p, num_sms, stream);
+    }
 }
 
 template <int G, bool MS>
@@ -579,11 +751,25 @@ static cudaError_t launch_t(const WalkParams& p, int num_sms, cudaStream_t strea
     return cudaGetLastError();
 }
 
-cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream) {
+cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches) {
+    const bool stats = p.bin_width && p.stats;
     if (lanes == 1) {
-        if (ms || !p.rows) return cudaErrorInvalidValue;
-        return (p.bin_width && p.stats) ? launch_fast<true>(p, num_sms, stream) : launch_fast<false>(p, num_sms, stream);
+        if (!p.rows || (ms && !p.msamp)) return cudaErrorInvalidValue;
+        cudaError_t e;
+        if (ms) {
+            e = p.row_ld ? launch_persistent(spb_move_kernel<true, false, 4, 1>, p, num_sms, stream)
+                         : launch_persistent(spb_move_kernel<true, false, 4, 0>, p, num_sms, stream);
+            if (e != cudaSuccess) return e;
+            e = stats ? launch_ms_lengths<true>(p, num_sms, stream) : launch_ms_lengths<false>(p, num_sms, stream);
+            if (launches) *launches = 2;
+            return e;
+        }
+        if (launches) *launches = 1;
+        if (p.row_ld) return stats ? launch_move_pml<true, 1>(p, num_sms, stream) : launch_move_pml<false, 1>(p, num_sms, stream);
+        return stats ? launch_move_pml<true, 0>(p, num_sms, stream) : launch_move_pml<false, 0>(p, num_sms, stream);
     }
+    if (p.out_width != 4) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths only
+    if (launches) *launches = 1;
     switch (lanes) {
         case 4: return ms ? launch_t<4, true>(p, num_sms, stream) : launch_t<4, false>(p, num_sms, stream);
         case 8: return ms ? launch_t<8, true>(p, num_sms, stream) : launch_t<8, false>(p, num_sms, stream);

@@ -25,19 +25,24 @@ struct WalkParams {
     const uint8_t* reads;      // 256-byte aligned
     const uint64_t* offsets;   // n_reads + 1
     uint64_t n_reads;
-    uint32_t* lengths;
+    void* lengths;             // u32, or u16 / u8 (thread-per-read kernels, out_width 2 / 1)
     uint64_t* pointers;        // MS only
     spb_bin_stats* stats;      // nullable
     uint32_t bin_width;
     uint64_t max_value_thr;
     unsigned long long* work_counter;  // zeroed before launch
-    // PML fast path (thread per read); rows == nullptr when the index has no fast symbols
+    // thread-per-read kernels over the move rows; rows == nullptr when the index has no fast symbols
     const uint4* rows;
-    const uint32_t* rl;
-    uint32_t init_off, init_h;
+    const uint4* msamp;        // MS only
+    uint32_t mv_end_k[4], mv_end_off[4];
+    uint64_t mv_end_sl[4];
+    uint32_t out_width;        // bytes per length value: 4, 2 or 1 (values above the maximum are clamped and counted)
+    uint32_t row_ld;           // development knob: 0 = rows bypass L1, 1 = rows allocate in L1
+    unsigned long long* saturated;  // nullable; += number of clamped length values
 };
 
-// lanes: 4/8/16/32 = cooperative walk kernel (PML or MS); 1 = PML fast path (thread per read)
-cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream);
+// lanes: 4/8/16/32 = cooperative walk kernel (PML or MS); 1 = thread-per-read kernels over the move rows.
+// work_counter must point at two zeroed counters.  *launches (nullable) receives the number of kernels launched.
+cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches);
 
 }  // namespace spb

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQIII4II"  # up to pad0 (then F[256], chartab[256])
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4Q"  # up to mv_end_sl (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -20,9 +20,9 @@ class FlatImage:
         self.b = b
         (self.magic, self.version, self.mode, self.n, self.R, self.n_text, self.last_run_sample, self.sigma,
          self.sigma_pad, self.blk_stride, self.num_blocks, self.num_crec, self.off_runs, self.off_blocks,
-         self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position, self.off_fast,
-         self.off_rl, self.num_fast, self.init_off, self.init_h, fs0, fs1, fs2, fs3, _pad) = struct.unpack_from(HDR_FMT, b, 0)
-        self.fast_sym = [fs0, fs1, fs2, fs3]
+         self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position, self.off_mrows,
+         self.off_msamp, self.num_fast, *rest) = struct.unpack_from(HDR_FMT, b, 0)
+        self.fast_sym, self.mv_end_k, self.mv_end_off, self.mv_end_sl = rest[0:4], rest[4:8], rest[8:12], rest[15:19]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -32,8 +32,9 @@ class FlatImage:
         self.runs = np.frombuffer(b, dtype=np.uint32, count=4 * nrec, offset=self.off_runs).reshape(nrec, 4)
         self.crec = np.frombuffer(b, dtype=np.uint32, count=4 * (self.num_crec + 1), offset=self.off_crec).reshape(-1, 4)
         if self.num_fast:
-            self.rows = np.frombuffer(b, dtype=np.uint32, count=16 * self.R, offset=self.off_fast).reshape(self.R, 4, 4)
-            self.rl = np.frombuffer(b, dtype=np.uint32, count=self.R + 16, offset=self.off_rl)
+            self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
+            if self.mode == 1:
+                self.msamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.R + 16), offset=self.off_msamp).reshape(-1, 2)
         if self.mode == 1:
             self.csamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.num_crec + 1), offset=self.off_csamp).reshape(-1, 2)
             self.text = b[self.off_text:self.off_text + self.n_text]
@@ -116,19 +117,28 @@ class FlatImage:
         return out
 
 
-    # ---- PML fast path (spb_pml_fast_kernel), including its fall-backs; sat26/sat29 let a test lower the
-    # saturation limits the way the SPB_FAST_SAT / SPB_RL_SAT test build does
-    def slow_step(self, k, off, c, length):
+    # ---- thread-per-read walk over the move rows (spb_move_kernel), including its fall-backs; the limits
+    # let a test decode an image written by the SPB_MV_* test build
+    def slow_step(self, k, off, c, length, sample):
         n, R = self.n, self.R
+        ms = self.mode == 1
+        if k < R:
+            if off == 0xFFFFFFFF:
+                pos = self.run(k + 1)["start"] - 1
+            else:
+                pos = self.run(k)["start"] + off
+                k = self.locate(pos, k)
+        else:
+            k, pos = R, n
         kr = self.run(k)
-        pos = kr["start"] + off if k < R else n
         ct = self.chartab[c]
         if ct[3] == 0xFFFFFFFF:
-            length = 0
+            length, sample = 0, 0
             npos, w0 = ct[0] | (ct[1] << 32), ct[2]
         elif k < R and kr["head"] == c and c < 0x80:
             length += 1
-            npos, w0 = kr["lf"] + off, kr["dest"]
+            sample = (sample - 1) & U64
+            npos, w0 = kr["lf"] + (pos - kr["start"]), kr["dest"]
         else:
             j = self.crun_ordinal(k, c, ct[3]) if k < R else ct[1]
             x, y, z, w = (int(v) for v in self.crec[ct[0] + j])
@@ -136,72 +146,88 @@ class FlatImage:
             down = pos < thr
             same = k < R and kr["head"] == c
             length = 0
-            npos = lf - 1 if down else (lf + off if same else lf)
+            if ms:
+                ss, sl = (int(v) for v in self.csamp[ct[0] + j])
+                if j < ct[1]:
+                    sample = ss
+                if down:
+                    sample = sl
+            npos = lf - 1 if down else (lf + (pos - kr["start"]) if same else lf)
             w0 = z - 1 if (down and z > 0) else z
         if npos >= n:
-            return R, 0, length
+            return R, 0, length, sample
         k2 = self.locate(npos, w0)
-        return k2, npos - self.run(k2)["start"], length
+        return k2, npos - self.run(k2)["start"], length, sample
 
     def fid(self, c):
         ct = self.chartab[c]
         return 5 if ct[3] == 0xFFFFFFFF else ct[2]
 
-    def walk_fast(self, read: bytes, sat26=0x3FFFFFF, sat29=0x1FFFFFFF):
-        assert self.num_fast and self.mode == 0
+    def walk_move(self, read: bytes, len_bits=20, dist_far=31):
+        """Returns (lengths, pointers or None, stats)."""
+        assert self.num_fast
+        ms = self.mode == 1
+        LAST, lmask = 0xFFFFFFFF, (1 << len_bits) - 1
         m, R = len(read), self.R
-        k, off, h, length = R - 1, self.init_off, self.init_h, 0
-        out = [0] * m
-        stats = {"fast": 0, "scan_iters": 0, "slow": 0}
+        k, off, length, sample = R - 1, LAST, 0, self.last_run_sample
+        out, ptr = [0] * m, [0] * m
+        stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0}
         for gi in range(m - 1, -1, -1):
             c = read[gi]
-            s = self.fid(c)
-            slow = not (s < 4 and h < 4)
+            slow = False
+            while True:  # STEP iterations (normalisation walks to the next row)
+                x, y, z, w = (int(v) for v in self.rows[k])
+                if (w >> 30) & 1:
+                    slow = True
+                    break
+                ln = y & lmask
+                if off == LAST:
+                    off = ln - 1
+                if off >= ln:
+                    off -= ln
+                    k += 1
+                    stats["norm_iters"] += 1
+                    continue
+                break
             if not slow:
-                match = s == h
-                x, y, z, w = (int(v) for v in self.rows[k][0 if match else 1 + s - (1 if s > h else 0)])
-                lt = off < x
-                if match:
-                    if lt:
-                        k, off, h, length = y, off + z, (w >> 26) & 7, length + 1
+                h, s = (w >> 27) & 7, self.fid(c)
+                if s >= 4:
+                    slow = True
+                elif s == h:
+                    length += 1
+                    sample = (sample - 1) & U64
+                    k, off = x, off + (z & lmask)
+                else:
+                    slot = s - (1 if s > h else 0)
+                    v = (y >> 20) if slot == 0 else ((z >> 20) if slot == 1 else (w & 0xFFF))
+                    d = (w >> (12 + 5 * slot)) & 31
+                    if v == 0xFFE or d == dist_far:
+                        slow = True
+                    elif d == 0:
+                        k, off, length, sample = self.mv_end_k[s], self.mv_end_off[s], 0, self.mv_end_sl[s]
+                        stats["end"] += 1
                     else:
-                        r2, len1 = off - x, w & 0x3FFFFFF
-                        if r2 < len1:
-                            k, off, h, length = y + 1, r2, w >> 29, length + 1
-                        elif len1 == sat26:
+                        down = v == 0xFFF or off < v
+                        k2 = k + d
+                        x2, y2, z2, w2 = (int(t) for t in self.rows[k2])
+                        stats["jump2"] += 1
+                        if (w2 >> 30) & 1:
                             slow = True
                         else:
-                            length += 1
-                            sk, rem = y + 2, r2 - len1
-                            while True:
-                                stats["scan_iters"] += 1
-                                wv = int(self.rl[sk])
-                                ln = wv & 0x1FFFFFFF
-                                if ln == sat29:
-                                    st = self.run(sk)["start"] + rem
-                                    k = self.locate(st, sk)
-                                    off = st - self.run(k)["start"]
-                                    h = min(self.fid(self.run(k)["head"]), 4)
-                                    break
-                                if rem < ln:
-                                    k, off, h = sk, rem, wv >> 29
-                                    break
-                                rem -= ln
-                                sk += 1
-                else:
-                    if not lt:
-                        nk, noff, nh = y, z & 0x3FFFFFF, (z >> 26) & 7
-                    else:
-                        nk, noff, nh = y - ((z >> 29) & 1), w & 0x3FFFFFF, (w >> 26) & 7
-                    if noff == sat26:
-                        slow = True
-                    else:
-                        k, off, h, length = nk, noff, nh, 0
-                if not slow:
-                    stats["fast"] += 1
+                            d2 = z2 & lmask
+                            if ms:
+                                sample = int(self.msamp[k2][1 if down else 0])
+                            if not down:
+                                k, off = x2, d2
+                            elif d2:
+                                k, off = x2, d2 - 1
+                            else:
+                                k, off = x2 - 1, LAST
+                            length = 0
             if slow:
                 stats["slow"] += 1
-                k, off, length = self.slow_step(k, off, c, length)
-                h = min(self.fid(self.run(k)["head"]), 4) if k < R else 4
-            out[gi] = length
-        return out, stats
+                k, off, length, sample = self.slow_step(k, off, c, length, sample)
+            else:
+                stats["fast"] += 1
+            out[gi], ptr[gi] = length, sample
+        return out, (ptr if ms else None), stats

@@ -26,11 +26,12 @@ def test_flat_image_matches_golden_vectors(tmp_path):
         for rd in case["reads"]:
             read = rd["read"].encode("latin1")
             assert fp.walk(read)[0] == rd["pml"]
-            if fp.num_fast:
-                assert fp.walk_fast(read)[0] == rd["pml"]
             _, ptr = fm.walk(read)
             assert [str(x) for x in ptr] == rd["ms_pointers"]
             assert fm.ms_lengths(read, ptr) == rd["ms_lengths"]
+            if fp.num_fast:
+                assert fp.walk_move(read)[0] == rd["pml"]
+                assert [str(x) for x in fm.walk_move(read)[1]] == rd["ms_pointers"]
 
 
 def test_flat_image_vs_oracle_random(tmp_path):
@@ -52,10 +53,11 @@ def test_flat_image_vs_oracle_random(tmp_path):
             read = bytes(rng.choice(b"ACGTNY\xe9") for _ in range(ln)) if rng.random() < 0.4 else (tb[rng.randint(0, max(0, len(tb) - ln)):][:ln] or b"A")
             want = po.matching_statistics(read).tolist()
             assert fp.walk(read)[0] == want
-            assert fp.walk_fast(read)[0] == want
+            assert fp.walk_move(read)[0] == want
             L, P = mo.matching_statistics(read)
             _, ptr = fm.walk(read)
             assert ptr == P.tolist() and fm.ms_lengths(read, ptr) == L.tolist()
+            assert fm.walk_move(read)[1] == P.tolist()
 
 
 def test_flat_roundtrip_and_header(small_index):
@@ -116,25 +118,28 @@ def test_nulldb_roundtrip(tmp_path):
     assert raw[32 + 8] == 4
 
 
-def test_fast_path_saturation_fallbacks_host_side(tmp_path):
-    """The sattest build stores every offset/length >= 7 (resp. 15) as 'saturated'; walking its flat image
-    with the same limits must still reproduce the oracle (exercises the slow/absolute fall-backs)."""
+def test_move_rows_saturation_fallbacks_host_side(tmp_path):
+    """The sattest build shrinks the move-row fields (3-bit len/delta, thresholds <= 4, jump distance < 3);
+    walking its flat image with the same limits must still reproduce the oracle (exercises the slow flag,
+    SPB_MV_THR_SLOW, SPB_MV_DIST_FAR and un-normalised states entering the generic step)."""
     import subprocess, sys, textwrap
     rng = random.Random(23)
     unit = "ACGTTGCAAGGCTTAACCGGT"
     text = "".join(unit if rng.random() < 0.9 else rng.choice("ACGT") for _ in range(120)) + "A" * 40 + "".join(rng.choice("ACGTN") for _ in range(300))
     ref = build_index(str(tmp_path), text=text.encode())
-    out = str(tmp_path / "flat.npy")
-    code = textwrap.dedent(f"""
-        import numpy as np, spumoni_b200 as sp
-        np.save({out!r}, np.array(sp.Index.open({ref!r}, 0).flat(), copy=True))
-    """)
     env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    subprocess.check_call([sys.executable, "-c", code], env=env)
-    img = FlatImage(np.load(out))
-    po = oracle.OracleIndex(ref, "pml")
+    imgs = {}
+    for mode in (0, 1):
+        out = str(tmp_path / f"flat{mode}.npy")
+        code = textwrap.dedent(f"""
+            import numpy as np, spumoni_b200 as sp
+            np.save({out!r}, np.array(sp.Index.open({ref!r}, {mode}).flat(), copy=True))
+        """)
+        subprocess.check_call([sys.executable, "-c", code], env=env)
+        imgs[mode] = FlatImage(np.load(out))
+    po, mo = oracle.OracleIndex(ref, "pml"), oracle.OracleIndex(ref, "ms")
     tb = text.encode()
-    used_slow = used_scan = 0
+    tot = {"slow": 0, "norm_iters": 0, "jump2": 0, "fast": 0, "end": 0}
     for _ in range(40):
         ln = rng.randint(5, 200)
         s0 = rng.randint(0, len(tb) - ln)
@@ -142,8 +147,10 @@ def test_fast_path_saturation_fallbacks_host_side(tmp_path):
         for i in range(len(read)):
             if rng.random() < 0.05:
                 read[i] = rng.choice(b"ACGTN")
-        got, st = img.walk_fast(bytes(read), sat26=7, sat29=15)
+        got, _, st = imgs[0].walk_move(bytes(read), len_bits=3, dist_far=3)
         assert got == po.matching_statistics(bytes(read)).tolist()
-        used_slow += st["slow"]
-        used_scan += st["scan_iters"]
-    assert used_slow > 0 and used_scan > 0
+        _, ptr, _ = imgs[1].walk_move(bytes(read), len_bits=3, dist_far=3)
+        assert ptr == mo.matching_statistics(bytes(read))[1].tolist()
+        for key in tot:
+            tot[key] += st[key]
+    assert tot["slow"] > 0 and tot["norm_iters"] > 0 and tot["jump2"] > 0 and tot["fast"] > 0

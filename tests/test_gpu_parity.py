@@ -14,11 +14,11 @@ from conftest import MKINDEX, build_index, load_bin_reads
 
 pytestmark = pytest.mark.gpu
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")
-LANES = [1, 4, 8, 16, 32]  # 1 = thread-per-read PML fast path; MS has no 1-lane kernel
+LANES = [1, 4, 8, 16, 32]  # 1 = thread-per-read kernels over the move rows (PML and MS); others = cooperative kernel
 
 
 def ms_lanes(lanes):
-    return 0 if lanes == 1 else lanes
+    return lanes
 
 
 def oracle_batch(ref, mode, buf, off):
@@ -117,7 +117,7 @@ def test_classifier_stats(small_index, mode):
     buf, off = load_bin_reads(small_index["reads_bin"])
     idx = sp.pml_t(small_index["ref"]) if mode == "pml" else sp.ms_t(small_index["ref"])
     for bw, thr in ((50, 7), (150, 13), (400, 3)):
-        for lanes in ([1, 8] if mode == "pml" else [4]):
+        for lanes in [1, 8]:
             L, _, S = idx.query_host(buf, off, bin_width=bw, max_value_thr=thr, lanes=lanes)
             for r in range(len(off) - 1):
                 found, summ, above, below, nb = naive.classify_bins(L[int(off[r]):int(off[r + 1])].tolist(), bw, thr)
@@ -152,6 +152,13 @@ def test_device_api_with_torch_tensors(small_index):
         idx.query_device(d_reads, d_off, len(off) - 1, d_len, stream=s.cuda_stream)
     s.synchronize()
     assert np.array_equal(d_len.cpu().numpy().astype(np.uint64), Lo)
+    # narrow device output + device-side clamp counter
+    d_len8 = torch.zeros(len(buf), dtype=torch.uint8, device=dev)
+    d_sat = torch.zeros(1, dtype=torch.int64, device=dev)
+    idx.query_device(d_reads, d_off, len(off) - 1, d_len8, d_saturated=d_sat)
+    torch.cuda.synchronize()
+    assert int(d_sat.item()) == int(np.count_nonzero(Lo > 255))
+    assert np.array_equal(d_len8.cpu().numpy().astype(np.uint64), np.minimum(Lo, 255))
     with pytest.raises(sp.SpumoniError):  # alignment contract
         idx.query_device(d_reads[16:], d_off, len(off) - 1, d_len)
     assert sp.kernel_launches() > 0
@@ -238,19 +245,80 @@ def test_medium_scale_properties(tmp_path):
     assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
 
 
-def test_fast_path_saturation_fallbacks_on_gpu(small_index, tmp_path):
-    """Same inputs through the test-only library build whose 26/29-bit fields saturate at 7/15: every
-    fall-back of the thread-per-read kernel (slow step, absolute scan) runs and must stay bit-exact."""
+def test_move_rows_saturation_fallbacks_on_gpu(small_index, tmp_path):
+    """Same inputs through the test-only library build whose move-row fields are tiny (3-bit len/delta,
+    thresholds <= 4, jump distance < 3): every fall-back of the thread-per-read kernels (slow rows, generic
+    step from un-normalised states, far jumps) runs and must stay bit-exact, PML and MS."""
     import sys, textwrap
     buf, off = load_bin_reads(small_index["reads_bin"])
     Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
-    out = str(tmp_path / "L.npy")
+    Lmo, Pmo = oracle_batch(small_index["ref"], "ms", buf, off)
+    out = str(tmp_path / "out.npz")
     code = textwrap.dedent(f"""
         import numpy as np, spumoni_b200 as sp
         buf = np.fromfile({small_index["reads_bin"]!r}, dtype=np.uint8); off = np.fromfile({small_index["reads_bin"] + ".off"!r}, dtype=np.uint64)
         L, _, S = sp.pml_t({small_index["ref"]!r}).query_host(buf, off, lanes=1, bin_width=150, max_value_thr=9)
-        np.save({out!r}, L)
+        Lm, Pm, _ = sp.ms_t({small_index["ref"]!r}).query_host(buf, off, lanes=1)
+        np.savez({out!r}, L=L, Lm=Lm, Pm=Pm)
     """)
     env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     subprocess.check_call([sys.executable, "-c", code], env=env)
-    assert np.array_equal(np.load(out).astype(np.uint64), Lo)
+    got = np.load(out)
+    assert np.array_equal(got["L"].astype(np.uint64), Lo)
+    assert np.array_equal(got["Pm"], Pmo) and np.array_equal(got["Lm"].astype(np.uint64), Lmo)
+
+
+@pytest.mark.parametrize("mode", ["pml", "ms"])
+def test_narrow_length_outputs(small_index, mode):
+    """uint16 / uint8 lengths are bit-identical to uint32 when nothing is clamped; a value that does not
+    fit is reported (SPB_ERR_OVERFLOW + count), never silently wrapped."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    idx = sp.pml_t(small_index["ref"]) if mode == "pml" else sp.ms_t(small_index["ref"])
+    L4, P4, S4 = idx.query_host(buf, off, bin_width=150, max_value_thr=9)
+    L2, P2, S2 = idx.query_host(buf, off, bin_width=150, max_value_thr=9, length_bytes=2)
+    assert L2.dtype == np.uint16 and np.array_equal(L2, L4) and np.array_equal(S2, S4)
+    if mode == "ms":
+        assert np.array_equal(P2, P4)
+    over = int(np.count_nonzero(L4 > 255))
+    if over == 0:
+        L1, _, S1 = idx.query_host(buf, off, bin_width=150, max_value_thr=9, length_bytes=1)
+        assert L1.dtype == np.uint8 and np.array_equal(L1, L4) and np.array_equal(S1, S4)
+    # a read that matches the reference exactly for > 255 bases must overflow uint8 loudly
+    text = open(small_index["ref"]).read().split("\n")[1][:600].encode()
+    rb, ro = sp.pack_reads([text, b"ACGT"])
+    Lw, _, _ = idx.query_host(rb, ro)
+    assert int(Lw.max()) > 255
+    with pytest.raises(sp.SpumoniError) as ei:
+        idx.query_host(rb, ro, length_bytes=1)
+    assert ei.value.code == sp.ERR_OVERFLOW and ei.value.saturated == int(np.count_nonzero(Lw > 255))
+    out1 = np.zeros(len(rb), dtype=np.uint8)
+    try:
+        idx.query_host(rb, ro, length_bytes=1, out_lengths=out1)
+    except sp.SpumoniError:
+        pass
+    assert np.array_equal(out1, np.minimum(Lw, 255).astype(np.uint8))  # clamped, otherwise complete
+    # the cooperative kernels only write uint32
+    with pytest.raises(sp.SpumoniError):
+        idx.query_host(rb, ro, lanes=8, length_bytes=2)
+
+
+def test_unaligned_read_boundaries_narrow(small_index):
+    """Reads of every length 1..70 back to back: 16-value output words straddle read boundaries."""
+    rng = random.Random(3)
+    text = open(small_index["ref"]).read().split("\n")[1]
+    reads = []
+    for ln in range(1, 71):
+        s0 = rng.randint(0, len(text) - ln)
+        r = bytearray(text[s0:s0 + ln].encode())
+        if ln > 4 and rng.random() < 0.7:
+            r[rng.randrange(ln)] = rng.choice(b"ACGT")
+        reads.append(bytes(r))
+    buf, off = sp.pack_reads(reads)
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    Lmo, Pmo = oracle_batch(small_index["ref"], "ms", buf, off)
+    pml, ms = sp.pml_t(small_index["ref"]), sp.ms_t(small_index["ref"])
+    for w in (1, 2, 4):
+        L, _, _ = pml.query_host(buf, off, length_bytes=w)
+        assert np.array_equal(L.astype(np.uint64), Lo), w
+        Lm, Pm, _ = ms.query_host(buf, off, length_bytes=w)
+        assert np.array_equal(Lm.astype(np.uint64), Lmo) and np.array_equal(Pm, Pmo), w
