@@ -33,8 +33,12 @@ int fail(int code, const std::string& msg) {
             return fail(SPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
     } while (0)
 
-constexpr int kSlots = 3;                         // pipeline depth of the host entry points
-constexpr uint64_t kChunkBases = 32ull << 20;     // bases per pipelined sub-batch
+// Host entry points: the batch is cut into sub-batches that rotate over `n_slots` streams.  One read is one thread,
+// so a sub-batch of 1 kb reads only fills a fraction of the ~150 000 resident lanes: several sub-batches must be in
+// flight (copies of some overlapping the kernels of others) to keep both the SMs and the PCIe link busy.
+constexpr int kMaxSlots = 16;
+constexpr int kDefaultSlots = 8;                       // SPUMONI_B200_SLOTS
+constexpr uint64_t kDefaultChunkBases = 32ull << 20;   // SPUMONI_B200_CHUNK_MB (in Mi bases)
 constexpr int kCounters = 64;     // pairs of work counters, rotated per launch
 constexpr int kDefaultLanes = 4;  // cooperative kernel (indexes without fast symbols)
 
@@ -65,8 +69,10 @@ struct spb_index {
     int num_sms = 0;
     unsigned long long* d_counters = nullptr;
     uint32_t counter_next = 0;
-    uint32_t row_ld = 0;
-    Slot slots[kSlots];
+    uint32_t row_ld = 1;  // move rows allocate in L1 (the neighbour rows of a jump / normalisation hit there); SPUMONI_B200_ROW_LD
+    Slot slots[kMaxSlots];
+    int n_slots = kDefaultSlots;
+    uint64_t chunk_bases = kDefaultChunkBases;
 };
 
 namespace {
@@ -85,6 +91,8 @@ int ensure_device_state(spb_index* idx) {
         if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);  // a hint: failure is not an error
         cudaGetLastError();
         if (const char* e = std::getenv("SPUMONI_B200_ROW_LD")) idx->row_ld = (uint32_t)std::atoi(e);  // development knob
+        if (const char* e = std::getenv("SPUMONI_B200_SLOTS")) { int v = std::atoi(e); if (v >= 1 && v <= kMaxSlots) idx->n_slots = v; }
+        if (const char* e = std::getenv("SPUMONI_B200_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 4096) idx->chunk_bases = (uint64_t)v << 20; }
     }
     return SPB_OK;
 }
@@ -189,6 +197,8 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
     uint64_t total_sat = 0;
     uint64_t r0 = 0;
     int chunk = 0;
+    const int kSlots = idx->n_slots;
+    const uint64_t kChunkBases = idx->chunk_bases;
     while (r0 < n_reads) {
         // sub-batch [r0, r1): at least one read, up to kChunkBases bases
         uint64_t r1 = r0 + 1;
@@ -221,7 +231,7 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         r0 = r1;
         chunk++;
     }
-    for (int i = 0; i < kSlots; i++) {
+    for (int i = 0; i < kMaxSlots; i++) {
         Slot& s = idx->slots[i];
         if (!s.stream) continue;
         SPB_CUDA(cudaStreamSynchronize(s.stream));
@@ -354,7 +364,7 @@ void spb_index_close(spb_index* idx) {
     if (!idx) return;
     if (idx->device >= 0) {
         cudaSetDevice(idx->device);
-        for (int i = 0; i < kSlots; i++) {
+        for (int i = 0; i < kMaxSlots; i++) {
             if (idx->slots[i].stream) cudaStreamSynchronize(idx->slots[i].stream);
             free_slot(idx->slots[i]);
             if (idx->slots[i].stream) cudaStreamDestroy(idx->slots[i].stream);

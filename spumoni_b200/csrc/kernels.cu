@@ -323,14 +323,15 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
 // ==========================================================================================
 #define SPB_MV_THREADS 128
 #ifndef SPB_MV_MINB
-#define SPB_MV_MINB 10  /* 128-thread CTAs per SM (register cap 48) */
+#define SPB_MV_MINB 8  /* 128-thread CTAs per SM: 64 registers, no spills (at 10 the 48-register cap spills inside the loop) */
 #endif
 
 template <int LD>
 __device__ __forceinline__ uint4 ld_row(const uint4* p) {
     uint4 r;
     if (LD == 0) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (LD == 1) asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));  // 64-byte instead of 128-byte L2 fills
     return r;
 }
 
@@ -364,9 +365,9 @@ __device__ __noinline__ ThreadLoc locate_thread(const uint4* __restrict__ runs, 
 // One reference step in absolute coordinates (same statements as spb_walk_kernel's body) for a single
 // thread.  In: state (k, off) -- off may be un-normalised (>= len[k]) or SPB_MV_OFF_LAST --, byte c.
 // Out: the normalised new state; PML length / MS sample updated in place.
-struct SlowOut { uint32_t k, off; };
+struct SlowOut { uint32_t k, off, length; uint64_t sample; };
 template <bool MS>
-__device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint32_t k, uint32_t off, uint32_t& length, uint64_t& sample) {
+__device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint32_t k, uint32_t off, uint32_t length, uint64_t sample) {
     const uint4* __restrict__ runs = p.runs;
     const uint64_t R = p.R, n = p.n;
     const uint4 ct = reinterpret_cast<const uint4*>(p.chartab)[c];
@@ -407,6 +408,8 @@ __device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint3
         w0 = (down && cr.z > 0) ? cr.z - 1 : cr.z;
     }
     SlowOut o;
+    o.length = length;
+    o.sample = sample;
     if (npos >= n) {
         o.k = (uint32_t)R;
         o.off = 0;
@@ -425,6 +428,8 @@ struct OutWord {
     static constexpr uint32_t VMAX = OW == 4 ? 0xFFFFFFFFu : (OW == 2 ? 0xFFFFu : 0xFFu);
     uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
     __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
+    __device__ __forceinline__ uint4 as_uint4() const { return make_uint4(w0, w1, w2, w3); }
+    __device__ __forceinline__ void from_uint4(const uint4& v) { w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w; }
     __device__ __forceinline__ void put(uint32_t slot, uint32_t v) {
         const uint32_t word = (slot * OW) >> 2, sh = ((slot * OW) & 3u) * 8u;
         const uint32_t bits = OW == 4 ? v : (v << sh);
@@ -455,6 +460,52 @@ __device__ __forceinline__ void flush_word(void* out, const OutWord<OW>& b, uint
     }
 }
 
+// ---- per-thread staging of the read and output streams in shared memory -----------------------
+// A lane consumes one read byte and produces one value per step, so a 128-byte line of either stream
+// stays "live" for > 100 steps of > 100 000 resident lanes: left to the L2, these half-used lines evict
+// the move rows (measured: tools/gather_bench2.cu, profiles/r1_gather_bench2.txt).  Each lane therefore
+// moves SPB_STAGE bytes at a time: reads are fetched as whole 64-byte blocks (evict-first, no L1) into
+// shared memory, outputs are collected there and written as full 32-byte sectors.  Chunk j (16 bytes) of
+// lane x lives at [j * SPB_MV_THREADS + x]: conflict-free for 16-byte lane accesses.
+#ifndef SPB_STAGE
+#define SPB_STAGE 64
+#endif
+#define SPB_STAGE_CH (SPB_STAGE / 16)
+#ifndef SPB_STAGE_RD
+#define SPB_STAGE_RD 1   /* development switches: 0 = fetch the read 8 bytes at a time straight from global memory */
+#endif
+#ifndef SPB_STAGE_WR
+#define SPB_STAGE_WR 1   /* 0 = write every 16-byte output word as soon as it is complete */
+#endif
+#ifndef SPB_CARVEOUT
+#define SPB_CARVEOUT 0   /* 0 = leave the L1 / shared memory split to the driver (measured best: the L1 serves the
+                            neighbour-row loads; forcing the maximum shared-memory carve-out halves the throughput);
+                            1 = maximum shared memory; other values = percent */
+#endif
+
+// one whole 32-byte sector per instruction (sm_100 256-bit load), evict-first in L2, not kept in L1
+__device__ __forceinline__ void ld_stream32(const void* p, uint4& a, uint4& b) {
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+// (re)fill the lane's staged block of the read buffer: the SPB_STAGE-aligned block containing byte gi
+__device__ __forceinline__ void stage_reads(uint4* s_rd, const uint8_t* reads, uint64_t gi) {
+    const uint8_t* src = reads + (gi & ~(uint64_t)(SPB_STAGE - 1));
+    uint4 v[SPB_STAGE_CH];
+#pragma unroll
+    for (int j = 0; j < SPB_STAGE_CH; j += 2) ld_stream32(src + 16 * j, v[j], v[j + 1]);
+#pragma unroll
+    for (int j = 0; j < SPB_STAGE_CH; j++) s_rd[j * SPB_MV_THREADS + threadIdx.x] = v[j];
+}
+__device__ __forceinline__ uint64_t ld_read8(const uint8_t* p) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint64_t staged_chunk(const uint4* s_rd, uint64_t gi) {  // the 8 bytes containing byte gi
+    return reinterpret_cast<const uint64_t*>(&s_rd[((gi & (SPB_STAGE - 1)) >> 4) * SPB_MV_THREADS + threadIdx.x])[(gi >> 3) & 1];
+}
+
 struct BinState {
     uint64_t bound = 0, sum_max = 0;
     uint32_t bin_max = 0, above = 0, below = 0;
@@ -465,6 +516,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
+    __shared__ uint4 s_rd[SPB_STAGE_RD ? SPB_STAGE_CH * SPB_MV_THREADS : 1];   // staged read bytes, see stage_reads
+    __shared__ uint4 s_out[SPB_STAGE_WR ? SPB_STAGE_CH * SPB_MV_THREADS : 1];  // staged output words (lengths, or MS pointers)
     for (int i = threadIdx.x; i < 256; i += SPB_MV_THREADS) {
         const SpbCharTab t = p.chartab[i];
         s_fid[i] = (uint8_t)(t.cidx == 0xFFFFFFFFu ? 5u : t.dest_f);
@@ -503,7 +556,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
             gi = end - 1;
             k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0; mode = 0;  // empty string: pos = n-1
             if (MS) sample = p.last_run_sample;
-            chunk = *reinterpret_cast<const uint64_t*>(p.reads + (gi & ~7ull));
+            if (SPB_STAGE_RD) { stage_reads(s_rd, p.reads, gi); chunk = staged_chunk(s_rd, gi); }
+            else chunk = ld_read8(p.reads + (gi & ~7ull));
             ob.clear();
             have = true;
             if (do_stats) {
@@ -567,19 +621,39 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
             }
         }
         if (slow) {  // ---- generic step in absolute coordinates
-            const SlowOut so = slow_step<MS>(p, c, k, off, length, sample);
-            k = so.k; off = so.off;
+            const SlowOut so = slow_step<MS>(p, c, k, off, length, sample);  // by value: no state lives in local memory
+            k = so.k; off = so.off; length = so.length;
+            if (MS) sample = so.sample;
             emit = true;
         }
 
         if (emit) {
             const bool last = (gi == base);
             if (MS) {
-                if (gi & 1ull) {
-                    if (last) p.pointers[gi] = sample; else pbuf = sample;
-                } else if (gi + 1 < end) {
-                    asm volatile("st.global.v2.u64 [%0], {%1,%2};" ::"l"(p.pointers + gi), "l"(sample), "l"(pbuf) : "memory");
-                } else p.pointers[gi] = sample;
+                // pointers: two per 16-byte word, SPB_STAGE_CH words per staged block
+                if (gi & 1ull) pbuf = sample;
+                if (!(gi & 1ull) || last) {
+                    const uint64_t g = gi & ~1ull;  // first pointer index of this word
+                    const uint32_t seg = SPB_STAGE_WR ? ((uint32_t)(g >> 1) & (SPB_STAGE_CH - 1)) : 0u;
+                    s_out[seg * SPB_MV_THREADS * (SPB_STAGE_WR ? 1 : 0) + (SPB_STAGE_WR ? threadIdx.x : 0)] = make_uint4((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)pbuf, (uint32_t)(pbuf >> 32));
+                    if (!SPB_STAGE_WR) {
+                        if (g >= gi && g + 2 <= end)
+                            asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(p.pointers + g), "l"(sample), "l"(pbuf) : "memory");
+                        else if (g >= gi) p.pointers[g] = sample;
+                        else p.pointers[g + 1] = pbuf;
+                    } else if (seg == 0 || last) {
+#pragma unroll
+                        for (uint32_t j = 0; j < SPB_STAGE_CH; j++) {
+                            const uint64_t gj = g + 2ull * (j - seg);
+                            if (j < seg || gj >= end) continue;
+                            const uint4 w = s_out[j * SPB_MV_THREADS + threadIdx.x];
+                            if (gj >= gi && gj + 2 <= end)
+                                asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p.pointers + gj), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+                            else if (gj >= gi) p.pointers[gj] = (uint64_t)w.x | ((uint64_t)w.y << 32);       // word cut by the read's end
+                            else p.pointers[gj + 1] = (uint64_t)w.z | ((uint64_t)w.w << 32);                  // word cut by the read's start
+                        }
+                    }
+                }
             } else {
                 constexpr uint32_t VPW = OutWord<OW>::VPW;
                 const uint32_t slot = (uint32_t)gi & (VPW - 1);
@@ -587,8 +661,25 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                 if (OW < 4 && v > OutWord<OW>::VMAX) { v = OutWord<OW>::VMAX; nsat++; }
                 ob.put(slot, v);
                 if (slot == 0 || last) {
-                    flush_word<OW>(p.lengths, ob, gi & ~(uint64_t)(VPW - 1), gi, end);
+                    const uint64_t g = gi & ~(uint64_t)(VPW - 1);  // first value index of this word
+                    const uint32_t seg = (uint32_t)(g / VPW) & (SPB_STAGE_CH - 1);
+                    if (!SPB_STAGE_WR) {
+                        flush_word<OW>(p.lengths, ob, g, gi, end);
+                        ob.clear();
+                    } else {
+                    s_out[seg * SPB_MV_THREADS + threadIdx.x] = ob.as_uint4();
                     ob.clear();
+                    }
+                    if (SPB_STAGE_WR && (seg == 0 || last)) {  // staged block complete (walking downwards), or the read ends inside it
+#pragma unroll
+                        for (uint32_t j = 0; j < SPB_STAGE_CH; j++) {
+                            const uint64_t gj = g + (uint64_t)VPW * (j - seg);
+                            if (j < seg || gj >= end) continue;
+                            OutWord<OW> w;
+                            w.from_uint4(s_out[j * SPB_MV_THREADS + threadIdx.x]);
+                            flush_word<OW>(p.lengths, w, gj, gi, end);
+                        }
+                    }
                 }
                 if (do_stats) {
                     if (gi < bs.bound) {  // left the bin [bound, ...): close it
@@ -610,7 +701,12 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                 have = false;
             } else {
                 --gi;
-                if ((gi & 7ull) == 7ull) chunk = *reinterpret_cast<const uint64_t*>(p.reads + (gi & ~7ull));
+                if ((gi & 7ull) == 7ull) {
+                    if (SPB_STAGE_RD) {
+                        if ((gi & (SPB_STAGE - 1)) == SPB_STAGE - 1) stage_reads(s_rd, p.reads, gi);
+                        chunk = staged_chunk(s_rd, gi);
+                    } else chunk = ld_read8(p.reads + (gi & ~7ull));
+                }
             }
         }
     }
@@ -709,7 +805,10 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const Wa
 template <typename K>
 static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms, cudaStream_t stream) {
     int occ = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SPB_MV_THREADS, 0);
+    cudaError_t e = cudaSuccess;
+    if (SPB_CARVEOUT) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SPB_CARVEOUT == 1 ? (int)cudaSharedmemCarveoutMaxShared : SPB_CARVEOUT);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SPB_MV_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     // persistent grid: a whole number of CTAs per SM; reads are pulled from the work counter
@@ -757,15 +856,17 @@ cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cu
         if (!p.rows || (ms && !p.msamp)) return cudaErrorInvalidValue;
         cudaError_t e;
         if (ms) {
-            e = p.row_ld ? launch_persistent(spb_move_kernel<true, false, 4, 1>, p, num_sms, stream)
-                         : launch_persistent(spb_move_kernel<true, false, 4, 0>, p, num_sms, stream);
+            e = p.row_ld == 2 ? launch_persistent(spb_move_kernel<true, false, 4, 2>, p, num_sms, stream)
+                : p.row_ld == 1 ? launch_persistent(spb_move_kernel<true, false, 4, 1>, p, num_sms, stream)
+                                : launch_persistent(spb_move_kernel<true, false, 4, 0>, p, num_sms, stream);
             if (e != cudaSuccess) return e;
             e = stats ? launch_ms_lengths<true>(p, num_sms, stream) : launch_ms_lengths<false>(p, num_sms, stream);
             if (launches) *launches = 2;
             return e;
         }
         if (launches) *launches = 1;
-        if (p.row_ld) return stats ? launch_move_pml<true, 1>(p, num_sms, stream) : launch_move_pml<false, 1>(p, num_sms, stream);
+        if (p.row_ld == 2) return stats ? launch_move_pml<true, 2>(p, num_sms, stream) : launch_move_pml<false, 2>(p, num_sms, stream);
+        if (p.row_ld == 1) return stats ? launch_move_pml<true, 1>(p, num_sms, stream) : launch_move_pml<false, 1>(p, num_sms, stream);
         return stats ? launch_move_pml<true, 0>(p, num_sms, stream) : launch_move_pml<false, 0>(p, num_sms, stream);
     }
     if (p.out_width != 4) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths only
