@@ -28,8 +28,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 MKINDEX = os.path.join(ROOT, "tools", "bin", "spumoni_mkindex")
 
-BYTES_PER_BASE_PML = 69  # 1 B read + 4 B length + 2 x 32 B index sectors
-METRIC = "bases/sec PML-mode classification"
+BYTES_PER_BASE = {"pml": 69,   # 1 B read + 4 B length + 2 x 32 B index sectors
+                  "ms": 117}   # + 8 B pointer + 8 B SA sample + 32 B text sector
+METRICS = {"pml": "bases/sec PML-mode classification", "ms": "bases/sec MS-mode (-M) matching statistics"}
+METRIC = METRICS["pml"]
 
 WORKLOADS = {
     # name: (genome args, reads per rank, read length, read args)
@@ -56,17 +58,18 @@ def cache_dir(name: str) -> str:
     return d
 
 
-def ensure_index(name: str) -> str:
+def ensure_index(name: str, mode: str = "pml") -> str:
     """Untimed setup: synthetic reference + `spumoni build` stand-in (tools/). Returns ref_file (<prefix>.fa)."""
     d = cache_dir(name)
     ref = os.path.join(d, "idx.fa")
-    if os.path.exists(ref + ".thrbv.spumoni") and os.path.exists(os.path.join(d, "ok")):
+    ext = ".thrbv.spumoni" if mode == "pml" else ".thrbv.ms"
+    if os.path.exists(ref + ext) and os.path.exists(os.path.join(d, "ok_" + mode)):
         return ref
     t0 = time.time()
     subprocess.check_call([MKINDEX, "genome", "--out", os.path.join(d, "raw.fa")] + WORKLOADS[name]["genome"], stdout=subprocess.DEVNULL)
-    subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--pml"], stdout=subprocess.DEVNULL)
+    subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--" + mode], stdout=subprocess.DEVNULL)
     os.remove(os.path.join(d, "raw.fa"))
-    open(os.path.join(d, "ok"), "w").write("ok")
+    open(os.path.join(d, "ok_" + mode), "w").write("ok")
     log(f"built index {name} in {time.time() - t0:.1f} s")
     return ref
 
@@ -144,12 +147,13 @@ def run_reference(args, name):
     if rank != 0:
         return
     import oracle
-    ref = ensure_index(name)
+    mode = args.mode
+    ref = ensure_index(name, mode)
     buf, off = ensure_reads(name, ref, seed=4)
     cores = os.cpu_count() or 1
     w = WORKLOADS[name]
-    sample_reads = min(len(off) - 1, max(200, 1000 * cores * 1000 // w["read_len"]))
-    idx = oracle.OracleIndex(ref, "pml")
+    sample_reads = min(len(off) - 1, max(200, (1000 if mode == "pml" else 400) * cores * 1000 // w["read_len"]))
+    idx = oracle.OracleIndex(ref, mode)
     sb, so = buf[: int(off[sample_reads])], off[: sample_reads + 1]
     for _ in range(args.warmup):
         idx.query_batch(sb[: int(so[max(1, sample_reads // 10)])], so[: max(1, sample_reads // 10) + 1], threads=cores, want_output=False)
@@ -159,10 +163,10 @@ def run_reference(args, name):
         secs.append(s)
     total = sum(secs)
     value = int(so[-1]) * args.steps / total
-    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
+    out = {"impl": "reference", "metric": METRICS[mode], "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-           "config": {"workload": w["desc"], "sample": f"first {sample_reads} reads ({int(so[-1])} bases) per step"},
+           "config": {"workload": w["desc"].replace("PML", mode.upper()), "sample": f"first {sample_reads} reads ({int(so[-1])} bases) per step"},
            "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
                             "sample": f"first {sample_reads} reads of the workload, {args.steps} steps, in-memory, OpenMP dynamic over reads"},
            "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -178,6 +182,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=0, help="lanes per read (tuning; 0 = library default)")
     ap.add_argument("--length-bytes", type=int, default=1, choices=[1, 2, 4],
                     help="element size of the lengths output (1/2 are checked lossless: a clamped value fails the step and it is redone wider)")
+    ap.add_argument("--mode", default="pml", choices=["pml", "ms"], help="pml = the headline metric (BASELINE configs[1]); ms = configs[2], a secondary line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra 4-byte-lengths measurement")
     args = ap.parse_args()
@@ -211,15 +216,17 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- untimed setup: index (rank 0 builds + parses, NCCL broadcast), reads per rank
+    mode = args.mode
+    MODE = sp.MODE_PML if mode == "pml" else sp.MODE_MS
     if rank == 0:
-        ref = ensure_index(name)
+        ref = ensure_index(name, mode)
     barrier()
     ref = os.path.join(cache_dir(name), "idx.fa")
     t0 = time.time()
     if world > 1:
-        idx = broadcast_index(sp.Index.open(ref, sp.MODE_PML) if rank == 0 else None, device=local, src=0)
+        idx = broadcast_index(sp.Index.open(ref, MODE) if rank == 0 else None, device=local, src=0)
     else:
-        idx = sp.Index.open(ref, sp.MODE_PML).to_device(local)
+        idx = sp.Index.open(ref, MODE).to_device(local)
     n, r = idx.get_bwt_stats()
     log(f"rank {rank}: index resident (n={n}, r={r}) in {time.time() - t0:.1f} s")
     buf, off = ensure_reads(name, ref, seed=4 + rank)
@@ -241,14 +248,17 @@ def main():
         d_len = torch.zeros(n_bases, dtype=TDT[width], device=dev)
         d_sat = torch.zeros(1, dtype=torch.int64, device=dev)
         np_len = h_len.numpy().view(NDT[width])
+        d_ptr = torch.zeros(n_bases, dtype=torch.int64, device=dev) if mode == "ms" else None
+        h_ptr = torch.empty(n_bases, dtype=torch.int64).pin_memory() if mode == "ms" else None
+        np_ptr = h_ptr.numpy().view(np.uint64) if mode == "ms" else None
 
         def step_device():
-            idx.query_device(d_reads, d_off, n_reads, d_len, lanes=args.lanes, stream=stream.cuda_stream, d_saturated=d_sat)
+            idx.query_device(d_reads, d_off, n_reads, d_len, d_pointers=d_ptr, lanes=args.lanes, stream=stream.cuda_stream, d_saturated=d_sat)
 
         def step_host():
             # the call a user makes: host buffers in, host buffers out (a clamped narrow value makes the call fail)
             try:
-                idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len, length_bytes=width)
+                idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len, out_pointers=np_ptr, length_bytes=width)
             except sp.SpumoniError as e:
                 raise SystemExit(f"bench.py: {e}; rerun with --length-bytes 2" if e.code == sp.ERR_OVERFLOW else f"bench.py: {e}")
 
@@ -283,20 +293,22 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         same = bool(np.array_equal(np_len, d_len.cpu().numpy().view(NDT[width])))
+        if mode == "ms":
+            same = same and bool(np.array_equal(np_ptr, d_ptr.cpu().numpy().view(np.uint64)))
         return {"value": n_bases * world * args.steps / (total_ms_max / 1e3), "ms_per_step": total_ms_max / args.steps,
                 "kernel_ms": sum(kern_ms) / len(kern_ms), "launches": int(launches),
                 "e2e": n_bases * world * args.steps / float(t.item()), "same": same,
-                "d2h_bytes_per_step": width * n_bases}, np_len
+                "d2h_bytes_per_step": (width + (8 if mode == "ms" else 0)) * n_bases}, np_len, np_ptr
 
     # ---------------- timed region (clock sampling covers the headline measurement)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    main_m, np_len = measure(args.length_bytes)
+    main_m, np_len, np_ptr = measure(args.length_bytes)
     clocks = sampler.stop() if rank == 0 else None
     other = {}
     if args.length_bytes != 4 and not args.no_variants:
-        other["u32"], _ = measure(4)
+        other["u32"], _, _ = measure(4)
     value, total_ms_max, kavg_ms, launches = main_m["value"], main_m["ms_per_step"] * args.steps, main_m["kernel_ms"], main_m["launches"]
     e2e_value, same = main_m["e2e"], main_m["same"]
 
@@ -305,11 +317,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         cores = os.cpu_count() or 1
-        sample_reads = min(n_reads, max(200, 2500 * cores * 1000 // w["read_len"]))
-        o = oracle.OracleIndex(ref, "pml")
-        sec, Lo, _ = o.query_batch(buf[: int(off[sample_reads])], off[: sample_reads + 1], threads=cores)
+        sample_reads = min(n_reads, max(200, (2500 if mode == "pml" else 800) * cores * 1000 // w["read_len"]))
+        o = oracle.OracleIndex(ref, mode)
+        sec, Lo, Po = o.query_batch(buf[: int(off[sample_reads])], off[: sample_reads + 1], threads=cores)
         sb = int(off[sample_reads])
         mism = int(np.count_nonzero(Lo != np_len[:sb].astype(np.uint64)))
+        if mode == "ms":
+            mism += int(np.count_nonzero(Po != np_ptr[:sb]))
         parity = {"reads_checked": sample_reads, "bases_checked": sb, "mismatches": mism, "host_equals_device_path": same}
         cpu_baseline = {"value": sb / sec, "unit": "bases/s", "cores": cores, "kind": "port",
                         "sample": f"first {sample_reads} reads ({sb} bases) of the same workload, in-memory, OpenMP over reads"}
@@ -318,22 +332,22 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        achieved = BYTES_PER_BASE_PML * n_bases / (kavg_ms / 1e3) / 1e9
+        achieved = BYTES_PER_BASE[mode] * n_bases / (kavg_ms / 1e3) / 1e9
         out = {
-            "metric": METRIC, "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRICS[mode], "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64", "data": "synthetic",
-            "config": {"workload": w["desc"], "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
+            "config": {"workload": w["desc"].replace("PML", mode.upper()), "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
                        "lanes_per_read": args.lanes or 1, "length_bytes": args.length_bytes,
                        "l2": "inputs (1 GB reads per step) and outputs (1-4 GB lengths) larger than L2; no explicit flush",
                        "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1), "d2h_bytes_per_step": main_m["d2h_bytes_per_step"],
-                    "api": f"spb_pml_query_host, pinned host buffers, uint{8 * args.length_bytes} lengths (lossless on this workload: 0 clamped values)"},
+                    "api": f"spb_{mode}_query_host, pinned host buffers, uint{8 * args.length_bytes} lengths (lossless on this workload: 0 clamped values)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "spb_move_kernel<PML>" if (args.lanes or 1) == 1 else "spb_walk_kernel<G,false>", "kernel_ms": kavg_ms,
-                         "bytes_per_base": BYTES_PER_BASE_PML, "peak_source": peak_src},
+                         "traffic": None, "kernel": ("spb_move_kernel<PML>" if mode == "pml" else "spb_move_kernel<MS> + spb_ms_lengths_kernel") if (args.lanes or 1) == 1 else "spb_walk_kernel<G>", "kernel_ms": kavg_ms,
+                         "bytes_per_base": BYTES_PER_BASE[mode], "peak_source": peak_src},
             "cpu_baseline": cpu_baseline, "parity": parity,
             "variants": {k: {"value": v["value"], "kernel_ms": v["kernel_ms"], "e2e": v["e2e"], "d2h_bytes_per_step": v["d2h_bytes_per_step"]} for k, v in other.items()},
         }

@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define SPB_FLAT_MAGIC 0x3030324250535F42ULL /* "B_SPB200" */
-#define SPB_FLAT_VERSION 4u
+#define SPB_FLAT_VERSION 5u
 #define SPB_RUN_PAD 64u  /* sentinel + padding run records past R (start = 2^40-1) */
 #define SPB_POS_MAX 0xFFFFFFFFFFULL
 
@@ -93,6 +93,26 @@ struct SpbCharTab {      // per byte value c; 16 bytes
 #define SPB_MV_ROW_PAD 16u
 struct SpbMoveRow { uint32_t x, y, z, w; };
 
+// ---- compact move rows (8 bytes per run) --------------------------------------------------------
+// The walk is bound by how many DRAM lines it fetches per step, i.e. by the L2 hit rate of the row table
+// (a B200 keeps ~60 MB of a randomly gathered table resident: tools/gather_bench*, profiles/).  Indexes
+// with fewer than 2^24 runs therefore get rows half the size; the semantics are those of SpbMoveRow:
+//   bits  0-23 dest        24-31 len (1..SPB_MV8_MAX)        32-39 delta (0..SPB_MV8_MAX)
+//   bits 40-42 fid         43    slow
+//   bits 44-49 threshold class of jump slot 0/1/2: 0 never down | 1 always down | 2 down iff off < T | 3 generic step
+//   bits 50-57 T           the one in-run threshold of this row (two slots with different T: the second is class 3)
+//   bits 58-63 distance class of jump slot 0/1/2: 0 no later c-run | 1 next row | 2 row k+2 | 3 search heads4 from k+3
+// heads4: one nibble per run (fid, SPB_SYM_SLOW for other heads and for padding), 16 runs per 64-bit word; the
+// kernel finds the next run headed by c with a carry-free zero-nibble test, SPB_MV8_SCAN_WORDS words at most.
+#ifndef SPB_MV8_MAX
+#define SPB_MV8_MAX 255u        /* the test build lowers these limits to exercise the fall-backs */
+#endif
+#ifndef SPB_MV8_SCAN_WORDS
+#define SPB_MV8_SCAN_WORDS 4u
+#endif
+#define SPB_MV8_MAX_RUNS (1ull << 24)
+#define SPB_MV8_HEADS_PAD 128u  /* padding nibbles past R (a multiple of 16, > 16 * SPB_MV8_SCAN_WORDS + 3) */
+
 struct SpbFlatHeader {
     uint64_t magic;
     uint32_t version;
@@ -113,6 +133,7 @@ struct SpbFlatHeader {
     uint32_t mv_end_off[4];
     uint32_t pad0[3];
     uint64_t mv_end_sl[4];       // MS: samples_last of the last c-run
+    uint64_t off_mrows8, off_heads4;  // compact rows ((R + SPB_MV_ROW_PAD) * 8 bytes) + head nibbles; 0 if not applicable (then off_mrows != 0)
     uint64_t F[256];
     SpbCharTab chartab[256];
 };

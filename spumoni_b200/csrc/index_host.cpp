@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <stdexcept>
@@ -442,9 +443,19 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         if (!num_fast) for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
     }
     h.num_fast = num_fast;
+    // row width: 8-byte rows whenever run indices fit 24 bits (SPUMONI_B200_ROWS=16 forces the wide rows, e.g. for tests)
+    bool rows8 = num_fast && R + SPB_MV_ROW_PAD < SPB_MV8_MAX_RUNS;
+    if (const char* e = std::getenv("SPUMONI_B200_ROWS")) if (std::atoi(e) == 16) rows8 = false;
     if (num_fast) {
-        h.off_mrows = off;
-        off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow), 256);
+        if (rows8) {
+            h.off_mrows8 = off;
+            off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(uint64_t), 256);
+            h.off_heads4 = off;
+            off = align_up(off + ((size_t)R + SPB_MV8_HEADS_PAD + 15) / 16 * sizeof(uint64_t), 256);
+        } else {
+            h.off_mrows = off;
+            off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow), 256);
+        }
         if (ms) {
             h.off_msamp = off;
             off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbCharSamp), 256);
@@ -544,7 +555,8 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     }
     if (ms) std::memcpy(blob.data() + h.off_text, text.data(), text.size());
     if (num_fast) {
-        SpbMoveRow* rows = reinterpret_cast<SpbMoveRow*>(blob.data() + h.off_mrows);
+        SpbMoveRow* rows = rows8 ? nullptr : reinterpret_cast<SpbMoveRow*>(blob.data() + h.off_mrows);
+        uint64_t* rows_c = rows8 ? reinterpret_cast<uint64_t*>(blob.data() + h.off_mrows8) : nullptr;
         SpbCharSamp* msamp = ms ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
         SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
         // next run (strictly after k) headed by each fast symbol, by a backward sweep
@@ -583,6 +595,24 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                     dist3[slot] = dd < SPB_MV_DIST_FAR ? (uint32_t)dd : SPB_MV_DIST_FAR;
                 }
             }
+            if (rows8) {
+                slow = hk >= SPB_SYM_SLOW || len_k > SPB_MV8_MAX || delta > SPB_MV8_MAX;
+                uint64_t cls = 0, dcls = 0, T = 0;
+                for (uint32_t slot = 0; slot < 3 && hk < SPB_SYM_SLOW; slot++) {
+                    const uint32_t v = thr3[slot];  // same derivation as the wide rows: 0 | value | SLOW | ALWAYS
+                    uint64_t c3;
+                    if (v == 0) c3 = 0;
+                    else if (v == SPB_MV_THR_ALWAYS) c3 = 1;
+                    else if (v == SPB_MV_THR_SLOW || v > SPB_MV8_MAX || (T != 0 && T != v)) c3 = 3;
+                    else { c3 = 2; T = v; }
+                    cls |= c3 << (2 * slot);
+                    const uint32_t dd = dist3[slot];
+                    dcls |= (uint64_t)(dd < 3 ? dd : 3u) << (2 * slot);
+                }
+                rows_c[k] = (uint64_t)de | ((uint64_t)std::min<uint64_t>(len_k, SPB_MV8_MAX) << 24) | ((uint64_t)std::min<uint64_t>(delta, SPB_MV8_MAX) << 32) |
+                            ((uint64_t)(hk > SPB_SYM_SLOW ? SPB_SYM_SLOW : hk) << 40) | ((uint64_t)(slow ? 1 : 0) << 43) | (cls << 44) | (T << 50) | (dcls << 58);
+                continue;
+            }
             SpbMoveRow r;
             r.x = (uint32_t)de;
             r.y = (uint32_t)(len_k > SPB_MV_LEN_MASK ? SPB_MV_LEN_MASK : len_k) | (thr3[0] << 20);
@@ -591,7 +621,22 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                   ((slow ? 1u : 0u) << 30);
             rows[k] = r;
         }
-        for (uint64_t k = R; k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
+        if (rows8) {
+            for (uint64_t k = R; k < R + SPB_MV_ROW_PAD; k++)  // row R = "pos == n": generic step only
+                rows_c[k] = (uint64_t)R | (1ull << 24) | ((uint64_t)SPB_SYM_SLOW << 40) | (1ull << 43);
+            uint64_t* hw = reinterpret_cast<uint64_t*>(blob.data() + h.off_heads4);
+            const uint64_t words = (R + SPB_MV8_HEADS_PAD + 15) / 16;
+            for (uint64_t w = 0; w < words; w++) {
+                uint64_t v = 0;
+                for (uint64_t t = 0; t < 16; t++) {
+                    const uint64_t k = w * 16 + t;
+                    const uint64_t f = k < R ? std::min<uint32_t>(fid[d.heads[(size_t)k]], SPB_SYM_SLOW) : SPB_SYM_SLOW;
+                    v |= f << (4 * t);
+                }
+                hw[w] = v;
+            }
+        }
+        for (uint64_t k = R; !rows8 && k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
             SpbMoveRow r;
             r.x = (uint32_t)R; r.y = 1; r.z = 0;
             r.w = (SPB_SYM_SLOW << 27) | (1u << 30);

@@ -330,8 +330,15 @@ template <int LD>
 __device__ __forceinline__ uint4 ld_row(const uint4* p) {
     uint4 r;
     if (LD == 0) asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else if (LD == 1) asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    else asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));  // 64-byte instead of 128-byte L2 fills
+    else asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <int LD>
+__device__ __forceinline__ uint64_t ld_row8(const uint64_t* p) {
+    uint64_t r;
+    if (LD == 0) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
+    else asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
     return r;
 }
 
@@ -511,7 +518,7 @@ struct BinState {
     uint32_t bin_max = 0, above = 0, below = 0;
 };
 
-template <bool MS, bool STATS, int OW, int LD>
+template <bool MS, bool STATS, int OW, int LD, bool ROW8>
 __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
@@ -536,7 +543,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
     bool have = false, down = false;
     unsigned long long r = 0;
     uint64_t base = 0, end = 0, gi = 0, chunk = 0;
-    uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2
+    uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2, 2 = SCAN (compact rows: search heads4)
+    uint32_t sk = 0, scan_left = 0, want = 0;
     uint64_t sample = 0, pbuf = 0;
     uint32_t nsat = 0;
     OutWord<OW> ob;
@@ -569,10 +577,70 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
         }
 
         // ---- one row load per lane per iteration
-        const uint4 rec = ld_row<LD>(rows + (mode ? k2 : k));
         uint32_t c = (uint32_t)(chunk >> ((gi & 7) * 8)) & 0xFFu;
         if (upper && c >= 'a' && c <= 'z') c -= 32;
         bool slow = false, emit = false;
+        if (ROW8) {
+            const uint64_t* addr = mode == 2 ? p.heads4 + (sk >> 4) : p.rows8 + (mode ? k2 : k);
+            const uint64_t v = ld_row8<LD>(addr);
+            if (mode == 0) {
+                if ((v >> 43) & 1ull) slow = true;
+                else {
+                    const uint32_t len = (uint32_t)(v >> 24) & 0xFFu;
+                    if (off == SPB_MV_OFF_LAST) off = len - 1;
+                    if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
+                    const uint32_t h = (uint32_t)(v >> 40) & 7u, s = s_fid[c];
+                    if (s >= SPB_SYM_SLOW) slow = true;
+                    else if (s == h) {  // bwt[pos] == c (:250 / :582)
+                        length++;
+                        if (MS) sample--;
+                        off += (uint32_t)(v >> 32) & 0xFFu;
+                        k = (uint32_t)v & 0xFFFFFFu;
+                        emit = true;
+                    } else {  // threshold jump (:251-279 / :583-616)
+                        const uint32_t slot = s - (s > h ? 1u : 0u);
+                        const uint32_t cls = (uint32_t)(v >> (44 + 2 * slot)) & 3u, dc = (uint32_t)(v >> (58 + 2 * slot)) & 3u;
+                        if (cls == 3) slow = true;
+                        else if (dc == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
+                            k = s_end_k[s]; off = s_end_off[s];
+                            length = 0;
+                            if (MS) sample = s_end_sl[s];
+                            emit = true;
+                        } else {
+                            down = (cls == 1) || (cls == 2 && off < ((uint32_t)(v >> 50) & 0xFFu));
+                            if (dc < 3) { k2 = k + dc; mode = 1; }
+                            else { sk = k + 3; scan_left = SPB_MV8_SCAN_WORDS; want = s; mode = 2; }
+                        }
+                    }
+                }
+            } else if (mode == 2) {
+                // v = head nibbles of runs (sk & ~15) .. +15: first nibble == want at or after sk (carry-free zero-nibble test)
+                uint64_t x = v ^ (0x1111111111111111ull * want);
+                x |= x >> 1;
+                x |= x >> 2;
+                const uint64_t z = ~x & 0x1111111111111111ull & (~0ull << (4 * (sk & 15u)));
+                if (z) { k2 = (sk & ~15u) + (uint32_t)((__ffsll((long long)z) - 1) >> 2); mode = 1; }
+                else if (--scan_left == 0) { mode = 0; slow = true; }
+                else sk = (sk & ~15u) + 16;
+                if (!slow) continue;
+            } else {
+                mode = 0;
+                if ((v >> 43) & 1ull) slow = true;  // landing state not encodable: redo the step from (k, off)
+                else {
+                    const uint32_t d2 = (uint32_t)(v >> 32) & 0xFFu, de = (uint32_t)v & 0xFFFFFFu;
+                    if (MS) {
+                        const uint4 sm = ldg_nc16(p.msamp + k2);
+                        sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                    }
+                    if (!down) { k = de; off = d2; }
+                    else if (d2) { k = de; off = d2 - 1; }
+                    else { k = de - 1; off = SPB_MV_OFF_LAST; }
+                    length = 0;
+                    emit = true;
+                }
+            }
+        } else {
+        const uint4 rec = ld_row<LD>(rows + (mode ? k2 : k));
         if (mode == 0) {
             if ((rec.w >> 30) & 1u) slow = true;
             else {
@@ -619,6 +687,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                 length = 0;
                 emit = true;
             }
+        }
         }
         if (slow) {  // ---- generic step in absolute coordinates
             const SlowOut so = slow_step<MS>(p, c, k, off, length, sample);  // by value: no state lives in local memory
@@ -819,13 +888,18 @@ static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms,
     return cudaGetLastError();
 }
 
-template <bool STATS, int LD>
+template <bool STATS, int LD, bool ROW8>
 static cudaError_t launch_move_pml(const WalkParams& p, int num_sms, cudaStream_t stream) {
     switch (p.out_width) {
-        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD>, p, num_sms, stream);
-        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD>, p, num_sms, stream);
-        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD>, p, num_sms, stream);
+        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD, ROW8>, p, num_sms, stream);
+        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD, ROW8>, p, num_sms, stream);
+        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD, ROW8>, p, num_sms, stream);
     }
+}
+template <int LD, bool ROW8>
+static cudaError_t launch_move(const WalkParams& p, bool ms, bool stats, int num_sms, cudaStream_t stream) {
+    if (ms) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8>, p, num_sms, stream);
+    return stats ? launch_move_pml<true, LD, ROW8>(p, num_sms, stream) : launch_move_pml<false, LD, ROW8>(p, num_sms, stream);
 }
 template <bool STATS>
 static cudaError_t launch_ms_lengths(const WalkParams& p, int num_sms, cudaStream_t stream) {
@@ -853,21 +927,16 @@ static cudaError_t launch_t(const WalkParams& p, int num_sms, cudaStream_t strea
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches) {
     const bool stats = p.bin_width && p.stats;
     if (lanes == 1) {
-        if (!p.rows || (ms && !p.msamp)) return cudaErrorInvalidValue;
+        if ((!p.rows && !p.rows8) || (ms && !p.msamp)) return cudaErrorInvalidValue;
         cudaError_t e;
-        if (ms) {
-            e = p.row_ld == 2 ? launch_persistent(spb_move_kernel<true, false, 4, 2>, p, num_sms, stream)
-                : p.row_ld == 1 ? launch_persistent(spb_move_kernel<true, false, 4, 1>, p, num_sms, stream)
-                                : launch_persistent(spb_move_kernel<true, false, 4, 0>, p, num_sms, stream);
-            if (e != cudaSuccess) return e;
+        if (p.rows8) e = p.row_ld ? launch_move<1, true>(p, ms, stats, num_sms, stream) : launch_move<0, true>(p, ms, stats, num_sms, stream);
+        else e = p.row_ld ? launch_move<1, false>(p, ms, stats, num_sms, stream) : launch_move<0, false>(p, ms, stats, num_sms, stream);
+        if (launches) *launches = 1;
+        if (ms && e == cudaSuccess) {
             e = stats ? launch_ms_lengths<true>(p, num_sms, stream) : launch_ms_lengths<false>(p, num_sms, stream);
             if (launches) *launches = 2;
-            return e;
         }
-        if (launches) *launches = 1;
-        if (p.row_ld == 2) return stats ? launch_move_pml<true, 2>(p, num_sms, stream) : launch_move_pml<false, 2>(p, num_sms, stream);
-        if (p.row_ld == 1) return stats ? launch_move_pml<true, 1>(p, num_sms, stream) : launch_move_pml<false, 1>(p, num_sms, stream);
-        return stats ? launch_move_pml<true, 0>(p, num_sms, stream) : launch_move_pml<false, 0>(p, num_sms, stream);
+        return e;
     }
     if (p.out_width != 4) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths only
     if (launches) *launches = 1;

@@ -32,12 +32,14 @@ struct WalkParams {
     uint64_t max_value_thr;
     unsigned long long* work_counter;  // zeroed before launch
     // thread-per-read kernels over the move rows; rows == nullptr when the index has no fast symbols
-    const uint4* rows;
+    const uint4* rows;         // 16-byte move rows, or
+    const uint64_t* rows8;     // 8-byte compact rows + head nibbles (exactly one of rows / rows8 is set)
+    const uint64_t* heads4;
     const uint4* msamp;        // MS only
     uint32_t mv_end_k[4], mv_end_off[4];
     uint64_t mv_end_sl[4];
     uint32_t out_width;        // bytes per length value: 4, 2 or 1 (values above the maximum are clamped and counted)
-    uint32_t row_ld;           // development knob: 0 = rows bypass L1, 1 = rows allocate in L1
+    uint32_t row_ld;           // 0 = rows bypass L1, 1 = rows allocate in L1 (default)
     unsigned long long* saturated;  // nullable; += number of clamped length values
 };
 
