@@ -97,15 +97,25 @@ struct SpbMoveRow { uint32_t x, y, z, w; };
 // The walk is bound by how many DRAM lines it fetches per step, i.e. by the L2 hit rate of the row table
 // (a B200 keeps ~60 MB of a randomly gathered table resident: tools/gather_bench*, profiles/).  Indexes
 // with fewer than 2^24 runs therefore get rows half the size; the semantics are those of SpbMoveRow:
-//   bits  0-23 dest        24-31 len (1..SPB_MV8_MAX)        32-39 delta (0..SPB_MV8_MAX)
-//   bits 40-42 fid         43    slow
-//   bits 44-49 threshold class of jump slot 0/1/2: 0 never down | 1 always down | 2 down iff off < T | 3 generic step
-//   bits 50-57 T           the one in-run threshold of this row (two slots with different T: the second is class 3)
-//   bits 58-63 distance class of jump slot 0/1/2: 0 no later c-run | 1 next row | 2 row k+2 | 3 search heads4 from k+3
+//   bits  0-23 dest        24-30 len (1..SPB_MV8_LEN_MAX)     31-38 delta (0..SPB_MV8_DELTA_MAX)
+//   bits 39-40 fid         41    slow (also set when the head is not a fast symbol)
+//   bits 42-47 threshold class of jump slot 0/1/2: 0 never down | 1 always down | 2 down iff off < T | 3 generic step
+//   bits 48-54 T           the one in-run threshold of this row (two slots with different T: the second is class 3)
+//   bits 55-63 distance of jump slot 0/1/2 (3 bits each): 0 no later c-run | 1..SPB_MV8_DIST_SCAN-1 the next c-run is
+//              row k + d | SPB_MV8_DIST_SCAN search heads4 from row k + SPB_MV8_DIST_SCAN
 // heads4: one nibble per run (fid, SPB_SYM_SLOW for other heads and for padding), 16 runs per 64-bit word; the
 // kernel finds the next run headed by c with a carry-free zero-nibble test, SPB_MV8_SCAN_WORDS words at most.
-#ifndef SPB_MV8_MAX
-#define SPB_MV8_MAX 255u        /* the test build lowers these limits to exercise the fall-backs */
+#ifndef SPB_MV8_LEN_MAX
+#define SPB_MV8_LEN_MAX 127u     /* the test build lowers these limits to exercise the fall-backs */
+#endif
+#ifndef SPB_MV8_DELTA_MAX
+#define SPB_MV8_DELTA_MAX 255u
+#endif
+#ifndef SPB_MV8_T_MAX
+#define SPB_MV8_T_MAX 127u
+#endif
+#ifndef SPB_MV8_DIST_SCAN
+#define SPB_MV8_DIST_SCAN 7u
 #endif
 #ifndef SPB_MV8_SCAN_WORDS
 #define SPB_MV8_SCAN_WORDS 4u

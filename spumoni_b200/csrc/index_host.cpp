@@ -596,21 +596,24 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                 }
             }
             if (rows8) {
-                slow = hk >= SPB_SYM_SLOW || len_k > SPB_MV8_MAX || delta > SPB_MV8_MAX;
-                uint64_t cls = 0, dcls = 0, T = 0;
-                for (uint32_t slot = 0; slot < 3 && hk < SPB_SYM_SLOW; slot++) {
+                slow = hk >= SPB_SYM_SLOW || len_k > SPB_MV8_LEN_MAX || delta > SPB_MV8_DELTA_MAX;
+                uint64_t cls = 0, dist = 0, T = 0;
+                for (uint32_t s = 0; s < num_fast && hk < SPB_SYM_SLOW; s++) {
+                    if (s == hk) continue;
+                    const uint32_t slot = s - (s > hk ? 1u : 0u);
                     const uint32_t v = thr3[slot];  // same derivation as the wide rows: 0 | value | SLOW | ALWAYS
                     uint64_t c3;
                     if (v == 0) c3 = 0;
                     else if (v == SPB_MV_THR_ALWAYS) c3 = 1;
-                    else if (v == SPB_MV_THR_SLOW || v > SPB_MV8_MAX || (T != 0 && T != v)) c3 = 3;
+                    else if (v == SPB_MV_THR_SLOW || v > SPB_MV8_T_MAX || (T != 0 && T != v)) c3 = 3;
                     else { c3 = 2; T = v; }
                     cls |= c3 << (2 * slot);
-                    const uint32_t dd = dist3[slot];
-                    dcls |= (uint64_t)(dd < 3 ? dd : 3u) << (2 * slot);
+                    const uint32_t k2 = nxt[(size_t)k * num_fast + s];
+                    const uint64_t dd = k2 == 0xFFFFFFFFu ? 0 : std::min<uint64_t>((uint64_t)k2 - k, SPB_MV8_DIST_SCAN);
+                    dist |= dd << (3 * slot);
                 }
-                rows_c[k] = (uint64_t)de | ((uint64_t)std::min<uint64_t>(len_k, SPB_MV8_MAX) << 24) | ((uint64_t)std::min<uint64_t>(delta, SPB_MV8_MAX) << 32) |
-                            ((uint64_t)(hk > SPB_SYM_SLOW ? SPB_SYM_SLOW : hk) << 40) | ((uint64_t)(slow ? 1 : 0) << 43) | (cls << 44) | (T << 50) | (dcls << 58);
+                rows_c[k] = (uint64_t)de | ((uint64_t)std::min<uint64_t>(len_k, SPB_MV8_LEN_MAX) << 24) | ((uint64_t)std::min<uint64_t>(delta, SPB_MV8_DELTA_MAX) << 31) |
+                            ((uint64_t)(hk & 3u) << 39) | ((uint64_t)(slow ? 1 : 0) << 41) | (cls << 42) | (T << 48) | (dist << 55);
                 continue;
             }
             SpbMoveRow r;
@@ -623,7 +626,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         }
         if (rows8) {
             for (uint64_t k = R; k < R + SPB_MV_ROW_PAD; k++)  // row R = "pos == n": generic step only
-                rows_c[k] = (uint64_t)R | (1ull << 24) | ((uint64_t)SPB_SYM_SLOW << 40) | (1ull << 43);
+                rows_c[k] = (uint64_t)R | (1ull << 24) | (1ull << 41);
             uint64_t* hw = reinterpret_cast<uint64_t*>(blob.data() + h.off_heads4);
             const uint64_t words = (R + SPB_MV8_HEADS_PAD + 15) / 16;
             for (uint64_t w = 0; w < words; w++) {

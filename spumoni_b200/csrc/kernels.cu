@@ -470,25 +470,18 @@ __device__ __forceinline__ void flush_word(void* out, const OutWord<OW>& b, uint
 // ---- per-thread staging of the read and output streams in shared memory -----------------------
 // A lane consumes one read byte and produces one value per step, so a 128-byte line of either stream
 // stays "live" for > 100 steps of > 100 000 resident lanes: left to the L2, these half-used lines evict
-// the move rows (measured: tools/gather_bench2.cu, profiles/r1_gather_bench2.txt).  Each lane therefore
-// moves SPB_STAGE bytes at a time: reads are fetched as whole 64-byte blocks (evict-first, no L1) into
-// shared memory, outputs are collected there and written as full 32-byte sectors.  Chunk j (16 bytes) of
-// lane x lives at [j * SPB_MV_THREADS + x]: conflict-free for 16-byte lane accesses.
+// the move rows (measured: tools/gather_bench2.cu, profiles/r1_gather_bench2_streams.txt).  Each lane
+// therefore moves SPB_STAGE bytes at a time: reads are fetched as whole 64-byte blocks (evict-first, no
+// L1) into shared memory and consumed from there one byte per step; values are stored into shared
+// memory one per step and written out as whole blocks.  Chunk j (16 bytes) of lane x lives at
+// [j * SPB_MV_THREADS + x].  Both per-step accesses are branch-free (the lanes of a warp sit at unrelated
+// positions of their reads, so any "every n-th step" branch would run for a few lanes almost every
+// iteration); only the block refill / flush branches, once per SPB_STAGE bytes.
 #ifndef SPB_STAGE
 #define SPB_STAGE 64
 #endif
 #define SPB_STAGE_CH (SPB_STAGE / 16)
-#ifndef SPB_STAGE_RD
-#define SPB_STAGE_RD 1   /* development switches: 0 = fetch the read 8 bytes at a time straight from global memory */
-#endif
-#ifndef SPB_STAGE_WR
-#define SPB_STAGE_WR 1   /* 0 = write every 16-byte output word as soon as it is complete */
-#endif
-#ifndef SPB_CARVEOUT
-#define SPB_CARVEOUT 0   /* 0 = leave the L1 / shared memory split to the driver (measured best: the L1 serves the
-                            neighbour-row loads; forcing the maximum shared-memory carve-out halves the throughput);
-                            1 = maximum shared memory; other values = percent */
-#endif
+#define SPB_STAGE_PLANE (SPB_MV_THREADS * 16)  /* bytes between chunk j and chunk j+1 of a lane */
 
 // one whole 32-byte sector per instruction (sm_100 256-bit load), evict-first in L2, not kept in L1
 __device__ __forceinline__ void ld_stream32(const void* p, uint4& a, uint4& b) {
@@ -504,13 +497,49 @@ __device__ __forceinline__ void stage_reads(uint4* s_rd, const uint8_t* reads, u
 #pragma unroll
     for (int j = 0; j < SPB_STAGE_CH; j++) s_rd[j * SPB_MV_THREADS + threadIdx.x] = v[j];
 }
-__device__ __forceinline__ uint64_t ld_read8(const uint8_t* p) {
-    uint64_t v;
-    asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(v) : "l"(p));
-    return v;
+__device__ __forceinline__ uint32_t staged_offset(uint32_t byte_in_block) {  // byte offset inside a lane's staging area
+    return (byte_in_block >> 4) * SPB_STAGE_PLANE + threadIdx.x * 16 + (byte_in_block & 15u);
 }
-__device__ __forceinline__ uint64_t staged_chunk(const uint4* s_rd, uint64_t gi) {  // the 8 bytes containing byte gi
-    return reinterpret_cast<const uint64_t*>(&s_rd[((gi & (SPB_STAGE - 1)) >> 4) * SPB_MV_THREADS + threadIdx.x])[(gi >> 3) & 1];
+__device__ __forceinline__ void st_stream16(void* p, const uint4& w) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+}
+// Slow half of the output flush: only bytes [lo, hi) of the staged block starting at array byte sb are valid
+// (the block holds the beginning or the end of a read).  EB = element size in bytes.
+template <int EB>
+__device__ __noinline__ void flush_partial(uint8_t* out, const uint4* s_out, uint64_t sb, uint64_t lo, uint64_t hi) {
+    const uint8_t* sp = reinterpret_cast<const uint8_t*>(s_out) + threadIdx.x * 16;
+    for (uint32_t j = 0; j < SPB_STAGE_CH; j++) {
+        const uint64_t wb = sb + 16 * j;
+        if (wb + 16 <= lo || wb >= hi) continue;
+        if (wb >= lo && wb + 16 <= hi) { st_stream16(out + wb, s_out[j * SPB_MV_THREADS + threadIdx.x]); continue; }
+        for (uint32_t b = 0; b < 16; b += EB) {
+            if (wb + b < lo || wb + b >= hi) continue;
+            const uint8_t* e = sp + j * SPB_STAGE_PLANE + b;
+            if (EB == 1) out[wb + b] = *e;
+            else if (EB == 2) *reinterpret_cast<uint16_t*>(out + wb + b) = *reinterpret_cast<const uint16_t*>(e);
+            else if (EB == 4) *reinterpret_cast<uint32_t*>(out + wb + b) = *reinterpret_cast<const uint32_t*>(e);
+            else *reinterpret_cast<uint64_t*>(out + wb + b) = *reinterpret_cast<const uint64_t*>(e);
+        }
+    }
+}
+// Stage value v of element gi (EB bytes) of the read [base, end) walked downwards; write the block out when it is complete.
+template <int EB>
+__device__ __forceinline__ void stage_value(uint4* s_out, void* out, uint64_t gi, uint64_t v, uint64_t end, bool last) {
+    const uint64_t bo = gi * EB;
+    const uint32_t so = (uint32_t)bo & (SPB_STAGE - 1);
+    uint8_t* sp = reinterpret_cast<uint8_t*>(s_out) + staged_offset(so);
+    if (EB == 1) *sp = (uint8_t)v;
+    else if (EB == 2) *reinterpret_cast<uint16_t*>(sp) = (uint16_t)v;
+    else if (EB == 4) *reinterpret_cast<uint32_t*>(sp) = (uint32_t)v;
+    else *reinterpret_cast<uint64_t*>(sp) = v;
+    if (so == 0 || last) {
+        const uint64_t sb = bo - so, hi = end * EB;
+        if (so == 0 && sb + SPB_STAGE <= hi) {
+#pragma unroll
+            for (int j = 0; j < SPB_STAGE_CH; j++) st_stream16(reinterpret_cast<uint8_t*>(out) + sb + 16 * j, s_out[j * SPB_MV_THREADS + threadIdx.x]);
+        } else
+            flush_partial<EB>(reinterpret_cast<uint8_t*>(out), s_out, sb, bo, hi < sb + SPB_STAGE ? hi : sb + SPB_STAGE);
+    }
 }
 
 struct BinState {
@@ -523,8 +552,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
-    __shared__ uint4 s_rd[SPB_STAGE_RD ? SPB_STAGE_CH * SPB_MV_THREADS : 1];   // staged read bytes, see stage_reads
-    __shared__ uint4 s_out[SPB_STAGE_WR ? SPB_STAGE_CH * SPB_MV_THREADS : 1];  // staged output words (lengths, or MS pointers)
+    __shared__ uint4 s_rd[SPB_STAGE_CH * SPB_MV_THREADS];   // staged read bytes, see stage_reads
+    __shared__ uint4 s_out[SPB_STAGE_CH * SPB_MV_THREADS];  // staged output values (lengths, or MS pointers)
     for (int i = threadIdx.x; i < 256; i += SPB_MV_THREADS) {
         const SpbCharTab t = p.chartab[i];
         s_fid[i] = (uint8_t)(t.cidx == 0xFFFFFFFFu ? 5u : t.dest_f);
@@ -538,16 +567,17 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
     const uint32_t R32 = (uint32_t)p.R;
     const bool upper = (p.flags & SPB_FLAG_TOUPPER) != 0;
     const bool do_stats = !MS && STATS && p.bin_width != 0 && p.stats != nullptr;
+    const uint8_t* rd_bytes = reinterpret_cast<const uint8_t*>(s_rd);
+    constexpr uint32_t VMAX = OW == 4 ? 0xFFFFFFFFu : (OW == 2 ? 0xFFFFu : 0xFFu);
 
     // lane state
     bool have = false, down = false;
     unsigned long long r = 0;
-    uint64_t base = 0, end = 0, gi = 0, chunk = 0;
+    uint64_t base = 0, end = 0, gi = 0;
     uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2, 2 = SCAN (compact rows: search heads4)
     uint32_t sk = 0, scan_left = 0, want = 0;
-    uint64_t sample = 0, pbuf = 0;
+    uint64_t sample = 0;
     uint32_t nsat = 0;
-    OutWord<OW> ob;
     BinState bs;
 
     for (;;) {
@@ -564,9 +594,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
             gi = end - 1;
             k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0; mode = 0;  // empty string: pos = n-1
             if (MS) sample = p.last_run_sample;
-            if (SPB_STAGE_RD) { stage_reads(s_rd, p.reads, gi); chunk = staged_chunk(s_rd, gi); }
-            else chunk = ld_read8(p.reads + (gi & ~7ull));
-            ob.clear();
+            stage_reads(s_rd, p.reads, gi);
             have = true;
             if (do_stats) {
                 const uint64_t bw = p.bin_width;
@@ -576,30 +604,30 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
             }
         }
 
-        // ---- one row load per lane per iteration
-        uint32_t c = (uint32_t)(chunk >> ((gi & 7) * 8)) & 0xFFu;
+        // ---- one index load per lane per iteration (+ the read byte from shared memory)
+        uint32_t c = rd_bytes[staged_offset((uint32_t)gi & (SPB_STAGE - 1))];
         if (upper && c >= 'a' && c <= 'z') c -= 32;
         bool slow = false, emit = false;
         if (ROW8) {
             const uint64_t* addr = mode == 2 ? p.heads4 + (sk >> 4) : p.rows8 + (mode ? k2 : k);
             const uint64_t v = ld_row8<LD>(addr);
             if (mode == 0) {
-                if ((v >> 43) & 1ull) slow = true;
+                if ((v >> 41) & 1ull) slow = true;
                 else {
-                    const uint32_t len = (uint32_t)(v >> 24) & 0xFFu;
+                    const uint32_t len = (uint32_t)(v >> 24) & 0x7Fu;
                     if (off == SPB_MV_OFF_LAST) off = len - 1;
                     if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
-                    const uint32_t h = (uint32_t)(v >> 40) & 7u, s = s_fid[c];
+                    const uint32_t h = (uint32_t)(v >> 39) & 3u, s = s_fid[c];
                     if (s >= SPB_SYM_SLOW) slow = true;
                     else if (s == h) {  // bwt[pos] == c (:250 / :582)
                         length++;
                         if (MS) sample--;
-                        off += (uint32_t)(v >> 32) & 0xFFu;
+                        off += (uint32_t)(v >> 31) & 0xFFu;
                         k = (uint32_t)v & 0xFFFFFFu;
                         emit = true;
                     } else {  // threshold jump (:251-279 / :583-616)
                         const uint32_t slot = s - (s > h ? 1u : 0u);
-                        const uint32_t cls = (uint32_t)(v >> (44 + 2 * slot)) & 3u, dc = (uint32_t)(v >> (58 + 2 * slot)) & 3u;
+                        const uint32_t cls = (uint32_t)(v >> (42 + 2 * slot)) & 3u, dc = (uint32_t)(v >> (55 + 3 * slot)) & 7u;
                         if (cls == 3) slow = true;
                         else if (dc == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
                             k = s_end_k[s]; off = s_end_off[s];
@@ -607,9 +635,9 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                             if (MS) sample = s_end_sl[s];
                             emit = true;
                         } else {
-                            down = (cls == 1) || (cls == 2 && off < ((uint32_t)(v >> 50) & 0xFFu));
-                            if (dc < 3) { k2 = k + dc; mode = 1; }
-                            else { sk = k + 3; scan_left = SPB_MV8_SCAN_WORDS; want = s; mode = 2; }
+                            down = (cls == 1) || (cls == 2 && off < ((uint32_t)(v >> 48) & 0x7Fu));
+                            if (dc < SPB_MV8_DIST_SCAN) { k2 = k + dc; mode = 1; }
+                            else { sk = k + SPB_MV8_DIST_SCAN; scan_left = SPB_MV8_SCAN_WORDS; want = s; mode = 2; }
                         }
                     }
                 }
@@ -625,9 +653,9 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                 if (!slow) continue;
             } else {
                 mode = 0;
-                if ((v >> 43) & 1ull) slow = true;  // landing state not encodable: redo the step from (k, off)
+                if ((v >> 41) & 1ull) slow = true;  // landing state not encodable: redo the step from (k, off)
                 else {
-                    const uint32_t d2 = (uint32_t)(v >> 32) & 0xFFu, de = (uint32_t)v & 0xFFFFFFu;
+                    const uint32_t d2 = (uint32_t)(v >> 31) & 0xFFu, de = (uint32_t)v & 0xFFFFFFu;
                     if (MS) {
                         const uint4 sm = ldg_nc16(p.msamp + k2);
                         sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
@@ -640,54 +668,54 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                 }
             }
         } else {
-        const uint4 rec = ld_row<LD>(rows + (mode ? k2 : k));
-        if (mode == 0) {
-            if ((rec.w >> 30) & 1u) slow = true;
-            else {
-                const uint32_t len = rec.y & SPB_MV_LEN_MASK;
-                if (off == SPB_MV_OFF_LAST) off = len - 1;
-                if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
-                const uint32_t h = (rec.w >> 27) & 7u, s = s_fid[c];
-                if (s >= SPB_SYM_SLOW) slow = true;
-                else if (s == h) {  // bwt[pos] == c (:250 / :582)
-                    length++;
-                    if (MS) sample--;
-                    off += rec.z & SPB_MV_LEN_MASK;
-                    k = rec.x;
-                    emit = true;
-                } else {  // threshold jump (:251-279 / :583-616)
-                    const uint32_t slot = s - (s > h ? 1u : 0u);
-                    const uint32_t v = slot == 0 ? (rec.y >> 20) : (slot == 1 ? (rec.z >> 20) : (rec.w & 0xFFFu));
-                    const uint32_t d = (rec.w >> (12u + 5u * slot)) & 31u;
-                    if (v == SPB_MV_THR_SLOW || d == SPB_MV_DIST_FAR) slow = true;
-                    else if (d == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
-                        k = s_end_k[s]; off = s_end_off[s];
-                        length = 0;
-                        if (MS) sample = s_end_sl[s];
+            const uint4 rec = ld_row<LD>(rows + (mode ? k2 : k));
+            if (mode == 0) {
+                if ((rec.w >> 30) & 1u) slow = true;
+                else {
+                    const uint32_t len = rec.y & SPB_MV_LEN_MASK;
+                    if (off == SPB_MV_OFF_LAST) off = len - 1;
+                    if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
+                    const uint32_t h = (rec.w >> 27) & 7u, s = s_fid[c];
+                    if (s >= SPB_SYM_SLOW) slow = true;
+                    else if (s == h) {  // bwt[pos] == c (:250 / :582)
+                        length++;
+                        if (MS) sample--;
+                        off += rec.z & SPB_MV_LEN_MASK;
+                        k = rec.x;
                         emit = true;
-                    } else {
-                        down = (v == SPB_MV_THR_ALWAYS) || (off < v);
-                        k2 = k + d;
-                        mode = 1;
+                    } else {  // threshold jump (:251-279 / :583-616)
+                        const uint32_t slot = s - (s > h ? 1u : 0u);
+                        const uint32_t v = slot == 0 ? (rec.y >> 20) : (slot == 1 ? (rec.z >> 20) : (rec.w & 0xFFFu));
+                        const uint32_t d = (rec.w >> (12u + 5u * slot)) & 31u;
+                        if (v == SPB_MV_THR_SLOW || d == SPB_MV_DIST_FAR) slow = true;
+                        else if (d == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
+                            k = s_end_k[s]; off = s_end_off[s];
+                            length = 0;
+                            if (MS) sample = s_end_sl[s];
+                            emit = true;
+                        } else {
+                            down = (v == SPB_MV_THR_ALWAYS) || (off < v);
+                            k2 = k + d;
+                            mode = 1;
+                        }
                     }
                 }
-            }
-        } else {
-            mode = 0;
-            if ((rec.w >> 30) & 1u) slow = true;  // landing state not encodable: redo the step from (k, off)
-            else {
-                const uint32_t d2 = rec.z & SPB_MV_LEN_MASK;
-                if (MS) {
-                    const uint4 sm = ldg_nc16(p.msamp + k2);
-                    sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+            } else {
+                mode = 0;
+                if ((rec.w >> 30) & 1u) slow = true;  // landing state not encodable: redo the step from (k, off)
+                else {
+                    const uint32_t d2 = rec.z & SPB_MV_LEN_MASK;
+                    if (MS) {
+                        const uint4 sm = ldg_nc16(p.msamp + k2);
+                        sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                    }
+                    if (!down) { k = rec.x; off = d2; }
+                    else if (d2) { k = rec.x; off = d2 - 1; }
+                    else { k = rec.x - 1; off = SPB_MV_OFF_LAST; }
+                    length = 0;
+                    emit = true;
                 }
-                if (!down) { k = rec.x; off = d2; }
-                else if (d2) { k = rec.x; off = d2 - 1; }
-                else { k = rec.x - 1; off = SPB_MV_OFF_LAST; }
-                length = 0;
-                emit = true;
             }
-        }
         }
         if (slow) {  // ---- generic step in absolute coordinates
             const SlowOut so = slow_step<MS>(p, c, k, off, length, sample);  // by value: no state lives in local memory
@@ -698,58 +726,11 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
 
         if (emit) {
             const bool last = (gi == base);
-            if (MS) {
-                // pointers: two per 16-byte word, SPB_STAGE_CH words per staged block
-                if (gi & 1ull) pbuf = sample;
-                if (!(gi & 1ull) || last) {
-                    const uint64_t g = gi & ~1ull;  // first pointer index of this word
-                    const uint32_t seg = SPB_STAGE_WR ? ((uint32_t)(g >> 1) & (SPB_STAGE_CH - 1)) : 0u;
-                    s_out[seg * SPB_MV_THREADS * (SPB_STAGE_WR ? 1 : 0) + (SPB_STAGE_WR ? threadIdx.x : 0)] = make_uint4((uint32_t)sample, (uint32_t)(sample >> 32), (uint32_t)pbuf, (uint32_t)(pbuf >> 32));
-                    if (!SPB_STAGE_WR) {
-                        if (g >= gi && g + 2 <= end)
-                            asm volatile("st.global.cs.v2.u64 [%0], {%1,%2};" ::"l"(p.pointers + g), "l"(sample), "l"(pbuf) : "memory");
-                        else if (g >= gi) p.pointers[g] = sample;
-                        else p.pointers[g + 1] = pbuf;
-                    } else if (seg == 0 || last) {
-#pragma unroll
-                        for (uint32_t j = 0; j < SPB_STAGE_CH; j++) {
-                            const uint64_t gj = g + 2ull * (j - seg);
-                            if (j < seg || gj >= end) continue;
-                            const uint4 w = s_out[j * SPB_MV_THREADS + threadIdx.x];
-                            if (gj >= gi && gj + 2 <= end)
-                                asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p.pointers + gj), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
-                            else if (gj >= gi) p.pointers[gj] = (uint64_t)w.x | ((uint64_t)w.y << 32);       // word cut by the read's end
-                            else p.pointers[gj + 1] = (uint64_t)w.z | ((uint64_t)w.w << 32);                  // word cut by the read's start
-                        }
-                    }
-                }
-            } else {
-                constexpr uint32_t VPW = OutWord<OW>::VPW;
-                const uint32_t slot = (uint32_t)gi & (VPW - 1);
+            if (MS) stage_value<8>(s_out, p.pointers, gi, sample, end, last);
+            else {
                 uint32_t v = length;
-                if (OW < 4 && v > OutWord<OW>::VMAX) { v = OutWord<OW>::VMAX; nsat++; }
-                ob.put(slot, v);
-                if (slot == 0 || last) {
-                    const uint64_t g = gi & ~(uint64_t)(VPW - 1);  // first value index of this word
-                    const uint32_t seg = (uint32_t)(g / VPW) & (SPB_STAGE_CH - 1);
-                    if (!SPB_STAGE_WR) {
-                        flush_word<OW>(p.lengths, ob, g, gi, end);
-                        ob.clear();
-                    } else {
-                    s_out[seg * SPB_MV_THREADS + threadIdx.x] = ob.as_uint4();
-                    ob.clear();
-                    }
-                    if (SPB_STAGE_WR && (seg == 0 || last)) {  // staged block complete (walking downwards), or the read ends inside it
-#pragma unroll
-                        for (uint32_t j = 0; j < SPB_STAGE_CH; j++) {
-                            const uint64_t gj = g + (uint64_t)VPW * (j - seg);
-                            if (j < seg || gj >= end) continue;
-                            OutWord<OW> w;
-                            w.from_uint4(s_out[j * SPB_MV_THREADS + threadIdx.x]);
-                            flush_word<OW>(p.lengths, w, gj, gi, end);
-                        }
-                    }
-                }
+                if (OW < 4 && v > VMAX) { v = VMAX; nsat++; }
+                stage_value<OW>(s_out, p.lengths, gi, v, end, last);
                 if (do_stats) {
                     if (gi < bs.bound) {  // left the bin [bound, ...): close it
                         if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;
@@ -770,12 +751,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                 have = false;
             } else {
                 --gi;
-                if ((gi & 7ull) == 7ull) {
-                    if (SPB_STAGE_RD) {
-                        if ((gi & (SPB_STAGE - 1)) == SPB_STAGE - 1) stage_reads(s_rd, p.reads, gi);
-                        chunk = staged_chunk(s_rd, gi);
-                    } else chunk = ld_read8(p.reads + (gi & ~7ull));
-                }
+                if (((uint32_t)gi & (SPB_STAGE - 1)) == SPB_STAGE - 1) stage_reads(s_rd, p.reads, gi);
             }
         }
     }
@@ -874,10 +850,9 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const Wa
 template <typename K>
 static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms, cudaStream_t stream) {
     int occ = 0;
-    cudaError_t e = cudaSuccess;
-    if (SPB_CARVEOUT) e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, SPB_CARVEOUT == 1 ? (int)cudaSharedmemCarveoutMaxShared : SPB_CARVEOUT);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SPB_MV_THREADS, 0);
+    // The L1 / shared-memory split is left to the driver: the L1 serves the neighbour-row loads, and forcing the
+    // maximum shared-memory carve-out halved the throughput (profiles/r1_move_kernel_variants.json).
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, SPB_MV_THREADS, 0);
     if (e != cudaSuccess) return e;
     if (occ < 1) occ = 1;
     // persistent grid: a whole number of CTAs per SM; reads are pulled from the work counter

@@ -31,6 +31,14 @@ def built():
     _ensure_built()
 
 
+@pytest.fixture(params=["8", "16"])
+def row_width(request, monkeypatch):
+    """Both move-row layouts of the flat image: compact 8-byte rows (the default when R < 2^24) and the wide
+    16-byte rows (larger indexes); the layout is chosen when an index is opened."""
+    monkeypatch.setenv("SPUMONI_B200_ROWS", request.param)
+    return request.param
+
+
 def mkindex(*args):
     out = subprocess.run([MKINDEX] + [str(a) for a in args], check=True, capture_output=True, text=True)
     return out.stdout

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4Q"  # up to mv_end_sl (then F[256], chartab[256])
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQ"  # up to off_heads4 (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -23,6 +23,7 @@ class FlatImage:
          self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position, self.off_mrows,
          self.off_msamp, self.num_fast, *rest) = struct.unpack_from(HDR_FMT, b, 0)
         self.fast_sym, self.mv_end_k, self.mv_end_off, self.mv_end_sl = rest[0:4], rest[4:8], rest[8:12], rest[15:19]
+        self.off_mrows8, self.off_heads4 = rest[19], rest[20]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -32,7 +33,11 @@ class FlatImage:
         self.runs = np.frombuffer(b, dtype=np.uint32, count=4 * nrec, offset=self.off_runs).reshape(nrec, 4)
         self.crec = np.frombuffer(b, dtype=np.uint32, count=4 * (self.num_crec + 1), offset=self.off_crec).reshape(-1, 4)
         if self.num_fast:
-            self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
+            if self.off_mrows8:
+                self.rows8 = np.frombuffer(b, dtype=np.uint64, count=self.R + 16, offset=self.off_mrows8)
+                self.heads4 = np.frombuffer(b, dtype=np.uint64, count=(self.R + 128 + 15) // 16, offset=self.off_heads4)
+            else:
+                self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
             if self.mode == 1:
                 self.msamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.R + 16), offset=self.off_msamp).reshape(-1, 2)
         if self.mode == 1:
@@ -163,9 +168,100 @@ class FlatImage:
         ct = self.chartab[c]
         return 5 if ct[3] == 0xFFFFFFFF else ct[2]
 
+    def walk_move8(self, read: bytes, scan_words=4, dist_scan=7):
+        """Compact 8-byte rows (spb_move_kernel<ROW8>). Returns (lengths, pointers or None, stats)."""
+        assert self.num_fast and self.off_mrows8
+        ms = self.mode == 1
+        LAST = 0xFFFFFFFF
+        m, R = len(read), self.R
+        k, off, length, sample = R - 1, LAST, 0, self.last_run_sample
+        out, ptr = [0] * m, [0] * m
+        stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0, "scan": 0}
+        for gi in range(m - 1, -1, -1):
+            c = read[gi]
+            slow = False
+            while True:
+                v = int(self.rows8[k])
+                if (v >> 41) & 1:
+                    slow = True
+                    break
+                ln = (v >> 24) & 0x7F
+                if off == LAST:
+                    off = ln - 1
+                if off >= ln:
+                    off -= ln
+                    k += 1
+                    stats["norm_iters"] += 1
+                    continue
+                break
+            if not slow:
+                h, s = (v >> 39) & 3, self.fid(c)
+                if s >= 4:
+                    slow = True
+                elif s == h:
+                    length += 1
+                    sample = (sample - 1) & U64
+                    k, off = v & 0xFFFFFF, off + ((v >> 31) & 0xFF)
+                else:
+                    slot = s - (1 if s > h else 0)
+                    cls, dc = (v >> (42 + 2 * slot)) & 3, (v >> (55 + 3 * slot)) & 7
+                    if cls == 3:
+                        slow = True
+                    elif dc == 0:
+                        k, off, length, sample = self.mv_end_k[s], self.mv_end_off[s], 0, self.mv_end_sl[s]
+                        stats["end"] += 1
+                    else:
+                        down = cls == 1 or (cls == 2 and off < ((v >> 48) & 0x7F))
+                        k2 = None
+                        if dc < dist_scan:
+                            k2 = k + dc
+                        else:
+                            sk, left = k + dist_scan, scan_words
+                            while k2 is None and left:
+                                stats["scan"] += 1
+                                w = int(self.heads4[sk >> 4])
+                                for t in range(sk & 15, 16):
+                                    if (w >> (4 * t)) & 15 == s:
+                                        k2 = (sk & ~15) + t
+                                        break
+                                sk = (sk & ~15) + 16
+                                left -= 1
+                        if k2 is None:
+                            slow = True
+                        else:
+                            v2 = int(self.rows8[k2])
+                            stats["jump2"] += 1
+                            if (v2 >> 41) & 1:
+                                slow = True
+                            else:
+                                assert (v2 >> 39) & 3 == s
+                                d2, de = (v2 >> 31) & 0xFF, v2 & 0xFFFFFF
+                                if ms:
+                                    sample = int(self.msamp[k2][1 if down else 0])
+                                if not down:
+                                    k, off = de, d2
+                                elif d2:
+                                    k, off = de, d2 - 1
+                                else:
+                                    k, off = de - 1, LAST
+                                length = 0
+            if slow:
+                stats["slow"] += 1
+                k, off, length, sample = self.slow_step(k, off, c, length, sample)
+            else:
+                stats["fast"] += 1
+            out[gi], ptr[gi] = length, sample
+        return out, (ptr if ms else None), stats
+
+    def walk_rows(self, read: bytes, **kw):
+        """Whichever row table the image holds."""
+        if self.off_mrows8:
+            return self.walk_move8(read, **{k: v for k, v in kw.items() if k in ("scan_words", "dist_scan")})
+        return self.walk_move(read, **{k: v for k, v in kw.items() if k in ("len_bits", "dist_far")})
+
     def walk_move(self, read: bytes, len_bits=20, dist_far=31):
         """Returns (lengths, pointers or None, stats)."""
-        assert self.num_fast
+        assert self.num_fast and not self.off_mrows8
         ms = self.mode == 1
         LAST, lmask = 0xFFFFFFFF, (1 << len_bits) - 1
         m, R = len(read), self.R

@@ -17,7 +17,7 @@ from flat_emulator import FlatImage
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")
 
 
-def test_flat_image_matches_golden_vectors(tmp_path):
+def test_flat_image_matches_golden_vectors(tmp_path, row_width):
     for ci, case in enumerate(json.load(open(GOLDEN))["cases"]):
         ref = build_index(str(tmp_path / f"c{ci}"), text=case["text"].encode("latin1"))
         pml, ms = sp.Index.open(ref, sp.MODE_PML), sp.Index.open(ref, sp.MODE_MS)
@@ -30,11 +30,12 @@ def test_flat_image_matches_golden_vectors(tmp_path):
             assert [str(x) for x in ptr] == rd["ms_pointers"]
             assert fm.ms_lengths(read, ptr) == rd["ms_lengths"]
             if fp.num_fast:
-                assert fp.walk_move(read)[0] == rd["pml"]
-                assert [str(x) for x in fm.walk_move(read)[1]] == rd["ms_pointers"]
+                assert bool(fp.off_mrows8) == (row_width == "8")
+                assert fp.walk_rows(read)[0] == rd["pml"]
+                assert [str(x) for x in fm.walk_rows(read)[1]] == rd["ms_pointers"]
 
 
-def test_flat_image_vs_oracle_random(tmp_path):
+def test_flat_image_vs_oracle_random(tmp_path, row_width):
     rng = random.Random(17)
     for trial in range(12):
         n = rng.randint(50, 4000)
@@ -53,11 +54,11 @@ def test_flat_image_vs_oracle_random(tmp_path):
             read = bytes(rng.choice(b"ACGTNY\xe9") for _ in range(ln)) if rng.random() < 0.4 else (tb[rng.randint(0, max(0, len(tb) - ln)):][:ln] or b"A")
             want = po.matching_statistics(read).tolist()
             assert fp.walk(read)[0] == want
-            assert fp.walk_move(read)[0] == want
+            assert fp.walk_rows(read)[0] == want
             L, P = mo.matching_statistics(read)
             _, ptr = fm.walk(read)
             assert ptr == P.tolist() and fm.ms_lengths(read, ptr) == L.tolist()
-            assert fm.walk_move(read)[1] == P.tolist()
+            assert fm.walk_rows(read)[1] == P.tolist()
 
 
 def test_flat_roundtrip_and_header(small_index):
@@ -118,16 +119,18 @@ def test_nulldb_roundtrip(tmp_path):
     assert raw[32 + 8] == 4
 
 
-def test_move_rows_saturation_fallbacks_host_side(tmp_path):
-    """The sattest build shrinks the move-row fields (3-bit len/delta, thresholds <= 4, jump distance < 3);
-    walking its flat image with the same limits must still reproduce the oracle (exercises the slow flag,
-    SPB_MV_THR_SLOW, SPB_MV_DIST_FAR and un-normalised states entering the generic step)."""
+def test_move_rows_saturation_fallbacks_host_side(tmp_path, row_width):
+    """The sattest build shrinks the move-row fields (3-bit len/delta, thresholds <= 4, jump distance < 3 /
+    one-word head scans); walking its flat image with the same limits must still reproduce the oracle
+    (exercises the slow flag, the generic-step threshold class, far jumps and un-normalised states
+    entering the generic step)."""
     import subprocess, sys, textwrap
     rng = random.Random(23)
     unit = "ACGTTGCAAGGCTTAACCGGT"
     text = "".join(unit if rng.random() < 0.9 else rng.choice("ACGT") for _ in range(120)) + "A" * 40 + "".join(rng.choice("ACGTN") for _ in range(300))
     ref = build_index(str(tmp_path), text=text.encode())
-    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, SPUMONI_B200_ROWS=row_width,
+               PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     imgs = {}
     for mode in (0, 1):
         out = str(tmp_path / f"flat{mode}.npy")
@@ -147,9 +150,9 @@ def test_move_rows_saturation_fallbacks_host_side(tmp_path):
         for i in range(len(read)):
             if rng.random() < 0.05:
                 read[i] = rng.choice(b"ACGTN")
-        got, _, st = imgs[0].walk_move(bytes(read), len_bits=3, dist_far=3)
+        got, _, st = imgs[0].walk_rows(bytes(read), len_bits=3, dist_far=3, scan_words=1, dist_scan=3)
         assert got == po.matching_statistics(bytes(read)).tolist()
-        _, ptr, _ = imgs[1].walk_move(bytes(read), len_bits=3, dist_far=3)
+        _, ptr, _ = imgs[1].walk_rows(bytes(read), len_bits=3, dist_far=3, scan_words=1, dist_scan=3)
         assert ptr == mo.matching_statistics(bytes(read))[1].tolist()
         for key in tot:
             tot[key] += st[key]

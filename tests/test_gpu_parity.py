@@ -28,7 +28,7 @@ def oracle_batch(ref, mode, buf, off):
 
 
 @pytest.mark.parametrize("lanes", LANES)
-def test_golden_vectors(tmp_path, lanes):
+def test_golden_vectors(tmp_path, lanes, row_width):
     for ci, case in enumerate(json.load(open(GOLDEN))["cases"]):
         ref = build_index(str(tmp_path / f"c{ci}"), text=case["text"].encode("latin1"))
         pml, ms = sp.pml_t(ref), sp.ms_t(ref)
@@ -47,7 +47,7 @@ def test_golden_vectors(tmp_path, lanes):
 
 
 @pytest.mark.parametrize("lanes", LANES)
-def test_small_index_all_reads(small_index, lanes):
+def test_small_index_all_reads(small_index, lanes, row_width):
     buf, off = load_bin_reads(small_index["reads_bin"])
     Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
     L, _, _ = sp.pml_t(small_index["ref"]).query_host(buf, off, lanes=lanes)
@@ -58,7 +58,7 @@ def test_small_index_all_reads(small_index, lanes):
     assert np.array_equal(L.astype(np.uint64), Lo)
 
 
-def test_edge_cases(small_index):
+def test_edge_cases(small_index, row_width):
     ref = small_index["ref"]
     pml, ms = sp.pml_t(ref), sp.ms_t(ref)
     # empty batch
@@ -91,7 +91,7 @@ def test_toupper_flag(small_index):
     assert np.array_equal(L0, L1) and not np.array_equal(L0, L2)
 
 
-def test_window_overflow_fallback(tmp_path):
+def test_window_overflow_fallback(tmp_path, row_width):
     """Long BWT runs whose LF image spans hundreds of runs: exercises locate_run's binary search."""
     rng = random.Random(5)
     w = "ACGTACGTTTGACAGGATTACA"
@@ -113,7 +113,7 @@ def test_window_overflow_fallback(tmp_path):
 
 
 @pytest.mark.parametrize("mode", ["pml", "ms"])
-def test_classifier_stats(small_index, mode):
+def test_classifier_stats(small_index, mode, row_width):
     buf, off = load_bin_reads(small_index["reads_bin"])
     idx = sp.pml_t(small_index["ref"]) if mode == "pml" else sp.ms_t(small_index["ref"])
     for bw, thr in ((50, 7), (150, 13), (400, 3)):
@@ -221,7 +221,7 @@ def test_cli_general_text(small_index, tmp_path):
     assert open(q + ".pseudo_lengths", "rb").read() == exp
 
 
-def test_medium_scale_properties(tmp_path):
+def test_medium_scale_properties(tmp_path, row_width):
     """2 Mb pangenome, 20k x 500 bp reads: full comparison with the (multi-threaded) oracle plus
     size-independent properties (PML <= MS, X[i] <= X[i+1]+1, pointers in range when no char is absent)."""
     d = str(tmp_path)
@@ -245,7 +245,7 @@ def test_medium_scale_properties(tmp_path):
     assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
 
 
-def test_move_rows_saturation_fallbacks_on_gpu(small_index, tmp_path):
+def test_move_rows_saturation_fallbacks_on_gpu(small_index, tmp_path, row_width):
     """Same inputs through the test-only library build whose move-row fields are tiny (3-bit len/delta,
     thresholds <= 4, jump distance < 3): every fall-back of the thread-per-read kernels (slow rows, generic
     step from un-normalised states, far jumps) runs and must stay bit-exact, PML and MS."""
@@ -261,7 +261,8 @@ def test_move_rows_saturation_fallbacks_on_gpu(small_index, tmp_path):
         Lm, Pm, _ = sp.ms_t({small_index["ref"]!r}).query_host(buf, off, lanes=1)
         np.savez({out!r}, L=L, Lm=Lm, Pm=Pm)
     """)
-    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, SPUMONI_B200_ROWS=row_width,
+               PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     subprocess.check_call([sys.executable, "-c", code], env=env)
     got = np.load(out)
     assert np.array_equal(got["L"].astype(np.uint64), Lo)
@@ -269,7 +270,7 @@ def test_move_rows_saturation_fallbacks_on_gpu(small_index, tmp_path):
 
 
 @pytest.mark.parametrize("mode", ["pml", "ms"])
-def test_narrow_length_outputs(small_index, mode):
+def test_narrow_length_outputs(small_index, mode, row_width):
     """uint16 / uint8 lengths are bit-identical to uint32 when nothing is clamped; a value that does not
     fit is reported (SPB_ERR_OVERFLOW + count), never silently wrapped."""
     buf, off = load_bin_reads(small_index["reads_bin"])
@@ -302,7 +303,7 @@ def test_narrow_length_outputs(small_index, mode):
         idx.query_host(rb, ro, lanes=8, length_bytes=2)
 
 
-def test_unaligned_read_boundaries_narrow(small_index):
+def test_unaligned_read_boundaries_narrow(small_index, row_width):
     """Reads of every length 1..70 back to back: 16-value output words straddle read boundaries."""
     rng = random.Random(3)
     text = open(small_index["ref"]).read().split("\n")[1]

@@ -1,0 +1,6 @@
+#!/bin/bash
+OUT=gpurun_out/exp11; mkdir -p $OUT
+timeout 1500 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest exit $?" >> $OUT/pytest_gpu.log; tail -8 $OUT/pytest_gpu.log
+SPUMONI_B200_ROWS=16 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import json,sys; d=json.load(sys.stdin); u=d['variants']['u32']; print('rows=16 u8 value %.2f kernel %.2f ms e2e %.2f | u32 value %.2f e2e %.2f' % (d['value']/1e9, d['roofline']['kernel_ms'], d['e2e']['value']/1e9, u['value']/1e9, u['e2e']/1e9))"
+bash tools/gpu_variants.sh exp11
+bash tools/gpu_ncu.sh exp11 spb_move
