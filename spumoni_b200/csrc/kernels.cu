@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
 // ==========================================================================================
 #define SPB_MV_THREADS 128
 #ifndef SPB_MV_MINB
-#define SPB_MV_MINB 8  /* 128-thread CTAs per SM: 64 registers, no spills (at 10 the 48-register cap spills inside the loop) */
+#define SPB_MV_MINB 9  /* 128-thread CTAs per SM: 56 registers, no spills (at 10 the 48-register cap spills inside the loop) */
 #endif
 
 template <int LD>
