@@ -171,7 +171,6 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.max_value_thr = opts ? opts->max_value_thr : 0;
     p.rows = (has_fast && h.off_mrows) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_mrows) : nullptr;
     p.rows8 = (has_fast && h.off_mrows8) ? reinterpret_cast<const uint64_t*>(idx->dev_blob + h.off_mrows8) : nullptr;
-    p.heads4 = (has_fast && h.off_mrows8) ? reinterpret_cast<const uint64_t*>(idx->dev_blob + h.off_heads4) : nullptr;
     p.msamp = (has_fast && ms) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_msamp) : nullptr;
     for (int i = 0; i < 4; i++) { p.mv_end_k[i] = h.mv_end_k[i]; p.mv_end_off[i] = h.mv_end_off[i]; p.mv_end_sl[i] = h.mv_end_sl[i]; }
     p.out_width = (uint32_t)width;

@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define SPB_FLAT_MAGIC 0x3030324250535F42ULL /* "B_SPB200" */
-#define SPB_FLAT_VERSION 5u
+#define SPB_FLAT_VERSION 6u
 #define SPB_RUN_PAD 64u  /* sentinel + padding run records past R (start = 2^40-1) */
 #define SPB_POS_MAX 0xFFFFFFFFFFULL
 
@@ -96,15 +96,15 @@ struct SpbMoveRow { uint32_t x, y, z, w; };
 // ---- compact move rows (8 bytes per run) --------------------------------------------------------
 // The walk is bound by how many DRAM lines it fetches per step, i.e. by the L2 hit rate of the row table
 // (a B200 keeps ~60 MB of a randomly gathered table resident: tools/gather_bench*, profiles/).  Indexes
-// with fewer than 2^24 runs therefore get rows half the size; the semantics are those of SpbMoveRow:
-//   bits  0-23 dest        24-30 len (1..SPB_MV8_LEN_MAX)     31-38 delta (0..SPB_MV8_DELTA_MAX)
-//   bits 39-40 fid         41    slow (also set when the head is not a fast symbol)
-//   bits 42-47 threshold class of jump slot 0/1/2: 0 never down | 1 always down | 2 down iff off < T | 3 generic step
-//   bits 48-54 T           the one in-run threshold of this row (two slots with different T: the second is class 3)
-//   bits 55-63 distance of jump slot 0/1/2 (3 bits each): 0 no later c-run | 1..SPB_MV8_DIST_SCAN-1 the next c-run is
-//              row k + d | SPB_MV8_DIST_SCAN search heads4 from row k + SPB_MV8_DIST_SCAN
-// heads4: one nibble per run (fid, SPB_SYM_SLOW for other heads and for padding), 16 runs per 64-bit word; the
-// kernel finds the next run headed by c with a carry-free zero-nibble test, SPB_MV8_SCAN_WORDS words at most.
+// with fewer than 2^24 runs therefore get rows half the size; the semantics are those of SpbMoveRow.
+// Every field lies inside one 32-bit half so that decoding needs no 64-bit shifts:
+//   lo:  bits  0-23 dest | 24-30 len (1..SPB_MV8_LEN_MAX) | 31 slow
+//   hi:  bits  0-7  delta (0..SPB_MV8_DELTA_MAX) | 8-10 fid (SPB_SYM_SLOW for other heads; then slow = 1)
+//        bits 11-16 threshold class of jump slot 0/1/2: 0 never down | 1 always down | 2 down iff off < T | 3 generic step
+//        bits 17-22 T    the one in-run threshold of this row (two slots with different T: the second is class 3)
+//        bits 23-31 distance of jump slot 0/1/2 (3 bits each): 0 no later c-run | 1..SPB_MV8_DIST_PROBE-1 the next
+//                   c-run is row k + d | SPB_MV8_DIST_PROBE it is row k + SPB_MV8_DIST_PROBE or later: the kernel
+//                   probes consecutive rows (fid == c?) from there, SPB_MV8_PROBES rows at most, then the generic step
 #ifndef SPB_MV8_LEN_MAX
 #define SPB_MV8_LEN_MAX 127u     /* the test build lowers these limits to exercise the fall-backs */
 #endif
@@ -112,16 +112,16 @@ struct SpbMoveRow { uint32_t x, y, z, w; };
 #define SPB_MV8_DELTA_MAX 255u
 #endif
 #ifndef SPB_MV8_T_MAX
-#define SPB_MV8_T_MAX 127u
+#define SPB_MV8_T_MAX 63u
 #endif
-#ifndef SPB_MV8_DIST_SCAN
-#define SPB_MV8_DIST_SCAN 7u
+#ifndef SPB_MV8_DIST_PROBE
+#define SPB_MV8_DIST_PROBE 7u
 #endif
-#ifndef SPB_MV8_SCAN_WORDS
-#define SPB_MV8_SCAN_WORDS 4u
+#ifndef SPB_MV8_PROBES
+#define SPB_MV8_PROBES 24u
 #endif
 #define SPB_MV8_MAX_RUNS (1ull << 24)
-#define SPB_MV8_HEADS_PAD 128u  /* padding nibbles past R (a multiple of 16, > 16 * SPB_MV8_SCAN_WORDS + 3) */
+#define SPB_MV8_ROW_PAD 64u      /* slow-flagged padding rows past R (probing may run past the last run) */
 
 struct SpbFlatHeader {
     uint64_t magic;
@@ -143,7 +143,8 @@ struct SpbFlatHeader {
     uint32_t mv_end_off[4];
     uint32_t pad0[3];
     uint64_t mv_end_sl[4];       // MS: samples_last of the last c-run
-    uint64_t off_mrows8, off_heads4;  // compact rows ((R + SPB_MV_ROW_PAD) * 8 bytes) + head nibbles; 0 if not applicable (then off_mrows != 0)
+    uint64_t off_mrows8;         // compact rows ((R + SPB_MV8_ROW_PAD) * 8 bytes); 0 if not applicable (then off_mrows != 0)
+    uint64_t reserved0;
     uint64_t F[256];
     SpbCharTab chartab[256];
 };

@@ -444,14 +444,12 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     }
     h.num_fast = num_fast;
     // row width: 8-byte rows whenever run indices fit 24 bits (SPUMONI_B200_ROWS=16 forces the wide rows, e.g. for tests)
-    bool rows8 = num_fast && R + SPB_MV_ROW_PAD < SPB_MV8_MAX_RUNS;
+    bool rows8 = num_fast && R + SPB_MV8_ROW_PAD < SPB_MV8_MAX_RUNS;
     if (const char* e = std::getenv("SPUMONI_B200_ROWS")) if (std::atoi(e) == 16) rows8 = false;
     if (num_fast) {
         if (rows8) {
             h.off_mrows8 = off;
-            off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(uint64_t), 256);
-            h.off_heads4 = off;
-            off = align_up(off + ((size_t)R + SPB_MV8_HEADS_PAD + 15) / 16 * sizeof(uint64_t), 256);
+            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(uint64_t), 256);
         } else {
             h.off_mrows = off;
             off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow), 256);
@@ -609,11 +607,12 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                     else { c3 = 2; T = v; }
                     cls |= c3 << (2 * slot);
                     const uint32_t k2 = nxt[(size_t)k * num_fast + s];
-                    const uint64_t dd = k2 == 0xFFFFFFFFu ? 0 : std::min<uint64_t>((uint64_t)k2 - k, SPB_MV8_DIST_SCAN);
+                    const uint64_t dd = k2 == 0xFFFFFFFFu ? 0 : std::min<uint64_t>((uint64_t)k2 - k, SPB_MV8_DIST_PROBE);
                     dist |= dd << (3 * slot);
                 }
-                rows_c[k] = (uint64_t)de | ((uint64_t)std::min<uint64_t>(len_k, SPB_MV8_LEN_MAX) << 24) | ((uint64_t)std::min<uint64_t>(delta, SPB_MV8_DELTA_MAX) << 31) |
-                            ((uint64_t)(hk & 3u) << 39) | ((uint64_t)(slow ? 1 : 0) << 41) | (cls << 42) | (T << 48) | (dist << 55);
+                const uint64_t lo = (uint64_t)de | ((uint64_t)std::min<uint64_t>(len_k, SPB_MV8_LEN_MAX) << 24) | ((uint64_t)(slow ? 1 : 0) << 31);
+                const uint64_t hi = (uint64_t)std::min<uint64_t>(delta, SPB_MV8_DELTA_MAX) | ((uint64_t)std::min<uint32_t>(hk, SPB_SYM_SLOW) << 8) | (cls << 11) | (T << 17) | (dist << 23);
+                rows_c[k] = lo | (hi << 32);
                 continue;
             }
             SpbMoveRow r;
@@ -625,19 +624,8 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
             rows[k] = r;
         }
         if (rows8) {
-            for (uint64_t k = R; k < R + SPB_MV_ROW_PAD; k++)  // row R = "pos == n": generic step only
-                rows_c[k] = (uint64_t)R | (1ull << 24) | (1ull << 41);
-            uint64_t* hw = reinterpret_cast<uint64_t*>(blob.data() + h.off_heads4);
-            const uint64_t words = (R + SPB_MV8_HEADS_PAD + 15) / 16;
-            for (uint64_t w = 0; w < words; w++) {
-                uint64_t v = 0;
-                for (uint64_t t = 0; t < 16; t++) {
-                    const uint64_t k = w * 16 + t;
-                    const uint64_t f = k < R ? std::min<uint32_t>(fid[d.heads[(size_t)k]], SPB_SYM_SLOW) : SPB_SYM_SLOW;
-                    v |= f << (4 * t);
-                }
-                hw[w] = v;
-            }
+            for (uint64_t k = R; k < R + SPB_MV8_ROW_PAD; k++)  // row R = "pos == n": generic step only
+                rows_c[k] = ((uint64_t)R | (1ull << 24) | (1ull << 31)) | ((uint64_t)(SPB_SYM_SLOW << 8) << 32);
         }
         for (uint64_t k = R; !rows8 && k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
             SpbMoveRow r;

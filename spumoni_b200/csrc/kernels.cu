@@ -335,10 +335,10 @@ __device__ __forceinline__ uint4 ld_row(const uint4* p) {
 }
 
 template <int LD>
-__device__ __forceinline__ uint64_t ld_row8(const uint64_t* p) {
-    uint64_t r;
-    if (LD == 0) asm volatile("ld.global.nc.L1::no_allocate.u64 %0, [%1];" : "=l"(r) : "l"(p));
-    else asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r) : "l"(p));
+__device__ __forceinline__ uint2 ld_row8(const uint64_t* p) {
+    uint2 r;
+    if (LD == 0) asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    else asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
     return r;
 }
 
@@ -548,7 +548,7 @@ struct BinState {
 };
 
 template <bool MS, bool STATS, int OW, int LD, bool ROW8>
-__global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
+__global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8 : SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
@@ -574,8 +574,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
     bool have = false, down = false;
     unsigned long long r = 0;
     uint64_t base = 0, end = 0, gi = 0;
-    uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2, 2 = SCAN (compact rows: search heads4)
-    uint32_t sk = 0, scan_left = 0, want = 0;
+    uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2 (compact rows: also probing for the c-run)
+    uint32_t want = 0, probes = 0;
     uint64_t sample = 0;
     uint32_t nsat = 0;
     BinState bs;
@@ -609,25 +609,24 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
         if (upper && c >= 'a' && c <= 'z') c -= 32;
         bool slow = false, emit = false;
         if (ROW8) {
-            const uint64_t* addr = mode == 2 ? p.heads4 + (sk >> 4) : p.rows8 + (mode ? k2 : k);
-            const uint64_t v = ld_row8<LD>(addr);
+            const uint2 v = ld_row8<LD>(p.rows8 + (mode ? k2 : k));  // x = lo, y = hi (flat_index.h)
             if (mode == 0) {
-                if ((v >> 41) & 1ull) slow = true;
+                if (v.x >> 31) slow = true;
                 else {
-                    const uint32_t len = (uint32_t)(v >> 24) & 0x7Fu;
+                    const uint32_t len = (v.x >> 24) & 0x7Fu;
                     if (off == SPB_MV_OFF_LAST) off = len - 1;
                     if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
-                    const uint32_t h = (uint32_t)(v >> 39) & 3u, s = s_fid[c];
+                    const uint32_t h = (v.y >> 8) & 7u, s = s_fid[c];
                     if (s >= SPB_SYM_SLOW) slow = true;
                     else if (s == h) {  // bwt[pos] == c (:250 / :582)
                         length++;
                         if (MS) sample--;
-                        off += (uint32_t)(v >> 31) & 0xFFu;
-                        k = (uint32_t)v & 0xFFFFFFu;
+                        off += v.y & 0xFFu;
+                        k = v.x & 0xFFFFFFu;
                         emit = true;
                     } else {  // threshold jump (:251-279 / :583-616)
                         const uint32_t slot = s - (s > h ? 1u : 0u);
-                        const uint32_t cls = (uint32_t)(v >> (42 + 2 * slot)) & 3u, dc = (uint32_t)(v >> (55 + 3 * slot)) & 7u;
+                        const uint32_t cls = (v.y >> (11 + 2 * slot)) & 3u, dc = (v.y >> (23 + 3 * slot)) & 7u;
                         if (cls == 3) slow = true;
                         else if (dc == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
                             k = s_end_k[s]; off = s_end_off[s];
@@ -635,36 +634,30 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, SPB_MV_MINB) spb_move_kernel(c
                             if (MS) sample = s_end_sl[s];
                             emit = true;
                         } else {
-                            down = (cls == 1) || (cls == 2 && off < ((uint32_t)(v >> 48) & 0x7Fu));
-                            if (dc < SPB_MV8_DIST_SCAN) { k2 = k + dc; mode = 1; }
-                            else { sk = k + SPB_MV8_DIST_SCAN; scan_left = SPB_MV8_SCAN_WORDS; want = s; mode = 2; }
+                            down = (cls == 1) || (cls == 2 && off < ((v.y >> 17) & 0x3Fu));
+                            k2 = k + dc; want = s; probes = SPB_MV8_PROBES;  // dc == SPB_MV8_DIST_PROBE: row k2 or a later one
+                            mode = 1;
                         }
                     }
                 }
-            } else if (mode == 2) {
-                // v = head nibbles of runs (sk & ~15) .. +15: first nibble == want at or after sk (carry-free zero-nibble test)
-                uint64_t x = v ^ (0x1111111111111111ull * want);
-                x |= x >> 1;
-                x |= x >> 2;
-                const uint64_t z = ~x & 0x1111111111111111ull & (~0ull << (4 * (sk & 15u)));
-                if (z) { k2 = (sk & ~15u) + (uint32_t)((__ffsll((long long)z) - 1) >> 2); mode = 1; }
-                else if (--scan_left == 0) { mode = 0; slow = true; }
-                else sk = (sk & ~15u) + 16;
-                if (!slow) continue;
             } else {
-                mode = 0;
-                if ((v >> 41) & 1ull) slow = true;  // landing state not encodable: redo the step from (k, off)
-                else {
-                    const uint32_t d2 = (uint32_t)(v >> 31) & 0xFFu, de = (uint32_t)v & 0xFFFFFFu;
-                    if (MS) {
-                        const uint4 sm = ldg_nc16(p.msamp + k2);
-                        sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                if (((v.y >> 8) & 7u) != want) {  // not headed by c yet: probe the next row
+                    if (--probes == 0) { mode = 0; slow = true; } else { k2++; continue; }
+                } else {
+                    mode = 0;
+                    if (v.x >> 31) slow = true;  // landing state not encodable: redo the step from (k, off)
+                    else {
+                        const uint32_t d2 = v.y & 0xFFu, de = v.x & 0xFFFFFFu;
+                        if (MS) {
+                            const uint4 sm = ldg_nc16(p.msamp + k2);
+                            sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                        }
+                        if (!down) { k = de; off = d2; }
+                        else if (d2) { k = de; off = d2 - 1; }
+                        else { k = de - 1; off = SPB_MV_OFF_LAST; }
+                        length = 0;
+                        emit = true;
                     }
-                    if (!down) { k = de; off = d2; }
-                    else if (d2) { k = de; off = d2 - 1; }
-                    else { k = de - 1; off = SPB_MV_OFF_LAST; }
-                    length = 0;
-                    emit = true;
                 }
             }
         } else {

@@ -33,8 +33,7 @@ struct WalkParams {
     unsigned long long* work_counter;  // zeroed before launch
     // thread-per-read kernels over the move rows; rows == nullptr when the index has no fast symbols
     const uint4* rows;         // 16-byte move rows, or
-    const uint64_t* rows8;     // 8-byte compact rows + head nibbles (exactly one of rows / rows8 is set)
-    const uint64_t* heads4;
+    const uint64_t* rows8;     // 8-byte compact rows (exactly one of rows / rows8 is set)
     const uint4* msamp;        // MS only
     uint32_t mv_end_k[4], mv_end_off[4];
     uint64_t mv_end_sl[4];

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQ"  # up to off_heads4 (then F[256], chartab[256])
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQ"  # up to reserved0 (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -23,7 +23,7 @@ class FlatImage:
          self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position, self.off_mrows,
          self.off_msamp, self.num_fast, *rest) = struct.unpack_from(HDR_FMT, b, 0)
         self.fast_sym, self.mv_end_k, self.mv_end_off, self.mv_end_sl = rest[0:4], rest[4:8], rest[8:12], rest[15:19]
-        self.off_mrows8, self.off_heads4 = rest[19], rest[20]
+        self.off_mrows8 = rest[19]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -34,8 +34,7 @@ class FlatImage:
         self.crec = np.frombuffer(b, dtype=np.uint32, count=4 * (self.num_crec + 1), offset=self.off_crec).reshape(-1, 4)
         if self.num_fast:
             if self.off_mrows8:
-                self.rows8 = np.frombuffer(b, dtype=np.uint64, count=self.R + 16, offset=self.off_mrows8)
-                self.heads4 = np.frombuffer(b, dtype=np.uint64, count=(self.R + 128 + 15) // 16, offset=self.off_heads4)
+                self.rows8 = np.frombuffer(b, dtype=np.uint64, count=self.R + 64, offset=self.off_mrows8)
             else:
                 self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
             if self.mode == 1:
@@ -168,7 +167,7 @@ class FlatImage:
         ct = self.chartab[c]
         return 5 if ct[3] == 0xFFFFFFFF else ct[2]
 
-    def walk_move8(self, read: bytes, scan_words=4, dist_scan=7):
+    def walk_move8(self, read: bytes, probes=24):
         """Compact 8-byte rows (spb_move_kernel<ROW8>). Returns (lengths, pointers or None, stats)."""
         assert self.num_fast and self.off_mrows8
         ms = self.mode == 1
@@ -176,16 +175,17 @@ class FlatImage:
         m, R = len(read), self.R
         k, off, length, sample = R - 1, LAST, 0, self.last_run_sample
         out, ptr = [0] * m, [0] * m
-        stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0, "scan": 0}
+        stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0, "probe": 0}
         for gi in range(m - 1, -1, -1):
             c = read[gi]
             slow = False
             while True:
                 v = int(self.rows8[k])
-                if (v >> 41) & 1:
+                lo, hi = v & 0xFFFFFFFF, v >> 32
+                if lo >> 31:
                     slow = True
                     break
-                ln = (v >> 24) & 0x7F
+                ln = (lo >> 24) & 0x7F
                 if off == LAST:
                     off = ln - 1
                 if off >= ln:
@@ -195,47 +195,43 @@ class FlatImage:
                     continue
                 break
             if not slow:
-                h, s = (v >> 39) & 3, self.fid(c)
+                h, s = (hi >> 8) & 7, self.fid(c)
                 if s >= 4:
                     slow = True
                 elif s == h:
                     length += 1
                     sample = (sample - 1) & U64
-                    k, off = v & 0xFFFFFF, off + ((v >> 31) & 0xFF)
+                    k, off = lo & 0xFFFFFF, off + (hi & 0xFF)
                 else:
                     slot = s - (1 if s > h else 0)
-                    cls, dc = (v >> (42 + 2 * slot)) & 3, (v >> (55 + 3 * slot)) & 7
+                    cls, dc = (hi >> (11 + 2 * slot)) & 3, (hi >> (23 + 3 * slot)) & 7
                     if cls == 3:
                         slow = True
                     elif dc == 0:
                         k, off, length, sample = self.mv_end_k[s], self.mv_end_off[s], 0, self.mv_end_sl[s]
                         stats["end"] += 1
                     else:
-                        down = cls == 1 or (cls == 2 and off < ((v >> 48) & 0x7F))
-                        k2 = None
-                        if dc < dist_scan:
-                            k2 = k + dc
-                        else:
-                            sk, left = k + dist_scan, scan_words
-                            while k2 is None and left:
-                                stats["scan"] += 1
-                                w = int(self.heads4[sk >> 4])
-                                for t in range(sk & 15, 16):
-                                    if (w >> (4 * t)) & 15 == s:
-                                        k2 = (sk & ~15) + t
-                                        break
-                                sk = (sk & ~15) + 16
-                                left -= 1
+                        down = cls == 1 or (cls == 2 and off < ((hi >> 17) & 0x3F))
+                        k2, left = k + dc, probes
+                        while True:
+                            v2 = int(self.rows8[k2])
+                            lo2, hi2 = v2 & 0xFFFFFFFF, v2 >> 32
+                            if (hi2 >> 8) & 7 == s:
+                                break
+                            stats["probe"] += 1
+                            left -= 1
+                            if left == 0:
+                                k2 = None
+                                break
+                            k2 += 1
                         if k2 is None:
                             slow = True
                         else:
-                            v2 = int(self.rows8[k2])
                             stats["jump2"] += 1
-                            if (v2 >> 41) & 1:
+                            if lo2 >> 31:
                                 slow = True
                             else:
-                                assert (v2 >> 39) & 3 == s
-                                d2, de = (v2 >> 31) & 0xFF, v2 & 0xFFFFFF
+                                d2, de = hi2 & 0xFF, lo2 & 0xFFFFFF
                                 if ms:
                                     sample = int(self.msamp[k2][1 if down else 0])
                                 if not down:
@@ -256,7 +252,7 @@ class FlatImage:
     def walk_rows(self, read: bytes, **kw):
         """Whichever row table the image holds."""
         if self.off_mrows8:
-            return self.walk_move8(read, **{k: v for k, v in kw.items() if k in ("scan_words", "dist_scan")})
+            return self.walk_move8(read, **{k: v for k, v in kw.items() if k in ("probes",)})
         return self.walk_move(read, **{k: v for k, v in kw.items() if k in ("len_bits", "dist_far")})
 
     def walk_move(self, read: bytes, len_bits=20, dist_far=31):

@@ -150,9 +150,9 @@ def test_move_rows_saturation_fallbacks_host_side(tmp_path, row_width):
         for i in range(len(read)):
             if rng.random() < 0.05:
                 read[i] = rng.choice(b"ACGTN")
-        got, _, st = imgs[0].walk_rows(bytes(read), len_bits=3, dist_far=3, scan_words=1, dist_scan=3)
+        got, _, st = imgs[0].walk_rows(bytes(read), len_bits=3, dist_far=3, probes=2)
         assert got == po.matching_statistics(bytes(read)).tolist()
-        _, ptr, _ = imgs[1].walk_rows(bytes(read), len_bits=3, dist_far=3, scan_words=1, dist_scan=3)
+        _, ptr, _ = imgs[1].walk_rows(bytes(read), len_bits=3, dist_far=3, probes=2)
         assert ptr == mo.matching_statistics(bytes(read))[1].tolist()
         for key in tot:
             tot[key] += st[key]
