@@ -33,8 +33,9 @@
 extern "C" {
 #endif
 
-#define SPB_ABI_VERSION 2
+#define SPB_ABI_VERSION 3
 #define SPB_QUERY_TOUPPER 1u
+#define SPB_OPEN_DOC 1u /* spb_index_open_ex: also load <ref_file>.doc (the reference's use_doc / -d) */
 
 typedef enum {
     SPB_OK = 0,
@@ -92,6 +93,9 @@ int spb_abi_version(void);
  * device layout.  MS mode takes the text from <ref_file> itself (the FASTA written by
  * `spumoni build`) instead of <ref_file>.slp -- see DESIGN.md. */
 int spb_index_open(const char* ref_file, int mode, spb_index** out);
+/* Same with flags.  SPB_OPEN_DOC: pml_t / ms_t constructed with use_doc = true (compute_ms_pml.cpp:712-720, :777-785)
+ * -> DocumentArray::load of <ref_file>.doc (doc_array.cpp:197-201); enables the *_doc queries below. */
+int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index** out);
 
 /* get_bwt_stats() compute_ms_pml.cpp:171-173 / :484-486 */
 int spb_index_stats(const spb_index* idx, uint64_t* n, uint64_t* r);
@@ -140,6 +144,24 @@ int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t*
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                         void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
                         const spb_query_opts* opts, void* cuda_stream);
+
+/* Document-number variants: pml_t::matching_statistics(read, len, lengths, doc_nums) compute_ms_pml.cpp:734-737 ->
+ * pml_pointers::_query :288-340, and ms_t::matching_statistics(read, len, lengths, pointers, doc_nums) :814-828 ->
+ * ms_pointers::_query :625-682.  doc_nums[offsets[i] + j] is the document of position j of read i.  The index must
+ * have been opened with SPB_OPEN_DOC; lengths are uint32_t (opts->length_bytes 0 or 4); thread-per-read kernels only. */
+int spb_pml_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                           uint32_t* lengths, uint32_t* doc_nums, spb_bin_stats* stats, const spb_query_opts* opts);
+int spb_ms_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                          uint32_t* lengths, uint64_t* pointers, uint32_t* doc_nums, spb_bin_stats* stats,
+                          const spb_query_opts* opts);
+int spb_pml_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                             uint32_t* d_lengths, uint32_t* d_doc_nums, spb_bin_stats* d_stats,
+                             const spb_query_opts* opts, void* cuda_stream);
+int spb_ms_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                            uint32_t* d_lengths, uint64_t* d_pointers, uint32_t* d_doc_nums, spb_bin_stats* d_stats,
+                            const spb_query_opts* opts, void* cuda_stream);
+/* number of documents in the loaded document array (0 if the index was opened without it) */
+uint32_t spb_index_num_docs(const spb_index* idx);
 
 /* ---- classification helpers ---------------------------------------------------------- */
 /* EmpNullDatabase::load emp_null_database.cpp:104-110 */

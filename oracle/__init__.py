@@ -36,6 +36,10 @@ def lib() -> ctypes.CDLL:
         L.orc_query_batch.restype = ctypes.c_double
         L.orc_query_batch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.orc_load_doc.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+        L.orc_query_batch_doc.restype = ctypes.c_double
+        L.orc_query_batch_doc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         L.orc_run.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_nulldb_percentile.restype = ctypes.c_double
@@ -47,10 +51,12 @@ def lib() -> ctypes.CDLL:
 class OracleIndex:
     """Reference-shaped index object: ``pml_t`` (mode 'pml') or ``ms_t`` (mode 'ms')."""
 
-    def __init__(self, ref_file: str, mode: str = "pml"):
+    def __init__(self, ref_file: str, mode: str = "pml", use_doc: bool = False):
         self.mode = mode
         self._h = lib().orc_open(ref_file.encode(), 1 if mode == "ms" else 0)
         if not self._h:
+            raise RuntimeError(lib().orc_last_error().decode())
+        if use_doc and lib().orc_load_doc(self._h, ref_file.encode()):  # pml_t/ms_t(filename, use_doc=true)
             raise RuntimeError(lib().orc_last_error().decode())
 
     def close(self):
@@ -90,11 +96,25 @@ class OracleIndex:
         return sec, L, P
 
 
+    def query_batch_doc(self, reads: np.ndarray, offsets: np.ndarray, threads: int = 1):
+        """Document-number variant (index opened with use_doc). Returns (lengths, pointers or None, doc_nums)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n, total = len(offsets) - 1, int(offsets[-1])
+        L, D = np.zeros(total, dtype=np.uint64), np.zeros(total, dtype=np.uint64)
+        P = np.zeros(total, dtype=np.uint64) if self.mode == "ms" else None
+        sec = lib().orc_query_batch_doc(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
+                                        P.ctypes.data if P is not None else None, D.ctypes.data, threads)
+        if sec < 0:
+            raise RuntimeError("oracle index was opened without its document array")
+        return L, P, D
+
+
 def run(ref_file: str, pattern_file: str, mode: str = "pml", report: bool = False, bin_width: int = 150,
-        threads: int = 1):
+        threads: int = 1, use_doc: bool = False):
     """File-to-file `spumoni run` restatement; returns (num_reads, seconds)."""
     nr, sec = ctypes.c_uint64(), ctypes.c_double()
-    rc = lib().orc_run(ref_file.encode(), pattern_file.encode(), 1 if mode == "ms" else 0, int(report), bin_width,
+    rc = lib().orc_run(ref_file.encode(), pattern_file.encode(), 1 if mode == "ms" else 0, int(report) | (2 if use_doc else 0), bin_width,
                        threads, ctypes.byref(nr), ctypes.byref(sec))
     if rc:
         raise RuntimeError(lib().orc_last_error().decode())

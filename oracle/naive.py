@@ -23,6 +23,8 @@ Reference lines followed (all under /root/reference):
   * read_samples              src/compute_ms_pml.cpp:404-439
   * thr_bv ctor / operator[]  include/thresholds_ds.hpp:384-440, :478-491
   * bin-max classifier        src/compute_ms_pml.cpp:969-995
+  * DocumentArray ctor        src/doc_array.cpp:18-108
+  * _query with doc numbers   src/compute_ms_pml.cpp:288-340 (PML), :625-682 (MS)
 """
 from __future__ import annotations
 
@@ -255,6 +257,104 @@ def ms_pointers_query(idx: NaiveIndex, pattern: bytes) -> List[int]:
         ptrs[m - i - 1] = sample
         pos = idx.LF(pos, cu)
     return ptrs
+
+
+def build_doc_array(idx: NaiveIndex, seq_lengths: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """DocumentArray::DocumentArray, src/doc_array.cpp:18-108: (start_runs_doc, end_runs_doc).
+    seq_lengths = per-document text lengths (the .fdi file); the terminator belongs to the last document."""
+    end_pos = []
+    acc = 0
+    for ln in seq_lengths:
+        acc += ln
+        end_pos.append(acc)
+    end_pos[-1] += 1  # :43-44
+
+    def doc_of(sample: int) -> int:  # convert_to_bwt_pos (:47-50) + rank over doc_ends (:66-90)
+        pos = sample - 1 if sample > 0 else end_pos[-1] - 1
+        return sum(1 for e in end_pos if e - 1 < pos)
+
+    start = [doc_of(idx.sa[s]) for s in idx.starts]
+    end = [doc_of(idx.sa[s + l - 1]) for s, l in zip(idx.starts, idx.lens)]
+    return start, end
+
+
+def pml_query_doc(idx: NaiveIndex, pattern: bytes, start_doc: Sequence[int], end_doc: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """pml_pointers::_query with document numbers, src/compute_ms_pml.cpp:288-340 (literal)."""
+    m = len(pattern)
+    lengths, docs = [0] * m, [0] * m
+    pos = idx.n - 1
+    length = 0
+    curr_doc_id = end_doc[len(idx.heads) - 1]
+    for i in range(m):
+        cu = pattern[m - i - 1]
+        c = _as_signed_char(cu)
+        if idx.number_of_letter(cu) == 0:
+            length = 0
+        elif pos < idx.n and idx.bwt[pos] == c:
+            length += 1
+        else:
+            rnk = idx.rank(pos, cu)
+            thr = idx.n + 1
+            next_pos = pos
+            if rnk < idx.number_of_letter(cu):
+                j = idx.select(rnk, cu)
+                run_of_j = idx.run_of_position(j)
+                thr = idx.threshold(run_of_j)
+                curr_doc_id = start_doc[run_of_j]
+                length = 0
+                next_pos = j
+            if pos < thr:
+                rnk -= 1
+                j = idx.select(rnk, cu)
+                run_of_j = idx.run_of_position(j)
+                curr_doc_id = end_doc[run_of_j]
+                length = 0
+                next_pos = j
+            pos = next_pos
+        lengths[m - i - 1] = length
+        docs[m - i - 1] = curr_doc_id
+        pos = idx.LF(pos, cu)
+    return lengths, docs
+
+
+def ms_pointers_query_doc(idx: NaiveIndex, pattern: bytes, start_doc: Sequence[int], end_doc: Sequence[int]) -> Tuple[List[int], List[int]]:
+    """ms_pointers::_query with document numbers, src/compute_ms_pml.cpp:625-682 (literal)."""
+    m = len(pattern)
+    ptrs, docs = [0] * m, [0] * m
+    pos = idx.n - 1
+    sample = idx.get_last_run_sample()
+    curr_doc_id = end_doc[len(idx.heads) - 1]
+    for i in range(m):
+        cu = pattern[m - i - 1]
+        c = _as_signed_char(cu)
+        if idx.number_of_letter(cu) == 0:
+            sample = 0
+            curr_doc_id = start_doc[idx.run_of_position(sample)]  # :640-642 (App. C-12)
+        elif pos < idx.n and idx.bwt[pos] == c:
+            sample = (sample - 1) & U64
+        else:
+            rnk = idx.rank(pos, cu)
+            thr = idx.n + 1
+            next_pos = pos
+            if rnk < idx.number_of_letter(cu):
+                j = idx.select(rnk, cu)
+                run_of_j = idx.run_of_position(j)
+                thr = idx.threshold(run_of_j)
+                sample = idx.samples_start[run_of_j]
+                curr_doc_id = start_doc[run_of_j]
+                next_pos = j
+            if pos < thr:
+                rnk -= 1
+                j = idx.select(rnk, cu)
+                run_of_j = idx.run_of_position(j)
+                sample = idx.samples_last[run_of_j]
+                curr_doc_id = end_doc[run_of_j]
+                next_pos = j
+            pos = next_pos
+        ptrs[m - i - 1] = sample
+        docs[m - i - 1] = curr_doc_id
+        pos = idx.LF(pos, cu)
+    return ptrs, docs
 
 
 def ms_lengths(idx: NaiveIndex, read: bytes, pointers: Sequence[int]) -> List[int]:

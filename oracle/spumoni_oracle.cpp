@@ -24,6 +24,8 @@
 //   thr_bv::operator[] / load         include/thresholds_ds.hpp:478-491, :517-523
 //   BatchLoader                       src/batch_loader.cpp:26-131
 //   EmpNullDatabase::load             src/emp_null_database.cpp:104-110
+//   DocumentArray::load               src/doc_array.cpp:197-201
+//   _query with document numbers      src/compute_ms_pml.cpp:288-340 (PML), :625-682 (MS), ms_t :814-828
 //   my_load                           include/common.hpp:487-495
 //   ri::rle_string / sparse_sd_vector / huff_string, sdsl::sd_vector / wt_huff / int_vector:
 //   third party, restated from their published sources.
@@ -375,6 +377,20 @@ static std::vector<uint8_t> slurp(const std::string& path) {
 }
 
 // ------------------------------------------------------------------ pml_pointers / ms_pointers
+// DocumentArray (src/doc_array.cpp:184-201): document of the BWT character at the start / end of every run
+struct DocArray {
+    ulint num_entries = 0;
+    IntVector start_runs_doc, end_runs_doc;
+    void load(const std::string& path) {
+        std::vector<uint8_t> buf = slurp(path);
+        Cursor c{buf.data(), buf.data() + buf.size()};
+        num_entries = c.get<uint64_t>();
+        start_runs_doc.load(c, 0);
+        end_runs_doc.load(c, 0);
+        if (c.p != c.end) throw std::runtime_error("oracle: trailing bytes in " + path);
+    }
+};
+
 struct Pointers {
     bool is_ms = false;
     ulint terminator_position = 0;
@@ -433,6 +449,86 @@ struct Pointers {
             pos = LF(pos, c);
         }
     }
+    // pml_pointers::_query with document numbers  (src/compute_ms_pml.cpp:288-340)
+    void query_pml(const char* pattern, size_t m, std::vector<size_t>& lengths, std::vector<size_t>& doc_nums, const DocArray& doc_arr) const {
+        lengths.resize(m);
+        doc_nums.resize(m);
+        auto pos = bwt_size() - 1;
+        auto length = 0;
+        size_t curr_doc_id = doc_arr.end_runs_doc[bwt.number_of_runs() - 1];
+        for (size_t i = 0; i < m; ++i) {
+            auto c = pattern[m - i - 1];
+            if (bwt.number_of_letter(c) == 0) { length = 0; }
+            else if (pos < bwt.size() && bwt[pos] == c) { length++; }
+            else {
+                ulint rnk = bwt.rank(pos, c);
+                size_t thr = bwt.size() + 1;
+                ulint next_pos = pos;
+                if (rnk < bwt.number_of_letter(c)) {
+                    ulint j = bwt.select(rnk, c);
+                    ulint run_of_j = bwt.run_of_position(j);
+                    thr = thresholds[run_of_j];
+                    curr_doc_id = doc_arr.start_runs_doc[run_of_j];
+                    length = 0;
+                    next_pos = j;
+                }
+                if (pos < thr) {
+                    rnk--;
+                    ulint j = bwt.select(rnk, c);
+                    ulint run_of_j = bwt.run_of_position(j);
+                    curr_doc_id = doc_arr.end_runs_doc[run_of_j];
+                    length = 0;
+                    next_pos = j;
+                }
+                pos = next_pos;
+            }
+            lengths[m - i - 1] = length;
+            doc_nums[m - i - 1] = curr_doc_id;
+            pos = LF(pos, c);
+        }
+    }
+    // ms_pointers::_query with document numbers  (src/compute_ms_pml.cpp:625-682)
+    void query_ms(const char* pattern, size_t m, std::vector<size_t>& ptrs, std::vector<size_t>& doc_nums, const DocArray& doc_arr) const {
+        ptrs.resize(m);
+        doc_nums.resize(m);
+        auto pos = bwt_size() - 1;
+        auto sample = get_last_run_sample();
+        size_t curr_doc_id = doc_arr.end_runs_doc[bwt.number_of_runs() - 1];
+        for (size_t i = 0; i < m; ++i) {
+            auto c = pattern[m - i - 1];
+            if (bwt.number_of_letter(c) == 0) {
+                sample = 0;
+                ulint run_of_j = bwt.run_of_position(sample);  // a text position used as a BWT position
+                curr_doc_id = doc_arr.start_runs_doc[run_of_j];
+            }
+            else if (pos < bwt.size() && bwt[pos] == c) { sample--; }
+            else {
+                ulint rnk = bwt.rank(pos, c);
+                size_t thr = bwt.size() + 1;
+                ulint next_pos = pos;
+                if (rnk < bwt.number_of_letter(c)) {
+                    ulint j = bwt.select(rnk, c);
+                    ulint run_of_j = bwt.run_of_position(j);
+                    thr = thresholds[run_of_j];
+                    sample = samples_start[run_of_j];
+                    curr_doc_id = doc_arr.start_runs_doc[run_of_j];
+                    next_pos = j;
+                }
+                if (pos < thr) {
+                    rnk--;
+                    ulint j = bwt.select(rnk, c);
+                    ulint run_of_j = bwt.run_of_position(j);
+                    sample = samples_last[run_of_j];
+                    curr_doc_id = doc_arr.end_runs_doc[run_of_j];
+                    next_pos = j;
+                }
+                pos = next_pos;
+            }
+            ptrs[m - i - 1] = sample;
+            doc_nums[m - i - 1] = curr_doc_id;
+            pos = LF(pos, c);
+        }
+    }
     // ms_pointers::_query  (src/compute_ms_pml.cpp:570-623)
     void query_ms(const char* pattern, size_t m, std::vector<size_t>& ptrs) const {
         ptrs.resize(m);
@@ -484,12 +580,30 @@ static std::string load_fasta_text(const std::string& path) {
 
 struct PmlT {
     Pointers ms;
+    DocArray doc_arr;
     void matching_statistics(const char* read, size_t len, std::vector<size_t>& lengths) const { ms.query_pml(read, len, lengths); }
+    void matching_statistics(const char* read, size_t len, std::vector<size_t>& lengths, std::vector<size_t>& doc_nums) const {
+        ms.query_pml(read, len, lengths, doc_nums, doc_arr);
+    }
 };
 struct MsT {
     Pointers ms;
+    DocArray doc_arr;
     std::string ra;
     size_t n = 0;
+    // ms_t::matching_statistics with document numbers  (src/compute_ms_pml.cpp:814-828)
+    void matching_statistics(const char* read, size_t read_length, std::vector<size_t>& lengths, std::vector<size_t>& pointers,
+                             std::vector<size_t>& doc_nums) const {
+        ms.query_ms(read, read_length, pointers, doc_nums, doc_arr);
+        lengths.resize(read_length);
+        size_t l = 0;
+        for (size_t i = 0; i < pointers.size(); ++i) {
+            size_t pos = pointers[i];
+            while ((i + l) < read_length && (pos + l) < n && (i < 1 || pos != (pointers[i - 1] + 1)) && read[i + l] == ra[pos + l]) ++l;
+            lengths[i] = l;
+            l = (l == 0 ? 0 : (l - 1));
+        }
+    }
     // ms_t::matching_statistics  (src/compute_ms_pml.cpp:795-812)
     void matching_statistics(const char* read, size_t read_length, std::vector<size_t>& lengths, std::vector<size_t>& pointers) const {
         ms.query_ms(read, read_length, pointers);
@@ -600,15 +714,17 @@ static void report_row(std::ofstream& f, const std::string& id, const BinStats& 
 
 struct RunOpts {
     std::string ref_file, pattern_file;  // ref_file already has ".fa" appended (spumoni.cpp:744-747)
-    bool ms = false, write_report = false;
+    bool ms = false, write_report = false, use_doc = false;
     size_t threads = 1, bin_width = 150;
 };
 
 // classify_reads_pml (src/compute_ms_pml.cpp:845-1034) / classify_reads_ms (:1036-1217), raw-DNA (-n) path
 static size_t classify_reads(const PmlT* pml, const MsT* mst, const RunOpts& o, double* seconds) {
     std::ofstream lengths_file(o.pattern_file + (o.ms ? ".lengths" : ".pseudo_lengths"));
-    std::ofstream pointers_file, report_file;
+    std::ofstream pointers_file, report_file, doc_file;
     if (o.ms) pointers_file.open(o.pattern_file + ".pointers");
+    if (o.use_doc) doc_file.open(o.pattern_file + ".doc_numbers");
+    std::ostream_iterator<size_t> doc_iter(doc_file, " ");
     std::ostream_iterator<size_t> lengths_iter(lengths_file, " ");
     std::ostream_iterator<size_t> pointers_iter(pointers_file, " ");
     if (o.write_report) report_file.open(o.pattern_file + ".report", std::ofstream::out);
@@ -641,15 +757,25 @@ static size_t classify_reads(const PmlT* pml, const MsT* mst, const RunOpts& o, 
                     std::fprintf(stderr, "Warning: %s was empty after digestion\n\n", rs.id.data());
                     std::exit(1);
                 }
-                std::vector<size_t> lengths, pointers;
-                if (o.ms) mst->matching_statistics(curr_read.c_str(), curr_read.size(), lengths, pointers);
-                else pml->matching_statistics(curr_read.c_str(), curr_read.size(), lengths);
+                std::vector<size_t> lengths, pointers, doc_nums;
+                if (o.ms) {
+                    if (o.use_doc) mst->matching_statistics(curr_read.c_str(), curr_read.size(), lengths, pointers, doc_nums);
+                    else mst->matching_statistics(curr_read.c_str(), curr_read.size(), lengths, pointers);
+                } else {
+                    if (o.use_doc) pml->matching_statistics(curr_read.c_str(), curr_read.size(), lengths, doc_nums);
+                    else pml->matching_statistics(curr_read.c_str(), curr_read.size(), lengths);
+                }
                 BinStats bs{false, 0, 0, 0, 0};
                 if (o.write_report) bs = classify(lengths, o.bin_width, max_value_thr);
 #pragma omp atomic
                 num_reads++;
 #pragma omp critical
                 {
+                    if (o.use_doc) {
+                        doc_file << '>' << rs.id << '\n';
+                        std::copy(doc_nums.begin(), doc_nums.end(), doc_iter);
+                        doc_file << '\n';
+                    }
                     lengths_file << '>' << rs.id << '\n';
                     std::copy(lengths.begin(), lengths.end(), lengths_iter);
                     lengths_file << '\n';
@@ -672,7 +798,7 @@ static size_t classify_reads(const PmlT* pml, const MsT* mst, const RunOpts& o, 
 // ====================================================================== C interface (ctypes)
 static thread_local std::string g_err;
 struct OrcHandle {
-    bool ms = false;
+    bool ms = false, has_doc = false;
     orc::PmlT pml;
     orc::MsT mst;
 };
@@ -700,6 +826,19 @@ void* orc_open(const char* ref_file, int mode) {
         return nullptr;
     }
 }
+// pml_t / ms_t constructor with use_doc (src/compute_ms_pml.cpp:712-720, :777-785): loads <ref_file>.doc
+int orc_load_doc(void* hv, const char* ref_file) {
+    OrcHandle* h = (OrcHandle*)hv;
+    try {
+        orc::DocArray& d = h->ms ? h->mst.doc_arr : h->pml.doc_arr;
+        d.load(std::string(ref_file) + ".doc");
+        h->has_doc = true;
+        return 0;
+    } catch (std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
 void orc_close(void* h) { delete (OrcHandle*)h; }
 void orc_stats(void* hv, uint64_t* n, uint64_t* r) {
     OrcHandle* h = (OrcHandle*)hv;
@@ -721,6 +860,27 @@ int orc_query(void* hv, const char* read, uint64_t m, uint64_t* lengths, uint64_
 }
 // batch over concatenated reads (in-memory timing leg): returns seconds spent in the query loop.
 // The per-read std::vector allocation of the reference is kept inside the loop on purpose.
+double orc_query_batch_doc(void* hv, const uint8_t* reads, const uint64_t* off, uint64_t n_reads, uint64_t* lengths,
+                           uint64_t* pointers, uint64_t* docs, int threads) {
+    OrcHandle* h = (OrcHandle*)hv;
+    if (!h->has_doc) return -1.0;
+#ifdef _OPENMP
+    omp_set_num_threads(threads > 0 ? threads : 1);
+#endif
+    auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t r = 0; r < (int64_t)n_reads; r++) {
+        std::vector<size_t> L, P, D;
+        const char* s = (const char*)reads + off[r];
+        size_t m = (size_t)(off[r + 1] - off[r]);
+        if (h->ms) h->mst.matching_statistics(s, m, L, P, D);
+        else h->pml.matching_statistics(s, m, L, D);
+        if (lengths) std::copy(L.begin(), L.end(), lengths + off[r]);
+        if (pointers && h->ms) std::copy(P.begin(), P.end(), pointers + off[r]);
+        if (docs) std::copy(D.begin(), D.end(), docs + off[r]);
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
 double orc_query_batch(void* hv, const uint8_t* reads, const uint64_t* off, uint64_t n_reads, uint64_t* lengths,
                        uint64_t* pointers, int threads) {
     OrcHandle* h = (OrcHandle*)hv;
@@ -743,8 +903,11 @@ double orc_query_batch(void* hv, const uint8_t* reads, const uint64_t* off, uint
 // `spumoni run -r <prefix> -p <pattern> -P|-M -n [-c] [-w bin] [-t threads]` file-to-file
 int orc_run(const char* ref_file, const char* pattern_file, int mode, int write_report, uint64_t bin_width,
             int threads, uint64_t* num_reads, double* seconds) {
+    const int use_doc = (write_report >> 1) & 1;  // bit 1 of write_report: -d
+    write_report &= 1;
     try {
         orc::RunOpts o;
+        o.use_doc = use_doc != 0;
         o.ref_file = ref_file;
         o.pattern_file = pattern_file;
         o.ms = mode == 1;
@@ -753,6 +916,7 @@ int orc_run(const char* ref_file, const char* pattern_file, int mode, int write_
         o.threads = threads > 0 ? threads : 1;
         OrcHandle* h = (OrcHandle*)orc_open(ref_file, mode);
         if (!h) return 1;
+        if (use_doc && orc_load_doc(h, ref_file)) { delete h; return 1; }
         size_t nr = orc::classify_reads(o.ms ? nullptr : &h->pml, o.ms ? &h->mst : nullptr, o, seconds);
         if (num_reads) *num_reads = nr;
         delete h;
@@ -794,12 +958,13 @@ int main(int argc, char** argv) {
         else if (a == "-p" && i + 1 < argc) pat = argv[++i];
         else if (a == "-P") mode = 0;
         else if (a == "-M") mode = 1;
-        else if (a == "-c") report = 1;
+        else if (a == "-c") report |= 1;
+        else if (a == "-d") report |= 2;
         else if (a == "-w" && i + 1 < argc) bin = std::strtoull(argv[++i], nullptr, 10);
         else if (a == "-t" && i + 1 < argc) threads = std::atoi(argv[++i]);
         else { std::fprintf(stderr, "oracle: unknown option %s\n", a.c_str()); return 1; }
     }
-    if (ref.empty() || pat.empty() || mode < 0) { std::fprintf(stderr, "usage: spumoni_oracle run -r PREFIX -p READS.fa -P|-M -n [-c] [-w N] [-t N]\n"); return 1; }
+    if (ref.empty() || pat.empty() || mode < 0) { std::fprintf(stderr, "usage: spumoni_oracle run -r PREFIX -p READS.fa -P|-M -n [-c] [-d] [-w N] [-t N]\n"); return 1; }
     uint64_t nr = 0;
     double sec = 0;
     if (orc_run((ref + ".fa").c_str(), pat.c_str(), mode, report, bin, threads, &nr, &sec)) {

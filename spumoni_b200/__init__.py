@@ -25,6 +25,7 @@ SATTEST_LIB_PATH = os.path.join(_HERE, "lib", "libspumoni_b200_sattest.so")  # t
 CLI_PATH = os.path.join(_HERE, "bin", "spumoni")
 MODE_PML, MODE_MS = 0, 1
 QUERY_TOUPPER = 1
+OPEN_DOC = 1
 ERR_OVERFLOW = 7
 _LEN_DTYPES = {4: np.uint32, 2: np.uint16, 1: np.uint8}
 
@@ -71,6 +72,13 @@ def load_library() -> ctypes.CDLL:
     L.spb_last_error.restype = cp
     L.spb_abi_version.restype = i32
     L.spb_index_open.argtypes = [cp, i32, ctypes.POINTER(vp)]
+    L.spb_index_open_ex.argtypes = [cp, i32, ctypes.c_uint32, ctypes.POINTER(vp)]
+    L.spb_index_num_docs.argtypes = [vp]
+    L.spb_index_num_docs.restype = ctypes.c_uint32
+    L.spb_pml_query_host_doc.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts)]
+    L.spb_ms_query_host_doc.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, ctypes.POINTER(QueryOpts)]
+    L.spb_pml_query_device_doc.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts), vp]
+    L.spb_ms_query_device_doc.argtypes = [vp, vp, vp, u64, vp, vp, vp, vp, ctypes.POINTER(QueryOpts), vp]
     L.spb_index_stats.argtypes = [vp, ctypes.POINTER(u64), ctypes.POINTER(u64)]
     L.spb_index_flat.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(u64)]
     L.spb_index_from_flat.argtypes = [vp, u64, ctypes.POINTER(vp)]
@@ -161,10 +169,14 @@ class Index:
 
     # ---- construction
     @classmethod
-    def open(cls, ref_file: str, mode: int) -> "Index":
+    def open(cls, ref_file: str, mode: int, use_doc: bool = False) -> "Index":
+        """use_doc: also load <ref_file>.doc (the reference's pml_t/ms_t(filename, use_doc=true))."""
         h = ctypes.c_void_p()
-        _check(load_library().spb_index_open(ref_file.encode(), mode, ctypes.byref(h)))
+        _check(load_library().spb_index_open_ex(ref_file.encode(), mode, OPEN_DOC if use_doc else 0, ctypes.byref(h)))
         return cls(h.value, mode)
+
+    def num_docs(self) -> int:
+        return int(load_library().spb_index_num_docs(self._h))
 
     @classmethod
     def from_flat(cls, blob: np.ndarray) -> "Index":
@@ -231,6 +243,26 @@ class Index:
         o.saturated = saturated
         return o
 
+    def query_host_doc(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0, toupper=False):
+        """Document-number variant (index opened with use_doc=True). Returns (lengths, pointers or None, stats, doc_nums)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        total = int(offsets[-1]) if n >= 0 and len(offsets) else 0
+        L, D = np.zeros(total, dtype=np.uint32), np.zeros(total, dtype=np.uint32)
+        S = np.zeros(n, dtype=BinStats) if bin_width else None
+        o = self._opts(bin_width, max_value_thr, lanes, toupper, 4, None)
+        lib = load_library()
+        sp_ = S.ctypes.data if S is not None else None
+        if self.mode == MODE_MS:
+            P = np.zeros(total, dtype=np.uint64)
+            _check(lib.spb_ms_query_host_doc(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data, P.ctypes.data,
+                                             D.ctypes.data, sp_, ctypes.byref(o)))
+            return L, P, S, D
+        _check(lib.spb_pml_query_host_doc(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data, D.ctypes.data,
+                                          sp_, ctypes.byref(o)))
+        return L, None, S, D
+
     def query_host(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0,
                    toupper=False, out_lengths=None, out_pointers=None, out_stats=None, length_bytes=4):
         """length_bytes 4/2/1 selects uint32/uint16/uint8 lengths; if a value does not fit, SpumoniError with
@@ -277,8 +309,8 @@ class Index:
 class pml_t(Index):
     """pml_t (compute_ms_pml.cpp:694-746): loads <ref_file>.thrbv.spumoni."""
 
-    def __init__(self, filename: str, device: Optional[int] = 0):
-        idx = Index.open(filename, MODE_PML)
+    def __init__(self, filename: str, device: Optional[int] = 0, use_doc: bool = False):
+        idx = Index.open(filename, MODE_PML, use_doc)
         super().__init__(idx._h.value, MODE_PML)
         idx._h = ctypes.c_void_p()
         if device is not None:
@@ -292,8 +324,8 @@ class pml_t(Index):
 class ms_t(Index):
     """ms_t (compute_ms_pml.cpp:748-838): loads <ref_file>.thrbv.ms; text from <ref_file>."""
 
-    def __init__(self, filename: str, device: Optional[int] = 0):
-        idx = Index.open(filename, MODE_MS)
+    def __init__(self, filename: str, device: Optional[int] = 0, use_doc: bool = False):
+        idx = Index.open(filename, MODE_MS, use_doc)
         super().__init__(idx._h.value, MODE_MS)
         idx._h = ctypes.c_void_p()
         if device is not None:

@@ -48,13 +48,14 @@ struct Slot {
     uint64_t* d_offsets = nullptr;
     uint32_t* d_lengths = nullptr;
     uint64_t* d_pointers = nullptr;
+    uint32_t* d_docs = nullptr;
     spb_bin_stats* d_stats = nullptr;
     uint64_t* h_offsets = nullptr;  // pinned staging for chunk-local offsets
     unsigned long long* d_sat = nullptr;  // clamped-value counter of the launch in flight
     unsigned long long* h_sat = nullptr;  // pinned copy
     bool sat_pending = false;
     uint64_t cap_bases = 0, cap_reads = 0;
-    bool cap_ms = false;
+    bool cap_ms = false, cap_doc = false;
 };
 
 }  // namespace
@@ -102,19 +103,22 @@ void free_slot(Slot& s) {
     if (s.d_offsets) cudaFree(s.d_offsets);
     if (s.d_lengths) cudaFree(s.d_lengths);
     if (s.d_pointers) cudaFree(s.d_pointers);
+    if (s.d_docs) cudaFree(s.d_docs);
     if (s.d_stats) cudaFree(s.d_stats);
     if (s.h_offsets) cudaFreeHost(s.h_offsets);
     if (s.d_sat) cudaFree(s.d_sat);
     if (s.h_sat) cudaFreeHost(s.h_sat);
     s.d_sat = nullptr; s.h_sat = nullptr; s.sat_pending = false;
-    s.d_reads = nullptr; s.d_offsets = nullptr; s.d_lengths = nullptr; s.d_pointers = nullptr; s.d_stats = nullptr;
+    s.d_reads = nullptr; s.d_offsets = nullptr; s.d_lengths = nullptr; s.d_pointers = nullptr; s.d_docs = nullptr; s.d_stats = nullptr;
     s.h_offsets = nullptr;
     s.cap_bases = s.cap_reads = 0;
 }
 
-int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms) {
+int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms, bool doc) {
     if (!s.stream) SPB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    if (bases <= s.cap_bases && reads <= s.cap_reads && (!ms || s.cap_ms)) return SPB_OK;
+    if (bases <= s.cap_bases && reads <= s.cap_reads && (!ms || s.cap_ms) && (!doc || s.cap_doc)) return SPB_OK;
+    ms = ms || s.cap_ms;
+    doc = doc || s.cap_doc;
     SPB_CUDA(cudaStreamSynchronize(s.stream));
     const uint64_t nb = bases > s.cap_bases ? bases : s.cap_bases, nr = reads > s.cap_reads ? reads : s.cap_reads;
     cudaStream_t keep = s.stream;
@@ -125,10 +129,11 @@ int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms) {
     SPB_CUDA(cudaMalloc(&s.d_lengths, (nb + 64) * sizeof(uint32_t)));
     SPB_CUDA(cudaMalloc(&s.d_stats, (nr + 1) * sizeof(spb_bin_stats)));
     if (ms) SPB_CUDA(cudaMalloc(&s.d_pointers, (nb + 64) * sizeof(uint64_t)));
+    if (doc) SPB_CUDA(cudaMalloc(&s.d_docs, (nb + 64) * sizeof(uint32_t)));
     SPB_CUDA(cudaMallocHost(&s.h_offsets, (nr + 1) * sizeof(uint64_t)));
     SPB_CUDA(cudaMalloc(&s.d_sat, sizeof(unsigned long long)));
     SPB_CUDA(cudaMallocHost(&s.h_sat, sizeof(unsigned long long)));
-    s.cap_bases = nb; s.cap_reads = nr; s.cap_ms = ms;
+    s.cap_bases = nb; s.cap_reads = nr; s.cap_ms = ms; s.cap_doc = doc;
     return SPB_OK;
 }
 
@@ -138,7 +143,7 @@ int length_bytes_of(const spb_query_opts* opts) {
 }
 
 int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                 void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats, const spb_query_opts* opts,
+                 void* d_lengths, uint64_t* d_pointers, uint32_t* d_docs, spb_bin_stats* d_stats, const spb_query_opts* opts,
                  unsigned long long* d_saturated, cudaStream_t stream) {
     if (n_reads == 0) return SPB_OK;
     if ((ms ? 1 : 0) != idx->mode) return fail(SPB_ERR_ARG, ms ? "MS query on a PML index" : "PML query on an MS index");
@@ -153,6 +158,12 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     const int width = length_bytes_of(opts);
     if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
     if (width != 4 && lanes != 1) return fail(SPB_ERR_ARG, "narrow length output needs lanes_per_read = 1");
+    if (d_docs) {
+        if (!h.num_docs || !h.off_cdoc) return fail(SPB_ERR_ARG, "document numbers requested but the index was opened without SPB_OPEN_DOC");
+        if (lanes != 1 || !h.off_mdoc) return fail(SPB_ERR_ARG, "document numbers need the thread-per-read kernels (lanes_per_read = 1, an index with fast symbols)");
+        if (width != 4) return fail(SPB_ERR_ARG, "document numbers need 4-byte lengths");
+        if (((uintptr_t)d_docs & 15u) != 0) return fail(SPB_ERR_ARG, "d_doc_nums must be 16-byte aligned");
+    }
     spb::WalkParams p;
     std::memset(&p, 0, sizeof(p));
     p.runs = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_runs);
@@ -176,6 +187,13 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.out_width = (uint32_t)width;
     p.row_ld = idx->row_ld;
     p.saturated = d_saturated;
+    p.docs = d_docs;
+    if (d_docs) {
+        p.cdoc = reinterpret_cast<const uint2*>(idx->dev_blob + h.off_cdoc);
+        p.mdoc = reinterpret_cast<const uint2*>(idx->dev_blob + h.off_mdoc);
+        p.doc_init = h.doc_init; p.doc_absent_ms = h.doc_absent_ms;
+        for (int i = 0; i < 4; i++) p.mv_end_doc[i] = h.mv_end_doc[i];
+    }
     p.work_counter = idx->d_counters + 2 * (idx->counter_next++ % (kCounters / 2));
     SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, 2 * sizeof(unsigned long long), stream));
     int launched = 0;
@@ -185,7 +203,7 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
 }
 
 int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-               void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
+               void* lengths, uint64_t* pointers, uint32_t* docs, spb_bin_stats* stats, const spb_query_opts* opts) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     if (opts && opts->saturated) *opts->saturated = 0;
     if (n_reads == 0) return SPB_OK;
@@ -207,7 +225,7 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         const uint64_t b0 = offsets[r0], nb = offsets[r1] - b0, nr = r1 - r0;
         if (offsets[r1] < b0) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
         Slot& s = idx->slots[chunk % kSlots];
-        rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), ms);
+        rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), ms, docs != nullptr);
         if (rc) return rc;
         SPB_CUDA(cudaStreamSynchronize(s.stream));  // previous use of this slot (incl. its pinned staging) is done
         if (s.sat_pending) { total_sat += *s.h_sat; s.sat_pending = false; }
@@ -220,10 +238,11 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
         if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
         if (width != 4) SPB_CUDA(cudaMemsetAsync(s.d_sat, 0, sizeof(unsigned long long), s.stream));
-        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, s.d_stats, opts, width != 4 ? s.d_sat : nullptr, s.stream);
+        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, docs ? s.d_docs : nullptr, s.d_stats, opts, width != 4 ? s.d_sat : nullptr, s.stream);
         if (rc) return rc;
         if (nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)lengths + b0 * (uint64_t)width, s.d_lengths, nb * (uint64_t)width, cudaMemcpyDeviceToHost, s.stream));
         if (ms && nb) SPB_CUDA(cudaMemcpyAsync(pointers + b0, s.d_pointers, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        if (docs && nb) SPB_CUDA(cudaMemcpyAsync(docs + b0, s.d_docs, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
         if (width != 4) {
             SPB_CUDA(cudaMemcpyAsync(s.h_sat, s.d_sat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
@@ -265,13 +284,16 @@ extern "C" {
 const char* spb_last_error(void) { return g_error.c_str(); }
 int spb_abi_version(void) { return SPB_ABI_VERSION; }
 
-int spb_index_open(const char* ref_file, int mode, spb_index** out) {
-    if (!ref_file || !out || (mode != SPB_MODE_PML && mode != SPB_MODE_MS)) return fail(SPB_ERR_ARG, "spb_index_open: bad argument");
+int spb_index_open(const char* ref_file, int mode, spb_index** out) { return spb_index_open_ex(ref_file, mode, 0, out); }
+
+int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index** out) {
+    if (!ref_file || !out || (mode != SPB_MODE_PML && mode != SPB_MODE_MS) || (flags & ~SPB_OPEN_DOC)) return fail(SPB_ERR_ARG, "spb_index_open: bad argument");
     *out = nullptr;
     return guarded([&]() -> int {
         const bool ms = mode == SPB_MODE_MS;
         const std::string ref(ref_file);
         spb::DecodedIndex d = spb::parse_index_file(ref + (ms ? ".thrbv.ms" : ".thrbv.spumoni"), ms);
+        if (flags & SPB_OPEN_DOC) spb::load_doc_array(ref + ".doc", d);
         std::string text;
         if (ms) text = spb::load_reference_text(ref);
         std::unique_ptr<spb_index> idx(new spb_index());
@@ -378,19 +400,47 @@ void spb_index_close(spb_index* idx) {
 
 int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                        void* lengths, spb_bin_stats* stats, const spb_query_opts* opts) {
-    return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, stats, opts);
+    return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, nullptr, stats, opts);
 }
+int spb_pml_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                           uint32_t* lengths, uint32_t* doc_nums, spb_bin_stats* stats, const spb_query_opts* opts) {
+    if (!doc_nums) return fail(SPB_ERR_ARG, "null doc_nums");
+    return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, doc_nums, stats, opts);
+}
+int spb_ms_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                          uint32_t* lengths, uint64_t* pointers, uint32_t* doc_nums, spb_bin_stats* stats,
+                          const spb_query_opts* opts) {
+    if (!doc_nums) return fail(SPB_ERR_ARG, "null doc_nums");
+    return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, doc_nums, stats, opts);
+}
+uint32_t spb_index_num_docs(const spb_index* idx) { return idx ? idx->hdr.num_docs : 0; }
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                       void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
-    return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, stats, opts);
+    return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, nullptr, stats, opts);
 }
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                          void* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_stats, opts,
+    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, nullptr, d_stats, opts,
                         opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
+}
+int spb_pml_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                             uint32_t* d_lengths, uint32_t* d_doc_nums, spb_bin_stats* d_stats,
+                             const spb_query_opts* opts, void* cuda_stream) {
+    if (!idx || !d_doc_nums) return fail(SPB_ERR_ARG, "null index / doc_nums");
+    int rc = ensure_device_state(idx);
+    if (rc) return rc;
+    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream);
+}
+int spb_ms_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+                            uint32_t* d_lengths, uint64_t* d_pointers, uint32_t* d_doc_nums, spb_bin_stats* d_stats,
+                            const spb_query_opts* opts, void* cuda_stream) {
+    if (!idx || !d_doc_nums) return fail(SPB_ERR_ARG, "null index / doc_nums");
+    int rc = ensure_device_state(idx);
+    if (rc) return rc;
+    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream);
 }
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                         void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
@@ -398,7 +448,7 @@ int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* 
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_stats, opts,
+    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, nullptr, d_stats, opts,
                         opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
 }
 

@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define SPB_FLAT_MAGIC 0x3030324250535F42ULL /* "B_SPB200" */
-#define SPB_FLAT_VERSION 6u
+#define SPB_FLAT_VERSION 7u
 #define SPB_RUN_PAD 64u  /* sentinel + padding run records past R (start = 2^40-1) */
 #define SPB_POS_MAX 0xFFFFFFFFFFULL
 
@@ -39,6 +39,8 @@ struct SpbCharRec { uint32_t x, y, z, w; };
 // MS only, same indexing as SpbCharRec: SA samples re-ordered per character
 //   ss = samples_start[j-th c-run]  (0 for the sentinel),  sl = samples_last[(j-1)-th c-run] (0 for j == 0)
 struct SpbCharSamp { uint64_t ss, sl; };
+// document numbers, same indexing as SpbCharSamp (and, per move row, as msamp)
+struct SpbDocPair { uint32_t sd, ed; };
 
 // Block header, one per 32 consecutive runs b: cnt[s] = number of runs with compact symbol s in
 // runs [0, 32b); then the 32 raw head bytes of the block.  Stride = 32 + 4*sigma_pad bytes.
@@ -144,7 +146,19 @@ struct SpbFlatHeader {
     uint32_t pad0[3];
     uint64_t mv_end_sl[4];       // MS: samples_last of the last c-run
     uint64_t off_mrows8;         // compact rows ((R + SPB_MV8_ROW_PAD) * 8 bytes); 0 if not applicable (then off_mrows != 0)
-    uint64_t reserved0;
+    // document array (-d; /root/reference/src/doc_array.cpp): present iff num_docs != 0
+    uint64_t off_cdoc;           // SpbDocPair per SpbCharRec (generic step): start_runs_doc[j-th c-run], end_runs_doc[(j-1)-th c-run]
+    uint64_t off_mdoc;           // SpbDocPair per move row k: start_runs_doc[k], end_runs_doc[previous run with the same head]
+    uint32_t num_docs;           // 1 + largest document number
+    uint32_t doc_init;           // end_runs_doc[R-1]: document of the empty match (compute_ms_pml.cpp:298, :634)
+    uint32_t doc_absent_ms;      // start_runs_doc[run_of_position(0)]: MS mode, character absent from the index (:640-642)
+    uint32_t mv_end_doc[4];      // end_runs_doc of the last c-run per fast symbol
+    uint32_t pad1;
+    uint64_t pad2;               // keeps chartab 16-byte aligned (the kernels load its entries as uint4)
     uint64_t F[256];
     SpbCharTab chartab[256];
 };
+#ifdef __cplusplus
+#include <cstddef>
+static_assert(offsetof(SpbFlatHeader, chartab) % 16 == 0, "chartab entries are loaded as 16-byte vectors");
+#endif

@@ -350,6 +350,27 @@ NullDb load_null_db(const std::string& path) {
     return db;
 }
 
+void load_doc_array(const std::string& path, DecodedIndex& d) {
+    std::vector<uint8_t> buf = slurp(path);
+    ByteReader in(buf.data(), buf.size());
+    try {
+        const uint64_t num_entries = in.u64();
+        PackedInts sd = read_packed(in, 0), ed = read_packed(in, 0);
+        if (in.remaining()) throw FormatError("trailing bytes");
+        if (num_entries != d.R || sd.count() != d.R || ed.count() != d.R) throw FormatError("document array does not have one entry per BWT run");
+        d.doc_start.resize((size_t)d.R);
+        d.doc_end.resize((size_t)d.R);
+        for (uint64_t k = 0; k < d.R; k++) {
+            const uint64_t a = sd.at(k), b = ed.at(k);
+            if (a >= 0xFFFFFFFFull || b >= 0xFFFFFFFFull) throw LimitError("document numbers >= 2^32-1 are not supported");
+            d.doc_start[(size_t)k] = (uint32_t)a;
+            d.doc_end[(size_t)k] = (uint32_t)b;
+        }
+    } catch (FormatError& e) {
+        throw FormatError(path + ": " + e.what());
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 static inline uint32_t pack_hi(uint64_t a, int shift) { return (uint32_t)((a >> 32) & 0xFF) << shift; }
 
@@ -459,6 +480,20 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
             off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbCharSamp), 256);
         }
     }
+    const bool use_doc = !d.doc_start.empty();
+    if (use_doc) {
+        h.off_cdoc = off;
+        off = align_up(off + ((size_t)num_crec + 1) * sizeof(SpbDocPair), 256);
+        if (num_fast) {
+            h.off_mdoc = off;
+            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(SpbDocPair), 256);
+        }
+        uint32_t mx = 0;
+        for (uint64_t k = 0; k < R; k++) mx = std::max(mx, std::max(d.doc_start[(size_t)k], d.doc_end[(size_t)k]));
+        h.num_docs = mx + 1;
+        h.doc_init = d.doc_end[(size_t)R - 1];
+        h.doc_absent_ms = d.doc_start[0];
+    }
     h.total_bytes = off;
     for (int c = 0; c < 256; c++) {
         h.F[c] = d.F[c];
@@ -516,6 +551,8 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     {
         SpbCharRec* crec = reinterpret_cast<SpbCharRec*>(blob.data() + h.off_crec);
         SpbCharSamp* csamp = ms ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_csamp) : nullptr;
+        SpbDocPair* cdoc = use_doc ? reinterpret_cast<SpbDocPair*>(blob.data() + h.off_cdoc) : nullptr;
+        std::vector<uint32_t> prev_ed(256, 0);
         std::vector<uint32_t> o(256, 0);
         std::vector<uint64_t> prev_sl(256, 0);
         for (uint64_t k = 0; k < R; k++) {
@@ -534,6 +571,11 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                 csamp[at].sl = prev_sl[c];
                 prev_sl[c] = d.samples_last[(size_t)k];
             }
+            if (use_doc) {
+                cdoc[at].sd = d.doc_start[(size_t)k];
+                cdoc[at].ed = prev_ed[c];
+                prev_ed[c] = d.doc_end[(size_t)k];
+            }
         }
         for (int c = 0; c < 256; c++) {
             if (!numRunsC[c]) continue;
@@ -548,6 +590,10 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
             if (ms) {
                 csamp[at].ss = 0;
                 csamp[at].sl = prev_sl[c];
+            }
+            if (use_doc) {
+                cdoc[at].sd = 0;
+                cdoc[at].ed = prev_ed[c];
             }
         }
     }
@@ -642,6 +688,17 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                 prev_sl[c] = d.samples_last[(size_t)k];
             }
             for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_sl[s] = prev_sl[h.fast_sym[s]];
+        }
+        if (use_doc) {
+            SpbDocPair* mdoc = reinterpret_cast<SpbDocPair*>(blob.data() + h.off_mdoc);
+            std::vector<uint32_t> pe(256, 0);
+            for (uint64_t k = 0; k < R; k++) {
+                const uint8_t c = d.heads[(size_t)k];
+                mdoc[k].sd = d.doc_start[(size_t)k];
+                mdoc[k].ed = pe[c];
+                pe[c] = d.doc_end[(size_t)k];
+            }
+            for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_doc[s] = pe[h.fast_sym[s]];
         }
         for (uint32_t s = 0; s < num_fast; s++) {
             const int c = (int)h.fast_sym[s];

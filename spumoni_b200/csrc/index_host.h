@@ -20,6 +20,7 @@ struct DecodedIndex {
     std::vector<uint64_t> thr;            // R thresholds (BWT positions; 0 for the first run of a letter)
     std::vector<uint64_t> samples_start;  // MS: R text positions
     std::vector<uint64_t> samples_last;   // MS: R text positions
+    std::vector<uint32_t> doc_start, doc_end;  // -d: R document numbers each (DocumentArray), empty otherwise
 };
 
 struct NullDb {
@@ -30,6 +31,8 @@ struct NullDb {
 DecodedIndex parse_index_file(const std::string& path, bool ms);
 std::string load_reference_text(const std::string& fasta_path);
 NullDb load_null_db(const std::string& path);
+// DocumentArray::load (/root/reference/src/doc_array.cpp:197-201) into d.doc_start / d.doc_end
+void load_doc_array(const std::string& path, DecodedIndex& d);
 std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std::string& text);
 void validate_flat_image(const void* blob, uint64_t bytes);
 

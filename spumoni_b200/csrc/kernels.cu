@@ -372,9 +372,9 @@ __device__ __noinline__ ThreadLoc locate_thread(const uint4* __restrict__ runs, 
 // One reference step in absolute coordinates (same statements as spb_walk_kernel's body) for a single
 // thread.  In: state (k, off) -- off may be un-normalised (>= len[k]) or SPB_MV_OFF_LAST --, byte c.
 // Out: the normalised new state; PML length / MS sample updated in place.
-struct SlowOut { uint32_t k, off, length; uint64_t sample; };
-template <bool MS>
-__device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint32_t k, uint32_t off, uint32_t length, uint64_t sample) {
+struct SlowOut { uint32_t k, off, length, doc; uint64_t sample; };
+template <bool MS, bool DOC>
+__device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint32_t k, uint32_t off, uint32_t length, uint64_t sample, uint32_t doc) {
     const uint4* __restrict__ runs = p.runs;
     const uint64_t R = p.R, n = p.n;
     const uint4 ct = reinterpret_cast<const uint4*>(p.chartab)[c];
@@ -392,6 +392,7 @@ __device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint3
     if (ct.w == 0xFFFFFFFFu) {
         length = 0;
         if (MS) sample = 0;
+        if (MS && DOC) doc = p.doc_absent_ms;  // :640-642; the PML variant leaves the document alone (:303)
         npos = (uint64_t)ct.x | ((uint64_t)ct.y << 32);
         w0 = ct.z;
     } else if (k < R && rec_head(krec) == c && c < 0x80u) {
@@ -410,6 +411,11 @@ __device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint3
             if (j < ct.y) sample = (uint64_t)cs.x | ((uint64_t)cs.y << 32);
             if (down) sample = (uint64_t)cs.z | ((uint64_t)cs.w << 32);
         }
+        if (DOC) {
+            const uint2 cd = __ldg(p.cdoc + (size_t)ct.x + j);
+            if (j < ct.y) doc = cd.x;  // start_runs_doc of the next c-run (:317 / :658)
+            if (down) doc = cd.y;      // end_runs_doc of the previous c-run (:327 / :669)
+        }
         const uint64_t lf = crec_lf(cr);
         npos = down ? lf - 1 : (same ? lf + (pos - rec_start(krec)) : lf);
         w0 = (down && cr.z > 0) ? cr.z - 1 : cr.z;
@@ -417,6 +423,7 @@ __device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint3
     SlowOut o;
     o.length = length;
     o.sample = sample;
+    o.doc = doc;
     if (npos >= n) {
         o.k = (uint32_t)R;
         o.off = 0;
@@ -547,20 +554,22 @@ struct BinState {
     uint32_t bin_max = 0, above = 0, below = 0;
 };
 
-template <bool MS, bool STATS, int OW, int LD, bool ROW8>
-__global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8 : SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
+template <bool MS, bool STATS, int OW, int LD, bool ROW8, bool DOC>
+__global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB > 8) ? 8 : SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
     __shared__ uint4 s_rd[SPB_STAGE_CH * SPB_MV_THREADS];   // staged read bytes, see stage_reads
     __shared__ uint4 s_out[SPB_STAGE_CH * SPB_MV_THREADS];  // staged output values (lengths, or MS pointers)
+    __shared__ uint4 s_doc[DOC ? SPB_STAGE_CH * SPB_MV_THREADS : 1];  // staged document numbers
+    __shared__ uint32_t s_end_doc[4];
     for (int i = threadIdx.x; i < 256; i += SPB_MV_THREADS) {
         const SpbCharTab t = p.chartab[i];
         s_fid[i] = (uint8_t)(t.cidx == 0xFFFFFFFFu ? 5u : t.dest_f);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++)
-        if (threadIdx.x == i) { s_end_k[i] = p.mv_end_k[i]; s_end_off[i] = p.mv_end_off[i]; s_end_sl[i] = p.mv_end_sl[i]; }
+        if (threadIdx.x == i) { s_end_k[i] = p.mv_end_k[i]; s_end_off[i] = p.mv_end_off[i]; s_end_sl[i] = p.mv_end_sl[i]; s_end_doc[i] = p.mv_end_doc[i]; }
     __syncthreads();
 
     const uint4* __restrict__ rows = p.rows;
@@ -577,7 +586,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
     uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2 (compact rows: also probing for the c-run)
     uint32_t want = 0, probes = 0;
     uint64_t sample = 0;
-    uint32_t nsat = 0;
+    uint32_t nsat = 0, doc = 0;
     BinState bs;
 
     for (;;) {
@@ -594,6 +603,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
             gi = end - 1;
             k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0; mode = 0;  // empty string: pos = n-1
             if (MS) sample = p.last_run_sample;
+            if (DOC) doc = p.doc_init;
             stage_reads(s_rd, p.reads, gi);
             have = true;
             if (do_stats) {
@@ -632,6 +642,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
                             k = s_end_k[s]; off = s_end_off[s];
                             length = 0;
                             if (MS) sample = s_end_sl[s];
+                            if (DOC) doc = s_end_doc[s];
                             emit = true;
                         } else {
                             down = (cls == 1) || (cls == 2 && off < ((v.y >> 17) & 0x3Fu));
@@ -652,6 +663,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
                             const uint4 sm = ldg_nc16(p.msamp + k2);
                             sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
                         }
+                        if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
                         if (!down) { k = de; off = d2; }
                         else if (d2) { k = de; off = d2 - 1; }
                         else { k = de - 1; off = SPB_MV_OFF_LAST; }
@@ -685,6 +697,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
                             k = s_end_k[s]; off = s_end_off[s];
                             length = 0;
                             if (MS) sample = s_end_sl[s];
+                            if (DOC) doc = s_end_doc[s];
                             emit = true;
                         } else {
                             down = (v == SPB_MV_THR_ALWAYS) || (off < v);
@@ -702,6 +715,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
                         const uint4 sm = ldg_nc16(p.msamp + k2);
                         sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
                     }
+                    if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
                     if (!down) { k = rec.x; off = d2; }
                     else if (d2) { k = rec.x; off = d2 - 1; }
                     else { k = rec.x - 1; off = SPB_MV_OFF_LAST; }
@@ -711,14 +725,16 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, (STATS && SPB_MV_MINB > 8) ? 8
             }
         }
         if (slow) {  // ---- generic step in absolute coordinates
-            const SlowOut so = slow_step<MS>(p, c, k, off, length, sample);  // by value: no state lives in local memory
+            const SlowOut so = slow_step<MS, DOC>(p, c, k, off, length, sample, doc);  // by value: no state lives in local memory
             k = so.k; off = so.off; length = so.length;
             if (MS) sample = so.sample;
+            if (DOC) doc = so.doc;
             emit = true;
         }
 
         if (emit) {
             const bool last = (gi == base);
+            if (DOC) stage_value<4>(s_doc, p.docs, gi, doc, end, last);
             if (MS) stage_value<8>(s_out, p.pointers, gi, sample, end, last);
             else {
                 uint32_t v = length;
@@ -859,14 +875,20 @@ static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms,
 template <bool STATS, int LD, bool ROW8>
 static cudaError_t launch_move_pml(const WalkParams& p, int num_sms, cudaStream_t stream) {
     switch (p.out_width) {
-        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD, ROW8>, p, num_sms, stream);
-        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD, ROW8>, p, num_sms, stream);
-        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD, ROW8>, p, num_sms, stream);
+        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD, ROW8, false>, p, num_sms, stream);
+        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD, ROW8, false>, p, num_sms, stream);
+        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD, ROW8, false>, p, num_sms, stream);
     }
 }
 template <int LD, bool ROW8>
 static cudaError_t launch_move(const WalkParams& p, bool ms, bool stats, int num_sms, cudaStream_t stream) {
-    if (ms) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8>, p, num_sms, stream);
+    if (p.docs) {  // document numbers: u32 lengths, L1-allocating rows only (keeps the number of kernel variants down)
+        if (p.out_width != 4) return cudaErrorInvalidValue;
+        if (ms) return launch_persistent(spb_move_kernel<true, false, 4, 1, ROW8, true>, p, num_sms, stream);
+        return stats ? launch_persistent(spb_move_kernel<false, true, 4, 1, ROW8, true>, p, num_sms, stream)
+                     : launch_persistent(spb_move_kernel<false, false, 4, 1, ROW8, true>, p, num_sms, stream);
+    }
+    if (ms) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8, false>, p, num_sms, stream);
     return stats ? launch_move_pml<true, LD, ROW8>(p, num_sms, stream) : launch_move_pml<false, LD, ROW8>(p, num_sms, stream);
 }
 template <bool STATS>
@@ -906,7 +928,7 @@ cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cu
         }
         return e;
     }
-    if (p.out_width != 4) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths only
+    if (p.out_width != 4 || p.docs) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths only, no document numbers
     if (launches) *launches = 1;
     switch (lanes) {
         case 4: return ms ? launch_t<4, true>(p, num_sms, stream) : launch_t<4, false>(p, num_sms, stream);

@@ -40,6 +40,12 @@ struct WalkParams {
     uint32_t out_width;        // bytes per length value: 4, 2 or 1 (values above the maximum are clamped and counted)
     uint32_t row_ld;           // 0 = rows bypass L1, 1 = rows allocate in L1 (default)
     unsigned long long* saturated;  // nullable; += number of clamped length values
+    // document numbers (-d), thread-per-read kernels only; docs == nullptr when not requested
+    uint32_t* docs;            // one per base, like lengths
+    const uint2* cdoc;         // SpbDocPair per SpbCharRec
+    const uint2* mdoc;         // SpbDocPair per move row
+    uint32_t doc_init, doc_absent_ms;
+    uint32_t mv_end_doc[4];
 };
 
 // lanes: 4/8/16/32 = cooperative walk kernel (PML or MS); 1 = thread-per-read kernels over the move rows.

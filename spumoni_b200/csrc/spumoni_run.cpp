@@ -10,8 +10,8 @@
 // Output files (<reads>.pseudo_lengths | .lengths + .pointers | .report) are byte-identical to the
 // reference's single-thread output.  Everything per-base runs on the GPU through
 // libspumoni_b200.so; this file only parses FASTA, batches reads, and formats results.
-// Not supported (outside SURVEY section 8): minimizer digestion (-m/-a, needs bonsai) and the
-// document array (-d).
+// The document array (-d) writes <reads>.doc_numbers (:859, :1003-1006).
+// Not supported (outside SURVEY section 8): minimizer digestion (-m/-a, needs bonsai).
 #include <getopt.h>
 #include <sys/stat.h>
 
@@ -121,7 +121,8 @@ static void validate(const RunOptions& o, bool ms) {  // SpumoniRunOptions::vali
     if (o.is_general_text && o.min_digest) fatal_warning("For general-text querying, minimizer digestion must be turned off with -n.");
     if (o.is_general_text && o.threads > 1) fatal_warning("For general-text querying, multi-threading is not available.");
     if (o.is_general_text && o.write_report) fatal_warning("For general-text querying, classification is not available.");
-    if (o.use_doc) fatal_warning("the document array (-d) is not supported by spumoni_b200.");
+    if (o.use_doc && !is_file(o.ref_file + ext + ".doc"))  // spumoni_main.hpp:301-302
+        fatal_warning("document array file (" + o.ref_file + ext + ".doc) is not present, so it cannot be used.");
     if (!is_file(o.ref_file + ext + (ms ? ".thrbv.ms" : ".thrbv.spumoni")))
         fatal_warning("The index required for this computation is not available, please use spumoni build.");
     if (o.k > 4) fatal_warning("small window size (k) cannot be larger than 4 characters.");
@@ -232,19 +233,28 @@ static void report_row(std::ofstream& f, const std::string& id, const spb_bin_st
 
 // ---------------------------------------------------------------------------------- driver
 struct Outputs {
-    std::ofstream lengths, pointers, report;
+    std::ofstream lengths, pointers, report, docs;
 };
 
 static void process_batch(spb_index* idx, bool ms, const RunOptions& o, const spb_query_opts& qo, ReadBatch& b, Outputs& out,
-                          std::vector<uint32_t>& L, std::vector<uint64_t>& P, std::vector<spb_bin_stats>& S) {
+                          std::vector<uint32_t>& L, std::vector<uint64_t>& P, std::vector<spb_bin_stats>& S, std::vector<uint32_t>& D) {
     const size_t nr = b.ids.size();
     if (!nr) return;
     L.resize(b.bases.size());
     if (ms) P.resize(b.bases.size());
+    if (o.use_doc) D.resize(b.bases.size());
     if (o.write_report) S.resize(nr);
-    if (ms) spb_or_die(spb_ms_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), P.data(), o.write_report ? S.data() : nullptr, &qo));
-    else spb_or_die(spb_pml_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), o.write_report ? S.data() : nullptr, &qo));
+    spb_bin_stats* sp = o.write_report ? S.data() : nullptr;
+    if (o.use_doc) {
+        if (ms) spb_or_die(spb_ms_query_host_doc(idx, b.bases.data(), b.offsets.data(), nr, L.data(), P.data(), D.data(), sp, &qo));
+        else spb_or_die(spb_pml_query_host_doc(idx, b.bases.data(), b.offsets.data(), nr, L.data(), D.data(), sp, &qo));
+    } else if (ms) spb_or_die(spb_ms_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), P.data(), sp, &qo));
+    else spb_or_die(spb_pml_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), sp, &qo));
     std::vector<std::string> parts;
+    if (o.use_doc) {  // the reference writes the document numbers first (:1003-1006)
+        format_values(b, D.data(), (int)o.threads, parts);
+        write_all(out.docs, parts);
+    }
     format_values(b, L.data(), (int)o.threads, parts);
     write_all(out.lengths, parts);
     if (ms) {
@@ -259,6 +269,7 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
     Outputs out;
     out.lengths.open(o.pattern_file + (ms ? ".lengths" : ".pseudo_lengths"));
     if (ms) out.pointers.open(o.pattern_file + ".pointers");
+    if (o.use_doc) out.docs.open(o.pattern_file + ".doc_numbers");
     spb_query_opts qo;
     std::memset(&qo, 0, sizeof(qo));
     qo.flags = o.is_general_text ? 0 : SPB_QUERY_TOUPPER;  // general text is used verbatim (:1219-1297)
@@ -281,12 +292,13 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
     std::vector<uint32_t> L;
     std::vector<uint64_t> P;
     std::vector<spb_bin_stats> S;
+    std::vector<uint32_t> D;
     size_t num_reads = 0;
     if (!o.is_general_text) {
         FastaSource src(o.pattern_file);
         while (src.next(b)) {
             num_reads++;
-            if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S); b.clear(); }
+            if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S, D); b.clear(); }
         }
     } else {  // classify_general_reads_*: reads are separated by 0x01, ids are read_<i>
         std::ifstream fd(o.pattern_file, std::ifstream::in | std::ifstream::binary);
@@ -296,14 +308,14 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
                 b.ids.push_back("read_" + std::to_string(num_reads));
                 b.offsets.push_back(b.bases.size());
                 num_reads++;
-                if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S); b.clear(); }
+                if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S, D); b.clear(); }
             } else
                 b.bases.push_back((uint8_t)ch);
             ch = (char)fd.get();
         }
         b.bases.resize(b.offsets.back());  // bytes after the last separator are never queried
     }
-    process_batch(idx, ms, o, qo, b, out, L, P, S);
+    process_batch(idx, ms, o, qo, b, out, L, P, S, D);
     return num_reads;
 }
 
@@ -319,7 +331,8 @@ static int run_main(int argc, char** argv) {
     status_log(ms ? "ms_construct" : "pml_construct", ms ? "loading the MS index" : "loading the PML index");
     double t0 = now_s();
     spb_index* idx = nullptr;
-    spb_or_die(spb_index_open(o.ref_file.c_str(), ms ? SPB_MODE_MS : SPB_MODE_PML, &idx));
+    spb_or_die(spb_index_open_ex(o.ref_file.c_str(), ms ? SPB_MODE_MS : SPB_MODE_PML, o.use_doc ? SPB_OPEN_DOC : 0, &idx));
+    if (o.use_doc) { done_log(now_s() - t0); status_log(ms ? "ms_construct" : "pml_construct", "loading the document array"); }
     int dev = 0;
     if (const char* e = std::getenv("SPUMONI_B200_DEVICE")) dev = std::atoi(e);
     spb_or_die(spb_index_to_device(idx, dev));

@@ -44,7 +44,7 @@ def mkindex(*args):
     return out.stdout
 
 
-def build_index(dirpath, text: bytes = None, fasta: str = None, revcomp=False, keep=False):
+def build_index(dirpath, text: bytes = None, fasta: str = None, revcomp=False, keep=False, docs=0):
     """Builds <dir>/idx.fa(.thrbv.spumoni|.thrbv.ms) from raw text or a FASTA file; returns ref_file path."""
     os.makedirs(dirpath, exist_ok=True)
     if fasta is None:
@@ -56,17 +56,19 @@ def build_index(dirpath, text: bytes = None, fasta: str = None, revcomp=False, k
         args.append("--no-revcomp")
     if keep:
         args.append("--keep")
+    if docs:
+        args += ["--docs", docs]  # also writes <prefix>.fa.fdi and <prefix>.fa.doc (spumoni build -d)
     mkindex(*args)
     return os.path.join(dirpath, "idx.fa")
 
 
 @pytest.fixture(scope="session")
 def small_index(tmp_path_factory):
-    """20 kb pangenome-like reference (4 haplotypes, +revcomp), PML + MS index, 300 mixed reads."""
+    """20 kb pangenome-like reference (4 haplotypes, +revcomp, 3 documents), PML + MS index + document array, 300 mixed reads."""
     d = str(tmp_path_factory.mktemp("small"))
     mkindex("genome", "--kind", "pangenome", "--len", 20000, "--haps", 4, "--snp", 0.01, "--indel", 0.001,
             "--seed", 7, "--out", os.path.join(d, "raw.fa"))
-    ref = build_index(d, fasta=os.path.join(d, "raw.fa"), revcomp=True)
+    ref = build_index(d, fasta=os.path.join(d, "raw.fa"), revcomp=True, docs=3)
     reads = os.path.join(d, "reads.fa")
     mkindex("reads", "--ref", ref, "--n", 300, "--len", 40, "--len-max", 400, "--sub", 0.05, "--ins", 0.01, "--del", 0.01,
             "--neg-frac", 0.3, "--seed", 9, "--out", reads, "--bin", os.path.join(d, "reads.bin"))

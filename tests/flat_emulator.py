@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQ"  # up to reserved0 (then F[256], chartab[256])
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQQ3I4IIQ"  # up to pad2 (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -23,7 +23,9 @@ class FlatImage:
          self.off_crec, self.off_csamp, self.off_text, self.total_bytes, self.terminator_position, self.off_mrows,
          self.off_msamp, self.num_fast, *rest) = struct.unpack_from(HDR_FMT, b, 0)
         self.fast_sym, self.mv_end_k, self.mv_end_off, self.mv_end_sl = rest[0:4], rest[4:8], rest[8:12], rest[15:19]
-        self.off_mrows8 = rest[19]
+        self.off_mrows8, self.off_cdoc, self.off_mdoc = rest[19], rest[20], rest[21]
+        self.num_docs, self.doc_init, self.doc_absent_ms = rest[22], rest[23], rest[24]
+        self.mv_end_doc = rest[25:29]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -39,6 +41,10 @@ class FlatImage:
                 self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
             if self.mode == 1:
                 self.msamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.R + 16), offset=self.off_msamp).reshape(-1, 2)
+        if self.num_docs:
+            self.cdoc = np.frombuffer(b, dtype=np.uint32, count=2 * (self.num_crec + 1), offset=self.off_cdoc).reshape(-1, 2)
+            if self.off_mdoc:
+                self.mdoc = np.frombuffer(b, dtype=np.uint32, count=2 * (self.R + 64), offset=self.off_mdoc).reshape(-1, 2)
         if self.mode == 1:
             self.csamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.num_crec + 1), offset=self.off_csamp).reshape(-1, 2)
             self.text = b[self.off_text:self.off_text + self.n_text]
@@ -123,7 +129,8 @@ class FlatImage:
 
     # ---- thread-per-read walk over the move rows (spb_move_kernel), including its fall-backs; the limits
     # let a test decode an image written by the SPB_MV_* test build
-    def slow_step(self, k, off, c, length, sample):
+    def slow_step(self, k, off, c, length, sample, doc=0):
+        """Returns (k, off, length, sample); the document number of the step is left in self.last_doc."""
         n, R = self.n, self.R
         ms = self.mode == 1
         if k < R:
@@ -138,6 +145,8 @@ class FlatImage:
         ct = self.chartab[c]
         if ct[3] == 0xFFFFFFFF:
             length, sample = 0, 0
+            if ms and self.num_docs:
+                doc = self.doc_absent_ms
             npos, w0 = ct[0] | (ct[1] << 32), ct[2]
         elif k < R and kr["head"] == c and c < 0x80:
             length += 1
@@ -156,8 +165,15 @@ class FlatImage:
                     sample = ss
                 if down:
                     sample = sl
+            if self.num_docs:
+                sd, ed = (int(v) for v in self.cdoc[ct[0] + j])
+                if j < ct[1]:
+                    doc = sd
+                if down:
+                    doc = ed
             npos = lf - 1 if down else (lf + (pos - kr["start"]) if same else lf)
             w0 = z - 1 if (down and z > 0) else z
+        self.last_doc = doc
         if npos >= n:
             return R, 0, length, sample
         k2 = self.locate(npos, w0)
@@ -174,7 +190,8 @@ class FlatImage:
         LAST = 0xFFFFFFFF
         m, R = len(read), self.R
         k, off, length, sample = R - 1, LAST, 0, self.last_run_sample
-        out, ptr = [0] * m, [0] * m
+        doc = self.doc_init if self.num_docs else 0
+        out, ptr, self.docs = [0] * m, [0] * m, [0] * m
         stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0, "probe": 0}
         for gi in range(m - 1, -1, -1):
             c = read[gi]
@@ -209,6 +226,8 @@ class FlatImage:
                         slow = True
                     elif dc == 0:
                         k, off, length, sample = self.mv_end_k[s], self.mv_end_off[s], 0, self.mv_end_sl[s]
+                        if self.num_docs:
+                            doc = self.mv_end_doc[s]
                         stats["end"] += 1
                     else:
                         down = cls == 1 or (cls == 2 and off < ((hi >> 17) & 0x3F))
@@ -234,6 +253,8 @@ class FlatImage:
                                 d2, de = hi2 & 0xFF, lo2 & 0xFFFFFF
                                 if ms:
                                     sample = int(self.msamp[k2][1 if down else 0])
+                                if self.num_docs:
+                                    doc = int(self.mdoc[k2][1 if down else 0])
                                 if not down:
                                     k, off = de, d2
                                 elif d2:
@@ -243,10 +264,11 @@ class FlatImage:
                                 length = 0
             if slow:
                 stats["slow"] += 1
-                k, off, length, sample = self.slow_step(k, off, c, length, sample)
+                k, off, length, sample = self.slow_step(k, off, c, length, sample, doc)
+                doc = self.last_doc
             else:
                 stats["fast"] += 1
-            out[gi], ptr[gi] = length, sample
+            out[gi], ptr[gi], self.docs[gi] = length, sample, doc
         return out, (ptr if ms else None), stats
 
     def walk_rows(self, read: bytes, **kw):
@@ -262,7 +284,8 @@ class FlatImage:
         LAST, lmask = 0xFFFFFFFF, (1 << len_bits) - 1
         m, R = len(read), self.R
         k, off, length, sample = R - 1, LAST, 0, self.last_run_sample
-        out, ptr = [0] * m, [0] * m
+        doc = self.doc_init if self.num_docs else 0
+        out, ptr, self.docs = [0] * m, [0] * m, [0] * m
         stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0}
         for gi in range(m - 1, -1, -1):
             c = read[gi]
@@ -297,6 +320,8 @@ class FlatImage:
                         slow = True
                     elif d == 0:
                         k, off, length, sample = self.mv_end_k[s], self.mv_end_off[s], 0, self.mv_end_sl[s]
+                        if self.num_docs:
+                            doc = self.mv_end_doc[s]
                         stats["end"] += 1
                     else:
                         down = v == 0xFFF or off < v
@@ -309,6 +334,8 @@ class FlatImage:
                             d2 = z2 & lmask
                             if ms:
                                 sample = int(self.msamp[k2][1 if down else 0])
+                            if self.num_docs:
+                                doc = int(self.mdoc[k2][1 if down else 0])
                             if not down:
                                 k, off = x2, d2
                             elif d2:
@@ -318,8 +345,9 @@ class FlatImage:
                             length = 0
             if slow:
                 stats["slow"] += 1
-                k, off, length, sample = self.slow_step(k, off, c, length, sample)
+                k, off, length, sample = self.slow_step(k, off, c, length, sample, doc)
+                doc = self.last_doc
             else:
                 stats["fast"] += 1
-            out[gi], ptr[gi] = length, sample
+            out[gi], ptr[gi], self.docs[gi] = length, sample, doc
         return out, (ptr if ms else None), stats

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = sp.load_library()
-    assert lib.spb_abi_version() == 2
+    assert lib.spb_abi_version() == 3
     assert ctypes.sizeof(sp.QueryOpts) == 32
     assert sp.BinStats.itemsize == 16
     assert sp.flat_header_bytes() % 8 == 0

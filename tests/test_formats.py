@@ -12,6 +12,7 @@ import pytest
 import oracle
 import spumoni_b200 as sp
 from conftest import MKINDEX, build_index
+from conftest import load_bin_reads
 from flat_emulator import FlatImage
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "golden_vectors.json")
@@ -157,3 +158,32 @@ def test_move_rows_saturation_fallbacks_host_side(tmp_path, row_width):
         for key in tot:
             tot[key] += st[key]
     assert tot["slow"] > 0 and tot["norm_iters"] > 0 and tot["jump2"] > 0 and tot["fast"] > 0
+
+
+def test_document_array_tables_vs_oracle(small_index, row_width):
+    """-d: the document tables of the flat image (per move row and per character record), walked on the CPU,
+    reproduce the oracle's document numbers (compute_ms_pml.cpp:288-340 / :625-682), both row layouts, PML and MS."""
+    ref = small_index["ref"]
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    fp = FlatImage(sp.Index.open(ref, sp.MODE_PML, use_doc=True).flat())
+    fm = FlatImage(sp.Index.open(ref, sp.MODE_MS, use_doc=True).flat())
+    assert fp.num_docs == 3 and fm.num_docs == 3
+    po, mo = oracle.OracleIndex(ref, "pml", use_doc=True), oracle.OracleIndex(ref, "ms", use_doc=True)
+    reads = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(0, 60)] + [b"ACGTNNACGT" * 5, b"N", b"ACG\xe9T" * 8]
+    rb, ro = sp.pack_reads(reads)
+    Lp, _, Dp = po.query_batch_doc(rb, ro)
+    Lm, Pm, Dm = mo.query_batch_doc(rb, ro)
+    for i, r in enumerate(reads):
+        a, b = int(ro[i]), int(ro[i + 1])
+        got, _, _ = fp.walk_rows(r)
+        assert got == Lp[a:b].tolist() and fp.docs == Dp[a:b].tolist(), (i, r[:20])
+        _, ptr, _ = fm.walk_rows(r)
+        assert ptr == Pm[a:b].tolist() and fm.docs == Dm[a:b].tolist(), (i, r[:20])
+    # an index opened without the document array has no document tables, and a missing .doc file fails loudly
+    assert FlatImage(sp.Index.open(ref, sp.MODE_PML).flat()).num_docs == 0
+    os.rename(ref + ".doc", ref + ".doc.bak")
+    try:
+        with pytest.raises(sp.SpumoniError):
+            sp.Index.open(ref, sp.MODE_PML, use_doc=True)
+    finally:
+        os.rename(ref + ".doc.bak", ref + ".doc")

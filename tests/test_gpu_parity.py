@@ -176,7 +176,7 @@ def test_attach_device_from_broadcast_buffer(small_index):
     assert np.array_equal(L, L2)
 
 
-@pytest.mark.parametrize("flags", [["-P"], ["-P", "-c"], ["-M"], ["-M", "-c", "-w", "100"]])
+@pytest.mark.parametrize("flags", [["-P"], ["-P", "-c"], ["-M"], ["-M", "-c", "-w", "100"], ["-P", "-d"], ["-M", "-d", "-c"]])
 def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
     ref = small_index["ref"]
     for ext in (".pmlnulldb", ".msnulldb"):
@@ -191,12 +191,14 @@ def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
     open(qb, "w").write(body)
     ms = "-M" in flags
     bw = int(flags[flags.index("-w") + 1]) if "-w" in flags else 150
-    oracle.run(ref, qa, "ms" if ms else "pml", report="-c" in flags, bin_width=bw, threads=1)
+    oracle.run(ref, qa, "ms" if ms else "pml", report="-c" in flags, bin_width=bw, threads=1, use_doc="-d" in flags)
     r = subprocess.run([sp.CLI_PATH, "run", "-r", ref[:-3], "-p", qb, "-n"] + flags, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     exts = [".lengths", ".pointers"] if ms else [".pseudo_lengths"]
     if "-c" in flags:
         exts.append(".report")
+    if "-d" in flags:
+        exts.append(".doc_numbers")
     for e in exts:
         assert open(qa + e, "rb").read() == open(qb + e, "rb").read(), e
     assert "finished processing 300 reads" in r.stderr
@@ -323,3 +325,47 @@ def test_unaligned_read_boundaries_narrow(small_index, row_width):
         assert np.array_equal(L.astype(np.uint64), Lo), w
         Lm, Pm, _ = ms.query_host(buf, off, length_bytes=w)
         assert np.array_equal(Lm.astype(np.uint64), Lmo) and np.array_equal(Pm, Pmo), w
+
+
+@pytest.mark.parametrize("mode", ["pml", "ms"])
+def test_document_numbers(small_index, mode, row_width):
+    """-d: document numbers (compute_ms_pml.cpp:288-340 / :625-682) bit-exact against the oracle, together with the
+    lengths / pointers / classifier stats of the same call; both row layouts; the fall-back build as well."""
+    import sys, textwrap
+    ref = small_index["ref"]
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    extra = [b"ACGTNNACGT" * 5, b"N", b"ACG\xe9T" * 8, b"", b"T"]
+    eb, eo = sp.pack_reads(extra)
+    buf2 = np.concatenate([buf, eb])
+    off2 = np.concatenate([off, eo[1:] + off[-1]]).astype(np.uint64)
+    o = oracle.OracleIndex(ref, mode, use_doc=True)
+    Lo, Po, Do = o.query_batch_doc(buf2, off2)
+    idx = (sp.pml_t if mode == "pml" else sp.ms_t)(ref, use_doc=True)
+    assert idx.num_docs() == 3
+    L, P, S, D = idx.query_host_doc(buf2, off2, bin_width=150, max_value_thr=9)
+    assert np.array_equal(D.astype(np.uint64), Do) and np.array_equal(L.astype(np.uint64), Lo)
+    if mode == "ms":
+        assert np.array_equal(P, Po)
+    L0, _, S0 = idx.query_host(buf2, off2, bin_width=150, max_value_thr=9)  # the same index still answers plain queries
+    assert np.array_equal(L0, L) and np.array_equal(S0, S)
+    with pytest.raises(sp.SpumoniError):  # index opened without the document array
+        (sp.pml_t if mode == "pml" else sp.ms_t)(ref).query_host_doc(buf2, off2)
+    with pytest.raises(sp.SpumoniError):  # cooperative kernels have no document support
+        idx.query_host_doc(buf2, off2, lanes=8)
+    out = str(tmp_path_for(small_index) / f"doc_{mode}_{row_width}.npy")
+    code = textwrap.dedent(f"""
+        import numpy as np, spumoni_b200 as sp
+        buf = np.load({out + ".buf.npy"!r}); off = np.load({out + ".off.npy"!r})
+        idx = (sp.pml_t if {mode!r} == "pml" else sp.ms_t)({ref!r}, use_doc=True)
+        np.save({out!r}, idx.query_host_doc(buf, off)[3])
+    """)
+    np.save(out + ".buf.npy", buf2); np.save(out + ".off.npy", off2)
+    env = dict(os.environ, SPUMONI_B200_LIB=sp.SATTEST_LIB_PATH, SPUMONI_B200_ROWS=row_width,
+               PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    subprocess.check_call([sys.executable, "-c", code], env=env)
+    assert np.array_equal(np.load(out).astype(np.uint64), Do)
+
+
+def tmp_path_for(small_index):
+    import pathlib
+    return pathlib.Path(small_index["dir"])

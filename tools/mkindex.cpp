@@ -239,13 +239,19 @@ static int cmd_build(const Args& a) {
     bool use_rc = !has(a, "no-revcomp"), verbose = has(a, "verbose");
     bool want_pml = has(a, "pml") || !has(a, "ms"), want_ms = has(a, "ms");
     bool keep = has(a, "keep");
+    // --docs N: the records are split into N contiguous groups ("documents": the reference groups whole input
+    // files, refbuilder.cpp:183-217); writes <prefix>.fa.fdi and <prefix>.fa.doc like `spumoni build -d`
+    const uint64_t ndocs = std::stoull(get(a, "docs", "0"));
     Fasta f = read_fasta(input);
+    if (ndocs > f.seqs.size()) die("build: --docs exceeds the number of records");
+    std::vector<uint64_t> doc_lengths(ndocs, 0);
     std::string ref = prefix + ".fa";
     std::vector<uint8_t> T;
     {
         std::ofstream o(ref);
         if (!o) die("cannot write " + ref);
         for (size_t k = 0; k < f.seqs.size(); k++) {
+            if (ndocs) doc_lengths[k * ndocs / f.seqs.size()] += f.seqs[k].size() * (use_rc ? 2 : 1);
             std::string s = f.seqs[k];
             for (auto& c : s) c = (char)std::toupper((unsigned char)c);
             o << '>' << f.names[k] << '\n' << s << '\n';
@@ -282,6 +288,12 @@ static int cmd_build(const Args& a) {
     if (want_ms) {
         std::ofstream o(ref + ".thrbv.ms", std::ios::binary);
         sdslw::write_ms_index(o, P);
+    }
+    if (ndocs) {
+        std::ofstream fdi(ref + ".fdi");
+        for (uint64_t g = 0; g < ndocs; g++) fdi << "group_" << (g + 1) << '\t' << doc_lengths[g] << '\n';
+        std::ofstream o(ref + ".doc", std::ios::binary);
+        sdslw::write_doc_array(o, P, doc_lengths);
     }
     if (verbose) std::fprintf(stderr, "[mkindex] serialise: %.2f s\n", now_s() - t0);
     std::printf("{\"n\": %llu, \"r\": %llu}\n", (unsigned long long)P.n, (unsigned long long)P.heads.size());

@@ -372,6 +372,29 @@ struct RlbwtParts {
     std::vector<uint64_t> ssa, esa;   // SA values at run start / end (as .ssa/.esa second column)
 };
 
+// DocumentArray ctor + serialize (/root/reference/src/doc_array.cpp:18-108, :184-195): the document of the BWT
+// character at every run boundary.  seq_lengths = the per-document text lengths of <prefix>.fa.fdi.
+inline void write_doc_array(std::ostream& o, const RlbwtParts& p, const std::vector<uint64_t>& seq_lengths) {
+    std::vector<uint64_t> end_pos(seq_lengths.size());
+    uint64_t sum = 0;
+    for (size_t i = 0; i < seq_lengths.size(); i++) { sum += seq_lengths[i]; end_pos[i] = sum; }
+    end_pos.back() += 1;  // the dollar sign belongs to the last document (:43-44)
+    auto doc_of = [&](uint64_t sample) {  // convert_to_bwt_pos (:47-50) then doc_ends_rank (:74-90)
+        const uint64_t pos = sample > 0 ? sample - 1 : end_pos.back() - 1;
+        return (uint64_t)(std::upper_bound(end_pos.begin(), end_pos.end(), pos) - end_pos.begin());  // #documents ending at or before pos
+    };
+    // max_width = ceil(log2(#docs)) (:97); sdsl turns a width of 0 into 64
+    uint32_t width = 0;
+    while ((1ULL << width) < seq_lengths.size()) width++;
+    if (width == 0) width = 64;
+    const size_t R = p.heads.size();
+    IntVec sd(R, (uint8_t)width), ed(R, (uint8_t)width);
+    for (size_t k = 0; k < R; k++) { sd.set(k, doc_of(p.ssa[k])); ed.set(k, doc_of(p.esa[k])); }
+    put_u64(o, (uint64_t)R);  // num_entries = file size / (2 * SSABYTES) (:26)
+    sd.write(o, true);
+    ed.write(o, true);
+}
+
 inline void write_pml_index(std::ostream& o, const RlbwtParts& p) {
     std::vector<uint64_t> F;
     uint64_t term = build_F(p.heads, p.lens, F);
