@@ -435,45 +435,6 @@ __device__ __noinline__ SlowOut slow_step(const WalkParams& p, uint32_t c, uint3
     return o;
 }
 
-// 16-byte output word holding 16/OW values of OW bytes each (lengths as u8 / u16 / u32)
-template <int OW>
-struct OutWord {
-    static constexpr uint32_t VPW = 16 / OW;
-    static constexpr uint32_t VMAX = OW == 4 ? 0xFFFFFFFFu : (OW == 2 ? 0xFFFFu : 0xFFu);
-    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-    __device__ __forceinline__ void clear() { w0 = w1 = w2 = w3 = 0; }
-    __device__ __forceinline__ uint4 as_uint4() const { return make_uint4(w0, w1, w2, w3); }
-    __device__ __forceinline__ void from_uint4(const uint4& v) { w0 = v.x; w1 = v.y; w2 = v.z; w3 = v.w; }
-    __device__ __forceinline__ void put(uint32_t slot, uint32_t v) {
-        const uint32_t word = (slot * OW) >> 2, sh = ((slot * OW) & 3u) * 8u;
-        const uint32_t bits = OW == 4 ? v : (v << sh);
-        if (word == 0) w0 |= bits; else if (word == 1) w1 |= bits; else if (word == 2) w2 |= bits; else w3 |= bits;
-    }
-    __device__ __forceinline__ uint32_t get(uint32_t slot) const {
-        const uint32_t word = (slot * OW) >> 2, sh = ((slot * OW) & 3u) * 8u;
-        const uint32_t w = word == 0 ? w0 : (word == 1 ? w1 : (word == 2 ? w2 : w3));
-        return OW == 4 ? w : ((w >> sh) & VMAX);
-    }
-};
-template <int OW>
-__device__ __forceinline__ void store_val(void* base, uint64_t idx, uint32_t v) {
-    if (OW == 4) reinterpret_cast<uint32_t*>(base)[idx] = v;
-    else if (OW == 2) reinterpret_cast<uint16_t*>(base)[idx] = (uint16_t)v;
-    else reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)v;
-}
-// Flush the word of group g (values g .. g+VPW-1); only entries in [lo, hi) were produced by this read.
-template <int OW>
-__device__ __forceinline__ void flush_word(void* out, const OutWord<OW>& b, uint64_t g, uint64_t lo, uint64_t hi) {
-    constexpr uint32_t VPW = OutWord<OW>::VPW;
-    if (lo <= g && g + VPW <= hi) {
-        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(reinterpret_cast<uint8_t*>(out) + g * OW), "r"(b.w0), "r"(b.w1), "r"(b.w2), "r"(b.w3) : "memory");
-    } else {
-#pragma unroll 1
-        for (uint32_t t = 0; t < VPW; t++)
-            if (g + t >= lo && g + t < hi) store_val<OW>(out, g + t, b.get(t));
-    }
-}
-
 // ---- per-thread staging of the read and output streams in shared memory -----------------------
 // A lane consumes one read byte and produces one value per step, so a 128-byte line of either stream
 // stays "live" for > 100 steps of > 100 000 resident lanes: left to the L2, these half-used lines evict
@@ -547,6 +508,41 @@ __device__ __forceinline__ void stage_value(uint4* s_out, void* out, uint64_t gi
         } else
             flush_partial<EB>(reinterpret_cast<uint8_t*>(out), s_out, sb, bo, hi < sb + SPB_STAGE ? hi : sb + SPB_STAGE);
     }
+}
+
+// Same for a read walked upwards (element gi of [base, end)): the block is complete when its last element arrives.
+template <int EB>
+__device__ __forceinline__ void stage_value_up(uint4* s_out, void* out, uint64_t gi, uint64_t v, uint64_t base, bool last) {
+    const uint64_t bo = gi * EB;
+    const uint32_t so = (uint32_t)bo & (SPB_STAGE - 1);
+    uint8_t* sp = reinterpret_cast<uint8_t*>(s_out) + staged_offset(so);
+    if (EB == 1) *sp = (uint8_t)v;
+    else if (EB == 2) *reinterpret_cast<uint16_t*>(sp) = (uint16_t)v;
+    else if (EB == 4) *reinterpret_cast<uint32_t*>(sp) = (uint32_t)v;
+    else *reinterpret_cast<uint64_t*>(sp) = v;
+    if (so + EB == SPB_STAGE || last) {
+        const uint64_t sb = bo - so, lo = base * EB;
+        if (so + EB == SPB_STAGE && sb >= lo) {
+#pragma unroll
+            for (int j = 0; j < SPB_STAGE_CH; j++) st_stream16(reinterpret_cast<uint8_t*>(out) + sb + 16 * j, s_out[j * SPB_MV_THREADS + threadIdx.x]);
+        } else
+            flush_partial<EB>(reinterpret_cast<uint8_t*>(out), s_out, sb, lo > sb ? lo : sb, bo + EB);
+    }
+}
+// The first `need` (1..8) bytes at an arbitrary byte address, in the low bytes of the result: two aligned loads +
+// funnel shift; the second word is only touched when one of the needed bytes lies in it.
+__device__ __forceinline__ uint64_t ld_unaligned8(const uint8_t* p, uint32_t need) {
+    const uint64_t* a = reinterpret_cast<const uint64_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)7);
+    const uint32_t sh = ((uint32_t)reinterpret_cast<uintptr_t>(p) & 7u) * 8u;
+    const uint64_t lo = __ldg(a);
+    if (sh + 8u * need <= 64u) return lo >> sh;
+    return (lo >> sh) | (__ldg(a + 1) << (64 - sh));
+}
+__device__ __forceinline__ uint64_t toupper8(uint64_t x) {  // ::toupper on 8 packed bytes ('a'..'z' only, C locale)
+    const uint64_t t = x & 0x7F7F7F7F7F7F7F7Full;
+    const uint64_t ge_a = t + 0x1F1F1F1F1F1F1F1Full, gt_z = t + 0x0505050505050505ull;
+    const uint64_t m = ge_a & ~gt_z & ~x & 0x8080808080808080ull;
+    return x - (m >> 2);
 }
 
 struct BinState {
@@ -768,18 +764,20 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
 }
 
 // MS pointers -> lengths (ms_t::matching_statistics, compute_ms_pml.cpp:795-812) + bin-max classifier
-// (:1150-1176); one thread per read, left to right, carrying l.  Each iteration either compares one
-// more character (read vs text at pointer + l) or emits one length.
+// (:1150-1176); one thread per read, left to right, carrying l.  Each iteration either compares up to eight
+// more characters (read vs text at pointer + l, word-wise) or emits one length; lengths are staged in shared
+// memory and written as whole blocks like the walk kernel's outputs.
 template <bool STATS, int OW>
-__global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const WalkParams p) {
+__global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const __grid_constant__ WalkParams p) {
+    __shared__ uint4 s_out[SPB_STAGE_CH * SPB_MV_THREADS];
     const bool upper = (p.flags & SPB_FLAG_TOUPPER) != 0;
     const bool do_stats = STATS && p.bin_width != 0 && p.stats != nullptr;
     const uint64_t n_text = p.n_text;
+    constexpr uint32_t VMAX = OW == 4 ? 0xFFFFFFFFu : (OW == 2 ? 0xFFFFu : 0xFFu);
     bool have = false, ext = false;
     unsigned long long r = 0;
     uint64_t base = 0, m = 0, i = 0, l = 0, ptr = 0, prev = 0, nbins = 1, bins_closed = 0;
     uint32_t nsat = 0;
-    OutWord<OW> ob;
     BinState bs;
     for (;;) {
         if (!have) {
@@ -794,7 +792,6 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const Wa
             i = 0; l = 0; prev = 0;
             ptr = p.pointers[base];
             ext = true;
-            ob.clear();
             have = true;
             if (do_stats) {
                 const uint64_t bw = p.bin_width;
@@ -805,28 +802,28 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const Wa
             }
         }
         if (ext) {
+            // while (i + l < m && ptr + l < n && read[i + l] == text[ptr + l]) ++l;   eight characters per iteration
             const uint64_t tp = ptr + l;  // wraps like size_t (App. C-4)
-            bool ok = (i + l < m) && (tp < n_text);
-            if (ok) {
-                uint32_t rc = p.reads[base + i + l];
-                if (upper && rc >= 'a' && rc <= 'z') rc -= 32;
-                ok = rc == (uint32_t)p.text[tp];
+            uint64_t room = (i + l < m) ? m - (i + l) : 0;
+            if (tp < n_text) { if (n_text - tp < room) room = n_text - tp; } else room = 0;
+            uint32_t adv = 0;
+            if (room) {
+                const uint32_t need = room < 8 ? (uint32_t)room : 8u;
+                uint64_t a = ld_unaligned8(p.reads + base + i + l, need);
+                if (upper) a = toupper8(a);
+                const uint64_t x = a ^ ld_unaligned8(p.text + tp, need);
+                adv = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+                if (adv > room) adv = (uint32_t)room;
             }
-            if (ok) { l++; continue; }
+            l += adv;
+            if (adv == 8) continue;
             ext = false;
         }
         // ---- emit lengths[i] = l
         {
-            constexpr uint32_t VPW = OutWord<OW>::VPW;
-            const uint64_t gidx = base + i;
-            const uint32_t slot = (uint32_t)gidx & (VPW - 1);
             uint32_t v = (uint32_t)l;
-            if (OW < 4 && v > OutWord<OW>::VMAX) { v = OutWord<OW>::VMAX; nsat++; }
-            ob.put(slot, v);
-            if (slot == VPW - 1 || i == m - 1) {
-                flush_word<OW>(p.lengths, ob, gidx & ~(uint64_t)(VPW - 1), base, gidx + 1);
-                ob.clear();
-            }
+            if (OW < 4 && v > VMAX) { v = VMAX; nsat++; }
+            stage_value_up<OW>(s_out, p.lengths, base + i, v, base, i == m - 1);
             if (do_stats) {
                 if (i >= bs.bound && bins_closed + 1 < nbins) {
                     if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;

@@ -23,8 +23,12 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -141,17 +145,53 @@ struct ReadBatch {
     std::vector<std::string> ids;
     std::vector<uint64_t> offsets{0};
     std::vector<uint8_t> bases;
-    void clear() { ids.clear(); offsets.assign(1, 0); bases.clear(); }
+    uint64_t max_len = 0;  // longest read of the batch
+    void clear() { ids.clear(); offsets.assign(1, 0); bases.clear(); max_len = 0; }
+};
+
+// std::getline semantics (lines split at '\n', a last line without terminator still counts) over 16 MiB reads
+class LineReader {
+public:
+    explicit LineReader(const std::string& path) : f_(std::fopen(path.c_str(), "rb")), buf_(16u << 20) {}
+    ~LineReader() { if (f_) std::fclose(f_); }
+    bool good() const { return f_ != nullptr; }
+    int peek() { return fill() ? (unsigned char)buf_[pos_] : EOF; }
+    bool getline(std::string& line) {
+        line.clear();
+        bool any = false;
+        for (;;) {
+            if (!fill()) return any;
+            any = true;
+            const char* p = buf_.data() + pos_;
+            const char* nl = (const char*)std::memchr(p, '\n', end_ - pos_);
+            if (nl) { line.append(p, (size_t)(nl - p)); pos_ = (size_t)(nl - buf_.data()) + 1; return true; }
+            line.append(p, end_ - pos_);
+            pos_ = end_;
+        }
+    }
+private:
+    bool fill() {
+        if (pos_ < end_) return true;
+        if (!f_ || eof_) return false;
+        end_ = std::fread(buf_.data(), 1, buf_.size(), f_);
+        pos_ = 0;
+        if (end_ == 0) eof_ = true;
+        return end_ > 0;
+    }
+    std::FILE* f_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, end_ = 0;
+    bool eof_ = false;
 };
 
 class FastaSource {  // sequential equivalent of BatchLoader::loadBatch + grabNextRead (FASTA)
 public:
-    explicit FastaSource(const std::string& path) : in_(path.c_str()) {
+    explicit FastaSource(const std::string& path) : in_(path) {
         if (!in_.good()) return;
         int pk = in_.peek();
         if (pk == EOF) { done_ = true; return; }
         if (pk != '>') fatal_error("unrecognized input query file type - expects FASTA or FASTQ.");
-        if (!std::getline(in_, line_)) done_ = true;
+        if (!in_.getline(line_)) done_ = true;
     }
     // appends one record; false at end of input
     bool next(ReadBatch& b) {
@@ -163,7 +203,7 @@ public:
         b.ids.push_back(line_.substr(1, idl));  // keeps the delimiter (batch_loader.cpp:104-106)
         const size_t before = b.bases.size();
         for (;;) {
-            if (!std::getline(in_, line_)) { done_ = true; break; }
+            if (!in_.getline(line_)) { done_ = true; break; }
             if (!line_.empty() && line_[0] == '>') break;
             size_t e = line_.size();
             while (e > 0 && std::isspace((unsigned char)line_[e - 1])) e--;
@@ -175,10 +215,11 @@ public:
                           "characters. Please remove read or run SPUMONI without minimizer digestion.");
         }
         b.offsets.push_back(b.bases.size());
+        if (b.bases.size() - before > b.max_len) b.max_len = b.bases.size() - before;
         return true;
     }
 private:
-    std::ifstream in_;
+    LineReader in_;
     std::string line_;
     bool done_ = false;
 };
@@ -232,37 +273,89 @@ static void report_row(std::ofstream& f, const std::string& id, const spb_bin_st
 }
 
 // ---------------------------------------------------------------------------------- driver
+// Three stages run concurrently on batches of ~64 Mi bases: a parser thread (FASTA -> batch), the calling thread
+// (GPU query through the C ABI) and a writer thread (decimal formatting on -t threads + file writes, in input
+// order -- the reference's own order for -t 1, App. C-11).
 struct Outputs {
     std::ofstream lengths, pointers, report, docs;
 };
 
-static void process_batch(spb_index* idx, bool ms, const RunOptions& o, const spb_query_opts& qo, ReadBatch& b, Outputs& out,
-                          std::vector<uint32_t>& L, std::vector<uint64_t>& P, std::vector<spb_bin_stats>& S, std::vector<uint32_t>& D) {
+struct Work {
+    ReadBatch b;
+    std::vector<uint32_t> L;
+    std::vector<uint16_t> L16;  // lengths travel as uint16 when every read of the batch is < 65536 bases (lossless)
+    std::vector<uint64_t> P;
+    std::vector<spb_bin_stats> S;
+    std::vector<uint32_t> D;
+    bool narrow = false;
+};
+
+class WorkQueue {  // bounded hand-off between two stages; nullptr = end of stream
+public:
+    void push(Work* w) {
+        std::unique_lock<std::mutex> lk(m_);
+        q_.push_back(w);
+        cv_.notify_all();
+    }
+    Work* pop() {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [&] { return !q_.empty(); });
+        Work* w = q_.front();
+        q_.pop_front();
+        return w;
+    }
+private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<Work*> q_;
+};
+
+static void query_batch(spb_index* idx, bool ms, const RunOptions& o, spb_query_opts qo, Work& w) {
+    ReadBatch& b = w.b;
     const size_t nr = b.ids.size();
     if (!nr) return;
-    L.resize(b.bases.size());
-    if (ms) P.resize(b.bases.size());
-    if (o.use_doc) D.resize(b.bases.size());
-    if (o.write_report) S.resize(nr);
-    spb_bin_stats* sp = o.write_report ? S.data() : nullptr;
+    w.narrow = !o.use_doc && b.max_len < 65536;
+    void* lengths;
+    if (w.narrow) { w.L16.resize(b.bases.size()); lengths = w.L16.data(); qo.length_bytes = 2; }
+    else { w.L.resize(b.bases.size()); lengths = w.L.data(); }
+    if (ms) w.P.resize(b.bases.size());
+    if (o.use_doc) w.D.resize(b.bases.size());
+    if (o.write_report) w.S.resize(nr);
+    spb_bin_stats* sp = o.write_report ? w.S.data() : nullptr;
     if (o.use_doc) {
-        if (ms) spb_or_die(spb_ms_query_host_doc(idx, b.bases.data(), b.offsets.data(), nr, L.data(), P.data(), D.data(), sp, &qo));
-        else spb_or_die(spb_pml_query_host_doc(idx, b.bases.data(), b.offsets.data(), nr, L.data(), D.data(), sp, &qo));
-    } else if (ms) spb_or_die(spb_ms_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), P.data(), sp, &qo));
-    else spb_or_die(spb_pml_query_host(idx, b.bases.data(), b.offsets.data(), nr, L.data(), sp, &qo));
+        if (ms) spb_or_die(spb_ms_query_host_doc(idx, b.bases.data(), b.offsets.data(), nr, w.L.data(), w.P.data(), w.D.data(), sp, &qo));
+        else spb_or_die(spb_pml_query_host_doc(idx, b.bases.data(), b.offsets.data(), nr, w.L.data(), w.D.data(), sp, &qo));
+    } else if (ms) spb_or_die(spb_ms_query_host(idx, b.bases.data(), b.offsets.data(), nr, lengths, w.P.data(), sp, &qo));
+    else spb_or_die(spb_pml_query_host(idx, b.bases.data(), b.offsets.data(), nr, lengths, sp, &qo));
+}
+
+static void write_batch(bool ms, const RunOptions& o, const Work& w, Outputs& out, double& t_format, double& t_write) {
+    const ReadBatch& b = w.b;
+    const size_t nr = b.ids.size();
+    if (!nr) return;
     std::vector<std::string> parts;
+    double t0 = now_s();
+    auto lap = [&](double& acc) { const double t1 = now_s(); acc += t1 - t0; t0 = t1; };
     if (o.use_doc) {  // the reference writes the document numbers first (:1003-1006)
-        format_values(b, D.data(), (int)o.threads, parts);
+        format_values(b, w.D.data(), (int)o.threads, parts);
+        lap(t_format);
         write_all(out.docs, parts);
+        lap(t_write);
     }
-    format_values(b, L.data(), (int)o.threads, parts);
+    if (w.narrow) format_values(b, w.L16.data(), (int)o.threads, parts);
+    else format_values(b, w.L.data(), (int)o.threads, parts);
+    lap(t_format);
     write_all(out.lengths, parts);
+    lap(t_write);
     if (ms) {
-        format_values(b, P.data(), (int)o.threads, parts);
+        format_values(b, w.P.data(), (int)o.threads, parts);
+        lap(t_format);
         write_all(out.pointers, parts);
+        lap(t_write);
     }
     if (o.write_report)
-        for (size_t r = 0; r < nr; r++) report_row(out.report, b.ids[r], S[r]);
+        for (size_t r = 0; r < nr; r++) report_row(out.report, b.ids[r], w.S[r]);
+    lap(t_write);
 }
 
 static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
@@ -287,35 +380,75 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
             report_header(out.report, qo.max_value_thr);
         }
     }
-    const uint64_t kBatchBases = 256ull << 20;
-    ReadBatch b;
-    std::vector<uint32_t> L;
-    std::vector<uint64_t> P;
-    std::vector<spb_bin_stats> S;
-    std::vector<uint32_t> D;
+    const uint64_t kBatchBases = 64ull << 20;
+    constexpr int kWorks = 4;
+    const bool timing = std::getenv("SPUMONI_B200_TIMING") != nullptr;  // per-stage busy time on stderr
+    double t_parse = 0, t_gpu = 0, t_format = 0, t_write = 0;
+    std::vector<Work> works(kWorks);
+    WorkQueue free_q, parsed_q, done_q;
+    for (auto& w : works) free_q.push(&w);
     size_t num_reads = 0;
-    if (!o.is_general_text) {
-        FastaSource src(o.pattern_file);
-        while (src.next(b)) {
-            num_reads++;
-            if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S, D); b.clear(); }
-        }
-    } else {  // classify_general_reads_*: reads are separated by 0x01, ids are read_<i>
-        std::ifstream fd(o.pattern_file, std::ifstream::in | std::ifstream::binary);
-        char ch = (char)fd.get();
-        while (fd.good()) {
-            if (ch == '\x01') {
-                b.ids.push_back("read_" + std::to_string(num_reads));
-                b.offsets.push_back(b.bases.size());
+
+    std::thread parser([&] {
+        Work* w = free_q.pop();
+        w->b.clear();
+        double t0 = now_s();
+        auto flush = [&](bool last) {
+            t_parse += now_s() - t0;
+            parsed_q.push(w);
+            if (last) { parsed_q.push(nullptr); return; }
+            w = free_q.pop();
+            w->b.clear();
+            t0 = now_s();
+        };
+        if (!o.is_general_text) {
+            FastaSource src(o.pattern_file);
+            while (src.next(w->b)) {
                 num_reads++;
-                if (b.bases.size() >= kBatchBases) { process_batch(idx, ms, o, qo, b, out, L, P, S, D); b.clear(); }
-            } else
-                b.bases.push_back((uint8_t)ch);
-            ch = (char)fd.get();
+                if (w->b.bases.size() >= kBatchBases) flush(false);
+            }
+        } else {  // classify_general_reads_*: reads are separated by 0x01, ids are read_<i>
+            std::ifstream fd(o.pattern_file, std::ifstream::in | std::ifstream::binary);
+            char ch = (char)fd.get();
+            uint64_t cur = 0;
+            while (fd.good()) {
+                if (ch == '\x01') {
+                    w->b.ids.push_back("read_" + std::to_string(num_reads));
+                    w->b.offsets.push_back(w->b.bases.size());
+                    if (cur > w->b.max_len) w->b.max_len = cur;
+                    cur = 0;
+                    num_reads++;
+                    if (w->b.bases.size() >= kBatchBases) flush(false);
+                } else {
+                    w->b.bases.push_back((uint8_t)ch);
+                    cur++;
+                }
+                ch = (char)fd.get();
+            }
+            w->b.bases.resize(w->b.offsets.back());  // bytes after the last separator are never queried
         }
-        b.bases.resize(b.offsets.back());  // bytes after the last separator are never queried
+        flush(true);
+    });
+    std::thread writer([&] {
+        for (;;) {
+            Work* w = done_q.pop();
+            if (!w) break;
+            write_batch(ms, o, *w, out, t_format, t_write);
+            free_q.push(w);
+        }
+    });
+    for (;;) {
+        Work* w = parsed_q.pop();
+        if (!w) break;
+        const double t0 = now_s();
+        query_batch(idx, ms, o, qo, *w);
+        t_gpu += now_s() - t0;
+        done_q.push(w);
     }
-    process_batch(idx, ms, o, qo, b, out, L, P, S, D);
+    done_q.push(nullptr);
+    parser.join();
+    writer.join();
+    if (timing) std::fprintf(stderr, "\n[timing] busy seconds per stage: parse %.3f | query (H2D + kernels + D2H) %.3f | format %.3f | write %.3f\n", t_parse, t_gpu, t_format, t_write);
     return num_reads;
 }
 
