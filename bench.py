@@ -317,7 +317,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         cores = os.cpu_count() or 1
-        sample_reads = min(n_reads, max(200, (2500 if mode == "pml" else 800) * cores * 1000 // w["read_len"]))
+        sample_reads = min(n_reads, max(200, (7000 if mode == "pml" else 6000) * cores * 1000 // w["read_len"]))  # ~10 s of CPU work
         o = oracle.OracleIndex(ref, mode)
         sec, Lo, Po = o.query_batch(buf[: int(off[sample_reads])], off[: sample_reads + 1], threads=cores)
         sb = int(off[sample_reads])

@@ -25,6 +25,7 @@
 #include <iostream>
 #include <condition_variable>
 #include <deque>
+#include <memory>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -233,29 +234,58 @@ static inline char* put_uint(char* p, uint64_t v) {
     return p;
 }
 
+static inline uint32_t digits10(uint64_t v) {
+    uint32_t d = 1;
+    while (v >= 10) { v /= 10; d++; }
+    return d;
+}
+
+// One output file's text for a batch: per read '>' id '\n' then every value followed by one space, then '\n'
+// (compute_ms_pml.cpp:1003-1010).  Two passes over the values on -t threads: exact sizes, then the bytes, into one
+// contiguous buffer that is reused between batches and written with a single call.
+struct TextBuffer {
+    std::unique_ptr<char[]> data;
+    size_t cap = 0, size = 0;
+    std::vector<uint64_t> start;  // per read
+    void reserve(size_t n) {
+        if (n > cap) { cap = n + n / 8; data.reset(new char[cap]); }
+    }
+};
+
 template <typename T>
-static void format_values(const ReadBatch& b, const T* vals, int threads, std::vector<std::string>& out) {
+static void format_values(const ReadBatch& b, const T* vals, int threads, TextBuffer& out) {
     const size_t nr = b.ids.size();
-    out.resize(nr);
-#pragma omp parallel for schedule(dynamic, 64) num_threads(threads)
+    out.start.resize(nr + 1);
+#pragma omp parallel for schedule(static) num_threads(threads)
     for (int64_t r = 0; r < (int64_t)nr; r++) {
         const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1];
-        std::string& s = out[r];
-        s.resize(b.ids[r].size() + 3 + (hi - lo) * 21);
-        char* p = &s[0];
+        uint64_t bytes = b.ids[r].size() + 3 + (hi - lo);  // '>' id '\n' ... '\n' + one space per value
+        for (uint64_t i = lo; i < hi; i++) bytes += vals[i] < 10 ? 1 : digits10((uint64_t)vals[i]);
+        out.start[r + 1] = bytes;
+    }
+    out.start[0] = 0;
+    for (size_t r = 0; r < nr; r++) out.start[r + 1] += out.start[r];
+    out.size = out.start[nr];
+    out.reserve(out.size);
+    char* base = out.data.get();
+#pragma omp parallel for schedule(static) num_threads(threads)
+    for (int64_t r = 0; r < (int64_t)nr; r++) {
+        const uint64_t lo = b.offsets[r], hi = b.offsets[r + 1];
+        char* p = base + out.start[r];
         *p++ = '>';
         std::memcpy(p, b.ids[r].data(), b.ids[r].size());
         p += b.ids[r].size();
         *p++ = '\n';
-        for (uint64_t i = lo; i < hi; i++) { p = put_uint(p, (uint64_t)vals[i]); *p++ = ' '; }
+        for (uint64_t i = lo; i < hi; i++) {
+            const uint64_t v = (uint64_t)vals[i];
+            if (v < 10) *p++ = (char)('0' + v); else p = put_uint(p, v);
+            *p++ = ' ';
+        }
         *p++ = '\n';
-        s.resize((size_t)(p - &s[0]));
     }
 }
 
-static void write_all(std::ofstream& f, const std::vector<std::string>& parts) {
-    for (const auto& s : parts) f.write(s.data(), (std::streamsize)s.size());
-}
+static void write_all(std::ofstream& f, const TextBuffer& t) { f.write(t.data.get(), (std::streamsize)t.size); }
 
 static void report_header(std::ofstream& f, size_t thr) {  // compute_ms_pml.cpp:877-886
     f.precision(4);
@@ -263,7 +293,7 @@ static void report_header(std::ofstream& f, size_t thr) {  // compute_ms_pml.cpp
       << "avg max-value (thr=" << std::setw(2) << std::left << thr << std::setw(5) << std::left << "):" << std::setw(12)
       << std::left << "above thr:" << std::setw(12) << std::left << "below thr:" << std::endl;
 }
-static void report_row(std::ofstream& f, const std::string& id, const spb_bin_stats& s) {  // :1012-1020
+static void report_row(std::ostream& f, const std::string& id, const spb_bin_stats& s) {  // :1012-1020
     const size_t nbins = (size_t)s.above + s.below;
     const bool found = (s.above / (s.above + s.below + 0.0) > 0.50);
     f.precision(3);
@@ -333,7 +363,7 @@ static void write_batch(bool ms, const RunOptions& o, const Work& w, Outputs& ou
     const ReadBatch& b = w.b;
     const size_t nr = b.ids.size();
     if (!nr) return;
-    std::vector<std::string> parts;
+    static thread_local TextBuffer parts;  // one writer thread: the buffer is reused between batches
     double t0 = now_s();
     auto lap = [&](double& acc) { const double t1 = now_s(); acc += t1 - t0; t0 = t1; };
     if (o.use_doc) {  // the reference writes the document numbers first (:1003-1006)
@@ -353,8 +383,18 @@ static void write_batch(bool ms, const RunOptions& o, const Work& w, Outputs& ou
         write_all(out.pointers, parts);
         lap(t_write);
     }
-    if (o.write_report)
-        for (size_t r = 0; r < nr; r++) report_row(out.report, b.ids[r], w.S[r]);
+    if (o.write_report) {  // rows are formatted on -t threads with the reference's manipulators, written in order
+        std::vector<std::string> rows((size_t)std::max<size_t>(1, o.threads));
+#pragma omp parallel num_threads((int)rows.size())
+        {
+            const size_t t = (size_t)omp_get_thread_num(), nt = (size_t)omp_get_num_threads();
+            std::ostringstream os;
+            for (size_t r = nr * t / nt; r < nr * (t + 1) / nt; r++) report_row(os, b.ids[r], w.S[r]);
+            rows[t] = os.str();
+        }
+        lap(t_format);
+        for (const auto& r : rows) out.report.write(r.data(), (std::streamsize)r.size());
+    }
     lap(t_write);
 }
 
