@@ -151,7 +151,7 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     if (((uintptr_t)d_reads & 255u) != 0) return fail(SPB_ERR_ARG, "d_reads must be 256-byte aligned");
     if (((uintptr_t)d_lengths & 15u) != 0 || ((uintptr_t)d_pointers & 15u) != 0) return fail(SPB_ERR_ARG, "d_lengths / d_pointers must be 16-byte aligned");
     const SpbFlatHeader& h = idx->hdr;
-    const bool has_fast = h.num_fast > 0 && (h.off_mrows != 0 || h.off_mrows8 != 0) && (!ms || h.off_msamp != 0);
+    const bool has_fast = h.num_fast > 0 && (h.off_mrows != 0 || h.off_mrows8 != 0) && (!ms || h.off_msamp != 0 || h.mrows8_stride == 16);
     int lanes = opts && opts->lanes_per_read ? (int)opts->lanes_per_read : (has_fast ? 1 : kDefaultLanes);
     if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SPB_ERR_ARG, "lanes_per_read must be 1, 4, 8, 16 or 32");
     if (lanes == 1 && !has_fast) return fail(SPB_ERR_ARG, "lanes_per_read = 1 needs an index with fast symbols (frequent run heads < 0x80)");
@@ -182,7 +182,8 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.max_value_thr = opts ? opts->max_value_thr : 0;
     p.rows = (has_fast && h.off_mrows) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_mrows) : nullptr;
     p.rows8 = (has_fast && h.off_mrows8) ? reinterpret_cast<const uint64_t*>(idx->dev_blob + h.off_mrows8) : nullptr;
-    p.msamp = (has_fast && ms) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_msamp) : nullptr;
+    p.msamp = (has_fast && ms && h.off_msamp) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_msamp) : nullptr;
+    p.rows8_stride = h.mrows8_stride;
     for (int i = 0; i < 4; i++) { p.mv_end_k[i] = h.mv_end_k[i]; p.mv_end_off[i] = h.mv_end_off[i]; p.mv_end_sl[i] = h.mv_end_sl[i]; }
     p.out_width = (uint32_t)width;
     p.row_ld = idx->row_ld;

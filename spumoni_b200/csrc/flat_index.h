@@ -153,7 +153,8 @@ struct SpbFlatHeader {
     uint32_t doc_init;           // end_runs_doc[R-1]: document of the empty match (compute_ms_pml.cpp:298, :634)
     uint32_t doc_absent_ms;      // start_runs_doc[run_of_position(0)]: MS mode, character absent from the index (:640-642)
     uint32_t mv_end_doc[4];      // end_runs_doc of the last c-run per fast symbol
-    uint32_t pad1;
+    uint32_t mrows8_stride;      // 8, or 16 (MS, n < 2^32): every compact row is followed by {u32 ss, u32 sl} -- the SpbCharSamp of
+                                 // that row in 32 bits -- so that a jump gets its SA sample from the row load itself (no msamp table)
     uint64_t pad2;               // keeps chartab 16-byte aligned (the kernels load its entries as uint4)
     uint64_t F[256];
     SpbCharTab chartab[256];

@@ -468,16 +468,20 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     bool rows8 = num_fast && R + SPB_MV8_ROW_PAD < SPB_MV8_MAX_RUNS;
     if (const char* e = std::getenv("SPUMONI_B200_ROWS")) if (std::atoi(e) == 16) rows8 = false;
     if (num_fast) {
+        // MS over compact rows: with 32-bit text positions the two samples of a row ride in the same 16 bytes
+        bool ms_inline = ms && rows8 && n < (1ull << 32);
+        if (const char* e = std::getenv("SPUMONI_B200_MSAMP")) if (std::string(e) == "wide") ms_inline = false;
+        h.mrows8_stride = rows8 ? (ms_inline ? 16u : 8u) : 0u;
         if (rows8) {
             h.off_mrows8 = off;
-            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(uint64_t), 256);
+            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * h.mrows8_stride, 256);
         } else {
             h.off_mrows = off;
             off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow), 256);
         }
-        if (ms) {
+        if (ms && !ms_inline) {
             h.off_msamp = off;
-            off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbCharSamp), 256);
+            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(SpbCharSamp), 256);
         }
     }
     const bool use_doc = !d.doc_start.empty();
@@ -601,7 +605,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
     if (num_fast) {
         SpbMoveRow* rows = rows8 ? nullptr : reinterpret_cast<SpbMoveRow*>(blob.data() + h.off_mrows);
         uint64_t* rows_c = rows8 ? reinterpret_cast<uint64_t*>(blob.data() + h.off_mrows8) : nullptr;
-        SpbCharSamp* msamp = ms ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
+        SpbCharSamp* msamp = (ms && h.off_msamp) ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
         SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
         // next run (strictly after k) headed by each fast symbol, by a backward sweep
         std::vector<uint32_t> nxt((size_t)R * num_fast);
@@ -658,7 +662,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                 }
                 const uint64_t lo = (uint64_t)de | ((uint64_t)std::min<uint64_t>(len_k, SPB_MV8_LEN_MAX) << 24) | ((uint64_t)(slow ? 1 : 0) << 31);
                 const uint64_t hi = (uint64_t)std::min<uint64_t>(delta, SPB_MV8_DELTA_MAX) | ((uint64_t)std::min<uint32_t>(hk, SPB_SYM_SLOW) << 8) | (cls << 11) | (T << 17) | (dist << 23);
-                rows_c[k] = lo | (hi << 32);
+                rows_c[k * (h.mrows8_stride / 8)] = lo | (hi << 32);
                 continue;
             }
             SpbMoveRow r;
@@ -671,7 +675,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         }
         if (rows8) {
             for (uint64_t k = R; k < R + SPB_MV8_ROW_PAD; k++)  // row R = "pos == n": generic step only
-                rows_c[k] = ((uint64_t)R | (1ull << 24) | (1ull << 31)) | ((uint64_t)(SPB_SYM_SLOW << 8) << 32);
+                rows_c[k * (h.mrows8_stride / 8)] = ((uint64_t)R | (1ull << 24) | (1ull << 31)) | ((uint64_t)(SPB_SYM_SLOW << 8) << 32);
         }
         for (uint64_t k = R; !rows8 && k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
             SpbMoveRow r;
@@ -683,8 +687,11 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
             std::vector<uint64_t> prev_sl(256, 0);
             for (uint64_t k = 0; k < R; k++) {
                 const uint8_t c = d.heads[(size_t)k];
-                msamp[k].ss = d.samples_start[(size_t)k];
-                msamp[k].sl = prev_sl[c];
+                if (msamp) {
+                    msamp[k].ss = d.samples_start[(size_t)k];
+                    msamp[k].sl = prev_sl[c];
+                } else  // inline: the second 8 bytes of the 16-byte row slot (text positions < n < 2^32)
+                    rows_c[k * 2 + 1] = (uint64_t)(uint32_t)d.samples_start[(size_t)k] | ((uint64_t)(uint32_t)prev_sl[c] << 32);
                 prev_sl[c] = d.samples_last[(size_t)k];
             }
             for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_sl[s] = prev_sl[h.fast_sym[s]];

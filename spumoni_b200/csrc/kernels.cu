@@ -550,7 +550,8 @@ struct BinState {
     uint32_t bin_max = 0, above = 0, below = 0;
 };
 
-template <bool MS, bool STATS, int OW, int LD, bool ROW8, bool DOC>
+// MSI (MS over compact rows only): every row slot is 16 bytes, {row, u32 ss, u32 sl}: the samples come with the row load
+template <bool MS, bool STATS, int OW, int LD, bool ROW8, bool DOC, bool MSI = false>
 __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB > 8) ? 8 : SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
@@ -615,7 +616,13 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         if (upper && c >= 'a' && c <= 'z') c -= 32;
         bool slow = false, emit = false;
         if (ROW8) {
-            const uint2 v = ld_row8<LD>(p.rows8 + (mode ? k2 : k));  // x = lo, y = hi (flat_index.h)
+            uint2 v;  // x = lo, y = hi (flat_index.h)
+            uint2 smp = make_uint2(0, 0);
+            if (MSI) {
+                const uint4 q = ld_row<LD>(reinterpret_cast<const uint4*>(p.rows8) + (mode ? k2 : k));
+                v = make_uint2(q.x, q.y);
+                smp = make_uint2(q.z, q.w);
+            } else v = ld_row8<LD>(p.rows8 + (mode ? k2 : k));
             if (mode == 0) {
                 if (v.x >> 31) slow = true;
                 else {
@@ -655,7 +662,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
                     if (v.x >> 31) slow = true;  // landing state not encodable: redo the step from (k, off)
                     else {
                         const uint32_t d2 = v.y & 0xFFu, de = v.x & 0xFFFFFFu;
-                        if (MS) {
+                        if (MS && MSI) sample = down ? smp.y : smp.x;
+                        else if (MS) {
                             const uint4 sm = ldg_nc16(p.msamp + k2);
                             sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
                         }
@@ -881,10 +889,12 @@ template <int LD, bool ROW8>
 static cudaError_t launch_move(const WalkParams& p, bool ms, bool stats, int num_sms, cudaStream_t stream) {
     if (p.docs) {  // document numbers: u32 lengths, L1-allocating rows only (keeps the number of kernel variants down)
         if (p.out_width != 4) return cudaErrorInvalidValue;
+        if (ms && ROW8 && p.rows8_stride == 16) return launch_persistent(spb_move_kernel<true, false, 4, 1, ROW8, true, ROW8>, p, num_sms, stream);
         if (ms) return launch_persistent(spb_move_kernel<true, false, 4, 1, ROW8, true>, p, num_sms, stream);
         return stats ? launch_persistent(spb_move_kernel<false, true, 4, 1, ROW8, true>, p, num_sms, stream)
                      : launch_persistent(spb_move_kernel<false, false, 4, 1, ROW8, true>, p, num_sms, stream);
     }
+    if (ms && ROW8 && p.rows8_stride == 16) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8, false, ROW8>, p, num_sms, stream);
     if (ms) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8, false>, p, num_sms, stream);
     return stats ? launch_move_pml<true, LD, ROW8>(p, num_sms, stream) : launch_move_pml<false, LD, ROW8>(p, num_sms, stream);
 }
@@ -914,7 +924,7 @@ static cudaError_t launch_t(const WalkParams& p, int num_sms, cudaStream_t strea
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches) {
     const bool stats = p.bin_width && p.stats;
     if (lanes == 1) {
-        if ((!p.rows && !p.rows8) || (ms && !p.msamp)) return cudaErrorInvalidValue;
+        if ((!p.rows && !p.rows8) || (ms && !p.msamp && p.rows8_stride != 16)) return cudaErrorInvalidValue;
         cudaError_t e;
         if (p.rows8) e = p.row_ld ? launch_move<1, true>(p, ms, stats, num_sms, stream) : launch_move<0, true>(p, ms, stats, num_sms, stream);
         else e = p.row_ld ? launch_move<1, false>(p, ms, stats, num_sms, stream) : launch_move<0, false>(p, ms, stats, num_sms, stream);

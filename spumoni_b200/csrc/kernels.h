@@ -34,6 +34,7 @@ struct WalkParams {
     // thread-per-read kernels over the move rows; rows == nullptr when the index has no fast symbols
     const uint4* rows;         // 16-byte move rows, or
     const uint64_t* rows8;     // 8-byte compact rows (exactly one of rows / rows8 is set)
+    uint32_t rows8_stride;     // 8, or 16 when every row carries its two 32-bit SA samples (MS; then msamp == nullptr)
     const uint4* msamp;        // MS only
     uint32_t mv_end_k[4], mv_end_off[4];
     uint64_t mv_end_sl[4];

@@ -26,6 +26,7 @@ class FlatImage:
         self.off_mrows8, self.off_cdoc, self.off_mdoc = rest[19], rest[20], rest[21]
         self.num_docs, self.doc_init, self.doc_absent_ms = rest[22], rest[23], rest[24]
         self.mv_end_doc = rest[25:29]
+        self.mrows8_stride = rest[29]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -36,10 +37,15 @@ class FlatImage:
         self.crec = np.frombuffer(b, dtype=np.uint32, count=4 * (self.num_crec + 1), offset=self.off_crec).reshape(-1, 4)
         if self.num_fast:
             if self.off_mrows8:
-                self.rows8 = np.frombuffer(b, dtype=np.uint64, count=self.R + 64, offset=self.off_mrows8)
+                st = self.mrows8_stride // 8
+                raw = np.frombuffer(b, dtype=np.uint64, count=(self.R + 64) * st, offset=self.off_mrows8).reshape(-1, st)
+                self.rows8 = raw[:, 0]
+                if st == 2:  # inline 32-bit samples: {ss, sl} per row, presented like msamp
+                    assert self.off_msamp == 0
+                    self.msamp = np.stack([raw[:, 1] & 0xFFFFFFFF, raw[:, 1] >> 32], axis=1)
             else:
                 self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
-            if self.mode == 1:
+            if self.mode == 1 and self.off_msamp:
                 self.msamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.R + 16), offset=self.off_msamp).reshape(-1, 2)
         if self.num_docs:
             self.cdoc = np.frombuffer(b, dtype=np.uint32, count=2 * (self.num_crec + 1), offset=self.off_cdoc).reshape(-1, 2)

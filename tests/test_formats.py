@@ -187,3 +187,21 @@ def test_document_array_tables_vs_oracle(small_index, row_width):
             sp.Index.open(ref, sp.MODE_PML, use_doc=True)
     finally:
         os.rename(ref + ".doc.bak", ref + ".doc")
+
+
+def test_ms_sample_layouts(small_index, monkeypatch):
+    """MS over compact rows: the SA samples either ride inside 16-byte row slots (text positions < 2^32, the
+    default) or live in the separate per-row table (SPUMONI_B200_MSAMP=wide, what n >= 2^32 would use)."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    mo = oracle.OracleIndex(small_index["ref"], "ms")
+    monkeypatch.setenv("SPUMONI_B200_ROWS", "8")
+    imgs = {}
+    for layout in ("inline", "wide"):
+        monkeypatch.setenv("SPUMONI_B200_MSAMP", layout)
+        imgs[layout] = FlatImage(sp.Index.open(small_index["ref"], sp.MODE_MS).flat())
+    assert imgs["inline"].mrows8_stride == 16 and imgs["inline"].off_msamp == 0
+    assert imgs["wide"].mrows8_stride == 8 and imgs["wide"].off_msamp != 0
+    for i in range(40):
+        r = bytes(buf[int(off[i]):int(off[i + 1])])
+        want = mo.matching_statistics(r)[1].tolist()
+        assert imgs["inline"].walk_rows(r)[1] == want and imgs["wide"].walk_rows(r)[1] == want

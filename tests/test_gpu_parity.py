@@ -369,3 +369,14 @@ def test_document_numbers(small_index, mode, row_width):
 def tmp_path_for(small_index):
     import pathlib
     return pathlib.Path(small_index["dir"])
+
+
+def test_ms_sample_layouts_on_gpu(small_index, monkeypatch):
+    """Both homes of the per-row SA samples (inline 32-bit in 16-byte row slots / separate table) give the oracle's pointers."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    Lo, Po = oracle_batch(small_index["ref"], "ms", buf, off)
+    monkeypatch.setenv("SPUMONI_B200_ROWS", "8")
+    for layout in ("inline", "wide"):
+        monkeypatch.setenv("SPUMONI_B200_MSAMP", layout)
+        L, P, _ = sp.ms_t(small_index["ref"]).query_host(buf, off)
+        assert np.array_equal(P, Po) and np.array_equal(L.astype(np.uint64), Lo), layout
