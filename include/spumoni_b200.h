@@ -166,6 +166,17 @@ uint32_t spb_index_num_docs(const spb_index* idx);
 /* ---- classification helpers ---------------------------------------------------------- */
 /* EmpNullDatabase::load emp_null_database.cpp:104-110 */
 int spb_nulldb_load(const char* path, spb_nulldb* out);
+/* Null-database generation (the last stage of `spumoni build`, run through the GPU path):
+ * generate_null_pml_statistics / generate_null_ms_statistics compute_ms_pml.cpp:1410-1486 -- every null read is
+ * upper-cased and reversed, queried, and its lengths appended to null_stats (offsets[n_reads] values, caller-
+ * allocated) -- followed by the EmpNullDatabase constructor emp_null_database.cpp:42-79 (num_values, mean_null_stat,
+ * percentile_value = largest value occurring >= 5 times).  ks_stat_threshold is set to 0: the reference derives it
+ * from rand()-sampled KS tests (compute_ms_pml.cpp:1549-1663) and never reads it in `run`. */
+int spb_nulldb_generate_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                             uint32_t* null_stats, spb_nulldb* summary);
+/* EmpNullDatabase::serialize emp_null_database.cpp:82-102 (int_vector width max(ceil(log2(max)), 1), values
+ * truncated to that width like sdsl does) */
+int spb_nulldb_save(const char* path, const spb_nulldb* summary, const uint32_t* null_stats);
 /* max_value_thr derivation compute_ms_pml.cpp:871-875 (PML) / :1061-1063 (MS) */
 uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dna_letters, int use_promotions);
 

@@ -40,6 +40,7 @@ def lib() -> ctypes.CDLL:
         L.orc_query_batch_doc.restype = ctypes.c_double
         L.orc_query_batch_doc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.orc_nulldb_generate.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_run.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.orc_nulldb_percentile.restype = ctypes.c_double
@@ -95,6 +96,15 @@ class OracleIndex:
                                     P.ctypes.data if P is not None else None, threads)
         return sec, L, P
 
+
+    def nulldb_generate(self, reads: np.ndarray, offsets: np.ndarray):
+        """EmpNullDatabase(ref, null_reads): returns (null_stats, mean_null_stat, percentile_value)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        stats = np.zeros(int(offsets[-1]), dtype=np.uint64)
+        summary = np.zeros(2, dtype=np.float64)
+        lib().orc_nulldb_generate(self._h, reads.ctypes.data, offsets.ctypes.data, len(offsets) - 1, stats.ctypes.data, summary.ctypes.data)
+        return stats, float(summary[0]), float(summary[1])
 
     def query_batch_doc(self, reads: np.ndarray, offsets: np.ndarray, threads: int = 1):
         """Document-number variant (index opened with use_doc). Returns (lengths, pointers or None, doc_nums)."""

@@ -25,6 +25,7 @@
 //   BatchLoader                       src/batch_loader.cpp:26-131
 //   EmpNullDatabase::load             src/emp_null_database.cpp:104-110
 //   DocumentArray::load               src/doc_array.cpp:197-201
+//   generate_null_*_statistics        src/compute_ms_pml.cpp:1410-1486; EmpNullDatabase ctor src/emp_null_database.cpp:19-80
 //   _query with document numbers      src/compute_ms_pml.cpp:288-340 (PML), :625-682 (MS), ms_t :814-828
 //   my_load                           include/common.hpp:487-495
 //   ri::rle_string / sparse_sd_vector / huff_string, sdsl::sd_vector / wt_huff / int_vector:
@@ -925,6 +926,40 @@ int orc_run(const char* ref_file, const char* pattern_file, int mode, int write_
         g_err = e.what();
         return 1;
     }
+}
+// EmpNullDatabase(ref_file, null_reads, ...) for raw-DNA FASTA input: generate_null_pml_statistics /
+// generate_null_ms_statistics (src/compute_ms_pml.cpp:1410-1486) + the constructor's summary
+// (src/emp_null_database.cpp:42-79).  stats: offsets[n_reads] values; summary = {mean_null_stat, percentile_value}.
+int orc_nulldb_generate(void* hv, const uint8_t* reads, const uint64_t* off, uint64_t n_reads, uint64_t* stats, double* summary) {
+    OrcHandle* h = (OrcHandle*)hv;
+    std::vector<size_t> output_stats;
+    for (uint64_t r = 0; r < n_reads; r++) {
+        std::string curr_read((const char*)reads + off[r], (size_t)(off[r + 1] - off[r]));
+        std::transform(curr_read.begin(), curr_read.end(), curr_read.begin(), ::toupper);
+        std::reverse(curr_read.begin(), curr_read.end());  // a reversed read is a null read
+        std::vector<size_t> lengths, pointers;
+        if (h->ms) h->mst.matching_statistics(curr_read.c_str(), curr_read.length(), lengths, pointers);
+        else h->pml.matching_statistics(curr_read.c_str(), curr_read.length(), lengths);
+        output_stats.insert(output_stats.end(), lengths.begin(), lengths.end());
+    }
+    std::copy(output_stats.begin(), output_stats.end(), stats);
+    double sum_values = 0.0;
+    for (size_t i = 0; i < output_stats.size(); i++) sum_values += output_stats[i];
+    summary[0] = sum_values / output_stats.size();
+    std::sort(output_stats.begin(), output_stats.end());
+    size_t largest_val = 0, curr_val = output_stats.empty() ? 0 : output_stats[0];
+    size_t num_occs = 0;
+    for (auto x : output_stats) {
+        if (x == curr_val) num_occs++;
+        else {
+            if (num_occs >= 5) largest_val = curr_val;
+            curr_val = x;
+            num_occs = 1;
+        }
+    }
+    if (num_occs >= 5) largest_val = curr_val;
+    summary[1] = (double)largest_val;
+    return 0;
 }
 double orc_nulldb_percentile(const char* path) {
     try {

@@ -16,7 +16,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["pml_t", "ms_t", "Index", "EmpNullDatabase", "SpumoniError", "load_library", "build_library",
+__all__ = ["pml_t", "ms_t", "Index", "EmpNullDatabase", "generate_null_database", "SpumoniError", "load_library", "build_library",
            "max_value_threshold", "kernel_launches", "device_count", "BinStats", "QueryOpts", "LIB_PATH", "CLI_PATH"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -93,6 +93,8 @@ def load_library() -> ctypes.CDLL:
     L.spb_pml_query_device.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(QueryOpts), vp]
     L.spb_ms_query_device.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts), vp]
     L.spb_nulldb_load.argtypes = [cp, ctypes.POINTER(_NullDb)]
+    L.spb_nulldb_generate_host.argtypes = [vp, vp, vp, u64, vp, ctypes.POINTER(_NullDb)]
+    L.spb_nulldb_save.argtypes = [cp, ctypes.POINTER(_NullDb), vp]
     L.spb_max_value_threshold.argtypes = [ctypes.c_double, i32, i32, i32]
     L.spb_max_value_threshold.restype = u64
     L.spb_host_alloc.argtypes = [ctypes.POINTER(vp), ctypes.c_size_t]
@@ -144,6 +146,25 @@ class EmpNullDatabase:
         self.num_values, self.ks_stat_threshold = db.num_values, db.ks_stat_threshold
         self.mean_null_stat, self.percentile_value = db.mean_null_stat, db.percentile_value
         return self
+
+
+def generate_null_database(index: "Index", reads: np.ndarray, offsets: np.ndarray, out_path: Optional[str] = None,
+                           ks_stat_threshold: float = 0.0):
+    """EmpNullDatabase(ref, null_reads, ...) through the GPU path (emp_null_database.cpp:19-80 with
+    compute_ms_pml.cpp:1410-1486): returns (EmpNullDatabase, null_stats); writes the .pmlnulldb/.msnulldb file if asked."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    stats = np.zeros(int(offsets[-1]), dtype=np.uint32)
+    db = _NullDb()
+    _check(load_library().spb_nulldb_generate_host(index._h, reads.ctypes.data, offsets.ctypes.data, len(offsets) - 1,
+                                                   stats.ctypes.data, ctypes.byref(db)))
+    db.ks_stat_threshold = ks_stat_threshold
+    if out_path:
+        _check(load_library().spb_nulldb_save(out_path.encode(), ctypes.byref(db), stats.ctypes.data))
+    out = EmpNullDatabase()
+    out.num_values, out.ks_stat_threshold = db.num_values, db.ks_stat_threshold
+    out.mean_null_stat, out.percentile_value = db.mean_null_stat, db.percentile_value
+    return out, stats
 
 
 def pack_reads(reads) -> Tuple[np.ndarray, np.ndarray]:

@@ -465,6 +465,50 @@ int spb_nulldb_load(const char* path, spb_nulldb* out) {
     });
 }
 
+int spb_nulldb_generate_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                             uint32_t* null_stats, spb_nulldb* summary) {
+    if (!idx || !offsets || !summary || (n_reads && (!reads || !null_stats))) return fail(SPB_ERR_ARG, "spb_nulldb_generate_host: bad argument");
+    return guarded([&]() -> int {
+        // null read = the read reversed (compute_ms_pml.cpp:1425-1426 / :1463-1464); ::toupper commutes with the reversal
+        const uint64_t total = offsets[n_reads];
+        std::vector<uint8_t> rev((size_t)total);
+        for (uint64_t r = 0; r < n_reads; r++) {
+            const uint64_t a = offsets[r], b = offsets[r + 1];
+            if (b < a || b > total) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
+            for (uint64_t i = a; i < b; i++) rev[(size_t)i] = reads[a + (b - 1 - i)];
+        }
+        spb_query_opts o;
+        std::memset(&o, 0, sizeof(o));
+        o.flags = SPB_QUERY_TOUPPER;
+        int rc;
+        if (idx->mode == SPB_MODE_MS) {
+            std::vector<uint64_t> ptrs((size_t)total);
+            rc = query_host(idx, true, rev.data(), offsets, n_reads, null_stats, ptrs.data(), nullptr, nullptr, &o);
+        } else
+            rc = query_host(idx, false, rev.data(), offsets, n_reads, null_stats, nullptr, nullptr, nullptr, &o);
+        if (rc) return rc;
+        const spb::NullDb db = spb::summarize_null_stats(null_stats, total);
+        summary->num_values = db.num_values;
+        summary->ks_stat_threshold = 0.0;
+        summary->mean_null_stat = db.mean_null_stat;
+        summary->percentile_value = db.percentile_value;
+        return SPB_OK;
+    });
+}
+
+int spb_nulldb_save(const char* path, const spb_nulldb* summary, const uint32_t* null_stats) {
+    if (!path || !summary || (summary->num_values && !null_stats)) return fail(SPB_ERR_ARG, "spb_nulldb_save: bad argument");
+    return guarded([&]() -> int {
+        spb::NullDb db;
+        db.num_values = summary->num_values;
+        db.ks_stat_threshold = summary->ks_stat_threshold;
+        db.mean_null_stat = summary->mean_null_stat;
+        db.percentile_value = summary->percentile_value;
+        spb::save_null_db(path, db, null_stats);
+        return SPB_OK;
+    });
+}
+
 uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dna_letters, int use_promotions) {
     uint64_t thr = (uint64_t)(percentile_value > 3.0 ? percentile_value : 3.0);
     if (use_dna_letters) thr++;

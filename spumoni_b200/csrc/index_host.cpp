@@ -350,6 +350,58 @@ NullDb load_null_db(const std::string& path) {
     return db;
 }
 
+NullDb summarize_null_stats(const uint32_t* stats, uint64_t n) {
+    NullDb db;
+    db.num_values = n;
+    double sum = 0.0;
+    for (uint64_t i = 0; i < n; i++) sum += stats[i];
+    db.mean_null_stat = sum / (double)n;  // 0/0 for an empty input, like the reference
+    std::vector<uint32_t> sorted(stats, stats + n);
+    std::sort(sorted.begin(), sorted.end());
+    uint64_t largest = 0, cur = n ? sorted[0] : 0, occ = 0;
+    for (uint32_t x : sorted) {
+        if (x == cur) occ++;
+        else {
+            if (occ >= 5) largest = cur;
+            cur = x;
+            occ = 1;
+        }
+    }
+    if (occ >= 5) largest = cur;
+    db.percentile_value = (double)largest;
+    return db;
+}
+
+void save_null_db(const std::string& path, const NullDb& db, const uint32_t* stats) {
+    uint32_t mx = 0;
+    for (uint64_t i = 0; i < db.num_values; i++) mx = std::max(mx, stats[i]);
+    // max(ceil(log2(max)), 1): a max that is an exact power of two does not fit its own width (reference quirk)
+    uint32_t width = 1;
+    if (mx > 1) {
+        uint32_t c = 0;
+        while ((1ull << c) < mx) c++;
+        width = c < 1 ? 1 : c;
+    }
+    const uint64_t bits = db.num_values * width, mask = width >= 64 ? ~0ull : ((1ull << width) - 1);
+    std::vector<uint64_t> words((size_t)((bits + 63) / 64), 0);
+    for (uint64_t i = 0; i < db.num_values; i++) {
+        const uint64_t v = stats[i] & mask, b = i * width;
+        words[(size_t)(b >> 6)] |= v << (b & 63);
+        if ((b & 63) + width > 64) words[(size_t)(b >> 6) + 1] |= v >> (64 - (b & 63));
+    }
+    std::ofstream o(path, std::ios::binary);
+    if (!o) throw IoError("cannot write " + path);
+    o.write((const char*)&db.num_values, 8);
+    o.write((const char*)&db.ks_stat_threshold, 8);
+    o.write((const char*)&db.mean_null_stat, 8);
+    o.write((const char*)&db.percentile_value, 8);
+    o.write((const char*)&bits, 8);
+    const uint8_t w8 = (uint8_t)width;
+    o.write((const char*)&w8, 1);
+    o.write((const char*)words.data(), (std::streamsize)(words.size() * 8));
+    if (!o) throw IoError("write failed: " + path);
+}
+
 void load_doc_array(const std::string& path, DecodedIndex& d) {
     std::vector<uint8_t> buf = slurp(path);
     ByteReader in(buf.data(), buf.size());

@@ -31,6 +31,9 @@ struct NullDb {
 DecodedIndex parse_index_file(const std::string& path, bool ms);
 std::string load_reference_text(const std::string& fasta_path);
 NullDb load_null_db(const std::string& path);
+// EmpNullDatabase constructor tail (/root/reference/src/emp_null_database.cpp:42-79) and serialize (:82-102)
+NullDb summarize_null_stats(const uint32_t* stats, uint64_t n);
+void save_null_db(const std::string& path, const NullDb& db, const uint32_t* stats);
 // DocumentArray::load (/root/reference/src/doc_array.cpp:197-201) into d.doc_start / d.doc_end
 void load_doc_array(const std::string& path, DecodedIndex& d);
 std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std::string& text);

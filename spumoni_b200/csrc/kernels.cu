@@ -1,14 +1,18 @@
 // Hand-written sm_100a kernels for SPUMONI's per-read MS/PML backward search.
 //
-//   spb_walk_kernel<G, MS>   K1/K2 (+K3, K4 fused)
-//       PML : pml_pointers::_query            /root/reference/src/compute_ms_pml.cpp:237-286
-//       MS  : ms_pointers::_query             /root/reference/src/compute_ms_pml.cpp:570-623
-//             ms_t::matching_statistics       /root/reference/src/compute_ms_pml.cpp:795-812
-//       bin-max classifier (epilogue)         /root/reference/src/compute_ms_pml.cpp:969-995
+//   spb_move_kernel<MS, STATS, OW, LD, ROW8, DOC, MSI>     one thread per read over the move rows (default path)
+//       PML : pml_pointers::_query            /root/reference/src/compute_ms_pml.cpp:237-286 (+ doc numbers :288-340)
+//       MS  : ms_pointers::_query             /root/reference/src/compute_ms_pml.cpp:570-623 (+ doc numbers :625-682)
+//       bin-max classifier (PML, fused)       /root/reference/src/compute_ms_pml.cpp:969-995
+//   spb_ms_lengths_kernel<STATS, OW>                       MS pointers -> lengths, one thread per read
+//       ms_t::matching_statistics             /root/reference/src/compute_ms_pml.cpp:795-812, classifier :1150-1176
+//   spb_walk_kernel<G, MS>                                 G lanes per read over the generic run records
+//       (indexes without fast symbols; every symbol and size; both MS phases in one launch)
 //
-// Work shape: integer pointer chasing, HBM/L2-latency bound; no tensor cores.  A group of G lanes
-// (G = 4/8/16/32, a template parameter) walks one read right-to-left.  Every step needs the run
-// containing the new BWT position; instead of a rank/select cascade the group issues ONE
+// Work shape: integer pointer chasing, one dependent chain per read; no tensor cores, no GEMM-shaped work.
+// What bounds it on a B200 and why the tables look the way they do: DESIGN.md section 4.3.
+// The generic kernel comes first: a group of G lanes (G = 4/8/16/32) walks one read right-to-left.  Every step
+// needs the run containing the new BWT position; instead of a rank/select cascade the group issues ONE
 // coalesced load of G consecutive 16-byte run records starting at a precomputed destination run
 // and resolves the predecessor with a ballot + popc; the winning lane's record is broadcast with
 // shuffles and becomes the state of the next step (see flat_index.h).  Reads are staged through

@@ -205,3 +205,19 @@ def test_ms_sample_layouts(small_index, monkeypatch):
         r = bytes(buf[int(off[i]):int(off[i + 1])])
         want = mo.matching_statistics(r)[1].tolist()
         assert imgs["inline"].walk_rows(r)[1] == want and imgs["wide"].walk_rows(r)[1] == want
+
+
+def test_nulldb_save_matches_fixture_writer(tmp_path):
+    """spb_nulldb_save (EmpNullDatabase::serialize, emp_null_database.cpp:82-102) writes the bytes the fixture writer does,
+    including the width quirk (a maximum that is an exact power of two is truncated)."""
+    import ctypes
+    lib = sp.load_library()
+    for vals in ([3, 3, 3, 3, 3, 9, 9, 9, 9, 9, 9, 11, 11, 2, 0, 16], [0, 0, 0], [1, 0, 1, 1, 1, 1], [5] * 7 + [700]):
+        a = np.array(vals, dtype=np.uint64)
+        a.tofile(str(tmp_path / "s.bin"))
+        subprocess.check_call([MKINDEX, "nulldb", "--stats", str(tmp_path / "s.bin"), "--out", str(tmp_path / "f.db"), "--ks-thr", "0.5"])
+        ref = sp.EmpNullDatabase().load(str(tmp_path / "f.db"))
+        db = sp._NullDb(len(vals), 0.5, ref.mean_null_stat, ref.percentile_value)
+        s32 = a.astype(np.uint32)
+        assert lib.spb_nulldb_save(str(tmp_path / "g.db").encode(), ctypes.byref(db), s32.ctypes.data) == 0
+        assert open(tmp_path / "g.db", "rb").read() == open(tmp_path / "f.db", "rb").read(), vals

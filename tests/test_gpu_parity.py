@@ -380,3 +380,56 @@ def test_ms_sample_layouts_on_gpu(small_index, monkeypatch):
         monkeypatch.setenv("SPUMONI_B200_MSAMP", layout)
         L, P, _ = sp.ms_t(small_index["ref"]).query_host(buf, off)
         assert np.array_equal(P, Po) and np.array_equal(L.astype(np.uint64), Lo), layout
+
+
+def test_long_and_mixed_length_reads(small_index, row_width):
+    """BASELINE config 5's shape in miniature: 150 bp .. 50 kb reads in one batch (a read is one dependent chain; the
+    work counter balances the ragged lengths), uint16 lengths where they fit, classifier stats on every read."""
+    rng = random.Random(11)
+    text = "".join(l for l in open(small_index["ref"]).read().split("\n") if not l.startswith(">"))
+    reads = []
+    for ln in (150, 500, 1000, 5000, 10000, 50000, 150, 10000, 33, 65535, 65536):
+        parts, tot = [], 0
+        while tot < ln:
+            a = rng.randint(0, len(text) - 2000)
+            seg = bytearray(text[a:a + rng.randint(200, 2000)].encode())
+            for i in range(len(seg)):
+                if rng.random() < 0.03:
+                    seg[i] = rng.choice(b"ACGT")
+            parts.append(bytes(seg))
+            tot += len(seg)
+        reads.append(b"".join(parts)[:ln])
+    buf, off = sp.pack_reads(reads)
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    Lmo, Pmo = oracle_batch(small_index["ref"], "ms", buf, off)
+    pml, ms = sp.pml_t(small_index["ref"]), sp.ms_t(small_index["ref"])
+    L, _, S = pml.query_host(buf, off, bin_width=150, max_value_thr=9)
+    assert np.array_equal(L.astype(np.uint64), Lo)
+    for r in range(len(reads)):
+        found, summ, above, below, nb = naive.classify_bins(Lo[int(off[r]):int(off[r + 1])].tolist(), 150, 9)
+        assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)
+    Lm, Pm, _ = ms.query_host(buf, off)
+    assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
+    L16, _, _ = pml.query_host(buf, off, length_bytes=2)  # a PML never exceeds the read length; here it stays far below 65536
+    assert np.array_equal(L16.astype(np.uint64), Lo)
+
+
+@pytest.mark.parametrize("mode", ["pml", "ms"])
+def test_null_database_generation(small_index, tmp_path, mode):
+    """The last stage of `spumoni build` through the GPU path: reversed null reads -> null statistics -> EmpNullDatabase
+    (compute_ms_pml.cpp:1410-1486, emp_null_database.cpp:19-102); statistics, summary and the serialised file match the
+    oracle / the fixture writer, and the file loads back through EmpNullDatabase::load."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    lower = np.where((buf >= 65) & (buf <= 90), buf + 32, buf).astype(np.uint8)  # null reads are upper-cased first
+    o = oracle.OracleIndex(small_index["ref"], mode)
+    so, mean_o, perc_o = o.nulldb_generate(lower, off)
+    idx = (sp.pml_t if mode == "pml" else sp.ms_t)(small_index["ref"])
+    out = str(tmp_path / ("x.pmlnulldb" if mode == "pml" else "x.msnulldb"))
+    db, stats = sp.generate_null_database(idx, lower, off, out_path=out, ks_stat_threshold=0.25)
+    assert np.array_equal(stats.astype(np.uint64), so)
+    assert db.num_values == len(buf) and db.mean_null_stat == mean_o and db.percentile_value == perc_o
+    so.tofile(str(tmp_path / "s.bin"))
+    subprocess.check_call([MKINDEX, "nulldb", "--stats", str(tmp_path / "s.bin"), "--out", out + ".fixture", "--ks-thr", "0.25"])
+    assert open(out, "rb").read() == open(out + ".fixture", "rb").read()
+    back = sp.EmpNullDatabase().load(out)
+    assert (back.num_values, back.percentile_value, back.mean_null_stat, back.ks_stat_threshold) == (len(buf), perc_o, mean_o, 0.25)
