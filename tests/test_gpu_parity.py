@@ -433,3 +433,27 @@ def test_null_database_generation(small_index, tmp_path, mode):
     assert open(out, "rb").read() == open(out + ".fixture", "rb").read()
     back = sp.EmpNullDatabase().load(out)
     assert (back.num_values, back.percentile_value, back.mean_null_stat, back.ks_stat_threshold) == (len(buf), perc_o, mean_o, 0.25)
+
+
+def test_baseline_config1_plumbing(tmp_path):
+    """BASELINE.json configs[0]: PML on a 1 Mb single-FASTA index (i.i.d. ACGT, + reverse complement, n = 2 000 001),
+    10 000 synthetic 150 bp reads (half mutated substrings, half random), `spumoni run -P -n -c`: every output file is
+    byte-for-byte the reference CPU path's (oracle CLI, 1 thread, so that the output order is defined)."""
+    d = str(tmp_path)
+    from conftest import mkindex
+    mkindex("genome", "--kind", "iid", "--len", 1000000, "--seed", 1, "--out", d + "/raw.fa")
+    ref = build_index(d, fasta=d + "/raw.fa", revcomp=True)
+    n, r = sp.Index.open(ref, 0).get_bwt_stats()
+    assert n == 2000001
+    mkindex("reads", "--ref", ref, "--n", 10000, "--len", 150, "--sub", 0.01, "--neg-frac", 0.5, "--seed", 2, "--out", d + "/a.fa")
+    import shutil
+    shutil.copy(d + "/a.fa", d + "/b.fa")
+    stats = (np.arange(1, 200, dtype=np.uint64) * 7) % 11
+    stats.tofile(d + "/stats.bin")
+    subprocess.check_call([MKINDEX, "nulldb", "--stats", d + "/stats.bin", "--out", ref + ".pmlnulldb"])
+    nr, _ = oracle.run(ref, d + "/a.fa", "pml", report=True, threads=1)
+    assert nr == 10000
+    res = subprocess.run([sp.CLI_PATH, "run", "-r", ref[:-3], "-p", d + "/b.fa", "-P", "-n", "-c", "-t", "4"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    for e in (".pseudo_lengths", ".report"):
+        assert open(d + "/a.fa" + e, "rb").read() == open(d + "/b.fa" + e, "rb").read(), e
