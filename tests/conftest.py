@@ -78,3 +78,81 @@ def small_index(tmp_path_factory):
 def load_bin_reads(path):
     import numpy as np
     return np.fromfile(path, dtype=np.uint8), np.fromfile(path + ".off", dtype=np.uint64)
+
+
+def _read5(path, cols):
+    import numpy as np
+    b = np.frombuffer(open(path, "rb").read(), dtype=np.uint8).reshape(-1, 5 * cols)
+    out = []
+    for c in range(cols):
+        v = np.zeros(len(b), dtype=np.uint64)
+        for j in range(5):
+            v |= b[:, 5 * c + j].astype(np.uint64) << np.uint64(8 * j)
+        out.append(v.astype(np.int64))
+    return out
+
+
+def _write5(path, *cols):
+    import numpy as np
+    rows = np.zeros((len(cols[0]), 5 * len(cols)), dtype=np.uint8)
+    for c, col in enumerate(cols):
+        v = np.asarray(col, dtype=np.uint64)
+        for j in range(5):
+            rows[:, 5 * c + j] = ((v >> np.uint64(8 * j)) & np.uint64(0xFF)).astype(np.uint8)
+    rows.tofile(path)
+
+
+@pytest.fixture(scope="session")
+def huge_periodic_index(tmp_path_factory):
+    """A PML index whose BWT positions exceed 2^32 (n = 48 * 90 000 000 + 1 = 4 320 000 001) without suffix-sorting
+    4 G characters: for the periodic text U^k every per-run quantity of the RLBWT (run lengths, thresholds, SA samples)
+    is affine in k, so the PFP intermediates (.bwt.heads/.bwt.len/.thr_pos/.ssa/.esa) of k = 6 and k = 7 are
+    extrapolated (and checked against a real k = 8 build) and serialised with `mkindex from-parts`, the stand-in for
+    build_spumoni_main (compute_ms_pml.cpp:1384-1408).  Exercises the 40-bit fields of every table."""
+    import random
+    import numpy as np
+    d = str(tmp_path_factory.mktemp("huge"))
+    rng = random.Random(3)
+    unit = "".join(rng.choice("ACGT") for _ in range(48))
+
+    def parts(k):
+        dk = os.path.join(d, f"k{k}")
+        build_index(dk, text=(unit * k).encode(), keep=True)
+        ref = os.path.join(dk, "idx.fa")
+        heads = open(ref + ".bwt.heads", "rb").read()
+        (lens,), (thr,) = _read5(ref + ".bwt.len", 1), _read5(ref + ".thr_pos", 1)
+        _, ssa = _read5(ref + ".ssa", 2)
+        _, esa = _read5(ref + ".esa", 2)
+        return heads, lens, thr, ssa, esa
+
+    p6, p7, p8 = parts(6), parts(7), parts(8)
+    assert p6[0] == p7[0] == p8[0]
+    K = 90_000_000
+    big = [p6[0]]
+    for i in range(1, 5):
+        slope = p7[i] - p6[i]
+        assert np.array_equal(p6[i] + 2 * slope, p8[i]), "the parts are not affine in k"
+        big.append(p6[i] + (K - 6) * slope)
+    ref = os.path.join(d, "idx.fa")
+    open(ref, "w").write(">periodic\n")  # placeholder: PML never reads the text
+    open(ref + ".bwt.heads", "wb").write(big[0])
+    _write5(ref + ".bwt.len", big[1])
+    _write5(ref + ".thr_pos", big[2])
+    starts = np.concatenate([[0], np.cumsum(big[1])[:-1]])
+    _write5(ref + ".ssa", starts, big[3])
+    _write5(ref + ".esa", starts + big[1] - 1, big[4])
+    out = mkindex("from-parts", "--prefix", os.path.join(d, "idx"), "--pml")
+    n = 48 * K + 1
+    assert f'"n": {n}' in out and n > (1 << 32)
+    reads = []
+    text3 = unit * 3
+    for _ in range(120):
+        ln = rng.randint(20, 140)
+        a = rng.randint(0, len(text3) - ln)
+        r = bytearray(text3[a:a + ln].encode())
+        for i in range(len(r)):
+            if rng.random() < 0.08:
+                r[i] = rng.choice(b"ACGTN")
+        reads.append(bytes(r))
+    reads += [unit.encode() * 2, b"N" * 5, bytes(rng.choice(b"ACGT") for _ in range(300))]
+    return {"ref": ref, "n": n, "reads": reads}

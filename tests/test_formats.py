@@ -221,3 +221,22 @@ def test_nulldb_save_matches_fixture_writer(tmp_path):
         s32 = a.astype(np.uint32)
         assert lib.spb_nulldb_save(str(tmp_path / "g.db").encode(), ctypes.byref(db), s32.ctypes.data) == 0
         assert open(tmp_path / "g.db", "rb").read() == open(tmp_path / "f.db", "rb").read(), vals
+
+
+def test_positions_beyond_2_32(huge_periodic_index, row_width):
+    """n > 2^32: on-disk parse (sd_vectors over a 4.3 G universe), 40-bit fields of the run / character records,
+    saturated move rows falling back to the generic step -- the flat image walked on the CPU equals the oracle."""
+    ref, reads = huge_periodic_index["ref"], huge_periodic_index["reads"]
+    idx = sp.Index.open(ref, sp.MODE_PML)
+    assert idx.get_bwt_stats()[0] == huge_periodic_index["n"]
+    fp = FlatImage(idx.flat())
+    po = oracle.OracleIndex(ref, "pml")
+    assert po.stats()[0] == huge_periodic_index["n"]
+    slow = 0
+    for r in reads:
+        want = po.matching_statistics(r).tolist()
+        assert fp.walk(r)[0] == want
+        got, _, st = fp.walk_rows(r)
+        assert got == want
+        slow += st["slow"]
+    assert slow > 0  # run lengths of ~10^8 do not fit the row fields

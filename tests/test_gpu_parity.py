@@ -457,3 +457,16 @@ def test_baseline_config1_plumbing(tmp_path):
     assert res.returncode == 0, res.stderr
     for e in (".pseudo_lengths", ".report"):
         assert open(d + "/a.fa" + e, "rb").read() == open(d + "/b.fa" + e, "rb").read(), e
+
+
+@pytest.mark.parametrize("lanes", [1, 8, 32])
+def test_positions_beyond_2_32_on_gpu(huge_periodic_index, lanes, row_width):
+    """BASELINE configs 4-5 territory: BWT positions > 2^32 (n = 4 320 000 001), all kernels, bit-exact vs the oracle."""
+    ref, reads = huge_periodic_index["ref"], huge_periodic_index["reads"]
+    buf, off = sp.pack_reads(reads)
+    Lo, _ = oracle_batch(ref, "pml", buf, off)
+    L, _, S = sp.pml_t(ref).query_host(buf, off, lanes=lanes, bin_width=50, max_value_thr=7)
+    assert np.array_equal(L.astype(np.uint64), Lo)
+    for r in range(len(reads)):
+        found, summ, above, below, nb = naive.classify_bins(Lo[int(off[r]):int(off[r + 1])].tolist(), 50, 7)
+        assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)

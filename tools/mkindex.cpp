@@ -379,8 +379,41 @@ static int cmd_nulldb(const Args& a) {
     return 0;
 }
 
+// ---------------------------------------------------------------- from-parts
+// What build_spumoni_main / build_spumoni_ms_main do (/root/reference/src/compute_ms_pml.cpp:1384-1408): construct the
+// index objects from the PFP intermediates <prefix>.fa.{bwt.heads,bwt.len,thr_pos,ssa,esa} (5-byte integers,
+// compute_ms_pml.cpp:44-60, :404-439; thresholds_ds.hpp:393-426) and serialise them.  Lets a test hand-craft run-length
+// data (e.g. an index whose positions exceed 2^32) without suffix-sorting a text of that size.
+static uint64_t get5(std::ifstream& f) { uint64_t v = 0; f.read((char*)&v, 5); return v; }
+static int cmd_from_parts(const Args& a) {
+    std::string prefix = get(a, "prefix");
+    if (prefix.empty()) die("from-parts: --prefix required");
+    const std::string ref = prefix + ".fa";
+    bool want_ms = has(a, "ms"), want_pml = has(a, "pml") || !want_ms;
+    std::ifstream h(ref + ".bwt.heads", std::ios::binary), l(ref + ".bwt.len", std::ios::binary), t(ref + ".thr_pos", std::ios::binary),
+        s(ref + ".ssa", std::ios::binary), e(ref + ".esa", std::ios::binary);
+    if (!h || !l || !t) die("from-parts: missing " + ref + ".bwt.heads/.bwt.len/.thr_pos");
+    sdslw::RlbwtParts P;
+    for (int c; (c = h.get()) != EOF;) P.heads.push_back((uint8_t)c);
+    for (size_t k = 0; k < P.heads.size(); k++) {
+        P.lens.push_back(get5(l));
+        P.thr.push_back(get5(t));
+        P.n += P.lens.back();
+        if (s && e) { get5(s); P.ssa.push_back(get5(s)); get5(e); P.esa.push_back(get5(e)); }
+    }
+    if (!l || !t) die("from-parts: .bwt.len / .thr_pos shorter than .bwt.heads");
+    if (want_pml) { std::ofstream o(ref + ".thrbv.spumoni", std::ios::binary); sdslw::write_pml_index(o, P); }
+    if (want_ms) {
+        if (P.ssa.size() != P.heads.size()) die("from-parts: --ms needs .ssa/.esa");
+        std::ofstream o(ref + ".thrbv.ms", std::ios::binary);
+        sdslw::write_ms_index(o, P);
+    }
+    std::printf("{\"n\": %llu, \"r\": %llu}\n", (unsigned long long)P.n, (unsigned long long)P.heads.size());
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) die("usage: spumoni_mkindex genome|build|reads|nulldb [--key value ...]");
+    if (argc < 2) die("usage: spumoni_mkindex genome|build|from-parts|reads|nulldb [--key value ...]");
     std::string cmd = argv[1];
     Args a = parse_args(argc, argv, 2);
 #ifdef _OPENMP
@@ -388,6 +421,7 @@ int main(int argc, char** argv) {
 #endif
     if (cmd == "genome") return cmd_genome(a);
     if (cmd == "build") return cmd_build(a);
+    if (cmd == "from-parts") return cmd_from_parts(a);
     if (cmd == "reads") return cmd_reads(a);
     if (cmd == "nulldb") return cmd_nulldb(a);
     die("unknown command " + cmd);
