@@ -145,6 +145,16 @@ int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* 
                         void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
                         const spb_query_opts* opts, void* cuda_stream);
 
+/* PML query + on-device decimal formatting (K5): instead of the lengths, the call returns the bytes the reference
+ * writes to <reads>.pseudo_lengths for these reads (compute_ms_pml.cpp:1007-1010): per read '>' id '\n', then every
+ * length followed by one space, then '\n'.  ids: the read ids back to back (id i = ids[id_offsets[i] .. id_offsets[i+1]),
+ * exactly as BatchLoader extracts them, batch_loader.cpp:104-106).  text: caller buffer of text_capacity bytes;
+ * *text_bytes receives the bytes written.  SPB_ERR_LIMIT if the buffer is too small (*text_bytes = bytes needed so
+ * far).  stats/opts as in spb_pml_query_host (opts->length_bytes is ignored). */
+int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                            const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
+                            uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts);
+
 /* Document-number variants: pml_t::matching_statistics(read, len, lengths, doc_nums) compute_ms_pml.cpp:734-737 ->
  * pml_pointers::_query :288-340, and ms_t::matching_statistics(read, len, lengths, pointers, doc_nums) :814-828 ->
  * ms_pointers::_query :625-682.  doc_nums[offsets[i] + j] is the document of position j of read i.  The index must

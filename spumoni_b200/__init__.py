@@ -92,6 +92,7 @@ def load_library() -> ctypes.CDLL:
     L.spb_ms_query_host.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts)]
     L.spb_pml_query_device.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(QueryOpts), vp]
     L.spb_ms_query_device.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts), vp]
+    L.spb_pml_query_host_text.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, ctypes.POINTER(u64), vp, ctypes.POINTER(QueryOpts)]
     L.spb_nulldb_load.argtypes = [cp, ctypes.POINTER(_NullDb)]
     L.spb_nulldb_generate_host.argtypes = [vp, vp, vp, u64, vp, ctypes.POINTER(_NullDb)]
     L.spb_nulldb_save.argtypes = [cp, ctypes.POINTER(_NullDb), vp]
@@ -263,6 +264,25 @@ class Index:
         o.length_bytes = length_bytes
         o.saturated = saturated
         return o
+
+    def query_host_text(self, reads: np.ndarray, offsets: np.ndarray, ids, bin_width=0, max_value_thr=0, toupper=False,
+                        capacity: Optional[int] = None):
+        """PML query + on-device decimal formatting: returns (the bytes of the .pseudo_lengths file for these reads, stats)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = len(offsets) - 1
+        idbuf, idoff = pack_reads([bytes(i) for i in ids])
+        cap = capacity if capacity is not None else int(offsets[-1]) * 11 + len(idbuf) + 3 * n + 64
+        text = np.zeros(cap, dtype=np.uint8)
+        S = np.zeros(n, dtype=BinStats) if bin_width else None
+        o = self._opts(bin_width, max_value_thr, 0, toupper, 4, None)
+        got = ctypes.c_uint64(0)
+        rc = load_library().spb_pml_query_host_text(self._h, reads.ctypes.data, offsets.ctypes.data, n, idbuf.ctypes.data,
+                                                    idoff.ctypes.data, text.ctypes.data, cap, ctypes.byref(got),
+                                                    S.ctypes.data if S is not None else None, ctypes.byref(o))
+        self.last_text_bytes = int(got.value)
+        _check(rc)
+        return text[: got.value].tobytes(), S
 
     def query_host_doc(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0, toupper=False):
         """Document-number variant (index opened with use_doc=True). Returns (lengths, pointers or None, stats, doc_nums)."""

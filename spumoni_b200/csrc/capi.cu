@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <deque>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -56,6 +57,11 @@ struct Slot {
     bool sat_pending = false;
     uint64_t cap_bases = 0, cap_reads = 0;
     bool cap_ms = false, cap_doc = false;
+    // on-device text formatting (spb_pml_query_host_text)
+    uint8_t* d_ids = nullptr;
+    uint64_t *d_id_offsets = nullptr, *d_starts = nullptr, *h_id_offsets = nullptr, *h_total = nullptr;
+    char* d_text = nullptr;
+    uint64_t cap_ids = 0, cap_text = 0, cap_text_reads = 0;
 };
 
 }  // namespace
@@ -108,6 +114,14 @@ void free_slot(Slot& s) {
     if (s.h_offsets) cudaFreeHost(s.h_offsets);
     if (s.d_sat) cudaFree(s.d_sat);
     if (s.h_sat) cudaFreeHost(s.h_sat);
+    if (s.d_ids) cudaFree(s.d_ids);
+    if (s.d_id_offsets) cudaFree(s.d_id_offsets);
+    if (s.d_starts) cudaFree(s.d_starts);
+    if (s.d_text) cudaFree(s.d_text);
+    if (s.h_id_offsets) cudaFreeHost(s.h_id_offsets);
+    if (s.h_total) cudaFreeHost(s.h_total);
+    s.d_ids = nullptr; s.d_id_offsets = nullptr; s.d_starts = nullptr; s.d_text = nullptr; s.h_id_offsets = nullptr; s.h_total = nullptr;
+    s.cap_ids = s.cap_text = s.cap_text_reads = 0;
     s.d_sat = nullptr; s.h_sat = nullptr; s.sat_pending = false;
     s.d_reads = nullptr; s.d_offsets = nullptr; s.d_lengths = nullptr; s.d_pointers = nullptr; s.d_docs = nullptr; s.d_stats = nullptr;
     s.h_offsets = nullptr;
@@ -263,6 +277,128 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
     return SPB_OK;
 }
 
+// buffers of the text path; grown on demand (the slot's stream is idle when this is called)
+int ensure_text_slot(Slot& s, uint64_t reads, uint64_t id_bytes, uint64_t text_bytes) {
+    if (reads > s.cap_text_reads) {
+        if (s.d_id_offsets) cudaFree(s.d_id_offsets);
+        if (s.d_starts) cudaFree(s.d_starts);
+        if (s.h_id_offsets) cudaFreeHost(s.h_id_offsets);
+        s.d_id_offsets = s.d_starts = s.h_id_offsets = nullptr;
+        const uint64_t nr = reads + reads / 4;
+        SPB_CUDA(cudaMalloc(&s.d_id_offsets, (nr + 1) * sizeof(uint64_t)));
+        SPB_CUDA(cudaMalloc(&s.d_starts, (nr + 1) * sizeof(uint64_t)));
+        SPB_CUDA(cudaMallocHost(&s.h_id_offsets, (nr + 1) * sizeof(uint64_t)));
+        s.cap_text_reads = nr;
+    }
+    if (!s.h_total) SPB_CUDA(cudaMallocHost(&s.h_total, sizeof(uint64_t)));
+    if (id_bytes > s.cap_ids) {
+        if (s.d_ids) cudaFree(s.d_ids);
+        s.d_ids = nullptr;
+        SPB_CUDA(cudaMalloc(&s.d_ids, id_bytes + id_bytes / 4 + 64));
+        s.cap_ids = id_bytes + id_bytes / 4;
+    }
+    if (text_bytes > s.cap_text) {
+        if (s.d_text) cudaFree(s.d_text);
+        s.d_text = nullptr;
+        SPB_CUDA(cudaMalloc(&s.d_text, text_bytes + text_bytes / 4 + 64));
+        s.cap_text = text_bytes + text_bytes / 4;
+    }
+    return SPB_OK;
+}
+
+struct TextChunk { int slot; uint64_t nr, id_bytes; uint32_t elem_bytes; };
+
+int query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads, const uint8_t* ids,
+                    const uint64_t* id_offsets, char* text, uint64_t text_capacity, uint64_t* text_bytes, spb_bin_stats* stats,
+                    const spb_query_opts* opts) {
+    if (!idx || !text_bytes) return fail(SPB_ERR_ARG, "null index / text_bytes");
+    *text_bytes = 0;
+    if (n_reads == 0) return SPB_OK;
+    if (!reads || !offsets || !ids || !id_offsets || !text) return fail(SPB_ERR_ARG, "null host buffer");
+    int rc = ensure_device_state(idx);
+    if (rc) return rc;
+    const bool want_stats = stats && opts && opts->bin_width;
+    const int kSlots = idx->n_slots;
+    const uint64_t kChunkBases = idx->chunk_bases;
+    spb_query_opts qo;
+    std::memset(&qo, 0, sizeof(qo));
+    if (opts) qo = *opts;
+    qo.saturated = nullptr;
+    uint64_t text_off = 0;
+    std::deque<TextChunk> inflight;
+
+    // stage 2 of the oldest chunk: its sizes are known -> format on the device, copy the text to its place
+    auto finish = [&]() -> int {
+        const TextChunk c = inflight.front();
+        inflight.pop_front();
+        Slot& s = idx->slots[c.slot];
+        SPB_CUDA(cudaStreamSynchronize(s.stream));
+        const uint64_t total = *s.h_total;
+        if (text_off + total > text_capacity) { *text_bytes = text_off + total; return fail(SPB_ERR_LIMIT, "text buffer too small"); }
+        int r2 = ensure_text_slot(s, c.nr, c.id_bytes, total);
+        if (r2) return r2;
+        spb::TextParams tp;
+        tp.values = s.d_lengths; tp.offsets = s.d_offsets; tp.ids = s.d_ids; tp.id_offsets = s.d_id_offsets;
+        tp.n_reads = c.nr; tp.starts = s.d_starts; tp.text = s.d_text; tp.elem_bytes = c.elem_bytes;
+        SPB_CUDA(spb::launch_text_format(tp, idx->num_sms, s.stream));
+        g_launches.fetch_add(1);
+        if (total) SPB_CUDA(cudaMemcpyAsync(text + text_off, s.d_text, total, cudaMemcpyDeviceToHost, s.stream));
+        text_off += total;
+        return SPB_OK;
+    };
+
+    uint64_t r0 = 0;
+    int chunk = 0;
+    while (r0 < n_reads) {
+        uint64_t r1 = r0 + 1;
+        while (r1 < n_reads && offsets[r1 + 1] - offsets[r0] <= kChunkBases) r1++;
+        const uint64_t b0 = offsets[r0], nb = offsets[r1] - b0, nr = r1 - r0;
+        if (offsets[r1] < b0) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
+        const int slot = chunk % kSlots;
+        while (!inflight.empty() && (int)inflight.size() >= (kSlots + 1) / 2) { rc = finish(); if (rc) return rc; }  // also frees `slot`'s previous use
+        Slot& s = idx->slots[slot];
+        rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), false, false);
+        if (rc) return rc;
+        SPB_CUDA(cudaStreamSynchronize(s.stream));
+        const uint64_t i0 = id_offsets[r0], id_bytes = id_offsets[r1] - i0;
+        rc = ensure_text_slot(s, nr, id_bytes, 0);
+        if (rc) return rc;
+        uint64_t max_len = 0;
+        for (uint64_t i = 0; i <= nr; i++) {
+            const uint64_t o = offsets[r0 + i];
+            if (o < b0 || (i && o < offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
+            if (i && o - offsets[r0 + i - 1] > max_len) max_len = o - offsets[r0 + i - 1];
+            s.h_offsets[i] = o - b0;
+            const uint64_t io = id_offsets[r0 + i];
+            if (io < i0 || (i && io < id_offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "id_offsets are not non-decreasing");
+            s.h_id_offsets[i] = io - i0;
+        }
+        if (max_len > 0xFFFFFFFFull) return fail(SPB_ERR_LIMIT, "read longer than 2^32-1 bases");
+        qo.length_bytes = max_len < 65536 ? 2 : 4;  // a PML never exceeds the read length: uint16 is lossless here
+        SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        SPB_CUDA(cudaMemcpyAsync(s.d_id_offsets, s.h_id_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
+        if (id_bytes) SPB_CUDA(cudaMemcpyAsync(s.d_ids, ids + i0, id_bytes, cudaMemcpyHostToDevice, s.stream));
+        rc = launch_query(idx, false, s.d_reads, s.d_offsets, nr, s.d_lengths, nullptr, nullptr, s.d_stats, &qo, nullptr, s.stream);
+        if (rc) return rc;
+        spb::TextParams tp;
+        tp.values = s.d_lengths; tp.offsets = s.d_offsets; tp.ids = s.d_ids; tp.id_offsets = s.d_id_offsets;
+        tp.n_reads = nr; tp.starts = s.d_starts; tp.text = nullptr; tp.elem_bytes = qo.length_bytes;
+        SPB_CUDA(spb::launch_text_sizes(tp, idx->num_sms, s.stream));
+        g_launches.fetch_add(2);
+        SPB_CUDA(cudaMemcpyAsync(s.h_total, s.d_starts + nr, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
+        inflight.push_back(TextChunk{slot, nr, id_bytes, qo.length_bytes});
+        r0 = r1;
+        chunk++;
+    }
+    while (!inflight.empty()) { rc = finish(); if (rc) return rc; }
+    for (int i = 0; i < kMaxSlots; i++)
+        if (idx->slots[i].stream) SPB_CUDA(cudaStreamSynchronize(idx->slots[i].stream));
+    *text_bytes = text_off;
+    return SPB_OK;
+}
+
 template <typename F>
 int guarded(F&& f) {
     try {
@@ -415,6 +551,12 @@ int spb_ms_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* 
     return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, doc_nums, stats, opts);
 }
 uint32_t spb_index_num_docs(const spb_index* idx) { return idx ? idx->hdr.num_docs : 0; }
+int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                            const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
+                            uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts) {
+    if (idx && idx->mode != SPB_MODE_PML) return fail(SPB_ERR_ARG, "spb_pml_query_host_text on an MS index");
+    return query_host_text(idx, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
+}
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                       void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
     return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, nullptr, stats, opts);

@@ -950,4 +950,110 @@ cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cu
     }
 }
 
+// ==========================================================================================
+// K5: on-device decimal formatting (one warp per read).
+// ==========================================================================================
+template <int EB>
+__device__ __forceinline__ uint64_t load_value(const void* v, uint64_t i) {
+    if (EB == 1) return reinterpret_cast<const uint8_t*>(v)[i];
+    if (EB == 2) return reinterpret_cast<const uint16_t*>(v)[i];
+    if (EB == 4) return reinterpret_cast<const uint32_t*>(v)[i];
+    return reinterpret_cast<const uint64_t*>(v)[i];
+}
+__device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
+    uint32_t d = 1;
+    while (v >= 10) { v /= 10; d++; }
+    return d;
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) spb_text_sizes_kernel(const TextParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < p.n_reads; r += warps) {
+        const uint64_t a = p.offsets[r], b = p.offsets[r + 1];
+        uint64_t bytes = 0;
+        for (uint64_t i = a + lane; i < b; i += 32) bytes += dec_digits(load_value<EB>(p.values, i)) + 1;  // digits + ' '
+        for (int o = 16; o; o >>= 1) bytes += __shfl_xor_sync(0xFFFFFFFFu, bytes, o);
+        if (lane == 0) p.starts[r + 1] = bytes + (p.id_offsets[r + 1] - p.id_offsets[r]) + 3;  // '>' id '\n' ... '\n'
+    }
+}
+
+// exclusive scan in place: starts[0] = 0, starts[r + 1] = sum of the sizes of reads 0..r.  One block; each thread owns
+// a contiguous slice (a sub-batch has at most a few hundred thousand reads).
+__global__ void __launch_bounds__(1024) spb_text_scan_kernel(uint64_t* starts, uint64_t n) {
+    __shared__ uint64_t part[1024];
+    const uint64_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint64_t lo = (uint64_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    uint64_t sum = 0;
+    for (uint64_t i = lo; i < hi; i++) sum += starts[i + 1];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < blockDim.x; o <<= 1) {  // Hillis-Steele over the 1024 slice sums
+        const uint64_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint64_t run = threadIdx.x ? part[threadIdx.x - 1] : 0;
+    if (threadIdx.x == 0) starts[0] = 0;
+    for (uint64_t i = lo; i < hi; i++) { run += starts[i + 1]; starts[i + 1] = run; }
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) spb_text_format_kernel(const TextParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    for (uint64_t r = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < p.n_reads; r += warps) {
+        const uint64_t a = p.offsets[r], b = p.offsets[r + 1];
+        const uint64_t ia = p.id_offsets[r], idl = p.id_offsets[r + 1] - ia;
+        char* out = p.text + p.starts[r];
+        if (lane == 0) { out[0] = '>'; out[1 + idl] = '\n'; }
+        for (uint64_t i = lane; i < idl; i += 32) out[1 + i] = (char)p.ids[ia + i];
+        uint64_t pos = idl + 2;  // bytes of this read's text written so far (uniform across the warp)
+        for (uint64_t i0 = a; i0 < b; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            uint64_t v = i < b ? load_value<EB>(p.values, i) : 0;
+            const uint32_t nd = i < b ? dec_digits(v) : 0, len = i < b ? nd + 1 : 0;
+            uint32_t incl = len;  // inclusive warp scan of the text lengths
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += t; }
+            if (i < b) {
+                char* q = out + pos + (incl - len);
+                for (uint32_t d = nd; d-- > 0;) { q[d] = (char)('0' + v % 10); v /= 10; }
+                q[nd] = ' ';
+            }
+            pos += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        if (lane == 0) out[pos] = '\n';
+    }
+}
+
+static unsigned text_grid(uint64_t n_reads, int num_sms) {
+    const uint64_t need = (n_reads + 7) / 8, cap = (uint64_t)num_sms * 8;  // 8 warps per 256-thread CTA
+    return (unsigned)(need < cap ? (need ? need : 1) : cap);
+}
+cudaError_t launch_text_sizes(const TextParams& p, int num_sms, cudaStream_t stream) {
+    const unsigned grid = text_grid(p.n_reads, num_sms);
+    switch (p.elem_bytes) {
+        case 1: spb_text_sizes_kernel<1><<<grid, 256, 0, stream>>>(p); break;
+        case 2: spb_text_sizes_kernel<2><<<grid, 256, 0, stream>>>(p); break;
+        case 4: spb_text_sizes_kernel<4><<<grid, 256, 0, stream>>>(p); break;
+        case 8: spb_text_sizes_kernel<8><<<grid, 256, 0, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    spb_text_scan_kernel<<<1, 1024, 0, stream>>>(p.starts, p.n_reads);
+    return cudaGetLastError();
+}
+cudaError_t launch_text_format(const TextParams& p, int num_sms, cudaStream_t stream) {
+    const unsigned grid = text_grid(p.n_reads, num_sms);
+    switch (p.elem_bytes) {
+        case 1: spb_text_format_kernel<1><<<grid, 256, 0, stream>>>(p); break;
+        case 2: spb_text_format_kernel<2><<<grid, 256, 0, stream>>>(p); break;
+        case 4: spb_text_format_kernel<4><<<grid, 256, 0, stream>>>(p); break;
+        case 8: spb_text_format_kernel<8><<<grid, 256, 0, stream>>>(p); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace spb

@@ -53,4 +53,22 @@ struct WalkParams {
 // work_counter must point at two zeroed counters.  *launches (nullable) receives the number of kernels launched.
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches);
 
+// K5: decimal formatting of a batch of per-base values on the device -- the text the reference writes with
+// std::copy(..., ostream_iterator<size_t>(f, " ")) (/root/reference/src/compute_ms_pml.cpp:1007-1010):
+//     '>' id '\n' v0 ' ' v1 ' ' ... '\n'       per read.
+// Three launches on `stream`: exact text size per read, exclusive scan over the reads (starts[n_reads] = total bytes),
+// then the bytes.  elem_bytes = size of one value (1, 2, 4 or 8).
+struct TextParams {
+    const void* values;        // one value per base (device)
+    const uint64_t* offsets;   // n_reads + 1 (device)
+    const uint8_t* ids;        // read ids back to back (device)
+    const uint64_t* id_offsets;  // n_reads + 1 (device)
+    uint64_t n_reads;
+    uint64_t* starts;          // out: n_reads + 1 byte offsets of every read's text (device)
+    char* text;                // out (device); written by launch_text_format only
+    uint32_t elem_bytes;
+};
+cudaError_t launch_text_sizes(const TextParams& p, int num_sms, cudaStream_t stream);   // sizes + scan -> starts
+cudaError_t launch_text_format(const TextParams& p, int num_sms, cudaStream_t stream);  // needs starts
+
 }  // namespace spb

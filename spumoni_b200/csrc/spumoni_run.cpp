@@ -318,6 +318,12 @@ struct Work {
     std::vector<spb_bin_stats> S;
     std::vector<uint32_t> D;
     bool narrow = false;
+    // PML without -d: the .pseudo_lengths bytes come formatted from the device (spb_pml_query_host_text)
+    std::vector<uint8_t> idcat;
+    std::vector<uint64_t> idoff;
+    std::unique_ptr<char[]> text;
+    uint64_t text_cap = 0, text_bytes = 0;
+    bool device_text = false;
 };
 
 class WorkQueue {  // bounded hand-off between two stages; nullptr = end of stream
@@ -343,7 +349,26 @@ private:
 static void query_batch(spb_index* idx, bool ms, const RunOptions& o, spb_query_opts qo, Work& w) {
     ReadBatch& b = w.b;
     const size_t nr = b.ids.size();
+    w.device_text = false;
     if (!nr) return;
+    static const bool host_format = std::getenv("SPUMONI_B200_HOST_FORMAT") != nullptr;  // keep the decimal formatting on the host
+    if (!ms && !o.use_doc && !host_format) {
+        w.idcat.clear();
+        w.idoff.assign(1, 0);
+        for (const auto& id : b.ids) { w.idcat.insert(w.idcat.end(), id.begin(), id.end()); w.idoff.push_back(w.idcat.size()); }
+        if (o.write_report) w.S.resize(nr);
+        uint64_t need = b.bases.size() * 3 + w.idcat.size() + 3 * nr + 64;  // typical PML text is ~2 bytes per base
+        for (;;) {
+            if (need > w.text_cap) { w.text.reset(new char[need]); w.text_cap = need; }
+            const int rc = spb_pml_query_host_text(idx, b.bases.data(), b.offsets.data(), nr, w.idcat.data(), w.idoff.data(), w.text.get(),
+                                                   w.text_cap, &w.text_bytes, o.write_report ? w.S.data() : nullptr, &qo);
+            if (rc == SPB_ERR_LIMIT && w.text_bytes > w.text_cap) { need = w.text_bytes + w.text_bytes / 2; continue; }  // rare: redo with a larger buffer
+            spb_or_die(rc);
+            break;
+        }
+        w.device_text = true;
+        return;
+    }
     w.narrow = !o.use_doc && b.max_len < 65536;
     void* lengths;
     if (w.narrow) { w.L16.resize(b.bases.size()); lengths = w.L16.data(); qo.length_bytes = 2; }
@@ -372,10 +397,13 @@ static void write_batch(bool ms, const RunOptions& o, const Work& w, Outputs& ou
         write_all(out.docs, parts);
         lap(t_write);
     }
-    if (w.narrow) format_values(b, w.L16.data(), (int)o.threads, parts);
-    else format_values(b, w.L.data(), (int)o.threads, parts);
-    lap(t_format);
-    write_all(out.lengths, parts);
+    if (w.device_text) out.lengths.write(w.text.get(), (std::streamsize)w.text_bytes);
+    else {
+        if (w.narrow) format_values(b, w.L16.data(), (int)o.threads, parts);
+        else format_values(b, w.L.data(), (int)o.threads, parts);
+        lap(t_format);
+        write_all(out.lengths, parts);
+    }
     lap(t_write);
     if (ms) {
         format_values(b, w.P.data(), (int)o.threads, parts);

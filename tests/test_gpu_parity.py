@@ -194,6 +194,13 @@ def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
     oracle.run(ref, qa, "ms" if ms else "pml", report="-c" in flags, bin_width=bw, threads=1, use_doc="-d" in flags)
     r = subprocess.run([sp.CLI_PATH, "run", "-r", ref[:-3], "-p", qb, "-n"] + flags, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+    if flags[0] == "-P" and "-d" not in flags:  # this path formats on the device; the host formatter must give the same bytes
+        qc = str(tmp_path / "c.fa")
+        open(qc, "w").write(body)
+        r2 = subprocess.run([sp.CLI_PATH, "run", "-r", ref[:-3], "-p", qc, "-n", "-t", "3"] + flags, capture_output=True, text=True,
+                            env=dict(os.environ, SPUMONI_B200_HOST_FORMAT="1"))
+        assert r2.returncode == 0, r2.stderr
+        assert open(qc + ".pseudo_lengths", "rb").read() == open(qb + ".pseudo_lengths", "rb").read()
     exts = [".lengths", ".pointers"] if ms else [".pseudo_lengths"]
     if "-c" in flags:
         exts.append(".report")
@@ -470,3 +477,29 @@ def test_positions_beyond_2_32_on_gpu(huge_periodic_index, lanes, row_width):
     for r in range(len(reads)):
         found, summ, above, below, nb = naive.classify_bins(Lo[int(off[r]):int(off[r + 1])].tolist(), 50, 7)
         assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)
+
+
+def test_on_device_text_formatting(small_index, monkeypatch, row_width):
+    """K5: spb_pml_query_host_text returns the bytes of the .pseudo_lengths file (compute_ms_pml.cpp:1003-1010): ids with the
+    trailing-delimiter quirk, empty ids, 1-base reads, a read above 65535 bases (uint32 values in that sub-batch), many
+    sub-batches in flight (1 Mi-base chunks), classifier stats alongside, and a too-small buffer reported as such."""
+    monkeypatch.setenv("SPUMONI_B200_CHUNK_MB", "1")
+    rng = random.Random(5)
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    reads = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    text = "".join(l for l in open(small_index["ref"]).read().split("\n") if not l.startswith(">"))
+    reads += [b"A", b"N", text[100:70100].encode(), b"ACGT" * 300] + [text[a:a + 5000].encode() for a in range(0, 600000, 4000)][:400]
+    ids = [b"read_%d" % i for i in range(len(reads))]
+    ids[3], ids[4], ids[5] = b"r3 ", b"x\t", b""
+    rb, ro = sp.pack_reads(reads)
+    Lo, _ = oracle_batch(small_index["ref"], "pml", rb, ro)
+    want = b"".join(b">" + ids[i] + b"\n" + b"".join(b"%d " % v for v in Lo[int(ro[i]):int(ro[i + 1])].tolist()) + b"\n" for i in range(len(reads)))
+    idx = sp.pml_t(small_index["ref"])
+    got, S = idx.query_host_text(rb, ro, ids, bin_width=150, max_value_thr=9)
+    assert got == want
+    _, _, S0 = idx.query_host(rb, ro, bin_width=150, max_value_thr=9)
+    assert np.array_equal(S, S0)
+    with pytest.raises(sp.SpumoniError) as ei:
+        idx.query_host_text(rb, ro, ids, capacity=len(want) - 1)
+    assert ei.value.code == 6 and 0 < idx.last_text_bytes <= len(want)
+    assert idx.query_host_text(np.zeros(0, np.uint8), np.zeros(1, np.uint64), [])[0] == b""
