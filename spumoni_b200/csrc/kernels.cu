@@ -554,7 +554,43 @@ struct BinState {
     uint32_t bin_max = 0, above = 0, below = 0;
 };
 
+// A decoded move row (either layout).  raw0..2 keep the words the jump fields are extracted from.
+struct RowView {
+    uint32_t dest, len, delta, hfid;
+    bool slow;
+    uint32_t raw0, raw1, raw2;
+    uint2 smp;  // MSI only: {ss, sl}
+};
 // MSI (MS over compact rows only): every row slot is 16 bytes, {row, u32 ss, u32 sl}: the samples come with the row load
+template <int LD, bool ROW8, bool MSI>
+__device__ __forceinline__ RowView load_row(const WalkParams& p, uint32_t k) {
+    RowView r;
+    r.smp = make_uint2(0, 0);
+    if (ROW8) {
+        uint2 v;  // x = lo, y = hi (flat_index.h)
+        if (MSI) {
+            const uint4 q = ld_row<LD>(reinterpret_cast<const uint4*>(p.rows8) + k);
+            v = make_uint2(q.x, q.y);
+            r.smp = make_uint2(q.z, q.w);
+        } else v = ld_row8<LD>(p.rows8 + k);
+        r.dest = v.x & 0xFFFFFFu; r.len = (v.x >> 24) & 0x7Fu; r.slow = (v.x >> 31) != 0;
+        r.delta = v.y & 0xFFu; r.hfid = (v.y >> 8) & 7u;
+        r.raw0 = v.y; r.raw1 = 0; r.raw2 = 0;
+    } else {
+        const uint4 q = ld_row<LD>(p.rows + k);
+        r.dest = q.x; r.len = q.y & SPB_MV_LEN_MASK; r.delta = q.z & SPB_MV_LEN_MASK;
+        r.hfid = (q.w >> 27) & 7u; r.slow = ((q.w >> 30) & 1u) != 0;
+        r.raw0 = q.y; r.raw1 = q.z; r.raw2 = q.w;
+    }
+    return r;
+}
+
+// One thread per read, ONE BACKWARD-SEARCH STEP PER LOOP ITERATION for every lane of the warp: load row[k] (walking
+// forward while off >= len), classify the read character (match / threshold jump / generic), for a jump load the row
+// of the next run headed by that character (probing consecutive rows with the compact layout), land, emit.  The
+// jump's second load is predicated, not a separate iteration: an earlier version advanced one *load* per iteration
+// (lanes in different modes) and ran at 14 of 32 lanes per issued instruction; the step-per-iteration form keeps
+// the whole warp on the same instructions and is issue-efficient (profiles/).
 template <bool MS, bool STATS, int OW, int LD, bool ROW8, bool DOC, bool MSI = false>
 __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB > 8) ? 8 : SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
@@ -573,7 +609,6 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         if (threadIdx.x == i) { s_end_k[i] = p.mv_end_k[i]; s_end_off[i] = p.mv_end_off[i]; s_end_sl[i] = p.mv_end_sl[i]; s_end_doc[i] = p.mv_end_doc[i]; }
     __syncthreads();
 
-    const uint4* __restrict__ rows = p.rows;
     const uint32_t R32 = (uint32_t)p.R;
     const bool upper = (p.flags & SPB_FLAG_TOUPPER) != 0;
     const bool do_stats = !MS && STATS && p.bin_width != 0 && p.stats != nullptr;
@@ -581,11 +616,10 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
     constexpr uint32_t VMAX = OW == 4 ? 0xFFFFFFFFu : (OW == 2 ? 0xFFFFu : 0xFFu);
 
     // lane state
-    bool have = false, down = false;
+    bool have = false;
     unsigned long long r = 0;
     uint64_t base = 0, end = 0, gi = 0;
-    uint32_t k = 0, off = 0, k2 = 0, length = 0, mode = 0;  // mode 0 = STEP, 1 = JUMP2 (compact rows: also probing for the c-run)
-    uint32_t want = 0, probes = 0;
+    uint32_t k = 0, off = 0, length = 0;
     uint64_t sample = 0;
     uint32_t nsat = 0, doc = 0;
     BinState bs;
@@ -602,7 +636,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             }
             end = base + m;
             gi = end - 1;
-            k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0; mode = 0;  // empty string: pos = n-1
+            k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0;  // empty string: pos = n-1
             if (MS) sample = p.last_run_sample;
             if (DOC) doc = p.doc_init;
             stage_reads(s_rd, p.reads, gi);
@@ -615,132 +649,89 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             }
         }
 
-        // ---- one index load per lane per iteration (+ the read byte from shared memory)
+        // ---- the row of the current position: walk forward while off >= len (the LF image of a run may span several runs)
         uint32_t c = rd_bytes[staged_offset((uint32_t)gi & (SPB_STAGE - 1))];
         if (upper && c >= 'a' && c <= 'z') c -= 32;
-        bool slow = false, emit = false;
-        if (ROW8) {
-            uint2 v;  // x = lo, y = hi (flat_index.h)
-            uint2 smp = make_uint2(0, 0);
-            if (MSI) {
-                const uint4 q = ld_row<LD>(reinterpret_cast<const uint4*>(p.rows8) + (mode ? k2 : k));
-                v = make_uint2(q.x, q.y);
-                smp = make_uint2(q.z, q.w);
-            } else v = ld_row8<LD>(p.rows8 + (mode ? k2 : k));
-            if (mode == 0) {
-                if (v.x >> 31) slow = true;
-                else {
-                    const uint32_t len = (v.x >> 24) & 0x7Fu;
-                    if (off == SPB_MV_OFF_LAST) off = len - 1;
-                    if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
-                    const uint32_t h = (v.y >> 8) & 7u, s = s_fid[c];
-                    if (s >= SPB_SYM_SLOW) slow = true;
-                    else if (s == h) {  // bwt[pos] == c (:250 / :582)
-                        length++;
-                        if (MS) sample--;
-                        off += v.y & 0xFFu;
-                        k = v.x & 0xFFFFFFu;
-                        emit = true;
-                    } else {  // threshold jump (:251-279 / :583-616)
-                        const uint32_t slot = s - (s > h ? 1u : 0u);
-                        const uint32_t cls = (v.y >> (11 + 2 * slot)) & 3u, dc = (v.y >> (23 + 3 * slot)) & 7u;
-                        if (cls == 3) slow = true;
-                        else if (dc == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
-                            k = s_end_k[s]; off = s_end_off[s];
-                            length = 0;
-                            if (MS) sample = s_end_sl[s];
-                            if (DOC) doc = s_end_doc[s];
-                            emit = true;
-                        } else {
-                            down = (cls == 1) || (cls == 2 && off < ((v.y >> 17) & 0x3Fu));
-                            k2 = k + dc; want = s; probes = SPB_MV8_PROBES;  // dc == SPB_MV8_DIST_PROBE: row k2 or a later one
-                            mode = 1;
-                        }
-                    }
-                }
-            } else {
-                if (((v.y >> 8) & 7u) != want) {  // not headed by c yet: probe the next row
-                    if (--probes == 0) { mode = 0; slow = true; } else { k2++; continue; }
+        RowView row = load_row<LD, ROW8, MSI>(p, k);
+        bool slow = false;
+        for (;;) {
+            if (row.slow) { slow = true; break; }
+            if (off == SPB_MV_OFF_LAST) off = row.len - 1;
+            if (off < row.len) break;
+            off -= row.len;
+            k++;
+            row = load_row<LD, ROW8, MSI>(p, k);
+        }
+        // ---- classify: match (bwt[pos] == c, :250 / :582), threshold jump (:251-279 / :583-616), or the generic step
+        const uint32_t s = s_fid[c];
+        bool jump = false, endcase = false, down = false;
+        uint32_t k2 = k;
+        if (!slow) {
+            if (s >= SPB_SYM_SLOW) slow = true;
+            else if (s != row.hfid) {
+                const uint32_t slot = s - (s > row.hfid ? 1u : 0u);
+                uint32_t d;
+                bool gen;
+                if (ROW8) {
+                    const uint32_t cls = (row.raw0 >> (11 + 2 * slot)) & 3u;
+                    d = (row.raw0 >> (23 + 3 * slot)) & 7u;
+                    gen = cls == 3;
+                    down = (cls == 1) || (cls == 2 && off < ((row.raw0 >> 17) & 0x3Fu));
                 } else {
-                    mode = 0;
-                    if (v.x >> 31) slow = true;  // landing state not encodable: redo the step from (k, off)
-                    else {
-                        const uint32_t d2 = v.y & 0xFFu, de = v.x & 0xFFFFFFu;
-                        if (MS && MSI) sample = down ? smp.y : smp.x;
-                        else if (MS) {
-                            const uint4 sm = ldg_nc16(p.msamp + k2);
-                            sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
-                        }
-                        if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
-                        if (!down) { k = de; off = d2; }
-                        else if (d2) { k = de; off = d2 - 1; }
-                        else { k = de - 1; off = SPB_MV_OFF_LAST; }
-                        length = 0;
-                        emit = true;
-                    }
+                    const uint32_t v = slot == 0 ? (row.raw0 >> 20) : (slot == 1 ? (row.raw1 >> 20) : (row.raw2 & 0xFFFu));
+                    d = (row.raw2 >> (12u + 5u * slot)) & 31u;
+                    gen = v == SPB_MV_THR_SLOW || d == SPB_MV_DIST_FAR;
+                    down = (v == SPB_MV_THR_ALWAYS) || (off < v);
                 }
-            }
-        } else {
-            const uint4 rec = ld_row<LD>(rows + (mode ? k2 : k));
-            if (mode == 0) {
-                if ((rec.w >> 30) & 1u) slow = true;
-                else {
-                    const uint32_t len = rec.y & SPB_MV_LEN_MASK;
-                    if (off == SPB_MV_OFF_LAST) off = len - 1;
-                    if (off >= len) { off -= len; k++; continue; }  // normalise: walk to the next row
-                    const uint32_t h = (rec.w >> 27) & 7u, s = s_fid[c];
-                    if (s >= SPB_SYM_SLOW) slow = true;
-                    else if (s == h) {  // bwt[pos] == c (:250 / :582)
-                        length++;
-                        if (MS) sample--;
-                        off += rec.z & SPB_MV_LEN_MASK;
-                        k = rec.x;
-                        emit = true;
-                    } else {  // threshold jump (:251-279 / :583-616)
-                        const uint32_t slot = s - (s > h ? 1u : 0u);
-                        const uint32_t v = slot == 0 ? (rec.y >> 20) : (slot == 1 ? (rec.z >> 20) : (rec.w & 0xFFFu));
-                        const uint32_t d = (rec.w >> (12u + 5u * slot)) & 31u;
-                        if (v == SPB_MV_THR_SLOW || d == SPB_MV_DIST_FAR) slow = true;
-                        else if (d == 0) {  // no later c-run: thr = n+1, previous c-run is the last one
-                            k = s_end_k[s]; off = s_end_off[s];
-                            length = 0;
-                            if (MS) sample = s_end_sl[s];
-                            if (DOC) doc = s_end_doc[s];
-                            emit = true;
-                        } else {
-                            down = (v == SPB_MV_THR_ALWAYS) || (off < v);
-                            k2 = k + d;
-                            mode = 1;
-                        }
-                    }
-                }
-            } else {
-                mode = 0;
-                if ((rec.w >> 30) & 1u) slow = true;  // landing state not encodable: redo the step from (k, off)
-                else {
-                    const uint32_t d2 = rec.z & SPB_MV_LEN_MASK;
-                    if (MS) {
-                        const uint4 sm = ldg_nc16(p.msamp + k2);
-                        sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
-                    }
-                    if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
-                    if (!down) { k = rec.x; off = d2; }
-                    else if (d2) { k = rec.x; off = d2 - 1; }
-                    else { k = rec.x - 1; off = SPB_MV_OFF_LAST; }
-                    length = 0;
-                    emit = true;
-                }
+                if (gen) slow = true;
+                else if (d == 0) endcase = true;  // no later c-run: thr = n+1, the previous c-run is the last one
+                else { jump = true; k2 = k + d; }
             }
         }
-        if (slow) {  // ---- generic step in absolute coordinates
+        // ---- a jump lands through the row of the next run headed by c (compact rows: row k2 or a later one: probe)
+        if (jump) {
+            row = load_row<LD, ROW8, MSI>(p, k2);
+            if (ROW8) {
+                uint32_t probes = SPB_MV8_PROBES;
+                while (row.hfid != s) {
+                    if (--probes == 0) { slow = true; break; }
+                    k2++;
+                    row = load_row<LD, ROW8, MSI>(p, k2);
+                }
+            }
+            if (row.slow) slow = true;  // landing state not encodable: generic step from (k, off)
+        }
+        // ---- land
+        if (slow) {  // generic step in absolute coordinates
             const SlowOut so = slow_step<MS, DOC>(p, c, k, off, length, sample, doc);  // by value: no state lives in local memory
             k = so.k; off = so.off; length = so.length;
             if (MS) sample = so.sample;
             if (DOC) doc = so.doc;
-            emit = true;
+        } else if (endcase) {
+            k = s_end_k[s]; off = s_end_off[s];
+            length = 0;
+            if (MS) sample = s_end_sl[s];
+            if (DOC) doc = s_end_doc[s];
+        } else if (!jump) {
+            length++;
+            if (MS) sample--;
+            off += row.delta;
+            k = row.dest;
+        } else {
+            if (MS && MSI) sample = down ? row.smp.y : row.smp.x;
+            else if (MS) {
+                const uint4 sm = ldg_nc16(p.msamp + k2);
+                sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+            }
+            if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
+            // first position of the c-run's LF image, or (down) one position before it
+            k = row.dest - ((down && row.delta == 0) ? 1u : 0u);
+            off = row.delta - (down ? 1u : 0u);  // down, delta == 0: 0xFFFFFFFF == SPB_MV_OFF_LAST (last position of the previous row)
+            length = 0;
         }
 
-        if (emit) {
+        // ---- emit
+        {
             const bool last = (gi == base);
             if (DOC) stage_value<4>(s_doc, p.docs, gi, doc, end, last);
             if (MS) stage_value<8>(s_out, p.pointers, gi, sample, end, last);
