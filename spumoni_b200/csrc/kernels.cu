@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
 // take the generic absolute-position step.
 // ==========================================================================================
 #define SPB_MV_THREADS 128
+/* (prefetching the following sectors of row[k]'s line into L1 was measured: -5 % / -15 % for one / two sectors) */
 #ifndef SPB_MV_MINB
 #define SPB_MV_MINB 9  /* 128-thread CTAs per SM: 56 registers, no spills (at 10 the 48-register cap spills inside the loop) */
 #endif
