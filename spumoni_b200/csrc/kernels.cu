@@ -768,9 +768,9 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
 }
 
 // MS pointers -> lengths (ms_t::matching_statistics, compute_ms_pml.cpp:795-812) + bin-max classifier
-// (:1150-1176); one thread per read, left to right, carrying l.  Each iteration either compares up to eight
-// more characters (read vs text at pointer + l, word-wise) or emits one length; lengths are staged in shared
-// memory and written as whole blocks like the walk kernel's outputs.
+// (:1150-1176); one thread per read, left to right, carrying l.  Each iteration emits one length; where the pointer
+// is not the previous one + 1 it first extends l, eight characters per round (read vs text at pointer + l,
+// word-wise); lengths are staged in shared memory and written as whole blocks like the walk kernel's outputs.
 template <bool STATS, int OW>
 __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const __grid_constant__ WalkParams p) {
     __shared__ uint4 s_out[SPB_STAGE_CH * SPB_MV_THREADS];
@@ -806,21 +806,24 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const __
             }
         }
         if (ext) {
-            // while (i + l < m && ptr + l < n && read[i + l] == text[ptr + l]) ++l;   eight characters per iteration
-            const uint64_t tp = ptr + l;  // wraps like size_t (App. C-4)
-            uint64_t room = (i + l < m) ? m - (i + l) : 0;
-            if (tp < n_text) { if (n_text - tp < room) room = n_text - tp; } else room = 0;
-            uint32_t adv = 0;
-            if (room) {
-                const uint32_t need = room < 8 ? (uint32_t)room : 8u;
-                uint64_t a = ld_unaligned8(p.reads + base + i + l, need);
-                if (upper) a = toupper8(a);
-                const uint64_t x = a ^ ld_unaligned8(p.text + tp, need);
-                adv = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
-                if (adv > room) adv = (uint32_t)room;
+            // while (i + l < m && ptr + l < n && read[i + l] == text[ptr + l]) ++l;   eight characters per round; the whole
+            // extension runs inside this iteration so that every lane emits one length per iteration
+            for (;;) {
+                const uint64_t tp = ptr + l;  // wraps like size_t (App. C-4)
+                uint64_t room = (i + l < m) ? m - (i + l) : 0;
+                if (tp < n_text) { if (n_text - tp < room) room = n_text - tp; } else room = 0;
+                uint32_t adv = 0;
+                if (room) {
+                    const uint32_t need = room < 8 ? (uint32_t)room : 8u;
+                    uint64_t a = ld_unaligned8(p.reads + base + i + l, need);
+                    if (upper) a = toupper8(a);
+                    const uint64_t x = a ^ ld_unaligned8(p.text + tp, need);
+                    adv = x ? (uint32_t)(__ffsll((long long)x) - 1) >> 3 : 8u;
+                    if (adv > room) adv = (uint32_t)room;
+                }
+                l += adv;
+                if (adv < 8) break;
             }
-            l += adv;
-            if (adv == 8) continue;
             ext = false;
         }
         // ---- emit lengths[i] = l
