@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <chrono>
 #include <deque>
 #include <cstdio>
 #include <cstdlib>
@@ -429,13 +430,19 @@ int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index*
     return guarded([&]() -> int {
         const bool ms = mode == SPB_MODE_MS;
         const std::string ref(ref_file);
+        const bool timing = std::getenv("SPUMONI_B200_TIMING") != nullptr;
+        auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = now();
         spb::DecodedIndex d = spb::parse_index_file(ref + (ms ? ".thrbv.ms" : ".thrbv.spumoni"), ms);
+        const double t1 = now();
         if (flags & SPB_OPEN_DOC) spb::load_doc_array(ref + ".doc", d);
         std::string text;
         if (ms) text = spb::load_reference_text(ref);
         std::unique_ptr<spb_index> idx(new spb_index());
         idx->mode = mode;
+        const double t2 = now();
         idx->host_blob = spb::build_flat_image(d, ms, text);
+        if (timing) std::fprintf(stderr, "[timing] index open: parse %.3f s | text/doc %.3f s | flatten %.3f s (%.1f MB)\n", t1 - t0, t2 - t1, now() - t2, idx->host_blob.size() / 1e6);
         std::memcpy(&idx->hdr, idx->host_blob.data(), sizeof(SpbFlatHeader));
         *out = idx.release();
         return SPB_OK;
