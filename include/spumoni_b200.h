@@ -21,7 +21,10 @@
  *   - "ref_file" is the path the reference passes around internally: "<prefix>.fa"
  *     (spumoni.cpp:744-747); the index is "<ref_file>.thrbv.spumoni" / "<ref_file>.thrbv.ms"
  *     (compute_ms_pml.cpp:215-217, :544-546), exactly as written by `spumoni build`;
- *   - the CUDA path is the only path: without a usable GPU the query calls fail loudly.
+ *   - the CUDA path is the only path: without a usable GPU the query calls fail loudly;
+ *   - an spb_index serialises nothing: use one host thread per handle (the reference shares one index between its
+ *     OpenMP threads because every call handles one read; here one call handles a whole batch and keeps several
+ *     sub-batches in flight on its own streams).  Different handles, e.g. one per GPU, are independent.
  */
 #ifndef SPUMONI_B200_H
 #define SPUMONI_B200_H
