@@ -49,6 +49,16 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: everything else that writes to fd 1 (the NCCL version banner, child
+# processes) is sent to stderr, and the result line goes to a private duplicate of the original stdout.
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    print(json.dumps(obj), file=_RESULT_OUT, flush=True)
+
+
 def cache_dir(name: str) -> str:
     w = WORKLOADS[name]
     key = hashlib.sha1(json.dumps([w["genome"], "fixture-v1"]).encode()).hexdigest()[:12]
@@ -170,7 +180,7 @@ def run_reference(args, name):
            "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
                             "sample": f"first {sample_reads} reads of the workload, {args.steps} steps, in-memory, OpenMP dynamic over reads"},
            "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def main():
@@ -359,7 +369,7 @@ def main():
                     out["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
             except Exception:
                 pass
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
