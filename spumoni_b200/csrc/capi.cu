@@ -152,6 +152,16 @@ int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms, bool doc) {
     return SPB_OK;
 }
 
+// The host entry points hand caller memory to asynchronous copies: whatever way they return (errors included), no
+// copy may still be in flight afterwards.
+struct DrainOnExit {
+    spb_index* idx;
+    ~DrainOnExit() {
+        for (int i = 0; i < kMaxSlots; i++)
+            if (idx->slots[i].stream) cudaStreamSynchronize(idx->slots[i].stream);
+    }
+};
+
 int length_bytes_of(const spb_query_opts* opts) {
     const uint32_t w = opts ? opts->length_bytes : 0;
     return w == 0 ? 4 : (int)w;
@@ -226,6 +236,7 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
     if (!reads || !offsets || !lengths || (ms && !pointers)) return fail(SPB_ERR_ARG, "null host buffer");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
+    DrainOnExit drain{idx};
     const bool want_stats = stats && opts && opts->bin_width;
     const int width = length_bytes_of(opts);
     if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
@@ -318,6 +329,7 @@ int query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offset
     if (!reads || !offsets || !ids || !id_offsets || !text) return fail(SPB_ERR_ARG, "null host buffer");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
+    DrainOnExit drain{idx};
     const bool want_stats = stats && opts && opts->bin_width;
     const int kSlots = idx->n_slots;
     const uint64_t kChunkBases = idx->chunk_bases;

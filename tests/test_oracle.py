@@ -133,3 +133,54 @@ def test_oracle_run_writes_reference_shaped_files(small_index, tmp_path):
     assert rep[0].startswith("read id:") and "avg max-value (thr=" in rep[0]
     assert rep[1].startswith("r1 ") and ("FOUND" in rep[1] or "NOT_PRESENT" in rep[1])
     assert oracle.nulldb_percentile(small_index["ref"] + ".pmlnulldb") == 6.0
+
+
+def test_cpp_oracle_document_numbers_vs_naive(tmp_path):
+    """-d: the C++ oracle's doc variants (compute_ms_pml.cpp:288-340, :625-682) and the fixture's .doc writer against
+    the literal Python restatement and a naive DocumentArray constructor (doc_array.cpp:18-108)."""
+    rng = random.Random(5)
+    base = "".join(rng.choice("ACGT") for _ in range(90))
+    recs = ["".join((ch if rng.random() > 0.1 else rng.choice("ACGT")) for ch in base) for _ in range(5)]
+    fa = str(tmp_path / "in.fa")
+    open(fa, "w").write("".join(">s%d\n%s\n" % (i, r) for i, r in enumerate(recs)))
+    ref = build_index(str(tmp_path), fasta=fa, docs=3)
+    text = "".join(recs).encode()
+    idx = naive.build_naive_index(text)
+    lens = [int(l.split("\t")[1]) for l in open(ref + ".fdi")]
+    assert sum(lens) == len(text) and len(lens) == 3
+    sd, ed = naive.build_doc_array(idx, lens)
+    assert sorted(set(sd + ed)) == [0, 1, 2]
+    po, mo = oracle.OracleIndex(ref, "pml", use_doc=True), oracle.OracleIndex(ref, "ms", use_doc=True)
+    for _ in range(60):
+        ln = rng.randint(1, 80)
+        s0 = rng.randint(0, len(text) - ln)
+        r = bytearray(text[s0:s0 + ln])
+        for i in range(len(r)):
+            if rng.random() < 0.1:
+                r[i] = rng.choice(b"ACGTN")
+        r = bytes(r)
+        buf, off = np.frombuffer(r, dtype=np.uint8), np.array([0, len(r)], dtype=np.uint64)
+        L, _, D = po.query_batch_doc(buf, off)
+        nl, nd = naive.pml_query_doc(idx, r, sd, ed)
+        assert L.tolist() == nl and D.tolist() == nd
+        assert L.tolist() == naive.pml_query(idx, r)  # the doc variant computes the same lengths
+        Lm, Pm, Dm = mo.query_batch_doc(buf, off)
+        np_, ndm = naive.ms_pointers_query_doc(idx, r, sd, ed)
+        assert Pm.tolist() == np_ and Dm.tolist() == ndm
+
+
+def test_cpp_oracle_null_database_vs_naive(small_index):
+    """generate_null_pml_statistics + EmpNullDatabase summary (compute_ms_pml.cpp:1448-1486, emp_null_database.cpp:42-79)."""
+    from conftest import load_bin_reads
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    buf, off = buf[: int(off[12])], off[:13]
+    o = oracle.OracleIndex(small_index["ref"], "pml")
+    stats, mean, perc = o.nulldb_generate(buf, off)
+    want = []
+    for i in range(12):
+        r = bytes(buf[int(off[i]):int(off[i + 1])]).upper()[::-1]
+        want += o.matching_statistics(r).tolist()
+    assert stats.tolist() == want and mean == sum(want) / len(want)
+    from collections import Counter
+    common = [v for v, c in Counter(want).items() if c >= 5]
+    assert perc == (max(common) if common else 0)
