@@ -317,7 +317,7 @@ def main():
     main_m, np_len, np_ptr = measure(args.length_bytes)
     clocks = sampler.stop() if rank == 0 else None
     other = {}
-    if args.length_bytes != 4 and not args.no_variants:
+    if args.length_bytes != 4 and not args.no_variants and world == 1:  # secondary line; N = 1 only (4 GB more pinned memory per rank)
         other["u32"], _, _ = measure(4)
     value, total_ms_max, kavg_ms, launches = main_m["value"], main_m["ms_per_step"] * args.steps, main_m["kernel_ms"], main_m["launches"]
     e2e_value, same = main_m["e2e"], main_m["same"]
