@@ -143,6 +143,28 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Run this rank (and first-touch its pinned buffers) on the host NUMA node its GPU hangs off: the end-to-end leg is a
+    PCIe + host-memory path.  Best effort; returns a short description for the log."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return f"gpu {local} ({bdf}): no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return f"gpu {local} ({bdf}): bound to NUMA node {node} ({len(cpus)} cpus)"
+    except Exception as e:  # unknown topology: leave the affinity alone
+        return f"gpu {local}: NUMA binding skipped ({type(e).__name__}: {e})"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -217,6 +239,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; spumoni_b200 has no CPU path to measure")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    log(f"rank {rank}: " + bind_to_gpu_numa_node(local))
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -326,6 +350,7 @@ def main():
     cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
         cores = os.cpu_count() or 1
         sample_reads = min(n_reads, max(200, (7000 if mode == "pml" else 6000) * cores * 1000 // w["read_len"]))  # ~10 s of CPU work
         o = oracle.OracleIndex(ref, mode)
