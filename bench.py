@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--length-bytes", type=int, default=1, choices=[1, 2, 4],
                     help="element size of the lengths output (1/2 are checked lossless: a clamped value fails the step and it is redone wider)")
     ap.add_argument("--mode", default="pml", choices=["pml", "ms"], help="pml = the headline metric (BASELINE configs[1]); ms = configs[2], a secondary line")
+    ap.add_argument("--pointers64", action="store_true", help="--mode ms: keep 64-bit pointers even when 32 bits are lossless")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra 4-byte-lengths measurement")
     args = ap.parse_args()
@@ -282,9 +283,11 @@ def main():
         d_len = torch.zeros(n_bases, dtype=TDT[width], device=dev)
         d_sat = torch.zeros(1, dtype=torch.int64, device=dev)
         np_len = h_len.numpy().view(NDT[width])
-        d_ptr = torch.zeros(n_bases, dtype=torch.int64, device=dev) if mode == "ms" else None
-        h_ptr = torch.empty(n_bases, dtype=torch.int64).pin_memory() if mode == "ms" else None
-        np_ptr = h_ptr.numpy().view(np.uint64) if mode == "ms" else None
+        # MS pointers travel as uint32 when the text has fewer than 2^32 - 1 positions (checked lossless like the lengths)
+        pw = 4 if (mode == "ms" and n < (1 << 32) - 1 and not args.pointers64) else 8
+        d_ptr = torch.zeros(n_bases, dtype=torch.int64 if pw == 8 else torch.int32, device=dev) if mode == "ms" else None
+        h_ptr = torch.empty(n_bases, dtype=torch.int64 if pw == 8 else torch.int32).pin_memory() if mode == "ms" else None
+        np_ptr = h_ptr.numpy().view(np.uint64 if pw == 8 else np.uint32) if mode == "ms" else None
 
         def step_device():
             idx.query_device(d_reads, d_off, n_reads, d_len, d_pointers=d_ptr, lanes=args.lanes, stream=stream.cuda_stream, d_saturated=d_sat)
@@ -292,7 +295,7 @@ def main():
         def step_host():
             # the call a user makes: host buffers in, host buffers out (a clamped narrow value makes the call fail)
             try:
-                idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len, out_pointers=np_ptr, length_bytes=width)
+                idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len, out_pointers=np_ptr, length_bytes=width, pointer_bytes=pw)
             except sp.SpumoniError as e:
                 raise SystemExit(f"bench.py: {e}; rerun with --length-bytes 2" if e.code == sp.ERR_OVERFLOW else f"bench.py: {e}")
 
@@ -328,11 +331,11 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         same = bool(np.array_equal(np_len, d_len.cpu().numpy().view(NDT[width])))
         if mode == "ms":
-            same = same and bool(np.array_equal(np_ptr, d_ptr.cpu().numpy().view(np.uint64)))
+            same = same and bool(np.array_equal(np_ptr, d_ptr.cpu().numpy().view(np_ptr.dtype)))
         return {"value": n_bases * world * args.steps / (total_ms_max / 1e3), "ms_per_step": total_ms_max / args.steps,
                 "kernel_ms": sum(kern_ms) / len(kern_ms), "launches": int(launches),
                 "e2e": n_bases * world * args.steps / float(t.item()), "same": same,
-                "d2h_bytes_per_step": (width + (8 if mode == "ms" else 0)) * n_bases}, np_len, np_ptr
+                "d2h_bytes_per_step": (width + (pw if mode == "ms" else 0)) * n_bases}, np_len, np_ptr
 
     # ---------------- timed region (clock sampling covers the headline measurement)
     sampler = ClockSampler(local)
@@ -358,7 +361,7 @@ def main():
         sb = int(off[sample_reads])
         mism = int(np.count_nonzero(Lo != np_len[:sb].astype(np.uint64)))
         if mode == "ms":
-            mism += int(np.count_nonzero(Po != np_ptr[:sb]))
+            mism += int(np.count_nonzero(Po != np_ptr[:sb].astype(np.uint64)))
         parity = {"reads_checked": sample_reads, "bases_checked": sb, "mismatches": mism, "host_equals_device_path": same}
         cpu_baseline = {"value": sb / sec, "unit": "bases/s", "cores": cores, "kind": "port",
                         "sample": f"first {sample_reads} reads ({sb} bases) of the same workload, in-memory, OpenMP over reads"}

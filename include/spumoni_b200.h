@@ -38,6 +38,11 @@ extern "C" {
 
 #define SPB_ABI_VERSION 3
 #define SPB_QUERY_TOUPPER 1u
+#define SPB_QUERY_POINTERS32 2u /* MS queries: `pointers` is a uint32_t array.  Lossless whenever every pointer is below 2^32 - 1
+                                   (text positions of an index with n < 2^32, reads without characters absent from the index --
+                                   the reference's size_t wrap-around after such a character, SURVEY App. C-4, does not fit).
+                                   A value that does not fit is clamped, counted in `saturated`, and the *_host call returns
+                                   SPB_ERR_OVERFLOW: discard the outputs and repeat with 64-bit pointers. */
 #define SPB_OPEN_DOC 1u /* spb_index_open_ex: also load <ref_file>.doc (the reference's use_doc / -d) */
 
 typedef enum {
@@ -69,7 +74,8 @@ typedef struct {
     uint32_t lanes_per_read; /* 0 = library default; 1 = thread-per-read kernels over the move rows (needs an index whose
                                 frequent run heads are < 0x80, e.g. DNA), 4/8/16/32 = cooperative generic kernel */
     uint64_t max_value_thr;  /* see spb_max_value_threshold */
-    uint32_t flags;          /* SPB_QUERY_TOUPPER: apply ::toupper to read bytes on the device (compute_ms_pml.cpp:916-917) */
+    uint32_t flags;          /* SPB_QUERY_TOUPPER: apply ::toupper to read bytes on the device (compute_ms_pml.cpp:916-917);
+                                SPB_QUERY_POINTERS32: see above */
     uint32_t length_bytes;   /* element size of the `lengths` output: 0 or 4 = uint32_t, 2 = uint16_t, 1 = uint8_t.  A PML/MS
                                 length never exceeds the read length, so 2 is lossless for reads < 65536 bases.  Values that do
                                 not fit are clamped to the maximum and counted (lanes_per_read 1 only). */
@@ -137,7 +143,8 @@ int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* off
 
 /* ms_t::matching_statistics compute_ms_pml.cpp:795-812 -> ms_pointers::_query :570-623 */
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-                      void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts);
+                      void* lengths, void* pointers /* uint64_t[], or uint32_t[] with SPB_QUERY_POINTERS32 */, spb_bin_stats* stats,
+                      const spb_query_opts* opts);
 
 /* Same, on buffers already resident on the index's device; asynchronous on `cuda_stream`
  * (a cudaStream_t passed as void*; NULL = default stream).  d_reads must be 256-byte aligned
@@ -145,7 +152,7 @@ int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offs
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                          void* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream);
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                        void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
+                        void* d_lengths, void* d_pointers, spb_bin_stats* d_stats,
                         const spb_query_opts* opts, void* cuda_stream);
 
 /* PML query + on-device decimal formatting (K5): instead of the lengths, the call returns the bytes the reference

@@ -25,6 +25,7 @@ SATTEST_LIB_PATH = os.path.join(_HERE, "lib", "libspumoni_b200_sattest.so")  # t
 CLI_PATH = os.path.join(_HERE, "bin", "spumoni")
 MODE_PML, MODE_MS = 0, 1
 QUERY_TOUPPER = 1
+QUERY_POINTERS32 = 2
 OPEN_DOC = 1
 ERR_OVERFLOW = 7
 _LEN_DTYPES = {4: np.uint32, 2: np.uint16, 1: np.uint8}
@@ -257,10 +258,10 @@ class Index:
         return self
 
     # ---- queries (host buffers)
-    def _opts(self, bin_width=0, max_value_thr=0, lanes=0, toupper=False, length_bytes=4, saturated=None) -> QueryOpts:
+    def _opts(self, bin_width=0, max_value_thr=0, lanes=0, toupper=False, length_bytes=4, saturated=None, pointer_bytes=8) -> QueryOpts:
         o = QueryOpts()
         o.bin_width, o.lanes_per_read, o.max_value_thr = bin_width, lanes, max_value_thr
-        o.flags = QUERY_TOUPPER if toupper else 0
+        o.flags = (QUERY_TOUPPER if toupper else 0) | (QUERY_POINTERS32 if pointer_bytes == 4 else 0)
         o.length_bytes = length_bytes
         o.saturated = saturated
         return o
@@ -305,9 +306,10 @@ class Index:
         return L, None, S, D
 
     def query_host(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0,
-                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None, length_bytes=4):
-        """length_bytes 4/2/1 selects uint32/uint16/uint8 lengths; if a value does not fit, SpumoniError with
-        code ERR_OVERFLOW is raised (``.saturated`` = number of clamped values) and the caller retries wider."""
+                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None, length_bytes=4, pointer_bytes=8):
+        """length_bytes 4/2/1 selects uint32/uint16/uint8 lengths, pointer_bytes 8/4 uint64/uint32 MS pointers; if a value
+        does not fit, SpumoniError with code ERR_OVERFLOW is raised (``.saturated`` = number of clamped values) and the
+        caller retries wider."""
         reads = np.ascontiguousarray(reads, dtype=np.uint8)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
@@ -318,11 +320,12 @@ class Index:
         if bin_width:
             S = out_stats if out_stats is not None else np.zeros(n, dtype=BinStats)
         sat = ctypes.c_uint64(0)
-        o = self._opts(bin_width, max_value_thr, lanes, toupper, length_bytes, ctypes.addressof(sat))
+        o = self._opts(bin_width, max_value_thr, lanes, toupper, length_bytes, ctypes.addressof(sat), pointer_bytes)
         self.last_saturated = sat  # keeps the counter alive for the duration of the call
         lib = load_library()
         if self.mode == MODE_MS:
-            P = out_pointers if out_pointers is not None else np.zeros(total, dtype=np.uint64)
+            P = out_pointers if out_pointers is not None else np.zeros(total, dtype=np.uint64 if pointer_bytes == 8 else np.uint32)
+            assert P.dtype.itemsize == pointer_bytes and P.size >= total
             _check(lib.spb_ms_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
                                          P.ctypes.data, S.ctypes.data if S is not None else None, ctypes.byref(o)), sat)
             return L, P, S
@@ -336,7 +339,8 @@ class Index:
         """d_lengths: int32/int16/uint8 CUDA tensor (its element size selects the output width);
         d_saturated: optional 1-element int64 CUDA tensor incremented by the number of clamped values."""
         o = self._opts(bin_width, max_value_thr, lanes, toupper, d_lengths.element_size(),
-                       d_saturated.data_ptr() if d_saturated is not None else None)
+                       d_saturated.data_ptr() if d_saturated is not None else None,
+                       d_pointers.element_size() if d_pointers is not None else 8)
         lib = load_library()
         sp = d_stats.data_ptr() if d_stats is not None else None
         if self.mode == MODE_MS:

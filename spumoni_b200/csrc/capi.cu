@@ -200,6 +200,8 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.n = h.n; p.R = h.R; p.n_text = h.n_text; p.last_run_sample = h.last_run_sample;
     p.blk_stride = h.blk_stride;
     p.flags = (opts && (opts->flags & SPB_QUERY_TOUPPER)) ? SPB_FLAG_TOUPPER : 0;
+    p.ptr32 = (ms && opts && (opts->flags & SPB_QUERY_POINTERS32)) ? 1u : 0u;
+    if (p.ptr32 && (lanes != 1 || d_docs)) return fail(SPB_ERR_ARG, "SPB_QUERY_POINTERS32 needs lanes_per_read = 1 and no document numbers");
     p.reads = d_reads; p.offsets = d_offsets; p.n_reads = n_reads;
     p.lengths = d_lengths; p.pointers = d_pointers;
     p.bin_width = (opts && d_stats) ? opts->bin_width : 0;
@@ -229,7 +231,7 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
 }
 
 int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-               void* lengths, uint64_t* pointers, uint32_t* docs, spb_bin_stats* stats, const spb_query_opts* opts) {
+               void* lengths, void* pointers, uint32_t* docs, spb_bin_stats* stats, const spb_query_opts* opts) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     if (opts && opts->saturated) *opts->saturated = 0;
     if (n_reads == 0) return SPB_OK;
@@ -240,6 +242,9 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
     const bool want_stats = stats && opts && opts->bin_width;
     const int width = length_bytes_of(opts);
     if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
+    const bool ptr32 = ms && opts && (opts->flags & SPB_QUERY_POINTERS32);
+    const bool count_sat = width != 4 || ptr32;
+    const uint64_t ptr_bytes = ptr32 ? 4 : 8;
     uint64_t total_sat = 0;
     uint64_t r0 = 0;
     int chunk = 0;
@@ -264,14 +269,14 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         }
         SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
         if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
-        if (width != 4) SPB_CUDA(cudaMemsetAsync(s.d_sat, 0, sizeof(unsigned long long), s.stream));
-        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, docs ? s.d_docs : nullptr, s.d_stats, opts, width != 4 ? s.d_sat : nullptr, s.stream);
+        if (count_sat) SPB_CUDA(cudaMemsetAsync(s.d_sat, 0, sizeof(unsigned long long), s.stream));
+        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, docs ? s.d_docs : nullptr, s.d_stats, opts, count_sat ? s.d_sat : nullptr, s.stream);
         if (rc) return rc;
         if (nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)lengths + b0 * (uint64_t)width, s.d_lengths, nb * (uint64_t)width, cudaMemcpyDeviceToHost, s.stream));
-        if (ms && nb) SPB_CUDA(cudaMemcpyAsync(pointers + b0, s.d_pointers, nb * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        if (ms && nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)pointers + b0 * ptr_bytes, s.d_pointers, nb * ptr_bytes, cudaMemcpyDeviceToHost, s.stream));
         if (docs && nb) SPB_CUDA(cudaMemcpyAsync(docs + b0, s.d_docs, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
-        if (width != 4) {
+        if (count_sat) {
             SPB_CUDA(cudaMemcpyAsync(s.h_sat, s.d_sat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
             s.sat_pending = true;
         }
@@ -285,7 +290,7 @@ int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* of
         if (s.sat_pending) { total_sat += *s.h_sat; s.sat_pending = false; }
     }
     if (opts && opts->saturated) *opts->saturated = total_sat;
-    if (total_sat) return fail(SPB_ERR_OVERFLOW, std::to_string(total_sat) + " length value(s) exceed the " + std::to_string(width) + "-byte output and were clamped; repeat with a wider length_bytes");
+    if (total_sat) return fail(SPB_ERR_OVERFLOW, std::to_string(total_sat) + " value(s) exceed the narrow length / pointer output and were clamped; repeat with wider outputs");
     return SPB_OK;
 }
 
@@ -577,7 +582,7 @@ int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t
     return query_host_text(idx, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
 }
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-                      void* lengths, uint64_t* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
+                      void* lengths, void* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
     return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, nullptr, stats, opts);
 }
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
@@ -605,12 +610,12 @@ int spb_ms_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64
     return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream);
 }
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
-                        void* d_lengths, uint64_t* d_pointers, spb_bin_stats* d_stats,
+                        void* d_lengths, void* d_pointers, spb_bin_stats* d_stats,
                         const spb_query_opts* opts, void* cuda_stream) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, nullptr, d_stats, opts,
+    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, (uint64_t*)d_pointers, nullptr, d_stats, opts,
                         opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
 }
 

@@ -735,7 +735,13 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         {
             const bool last = (gi == base);
             if (DOC) stage_value<4>(s_doc, p.docs, gi, doc, end, last);
-            if (MS) stage_value<8>(s_out, p.pointers, gi, sample, end, last);
+            if (MS) {
+                if (p.ptr32) {  // uniform branch: 32-bit pointer output, anything that does not fit is clamped and counted
+                    uint32_t v = (uint32_t)sample;
+                    if (sample > 0xFFFFFFFEull) { v = 0xFFFFFFFFu; nsat++; }
+                    stage_value<4>(s_out, p.pointers, gi, v, end, last);
+                } else stage_value<8>(s_out, p.pointers, gi, sample, end, last);
+            }
             else {
                 uint32_t v = length;
                 if (OW < 4 && v > VMAX) { v = VMAX; nsat++; }
@@ -764,7 +770,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             }
         }
     }
-    if (OW < 4 && nsat && p.saturated) atomicAdd(p.saturated, (unsigned long long)nsat);
+    if (nsat && p.saturated) atomicAdd(p.saturated, (unsigned long long)nsat);
 }
 
 // MS pointers -> lengths (ms_t::matching_statistics, compute_ms_pml.cpp:795-812) + bin-max classifier
@@ -794,7 +800,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const __
                 continue;
             }
             i = 0; l = 0; prev = 0;
-            ptr = p.pointers[base];
+            ptr = p.ptr32 ? (uint64_t)reinterpret_cast<const uint32_t*>(p.pointers)[base] : p.pointers[base];
             ext = true;
             have = true;
             if (do_stats) {
@@ -853,7 +859,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS) spb_ms_lengths_kernel(const __
             }
             have = false;
         } else {
-            ptr = p.pointers[base + i];
+            ptr = p.ptr32 ? (uint64_t)reinterpret_cast<const uint32_t*>(p.pointers)[base + i] : p.pointers[base + i];
             ext = ptr != prev + 1;
         }
     }
@@ -934,7 +940,7 @@ cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cu
         }
         return e;
     }
-    if (p.out_width != 4 || p.docs) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths only, no document numbers
+    if (p.out_width != 4 || p.docs || p.ptr32) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths / u64 pointers only, no document numbers
     if (launches) *launches = 1;
     switch (lanes) {
         case 4: return ms ? launch_t<4, true>(p, num_sms, stream) : launch_t<4, false>(p, num_sms, stream);

@@ -26,7 +26,8 @@ struct WalkParams {
     const uint64_t* offsets;   // n_reads + 1
     uint64_t n_reads;
     void* lengths;             // u32, or u16 / u8 (thread-per-read kernels, out_width 2 / 1)
-    uint64_t* pointers;        // MS only
+    uint64_t* pointers;        // MS only; uint32_t[] when ptr32 (thread-per-read kernels)
+    uint32_t ptr32;            // MS: write / read 32-bit pointers; values above 2^32 - 2 are clamped and counted
     spb_bin_stats* stats;      // nullable
     uint32_t bin_width;
     uint64_t max_value_thr;

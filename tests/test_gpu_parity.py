@@ -503,3 +503,25 @@ def test_on_device_text_formatting(small_index, monkeypatch, row_width):
         idx.query_host_text(rb, ro, ids, capacity=len(want) - 1)
     assert ei.value.code == 6 and 0 < idx.last_text_bytes <= len(want)
     assert idx.query_host_text(np.zeros(0, np.uint8), np.zeros(1, np.uint64), [])[0] == b""
+
+
+def test_ms_pointers32(small_index, tmp_path, row_width):
+    """SPB_QUERY_POINTERS32: uint32 MS pointers equal the uint64 ones when every value fits; a read with a character absent
+    from the index makes the reference's pointer wrap around (App. C-4), which is reported, never truncated silently."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    ms = sp.ms_t(small_index["ref"])
+    L8, P8, S8 = ms.query_host(buf, off, bin_width=150, max_value_thr=9)
+    clean = int(P8.max()) < (1 << 32) - 1
+    if clean:
+        L4, P4, S4 = ms.query_host(buf, off, bin_width=150, max_value_thr=9, pointer_bytes=4, length_bytes=2)
+        assert P4.dtype == np.uint32 and np.array_equal(P4.astype(np.uint64), P8) and np.array_equal(L4, L8) and np.array_equal(S4, S8)
+    # SURVEY Appendix D: in CCGATNAGATT the N resets the sample to 0 and the matches to its left wrap to 2^64 - 1 ...
+    ms = sp.ms_t(build_index(str(tmp_path), text=b"GATTACAGATTACCGATTAGA"))
+    rb, ro = sp.pack_reads([b"CCGATNAGATT", b"TTACAGGATTAG"])
+    _, Pw, _ = ms.query_host(rb, ro)
+    assert Pw[:5].tolist() == [12, 13, 18446744073709551613, 18446744073709551614, 18446744073709551615]
+    with pytest.raises(sp.SpumoniError) as ei:
+        ms.query_host(rb, ro, pointer_bytes=4)
+    assert ei.value.code == sp.ERR_OVERFLOW and ei.value.saturated == 3
+    with pytest.raises(sp.SpumoniError):
+        ms.query_host(rb, ro, pointer_bytes=4, lanes=8)
