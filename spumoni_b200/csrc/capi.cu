@@ -70,7 +70,7 @@ struct Slot {
 struct spb_index {
     int mode = 0;
     SpbFlatHeader hdr;
-    std::vector<uint8_t> host_blob;
+    spb::FlatBlob host_blob;
     int device = -1;
     const uint8_t* dev_blob = nullptr;
     bool own_dev = false;

@@ -56,20 +56,27 @@ private:
     const uint8_t* end_;
 };
 
-// sdsl::int_vector<w>: bit length, [width byte if w == 0], ceil(bits/64) words
+// sdsl::int_vector<w>: bit length, [width byte if w == 0], ceil(bits/64) words. A view into the file buffer (sections
+// are not 8-byte aligned: words are fetched with memcpy).
 struct PackedInts {
     uint64_t bits = 0;
     uint32_t width = 0;
-    std::vector<uint64_t> words;
+    const uint8_t* raw = nullptr;
     uint64_t count() const { return width ? bits / width : 0; }
+    uint64_t num_words() const { return (bits + 63) / 64; }
+    uint64_t word(uint64_t w) const {
+        uint64_t v;
+        std::memcpy(&v, raw + w * 8, 8);
+        return v;
+    }
     uint64_t at(uint64_t i) const {
         const uint64_t b = i * width;
         const uint32_t sh = (uint32_t)(b & 63);
-        uint64_t v = words[b >> 6] >> sh;
-        if (sh + width > 64) v |= words[(b >> 6) + 1] << (64 - sh);
+        uint64_t v = word(b >> 6) >> sh;
+        if (sh + width > 64) v |= word((b >> 6) + 1) << (64 - sh);
         return width >= 64 ? v : v & ((uint64_t(1) << width) - 1);
     }
-    bool bit(uint64_t i) const { return (words[i >> 6] >> (i & 63)) & 1u; }
+    bool bit(uint64_t i) const { return (word(i >> 6) >> (i & 63)) & 1u; }
 };
 
 PackedInts read_packed(ByteReader& in, uint32_t fixed_width) {
@@ -79,11 +86,14 @@ PackedInts read_packed(ByteReader& in, uint32_t fixed_width) {
     if (v.width == 0 || v.width > 64) throw FormatError("int_vector with invalid width");
     const uint64_t nwords = (v.bits + 63) / 64;
     if (nwords > in.remaining() / 8) throw FormatError("int_vector longer than file");
-    const uint8_t* src = in.bytes((size_t)nwords * 8);
-    v.words.resize((size_t)nwords + 1, 0);
-    std::memcpy(v.words.data(), src, (size_t)nwords * 8);
+    v.raw = in.bytes((size_t)nwords * 8);
     return v;
 }
+
+// slices of [0, total) for the passes that run on all host cores; the slice count is fixed, so nothing that is
+// computed depends on the number of threads
+constexpr int kSlices = 64;
+inline uint64_t slice_lo(uint64_t total, int c) { return (uint64_t)((unsigned __int128)total * (unsigned)c / kSlices); }
 
 // sdsl::select_support_mcl: only its extent matters (it is an accelerator, not data)
 void skip_select_support(ByteReader& in) {
@@ -98,7 +108,7 @@ void skip_select_support(ByteReader& in) {
 // ri::sparse_sd_vector -> sorted positions of the set bits
 struct SparseBits {
     uint64_t universe = 0;
-    std::vector<uint64_t> ones;
+    RawVec<uint64_t> ones;
 };
 SparseBits read_sparse_bits(ByteReader& in) {
     SparseBits s;
@@ -116,31 +126,50 @@ SparseBits read_sparse_bits(ByteReader& in) {
     skip_select_support(in);
     if (size != s.universe) throw FormatError("sparse_sd_vector: size != universe");
     if (declared && low.width != wl) throw FormatError("sparse_sd_vector: low width != wl");
-    s.ones.reserve((size_t)declared);
-    // Elias-Fano: the i-th set bit of `high` at index b encodes bucket b - i
-    uint64_t seen = 0;
-    const uint64_t hw = (high.bits + 63) / 64;
-    for (uint64_t w = 0; w < hw; w++) {
-        uint64_t word = high.words[w];
-        while (word) {
-            const uint32_t t = (uint32_t)__builtin_ctzll(word);
-            word &= word - 1;
-            const uint64_t b = w * 64 + t;
-            if (b >= high.bits) break;
-            if (seen >= low.count()) throw FormatError("sparse_sd_vector: more high bits than low entries");
-            const uint64_t v = ((b - seen) << wl) | low.at(seen);
-            if (v >= s.universe || (!s.ones.empty() && v <= s.ones.back()))
-                throw FormatError("sparse_sd_vector: positions not increasing / out of universe");
-            s.ones.push_back(v);
-            seen++;
-        }
+    // Elias-Fano: the i-th set bit of `high` at index b encodes bucket b - i. Slices of `high` decode independently once
+    // the number of set bits before each slice is known.
+    const uint64_t hw = high.num_words();
+    auto hword = [&](uint64_t w) {
+        uint64_t x = high.word(w);
+        if (w == hw - 1 && (high.bits & 63)) x &= (uint64_t(1) << (high.bits & 63)) - 1;
+        return x;
+    };
+    uint64_t before[kSlices + 1] = {0};
+#pragma omp parallel for schedule(static) if (hw > 8192)
+    for (int c = 0; c < kSlices; c++) {
+        uint64_t cnt = 0;
+        for (uint64_t w = slice_lo(hw, c), e = slice_lo(hw, c + 1); w < e; w++) cnt += (uint64_t)__builtin_popcountll(hword(w));
+        before[c + 1] = cnt;
     }
-    if (seen != declared) throw FormatError("sparse_sd_vector: declared count != decoded count");
+    for (int c = 0; c < kSlices; c++) before[c + 1] += before[c];
+    if (before[kSlices] > low.count()) throw FormatError("sparse_sd_vector: more high bits than low entries");
+    if (before[kSlices] != declared) throw FormatError("sparse_sd_vector: declared count != decoded count");
+    s.ones.resize((size_t)declared);
+    int bad = 0;
+#pragma omp parallel for schedule(static) reduction(| : bad) if (hw > 8192)
+    for (int c = 0; c < kSlices; c++) {
+        uint64_t seen = before[c];
+        bool ok = true;
+        for (uint64_t w = slice_lo(hw, c), e = slice_lo(hw, c + 1); w < e; w++) {
+            uint64_t word = hword(w);
+            while (word) {
+                const uint64_t b = w * 64 + (uint32_t)__builtin_ctzll(word);
+                word &= word - 1;
+                const uint64_t v = ((b - seen) << wl) | low.at(seen);
+                ok &= v < s.universe && (seen == before[c] || v > s.ones[(size_t)seen - 1]);
+                s.ones[(size_t)seen++] = v;
+            }
+        }
+        bad |= !ok;
+    }
+    for (int c = 1; c < kSlices; c++)  // the first position of a non-empty slice against the last one before it
+        if (before[c] && before[c] < before[c + 1] && s.ones[(size_t)before[c]] <= s.ones[(size_t)before[c] - 1]) bad = 1;
+    if (bad) throw FormatError("sparse_sd_vector: positions not increasing / out of universe");
     return s;
 }
 
 // ri::huff_string (sdsl::wt_huff<>) -> the plain byte string
-std::vector<uint8_t> read_wavelet_string(ByteReader& in) {
+RawVec<uint8_t> read_wavelet_string(ByteReader& in) {
     const uint64_t size = in.u64();
     const uint64_t sigma = in.u64();
     PackedInts bv = read_packed(in, 1);
@@ -171,16 +200,16 @@ std::vector<uint8_t> read_wavelet_string(ByteReader& in) {
             leaves++;
         }
     if (leaves != sigma) throw FormatError("wt_huff: sigma != number of leaves");
-    std::vector<uint8_t> out((size_t)size);
+    RawVec<uint8_t> out((size_t)size);
     if (size == 0) return out;
     if (nnodes == 0) throw FormatError("wt_huff: empty tree for non-empty string");
     // rank directory: ones before each 64-bit word
     const uint64_t nwords = (bv.bits + 63) / 64;
     std::vector<uint64_t> before((size_t)nwords + 1, 0);
-    for (uint64_t w = 0; w < nwords; w++) before[w + 1] = before[w] + (uint64_t)__builtin_popcountll(bv.words[w]);
+    for (uint64_t w = 0; w < nwords; w++) before[w + 1] = before[w] + (uint64_t)__builtin_popcountll(bv.word(w));
     auto rank1 = [&](uint64_t i) {
         uint64_t r = before[i >> 6];
-        if (i & 63) r += (uint64_t)__builtin_popcountll(bv.words[i >> 6] & ((uint64_t(1) << (i & 63)) - 1));
+        if (i & 63) r += (uint64_t)__builtin_popcountll(bv.word(i >> 6) & ((uint64_t(1) << (i & 63)) - 1));
         return r;
     };
     std::vector<uint64_t> node_rank((size_t)nnodes, 0), node_len((size_t)nnodes, 0);
@@ -211,12 +240,12 @@ std::vector<uint8_t> read_wavelet_string(ByteReader& in) {
     return out;
 }
 
-std::vector<uint8_t> slurp(const std::string& path) {
+RawVec<uint8_t> slurp(const std::string& path) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
     if (!f) throw IoError("cannot open " + path);
     const std::streamoff sz = f.tellg();
     f.seekg(0);
-    std::vector<uint8_t> b((size_t)sz);
+    RawVec<uint8_t> b((size_t)sz);
     if (sz && !f.read((char*)b.data(), sz)) throw IoError("cannot read " + path);
     return b;
 }
@@ -227,7 +256,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------
 DecodedIndex parse_index_file(const std::string& path, bool ms) {
-    std::vector<uint8_t> buf = slurp(path);
+    RawVec<uint8_t> buf = slurp(path);
     ByteReader in(buf.data(), buf.size());
     DecodedIndex d;
     try {
@@ -246,73 +275,103 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
         for (int c = 0; c < 256; c++) per_letter[c] = read_sparse_bits(in);
         d.heads = read_wavelet_string(in);
         if (d.heads.size() != d.R) throw FormatError("run_heads.size() != R");
-        // run lengths: the j-th c-run ends at c-local index per_letter[c].ones[j]
-        d.lens.resize((size_t)d.R);
-        std::vector<uint64_t> ord(256, 0);
-        uint64_t total = 0;
-        for (uint64_t k = 0; k < d.R; k++) {
-            const uint8_t c = d.heads[(size_t)k];
-            const SparseBits& s = per_letter[c];
-            const uint64_t j = ord[c]++;
-            if (j >= s.ones.size()) throw FormatError("more runs of a letter than runs_per_letter bits");
-            const uint64_t len = j ? s.ones[(size_t)j] - s.ones[(size_t)j - 1] : s.ones[0] + 1;
-            d.lens[(size_t)k] = len;
-            total += len;
+        const uint64_t R = d.R;
+        // ordinal of every run among the runs of its letter: per-slice letter counts, then an exclusive scan
+        std::vector<uint64_t> ord0((size_t)(kSlices + 1) * 256, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kSlices; c++) {
+            uint64_t* cnt = &ord0[(size_t)(c + 1) * 256];
+            for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) cnt[d.heads[(size_t)k]]++;
         }
-        if (total != d.n) throw FormatError("sum of run lengths != n");
-        for (int c = 0; c < 256; c++) {
-            if (ord[c] != per_letter[c].ones.size()) throw FormatError("runs_per_letter has unused bits");
-            if (per_letter[c].ones.size() && per_letter[c].ones.back() + 1 != per_letter[c].universe)
+        for (int c = 0; c < kSlices; c++)
+            for (int a = 0; a < 256; a++) ord0[(size_t)(c + 1) * 256 + a] += ord0[(size_t)c * 256 + a];
+        const uint64_t* runs_of = &ord0[(size_t)kSlices * 256];  // runs per letter
+        for (int a = 0; a < 256; a++) {
+            if (runs_of[a] > per_letter[a].ones.size()) throw FormatError("more runs of a letter than runs_per_letter bits");
+            if (runs_of[a] != per_letter[a].ones.size()) throw FormatError("runs_per_letter has unused bits");
+            if (per_letter[a].ones.size() && per_letter[a].ones.back() + 1 != per_letter[a].universe)
                 throw FormatError("runs_per_letter universe != letter count");
         }
+        // run lengths: the j-th c-run ends at c-local index per_letter[c].ones[j]
+        d.lens.resize((size_t)R);
+        std::vector<uint64_t> slice_pos((size_t)kSlices + 1, 0), slice_cnt((size_t)kSlices * 256, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kSlices; c++) {
+            uint64_t ord[256];
+            std::memcpy(ord, &ord0[(size_t)c * 256], sizeof(ord));
+            uint64_t* cnt = &slice_cnt[(size_t)c * 256];
+            uint64_t tot = 0;
+            for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) {
+                const uint8_t a = d.heads[(size_t)k];
+                const RawVec<uint64_t>& ones = per_letter[a].ones;
+                const uint64_t j = ord[a]++;
+                const uint64_t len = j ? ones[(size_t)j] - ones[(size_t)j - 1] : ones[0] + 1;
+                d.lens[(size_t)k] = len;
+                cnt[a] += len;
+                tot += len;
+            }
+            slice_pos[(size_t)c + 1] = tot;
+        }
+        for (int c = 0; c < kSlices; c++) slice_pos[(size_t)c + 1] += slice_pos[(size_t)c];
+        if (slice_pos[(size_t)kSlices] != d.n) throw FormatError("sum of run lengths != n");
         {   // `runs` marks the last position of every B-th run (ms_rle_string.hpp:255-256)
             if (runs.universe != d.n) throw FormatError("runs bit vector universe != n");
-            uint64_t pos = 0, t = 0;
-            for (uint64_t k = 0; k < d.R; k++) {
-                pos += d.lens[(size_t)k];
-                if (k % B == B - 1) {
-                    if (t >= runs.ones.size() || runs.ones[(size_t)t] != pos - 1) throw FormatError("runs bit vector disagrees with run lengths");
-                    t++;
+            if (runs.ones.size() < R / B) throw FormatError("runs bit vector disagrees with run lengths");
+            if (runs.ones.size() > R / B) throw FormatError("runs bit vector has extra bits");
+            int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad)
+            for (int c = 0; c < kSlices; c++) {
+                uint64_t pos = slice_pos[(size_t)c];
+                for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) {
+                    pos += d.lens[(size_t)k];
+                    if (k % B == B - 1) bad |= runs.ones[(size_t)(k / B)] != pos - 1;
                 }
             }
-            if (t != runs.ones.size()) throw FormatError("runs bit vector has extra bits");
+            if (bad) throw FormatError("runs bit vector disagrees with run lengths");
         }
         {   // F must equal build_F_ of the decoded runs (compute_ms_pml.cpp:119-147)
             std::vector<uint64_t> cnt(256, 0), F(256, 0);
-            for (uint64_t k = 0; k < d.R; k++) cnt[d.heads[(size_t)k]] += d.lens[(size_t)k];
+            for (int c = 0; c < kSlices; c++)
+                for (int a = 0; a < 256; a++) cnt[a] += slice_cnt[(size_t)c * 256 + a];
             uint64_t acc = 0;
             for (int c = 0; c < 256; c++) { F[c] = acc; acc += cnt[c]; }
             if (F != d.F) throw FormatError("F array disagrees with the run-length BWT");
         }
+        auto unpack = [&](const PackedInts& v, RawVec<uint64_t>& out) {
+            out.resize((size_t)R);
+#pragma omp parallel for schedule(static)
+            for (int64_t k = 0; k < (int64_t)R; k++) out[(size_t)k] = v.at((uint64_t)k);
+        };
         if (ms) {
             PackedInts sl = read_packed(in, 0);
-            if (sl.count() != d.R) throw FormatError("samples_last has != R entries");
-            d.samples_last.resize((size_t)d.R);
-            for (uint64_t k = 0; k < d.R; k++) d.samples_last[(size_t)k] = sl.at(k);
+            if (sl.count() != R) throw FormatError("samples_last has != R entries");
+            unpack(sl, d.samples_last);
         }
         // thr_bv: thresholds of the j-th c-run (j >= 1) is the (j-1)-th bit of thresholds_per_letter[c]
         {
             std::vector<SparseBits> thr(256);
             for (int c = 0; c < 256; c++) thr[c] = read_sparse_bits(in);
-            d.thr.assign((size_t)d.R, 0);
-            std::vector<uint64_t> o(256, 0);
-            for (uint64_t k = 0; k < d.R; k++) {
-                const uint8_t c = d.heads[(size_t)k];
-                const uint64_t j = o[c]++;
-                if (j == 0) continue;
-                if (j - 1 >= thr[c].ones.size()) throw FormatError("fewer thresholds than runs for a letter");
-                d.thr[(size_t)k] = thr[c].ones[(size_t)j - 1];
+            for (int a = 0; a < 256; a++) {
+                const uint64_t want = runs_of[a] ? runs_of[a] - 1 : 0;
+                if (thr[a].ones.size() < want) throw FormatError("fewer thresholds than runs for a letter");
+                if (thr[a].ones.size() != want) throw FormatError("threshold count != runs-1 for a letter");
             }
-            for (int c = 0; c < 256; c++) {
-                const uint64_t want = o[c] ? o[c] - 1 : 0;
-                if (thr[c].ones.size() != want) throw FormatError("threshold count != runs-1 for a letter");
+            d.thr.resize((size_t)R);
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int c = 0; c < kSlices; c++) {
+                uint64_t ord[256];
+                std::memcpy(ord, &ord0[(size_t)c * 256], sizeof(ord));
+                for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) {
+                    const uint8_t a = d.heads[(size_t)k];
+                    const uint64_t j = ord[a]++;
+                    d.thr[(size_t)k] = j ? thr[a].ones[(size_t)j - 1] : 0;
+                }
             }
         }
         if (ms) {
             PackedInts ss = read_packed(in, 0);
-            if (ss.count() != d.R) throw FormatError("samples_start has != R entries");
-            d.samples_start.resize((size_t)d.R);
-            for (uint64_t k = 0; k < d.R; k++) d.samples_start[(size_t)k] = ss.at(k);
+            if (ss.count() != R) throw FormatError("samples_start has != R entries");
+            unpack(ss, d.samples_start);
         }
         if (!in.at_end()) throw FormatError("trailing bytes after the index");
     } catch (FormatError& e) {
@@ -334,7 +393,7 @@ std::string load_reference_text(const std::string& fasta_path) {
 }
 
 NullDb load_null_db(const std::string& path) {
-    std::vector<uint8_t> buf = slurp(path);
+    RawVec<uint8_t> buf = slurp(path);
     ByteReader in(buf.data(), buf.size());
     NullDb db;
     try {
@@ -403,7 +462,7 @@ void save_null_db(const std::string& path, const NullDb& db, const uint32_t* sta
 }
 
 void load_doc_array(const std::string& path, DecodedIndex& d) {
-    std::vector<uint8_t> buf = slurp(path);
+    RawVec<uint8_t> buf = slurp(path);
     ByteReader in(buf.data(), buf.size());
     try {
         const uint64_t num_entries = in.u64();
@@ -412,12 +471,15 @@ void load_doc_array(const std::string& path, DecodedIndex& d) {
         if (num_entries != d.R || sd.count() != d.R || ed.count() != d.R) throw FormatError("document array does not have one entry per BWT run");
         d.doc_start.resize((size_t)d.R);
         d.doc_end.resize((size_t)d.R);
-        for (uint64_t k = 0; k < d.R; k++) {
-            const uint64_t a = sd.at(k), b = ed.at(k);
-            if (a >= 0xFFFFFFFFull || b >= 0xFFFFFFFFull) throw LimitError("document numbers >= 2^32-1 are not supported");
+        int too_big = 0;
+#pragma omp parallel for schedule(static) reduction(| : too_big)
+        for (int64_t k = 0; k < (int64_t)d.R; k++) {
+            const uint64_t a = sd.at((uint64_t)k), b = ed.at((uint64_t)k);
+            too_big |= a >= 0xFFFFFFFFull || b >= 0xFFFFFFFFull;
             d.doc_start[(size_t)k] = (uint32_t)a;
             d.doc_end[(size_t)k] = (uint32_t)b;
         }
+        if (too_big) throw LimitError("document numbers >= 2^32-1 are not supported");
     } catch (FormatError& e) {
         throw FormatError(path + ": " + e.what());
     }
@@ -426,34 +488,78 @@ void load_doc_array(const std::string& path, DecodedIndex& d) {
 // ------------------------------------------------------------------------------------------
 static inline uint32_t pack_hi(uint64_t a, int shift) { return (uint32_t)((a >> 32) & 0xFF) << shift; }
 
-std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std::string& text) {
+FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& text) {
     const uint64_t n = d.n, R = d.R;
     if (n >= SPB_POS_MAX - 1) throw LimitError("BWT length >= 2^40-2 is not supported");
     if (R >= 0xFFFFFFFFull - SPB_RUN_PAD) throw LimitError("more than 2^32-64 runs are not supported");
     if (ms && text.size() + 1 != n) throw FormatError("reference text length + 1 != BWT length (is <prefix>.fa the indexed text?)");
 
-    // per-run tables
-    std::vector<uint64_t> start((size_t)R + 1), lf((size_t)R);
+    // per-run tables, in kSlices contiguous slices of the run range so that every O(R) pass below runs on all host cores
+    const int kChunks = kSlices;
+    auto chunk_lo = [&](int c) -> uint64_t { return slice_lo(R, c); };
+    RawVec<uint64_t> start((size_t)R + 1), lf((size_t)R);
     std::vector<uint64_t> numC(256, 0);
     std::vector<uint32_t> numRunsC(256, 0);
     {
-        uint64_t pos = 0;
-        for (uint64_t k = 0; k < R; k++) {
-            start[(size_t)k] = pos;
-            const uint8_t c = d.heads[(size_t)k];
-            lf[(size_t)k] = d.F[c] + numC[c];
-            numC[c] += d.lens[(size_t)k];
-            numRunsC[c]++;
-            pos += d.lens[(size_t)k];
+        // pass 1: per-slice length sums per head; exclusive scan; pass 2: fill start / lf from the slice's prefix
+        std::vector<uint64_t> sliceC((size_t)(kChunks + 1) * 256, 0), slicePos((size_t)kChunks + 1, 0);
+        std::vector<uint32_t> sliceRuns((size_t)kChunks * 256, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kChunks; c++) {
+            uint64_t* cc = &sliceC[(size_t)(c + 1) * 256];
+            uint32_t* cr = &sliceRuns[(size_t)c * 256];
+            uint64_t tot = 0;
+            for (uint64_t k = chunk_lo(c), e = chunk_lo(c + 1); k < e; k++) {
+                const uint64_t l = d.lens[(size_t)k];
+                cc[d.heads[(size_t)k]] += l;
+                cr[d.heads[(size_t)k]]++;
+                tot += l;
+            }
+            slicePos[(size_t)c + 1] = tot;
+        }
+        for (int c = 0; c < kChunks; c++) {
+            slicePos[(size_t)c + 1] += slicePos[(size_t)c];
+            for (int a = 0; a < 256; a++) {
+                sliceC[(size_t)(c + 1) * 256 + a] += sliceC[(size_t)c * 256 + a];
+                numRunsC[a] += sliceRuns[(size_t)c * 256 + a];
+            }
+        }
+        for (int a = 0; a < 256; a++) numC[a] = sliceC[(size_t)kChunks * 256 + a];
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kChunks; c++) {
+            uint64_t seen[256];
+            for (int a = 0; a < 256; a++) seen[a] = d.F[a] + sliceC[(size_t)c * 256 + a];
+            uint64_t pos = slicePos[(size_t)c];
+            for (uint64_t k = chunk_lo(c), e = chunk_lo(c + 1); k < e; k++) {
+                start[(size_t)k] = pos;
+                const uint8_t a = d.heads[(size_t)k];
+                lf[(size_t)k] = seen[a];
+                seen[a] += d.lens[(size_t)k];
+                pos += d.lens[(size_t)k];
+            }
         }
         start[(size_t)R] = n;
     }
     auto run_of = [&](uint64_t p) -> uint64_t {  // run containing BWT position p (R if p == n)
         return (uint64_t)(std::upper_bound(start.begin(), start.end(), p) - start.begin()) - 1;
     };
-    std::vector<uint32_t> dest((size_t)R);
-#pragma omp parallel for schedule(static)
-    for (int64_t k = 0; k < (int64_t)R; k++) dest[(size_t)k] = (uint32_t)run_of(lf[(size_t)k]);
+    // dest[k] = run holding LF(start of run k). Within one head LF is increasing in k, so after one binary search per
+    // (slice, head) the destination only ever moves forward.
+    RawVec<uint32_t> dest((size_t)R);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < kChunks; c++) {
+        uint64_t cur[256];
+        for (int a = 0; a < 256; a++) cur[a] = ~0ull;
+        for (uint64_t k = chunk_lo(c), e = chunk_lo(c + 1); k < e; k++) {
+            const uint8_t a = d.heads[(size_t)k];
+            const uint64_t p = lf[(size_t)k];
+            uint64_t i = cur[a];
+            if (i == ~0ull) i = run_of(p);
+            else while (start[(size_t)i + 1] <= p) i++;
+            cur[a] = i;
+            dest[(size_t)k] = (uint32_t)i;
+        }
+    }
 
     // compact alphabet
     uint32_t sigma = 0;
@@ -567,7 +673,15 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         }
     }
 
-    std::vector<uint8_t> blob(h.total_bytes, 0);
+    FlatBlob blob(h.total_bytes);
+    {  // zero-fill (padding bytes are part of the image) with every core taking its share of the page faults
+        const int64_t pieces = (int64_t)((h.total_bytes + (4u << 20) - 1) / (4u << 20));
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < pieces; i++) {
+            const size_t a = (size_t)i * (4u << 20);
+            std::memset(blob.data() + a, 0, std::min<size_t>(4u << 20, h.total_bytes - a));
+        }
+    }
     std::memcpy(blob.data(), &h, sizeof(h));
     SpbRunRec* runs = reinterpret_cast<SpbRunRec*>(blob.data() + h.off_runs);
 #pragma omp parallel for schedule(static)
@@ -659,19 +773,31 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
         uint64_t* rows_c = rows8 ? reinterpret_cast<uint64_t*>(blob.data() + h.off_mrows8) : nullptr;
         SpbCharSamp* msamp = (ms && h.off_msamp) ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
         SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
-        // next run (strictly after k) headed by each fast symbol, by a backward sweep
-        std::vector<uint32_t> nxt((size_t)R * num_fast);
+        // next run (strictly after k) headed by each fast symbol: one cheap backward sweep records the state at every slice
+        // boundary, then each slice walks backwards on its own
+        std::vector<uint32_t> edge((size_t)kChunks * 4, 0xFFFFFFFFu);
         {
             uint32_t cur[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-            for (uint64_t k = R; k-- > 0;) {
-                for (uint32_t s = 0; s < num_fast; s++) nxt[(size_t)k * num_fast + s] = cur[s];
-                const uint32_t f = fid[d.heads[(size_t)k]];
-                if (f < SPB_SYM_SLOW) cur[f] = (uint32_t)k;
+            int c = kChunks - 1;
+            for (uint64_t k = R;; k--) {  // invariant: cur = next fast runs at index >= k
+                while (c >= 0 && chunk_lo(c + 1) == k) {
+                    for (int s = 0; s < 4; s++) edge[(size_t)c * 4 + s] = cur[s];
+                    c--;
+                }
+                if (k == 0) break;
+                const uint32_t f = fid[d.heads[(size_t)k - 1]];
+                if (f < SPB_SYM_SLOW) cur[f] = (uint32_t)(k - 1);
             }
         }
-#pragma omp parallel for schedule(static)
-        for (int64_t kk = 0; kk < (int64_t)R; kk++) {
-            const uint64_t k = (uint64_t)kk;
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kChunks; c++) {
+        uint32_t nxt[4];  // next runs strictly after k
+        for (int s = 0; s < 4; s++) nxt[s] = edge[(size_t)c * 4 + s];
+        for (uint64_t k = chunk_lo(c + 1), lo = chunk_lo(c); k-- > lo;) {
+            struct Advance {  // after row k is built (any exit path), run k becomes the next run of its own head
+                uint32_t* nxt; uint32_t f; uint32_t k;
+                ~Advance() { if (f < SPB_SYM_SLOW) nxt[f] = k; }
+            } advance{nxt, fid[d.heads[(size_t)k]], (uint32_t)k};
             const uint32_t hk = fid[d.heads[(size_t)k]];
             const uint64_t len_k = d.lens[(size_t)k], st = start[(size_t)k];
             const uint64_t de = dest[(size_t)k], delta = lf[(size_t)k] - start[(size_t)de];
@@ -681,7 +807,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                 for (uint32_t s = 0; s < num_fast; s++) {
                     if (s == hk) continue;
                     const uint32_t slot = s - (s > hk ? 1u : 0u);
-                    const uint32_t k2 = nxt[(size_t)k * num_fast + s];
+                    const uint32_t k2 = nxt[s];
                     if (k2 == 0xFFFFFFFFu) {  // no later c-run: thr = n+1 (App. C-6), the jump always goes down
                         thr3[slot] = SPB_MV_THR_ALWAYS;
                         dist3[slot] = 0;
@@ -708,7 +834,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
                     else if (v == SPB_MV_THR_SLOW || v > SPB_MV8_T_MAX || (T != 0 && T != v)) c3 = 3;
                     else { c3 = 2; T = v; }
                     cls |= c3 << (2 * slot);
-                    const uint32_t k2 = nxt[(size_t)k * num_fast + s];
+                    const uint32_t k2 = nxt[s];
                     const uint64_t dd = k2 == 0xFFFFFFFFu ? 0 : std::min<uint64_t>((uint64_t)k2 - k, SPB_MV8_DIST_PROBE);
                     dist |= dd << (3 * slot);
                 }
@@ -724,6 +850,7 @@ std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std:
             r.w = thr3[2] | (dist3[0] << 12) | (dist3[1] << 17) | (dist3[2] << 22) | ((hk > SPB_SYM_SLOW ? SPB_SYM_SLOW : hk) << 27) |
                   ((slow ? 1u : 0u) << 30);
             rows[k] = r;
+        }
         }
         if (rows8) {
             for (uint64_t k = R; k < R + SPB_MV8_ROW_PAD; k++)  // row R = "pos == n": generic step only

@@ -1,8 +1,10 @@
 // Host-side index handling: on-disk format -> decoded arrays -> flat device image.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 #include "flat_index.h"
 
@@ -11,16 +13,29 @@ namespace spb {
 struct IoError : std::runtime_error { explicit IoError(const std::string& m) : std::runtime_error(m) {} };
 struct LimitError : std::runtime_error { explicit LimitError(const std::string& m) : std::runtime_error(m) {} };
 
+// vector whose resize()/sized constructor leaves trivially-constructible elements uninitialised: value-initialising a
+// 400 MB image (or an 80 MB per-run table) is half a second of serial page faults before the first useful store
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = DefaultInitAlloc<U>; };
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+};
+template <class T> using RawVec = std::vector<T, DefaultInitAlloc<T>>;
+using FlatBlob = RawVec<uint8_t>;
+
 // pml_pointers / ms_pointers after decoding every succinct component into plain arrays
 struct DecodedIndex {
     uint64_t n = 0, R = 0, terminator_position = 0;
     std::vector<uint64_t> F;              // 256 entries
-    std::vector<uint8_t> heads;           // R run heads (bytes <= 1 already stored as 1)
-    std::vector<uint64_t> lens;           // R run lengths
-    std::vector<uint64_t> thr;            // R thresholds (BWT positions; 0 for the first run of a letter)
-    std::vector<uint64_t> samples_start;  // MS: R text positions
-    std::vector<uint64_t> samples_last;   // MS: R text positions
-    std::vector<uint32_t> doc_start, doc_end;  // -d: R document numbers each (DocumentArray), empty otherwise
+    RawVec<uint8_t> heads;                // R run heads (bytes <= 1 already stored as 1)
+    RawVec<uint64_t> lens;                // R run lengths
+    RawVec<uint64_t> thr;                 // R thresholds (BWT positions; 0 for the first run of a letter)
+    RawVec<uint64_t> samples_start;       // MS: R text positions
+    RawVec<uint64_t> samples_last;        // MS: R text positions
+    RawVec<uint32_t> doc_start, doc_end;  // -d: R document numbers each (DocumentArray), empty otherwise
 };
 
 struct NullDb {
@@ -36,7 +51,7 @@ NullDb summarize_null_stats(const uint32_t* stats, uint64_t n);
 void save_null_db(const std::string& path, const NullDb& db, const uint32_t* stats);
 // DocumentArray::load (/root/reference/src/doc_array.cpp:197-201) into d.doc_start / d.doc_end
 void load_doc_array(const std::string& path, DecodedIndex& d);
-std::vector<uint8_t> build_flat_image(const DecodedIndex& d, bool ms, const std::string& text);
+FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& text);
 void validate_flat_image(const void* blob, uint64_t bytes);
 
 }  // namespace spb
