@@ -1,0 +1,3 @@
+// stand-in for the un-vendored sdsl-lite header of the same name (test infrastructure; see ../spumoni_ref_shim.hpp)
+#pragma once
+#include "../spumoni_ref_shim.hpp"
