@@ -8,11 +8,11 @@ over a plain (uncompressed) BWT with naive O(n) rank/select, used to pin the C++
 (``oracle/spumoni_oracle.cpp``) and the CUDA path on hand-sized inputs and on the golden
 vectors of SURVEY.md Appendix D.
 
-PARITY STATUS: **parity unpinned** against the real reference binary -- the reference ships no
-tests, fixtures or golden vectors for this path and cannot be compiled in
-this image (12 un-vendored third-party repositories).  The pins available are SURVEY.md
-Appendix D (survey-generated) and brute-force matching statistics (independent ground truth
-for MS lengths whenever every read character occurs in the index).
+PARITY STATUS: pinned through ``oracle/spumoni_oracle.cpp``, whose outputs are byte-identical to the reference's
+own translation units compiled against stand-ins for its un-vendored third-party headers (``oracle/shim/``,
+``oracle/_ref/spumoni_ref``, ``tests/test_reference_pin.py``); this module is checked against that C++ oracle on
+random cases, against SURVEY.md Appendix D and against brute-force matching statistics. The third-party succinct
+containers themselves remain unpinned.
 
 Reference lines followed (all under /root/reference):
   * pml_pointers::_query      src/compute_ms_pml.cpp:237-286

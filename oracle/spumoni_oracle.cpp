@@ -9,11 +9,16 @@
 // same per-read loops and the same OpenMP batch/critical skeleton, so that it can also serve as
 // the timed CPU baseline (kind = "port").
 //
-// PARITY STATUS: **parity unpinned**.  The reference has no tests/fixtures for this path and
-// cannot be compiled here (its arithmetic lives in un-vendored sdsl-lite / r-index / ShapedSlp,
-// fetched at CMake time: /root/reference/thirdparty/CMakeLists.txt:118-122,159-162,216-220).
-// This file is pinned against oracle/naive.py (literal loops over naive rank/select), the golden
-// vectors of SURVEY.md Appendix D and brute-force matching statistics (tests/test_oracle.py).
+// PARITY STATUS: pinned against the reference's OWN code, with its third-party containers stood in for.
+// The reference has no tests/fixtures for this path and its build cannot run here (12 repositories fetched at
+// CMake time: /root/reference/thirdparty/CMakeLists.txt), but its translation units compile where they lie
+// against stand-ins for the un-vendored sdsl-lite / r-index / ShapedSlp / klib / bonsai headers (oracle/shim/,
+// recipe oracle/Makefile.ref -> oracle/_ref/spumoni_ref). This file's `spumoni run` output is byte-identical to
+// that binary's in every mode (PML/MS x report x document numbers; tests/test_reference_pin.py, committed
+// outputs under tests/golden/reference_run/). What that pin does NOT cover: the succinct containers of
+// sdsl-lite / r-index themselves (the stand-ins answer rank/select by definition) -- "parity unpinned" still
+// holds for SURVEY.md App. A's reconstruction of their byte formats. Further pins: oracle/naive.py, SURVEY.md
+// Appendix D, brute-force matching statistics (tests/test_oracle.py).
 //
 // Reference lines followed (under /root/reference):
 //   pml_pointers::load/_query/LF      src/compute_ms_pml.cpp:222-229, :237-286, :180-187

@@ -2,7 +2,8 @@
 
 The reference ships no golden vectors for this path and cannot be executed
 in this image, so these vectors come from the literal restatement in oracle/naive.py, which
-itself reproduces SURVEY.md Appendix D (checked in tests/test_oracle.py).  "parity unpinned".
+itself reproduces SURVEY.md Appendix D (checked in tests/test_oracle.py). Outputs of the reference's own
+code live next door: tests/golden/reference_run/ (make_reference_golden.py).
 """
 import json
 import os

@@ -211,6 +211,51 @@ def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
     assert "finished processing 300 reads" in r.stderr
 
 
+REFERENCE_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run")
+
+
+@pytest.mark.parametrize("mode,flags", [("P", ["-P", "-c"]), ("Pd", ["-P", "-d"]), ("M", ["-M", "-c"]), ("Md", ["-M", "-d", "-c"])])
+def test_cli_outputs_byte_identical_to_reference(tmp_path, row_width, mode, flags):
+    """The product CLI against files written by the REFERENCE's own code (tests/golden/reference_run, produced by
+    oracle/_ref/spumoni_ref: index, document array and null databases from the reference's build functions, outputs from
+    its `spumoni run`). No oracle in between."""
+    import shutil
+    d = str(tmp_path / "g")
+    shutil.copytree(REFERENCE_GOLDEN, d, ignore=shutil.ignore_patterns("expected"))
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", os.path.join(d, "idx"), "-p", os.path.join(d, "reads.fa"), "-n"] + flags,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    want = os.path.join(REFERENCE_GOLDEN, "expected", mode)
+    names = sorted(os.listdir(want))
+    assert names
+    for f in names:
+        assert open(os.path.join(d, f), "rb").read() == open(os.path.join(want, f), "rb").read(), f
+
+
+def test_abi_values_equal_reference_golden(row_width):
+    """C ABI (host entry points, PML + MS + document numbers) against the integers in the reference-written files."""
+    def parse(path):
+        return [np.array(line.split(), dtype=np.uint64) for line in open(path) if not line.startswith(">")]
+    reads = [line.strip().encode() for line in open(os.path.join(REFERENCE_GOLDEN, "reads.fa")) if not line.startswith(">")]
+    # the last record of the file spans three lines
+    reads = reads[:-3] + [b"".join(reads[-3:])]
+    buf = np.frombuffer(b"".join(reads), dtype=np.uint8)
+    off = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.uint64)
+    ref = os.path.join(REFERENCE_GOLDEN, "idx.fa")
+    pml = sp.pml_t(ref, device=0, use_doc=True)
+    L, _, _, D = pml.query_host_doc(buf, off, toupper=True)
+    want_l = np.concatenate(parse(os.path.join(REFERENCE_GOLDEN, "expected", "Pd", "reads.fa.pseudo_lengths")))
+    want_d = np.concatenate(parse(os.path.join(REFERENCE_GOLDEN, "expected", "Pd", "reads.fa.doc_numbers")))
+    assert np.array_equal(L.astype(np.uint64), want_l) and np.array_equal(D.astype(np.uint64), want_d)
+    ms = sp.ms_t(ref, device=0, use_doc=True)
+    L, P, _, D = ms.query_host_doc(buf, off, toupper=True)
+    want_l = np.concatenate(parse(os.path.join(REFERENCE_GOLDEN, "expected", "Md", "reads.fa.lengths")))
+    want_p = np.concatenate(parse(os.path.join(REFERENCE_GOLDEN, "expected", "Md", "reads.fa.pointers")))
+    want_d = np.concatenate(parse(os.path.join(REFERENCE_GOLDEN, "expected", "Md", "reads.fa.doc_numbers")))
+    assert np.array_equal(L.astype(np.uint64), want_l) and np.array_equal(P.astype(np.uint64), want_p)
+    assert np.array_equal(D.astype(np.uint64), want_d)
+
+
 def test_cli_empty_read_aborts_like_reference(small_index, tmp_path):
     q = str(tmp_path / "q.fa")
     open(q, "w").write(">r_a\nACGT\n>r_b\n>r_c\nACGT\n")

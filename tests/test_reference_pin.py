@@ -1,0 +1,171 @@
+"""Pins the CPU oracle to the reference's OWN code.
+
+oracle/_ref/spumoni_ref = /root/reference's translation units compiled where they lie against stand-ins for its
+un-vendored third-party headers (oracle/shim/, oracle/Makefile.ref). tests/golden/reference_run/ holds what that binary
+wrote for a small index (tests/golden/make_reference_golden.py); those files are committed, so the first group of tests
+runs anywhere. The second group needs the binary (present where /root/reference is, or shipped prebuilt in oracle/_ref/)
+and compares larger, uncommitted fixtures.
+"""
+import ctypes
+import filecmp
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import MKINDEX, ROOT, build_index, mkindex
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_run")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spumoni_ref")
+MODES = {"P": ("pml", True, False, ["-P", "-n", "-c"]), "Pd": ("pml", False, True, ["-P", "-n", "-d"]),
+         "M": ("ms", True, False, ["-M", "-n", "-c"]), "Md": ("ms", True, True, ["-M", "-n", "-d", "-c"])}
+
+
+def _outputs(d, stem):
+    return sorted(f for f in os.listdir(d) if f.startswith(stem + "."))
+
+
+def _assert_same_outputs(got_dir, want_dir, stem):
+    want = _outputs(want_dir, stem)
+    assert want, "no expected outputs in " + want_dir
+    for f in want:
+        assert os.path.exists(os.path.join(got_dir, f)), f + " not written"
+        assert filecmp.cmp(os.path.join(got_dir, f), os.path.join(want_dir, f), shallow=False), f + " differs from the reference's"
+
+
+@pytest.fixture()
+def golden_copy(tmp_path):
+    d = str(tmp_path / "g")
+    shutil.copytree(GOLDEN, d, ignore=shutil.ignore_patterns("expected"))
+    return d
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_oracle_equals_committed_reference_outputs(golden_copy, mode):
+    """oracle `spumoni run` == the files the reference's code wrote (PML/MS x report x document numbers; reads with lower
+    case, N runs, characters absent from the index, one-base reads, the read-id quirk of multi-word headers)."""
+    kind, report, use_doc, _ = MODES[mode]
+    oracle.run(os.path.join(golden_copy, "idx.fa"), os.path.join(golden_copy, "reads.fa"), kind, report=report, use_doc=use_doc)
+    _assert_same_outputs(golden_copy, os.path.join(GOLDEN, "expected", mode), "reads.fa")
+
+
+def test_product_parser_accepts_reference_written_index():
+    """The index files in the golden directory were serialised by the reference's build code: the product's host parser
+    (no GPU needed) must accept them and agree on n and r."""
+    import spumoni_b200 as sp
+    for mode in (sp.MODE_PML, sp.MODE_MS):
+        idx = sp.Index.open(os.path.join(GOLDEN, "idx.fa"), mode, use_doc=True)
+        assert idx.get_bwt_stats() == (2403, 769)
+        assert idx.num_docs() == 2
+        idx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# below: needs the binary
+
+
+@pytest.fixture(scope="session")
+def ref_bin():
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref", "-s"])
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/spumoni_ref is not built (needs /root/reference)")
+    return REF_BIN
+
+
+def _write_slp(ref):
+    with open(ref + ".slp", "w") as f:  # the stand-in for the SLP random-access structure reads the plain text
+        f.write("".join(line.strip() for line in open(ref) if not line.startswith(">")))
+
+
+def _run_ref(ref_bin, ref, reads, flags):
+    subprocess.run([ref_bin, "run", "-r", ref[:-3], "-p", reads] + flags, check=True, capture_output=True)
+
+
+def test_reference_binary_reproduces_committed_outputs(ref_bin, golden_copy):
+    _write_slp(os.path.join(golden_copy, "idx.fa"))
+    for mode, (_, _, _, flags) in MODES.items():
+        _run_ref(ref_bin, os.path.join(golden_copy, "idx.fa"), os.path.join(golden_copy, "reads.fa"), flags)
+        _assert_same_outputs(golden_copy, os.path.join(GOLDEN, "expected", mode), "reads.fa")
+        for f in _outputs(golden_copy, "reads.fa"):
+            os.remove(os.path.join(golden_copy, f))
+
+
+@pytest.fixture(scope="session")
+def pinned_index(ref_bin, tmp_path_factory):
+    """40 kb pangenome (+revcomp, 3 documents) whose index files, document array and null databases are all written by
+    the reference's code from mkindex's PFP-style intermediates; 400 mixed reads."""
+    d = str(tmp_path_factory.mktemp("pinned"))
+    mkindex("genome", "--kind", "pangenome", "--len", 20000, "--haps", 4, "--snp", 0.01, "--indel", 0.001, "--seed", 23,
+            "--out", os.path.join(d, "raw.fa"))
+    ref = build_index(d, fasta=os.path.join(d, "raw.fa"), revcomp=True, keep=True, docs=3)
+    mk = {}
+    for ext in (".thrbv.spumoni", ".thrbv.ms", ".doc"):
+        mk[ext] = open(ref + ext, "rb").read()
+        os.remove(ref + ext)
+    out = subprocess.check_output([ref_bin, "x-build-pml", ref], text=True)
+    runs = int(out.split()[3])
+    subprocess.check_call([ref_bin, "x-build-ms", ref], stdout=subprocess.DEVNULL)
+    subprocess.check_call([ref_bin, "x-doc", ref, str(runs)])
+    _write_slp(ref)
+    reads = os.path.join(d, "reads.fa")
+    mkindex("reads", "--ref", ref, "--n", 400, "--len", 30, "--len-max", 500, "--sub", 0.05, "--ins", 0.01, "--del", 0.01,
+            "--neg-frac", 0.3, "--seed", 5, "--out", reads, "--bin", os.path.join(d, "reads.bin"))
+    null_reads = os.path.join(d, "null.fa")
+    mkindex("reads", "--ref", ref, "--n", 60, "--len", 150, "--len-max", 150, "--sub", 0.0, "--ins", 0.0, "--del", 0.0,
+            "--neg-frac", 0.0, "--seed", 6, "--out", null_reads, "--bin", os.path.join(d, "null.bin"))
+    db = {}
+    for kind in ("pml", "ms"):
+        db[kind] = subprocess.check_output([ref_bin, "x-nulldb", ref, null_reads, kind, "150"], text=True,
+                                           stderr=subprocess.DEVNULL).split()
+    return {"dir": d, "ref": ref, "reads_fa": reads, "null_bin": os.path.join(d, "null.bin"), "mkindex_bytes": mk, "db": db,
+            "runs": runs}
+
+
+def test_reference_serialisation_equals_fixture_builder(pinned_index):
+    """pml_pointers / ms_pointers constructors + serialize (compute_ms_pml.cpp:43-80, :192-213, :355-400, :517-542), thr_bv
+    (thresholds_ds.hpp:384-440) and DocumentArray (doc_array.cpp:18-108) run by the reference write the very bytes
+    tools/mkindex writes: the fixture builder's reading of the reference's build side is right."""
+    for ext, data in pinned_index["mkindex_bytes"].items():
+        assert open(pinned_index["ref"] + ext, "rb").read() == data, ext
+
+
+@pytest.mark.parametrize("mode", sorted(MODES))
+def test_oracle_equals_reference_binary(ref_bin, pinned_index, tmp_path, mode):
+    kind, report, use_doc, flags = MODES[mode]
+    reads = str(tmp_path / "reads.fa")
+    shutil.copy(pinned_index["reads_fa"], reads)
+    _run_ref(ref_bin, pinned_index["ref"], reads, flags)
+    want = str(tmp_path / "want")
+    os.makedirs(want)
+    for f in _outputs(str(tmp_path), "reads.fa"):
+        shutil.move(str(tmp_path / f), os.path.join(want, f))
+    oracle.run(pinned_index["ref"], reads, kind, report=report, use_doc=use_doc)
+    _assert_same_outputs(str(tmp_path), want, "reads.fa")
+
+
+@pytest.mark.parametrize("kind", ["pml", "ms"])
+def test_oracle_null_database_equals_reference(pinned_index, kind):
+    """EmpNullDatabase as the reference builds it (reversed, upper-cased null reads -> statistics -> mean, percentile,
+    packed vector) against the oracle's generator on the same reads; ks_stat_threshold is rand()-driven in the
+    reference and caller-supplied here, so it is the one field left out."""
+    from conftest import load_bin_reads
+    buf, off = load_bin_reads(pinned_index["null_bin"])
+    o = oracle.OracleIndex(pinned_index["ref"], kind)
+    stats, mean, perc = o.nulldb_generate(buf, off)
+    rep = pinned_index["db"][kind]  # num_values N ks_stat_threshold T mean M percentile P
+    assert int(rep[1]) == len(stats)
+    assert float(rep[5]) == mean and float(rep[7]) == perc
+    raw = open(pinned_index["ref"] + (".pmlnulldb" if kind == "pml" else ".msnulldb"), "rb").read()
+    assert np.frombuffer(raw[:8], dtype="<u8")[0] == len(stats)
+    assert np.frombuffer(raw[16:32], dtype="<f8").tolist() == [mean, perc]
+    bits = int(np.frombuffer(raw[32:40], dtype="<u8")[0])
+    width = raw[40]
+    assert bits == len(stats) * width
+    words = np.frombuffer(raw[41:], dtype="<u8")
+    got = [int((int(words[(i * width) >> 6]) >> ((i * width) & 63) | (int(words[((i * width) >> 6) + 1]) << (64 - ((i * width) & 63))
+                if ((i * width) & 63) + width > 64 else 0)) & ((1 << width) - 1)) for i in range(len(stats))]
+    assert got == [int(s) for s in stats]
