@@ -6,7 +6,9 @@ Workload (BASELINE.json configs[1]): PML on a 100 Mb pangenome index (20 x 5 Mb 
 10 % negatives) per GPU.  A "step" is one pass of the hot path over the rank's 1 M reads (1e9 bases).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          this repo's CUDA path
-  python bench.py --impl reference [--gpus N] ...              the CPU path (oracle port), all host threads
+  python bench.py --impl reference [--gpus N] ...              the reference's own CPU code (oracle/_ref/spumoni_ref: its translation
+                                                               units over stand-in third-party containers) when that binary was
+                                                               built, else the oracle port; all host threads
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what each key means.
 """
@@ -16,6 +18,7 @@ import argparse
 import hashlib
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -27,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 MKINDEX = os.path.join(ROOT, "tools", "bin", "spumoni_mkindex")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spumoni_ref")  # built where /root/reference exists; travels prebuilt to the GPU box
 
 BYTES_PER_BASE = {"pml": 69,   # 1 B read + 4 B length + 2 x 32 B index sectors
                   "ms": 117}   # + 8 B pointer + 8 B SA sample + 32 B text sector
@@ -172,9 +176,47 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def reference_binary_seconds(ref, buf, off, n_reads, mode, threads):
+    """One `spumoni run -n -t threads` of the REFERENCE's own code (oracle/_ref/spumoni_ref) over the first n_reads reads:
+    FASTA in, text files out, as the reference does it. Returns the seconds of its own "processing the patterns/reads"
+    timer (compute_ms_pml.cpp:1324-1337, :1365-1378; index loading is outside it), or None without the binary."""
+    if not os.path.exists(REF_BIN):
+        return None
+    d = os.path.dirname(ref)
+    fa = os.path.join(d, f"sample_{n_reads}.fa")
+    if not os.path.exists(fa):
+        with open(fa + ".tmp", "wb") as f:
+            for i in range(n_reads):
+                f.write(b">r%d\n" % i)
+                f.write(buf[int(off[i]): int(off[i + 1])].tobytes())
+                f.write(b"\n")
+        os.replace(fa + ".tmp", fa)
+    db = ref + (".pmlnulldb" if mode == "pml" else ".msnulldb")  # loaded by every run, used only with -c
+    if not os.path.exists(db):
+        stats = os.path.join(d, "null_stats.bin")
+        ((np.arange(1, 2000, dtype=np.uint64) * 7) % 23).tofile(stats)
+        subprocess.check_call([MKINDEX, "nulldb", "--stats", stats, "--out", db], stdout=subprocess.DEVNULL)
+    if mode == "ms" and not os.path.exists(ref + ".slp"):  # the stand-in for the SLP reads the plain text
+        with open(ref) as src, open(ref + ".slp.tmp", "w") as dst:
+            for line in src:
+                if not line.startswith(">"):
+                    dst.write(line.strip())
+        os.replace(ref + ".slp.tmp", ref + ".slp")
+    r = subprocess.run([REF_BIN, "run", "-r", ref[:-3], "-p", fa, "-P" if mode == "pml" else "-M", "-n", "-t", str(threads)],
+                       capture_output=True, text=True)
+    for ext in (".pseudo_lengths", ".lengths", ".pointers"):
+        if os.path.exists(fa + ext):
+            os.remove(fa + ext)
+    m = re.search(r"processing the (?:patterns|reads)[^(]*\(([0-9.]+) sec\)", r.stderr)
+    if r.returncode != 0 or not m:
+        raise SystemExit("bench.py: oracle/_ref/spumoni_ref failed:\n" + r.stderr[-2000:])
+    return float(m.group(1))
+
+
 def run_reference(args, name):
-    """Reference arm: the CPU path (oracle port of compute_ms_pml.cpp:237-286) on all host threads.
-    Each step is a bounded sample of the same workload."""
+    """Reference arm: the reference's own CPU code on all host threads (oracle/_ref/spumoni_ref, `kind: "reference"`) when
+    that binary exists, else the oracle port of compute_ms_pml.cpp:237-286 (`kind: "port"`). Each step is a bounded
+    sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -187,21 +229,33 @@ def run_reference(args, name):
     sample_reads = min(len(off) - 1, max(200, (1000 if mode == "pml" else 400) * cores * 1000 // w["read_len"]))
     idx = oracle.OracleIndex(ref, mode)
     sb, so = buf[: int(off[sample_reads])], off[: sample_reads + 1]
+    use_bin = os.path.exists(REF_BIN)
     for _ in range(args.warmup):
-        idx.query_batch(sb[: int(so[max(1, sample_reads // 10)])], so[: max(1, sample_reads // 10) + 1], threads=cores, want_output=False)
+        if use_bin:
+            reference_binary_seconds(ref, buf, off, max(1, sample_reads // 10), mode, cores)
+        else:
+            idx.query_batch(sb[: int(so[max(1, sample_reads // 10)])], so[: max(1, sample_reads // 10) + 1], threads=cores, want_output=False)
     secs = []
     for _ in range(args.steps):
-        s, _, _ = idx.query_batch(sb, so, threads=cores, want_output=False)
-        secs.append(s)
+        if use_bin:
+            secs.append(reference_binary_seconds(ref, buf, off, sample_reads, mode, cores))
+        else:
+            secs.append(idx.query_batch(sb, so, threads=cores, want_output=False)[0])
     total = sum(secs)
     value = int(so[-1]) * args.steps / total
+    port_sec = idx.query_batch(sb, so, threads=cores, want_output=False)[0] if use_bin else None
+    sample = (f"first {sample_reads} reads of the workload, {args.steps} steps; " +
+              ("`spumoni run -n -t %d` of the reference's own translation units compiled against stand-in third-party containers "
+               "(oracle/shim), FASTA in / text out, its own phase timer" % cores if use_bin
+               else "oracle port, in-memory, OpenMP dynamic over reads"))
     out = {"impl": "reference", "metric": METRICS[mode], "value": value, "unit": "bases/s", "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
            "config": {"workload": w["desc"].replace("PML", mode.upper()), "sample": f"first {sample_reads} reads ({int(so[-1])} bases) per step"},
-           "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "port",
-                            "sample": f"first {sample_reads} reads of the workload, {args.steps} steps, in-memory, OpenMP dynamic over reads"},
+           "cpu_baseline": {"value": value, "unit": "bases/s", "cores": cores, "kind": "reference" if use_bin else "port", "sample": sample},
            "e2e": {"value": value, "unit": "bases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if port_sec:
+        out["oracle_port"] = {"value": int(so[-1]) / port_sec, "unit": "bases/s", "cores": cores, "sample": "same reads, in-memory, one step"}
     emit(out)
 
 
@@ -365,6 +419,12 @@ def main():
         parity = {"reads_checked": sample_reads, "bases_checked": sb, "mismatches": mism, "host_equals_device_path": same}
         cpu_baseline = {"value": sb / sec, "unit": "bases/s", "cores": cores, "kind": "port",
                         "sample": f"first {sample_reads} reads ({sb} bases) of the same workload, in-memory, OpenMP over reads"}
+        ref_sec = reference_binary_seconds(ref, buf, off, sample_reads, mode, cores)
+        if ref_sec:  # the reference's own code when it was built: that is the baseline, the port stays next to it
+            cpu_baseline = {"value": sb / ref_sec, "unit": "bases/s", "cores": cores, "kind": "reference",
+                            "sample": f"first {sample_reads} reads ({sb} bases) of the same workload through `spumoni run -n -t {cores}` of the "
+                                      "reference's own translation units (oracle/_ref, stand-in third-party containers), its own phase timer",
+                            "oracle_port": cpu_baseline["value"]}
         if mism or not same:
             raise SystemExit(f"bench.py: PARITY FAILURE vs oracle: {parity}")
 

@@ -241,14 +241,20 @@ public:
     explicit sparse_sd_vector(const std::vector<bool>& b) : u_(b.size()) {
         for (size_t i = 0; i < b.size(); i++)
             if (b[i]) ones_.push_back(i);
+        index();
     }
-    sparse_sd_vector(const std::vector<ulint>& onset, ulint universe) : u_(universe), ones_(onset) {}
+    sparse_sd_vector(const std::vector<ulint>& onset, ulint universe) : u_(universe), ones_(onset) { index(); }
     ulint size() const { return u_; }
     ulint number_of_1() const { return ones_.size(); }
     bool operator[](ulint i) const { return std::binary_search(ones_.begin(), ones_.end(), i); }
     bool at(ulint i) const { return (*this)[i]; }
-    // ones in [0, i)
-    ulint rank(ulint i) const { return (ulint)(std::lower_bound(ones_.begin(), ones_.end(), i) - ones_.begin()); }
+    // ones in [0, i): the bucket of i's high bits bounds the search to the few ones that share them
+    ulint rank(ulint i) const {
+        if (ones_.empty()) return 0;
+        if (i >= u_) return ones_.size();
+        const ulint h = i >> shift_;
+        return (ulint)(std::lower_bound(ones_.begin() + bucket_[h], ones_.begin() + bucket_[h + 1], i) - ones_.begin());
+    }
     // position of the i-th one (0-based)
     ulint select(ulint i) const { return ones_.at((size_t)i); }
     // position of the last one at or before i, as a rank: number of ones in [0, i] minus one (there must be one)
@@ -268,6 +274,7 @@ public:
     void load(std::istream& in) {
         using namespace sdsl::shim_detail;
         ones_.clear();
+        bucket_.clear();
         u_ = get_u64(in);
         const uint64_t declared = get_u64(in);
         if (u_ == 0) return;
@@ -284,24 +291,40 @@ public:
                 seen++;
             }
         if (seen != declared) throw std::runtime_error("shim: sd_vector count mismatch");
+        index();
     }
 private:
+    // bucket_[h] = number of ones whose value >> shift_ is < h (about one bucket per one); built with the vector, read-only afterwards
+    void index() {
+        shift_ = 0;
+        while ((u_ >> shift_) > 2 * ones_.size() + 1) shift_++;
+        std::vector<ulint> b((size_t)(u_ >> shift_) + 3, 0);
+        for (ulint v : ones_) b[(size_t)(v >> shift_) + 1]++;
+        for (size_t k = 1; k < b.size(); k++) b[k] += b[k - 1];
+        bucket_.swap(b);
+    }
     ulint u_ = 0;
     std::vector<ulint> ones_;
+    std::vector<ulint> bucket_;
+    uint32_t shift_ = 0;
 };
 typedef sparse_sd_vector sparse_hyb_vector;  // only named in a typedef of the reference, never instantiated
 
 // byte string with rank / select per symbol (sdsl::wt_huff<> on disk)
 class huff_string {
 public:
-    huff_string() {}
+    huff_string() { index(); }
     explicit huff_string(const std::string& s) : s_(s.begin(), s.end()) { index(); }
     uchar operator[](ulint i) const { return s_[(size_t)i]; }
     ulint size() const { return s_.size(); }
-    // occurrences of c in [0, i)
+    // occurrences of c in [0, i): count sampled every kBlock positions + a scan of the block
     ulint rank(ulint i, uchar c) const {
-        const std::vector<ulint>& p = occ_[c];
-        return (ulint)(std::lower_bound(p.begin(), p.end(), i) - p.begin());
+        const int slot = slot_[c];
+        if (slot < 0) return 0;
+        const size_t blk = (size_t)(i / kBlock);
+        ulint r = sampled_[blk * nslots_ + (size_t)slot];
+        for (size_t j = blk * kBlock; j < i; j++) r += s_[j] == c;
+        return r;
     }
     // position of the i-th c (0-based)
     ulint select(ulint i, uchar c) const { return occ_[c].at((size_t)i); }
@@ -360,12 +383,25 @@ public:
         index();
     }
 private:
+    static const size_t kBlock = 32;
     void index() {
         for (auto& p : occ_) p.clear();
         for (size_t i = 0; i < s_.size(); i++) occ_[s_[i]].push_back(i);
+        nslots_ = 0;
+        for (int c = 0; c < 256; c++) slot_[c] = occ_[c].empty() ? -1 : (int)nslots_++;
+        sampled_.assign((s_.size() / kBlock + 1) * nslots_, 0);
+        std::vector<ulint> cnt(nslots_, 0);
+        for (size_t i = 0; i < s_.size(); i++) {
+            if (i % kBlock == 0) std::copy(cnt.begin(), cnt.end(), sampled_.begin() + (i / kBlock) * nslots_);
+            cnt[(size_t)slot_[s_[i]]]++;
+        }
+        if (s_.size() % kBlock == 0 && nslots_) std::copy(cnt.begin(), cnt.end(), sampled_.begin() + (s_.size() / kBlock) * nslots_);
     }
     std::vector<uint8_t> s_;
     std::vector<ulint> occ_[256];
+    std::vector<ulint> sampled_;
+    int slot_[256];
+    size_t nslots_ = 0;
 };
 
 // run-length encoded string: heads + per-letter run ends + every B-th run end
