@@ -24,7 +24,10 @@ MKINDEX = os.path.join(ROOT, "tools", "bin", "spumoni_mkindex")
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spumoni_ref")
 OUT = os.path.join(ROOT, "tests", "golden", "reference_run")
 
-MODES = {"P": ["-P", "-n", "-c"], "Pd": ["-P", "-n", "-d"], "M": ["-M", "-n", "-c"], "Md": ["-M", "-n", "-d", "-c"]}
+MODES = {"P": ("reads.fa", ["-P", "-n", "-c"]), "Pd": ("reads.fa", ["-P", "-n", "-d"]), "M": ("reads.fa", ["-M", "-n", "-c"]),
+         "Md": ("reads.fa", ["-M", "-n", "-d", "-c"]),
+         # general text (-g): reads separated by 0x01, used verbatim (no upper-casing), ids are read_<i>
+         "Pg": ("general.txt", ["-P", "-n", "-g"]), "Mg": ("general.txt", ["-M", "-n", "-g"])}
 
 
 def fasta_text(path):
@@ -78,6 +81,12 @@ def main():
         open(ref + ".slp", "w").write(text)  # the shim's random-access text (stands in for the SLP grammar)
         reads = os.path.join(d, "reads.fa")
         write_reads(reads, text, rng)
+        general = os.path.join(d, "general.txt")
+        with open(general, "wb") as f:
+            for seq in (text[50:170], text[200:260].lower(), "ACGT\nACGT", ">not a header", text[300:330] + "N" + text[331:380], "A", "",
+                        text[400:1000], "GATTACA" * 9, "acgtACGTxyz", text[-80:]):
+                f.write(seq.encode() + b"\x01")
+            f.write(b"trailing bytes without a separator are not a read")
         null_reads = os.path.join(d, "null_reads.fa")
         with open(null_reads, "w") as f:
             for i in range(12):
@@ -90,15 +99,15 @@ def main():
         shutil.rmtree(OUT, ignore_errors=True)
         os.makedirs(OUT)
         for name in ("idx.fa", "idx.fa.fdi", "idx.fa.thrbv.spumoni", "idx.fa.thrbv.ms", "idx.fa.doc", "idx.fa.pmlnulldb",
-                     "idx.fa.msnulldb", "reads.fa", "null_reads.fa"):
+                     "idx.fa.msnulldb", "reads.fa", "general.txt", "null_reads.fa"):
             shutil.copy(os.path.join(d, name), os.path.join(OUT, name))
-        for mode, flags in MODES.items():
-            subprocess.check_call([REF_BIN, "run", "-r", os.path.join(d, "idx"), "-p", reads] + flags,
+        for mode, (pattern, flags) in MODES.items():
+            subprocess.check_call([REF_BIN, "run", "-r", os.path.join(d, "idx"), "-p", os.path.join(d, pattern)] + flags,
                                   stderr=subprocess.DEVNULL, stdout=subprocess.DEVNULL)
             dst = os.path.join(OUT, "expected", mode)
             os.makedirs(dst)
             for f in sorted(os.listdir(d)):
-                if f.startswith("reads.fa."):
+                if f.startswith(pattern + "."):
                     shutil.move(os.path.join(d, f), os.path.join(dst, f))
         with open(os.path.join(OUT, "README.txt"), "w") as f:
             f.write("Written by tests/golden/make_reference_golden.py from oracle/_ref/spumoni_ref (the reference's own code).\n"

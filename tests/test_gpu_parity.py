@@ -214,7 +214,8 @@ def test_cli_outputs_byte_identical_to_oracle(small_index, tmp_path, flags):
 REFERENCE_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_run")
 
 
-@pytest.mark.parametrize("mode,flags", [("P", ["-P", "-c"]), ("Pd", ["-P", "-d"]), ("M", ["-M", "-c"]), ("Md", ["-M", "-d", "-c"])])
+@pytest.mark.parametrize("mode,flags", [("P", ["-P", "-c"]), ("Pd", ["-P", "-d"]), ("M", ["-M", "-c"]), ("Md", ["-M", "-d", "-c"]),
+                                        ("Pg", ["-P", "-g"]), ("Mg", ["-M", "-g"])])
 def test_cli_outputs_byte_identical_to_reference(tmp_path, row_width, mode, flags):
     """The product CLI against files written by the REFERENCE's own code (tests/golden/reference_run, produced by
     oracle/_ref/spumoni_ref: index, document array and null databases from the reference's build functions, outputs from
@@ -222,7 +223,8 @@ def test_cli_outputs_byte_identical_to_reference(tmp_path, row_width, mode, flag
     import shutil
     d = str(tmp_path / "g")
     shutil.copytree(REFERENCE_GOLDEN, d, ignore=shutil.ignore_patterns("expected"))
-    r = subprocess.run([sp.CLI_PATH, "run", "-r", os.path.join(d, "idx"), "-p", os.path.join(d, "reads.fa"), "-n"] + flags,
+    pattern = "general.txt" if "-g" in flags else "reads.fa"  # -g: reads separated by 0x01, used verbatim
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", os.path.join(d, "idx"), "-p", os.path.join(d, pattern), "-n"] + flags,
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     want = os.path.join(REFERENCE_GOLDEN, "expected", mode)

@@ -43,6 +43,31 @@ def golden_copy(tmp_path):
     return d
 
 
+GENERAL = {"Pg": ("pml", ["-P", "-n", "-g"]), "Mg": ("ms", ["-M", "-n", "-g"])}
+
+
+def _oracle_general_text(ref, pattern, kind):
+    """classify_general_reads_* (compute_ms_pml.cpp:1219-1297) over the oracle's per-read query: reads end at 0x01, are used
+    verbatim, bytes after the last separator are dropped; every value is followed by a blank."""
+    o = oracle.OracleIndex(ref, kind)
+    reads = open(pattern, "rb").read().split(b"\x01")[:-1]
+    fmt = lambda v: b"".join(b"%d " % int(x) for x in v) + b"\n"
+    if kind == "pml":
+        body = b"".join(b">read_%d\n" % i + fmt(o.matching_statistics(r)) for i, r in enumerate(reads))
+        open(pattern + ".pseudo_lengths", "wb").write(body)
+    else:
+        res = [o.matching_statistics(r) for r in reads]
+        open(pattern + ".lengths", "wb").write(b"".join(b">read_%d\n" % i + fmt(L) for i, (L, P) in enumerate(res)))
+        open(pattern + ".pointers", "wb").write(b"".join(b">read_%d\n" % i + fmt(P) for i, (L, P) in enumerate(res)))
+
+
+@pytest.mark.parametrize("mode", sorted(GENERAL))
+def test_oracle_equals_committed_reference_outputs_general_text(golden_copy, mode):
+    kind, _ = GENERAL[mode]
+    _oracle_general_text(os.path.join(golden_copy, "idx.fa"), os.path.join(golden_copy, "general.txt"), kind)
+    _assert_same_outputs(golden_copy, os.path.join(GOLDEN, "expected", mode), "general.txt")
+
+
 @pytest.mark.parametrize("mode", sorted(MODES))
 def test_oracle_equals_committed_reference_outputs(golden_copy, mode):
     """oracle `spumoni run` == the files the reference's code wrote (PML/MS x report x document numbers; reads with lower
@@ -77,8 +102,8 @@ def ref_bin():
 
 
 def _write_slp(ref):
-    with open(ref + ".slp", "w") as f:  # the stand-in for the SLP random-access structure reads the plain text
-        f.write("".join(line.strip() for line in open(ref) if not line.startswith(">")))
+    with open(ref + ".slp", "wb") as f:  # the stand-in for the SLP random-access structure reads the plain text
+        f.write(b"".join(line.rstrip(b"\r\n") for line in open(ref, "rb") if not line.startswith(b">")))
 
 
 def _run_ref(ref_bin, ref, reads, flags):
@@ -87,10 +112,12 @@ def _run_ref(ref_bin, ref, reads, flags):
 
 def test_reference_binary_reproduces_committed_outputs(ref_bin, golden_copy):
     _write_slp(os.path.join(golden_copy, "idx.fa"))
-    for mode, (_, _, _, flags) in MODES.items():
-        _run_ref(ref_bin, os.path.join(golden_copy, "idx.fa"), os.path.join(golden_copy, "reads.fa"), flags)
-        _assert_same_outputs(golden_copy, os.path.join(GOLDEN, "expected", mode), "reads.fa")
-        for f in _outputs(golden_copy, "reads.fa"):
+    runs = [(mode, "reads.fa", flags) for mode, (_, _, _, flags) in MODES.items()]
+    runs += [(mode, "general.txt", flags) for mode, (_, flags) in GENERAL.items()]
+    for mode, pattern, flags in runs:
+        _run_ref(ref_bin, os.path.join(golden_copy, "idx.fa"), os.path.join(golden_copy, pattern), flags)
+        _assert_same_outputs(golden_copy, os.path.join(GOLDEN, "expected", mode), pattern)
+        for f in _outputs(golden_copy, pattern):
             os.remove(os.path.join(golden_copy, f))
 
 
@@ -169,3 +196,61 @@ def test_oracle_null_database_equals_reference(pinned_index, kind):
     got = [int((int(words[(i * width) >> 6]) >> ((i * width) & 63) | (int(words[((i * width) >> 6) + 1]) << (64 - ((i * width) & 63))
                 if ((i * width) & 63) + width > 64 else 0)) & ((1 << width) - 1)) for i in range(len(stats))]
     assert got == [int(s) for s in stats]
+
+
+@pytest.mark.parametrize("seed,alphabet", [(1, b"ACGT\xe9N"), (2, b"AC"), (3, b"A"), (4, b"ACGTN"), (5, b"\x02\x7f\x80\xffAC"), (6, b"acgtACGT")])
+def test_oracle_equals_reference_binary_on_odd_alphabets(ref_bin, tmp_path, seed, alphabet):
+    """Random texts over small / non-DNA alphabets (bytes >= 0x80 exercise the reference's signed-char comparisons, App. C-1;
+    lower-case text vs upper-cased reads), reads with characters that never occur in the index."""
+    import random
+    rng = random.Random(seed)
+    d = str(tmp_path)
+    text = bytes(rng.choice(alphabet) for _ in range(rng.randint(50, 2500)))
+    ref = build_index(d, text=text)
+    _write_slp(ref)
+    for ext in (".pmlnulldb", ".msnulldb"):
+        shutil.copy(os.path.join(GOLDEN, "idx.fa.pmlnulldb"), ref + ext)
+    pool = bytes(set(alphabet + b"ACGTNY\xe9\xfc"))
+    reads = os.path.join(d, "reads.fa")
+    with open(reads, "wb") as f:
+        for i in range(60):
+            ln = rng.randint(1, 90)
+            if rng.random() < 0.6 and len(text) > ln:
+                s = rng.randint(0, len(text) - ln)
+                r = bytearray(text[s:s + ln])
+                for k in range(len(r)):
+                    if rng.random() < 0.1:
+                        r[k] = rng.choice(pool)
+            else:
+                r = bytearray(rng.choice(pool) for _ in range(ln))
+            f.write(b">r%d\n" % i + bytes(r) + b"\n")
+    want = os.path.join(d, "want")
+    os.makedirs(want)
+    for flags in (["-P", "-n", "-c"], ["-M", "-n", "-c"]):
+        _run_ref(ref_bin, ref, reads, flags)
+        for f in _outputs(d, "reads.fa"):
+            shutil.move(os.path.join(d, f), os.path.join(want, f if not f.endswith(".report") else flags[0] + f))
+    for kind, flag in (("pml", "-P"), ("ms", "-M")):
+        oracle.run(ref, reads, kind, report=True)
+        os.replace(reads + ".report", os.path.join(d, flag + "reads.fa.report"))
+    for f in sorted(os.listdir(want)):
+        assert filecmp.cmp(os.path.join(d, f), os.path.join(want, f), shallow=False), f
+
+
+def test_oracle_equals_reference_binary_multithreaded(ref_bin, pinned_index, tmp_path):
+    """-t 4 on both sides: record order is not deterministic (compute_ms_pml.cpp:1001), the set of records is."""
+    def records(path):
+        rec, cur = {}, None
+        for line in open(path, "rb"):
+            if line.startswith(b">"):
+                cur = line
+            else:
+                rec[cur] = line
+        return rec
+    reads = str(tmp_path / "reads.fa")
+    shutil.copy(pinned_index["reads_fa"], reads)
+    _run_ref(ref_bin, pinned_index["ref"], reads, ["-M", "-n", "-t", "4"])
+    want = {e: records(reads + e) for e in (".lengths", ".pointers")}
+    oracle.run(pinned_index["ref"], reads, "ms", threads=4)
+    for e in want:
+        assert records(reads + e) == want[e] and len(want[e]) == 400
