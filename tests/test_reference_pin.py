@@ -254,3 +254,31 @@ def test_oracle_equals_reference_binary_multithreaded(ref_bin, pinned_index, tmp
     oracle.run(pinned_index["ref"], reads, "ms", threads=4)
     for e in want:
         assert records(reads + e) == want[e] and len(want[e]) == 400
+
+
+def test_flat_image_reproduces_reference_outputs(row_width):
+    """The product's host side (parse of the reference-written index files -> flat device image), walked on the CPU by
+    tests/flat_emulator.py, gives the integers the reference's code wrote: PML, MS pointers + lengths, document numbers.
+    No oracle and no GPU in the loop."""
+    import spumoni_b200 as sp
+    from flat_emulator import FlatImage
+
+    def parse(path):
+        return [[int(x) for x in line.split()] for line in open(path) if not line.startswith(">")]
+    lines = [line.rstrip("\n") for line in open(os.path.join(GOLDEN, "reads.fa")) if not line.startswith(">")]
+    reads = [r.upper().encode() for r in lines[:-3] + ["".join(lines[-3:])]]  # the last record spans three lines; :916-917 upper-cases
+    ref = os.path.join(GOLDEN, "idx.fa")
+    fp = FlatImage(sp.Index.open(ref, sp.MODE_PML, use_doc=True).flat())
+    fm = FlatImage(sp.Index.open(ref, sp.MODE_MS, use_doc=True).flat())
+    assert bool(fp.off_mrows8) == (row_width == "8")
+    want = {k: parse(os.path.join(GOLDEN, "expected", m, "reads.fa." + k)) for m, k in
+            (("Pd", "pseudo_lengths"), ("Pd", "doc_numbers"), ("Md", "lengths"), ("Md", "pointers"))}
+    want_md = parse(os.path.join(GOLDEN, "expected", "Md", "reads.fa.doc_numbers"))
+    assert len(reads) == len(want["pseudo_lengths"])
+    for i, r in enumerate(reads):
+        got, _, _ = fp.walk_rows(r)
+        assert got == want["pseudo_lengths"][i] and fp.docs == want["doc_numbers"][i], i
+        assert fp.walk(r)[0] == want["pseudo_lengths"][i], i
+        _, ptr, _ = fm.walk_rows(r)
+        assert ptr == want["pointers"][i] and fm.docs == want_md[i], i
+        assert fm.ms_lengths(r, ptr) == want["lengths"][i], i
