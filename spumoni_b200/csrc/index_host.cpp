@@ -380,14 +380,46 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
     return d;
 }
 
+// The indexed text: every line of <prefix>.fa that is not a '>' header, trailing white space stripped, concatenated.
+// The file is cut into slices at line starts; each slice is measured, then copied to its final place.
 std::string load_reference_text(const std::string& fasta_path) {
-    std::ifstream f(fasta_path);
-    if (!f) throw IoError("cannot open " + fasta_path);
-    std::string text, line;
-    while (std::getline(f, line)) {
-        if (!line.empty() && line[0] == '>') continue;
-        while (!line.empty() && std::isspace((unsigned char)line.back())) line.pop_back();
-        text += line;
+    const RawVec<uint8_t> buf = slurp(fasta_path);
+    const uint8_t* b = buf.data();
+    const size_t N = buf.size();
+    size_t lo[kSlices + 1];
+    lo[0] = 0;
+    for (int c = 1; c < kSlices; c++) {
+        const size_t p = std::max<size_t>((size_t)slice_lo(N, c), lo[c - 1]);
+        const void* nl = p == 0 ? b : (p - 1 < N ? std::memchr(b + p - 1, '\n', N - (p - 1)) : nullptr);
+        lo[c] = p == 0 ? 0 : (nl ? (size_t)((const uint8_t*)nl - b) + 1 : N);
+    }
+    lo[kSlices] = N;
+    // calls emit(first, length) for the kept part of every line in [from, to)
+    auto for_each_line = [&](size_t from, size_t to, auto&& emit) {
+        for (size_t s0 = from; s0 < to;) {
+            const void* nl = std::memchr(b + s0, '\n', to - s0);
+            size_t e = nl ? (size_t)((const uint8_t*)nl - b) : to;
+            const size_t next = e + 1;
+            if (!(e > s0 && b[s0] == '>')) {
+                while (e > s0 && std::isspace(b[e - 1])) e--;
+                if (e > s0) emit(s0, e - s0);
+            }
+            s0 = next;
+        }
+    };
+    size_t at[kSlices + 1] = {0};
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < kSlices; c++) {
+        size_t kept = 0;
+        for_each_line(lo[c], lo[c + 1], [&](size_t, size_t len) { kept += len; });
+        at[c + 1] = kept;
+    }
+    for (int c = 0; c < kSlices; c++) at[c + 1] += at[c];
+    std::string text(at[kSlices], '\0');
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int c = 0; c < kSlices; c++) {
+        char* dst = &text[0] + at[c];
+        for_each_line(lo[c], lo[c + 1], [&](size_t first, size_t len) { std::memcpy(dst, b + first, len); dst += len; });
     }
     return text;
 }
