@@ -53,8 +53,8 @@ typedef enum {
     SPB_ERR_CUDA = 4,      /* CUDA runtime error (message has the cudaError string) */
     SPB_ERR_NO_DEVICE = 5, /* index not resident on a GPU / no GPU present */
     SPB_ERR_LIMIT = 6,     /* size outside supported range (n >= 2^40-2, r >= 2^32-64, read >= 2^32) */
-    SPB_ERR_OVERFLOW = 7   /* narrow (1/2-byte) length output clamped at least one value; outputs are otherwise complete:
-                              repeat the call with a wider length_bytes */
+    SPB_ERR_OVERFLOW = 7   /* a narrow output (1/2-byte lengths, 32-bit MS pointers) clamped at least one value; outputs are
+                              otherwise complete: repeat the call with a wider length_bytes / without SPB_QUERY_POINTERS32 */
 } spb_status;
 
 typedef enum { SPB_MODE_PML = 0, SPB_MODE_MS = 1 } spb_mode;
