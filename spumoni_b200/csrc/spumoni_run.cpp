@@ -310,6 +310,34 @@ struct Outputs {
     std::ofstream lengths, pointers, report, docs;
 };
 
+// The device-formatted text of a batch lands here. Page-locked (spb_host_alloc) so that the D2H copies of its sub-batches are
+// real DMA transfers that overlap the kernels; allocated once per Work and reused, so the cost of pinning is paid once.
+// SPUMONI_B200_PAGEABLE_TEXT=1 keeps it in ordinary memory.
+class TextArena {
+public:
+    TextArena() = default;
+    TextArena(const TextArena&) = delete;
+    TextArena& operator=(const TextArena&) = delete;
+    ~TextArena() { release(); }
+    void reset(uint64_t bytes) {
+        release();
+        static const bool pageable = std::getenv("SPUMONI_B200_PAGEABLE_TEXT") != nullptr;
+        void* q = nullptr;
+        if (!pageable && spb_host_alloc(&q, (size_t)bytes) == SPB_OK) { p_ = (char*)q; pinned_ = true; }
+        else { p_ = new char[bytes]; pinned_ = false; }
+    }
+    char* get() const { return p_; }
+private:
+    void release() {
+        if (!p_) return;
+        if (pinned_) spb_host_free(p_);
+        else delete[] p_;
+        p_ = nullptr;
+    }
+    char* p_ = nullptr;
+    bool pinned_ = false;
+};
+
 struct Work {
     ReadBatch b;
     std::vector<uint32_t> L;
@@ -321,7 +349,7 @@ struct Work {
     // PML without -d: the .pseudo_lengths bytes come formatted from the device (spb_pml_query_host_text)
     std::vector<uint8_t> idcat;
     std::vector<uint64_t> idoff;
-    std::unique_ptr<char[]> text;
+    TextArena text;
     uint64_t text_cap = 0, text_bytes = 0;
     bool device_text = false;
 };
@@ -359,7 +387,7 @@ static void query_batch(spb_index* idx, bool ms, const RunOptions& o, spb_query_
         if (o.write_report) w.S.resize(nr);
         uint64_t need = b.bases.size() * 3 + w.idcat.size() + 3 * nr + 64;  // typical PML text is ~2 bytes per base
         for (;;) {
-            if (need > w.text_cap) { w.text.reset(new char[need]); w.text_cap = need; }
+            if (need > w.text_cap) { w.text.reset(need); w.text_cap = need; }
             const int rc = spb_pml_query_host_text(idx, b.bases.data(), b.offsets.data(), nr, w.idcat.data(), w.idoff.data(), w.text.get(),
                                                    w.text_cap, &w.text_bytes, o.write_report ? w.S.data() : nullptr, &qo);
             if (rc == SPB_ERR_LIMIT && w.text_bytes > w.text_cap) { need = w.text_bytes + w.text_bytes / 2; continue; }  // rare: redo with a larger buffer
