@@ -1,5 +1,5 @@
 #!/bin/bash
-# CLI text arena: page-locked (default) against pageable (SPUMONI_B200_PAGEABLE_TEXT=1) on 10^9 bases of FASTA
+# CLI text arena: page-locked (SPUMONI_B200_PINNED_TEXT=1) against pageable (default) on 10^9 bases of FASTA
 # (4 Mb pangenome index: the index size only moves the kernel time, which is not what this measures).
 # usage: bash tools/gpu_cli_pinned.sh <tag>
 OUT=gpurun_out/${1:-clip}; mkdir -p $OUT
@@ -11,7 +11,7 @@ $M reads --ref $D/idx.fa --n 1000000 --len 1000 --sub 0.06 --ins 0.02 --del 0.02
 python -c "
 import numpy as np; (np.arange(1,200,dtype=np.uint64)*7%11).tofile('/tmp/stats.bin')" && $M nulldb --stats /tmp/stats.bin --out $D/idx.fa.pmlnulldb
 for mode in pinned pageable pinned pageable; do
-  if [ $mode = pageable ]; then export SPUMONI_B200_PAGEABLE_TEXT=1; else unset SPUMONI_B200_PAGEABLE_TEXT; fi
+  if [ $mode = pinned ]; then export SPUMONI_B200_PINNED_TEXT=1; else unset SPUMONI_B200_PINNED_TEXT; fi
   SPUMONI_B200_TIMING=1 timeout 60 spumoni_b200/bin/spumoni run -r $D/idx -p $D/reads.fa -P -n -c -t 1 2> $OUT/cli_$mode.log
   echo "$mode: $(sed 's/\x1b\[[0-9;]*m//g' $OUT/cli_$mode.log | grep -a 'busy\|processing' | tr '\n' ' ')  md5 $(md5sum < $D/reads.fa.pseudo_lengths | cut -c1-12)" | tee -a $OUT/summary.txt
 done
