@@ -282,3 +282,35 @@ def test_flat_image_reproduces_reference_outputs(row_width):
         _, ptr, _ = fm.walk_rows(r)
         assert ptr == want["pointers"][i] and fm.docs == want_md[i], i
         assert fm.ms_lengths(r, ptr) == want["lengths"][i], i
+
+
+def test_cli_validation_equals_reference_binary(ref_bin, golden_copy, tmp_path):
+    """Option parsing and validation of the product's `spumoni run` against the reference's own spumoni.cpp /
+    spumoni_main.hpp (:267-329): same exit code and, apart from the version banner, the same stderr text. Every case fails
+    (or prints usage) before an index is loaded, so no GPU is involved."""
+    import re
+    import spumoni_b200 as sp
+    P, Q = os.path.join(golden_copy, "idx"), os.path.join(golden_copy, "reads.fa")
+    bad = str(tmp_path / "reads.txt")
+    open(bad, "w").write(">a\nACGT\n")
+    cases = [["run", "-r", P, "-P", "-n"], ["run", "-p", Q, "-P", "-n"], ["run", "-r", P, "-p", Q, "-n"],
+             ["run", "-r", P, "-p", Q, "-n", "-M", "-P"], ["run", "-r", P, "-p", bad, "-P", "-n"],
+             ["run", "-r", P, "-p", Q, "-P", "-n", "-w", "10"], ["run", "-r", P, "-p", Q, "-P", "-n", "-w", "500"],
+             ["run", "-r", P, "-p", Q, "-P"], ["run", "-r", P, "-p", Q, "-P", "-m", "-a"], ["run", "-r", P, "-p", Q, "-P", "-n", "-m"],
+             ["run", "-r", P + "_missing", "-p", Q, "-P", "-n"], ["run", "-r", P, "-p", Q + "_missing.fa", "-P", "-n"],
+             ["run", "-r", P, "-p", Q, "-P", "-n", "-K", "5"], ["run", "-r", P, "-p", Q, "-P", "-n", "-K", "4", "-W", "3"],
+             ["run", "-r", P, "-p", Q, "-P", "-g", "-t", "2"], ["run", "-r", P, "-p", Q, "-P", "-n", "-g", "-t", "2"],
+             ["run", "-r", P, "-p", Q, "-P", "-n", "-g", "-c"], ["run", "-r", P, "-p", Q, "-M", "-n", "-d", "-x"], ["run"], ["run", "-h"]]
+    os.remove(os.path.join(golden_copy, "idx.fa.doc"))
+    cases.append(["run", "-r", P, "-p", Q, "-P", "-n", "-d"])  # document array requested but absent
+    os.remove(os.path.join(golden_copy, "idx.fa.thrbv.ms"))
+    cases.append(["run", "-r", P, "-p", Q, "-M", "-n"])  # index of the requested type absent
+
+    def clean(s):
+        s = re.sub(r"\x1b\[[0-9;]*m", "", s).replace(" (spumoni_b200 query engine)", " ")
+        return "\n".join(line.rstrip() for line in s.strip().splitlines())
+    for c in cases:
+        a = subprocess.run([ref_bin] + c, capture_output=True, text=True)
+        b = subprocess.run([sp.CLI_PATH] + c, capture_output=True, text=True)
+        assert a.returncode == b.returncode, c
+        assert clean(a.stderr) == clean(b.stderr) and a.stdout == b.stdout, (c, clean(a.stderr)[-300:], clean(b.stderr)[-300:])
