@@ -1,0 +1,95 @@
+"""Synthetic run-length BWTs (tools/mkindex `synth`): indexes of any size without a suffix array, serialised like real
+ones. They are not the BWT of a text -- the query path is rank/select/threshold arithmetic and does not care -- so the
+reference's own code, the oracle, the CPU walk of the flat image and the CUDA path must all still agree. This is the
+stand-in for the n > 2^32, r ~ 10^8 configurations (BASELINE configs 4-5). (File name: sorts last, so the round-end
+`pytest -x` reaches it after every other GPU test.)"""
+import filecmp
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+import spumoni_b200 as sp
+from conftest import ROOT, load_bin_reads, mkindex
+from flat_emulator import FlatImage
+
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spumoni_ref")
+SHAPES = {
+    # pangenome-like: short runs, a few long ones; 8 % of the steps jump
+    "typical": ["--runs", 30000, "--mean-len", 20, "--seed", 3, "--n", 300, "--len", 400, "--sub", 0.08],
+    # jump-heavy like the c2 reads (58 % jumps)
+    "jumpy": ["--runs", 30000, "--mean-len", 6, "--seed", 4, "--n", 300, "--len", 400, "--sub", 0.55],
+    # n > 2^32 (40-bit positions in every generic table) with mostly short runs: 3 % of the runs are ~5 * 10^7 long
+    "huge": ["--runs", 6000, "--mean-len", 25, "--tail-frac", 0.03, "--tail-mul", 2000000, "--seed", 5, "--n", 200, "--len", 300,
+             "--sub", 0.1],
+    # runs longer than 2^32: no move rows at all, the generic kernels serve every step
+    "giant": ["--runs", 3000, "--mean-len", 25, "--tail-frac", 0.005, "--tail-mul", 400000000, "--seed", 6, "--n", 100, "--len", 200,
+              "--sub", 0.1],
+}
+
+
+@pytest.fixture(scope="module", params=sorted(SHAPES))
+def synth(request, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("synth_" + request.param))
+    out = mkindex("synth", "--prefix", os.path.join(d, "idx"), "--bin", os.path.join(d, "r.bin"), "--out", os.path.join(d, "reads.fa"),
+                  *SHAPES[request.param])
+    n = int(out.split('"n":')[1].split(",")[0])
+    assert (n > 2 ** 32) == (request.param in ("huge", "giant"))
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "reference_run", "idx.fa.pmlnulldb"), os.path.join(d, "idx.fa.pmlnulldb"))
+    return {"dir": d, "ref": os.path.join(d, "idx.fa"), "reads_fa": os.path.join(d, "reads.fa"), "reads_bin": os.path.join(d, "r.bin"),
+            "shape": request.param}
+
+
+def test_synthetic_oracle_equals_reference_binary(synth, tmp_path):
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref", "-s"])
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/spumoni_ref is not built (needs /root/reference)")
+    reads = str(tmp_path / "reads.fa")
+    shutil.copy(synth["reads_fa"], reads)
+    subprocess.run([REF_BIN, "run", "-r", synth["ref"][:-3], "-p", reads, "-P", "-n", "-c"], check=True, capture_output=True)
+    want = str(tmp_path / "want")
+    os.makedirs(want)
+    for e in (".pseudo_lengths", ".report"):
+        shutil.move(reads + e, os.path.join(want, "reads.fa" + e))
+    oracle.run(synth["ref"], reads, "pml", report=True)
+    for e in (".pseudo_lengths", ".report"):
+        assert filecmp.cmp(reads + e, os.path.join(want, "reads.fa" + e), shallow=False), e
+
+
+def test_synthetic_flat_image_equals_oracle(synth, row_width):
+    buf, off = load_bin_reads(synth["reads_bin"])
+    o = oracle.OracleIndex(synth["ref"], "pml")
+    fi = FlatImage(sp.Index.open(synth["ref"], sp.MODE_PML).flat())
+    assert (fi.num_fast == 0) == (synth["shape"] == "giant")
+    if fi.num_fast:
+        assert bool(fi.off_mrows8) == (row_width == "8")
+    matched = 0
+    for i in range(0, 40):
+        r = bytes(buf[int(off[i]):int(off[i + 1])])
+        want = o.matching_statistics(r).tolist()
+        assert fi.walk(r)[0] == want, i
+        if fi.num_fast:
+            assert fi.walk_rows(r)[0] == want, i
+        matched += sum(1 for v in want if v > 0)
+    assert matched > 1000 or synth["shape"] == "jumpy"  # the generated reads do match in stretches
+
+
+@pytest.mark.gpu
+def test_synthetic_cuda_equals_oracle(synth, row_width):
+    buf, off = load_bin_reads(synth["reads_bin"])
+    _, Lo, _ = oracle.OracleIndex(synth["ref"], "pml").query_batch(buf, off, threads=os.cpu_count() or 1)
+    idx = sp.pml_t(synth["ref"], device=0)
+    L, _, S = idx.query_host(buf, off, bin_width=150, max_value_thr=7)
+    assert np.array_equal(L.astype(np.uint64), Lo)
+    for lanes in (8, 32):  # the cooperative generic kernel on the same image
+        Lg, _, _ = idx.query_host(buf, off, lanes=lanes)
+        assert np.array_equal(Lg, L), lanes
+    # bin-max classifier against the literal restatement
+    from oracle import naive
+    for r in range(0, len(off) - 1, 37):
+        _, summ, above, below, _ = naive.classify_bins(Lo[int(off[r]):int(off[r + 1])].tolist(), 150, 7)
+        assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)

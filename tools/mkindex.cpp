@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cctype>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -364,6 +365,144 @@ static int cmd_reads(const Args& a) {
     return 0;
 }
 
+// ---------------------------------------------------------------- synth
+// A PML index of any size WITHOUT a suffix array: a synthetic run-length BWT (heads over ACGT with one terminator run,
+// run lengths drawn to a target mean with a heavy tail) and a threshold for every run placed somewhere in the gap to the
+// previous run of its letter, serialised exactly like a real one. It is not the BWT of a text, and neither the reference's
+// loops nor ours care: every query is rank / select / threshold arithmetic on these arrays. Reads are produced by running
+// the backward search forward in time and letting it choose the characters (so they match in stretches, like reads sampled
+// with errors from an indexed genome), plus a share of random negatives. This is how the n > 2^32, r ~ 10^8 configurations get a stand-in whose
+// tables have the real sizes; generation is O(r) in time and memory.
+static int cmd_synth(const Args& a) {
+    const std::string prefix = get(a, "prefix"), bin = get(a, "bin"), out = get(a, "out");
+    if (prefix.empty()) die("synth: --prefix required");
+    const uint64_t R = std::stoull(get(a, "runs", "100000")), seed = std::stoull(get(a, "seed", "1"));
+    const double mean_len = std::stod(get(a, "mean-len", "20")), tail = std::stod(get(a, "tail-frac", "0.002"));
+    const uint64_t tail_mul = std::stoull(get(a, "tail-mul", "500"));
+    const uint64_t N = std::stoull(get(a, "n", "0")), L = std::stoull(get(a, "len", "1000"));
+    const double sub = std::stod(get(a, "sub", "0.08")), neg = std::stod(get(a, "neg-frac", "0.1"));
+    if (R < 8) die("synth: --runs must be at least 8");
+    sdslw::RlbwtParts P;
+    P.heads.resize(R);
+    P.lens.resize(R);
+    P.thr.assign(R, 0);
+    Rng g(seed * 0x9E3779B97F4A7C15ULL + 17);
+    const uint64_t term_run = 1 + g.below(R - 2);
+    uint8_t prev = 0;
+    P.n = 0;
+    for (uint64_t k = 0; k < R; k++) {
+        if (k == term_run) { P.heads[k] = 0; P.lens[k] = 1; prev = 0; P.n += 1; continue; }
+        uint8_t c;
+        do c = (uint8_t)ACGT[g.next() & 3]; while (c == prev);
+        prev = c;
+        // geometric with the requested mean, a small share of runs `tail_mul` times longer
+        uint64_t len = 1 + (uint64_t)(-std::log(1.0 - g.unif()) * (mean_len - 1.0));
+        if (g.unif() < tail) len *= tail_mul;
+        P.heads[k] = c;
+        P.lens[k] = len;
+        P.n += len;
+    }
+    if (P.n >= (1ULL << 40) - 2) die("synth: n >= 2^40 - 2");
+    // thresholds: a position in (end of the previous run of the letter, start of this run]
+    std::vector<uint64_t> start(R + 1);
+    {
+        uint64_t pos = 0, last_end[256];
+        bool seen[256] = {false};
+        for (uint64_t k = 0; k < R; k++) {
+            start[k] = pos;
+            const uint8_t c = P.heads[k] <= 1 ? 1 : P.heads[k];
+            if (seen[c]) P.thr[k] = last_end[c] + 1 + g.below(pos - last_end[c]);
+            seen[c] = true;
+            pos += P.lens[k];
+            last_end[c] = pos - 1;
+        }
+        start[R] = pos;
+    }
+    {
+        std::ofstream fa(prefix + ".fa");
+        fa << ">synthetic_rlbwt_no_text\nN\n";
+        std::ofstream o(prefix + ".fa.thrbv.spumoni", std::ios::binary);
+        sdslw::write_pml_index(o, P);
+    }
+    std::printf("{\"n\": %llu, \"r\": %llu}\n", (unsigned long long)P.n, (unsigned long long)R);
+    if (!N) return 0;
+    // LF as a move structure: lf0[k] = LF(start of run k), dest[k] = run holding it (one forward merge per letter)
+    std::vector<uint64_t> F;
+    sdslw::build_F(P.heads, P.lens, F);
+    std::vector<uint64_t> lf0(R);
+    std::vector<uint32_t> dest(R);
+    {
+        uint64_t cnt[256] = {0}, cur[256];
+        for (int c = 0; c < 256; c++) cur[c] = ~0ull;
+        for (uint64_t k = 0; k < R; k++) {
+            const uint8_t c = P.heads[k] <= 1 ? 1 : P.heads[k];
+            lf0[k] = F[c] + cnt[c];
+            cnt[c] += P.lens[k];
+            uint64_t i = cur[c];
+            if (i == ~0ull) i = (uint64_t)(std::upper_bound(start.begin(), start.end(), lf0[k]) - start.begin()) - 1;
+            else while (start[i + 1] <= lf0[k]) i++;
+            cur[c] = i;
+            dest[k] = (uint32_t)i;
+        }
+    }
+    std::vector<uint64_t> off(N + 1, 0);
+    for (uint64_t r = 0; r < N; r++) off[r + 1] = off[r] + L;
+    std::vector<uint8_t> buf(off[N]);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t r = 0; r < (int64_t)N; r++) {
+        Rng q((seed << 32) ^ ((uint64_t)r + 1) * 0xD1B54A32D192ED03ULL);
+        uint8_t* o = buf.data() + off[r];
+        if (q.unif() < neg) {
+            for (uint64_t i = 0; i < L; i++) o[i] = (uint8_t)ACGT[q.next() & 3];
+            continue;
+        }
+        // Follow the backward search itself (compute_ms_pml.cpp:237-286) from its initial state pos = n - 1 and let it
+        // decide the read: with probability 1 - sub the next character is the one under the cursor (a match), otherwise
+        // another letter, and the cursor moves as the search would (threshold of the next run of that letter decides
+        // between the run above and the run below). Matches then come in stretches of mean length 1 / sub, as for reads
+        // sampled with errors from an indexed text.
+        uint64_t k = R - 1, in = P.lens[R - 1] - 1;
+        for (uint64_t i = L; i-- > 0;) {
+            uint8_t c = P.heads[k];
+            if (c <= 1 || q.unif() < sub) {
+                uint8_t d;
+                do d = (uint8_t)ACGT[q.next() & 3]; while (d == c);
+                c = d;
+                uint64_t dn = k + 1, up = k;
+                while (dn < R && P.heads[dn] != c) dn++;
+                bool has_up = false;
+                while (up-- > 0)
+                    if (P.heads[up] == c) { has_up = true; break; }
+                const bool go_up = dn >= R || (has_up && start[k] + in < P.thr[dn]);
+                if (go_up && has_up) { k = up; in = P.lens[up] - 1; }
+                else if (dn < R) { k = dn; in = 0; }
+                else { k = term_run + 1 < R ? term_run + 1 : 0; in = 0; c = P.heads[k]; }  // letter without runs: cannot happen for ACGT at this size
+            }
+            o[i] = c;
+            const uint64_t t = dest[k];
+            in += lf0[k] - start[t];  // LF(start[k] + in) = lf0[k] + in, expressed relative to run t
+            uint64_t tt = t;
+            while (in >= P.lens[tt]) in -= P.lens[tt++];
+            k = tt;
+        }
+    }
+    if (!out.empty()) {
+        std::ofstream o(out, std::ios::binary);
+        for (uint64_t r = 0; r < N; r++) {
+            const std::string line = ">read_" + std::to_string(r) + "\n";
+            o.write(line.data(), (std::streamsize)line.size());
+            o.write((const char*)buf.data() + off[r], (std::streamsize)L);
+            o.put('\n');
+        }
+    }
+    if (!bin.empty()) {
+        std::ofstream o(bin, std::ios::binary), q(bin + ".off", std::ios::binary);
+        o.write((const char*)buf.data(), (std::streamsize)buf.size());
+        q.write((const char*)off.data(), (std::streamsize)(off.size() * 8));
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------- nulldb
 static int cmd_nulldb(const Args& a) {
     std::string stats = get(a, "stats"), out = get(a, "out");
@@ -413,7 +552,7 @@ static int cmd_from_parts(const Args& a) {
 }
 
 int main(int argc, char** argv) {
-    if (argc < 2) die("usage: spumoni_mkindex genome|build|from-parts|reads|nulldb [--key value ...]");
+    if (argc < 2) die("usage: spumoni_mkindex genome|build|from-parts|reads|nulldb|synth [--key value ...]");
     std::string cmd = argv[1];
     Args a = parse_args(argc, argv, 2);
 #ifdef _OPENMP
@@ -424,6 +563,7 @@ int main(int argc, char** argv) {
     if (cmd == "from-parts") return cmd_from_parts(a);
     if (cmd == "reads") return cmd_reads(a);
     if (cmd == "nulldb") return cmd_nulldb(a);
+    if (cmd == "synth") return cmd_synth(a);
     die("unknown command " + cmd);
     return 1;
 }
