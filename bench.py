@@ -42,6 +42,16 @@ WORKLOADS = {
     "c2": dict(genome=["--kind", "pangenome", "--len", "100000000", "--haps", "20", "--snp", "0.001", "--indel", "0.0001", "--seed", "3"],
                n_reads=1_000_000, read_len=1000, reads=["--sub", "0.06", "--ins", "0.02", "--del", "0.02", "--neg-frac", "0.1"],
                desc="PML, 100 Mb pangenome index (20x5 Mb, +revcomp), 1 M x 1 kb ONT-like reads per GPU"),
+    # Stand-in for BASELINE configs[3] (3 Gb pangenome, n > 2^32), NOT a bench line of this round: a synthetic run-length BWT
+    # (tools/mkindex synth: no suffix array, not the BWT of a text) with the table sizes of such an index
+    # -- r = 1.5e8 runs: 16-byte move rows, 2.4 GB row table >> L2 -- and reads driven by the search itself, 55 % jumps like
+    # the c2 reads. PML only (there is no text for MS). SPB_BENCH_WORKLOAD=c4s
+    "c4s": dict(synth=["--runs", "150000000", "--mean-len", "40", "--seed", "5"],
+                n_reads=1_000_000, read_len=1000, reads=["--sub", "0.55", "--neg-frac", "0.1"],
+                desc="PML, synthetic RLBWT stand-in for config 4 (n ~ 6e9 > 2^32, r = 1.5e8), 1 M x 1 kb search-driven reads per GPU"),
+    "c4s_dev": dict(synth=["--runs", "2000000", "--mean-len", "40", "--seed", "5"],
+                    n_reads=20_000, read_len=1000, reads=["--sub", "0.55", "--neg-frac", "0.1"],
+                    desc="DEV ONLY: PML, synthetic RLBWT (r = 2e6), 20 k x 1 kb search-driven reads per GPU"),
     # development-size stand-in (NOT a bench line): SPB_BENCH_WORKLOAD=dev
     "dev": dict(genome=["--kind", "pangenome", "--len", "4000000", "--haps", "8", "--snp", "0.001", "--indel", "0.0001", "--seed", "3"],
                 n_reads=50_000, read_len=1000, reads=["--sub", "0.06", "--ins", "0.02", "--del", "0.02", "--neg-frac", "0.1"],
@@ -65,7 +75,7 @@ def emit(obj):
 
 def cache_dir(name: str) -> str:
     w = WORKLOADS[name]
-    key = hashlib.sha1(json.dumps([w["genome"], "fixture-v1"]).encode()).hexdigest()[:12]
+    key = hashlib.sha1(json.dumps([w.get("genome") or w["synth"], "fixture-v1"]).encode()).hexdigest()[:12]
     base = os.environ.get("SPUMONI_B200_CACHE", "/tmp/spumoni_b200_cache")
     d = os.path.join(base, f"{name}_{key}")
     os.makedirs(d, exist_ok=True)
@@ -80,6 +90,19 @@ def ensure_index(name: str, mode: str = "pml") -> str:
     if os.path.exists(ref + ext) and os.path.exists(os.path.join(d, "ok_" + mode)):
         return ref
     t0 = time.time()
+    w = WORKLOADS[name]
+    if "synth" in w:  # index and reads come out of one pass over the synthetic run arrays
+        if mode != "pml":
+            raise SystemExit("bench.py: synthetic workloads have no text: PML only")
+        tmp = os.path.join(d, f"reads.tmp{os.getpid()}")
+        subprocess.check_call([MKINDEX, "synth", "--prefix", os.path.join(d, "idx"), "--n", str(w["n_reads"]), "--len", str(w["read_len"]),
+                               "--bin", tmp] + w["synth"] + w["reads"], stdout=subprocess.DEVNULL)
+        path = os.path.join(d, f"reads_{w['n_reads']}_{w['read_len']}_s4.bin")
+        os.replace(tmp + ".off", path + ".off")
+        os.replace(tmp, path)
+        open(os.path.join(d, "ok_" + mode), "w").write("ok")
+        log(f"built synthetic index {name} in {time.time() - t0:.1f} s")
+        return ref
     subprocess.check_call([MKINDEX, "genome", "--out", os.path.join(d, "raw.fa")] + WORKLOADS[name]["genome"], stdout=subprocess.DEVNULL)
     subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--" + mode], stdout=subprocess.DEVNULL)
     os.remove(os.path.join(d, "raw.fa"))
@@ -92,6 +115,8 @@ def ensure_reads(name: str, ref: str, seed: int):
     w = WORKLOADS[name]
     path = os.path.join(cache_dir(name), f"reads_{w['n_reads']}_{w['read_len']}_s{seed}.bin")
     if not (os.path.exists(path) and os.path.exists(path + ".off")):
+        if "synth" in w:
+            raise SystemExit("bench.py: the reads of a synthetic workload are written with its index; remove the cache directory")
         tmp = path + f".tmp{os.getpid()}"
         subprocess.check_call([MKINDEX, "reads", "--ref", ref, "--n", str(w["n_reads"]), "--len", str(w["read_len"]), "--seed", str(seed),
                                "--bin", tmp] + w["reads"], stdout=subprocess.DEVNULL)
