@@ -29,21 +29,49 @@ SHAPES = {
     "giant": ["--runs", 3000, "--mean-len", 25, "--tail-frac", 0.005, "--tail-mul", 400000000, "--seed", 6, "--n", 100, "--len", 200,
               "--sub", 0.1],
 }
+# corner shapes, CPU comparisons only: 8 runs, every run of length 1, long runs only, 9 runs of ~10^5, a third of the runs long
+CORNERS = {
+    "tiny8": ["--runs", 8, "--mean-len", 3, "--seed", 9, "--n", 60, "--len", 120, "--sub", 0.2],
+    "len1": ["--runs", 5000, "--mean-len", 1, "--seed", 9, "--n", 60, "--len", 120, "--sub", 0.2],
+    "long": ["--runs", 2000, "--mean-len", 1000, "--tail-frac", 0, "--seed", 9, "--n", 60, "--len", 120, "--sub", 0.2],
+    "tiny_long": ["--runs", 9, "--mean-len", 100000, "--seed", 9, "--n", 60, "--len", 120, "--sub", 0.2],
+    "mixed": ["--runs", 70000, "--mean-len", 2, "--tail-frac", 0.3, "--tail-mul", 300, "--seed", 9, "--n", 60, "--len", 120, "--sub", 0.2],
+}
+
+
+def _make(shape, args, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("synth_" + shape))
+    out = mkindex("synth", "--prefix", os.path.join(d, "idx"), "--bin", os.path.join(d, "r.bin"), "--out", os.path.join(d, "reads.fa"), *args)
+    n = int(out.split('"n":')[1].split(",")[0])
+    assert (n > 2 ** 32) == (shape in ("huge", "giant"))
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "reference_run", "idx.fa.pmlnulldb"), os.path.join(d, "idx.fa.pmlnulldb"))
+    return {"dir": d, "ref": os.path.join(d, "idx.fa"), "reads_fa": os.path.join(d, "reads.fa"), "reads_bin": os.path.join(d, "r.bin"),
+            "shape": shape}
 
 
 @pytest.fixture(scope="module", params=sorted(SHAPES))
 def synth(request, tmp_path_factory):
-    d = str(tmp_path_factory.mktemp("synth_" + request.param))
-    out = mkindex("synth", "--prefix", os.path.join(d, "idx"), "--bin", os.path.join(d, "r.bin"), "--out", os.path.join(d, "reads.fa"),
-                  *SHAPES[request.param])
-    n = int(out.split('"n":')[1].split(",")[0])
-    assert (n > 2 ** 32) == (request.param in ("huge", "giant"))
-    shutil.copy(os.path.join(ROOT, "tests", "golden", "reference_run", "idx.fa.pmlnulldb"), os.path.join(d, "idx.fa.pmlnulldb"))
-    return {"dir": d, "ref": os.path.join(d, "idx.fa"), "reads_fa": os.path.join(d, "reads.fa"), "reads_bin": os.path.join(d, "r.bin"),
-            "shape": request.param}
+    return _make(request.param, SHAPES[request.param], tmp_path_factory)
+
+
+@pytest.fixture(scope="module", params=sorted(CORNERS))
+def corner(request, tmp_path_factory):
+    return _make(request.param, CORNERS[request.param], tmp_path_factory)
 
 
 def test_synthetic_oracle_equals_reference_binary(synth, tmp_path):
+    _oracle_equals_reference_binary(synth, tmp_path)
+
+
+def test_corner_shapes_oracle_equals_reference_binary(corner, tmp_path):
+    _oracle_equals_reference_binary(corner, tmp_path)
+
+
+def test_corner_shapes_flat_image_equals_oracle(corner, row_width):
+    test_synthetic_flat_image_equals_oracle(corner, row_width)
+
+
+def _oracle_equals_reference_binary(synth, tmp_path):
     if os.path.isdir("/root/reference"):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref", "-s"])
     if not os.path.exists(REF_BIN):
@@ -68,14 +96,14 @@ def test_synthetic_flat_image_equals_oracle(synth, row_width):
     if fi.num_fast:
         assert bool(fi.off_mrows8) == (row_width == "8")
     matched = 0
-    for i in range(0, 40):
+    for i in range(0, min(40, len(off) - 1)):
         r = bytes(buf[int(off[i]):int(off[i + 1])])
         want = o.matching_statistics(r).tolist()
         assert fi.walk(r)[0] == want, i
         if fi.num_fast:
             assert fi.walk_rows(r)[0] == want, i
         matched += sum(1 for v in want if v > 0)
-    assert matched > 1000 or synth["shape"] == "jumpy"  # the generated reads do match in stretches
+    assert matched > 1000 or synth["shape"] not in ("typical", "huge", "giant")  # the generated reads do match in stretches
 
 
 @pytest.mark.gpu
