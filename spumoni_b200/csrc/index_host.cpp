@@ -532,6 +532,7 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
     RawVec<uint64_t> start((size_t)R + 1), lf((size_t)R);
     std::vector<uint64_t> numC(256, 0);
     std::vector<uint32_t> numRunsC(256, 0);
+    std::vector<uint32_t> ordBefore((size_t)(kChunks + 1) * 256, 0);  // runs of each letter before a slice
     {
         // pass 1: per-slice length sums per head; exclusive scan; pass 2: fill start / lf from the slice's prefix
         std::vector<uint64_t> sliceC((size_t)(kChunks + 1) * 256, 0), slicePos((size_t)kChunks + 1, 0);
@@ -554,6 +555,7 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             for (int a = 0; a < 256; a++) {
                 sliceC[(size_t)(c + 1) * 256 + a] += sliceC[(size_t)c * 256 + a];
                 numRunsC[a] += sliceRuns[(size_t)c * 256 + a];
+                ordBefore[(size_t)(c + 1) * 256 + a] = numRunsC[a];
             }
         }
         for (int a = 0; a < 256; a++) numC[a] = sliceC[(size_t)kChunks * 256 + a];
@@ -649,8 +651,10 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         if (cand.size() > 4) cand.resize(4);
         std::sort(cand.begin(), cand.end());
         for (int c : cand) { h.fast_sym[num_fast] = (uint32_t)c; fid[c] = num_fast++; }
-        for (uint64_t k = 0; k < R; k++)
-            if (d.lens[(size_t)k] >= 0xFFFFFFFEull) num_fast = 0;  // 32-bit in-run offsets would overflow: generic kernels only
+        int too_long = 0;  // 32-bit in-run offsets would overflow: generic kernels only
+#pragma omp parallel for schedule(static) reduction(| : too_long)
+        for (int64_t k = 0; k < (int64_t)R; k++) too_long |= d.lens[(size_t)k] >= 0xFFFFFFFEull;
+        if (too_long) num_fast = 0;
         if (!num_fast) for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
     }
     h.num_fast = num_fast;
@@ -683,7 +687,8 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(SpbDocPair), 256);
         }
         uint32_t mx = 0;
-        for (uint64_t k = 0; k < R; k++) mx = std::max(mx, std::max(d.doc_start[(size_t)k], d.doc_end[(size_t)k]));
+#pragma omp parallel for schedule(static) reduction(max : mx)
+        for (int64_t k = 0; k < (int64_t)R; k++) mx = std::max(mx, std::max(d.doc_start[(size_t)k], d.doc_end[(size_t)k]));
         h.num_docs = mx + 1;
         h.doc_init = d.doc_end[(size_t)R - 1];
         h.doc_absent_ms = d.doc_start[0];
@@ -734,17 +739,29 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         r.w = pack_hi(s, 8);  // head 0: never equals a present character
         runs[k] = r;
     }
-    // block headers
+    // block headers: the heads of 32 runs + the number of runs of every letter before the block
     {
-        std::vector<uint32_t> cnt(sigma_pad, 0);
-        for (uint32_t b = 0; b < num_blocks; b++) {
-            uint8_t* hdr = blob.data() + h.off_blocks + (size_t)b * blk_stride;
-            std::memcpy(hdr + 32, cnt.data(), 4 * (size_t)sigma_pad);
-            for (uint32_t t = 0; t < 32; t++) {
-                const uint64_t k = (uint64_t)b * 32 + t;
-                if (k < R) {
-                    hdr[t] = d.heads[(size_t)k];
-                    cnt[cidx[d.heads[(size_t)k]]]++;
+        auto blk_lo = [&](int c) -> uint32_t { return (uint32_t)slice_lo(num_blocks, c); };
+        std::vector<uint32_t> before((size_t)(kChunks + 1) * sigma_pad, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kChunks; c++) {
+            uint32_t* cnt = &before[(size_t)(c + 1) * sigma_pad];
+            for (uint64_t k = (uint64_t)blk_lo(c) * 32, e = std::min<uint64_t>((uint64_t)blk_lo(c + 1) * 32, R); k < e; k++) cnt[cidx[d.heads[(size_t)k]]]++;
+        }
+        for (int c = 0; c < kChunks; c++)
+            for (uint32_t a = 0; a < sigma_pad; a++) before[(size_t)(c + 1) * sigma_pad + a] += before[(size_t)c * sigma_pad + a];
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kChunks; c++) {
+            std::vector<uint32_t> cnt(before.begin() + (size_t)c * sigma_pad, before.begin() + (size_t)(c + 1) * sigma_pad);
+            for (uint32_t b = blk_lo(c); b < blk_lo(c + 1); b++) {
+                uint8_t* hdr = blob.data() + h.off_blocks + (size_t)b * blk_stride;
+                std::memcpy(hdr + 32, cnt.data(), 4 * (size_t)sigma_pad);
+                for (uint32_t t = 0; t < 32; t++) {
+                    const uint64_t k = (uint64_t)b * 32 + t;
+                    if (k < R) {
+                        hdr[t] = d.heads[(size_t)k];
+                        cnt[cidx[d.heads[(size_t)k]]]++;
+                    }
                 }
             }
         }
@@ -754,31 +771,36 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         SpbCharRec* crec = reinterpret_cast<SpbCharRec*>(blob.data() + h.off_crec);
         SpbCharSamp* csamp = ms ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_csamp) : nullptr;
         SpbDocPair* cdoc = use_doc ? reinterpret_cast<SpbDocPair*>(blob.data() + h.off_cdoc) : nullptr;
-        std::vector<uint32_t> prev_ed(256, 0);
-        std::vector<uint32_t> o(256, 0);
-        std::vector<uint64_t> prev_sl(256, 0);
-        for (uint64_t k = 0; k < R; k++) {
-            const uint8_t c = d.heads[(size_t)k];
-            const size_t at = (size_t)crec_base[c] + o[c]++;
-            const uint64_t thr = d.thr[(size_t)k];
-            if (thr > n) throw FormatError("threshold beyond the BWT");
-            SpbCharRec r;
-            r.x = (uint32_t)thr;
-            r.y = (uint32_t)lf[(size_t)k];
-            r.z = dest[(size_t)k];
-            r.w = pack_hi(thr, 0) | pack_hi(lf[(size_t)k], 8);
-            crec[at] = r;
-            if (ms) {
-                csamp[at].ss = d.samples_start[(size_t)k];
-                csamp[at].sl = prev_sl[c];
-                prev_sl[c] = d.samples_last[(size_t)k];
-            }
-            if (use_doc) {
-                cdoc[at].sd = d.doc_start[(size_t)k];
-                cdoc[at].ed = prev_ed[c];
-                prev_ed[c] = d.doc_end[(size_t)k];
+        // The "last sample / last document of the previous run of the letter" fields of a record belong to the run before it:
+        // every run writes them into the NEXT record of its letter (the first record keeps the zero of the image, the
+        // sentinel after the last run receives the last run's), which makes the slices independent.
+        int bad_thr = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(| : bad_thr)
+        for (int sl = 0; sl < kChunks; sl++) {
+            uint32_t o[256];
+            std::memcpy(o, &ordBefore[(size_t)sl * 256], sizeof(o));
+            for (uint64_t k = chunk_lo(sl), e = chunk_lo(sl + 1); k < e; k++) {
+                const uint8_t c = d.heads[(size_t)k];
+                const size_t at = (size_t)crec_base[c] + o[c]++;
+                const uint64_t thr = d.thr[(size_t)k];
+                bad_thr |= thr > n;
+                SpbCharRec r;
+                r.x = (uint32_t)thr;
+                r.y = (uint32_t)lf[(size_t)k];
+                r.z = dest[(size_t)k];
+                r.w = pack_hi(thr, 0) | pack_hi(lf[(size_t)k], 8);
+                crec[at] = r;
+                if (ms) {
+                    csamp[at].ss = d.samples_start[(size_t)k];
+                    csamp[at + 1].sl = d.samples_last[(size_t)k];
+                }
+                if (use_doc) {
+                    cdoc[at].sd = d.doc_start[(size_t)k];
+                    cdoc[at + 1].ed = d.doc_end[(size_t)k];
+                }
             }
         }
+        if (bad_thr) throw FormatError("threshold beyond the BWT");
         for (int c = 0; c < 256; c++) {
             if (!numRunsC[c]) continue;
             const size_t at = (size_t)crec_base[c] + numRunsC[c];
@@ -789,14 +811,8 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             r.z = (uint32_t)run_of(end);
             r.w = pack_hi(n + 1, 0) | pack_hi(end, 8);
             crec[at] = r;
-            if (ms) {
-                csamp[at].ss = 0;
-                csamp[at].sl = prev_sl[c];
-            }
-            if (use_doc) {
-                cdoc[at].sd = 0;
-                cdoc[at].ed = prev_ed[c];
-            }
+            if (ms) csamp[at].ss = 0;    // .sl was written by the last run of the letter
+            if (use_doc) cdoc[at].sd = 0;  // .ed likewise
         }
     }
     if (ms) std::memcpy(blob.data() + h.off_text, text.data(), text.size());
@@ -805,22 +821,20 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         uint64_t* rows_c = rows8 ? reinterpret_cast<uint64_t*>(blob.data() + h.off_mrows8) : nullptr;
         SpbCharSamp* msamp = (ms && h.off_msamp) ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
         SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
-        // next run (strictly after k) headed by each fast symbol: one cheap backward sweep records the state at every slice
-        // boundary, then each slice walks backwards on its own
-        std::vector<uint32_t> edge((size_t)kChunks * 4, 0xFFFFFFFFu);
-        {
-            uint32_t cur[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-            int c = kChunks - 1;
-            for (uint64_t k = R;; k--) {  // invariant: cur = next fast runs at index >= k
-                while (c >= 0 && chunk_lo(c + 1) == k) {
-                    for (int s = 0; s < 4; s++) edge[(size_t)c * 4 + s] = cur[s];
-                    c--;
-                }
-                if (k == 0) break;
-                const uint32_t f = fid[d.heads[(size_t)k - 1]];
-                if (f < SPB_SYM_SLOW) cur[f] = (uint32_t)(k - 1);
+        // next run (strictly after k) headed by each fast symbol: the state at every slice boundary comes from the first fast
+        // runs of the slices after it, then each slice walks backwards on its own
+        std::vector<uint32_t> edge((size_t)kChunks * 4, 0xFFFFFFFFu), first((size_t)kChunks * 4, 0xFFFFFFFFu);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kChunks; c++) {  // first run of each fast symbol inside slice c (stops as soon as all are seen)
+            uint32_t found = 0;
+            for (uint64_t k = chunk_lo(c), e = chunk_lo(c + 1); k < e && found < num_fast; k++) {
+                const uint32_t f = fid[d.heads[(size_t)k]];
+                if (f < SPB_SYM_SLOW && first[(size_t)c * 4 + f] == 0xFFFFFFFFu) { first[(size_t)c * 4 + f] = (uint32_t)k; found++; }
             }
         }
+        for (int c = kChunks - 2; c >= 0; c--)  // edge[c] = next fast runs at or after the end of slice c
+            for (int f = 0; f < 4; f++)
+                edge[(size_t)c * 4 + f] = first[(size_t)(c + 1) * 4 + f] != 0xFFFFFFFFu ? first[(size_t)(c + 1) * 4 + f] : edge[(size_t)(c + 1) * 4 + f];
 #pragma omp parallel for schedule(dynamic, 1)
         for (int c = 0; c < kChunks; c++) {
         uint32_t nxt[4];  // next runs strictly after k
