@@ -908,29 +908,58 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             r.w = (SPB_SYM_SLOW << 27) | (1u << 30);
             rows[k] = r;
         }
-        if (ms) {
-            std::vector<uint64_t> prev_sl(256, 0);
-            for (uint64_t k = 0; k < R; k++) {
-                const uint8_t c = d.heads[(size_t)k];
-                if (msamp) {
-                    msamp[k].ss = d.samples_start[(size_t)k];
-                    msamp[k].sl = prev_sl[c];
-                } else  // inline: the second 8 bytes of the 16-byte row slot (text positions < n < 2^32)
-                    rows_c[k * 2 + 1] = (uint64_t)(uint32_t)d.samples_start[(size_t)k] | ((uint64_t)(uint32_t)prev_sl[c] << 32);
-                prev_sl[c] = d.samples_last[(size_t)k];
+        // per-row "previous run of the same letter" fields (MS samples, documents): the last run of every letter before each
+        // slice is found first, then the slices fill their rows independently
+        const uint64_t kNone = ~0ull;
+        std::vector<uint64_t> last_before((size_t)(kChunks + 1) * 256, kNone);
+        if (ms || use_doc) {
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int c = 0; c < kChunks; c++) {
+                uint64_t* last = &last_before[(size_t)(c + 1) * 256];
+                for (uint64_t k = chunk_lo(c), e = chunk_lo(c + 1); k < e; k++) last[d.heads[(size_t)k]] = k;
             }
-            for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_sl[s] = prev_sl[h.fast_sym[s]];
+            for (int c = 0; c < kChunks; c++)
+                for (int a = 0; a < 256; a++)
+                    if (last_before[(size_t)(c + 1) * 256 + a] == kNone) last_before[(size_t)(c + 1) * 256 + a] = last_before[(size_t)c * 256 + a];
+        }
+        const uint64_t* last_run = &last_before[(size_t)kChunks * 256];  // last run of every letter
+        if (ms) {
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int sl = 0; sl < kChunks; sl++) {
+                uint64_t prev_sl[256];
+                for (int a = 0; a < 256; a++) {
+                    const uint64_t kb = last_before[(size_t)sl * 256 + a];
+                    prev_sl[a] = kb == kNone ? 0 : d.samples_last[(size_t)kb];
+                }
+                for (uint64_t k = chunk_lo(sl), e = chunk_lo(sl + 1); k < e; k++) {
+                    const uint8_t c = d.heads[(size_t)k];
+                    if (msamp) {
+                        msamp[k].ss = d.samples_start[(size_t)k];
+                        msamp[k].sl = prev_sl[c];
+                    } else  // inline: the second 8 bytes of the 16-byte row slot (text positions < n < 2^32)
+                        rows_c[k * 2 + 1] = (uint64_t)(uint32_t)d.samples_start[(size_t)k] | ((uint64_t)(uint32_t)prev_sl[c] << 32);
+                    prev_sl[c] = d.samples_last[(size_t)k];
+                }
+            }
+            for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_sl[s] = d.samples_last[(size_t)last_run[h.fast_sym[s]]];
         }
         if (use_doc) {
             SpbDocPair* mdoc = reinterpret_cast<SpbDocPair*>(blob.data() + h.off_mdoc);
-            std::vector<uint32_t> pe(256, 0);
-            for (uint64_t k = 0; k < R; k++) {
-                const uint8_t c = d.heads[(size_t)k];
-                mdoc[k].sd = d.doc_start[(size_t)k];
-                mdoc[k].ed = pe[c];
-                pe[c] = d.doc_end[(size_t)k];
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int sl = 0; sl < kChunks; sl++) {
+                uint32_t pe[256];
+                for (int a = 0; a < 256; a++) {
+                    const uint64_t kb = last_before[(size_t)sl * 256 + a];
+                    pe[a] = kb == kNone ? 0 : d.doc_end[(size_t)kb];
+                }
+                for (uint64_t k = chunk_lo(sl), e = chunk_lo(sl + 1); k < e; k++) {
+                    const uint8_t c = d.heads[(size_t)k];
+                    mdoc[k].sd = d.doc_start[(size_t)k];
+                    mdoc[k].ed = pe[c];
+                    pe[c] = d.doc_end[(size_t)k];
+                }
             }
-            for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_doc[s] = pe[h.fast_sym[s]];
+            for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_doc[s] = d.doc_end[(size_t)last_run[h.fast_sym[s]]];
         }
         for (uint32_t s = 0; s < num_fast; s++) {
             const int c = (int)h.fast_sym[s];
