@@ -643,7 +643,7 @@ struct NullDb {
 // ------------------------------------------------------------------ BatchLoader (src/batch_loader.cpp)
 struct Read { std::string header_line, id, seq; };
 struct BatchLoader {
-    int fmt = 0;  // 0 unknown, 1 FASTA
+    int fmt = 0;  // 0 unknown, 1 FASTA, 2 FASTQ
     std::string buf;
     std::stringstream batch;
     bool loadBatch(std::ifstream& input, size_t num_bases) {
@@ -651,18 +651,22 @@ struct BatchLoader {
             if (!input.good()) return false;
             int pk = input.peek();
             if (pk == '>') fmt = 1;
+            else if (pk == '@') fmt = 2;
             else if (pk == EOF) return false;
             else throw std::runtime_error("unrecognized input query file type - expects FASTA or FASTQ.");
         }
         batch.clear();
         batch.str("");
-        size_t covered = 0, record = 0;
+        size_t covered = 0, record = 0, lines = 0;
         bool valid = false;
         while (input.good() && covered < num_bases) {
-            if (!std::getline(input, buf)) return false;
+            if (!std::getline(input, buf)) return false;  // FASTQ: the records gathered so far are lost with it (:51)
+            lines++;
             record += buf.size();
             valid = true;
-            if (input.peek() == '>') { covered += record; record = 0; }
+            if (fmt == 2) {
+                if (lines % 4 == 0) { covered += record / 2; record = 0; }  // half of a record's four lines is its read (:61-66)
+            } else if (input.peek() == '>') { covered += record; record = 0; }
             batch << buf << '\n';
         }
         return valid;
@@ -670,13 +674,22 @@ struct BatchLoader {
     bool grabNextRead(Read& r) {
         if (!std::getline(batch, buf)) return false;
         if (!buf.size()) return false;
-        if (buf[0] != '>') throw std::runtime_error("Incorrect FASTA entry, it should start with '>'");
+        if (fmt == 2 && buf[0] != '@') throw std::runtime_error("Incorrect FASTQ entry, it should start with '@'");
+        if (fmt == 1 && buf[0] != '>') throw std::runtime_error("Incorrect FASTA entry, it should start with '>'");
         r.header_line.assign(buf);
         if (buf.size() <= 2) throw std::runtime_error("header line is missing an id. invalid query cannot be processed.");
         auto id_length = buf.find_first_of(" \t\r", 1);
         id_length = (id_length == std::string::npos) ? buf.size() : id_length;
         r.id.assign(buf.substr(1, id_length));
         r.seq.assign("");
+        if (fmt == 2) {  // sequence line, '+' line, quality line (:108-120)
+            if (!std::getline(batch, buf)) return false;
+            while (!buf.empty() && std::isspace((unsigned char)buf.back())) buf.pop_back();
+            r.seq.assign(buf);
+            if (!std::getline(batch, buf)) return false;
+            if (!std::getline(batch, buf)) return false;
+            return true;
+        }
         while (batch.good() && batch.peek() != '>') {
             if (!std::getline(batch, buf)) return r.seq.size();
             while (!buf.empty() && std::isspace((unsigned char)buf.back())) buf.pop_back();

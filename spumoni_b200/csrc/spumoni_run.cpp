@@ -156,12 +156,14 @@ public:
     explicit LineReader(const std::string& path) : f_(std::fopen(path.c_str(), "rb")), buf_(16u << 20) {}
     ~LineReader() { if (f_) std::fclose(f_); }
     bool good() const { return f_ != nullptr; }
+    // what std::istream::good() would say after the reads so far: false once a line had to be ended by the end of the file
+    bool stream_good() const { return f_ != nullptr && !hit_eof_; }
     int peek() { return fill() ? (unsigned char)buf_[pos_] : EOF; }
     bool getline(std::string& line) {
         line.clear();
         bool any = false;
         for (;;) {
-            if (!fill()) return any;
+            if (!fill()) { hit_eof_ = true; return any; }
             any = true;
             const char* p = buf_.data() + pos_;
             const char* nl = (const char*)std::memchr(p, '\n', end_ - pos_);
@@ -182,20 +184,22 @@ private:
     std::FILE* f_;
     std::vector<char> buf_;
     size_t pos_ = 0, end_ = 0;
-    bool eof_ = false;
+    bool eof_ = false, hit_eof_ = false;
 };
 
-class FastaSource {  // sequential equivalent of BatchLoader::loadBatch + grabNextRead (FASTA)
+class FastaSource {  // sequential equivalent of BatchLoader::loadBatch + grabNextRead (FASTA, and FASTQ records)
 public:
     explicit FastaSource(const std::string& path) : in_(path) {
         if (!in_.good()) return;
         int pk = in_.peek();
         if (pk == EOF) { done_ = true; return; }
+        if (pk == '@') { fastq_ = true; return; }
         if (pk != '>') fatal_error("unrecognized input query file type - expects FASTA or FASTQ.");
         if (!in_.getline(line_)) done_ = true;
     }
     // appends one record; false at end of input
     bool next(ReadBatch& b) {
+        if (fastq_) return next_fastq(b);
         if (done_ || line_.empty()) return false;  // an empty header line ends the input (batch_loader.cpp:87)
         if (line_[0] != '>') fatal_error(std::string("Incorrect FASTA entry, it should start with '>' but found ") + line_[0]);
         if (line_.size() <= 2) fatal_error("header line is missing an id. invalid query cannot be processed.");
@@ -220,9 +224,61 @@ public:
         return true;
     }
 private:
+    // FASTQ (batch_loader.cpp:33-34, :61-66, :108-120), kept batch for batch because the batches are observable: the
+    // reference gathers lines until the records seen so far hold >= 1000 bases by its estimate (half of the four lines'
+    // lengths, :903), and when the file ends inside that loop -- always, if the last line is newline-terminated and the
+    // estimate is still below 1000 -- loadBatch returns false and the gathered records are never processed (:51). Inside
+    // a batch an empty header line, or a record cut short, ends the batch.
+    bool load_fastq_batch() {
+        lines_.clear();
+        next_line_ = 0;
+        size_t covered = 0, record = 0;
+        bool valid = false;
+        while (in_.stream_good() && covered < 1000) {
+            std::string line;
+            if (!in_.getline(line)) { lines_.clear(); return false; }
+            record += line.size();
+            valid = true;
+            lines_.push_back(std::move(line));
+            if (lines_.size() % 4 == 0) { covered += record / 2; record = 0; }
+        }
+        return valid;
+    }
+    bool next_fastq(ReadBatch& b) {
+        for (;;) {
+            if (done_) return false;
+            if (next_line_ >= lines_.size()) {
+                if (!load_fastq_batch()) { done_ = true; return false; }
+                continue;
+            }
+            const std::string& hd = lines_[next_line_++];
+            if (hd.empty()) { next_line_ = lines_.size(); continue; }  // the rest of the batch is skipped (:87)
+            if (hd[0] != '@') fatal_error(std::string("Incorrect FASTQ entry, it should start with '@' but found ") + hd[0]);
+            if (hd.size() <= 2) fatal_error("header line is missing an id. invalid query cannot be processed.");
+            if (next_line_ + 2 >= lines_.size()) { next_line_ = lines_.size(); continue; }  // record cut short by the end of the file
+            size_t idl = hd.find_first_of(" \t\r", 1);
+            idl = (idl == std::string::npos) ? hd.size() : idl;
+            b.ids.push_back(hd.substr(1, idl));
+            const std::string& seq = lines_[next_line_];
+            next_line_ += 3;  // sequence, '+' line, qualities
+            size_t e = seq.size();
+            while (e > 0 && std::isspace((unsigned char)seq[e - 1])) e--;
+            if (e == 0) {  // compute_ms_pml.cpp:926-931
+                std::cout << "\n\n";
+                fatal_warning(b.ids.back() + " was empty after digestion, commonly due to reads consisting of mostly non-ACGT "
+                              "characters. Please remove read or run SPUMONI without minimizer digestion.");
+            }
+            b.bases.insert(b.bases.end(), seq.begin(), seq.begin() + e);
+            b.offsets.push_back(b.bases.size());
+            if (e > b.max_len) b.max_len = e;
+            return true;
+        }
+    }
     LineReader in_;
     std::string line_;
-    bool done_ = false;
+    bool done_ = false, fastq_ = false;
+    std::vector<std::string> lines_;  // FASTQ: the lines of the current batch
+    size_t next_line_ = 0;
 };
 
 // ---------------------------------------------------------------------------------- output

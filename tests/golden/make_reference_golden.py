@@ -27,7 +27,10 @@ OUT = os.path.join(ROOT, "tests", "golden", "reference_run")
 MODES = {"P": ("reads.fa", ["-P", "-n", "-c"]), "Pd": ("reads.fa", ["-P", "-n", "-d"]), "M": ("reads.fa", ["-M", "-n", "-c"]),
          "Md": ("reads.fa", ["-M", "-n", "-d", "-c"]),
          # general text (-g): reads separated by 0x01, used verbatim (no upper-casing), ids are read_<i>
-         "Pg": ("general.txt", ["-P", "-n", "-g"]), "Mg": ("general.txt", ["-M", "-n", "-g"])}
+         "Pg": ("general.txt", ["-P", "-n", "-g"]), "Mg": ("general.txt", ["-M", "-n", "-g"]),
+         # FASTQ records in a file with a FASTA extension (the extension is all that is validated): BatchLoader takes them,
+         # and loses the records of the last, short batch when the file ends with a newline (batch_loader.cpp:51)
+         "Pq": ("fastq_reads.fa", ["-P", "-n", "-c"]), "Mq": ("fastq_reads.fa", ["-M", "-n"])}
 
 
 def fasta_text(path):
@@ -87,6 +90,11 @@ def main():
                         text[400:1000], "GATTACA" * 9, "acgtACGTxyz", text[-80:]):
                 f.write(seq.encode() + b"\x01")
             f.write(b"trailing bytes without a separator are not a read")
+        fq_rng = random.Random(777)  # its own stream: the files made before FASTQ support stay byte-identical
+        with open(os.path.join(d, "fastq_reads.fa"), "w") as f:
+            for i in range(23):
+                p0 = fq_rng.randint(0, len(text) - 151)
+                f.write("@fq%d comment\n%s\n+\n%s\n" % (i, text[p0:p0 + 150], "I" * 150))
         null_reads = os.path.join(d, "null_reads.fa")
         with open(null_reads, "w") as f:
             for i in range(12):
@@ -99,7 +107,7 @@ def main():
         shutil.rmtree(OUT, ignore_errors=True)
         os.makedirs(OUT)
         for name in ("idx.fa", "idx.fa.fdi", "idx.fa.thrbv.spumoni", "idx.fa.thrbv.ms", "idx.fa.doc", "idx.fa.pmlnulldb",
-                     "idx.fa.msnulldb", "reads.fa", "general.txt", "null_reads.fa"):
+                     "idx.fa.msnulldb", "reads.fa", "general.txt", "fastq_reads.fa", "null_reads.fa"):
             shutil.copy(os.path.join(d, name), os.path.join(OUT, name))
         for mode, (pattern, flags) in MODES.items():
             subprocess.check_call([REF_BIN, "run", "-r", os.path.join(d, "idx"), "-p", os.path.join(d, pattern)] + flags,

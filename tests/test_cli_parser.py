@@ -1,0 +1,110 @@
+"""CPU: the product CLI's input parser (FastaSource / LineReader in spumoni_b200/csrc/spumoni_run.cpp, compiled as is into
+tests/harness/cli_parser_harness.cpp) against the reference's BatchLoader (src/batch_loader.cpp:26-131), observed through
+the reference's own outputs: the record ids it wrote and the number of values per record. FASTA and FASTQ records, CRLF,
+blank lines, multi-line sequences, headers with blanks, '>' inside a sequence, missing trailing newline, and the inputs
+both sides reject."""
+import os
+import random
+import subprocess
+
+import pytest
+
+import spumoni_b200 as sp
+from conftest import ROOT
+
+GOLDEN = os.path.join(ROOT, "tests", "golden", "reference_run")
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "spumoni_ref")
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    exe = str(tmp_path_factory.mktemp("harness") / "cli_parser_harness")
+    lib_dir = os.path.dirname(sp.LIB_PATH)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "harness", "cli_parser_harness.cpp"), "-L" + lib_dir, "-lspumoni_b200",
+                           "-Wl,-rpath," + lib_dir])
+    return exe
+
+
+def _parsed(harness, path):
+    r = subprocess.run([harness, path], capture_output=True)
+    out = r.stdout.split(b"\n")
+    return r.returncode, [(out[i], out[i + 1]) for i in range(0, len(out) - 1, 2)]
+
+
+def _reference_records(path):
+    lines = open(path, "rb").read().split(b"\n")
+    return [(lines[i], len(lines[i + 1].split())) for i in range(0, len(lines) - 1, 2)]
+
+
+@pytest.mark.parametrize("pattern,mode,ext", [("reads.fa", "P", "pseudo_lengths"), ("fastq_reads.fa", "Pq", "pseudo_lengths"),
+                                              ("fastq_reads.fa", "Mq", "lengths")])
+def test_parser_equals_committed_reference_records(harness, pattern, mode, ext):
+    rc, got = _parsed(harness, os.path.join(GOLDEN, pattern))
+    want = _reference_records(os.path.join(GOLDEN, "expected", mode, pattern + "." + ext))
+    assert rc == 0 and [(i, len(s)) for i, s in got] == want
+    if pattern == "fastq_reads.fa":  # sequences are the second line of every kept record
+        lines = open(os.path.join(GOLDEN, pattern), "rb").read().split(b"\n")
+        assert [s for _, s in got] == [lines[4 * k + 1] for k in range(len(got))] and len(got) == 21
+
+
+def _nasty_files(d, text):
+    rng = random.Random(4)
+
+    def fq(n, length, trail=True):
+        out = ""
+        for i in range(n):
+            p = rng.randint(0, len(text) - length - 1)
+            out += "@q%d some comment\n%s\n+\n%s\n" % (i, text[p:p + length], "I" * length)
+        return out if trail else out.rstrip("\n")
+    t = text
+    cases = {
+        "crlf": ">r1\r\n" + t[10:60] + "\r\n>r2 desc\r\n" + t[100:140] + "\r\n",
+        "blank_lines": "\n\n>r1\n" + t[10:60] + "\n\n>r2\n\n" + t[100:140] + "\n\n",
+        "multiline": ">r1\n" + t[10:40] + "\n" + t[40:70] + "\n" + t[70:75] + "\n>r2\n" + t[100:140] + "\n",
+        "notrail": ">r1\n" + t[10:60] + "\n>r2\n" + t[100:140],
+        "tabs": ">r1\tx y\n" + t[10:60] + "\n>r2  two  spaces\n" + t[100:140] + "\n",
+        "gt_in_seq": ">r1\n" + t[10:30] + ">" + t[30:60] + "\n>r2\n" + t[100:140] + "\n",
+        "no_header_first": t[10:60] + "\n>r2\n" + t[100:140] + "\n",
+        "spaces_in_seq": ">r1\n" + t[10:30] + " " + t[30:60] + "\n>r2\n" + t[100:140] + " \n",
+        "lower": ">r1\n" + t[10:60].lower() + "\n",
+        "empty_id": ">\n" + t[10:60] + "\n> \n" + t[100:140] + "\n",
+        "one_char_id": ">r\n" + t[10:60] + "\n>r\n" + t[100:140] + "\n",
+        "long_id": ">" + "x" * 300 + " d\n" + t[10:60] + "\n",
+        "short_reads": "".join(">s%d\n%s\n" % (i, t[i * 3:i * 3 + 1 + i % 4]) for i in range(40)),
+        "fq_short": fq(23, 150), "fq_short_notrail": fq(23, 150, False), "fq_long": fq(5, 1200), "fq_long_notrail": fq(5, 1200, False),
+        "fq_mixed": fq(9, 150) + fq(2, 1500) + fq(5, 60), "fq_one": fq(1, 100), "fq_one_notrail": fq(1, 100, False),
+        "fq_crlf": fq(12, 150).replace("\n", "\r\n"), "fq_truncated": fq(10, 400) + "@last\nACGT\n",
+        "fq_blank_mid": fq(3, 600) + "\n" + fq(3, 600), "fq_plus_named": fq(4, 500).replace("\n+\n", "\n+same id\n"),
+    }
+    paths = {}
+    for name, body in cases.items():
+        paths[name] = os.path.join(d, name + ".fa")
+        with open(paths[name], "w", newline="") as f:
+            f.write(body)
+    return paths
+
+
+def test_parser_equals_reference_binary_on_odd_inputs(harness, tmp_path):
+    if os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-f", "Makefile.ref", "-s"])
+    if not os.path.exists(REF_BIN):
+        pytest.skip("oracle/_ref/spumoni_ref is not built (needs /root/reference)")
+    import shutil
+    d = str(tmp_path)
+    for f in os.listdir(GOLDEN):
+        if f.startswith("idx.fa"):
+            shutil.copy(os.path.join(GOLDEN, f), os.path.join(d, f))
+    text = "".join(line.strip() for line in open(os.path.join(d, "idx.fa")) if not line.startswith(">"))
+    seen_reject = seen_drop = 0
+    for name, path in sorted(_nasty_files(d, text).items()):
+        ref = subprocess.run([REF_BIN, "run", "-r", os.path.join(d, "idx"), "-p", path, "-P", "-n"], capture_output=True)
+        rc, got = _parsed(harness, path)
+        assert (rc != 0) == (ref.returncode != 0), name
+        if ref.returncode != 0:
+            seen_reject += 1
+            continue
+        want = _reference_records(path + ".pseudo_lengths")
+        assert [(i, len(s)) for i, s in got] == want, name
+        seen_drop += name.startswith("fq_") and len(want) < open(path).read().count("\n@") + 1
+    assert seen_reject >= 4 and seen_drop >= 4

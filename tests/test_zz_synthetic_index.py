@@ -121,3 +121,21 @@ def test_synthetic_cuda_equals_oracle(synth, row_width):
     for r in range(0, len(off) - 1, 37):
         _, summ, above, below, _ = naive.classify_bins(Lo[int(off[r]):int(off[r + 1])].tolist(), 150, 7)
         assert (int(S[r]["sum_max"]), int(S[r]["above"]), int(S[r]["below"])) == (summ, above, below)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,flags,exts", [("Pq", ["-P", "-c"], (".pseudo_lengths", ".report")), ("Mq", ["-M"], (".lengths", ".pointers"))])
+def test_zz_cli_fastq_records_equal_reference(tmp_path, mode, flags, exts):
+    """FASTQ records through the product CLI against the reference's own outputs (tests/golden/reference_run): BatchLoader
+    accepts '@' records, and loses the last short batch of a newline-terminated file (21 of 23 records survive). Last test of
+    the suite on purpose: it was written after the last GPU minutes of the round were spent (the parser itself is covered on
+    the CPU by tests/test_cli_parser.py)."""
+    golden = os.path.join(ROOT, "tests", "golden", "reference_run")
+    d = str(tmp_path / "g")
+    shutil.copytree(golden, d, ignore=shutil.ignore_patterns("expected"))
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", os.path.join(d, "idx"), "-p", os.path.join(d, "fastq_reads.fa"), "-n"] + flags,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for e in exts:
+        assert open(os.path.join(d, "fastq_reads.fa" + e), "rb").read() == open(os.path.join(golden, "expected", mode, "fastq_reads.fa" + e), "rb").read(), e
+    assert "finished processing 21 reads" in r.stderr
