@@ -111,14 +111,16 @@ public:
         reference& operator++() { return *this = (uint64_t)*this + 1; }
         reference& operator+=(uint64_t x) { return *this = (uint64_t)*this + x; }
     };
-    int_vector(size_type n = 0, value_type def = 0, uint8_t width = t_width ? t_width : 64) : width_(t_width ? t_width : width) {
+    // a runtime width outside 1..64 becomes 64, as in sdsl (the reference relies on it: a one-document array asks for width 0)
+    int_vector(size_type n = 0, value_type def = 0, uint8_t width = t_width ? t_width : 64)
+        : width_(t_width ? t_width : (width >= 1 && width <= 64 ? width : 64)) {
         vals_.assign(n, def & mask());
     }
     size_type size() const { return vals_.size(); }
     bool empty() const { return vals_.empty(); }
     uint8_t width() const { return width_; }
     void width(uint8_t w) {
-        if (!t_width) width_ = w;
+        if (!t_width) width_ = (w >= 1 && w <= 64) ? w : 64;
     }
     void resize(size_type n) { vals_.resize(n, 0); }
     reference operator[](size_type i) { return reference{this, i}; }

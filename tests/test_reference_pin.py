@@ -326,3 +326,58 @@ def test_cli_validation_equals_reference_binary(ref_bin, golden_copy, tmp_path):
         b = subprocess.run([sp.CLI_PATH] + c, capture_output=True, text=True)
         assert a.returncode == b.returncode, c
         assert clean(a.stderr) == clean(b.stderr) and a.stdout == b.stdout, (c, clean(a.stderr)[-300:], clean(b.stderr)[-300:])
+
+
+@pytest.mark.parametrize("docs", [1, 5])
+def test_document_array_counts_against_reference_binary(ref_bin, tmp_path, docs):
+    """One document (DocumentArray asks sdsl for width 0, which sdsl turns into 64) and five (3-bit entries): the array the
+    reference builds equals the fixture builder's, and the oracle's -d outputs equal the reference's."""
+    d = str(tmp_path)
+    mkindex("genome", "--kind", "pangenome", "--len", 6000, "--haps", 8, "--snp", 0.01, "--indel", 0.001, "--seed", 31, "--out", d + "/raw.fa")
+    ref = build_index(d, fasta=d + "/raw.fa", revcomp=True, keep=True, docs=docs)
+    mk_doc = open(ref + ".doc", "rb").read()
+    runs = subprocess.check_output([ref_bin, "x-build-pml", ref], text=True).split()[3]
+    subprocess.check_call([ref_bin, "x-doc", ref, runs])
+    assert open(ref + ".doc", "rb").read() == mk_doc
+    _write_slp(ref)
+    reads = d + "/reads.fa"
+    mkindex("reads", "--ref", ref, "--n", 80, "--len", 60, "--len-max", 300, "--sub", 0.05, "--neg-frac", 0.3, "--seed", 5, "--out", reads,
+            "--bin", d + "/r.bin")
+    for ext in (".pmlnulldb", ".msnulldb"):
+        shutil.copy(os.path.join(GOLDEN, "idx.fa.pmlnulldb"), ref + ext)
+    for kind, flag, exts in (("pml", "-P", ("pseudo_lengths", "doc_numbers")), ("ms", "-M", ("lengths", "pointers", "doc_numbers"))):
+        _run_ref(ref_bin, ref, reads, [flag, "-n", "-d"])
+        for e in exts:
+            shutil.move(reads + "." + e, d + "/want." + e)
+        oracle.run(ref, reads, kind, use_doc=True)
+        for e in exts:
+            assert filecmp.cmp(reads + "." + e, d + "/want." + e, shallow=False), (kind, e)
+
+
+def test_report_bin_widths_and_thresholds_against_reference_binary(ref_bin, pinned_index, tmp_path):
+    """The classifier's two inputs, swept: bin widths around the read lengths (-w 50 ... 400) and null databases whose
+    percentile value lands below the floor of 3, on a power of two, or high (threshold = max(percentile, 3) [+ 4 for PML])."""
+    reads = str(tmp_path / "reads.fa")
+    shutil.copy(pinned_index["reads_fa"], reads)
+    ref = pinned_index["ref"]
+    saved = {e: open(ref + e, "rb").read() for e in (".pmlnulldb", ".msnulldb")}
+    try:
+        for kind, flag in (("pml", "-P"), ("ms", "-M")):
+            for w in (50, 51, 150, 399, 400):
+                _run_ref(ref_bin, ref, reads, [flag, "-n", "-c", "-w", str(w)])
+                shutil.move(reads + ".report", str(tmp_path / "want.report"))
+                oracle.run(ref, reads, kind, report=True, bin_width=w)
+                assert filecmp.cmp(reads + ".report", str(tmp_path / "want.report"), shallow=False), (kind, w)
+        for name, stats in (("ones", [1] * 100), ("high", list(range(10, 40)) * 6), ("rare_high", [3] * 50 + [90] * 4), ("pow2", [16] * 10 + [2] * 10),
+                            ("zeros", [0] * 30)):
+            np.array(stats, dtype=np.uint64).tofile(str(tmp_path / "st.bin"))
+            for e in (".pmlnulldb", ".msnulldb"):
+                subprocess.check_call([MKINDEX, "nulldb", "--stats", str(tmp_path / "st.bin"), "--out", ref + e], stdout=subprocess.DEVNULL)
+            for kind, flag in (("pml", "-P"), ("ms", "-M")):
+                _run_ref(ref_bin, ref, reads, [flag, "-n", "-c"])
+                shutil.move(reads + ".report", str(tmp_path / "want.report"))
+                oracle.run(ref, reads, kind, report=True)
+                assert filecmp.cmp(reads + ".report", str(tmp_path / "want.report"), shallow=False), (name, kind)
+    finally:
+        for e, data in saved.items():
+            open(ref + e, "wb").write(data)
