@@ -378,6 +378,11 @@ def test_report_bin_widths_and_thresholds_against_reference_binary(ref_bin, pinn
                 shutil.move(reads + ".report", str(tmp_path / "want.report"))
                 oracle.run(ref, reads, kind, report=True)
                 assert filecmp.cmp(reads + ".report", str(tmp_path / "want.report"), shallow=False), (name, kind)
+                # the product's own loader + threshold rule (host code of the C ABI) against the reference's report header
+                import spumoni_b200 as sp
+                db = sp.EmpNullDatabase().load(ref + (".pmlnulldb" if kind == "pml" else ".msnulldb"))
+                header = open(str(tmp_path / "want.report")).readline()
+                assert int(header.split("thr=")[1].split(")")[0]) == sp.max_value_threshold(db.percentile_value, kind == "pml"), (name, kind)
     finally:
         for e, data in saved.items():
             open(ref + e, "wb").write(data)
