@@ -208,6 +208,15 @@ def test_oracle_null_database_equals_reference(pinned_index, kind):
     got = [int((int(words[(i * width) >> 6]) >> ((i * width) & 63) | (int(words[((i * width) >> 6) + 1]) << (64 - ((i * width) & 63))
                 if ((i * width) & 63) + width > 64 else 0)) & ((1 << width) - 1)) for i in range(len(stats))]
     assert got == [int(s) for s in stats]
+    # the product's writer (spb_nulldb_save) given the same statistics and scalars: the reference's file, byte for byte
+    import spumoni_b200 as sp
+    db = sp.EmpNullDatabase().load(pinned_index["ref"] + (".pmlnulldb" if kind == "pml" else ".msnulldb"))
+    assert (db.num_values, db.mean_null_stat, db.percentile_value) == (len(stats), mean, perc)
+    out = pinned_index["ref"] + ".product_" + kind + "nulldb"
+    c = sp._NullDb(len(stats), db.ks_stat_threshold, db.mean_null_stat, db.percentile_value)
+    s32 = np.ascontiguousarray(stats, dtype=np.uint32)
+    assert sp.load_library().spb_nulldb_save(out.encode(), ctypes.byref(c), s32.ctypes.data) == 0
+    assert open(out, "rb").read() == raw
 
 
 @pytest.mark.parametrize("seed,alphabet", [(1, b"ACGT\xe9N"), (2, b"AC"), (3, b"A"), (4, b"ACGTN"), (5, b"\x02\x7f\x80\xffAC"), (6, b"acgtACGT")])
