@@ -23,8 +23,9 @@
  *     (compute_ms_pml.cpp:215-217, :544-546), exactly as written by `spumoni build`;
  *   - the CUDA path is the only path: without a usable GPU the query calls fail loudly;
  *   - an spb_index serialises nothing: use one host thread per handle (the reference shares one index between its
- *     OpenMP threads because every call handles one read; here one call handles a whole batch and keeps several
- *     sub-batches in flight on its own streams).  Different handles, e.g. one per GPU, are independent.
+ *     OpenMP threads because every call handles one read; here one call handles a whole batch, keeps several
+ *     sub-batches in flight on its own streams and, for an index replicated on several GPUs, drives one host thread
+ *     per GPU itself).  Different handles are independent.
  */
 #ifndef SPUMONI_B200_H
 #define SPUMONI_B200_H
@@ -36,13 +37,14 @@
 extern "C" {
 #endif
 
-#define SPB_ABI_VERSION 3
+#define SPB_ABI_VERSION 4
 #define SPB_QUERY_TOUPPER 1u
 #define SPB_QUERY_POINTERS32 2u /* MS queries: `pointers` is a uint32_t array.  Lossless whenever every pointer is below 2^32 - 1
                                    (text positions of an index with n < 2^32, reads without characters absent from the index --
                                    the reference's size_t wrap-around after such a character, SURVEY App. C-4, does not fit).
                                    A value that does not fit is clamped, counted in `saturated`, and the *_host call returns
                                    SPB_ERR_OVERFLOW: discard the outputs and repeat with 64-bit pointers. */
+#define SPB_LENGTH_BITS 0x80u /* spb_query_opts.length_bytes: PML lengths as one bit per base (see spb_pml_expand_bits) */
 #define SPB_OPEN_DOC 1u /* spb_index_open_ex: also load <ref_file>.doc (the reference's use_doc / -d) */
 
 typedef enum {
@@ -53,8 +55,9 @@ typedef enum {
     SPB_ERR_CUDA = 4,      /* CUDA runtime error (message has the cudaError string) */
     SPB_ERR_NO_DEVICE = 5, /* index not resident on a GPU / no GPU present */
     SPB_ERR_LIMIT = 6,     /* size outside supported range (n >= 2^40-2, r >= 2^32-64, read >= 2^32) */
-    SPB_ERR_OVERFLOW = 7   /* a narrow output (1/2-byte lengths, 32-bit MS pointers) clamped at least one value; outputs are
-                              otherwise complete: repeat the call with a wider length_bytes / without SPB_QUERY_POINTERS32 */
+    SPB_ERR_OVERFLOW = 7   /* MS queries only: a narrow output (1/2-byte lengths, 32-bit pointers) clamped at least one value; the
+                              outputs are otherwise complete: repeat the call with a wider length_bytes / without
+                              SPB_QUERY_POINTERS32.  (Clamped PML lengths lose nothing and are not an error, see length_bytes.) */
 } spb_status;
 
 typedef enum { SPB_MODE_PML = 0, SPB_MODE_MS = 1 } spb_mode;
@@ -78,9 +81,15 @@ typedef struct {
                                 SPB_QUERY_POINTERS32: see above */
     uint32_t length_bytes;   /* element size of the `lengths` output: 0 or 4 = uint32_t, 2 = uint16_t, 1 = uint8_t.  A PML/MS
                                 length never exceeds the read length, so 2 is lossless for reads < 65536 bases.  Values that do
-                                not fit are clamped to the maximum and counted (lanes_per_read 1 only). */
-    uint64_t* saturated;     /* optional.  *_host calls: host pointer, receives the number of clamped values (the call then
-                                returns SPB_ERR_OVERFLOW).  *_device calls: device pointer, incremented by the kernels. */
+                                not fit are clamped to the maximum and counted (lanes_per_read 1 only).  For PML a clamped
+                                array is still lossless -- lengths[j] = lengths[j] != 0 ? lengths[j + 1] + 1 : 0
+                                (compute_ms_pml.cpp:249-281), and clamping keeps zero / non-zero -- so the call succeeds and
+                                spb_pml_widen_lengths rebuilds the exact values where `saturated` says some were clamped.
+                                SPB_LENGTH_BITS (PML, lanes_per_read 1): `lengths` is a bit map of spb_bits_bytes(total bases)
+                                bytes, bit i (bit i % 64 of 64-bit word i / 64) set iff the PML at base i is non-zero:
+                                1/8 byte per base over PCIe for any read length; spb_pml_expand_bits turns it into lengths. */
+    uint64_t* saturated;     /* optional.  *_host calls: host pointer, receives the number of clamped values (MS calls then
+                                return SPB_ERR_OVERFLOW).  *_device calls: device pointer, incremented by the kernels. */
 } spb_query_opts;
 
 /* EmpNullDatabase (emp_null_database.hpp:16-33); values are not kept, only the scalars */
@@ -121,6 +130,15 @@ int spb_index_from_header(const void* header, uint64_t bytes, spb_index** out);
 
 /* Make the index resident on `device`: library-owned allocation + H2D copy ... */
 int spb_index_to_device(spb_index* idx, int device);
+/* ... or on several GPUs at once: one H2D copy to devices[0], then ONE broadcast of the flat image to the others over
+ * NVLink (ncclBroadcast when libnccl can be loaded, peer-to-peer copies otherwise; spb_replicate_method() says which).
+ * Afterwards every *_host query of this handle cuts its reads into contiguous ranges balanced by bases, one range per
+ * GPU, driven by one host thread per GPU, no collective in the steady state -- the shape of the reference's `-t` region
+ * (`#pragma omp parallel` over batches of reads on a shared read-only index, compute_ms_pml.cpp:890-894, :1080-1084).
+ * The *_device entry points and spb_pml_query_host_text keep using devices[0].  Replaces any previous residency. */
+int spb_index_replicate(spb_index* idx, const int* devices, int n_devices);
+int spb_index_device_count(const spb_index* idx); /* GPUs the index is resident on */
+const char* spb_replicate_method(void);           /* "ncclBroadcast" | "cudaMemcpyPeer tree" | "" (last replicate of this process) */
 /* ... or adopt caller-owned device memory that already holds the flat image (e.g. the
  * receive buffer of an ncclBroadcast).  The memory must stay valid until spb_index_close. */
 int spb_index_attach_device(spb_index* idx, int device, const void* dev_blob, uint64_t bytes);
@@ -141,6 +159,11 @@ int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* off
                        void* lengths /* uint32_t[], or uint16_t[] / uint8_t[] per opts->length_bytes */, spb_bin_stats* stats,
                        const spb_query_opts* opts);
 
+/* Same query, reads passed as 2 bits per base (spb_pack_reads): a quarter of the host-to-device bytes.  packed / exc_*
+ * are what spb_pack_reads produced for the concatenated reads; offsets / outputs as in spb_pml_query_host. */
+int spb_pml_query_host_packed(spb_index* idx, const uint8_t* packed, const uint64_t* exc_pos, const uint8_t* exc_val, uint64_t n_exc,
+                              const uint64_t* offsets, uint64_t n_reads, void* lengths, spb_bin_stats* stats, const spb_query_opts* opts);
+
 /* ms_t::matching_statistics compute_ms_pml.cpp:795-812 -> ms_pointers::_query :570-623 */
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                       void* lengths, void* pointers /* uint64_t[], or uint32_t[] with SPB_QUERY_POINTERS32 */, spb_bin_stats* stats,
@@ -148,7 +171,9 @@ int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offs
 
 /* Same, on buffers already resident on the index's device; asynchronous on `cuda_stream`
  * (a cudaStream_t passed as void*; NULL = default stream).  d_reads must be 256-byte aligned
- * and readable up to the next multiple of 256 bytes past offsets[n_reads]; d_lengths must be 16-byte aligned. */
+ * and readable up to the next multiple of 256 bytes past offsets[n_reads]; d_lengths must be 16-byte aligned
+ * (SPB_LENGTH_BITS: 32-byte aligned, spb_bits_bytes(total bases) bytes, ZEROED by the caller before the call).
+ * At most 1024 launches of one handle may be in flight at a time (work counters are recycled after that many). */
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                          void* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream);
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
@@ -200,8 +225,30 @@ int spb_nulldb_save(const char* path, const spb_nulldb* summary, const uint32_t*
 /* max_value_thr derivation compute_ms_pml.cpp:871-875 (PML) / :1061-1063 (MS) */
 uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dna_letters, int use_promotions);
 
+/* ---- compact transports (host side, no GPU needed) ----------------------------------------------- */
+/* bytes of the bit map for n_bases bases (whole 32-byte blocks) / of the packed array (incl. the padding the device reads) */
+uint64_t spb_bits_bytes(uint64_t n_bases);
+uint64_t spb_packed_bytes(uint64_t n_bases);
+/* reads (n_bases bytes, all reads back to back) -> 2 bits per base, base i in bits 2 (i % 4) .. of byte i / 4, A C G T = 0 1 2 3
+ * (with SPB_QUERY_TOUPPER in `flags` also a c g t, as the query will upper-case them anyway).  Every other byte is recorded
+ * verbatim in the exception list (positions ascending): arbitrary bytes stay legal input.  packed: spb_packed_bytes(n_bases)
+ * bytes.  SPB_ERR_LIMIT if exc_capacity is too small (*n_exc = entries needed).  Runs on all host cores (OpenMP). */
+int spb_pack_reads(const uint8_t* reads, uint64_t n_bases, uint32_t flags, uint8_t* packed, uint64_t* exc_pos,
+                   uint8_t* exc_val, uint64_t exc_capacity, uint64_t* n_exc);
+/* bit map (SPB_LENGTH_BITS) -> lengths of `length_bytes` (0/4, 2, 1; clamped like the device would) */
+int spb_pml_expand_bits(const void* bits, const uint64_t* offsets, uint64_t n_reads, uint32_t length_bytes, void* lengths);
+/* clamped 1- / 2-byte PML lengths -> exact uint32_t lengths */
+int spb_pml_widen_lengths(const void* narrow, uint32_t narrow_bytes, const uint64_t* offsets, uint64_t n_reads, uint32_t* lengths);
+/* contiguous read ranges balanced by bases: cuts[s] .. cuts[s + 1] is the range of shard s (cuts has n_shards + 1 entries) */
+int spb_shard_by_bases(const uint64_t* offsets, uint64_t n_reads, uint32_t n_shards, uint64_t* cuts);
+/* test hooks of the host-side planning: sub-batches of a host call (first read of each, then n_reads) and the
+ * longest-first processing order of a sub-batch (*sorted = 0: lengths uniform, order not used) */
+int spb_plan_chunks(const uint64_t* offsets, uint64_t n_reads, uint64_t want_reads, uint64_t min_bases, uint64_t max_bases,
+                    uint64_t* chunk_first_read, uint64_t capacity, uint64_t* n_chunks);
+int spb_plan_order(const uint64_t* offsets, uint64_t n_reads, uint32_t* order, int* sorted);
+
 /* ---- utilities ----------------------------------------------------------------------- */
-int spb_host_alloc(void** p, size_t bytes); /* pinned host memory */
+int spb_host_alloc(void** p, size_t bytes); /* pinned host memory (portable: page-locked for every GPU) */
 void spb_host_free(void* p);
 int spb_device_count(void);
 /* number of kernels this library has launched in the calling process (bench `gpu_launches`) */

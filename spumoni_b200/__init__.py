@@ -28,6 +28,7 @@ QUERY_TOUPPER = 1
 QUERY_POINTERS32 = 2
 OPEN_DOC = 1
 ERR_OVERFLOW = 7
+LENGTH_BITS = 0x80  # length_bytes value: one bit per base (PML)
 _LEN_DTYPES = {4: np.uint32, 2: np.uint16, 1: np.uint8}
 
 BinStats = np.dtype([("sum_max", np.uint64), ("above", np.uint32), ("below", np.uint32)])
@@ -104,6 +105,20 @@ def load_library() -> ctypes.CDLL:
     L.spb_host_free.restype = None
     L.spb_device_count.restype = i32
     L.spb_kernel_launches.restype = u64
+    L.spb_index_replicate.argtypes = [vp, ctypes.POINTER(i32), i32]
+    L.spb_index_device_count.argtypes = [vp]
+    L.spb_replicate_method.restype = cp
+    L.spb_pml_query_host_packed.argtypes = [vp, vp, vp, vp, u64, vp, u64, vp, vp, ctypes.POINTER(QueryOpts)]
+    L.spb_bits_bytes.argtypes = [u64]
+    L.spb_bits_bytes.restype = u64
+    L.spb_packed_bytes.argtypes = [u64]
+    L.spb_packed_bytes.restype = u64
+    L.spb_pack_reads.argtypes = [vp, u64, ctypes.c_uint32, vp, vp, vp, u64, ctypes.POINTER(u64)]
+    L.spb_pml_expand_bits.argtypes = [vp, vp, u64, ctypes.c_uint32, vp]
+    L.spb_pml_widen_lengths.argtypes = [vp, ctypes.c_uint32, vp, u64, vp]
+    L.spb_shard_by_bases.argtypes = [vp, u64, ctypes.c_uint32, vp]
+    L.spb_plan_chunks.argtypes = [vp, u64, u64, u64, u64, vp, u64, ctypes.POINTER(u64)]
+    L.spb_plan_order.argtypes = [vp, u64, vp, ctypes.POINTER(i32)]
     _lib = L
     return L
 
@@ -167,6 +182,70 @@ def generate_null_database(index: "Index", reads: np.ndarray, offsets: np.ndarra
     out.num_values, out.ks_stat_threshold = db.num_values, db.ks_stat_threshold
     out.mean_null_stat, out.percentile_value = db.mean_null_stat, db.percentile_value
     return out, stats
+
+
+def bits_bytes(n_bases: int) -> int:
+    return int(load_library().spb_bits_bytes(n_bases))
+
+
+def pack_reads_2bit(reads: np.ndarray, toupper: bool = False):
+    """spb_pack_reads: concatenated reads -> (packed uint8[spb_packed_bytes], exc_pos uint64[], exc_val uint8[])."""
+    reads = np.ascontiguousarray(reads, dtype=np.uint8)
+    lib = load_library()
+    packed = np.zeros(int(lib.spb_packed_bytes(reads.size)), dtype=np.uint8)
+    cap = max(1024, reads.size // 64)
+    while True:
+        pos, val, n = np.zeros(cap, dtype=np.uint64), np.zeros(cap, dtype=np.uint8), ctypes.c_uint64(0)
+        rc = lib.spb_pack_reads(reads.ctypes.data, reads.size, QUERY_TOUPPER if toupper else 0, packed.ctypes.data,
+                                pos.ctypes.data, val.ctypes.data, cap, ctypes.byref(n))
+        if rc == 6 and n.value > cap:  # SPB_ERR_LIMIT: the exception list did not fit
+            cap = int(n.value)
+            continue
+        _check(rc)
+        return packed, pos[: n.value].copy(), val[: n.value].copy()
+
+
+def expand_bits(bits: np.ndarray, offsets: np.ndarray, length_bytes: int = 4) -> np.ndarray:
+    """spb_pml_expand_bits: bit map (LENGTH_BITS output) -> PML lengths."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    out = np.zeros(int(offsets[-1]) if len(offsets) else 0, dtype=_LEN_DTYPES[length_bytes])
+    _check(load_library().spb_pml_expand_bits(bits.ctypes.data, offsets.ctypes.data, len(offsets) - 1, length_bytes, out.ctypes.data))
+    return out
+
+
+def widen_lengths(narrow: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+    """spb_pml_widen_lengths: clamped uint8 / uint16 PML lengths -> exact uint32 lengths."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    narrow = np.ascontiguousarray(narrow)
+    out = np.zeros(int(offsets[-1]) if len(offsets) else 0, dtype=np.uint32)
+    _check(load_library().spb_pml_widen_lengths(narrow.ctypes.data, narrow.dtype.itemsize, offsets.ctypes.data, len(offsets) - 1, out.ctypes.data))
+    return out
+
+
+def shard_by_bases(offsets: np.ndarray, n_shards: int) -> np.ndarray:
+    """spb_shard_by_bases: cuts[s] .. cuts[s+1] = contiguous read range of shard s, balanced by bases."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    cuts = np.zeros(n_shards + 1, dtype=np.uint64)
+    _check(load_library().spb_shard_by_bases(offsets.ctypes.data, len(offsets) - 1, n_shards, cuts.ctypes.data))
+    return cuts
+
+
+def plan_chunks(offsets: np.ndarray, want_reads: int, min_bases: int, max_bases: int) -> np.ndarray:
+    """Sub-batch boundaries (first read of every sub-batch, then n_reads) of a host call -- test hook."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    out, cnt = np.zeros(n + 2, dtype=np.uint64), ctypes.c_uint64(0)
+    _check(load_library().spb_plan_chunks(offsets.ctypes.data, n, want_reads, min_bases, max_bases, out.ctypes.data, len(out), ctypes.byref(cnt)))
+    return out[: cnt.value + 1].copy()
+
+
+def plan_order(offsets: np.ndarray):
+    """Longest-first processing order of a sub-batch, or None when its lengths are uniform -- test hook."""
+    offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+    n = len(offsets) - 1
+    order, flag = np.zeros(max(n, 1), dtype=np.uint32), ctypes.c_int(0)
+    _check(load_library().spb_plan_order(offsets.ctypes.data, n, order.ctypes.data, ctypes.byref(flag)))
+    return order[:n].copy() if flag.value else None
 
 
 def pack_reads(reads) -> Tuple[np.ndarray, np.ndarray]:
@@ -251,6 +330,15 @@ class Index:
         _check(load_library().spb_index_to_device(self._h, device))
         return self
 
+    def replicate(self, devices) -> "Index":
+        """Resident on several GPUs (one broadcast of the flat image); host queries are then sharded over them by bases."""
+        arr = (ctypes.c_int * len(devices))(*devices)
+        _check(load_library().spb_index_replicate(self._h, arr, len(devices)))
+        return self
+
+    def device_count(self) -> int:
+        return int(load_library().spb_index_device_count(self._h))
+
     def attach_device(self, device: int, dev_tensor) -> "Index":
         """Adopt a torch uint8 CUDA tensor already holding the flat image (e.g. after a broadcast)."""
         _check(load_library().spb_index_attach_device(self._h, device, dev_tensor.data_ptr(), dev_tensor.numel()))
@@ -306,16 +394,21 @@ class Index:
         return L, None, S, D
 
     def query_host(self, reads: np.ndarray, offsets: np.ndarray, bin_width=0, max_value_thr=0, lanes=0,
-                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None, length_bytes=4, pointer_bytes=8):
-        """length_bytes 4/2/1 selects uint32/uint16/uint8 lengths, pointer_bytes 8/4 uint64/uint32 MS pointers; if a value
-        does not fit, SpumoniError with code ERR_OVERFLOW is raised (``.saturated`` = number of clamped values) and the
-        caller retries wider."""
-        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+                   toupper=False, out_lengths=None, out_pointers=None, out_stats=None, length_bytes=4, pointer_bytes=8, packed=None):
+        """length_bytes 4/2/1 selects uint32/uint16/uint8 lengths (LENGTH_BITS: a uint64 bit map, one bit per base, PML only),
+        pointer_bytes 8/4 uint64/uint32 MS pointers.  Clamped PML lengths are not an error (``last_saturated`` counts them,
+        widen_lengths rebuilds them); a clamped MS value raises SpumoniError with code ERR_OVERFLOW.
+        packed = (packed, exc_pos, exc_val) from pack_reads_2bit: the reads travel as 2 bits per base (PML only)."""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8) if reads is not None else None
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         n = len(offsets) - 1
         total = int(offsets[-1]) if n >= 0 and len(offsets) else 0
-        L = out_lengths if out_lengths is not None else np.zeros(total, dtype=_LEN_DTYPES[length_bytes])
-        assert L.dtype.itemsize == length_bytes and L.size >= total
+        if length_bytes == LENGTH_BITS:
+            L = out_lengths if out_lengths is not None else np.zeros(bits_bytes(total) // 8, dtype=np.uint64)
+            assert L.dtype.itemsize == 8 and L.nbytes >= bits_bytes(total)
+        else:
+            L = out_lengths if out_lengths is not None else np.zeros(total, dtype=_LEN_DTYPES[length_bytes])
+            assert L.dtype.itemsize == length_bytes and L.size >= total
         S = None
         if bin_width:
             S = out_stats if out_stats is not None else np.zeros(n, dtype=BinStats)
@@ -329,6 +422,12 @@ class Index:
             _check(lib.spb_ms_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
                                          P.ctypes.data, S.ctypes.data if S is not None else None, ctypes.byref(o)), sat)
             return L, P, S
+        if packed is not None:
+            pk, ep, ev = packed
+            _check(lib.spb_pml_query_host_packed(self._h, pk.ctypes.data, ep.ctypes.data if ep.size else None, ev.ctypes.data if ev.size else None,
+                                                 ep.size, offsets.ctypes.data, n, L.ctypes.data, S.ctypes.data if S is not None else None,
+                                                 ctypes.byref(o)), sat)
+            return L, None, S
         _check(lib.spb_pml_query_host(self._h, reads.ctypes.data, offsets.ctypes.data, n, L.ctypes.data,
                                       S.ctypes.data if S is not None else None, ctypes.byref(o)), sat)
         return L, None, S
@@ -336,9 +435,10 @@ class Index:
     # ---- queries (torch CUDA tensors, asynchronous on `stream`)
     def query_device(self, d_reads, d_offsets, n_reads: int, d_lengths, d_pointers=None, d_stats=None, bin_width=0,
                      max_value_thr=0, lanes=0, toupper=False, stream: int = 0, d_saturated=None) -> None:
-        """d_lengths: int32/int16/uint8 CUDA tensor (its element size selects the output width);
-        d_saturated: optional 1-element int64 CUDA tensor incremented by the number of clamped values."""
-        o = self._opts(bin_width, max_value_thr, lanes, toupper, d_lengths.element_size(),
+        """d_lengths: int32/int16/uint8 CUDA tensor (its element size selects the output width), or an int64 tensor = the
+        bit map of LENGTH_BITS (zeroed by the caller); d_saturated: optional 1-element int64 CUDA tensor incremented by the
+        number of clamped values."""
+        o = self._opts(bin_width, max_value_thr, lanes, toupper, LENGTH_BITS if d_lengths.element_size() == 8 else d_lengths.element_size(),
                        d_saturated.data_ptr() if d_saturated is not None else None,
                        d_pointers.element_size() if d_pointers is not None else 8)
         lib = load_library()

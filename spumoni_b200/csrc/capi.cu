@@ -1,9 +1,11 @@
 // C ABI of libspumoni_b200.so (declared in include/spumoni_b200.h).
 //
-// Host plumbing only: index lifetime, device residency, batch pipelining (H2D / kernel / D2H on
-// rotating streams) and error translation.  All per-base work happens in kernels.cu.
+// Host plumbing only: index lifetime, device residency (one or several GPUs), batch pipelining (H2D / kernels / D2H on
+// rotating streams, one host thread per GPU) and error translation.  All per-base work happens in kernels.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <deque>
@@ -12,10 +14,12 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/spumoni_b200.h"
 #include "flat_index.h"
+#include "host_util.h"
 #include "index_host.h"
 #include "kernels.h"
 
@@ -35,34 +39,101 @@ int fail(int code, const std::string& msg) {
             return fail(SPB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));               \
     } while (0)
 
-// Host entry points: the batch is cut into sub-batches that rotate over `n_slots` streams.  One read is one thread,
-// so a sub-batch of 1 kb reads only fills a fraction of the ~150 000 resident lanes: several sub-batches must be in
-// flight (copies of some overlapping the kernels of others) to keep both the SMs and the PCIe link busy.
+// Host entry points: the batch is cut into sub-batches that rotate over `n_slots` streams.  One read is one thread, so
+// what keeps the ~170 000 resident lanes of a B200 busy is the number of READS in flight: a sub-batch is sized by reads
+// (kWantReads, so that the slots together hold about two waves), bounded below and above in bases (copy efficiency, device
+// buffers), and several sub-batches are in flight (copies of some overlapping the kernels of others).
 constexpr int kMaxSlots = 16;
 constexpr int kDefaultSlots = 8;                       // SPUMONI_B200_SLOTS
-constexpr uint64_t kDefaultChunkBases = 32ull << 20;   // SPUMONI_B200_CHUNK_MB (in Mi bases)
-constexpr int kCounters = 64;     // pairs of work counters, rotated per launch
+constexpr uint64_t kWantReads = 43000;                 // SPUMONI_B200_CHUNK_READS
+constexpr uint64_t kMinChunkBases = 8ull << 20;        // SPUMONI_B200_CHUNK_MB (in Mi bases): lower bound of a sub-batch that has enough reads
+constexpr uint64_t kMaxChunkBases = 256ull << 20;      // upper bound (device buffers: 8 slots x (1 + 4 [+ 8 + 4]) bytes per base)
+constexpr int kCounters = 2048;   // work-counter pairs are rotated per launch: at most kCounters / 2 launches of one handle in flight
 constexpr int kDefaultLanes = 4;  // cooperative kernel (indexes without fast symbols)
+
+// a device buffer that only ever grows; the owner's stream must be idle when it does
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(size_t n, size_t slack = 0) {
+        if (n <= cap) return SPB_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        SPB_CUDA(cudaMalloc(&p, (n + slack) * sizeof(T)));
+        cap = n;
+        return SPB_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t n) {
+        if (n <= cap) return SPB_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        SPB_CUDA(cudaMallocHost(&p, n * sizeof(T)));
+        cap = n;
+        return SPB_OK;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    uint8_t* d_reads = nullptr;
-    uint64_t* d_offsets = nullptr;
-    uint32_t* d_lengths = nullptr;
-    uint64_t* d_pointers = nullptr;
-    uint32_t* d_docs = nullptr;
-    spb_bin_stats* d_stats = nullptr;
-    uint64_t* h_offsets = nullptr;  // pinned staging for chunk-local offsets
+    DevBuf<uint8_t> d_reads, d_out;      // d_out: lengths at the requested width, or the bit map
+    DevBuf<uint64_t> d_offsets, d_pointers_raw;  // pointers: bytes / 8
+    DevBuf<uint32_t> d_docs, d_order, d_packed;
+    DevBuf<spb_bin_stats> d_stats;
+    DevBuf<uint64_t> d_exc_pos;
+    DevBuf<uint8_t> d_exc_val;
+    PinBuf<uint64_t> h_offsets;
+    PinBuf<uint32_t> h_order;
     unsigned long long* d_sat = nullptr;  // clamped-value counter of the launch in flight
     unsigned long long* h_sat = nullptr;  // pinned copy
     bool sat_pending = false;
-    uint64_t cap_bases = 0, cap_reads = 0;
-    bool cap_ms = false, cap_doc = false;
     // on-device text formatting (spb_pml_query_host_text)
-    uint8_t* d_ids = nullptr;
-    uint64_t *d_id_offsets = nullptr, *d_starts = nullptr, *h_id_offsets = nullptr, *h_total = nullptr;
-    char* d_text = nullptr;
-    uint64_t cap_ids = 0, cap_text = 0, cap_text_reads = 0;
+    DevBuf<uint8_t> d_ids;
+    DevBuf<uint64_t> d_id_offsets, d_starts;
+    DevBuf<char> d_text;
+    PinBuf<uint64_t> h_id_offsets;
+    uint64_t* h_total = nullptr;
+    void release() {
+        d_reads.release(); d_out.release(); d_offsets.release(); d_pointers_raw.release(); d_docs.release(); d_order.release();
+        d_packed.release(); d_stats.release(); d_exc_pos.release(); d_exc_val.release(); h_offsets.release(); h_order.release();
+        d_ids.release(); d_id_offsets.release(); d_starts.release(); d_text.release(); h_id_offsets.release();
+        if (d_sat) cudaFree(d_sat);
+        if (h_sat) cudaFreeHost(h_sat);
+        if (h_total) cudaFreeHost(h_total);
+        d_sat = nullptr; h_sat = nullptr; h_total = nullptr; sat_pending = false;
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+// everything one GPU needs to serve queries on a resident copy of the flat image
+struct DeviceCtx {
+    int device = -1;
+    const uint8_t* dev_blob = nullptr;
+    bool own_dev = false;
+    int num_sms = 0;
+    unsigned long long* d_counters = nullptr;
+    std::atomic<uint32_t> counter_next{0};
+    Slot slots[kMaxSlots];
+    PinBuf<uint8_t> h_edges;  // bit-map transport: first / last 32-byte block of every sub-batch (merged by the host)
+    ~DeviceCtx() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        for (auto& s : slots) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.release();
+        }
+        h_edges.release();
+        if (d_counters) cudaFree(d_counters);
+        if (own_dev && dev_blob) cudaFree((void*)dev_blob);
+    }
 };
 
 }  // namespace
@@ -71,118 +142,107 @@ struct spb_index {
     int mode = 0;
     SpbFlatHeader hdr;
     spb::FlatBlob host_blob;
-    int device = -1;
-    const uint8_t* dev_blob = nullptr;
-    bool own_dev = false;
-    int num_sms = 0;
-    unsigned long long* d_counters = nullptr;
-    uint32_t counter_next = 0;
-    uint32_t row_ld = 1;  // move rows allocate in L1 (the neighbour rows of a jump / normalisation hit there); SPUMONI_B200_ROW_LD
-    Slot slots[kMaxSlots];
+    std::vector<std::unique_ptr<DeviceCtx>> devs;  // devs[0] serves the *_device entry points
+    uint32_t row_ld = 1;  // full (32-byte) rows allocate in L1 like the others; SPUMONI_B200_ROW_LD=0 makes them bypass it
     int n_slots = kDefaultSlots;
-    uint64_t chunk_bases = kDefaultChunkBases;
+    uint64_t want_reads = kWantReads, min_chunk_bases = kMinChunkBases, max_chunk_bases = kMaxChunkBases;
+    bool configured = false;
 };
 
 namespace {
 
-int ensure_device_state(spb_index* idx) {
-    if (idx->device < 0 || !idx->dev_blob) return fail(SPB_ERR_NO_DEVICE, "index is not resident on a GPU (call spb_index_to_device)");
-    SPB_CUDA(cudaSetDevice(idx->device));
-    if (!idx->d_counters) {
-        SPB_CUDA(cudaMalloc(&idx->d_counters, kCounters * sizeof(unsigned long long)));
-        SPB_CUDA(cudaDeviceGetAttribute(&idx->num_sms, cudaDevAttrMultiProcessorCount, idx->device));
-        // Every backward-search step is one random 16/32-byte gather; the default L2 fill granularity
-        // drags whole 128-byte lines out of HBM for each of them (ncu: 128 B of DRAM traffic per
-        // step).  Ask for sector-sized fills.  SPUMONI_B200_L2_FETCH=0 keeps the device default.
-        size_t gran = 32;
-        if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) gran = (size_t)std::atoi(e);
-        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);  // a hint: failure is not an error
-        cudaGetLastError();
-        if (const char* e = std::getenv("SPUMONI_B200_ROW_LD")) idx->row_ld = (uint32_t)std::atoi(e);  // development knob
-        if (const char* e = std::getenv("SPUMONI_B200_SLOTS")) { int v = std::atoi(e); if (v >= 1 && v <= kMaxSlots) idx->n_slots = v; }
-        if (const char* e = std::getenv("SPUMONI_B200_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 4096) idx->chunk_bases = (uint64_t)v << 20; }
+void configure(spb_index* idx) {
+    if (idx->configured) return;
+    idx->configured = true;
+    if (const char* e = std::getenv("SPUMONI_B200_ROW_LD")) idx->row_ld = (uint32_t)std::atoi(e);  // development knob
+    if (const char* e = std::getenv("SPUMONI_B200_SLOTS")) { int v = std::atoi(e); if (v >= 1 && v <= kMaxSlots) idx->n_slots = v; }
+    if (const char* e = std::getenv("SPUMONI_B200_CHUNK_MB")) { long v = std::atol(e); if (v >= 1 && v <= 4096) idx->min_chunk_bases = (uint64_t)v << 20; }
+    if (const char* e = std::getenv("SPUMONI_B200_CHUNK_READS")) { long v = std::atol(e); if (v >= 1) idx->want_reads = (uint64_t)v; }
+    if (const char* e = std::getenv("SPUMONI_B200_TEST_CHUNK_BASES")) { long v = std::atol(e); if (v >= 1) idx->min_chunk_bases = idx->max_chunk_bases = (uint64_t)v; }  // tests: tiny sub-batches
+    if (idx->max_chunk_bases < idx->min_chunk_bases) idx->max_chunk_bases = idx->min_chunk_bases;
+}
+
+int ensure_ctx(spb_index* idx, DeviceCtx& c) {
+    configure(idx);
+    SPB_CUDA(cudaSetDevice(c.device));
+    if (!c.d_counters) {
+        SPB_CUDA(cudaMalloc(&c.d_counters, kCounters * sizeof(unsigned long long)));
+        SPB_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
+        // Opt-in only (it is a process-wide device setting): SPUMONI_B200_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity.
+        // Measured without effect on the gathers of this path (profiles/r1_gather_bench_exp1.txt), so the default leaves it alone.
+        if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) {
+            const size_t gran = (size_t)std::atoi(e);
+            if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);  // a hint: failure is not an error
+            cudaGetLastError();
+        }
     }
     return SPB_OK;
 }
 
-void free_slot(Slot& s) {
-    if (s.d_reads) cudaFree(s.d_reads);
-    if (s.d_offsets) cudaFree(s.d_offsets);
-    if (s.d_lengths) cudaFree(s.d_lengths);
-    if (s.d_pointers) cudaFree(s.d_pointers);
-    if (s.d_docs) cudaFree(s.d_docs);
-    if (s.d_stats) cudaFree(s.d_stats);
-    if (s.h_offsets) cudaFreeHost(s.h_offsets);
-    if (s.d_sat) cudaFree(s.d_sat);
-    if (s.h_sat) cudaFreeHost(s.h_sat);
-    if (s.d_ids) cudaFree(s.d_ids);
-    if (s.d_id_offsets) cudaFree(s.d_id_offsets);
-    if (s.d_starts) cudaFree(s.d_starts);
-    if (s.d_text) cudaFree(s.d_text);
-    if (s.h_id_offsets) cudaFreeHost(s.h_id_offsets);
-    if (s.h_total) cudaFreeHost(s.h_total);
-    s.d_ids = nullptr; s.d_id_offsets = nullptr; s.d_starts = nullptr; s.d_text = nullptr; s.h_id_offsets = nullptr; s.h_total = nullptr;
-    s.cap_ids = s.cap_text = s.cap_text_reads = 0;
-    s.d_sat = nullptr; s.h_sat = nullptr; s.sat_pending = false;
-    s.d_reads = nullptr; s.d_offsets = nullptr; s.d_lengths = nullptr; s.d_pointers = nullptr; s.d_docs = nullptr; s.d_stats = nullptr;
-    s.h_offsets = nullptr;
-    s.cap_bases = s.cap_reads = 0;
+DeviceCtx* primary(spb_index* idx) { return idx->devs.empty() ? nullptr : idx->devs[0].get(); }
+
+int ensure_device_state(spb_index* idx) {
+    DeviceCtx* c = primary(idx);
+    if (!c || !c->dev_blob) return fail(SPB_ERR_NO_DEVICE, "index is not resident on a GPU (call spb_index_to_device)");
+    return ensure_ctx(idx, *c);
 }
 
-int ensure_slot(Slot& s, uint64_t bases, uint64_t reads, bool ms, bool doc) {
+int ensure_slot_base(Slot& s) {
     if (!s.stream) SPB_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-    if (bases <= s.cap_bases && reads <= s.cap_reads && (!ms || s.cap_ms) && (!doc || s.cap_doc)) return SPB_OK;
-    ms = ms || s.cap_ms;
-    doc = doc || s.cap_doc;
-    SPB_CUDA(cudaStreamSynchronize(s.stream));
-    const uint64_t nb = bases > s.cap_bases ? bases : s.cap_bases, nr = reads > s.cap_reads ? reads : s.cap_reads;
-    cudaStream_t keep = s.stream;
-    free_slot(s);
-    s.stream = keep;
-    SPB_CUDA(cudaMalloc(&s.d_reads, nb + 512));
-    SPB_CUDA(cudaMalloc(&s.d_offsets, (nr + 1) * sizeof(uint64_t)));
-    SPB_CUDA(cudaMalloc(&s.d_lengths, (nb + 64) * sizeof(uint32_t)));
-    SPB_CUDA(cudaMalloc(&s.d_stats, (nr + 1) * sizeof(spb_bin_stats)));
-    if (ms) SPB_CUDA(cudaMalloc(&s.d_pointers, (nb + 64) * sizeof(uint64_t)));
-    if (doc) SPB_CUDA(cudaMalloc(&s.d_docs, (nb + 64) * sizeof(uint32_t)));
-    SPB_CUDA(cudaMallocHost(&s.h_offsets, (nr + 1) * sizeof(uint64_t)));
-    SPB_CUDA(cudaMalloc(&s.d_sat, sizeof(unsigned long long)));
-    SPB_CUDA(cudaMallocHost(&s.h_sat, sizeof(unsigned long long)));
-    s.cap_bases = nb; s.cap_reads = nr; s.cap_ms = ms; s.cap_doc = doc;
+    if (!s.d_sat) SPB_CUDA(cudaMalloc(&s.d_sat, sizeof(unsigned long long)));
+    if (!s.h_sat) SPB_CUDA(cudaMallocHost(&s.h_sat, sizeof(unsigned long long)));
     return SPB_OK;
 }
 
 // The host entry points hand caller memory to asynchronous copies: whatever way they return (errors included), no
-// copy may still be in flight afterwards.
+// copy may still be in flight afterwards, and no clamped-value count of this call may leak into the next one.
 struct DrainOnExit {
     spb_index* idx;
     ~DrainOnExit() {
-        for (int i = 0; i < kMaxSlots; i++)
-            if (idx->slots[i].stream) cudaStreamSynchronize(idx->slots[i].stream);
+        for (auto& c : idx->devs) {
+            cudaSetDevice(c->device);
+            for (auto& s : c->slots) {
+                if (s.stream) cudaStreamSynchronize(s.stream);
+                s.sat_pending = false;
+            }
+        }
     }
 };
 
-int length_bytes_of(const spb_query_opts* opts) {
+// SPB_LENGTH_BITS -> 0 (kernels' out_width); 0 -> 4
+int out_width_of(const spb_query_opts* opts) {
     const uint32_t w = opts ? opts->length_bytes : 0;
+    if (w == SPB_LENGTH_BITS) return 0;
     return w == 0 ? 4 : (int)w;
 }
+bool width_ok(const spb_query_opts* opts) {
+    const uint32_t w = opts ? opts->length_bytes : 0;
+    return w == 0 || w == 1 || w == 2 || w == 4 || w == SPB_LENGTH_BITS;
+}
 
-int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
+struct LaunchExtras {
+    const uint32_t* d_order = nullptr;
+    uint64_t bit_shift = 0;
+};
+
+int launch_query(spb_index* idx, DeviceCtx& c, bool ms, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                  void* d_lengths, uint64_t* d_pointers, uint32_t* d_docs, spb_bin_stats* d_stats, const spb_query_opts* opts,
-                 unsigned long long* d_saturated, cudaStream_t stream) {
+                 unsigned long long* d_saturated, cudaStream_t stream, const LaunchExtras& ex) {
     if (n_reads == 0) return SPB_OK;
     if ((ms ? 1 : 0) != idx->mode) return fail(SPB_ERR_ARG, ms ? "MS query on a PML index" : "PML query on an MS index");
     if (!d_reads || !d_offsets || !d_lengths || (ms && !d_pointers)) return fail(SPB_ERR_ARG, "null device buffer");
     if (((uintptr_t)d_reads & 255u) != 0) return fail(SPB_ERR_ARG, "d_reads must be 256-byte aligned");
     if (((uintptr_t)d_lengths & 15u) != 0 || ((uintptr_t)d_pointers & 15u) != 0) return fail(SPB_ERR_ARG, "d_lengths / d_pointers must be 16-byte aligned");
     const SpbFlatHeader& h = idx->hdr;
-    const bool has_fast = h.num_fast > 0 && (h.off_mrows != 0 || h.off_mrows8 != 0) && (!ms || h.off_msamp != 0 || h.mrows8_stride == 16);
+    const bool has_fast = h.num_fast > 0 && (h.off_mrows != 0 || h.off_mrows8 != 0 || h.off_mrows32 != 0) && (!ms || h.off_msamp != 0 || h.mrows8_stride == 16);
     int lanes = opts && opts->lanes_per_read ? (int)opts->lanes_per_read : (has_fast ? 1 : kDefaultLanes);
     if (lanes != 1 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) return fail(SPB_ERR_ARG, "lanes_per_read must be 1, 4, 8, 16 or 32");
     if (lanes == 1 && !has_fast) return fail(SPB_ERR_ARG, "lanes_per_read = 1 needs an index with fast symbols (frequent run heads < 0x80)");
-    const int width = length_bytes_of(opts);
-    if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
+    if (!width_ok(opts)) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2, 4 or SPB_LENGTH_BITS");
+    const int width = out_width_of(opts);
     if (width != 4 && lanes != 1) return fail(SPB_ERR_ARG, "narrow length output needs lanes_per_read = 1");
+    if (width == 0 && (ms || d_docs)) return fail(SPB_ERR_ARG, "SPB_LENGTH_BITS describes PML lengths only (no MS, no document numbers)");
+    if (width == 0 && ((uintptr_t)d_lengths & 31u) != 0) return fail(SPB_ERR_ARG, "the bit map must be 32-byte aligned");
     if (d_docs) {
         if (!h.num_docs || !h.off_cdoc) return fail(SPB_ERR_ARG, "document numbers requested but the index was opened without SPB_OPEN_DOC");
         if (lanes != 1 || !h.off_mdoc) return fail(SPB_ERR_ARG, "document numbers need the thread-per-read kernels (lanes_per_read = 1, an index with fast symbols)");
@@ -191,12 +251,12 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     }
     spb::WalkParams p;
     std::memset(&p, 0, sizeof(p));
-    p.runs = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_runs);
-    p.blocks = idx->dev_blob + h.off_blocks;
-    p.crec = reinterpret_cast<const uint4*>(idx->dev_blob + h.off_crec);
-    p.csamp = ms ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_csamp) : nullptr;
-    p.text = ms ? idx->dev_blob + h.off_text : nullptr;
-    p.chartab = reinterpret_cast<const SpbCharTab*>(idx->dev_blob + offsetof(SpbFlatHeader, chartab));
+    p.runs = reinterpret_cast<const uint4*>(c.dev_blob + h.off_runs);
+    p.blocks = c.dev_blob + h.off_blocks;
+    p.crec = reinterpret_cast<const uint4*>(c.dev_blob + h.off_crec);
+    p.csamp = ms ? reinterpret_cast<const uint4*>(c.dev_blob + h.off_csamp) : nullptr;
+    p.text = ms ? c.dev_blob + h.off_text : nullptr;
+    p.chartab = reinterpret_cast<const SpbCharTab*>(c.dev_blob + offsetof(SpbFlatHeader, chartab));
     p.n = h.n; p.R = h.R; p.n_text = h.n_text; p.last_run_sample = h.last_run_sample;
     p.blk_stride = h.blk_stride;
     p.flags = (opts && (opts->flags & SPB_QUERY_TOUPPER)) ? SPB_FLAG_TOUPPER : 0;
@@ -207,122 +267,232 @@ int launch_query(spb_index* idx, bool ms, const uint8_t* d_reads, const uint64_t
     p.bin_width = (opts && d_stats) ? opts->bin_width : 0;
     p.stats = p.bin_width ? d_stats : nullptr;
     p.max_value_thr = opts ? opts->max_value_thr : 0;
-    p.rows = (has_fast && h.off_mrows) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_mrows) : nullptr;
-    p.rows8 = (has_fast && h.off_mrows8) ? reinterpret_cast<const uint64_t*>(idx->dev_blob + h.off_mrows8) : nullptr;
-    p.msamp = (has_fast && ms && h.off_msamp) ? reinterpret_cast<const uint4*>(idx->dev_blob + h.off_msamp) : nullptr;
+    p.rows = (has_fast && h.off_mrows) ? reinterpret_cast<const uint4*>(c.dev_blob + h.off_mrows) : nullptr;
+    p.rows8 = (has_fast && h.off_mrows8) ? reinterpret_cast<const uint64_t*>(c.dev_blob + h.off_mrows8) : nullptr;
+    p.rows32 = (has_fast && h.off_mrows32) ? c.dev_blob + h.off_mrows32 : nullptr;
+    p.msamp = (has_fast && ms && h.off_msamp) ? reinterpret_cast<const uint4*>(c.dev_blob + h.off_msamp) : nullptr;
     p.rows8_stride = h.mrows8_stride;
     for (int i = 0; i < 4; i++) { p.mv_end_k[i] = h.mv_end_k[i]; p.mv_end_off[i] = h.mv_end_off[i]; p.mv_end_sl[i] = h.mv_end_sl[i]; }
     p.out_width = (uint32_t)width;
+    p.bit_shift = ex.bit_shift;
+    p.order = lanes == 1 ? ex.d_order : nullptr;
     p.row_ld = idx->row_ld;
     p.saturated = d_saturated;
     p.docs = d_docs;
     if (d_docs) {
-        p.cdoc = reinterpret_cast<const uint2*>(idx->dev_blob + h.off_cdoc);
-        p.mdoc = reinterpret_cast<const uint2*>(idx->dev_blob + h.off_mdoc);
+        p.cdoc = reinterpret_cast<const uint2*>(c.dev_blob + h.off_cdoc);
+        p.mdoc = reinterpret_cast<const uint2*>(c.dev_blob + h.off_mdoc);
         p.doc_init = h.doc_init; p.doc_absent_ms = h.doc_absent_ms;
         for (int i = 0; i < 4; i++) p.mv_end_doc[i] = h.mv_end_doc[i];
     }
-    p.work_counter = idx->d_counters + 2 * (idx->counter_next++ % (kCounters / 2));
+    p.work_counter = c.d_counters + 2 * (c.counter_next.fetch_add(1) % (kCounters / 2));
     SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, 2 * sizeof(unsigned long long), stream));
     int launched = 0;
-    SPB_CUDA(spb::launch_walk(p, ms, lanes, idx->num_sms, stream, &launched));
+    SPB_CUDA(spb::launch_walk(p, ms, lanes, c.num_sms, stream, &launched));
     g_launches.fetch_add((uint64_t)launched);
     return SPB_OK;
 }
 
-int query_host(spb_index* idx, bool ms, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
-               void* lengths, void* pointers, uint32_t* docs, spb_bin_stats* stats, const spb_query_opts* opts) {
-    if (!idx) return fail(SPB_ERR_ARG, "null index");
-    if (opts && opts->saturated) *opts->saturated = 0;
-    if (n_reads == 0) return SPB_OK;
-    if (!reads || !offsets || !lengths || (ms && !pointers)) return fail(SPB_ERR_ARG, "null host buffer");
-    int rc = ensure_device_state(idx);
+// ---- host query ------------------------------------------------------------------------------------------------------
+struct HostJob {
+    bool ms = false;
+    const uint8_t* reads = nullptr;           // one byte per base, or
+    const uint8_t* packed = nullptr;          // 2 bits per base + exceptions
+    const uint64_t* exc_pos = nullptr;
+    const uint8_t* exc_val = nullptr;
+    uint64_t n_exc = 0;
+    const uint64_t* offsets = nullptr;
+    void* lengths = nullptr;
+    void* pointers = nullptr;
+    uint32_t* docs = nullptr;
+    spb_bin_stats* stats = nullptr;
+    const spb_query_opts* opts = nullptr;
+    int width = 4;          // 4 / 2 / 1 bytes, 0 = bits
+    bool ptr32 = false, want_stats = false, count_sat = false;
+};
+
+struct EdgeRec { uint64_t first_blk, n_blk; };  // bit-map blocks of a sub-batch (32 bytes each), global block indices
+
+// All sub-batches chunks[c_begin, c_end) on one GPU.  edges: 64 bytes per chunk (first / last block of its bit map).
+int run_chunks(spb_index* idx, DeviceCtx& c, const HostJob& job, const std::vector<spb::Chunk>& chunks, size_t c_begin, size_t c_end,
+               uint64_t* total_sat, std::vector<EdgeRec>* edge_recs) {
+    int rc = ensure_ctx(idx, c);
     if (rc) return rc;
-    DrainOnExit drain{idx};
-    const bool want_stats = stats && opts && opts->bin_width;
-    const int width = length_bytes_of(opts);
-    if (width != 1 && width != 2 && width != 4) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2 or 4");
-    const bool ptr32 = ms && opts && (opts->flags & SPB_QUERY_POINTERS32);
-    const bool count_sat = width != 4 || ptr32;
-    const uint64_t ptr_bytes = ptr32 ? 4 : 8;
-    uint64_t total_sat = 0;
-    uint64_t r0 = 0;
-    int chunk = 0;
     const int kSlots = idx->n_slots;
-    const uint64_t kChunkBases = idx->chunk_bases;
-    while (r0 < n_reads) {
-        // sub-batch [r0, r1): at least one read, up to kChunkBases bases
-        uint64_t r1 = r0 + 1;
-        while (r1 < n_reads && offsets[r1 + 1] - offsets[r0] <= kChunkBases) r1++;
-        const uint64_t b0 = offsets[r0], nb = offsets[r1] - b0, nr = r1 - r0;
-        if (offsets[r1] < b0) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
-        Slot& s = idx->slots[chunk % kSlots];
-        rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), ms, docs != nullptr);
+    const bool bits = job.width == 0;
+    const uint64_t ptr_bytes = job.ptr32 ? 4 : 8;
+    if (bits) { rc = c.h_edges.reserve((c_end - c_begin) * 64 + 64); if (rc) return rc; }
+    for (int i = 0; i < kSlots; i++) c.slots[i].sat_pending = false;
+    for (size_t ci = c_begin; ci < c_end; ci++) {
+        const spb::Chunk& ch = chunks[ci];
+        const uint64_t nr = ch.r1 - ch.r0, nb = ch.nb, b0 = ch.b0;
+        Slot& s = c.slots[(ci - c_begin) % (size_t)kSlots];
+        rc = ensure_slot_base(s);
         if (rc) return rc;
         SPB_CUDA(cudaStreamSynchronize(s.stream));  // previous use of this slot (incl. its pinned staging) is done
-        if (s.sat_pending) { total_sat += *s.h_sat; s.sat_pending = false; }
-        for (uint64_t i = 0; i <= nr; i++) {
-            const uint64_t o = offsets[r0 + i];
-            if (o < b0 || (i && o < offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
-            if (i && o - offsets[r0 + i - 1] > 0xFFFFFFFFull) return fail(SPB_ERR_LIMIT, "read longer than 2^32-1 bases");
-            s.h_offsets[i] = o - b0;
+        if (s.sat_pending) { *total_sat += *s.h_sat; s.sat_pending = false; }
+        // buffers (the stream is idle: growing is safe)
+        const uint64_t bit_shift = bits ? (b0 & 255u) : 0;
+        const uint64_t n_blk = bits ? (nb + bit_shift + 255) / 256 : 0;
+        const size_t out_bytes = bits ? (size_t)n_blk * 32 : (size_t)nb * (size_t)job.width;
+        if ((rc = s.d_reads.reserve((size_t)nb + 16, 512)) || (rc = s.d_offsets.reserve((size_t)nr + 1)) || (rc = s.h_offsets.reserve((size_t)nr + 1)) ||
+            (rc = s.d_out.reserve(out_bytes + 64)) || (rc = s.d_stats.reserve(job.want_stats ? (size_t)nr : 0)))
+            return rc;
+        if (job.ms && (rc = s.d_pointers_raw.reserve(((size_t)nb * ptr_bytes + 7) / 8 + 8))) return rc;
+        if (job.docs && (rc = s.d_docs.reserve((size_t)nb + 16))) return rc;
+        for (uint64_t i = 0; i <= nr; i++) s.h_offsets.p[i] = job.offsets[ch.r0 + i] - b0;
+        SPB_CUDA(cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        LaunchExtras ex;
+        ex.bit_shift = bit_shift;
+        // mixed read lengths: the kernel pulls the long reads first
+        if ((rc = s.h_order.reserve((size_t)nr)) || (rc = s.d_order.reserve((size_t)nr))) return rc;
+        if (spb::longest_first_order(job.offsets, ch, s.h_order.p)) {
+            SPB_CUDA(cudaMemcpyAsync(s.d_order.p, s.h_order.p, nr * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            ex.d_order = s.d_order.p;
         }
-        SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-        if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
-        if (count_sat) SPB_CUDA(cudaMemsetAsync(s.d_sat, 0, sizeof(unsigned long long), s.stream));
-        rc = launch_query(idx, ms, s.d_reads, s.d_offsets, nr, s.d_lengths, s.d_pointers, docs ? s.d_docs : nullptr, s.d_stats, opts, count_sat ? s.d_sat : nullptr, s.stream);
+        if (nb && job.packed) {
+            // packed base b0 + i = bit pair (b0 + i) of the caller's array: copy whole 32-bit words, the kernel shifts
+            const uint64_t w0 = b0 / 16, shift = b0 % 16, n_words = (nb + shift + 15) / 16 + 1;
+            if ((rc = s.d_packed.reserve((size_t)n_words))) return rc;
+            SPB_CUDA(cudaMemcpyAsync(s.d_packed.p, job.packed + w0 * 4, n_words * 4, cudaMemcpyHostToDevice, s.stream));
+            const uint64_t* e0 = std::lower_bound(job.exc_pos, job.exc_pos + job.n_exc, b0);
+            const uint64_t* e1 = std::lower_bound(e0, job.exc_pos + job.n_exc, b0 + nb);
+            const uint64_t ne = (uint64_t)(e1 - e0);
+            if (ne) {
+                if ((rc = s.d_exc_pos.reserve((size_t)ne)) || (rc = s.d_exc_val.reserve((size_t)ne))) return rc;
+                SPB_CUDA(cudaMemcpyAsync(s.d_exc_pos.p, e0, ne * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+                SPB_CUDA(cudaMemcpyAsync(s.d_exc_val.p, job.exc_val + (e0 - job.exc_pos), ne, cudaMemcpyHostToDevice, s.stream));
+            }
+            int nl = 0;
+            SPB_CUDA(spb::launch_unpack(s.d_packed.p, (uint32_t)shift, nb, s.d_reads.p, s.d_exc_pos.p, s.d_exc_val.p, ne, b0, c.num_sms, s.stream, &nl));
+            g_launches.fetch_add((uint64_t)nl);
+        } else if (nb)
+            SPB_CUDA(cudaMemcpyAsync(s.d_reads.p, job.reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
+        if (job.count_sat) SPB_CUDA(cudaMemsetAsync(s.d_sat, 0, sizeof(unsigned long long), s.stream));
+        if (bits && n_blk) SPB_CUDA(cudaMemsetAsync(s.d_out.p, 0, (size_t)n_blk * 32, s.stream));
+        rc = launch_query(idx, c, job.ms, s.d_reads.p, s.d_offsets.p, nr, s.d_out.p, job.ms ? s.d_pointers_raw.p : nullptr, job.docs ? s.d_docs.p : nullptr,
+                          job.want_stats ? s.d_stats.p : nullptr, job.opts, job.count_sat ? s.d_sat : nullptr, s.stream, ex);
         if (rc) return rc;
-        if (nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)lengths + b0 * (uint64_t)width, s.d_lengths, nb * (uint64_t)width, cudaMemcpyDeviceToHost, s.stream));
-        if (ms && nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)pointers + b0 * ptr_bytes, s.d_pointers, nb * ptr_bytes, cudaMemcpyDeviceToHost, s.stream));
-        if (docs && nb) SPB_CUDA(cudaMemcpyAsync(docs + b0, s.d_docs, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
-        if (count_sat) {
+        if (bits) {
+            // block g of the caller's map = bases [256 g, 256 g + 256).  The first and the last block of a sub-batch are shared
+            // with its neighbours: they travel through the pinned edge buffer and are OR-ed in by query_host; the blocks in
+            // between go straight to their place.
+            const uint64_t g0 = (b0 - bit_shift) / 256;
+            uint8_t* edge = c.h_edges.p + (ci - c_begin) * 64;
+            (*edge_recs)[ci] = EdgeRec{g0, n_blk};
+            if (n_blk) {
+                SPB_CUDA(cudaMemcpyAsync(edge, s.d_out.p, 32, cudaMemcpyDeviceToHost, s.stream));
+                if (n_blk > 1) SPB_CUDA(cudaMemcpyAsync(edge + 32, s.d_out.p + (n_blk - 1) * 32, 32, cudaMemcpyDeviceToHost, s.stream));
+                if (n_blk > 2) SPB_CUDA(cudaMemcpyAsync((uint8_t*)job.lengths + (g0 + 1) * 32, s.d_out.p + 32, (n_blk - 2) * 32, cudaMemcpyDeviceToHost, s.stream));
+            }
+        } else if (nb)
+            SPB_CUDA(cudaMemcpyAsync((uint8_t*)job.lengths + b0 * (uint64_t)job.width, s.d_out.p, nb * (uint64_t)job.width, cudaMemcpyDeviceToHost, s.stream));
+        if (job.ms && nb) SPB_CUDA(cudaMemcpyAsync((uint8_t*)job.pointers + b0 * ptr_bytes, s.d_pointers_raw.p, nb * ptr_bytes, cudaMemcpyDeviceToHost, s.stream));
+        if (job.docs && nb) SPB_CUDA(cudaMemcpyAsync(job.docs + b0, s.d_docs.p, nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (job.want_stats) SPB_CUDA(cudaMemcpyAsync(job.stats + ch.r0, s.d_stats.p, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
+        if (job.count_sat) {
             SPB_CUDA(cudaMemcpyAsync(s.h_sat, s.d_sat, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
             s.sat_pending = true;
         }
-        r0 = r1;
-        chunk++;
     }
     for (int i = 0; i < kMaxSlots; i++) {
-        Slot& s = idx->slots[i];
+        Slot& s = c.slots[i];
         if (!s.stream) continue;
         SPB_CUDA(cudaStreamSynchronize(s.stream));
-        if (s.sat_pending) { total_sat += *s.h_sat; s.sat_pending = false; }
+        if (s.sat_pending) { *total_sat += *s.h_sat; s.sat_pending = false; }
     }
+    return SPB_OK;
+}
+
+int query_host(spb_index* idx, HostJob job, uint64_t n_reads) {
+    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    const spb_query_opts* opts = job.opts;
+    if (opts && opts->saturated) *opts->saturated = 0;
+    if (n_reads == 0) return SPB_OK;
+    if ((!job.reads && !job.packed) || !job.offsets || !job.lengths || (job.ms && !job.pointers)) return fail(SPB_ERR_ARG, "null host buffer");
+    if (job.packed && job.n_exc && (!job.exc_pos || !job.exc_val)) return fail(SPB_ERR_ARG, "null exception list");
+    if (idx->devs.empty() || !idx->devs[0]->dev_blob) return fail(SPB_ERR_NO_DEVICE, "index is not resident on a GPU (call spb_index_to_device)");
+    configure(idx);
+    if (!width_ok(opts)) return fail(SPB_ERR_ARG, "length_bytes must be 0, 1, 2, 4 or SPB_LENGTH_BITS");
+    job.width = out_width_of(opts);
+    if (job.width == 0 && (job.ms || job.docs)) return fail(SPB_ERR_ARG, "SPB_LENGTH_BITS describes PML lengths only (no MS, no document numbers)");
+    job.want_stats = job.stats && opts && opts->bin_width;
+    job.ptr32 = job.ms && opts && (opts->flags & SPB_QUERY_POINTERS32);
+    job.count_sat = (job.width == 1 || job.width == 2) || job.ptr32;
+    DrainOnExit drain{idx};
+
+    // sub-batches, then contiguous ranges of them per GPU, balanced by bases
+    const size_t n_dev = idx->devs.size();
+    std::vector<spb::Chunk> chunks;
+    try {
+        const uint64_t want = n_dev > 1 ? std::max<uint64_t>(1024, std::min<uint64_t>(idx->want_reads, n_reads / (n_dev * 4) + 1)) : idx->want_reads;
+        chunks = spb::plan_chunks(job.offsets, 0, n_reads, want, idx->min_chunk_bases, idx->max_chunk_bases);
+    } catch (std::length_error& e) {
+        return fail(SPB_ERR_LIMIT, e.what());
+    } catch (std::exception& e) {
+        return fail(SPB_ERR_ARG, e.what());
+    }
+    std::vector<size_t> dev_cut(n_dev + 1, chunks.size());
+    dev_cut[0] = 0;
+    {
+        const uint64_t base0 = job.offsets[0], total = job.offsets[n_reads] - base0;
+        size_t ci = 0;
+        for (size_t d = 1; d < n_dev; d++) {
+            const uint64_t want = base0 + (uint64_t)((unsigned __int128)total * d / n_dev);
+            while (ci < chunks.size() && chunks[ci].b0 + chunks[ci].nb / 2 < want) ci++;
+            dev_cut[d] = ci;
+        }
+    }
+    std::vector<EdgeRec> edge_recs(job.width == 0 ? chunks.size() : 0);
+    std::vector<uint64_t> sat(n_dev, 0);
+    std::vector<int> rcs(n_dev, SPB_OK);
+    std::vector<std::string> errs(n_dev);
+    if (n_dev == 1) {
+        rcs[0] = run_chunks(idx, *idx->devs[0], job, chunks, 0, chunks.size(), &sat[0], &edge_recs);
+        if (rcs[0]) return rcs[0];
+    } else {
+        // one host thread per GPU (the reference's `-t` region, compute_ms_pml.cpp:890-894, is the same shape: independent
+        // workers over disjoint batches of reads sharing a read-only index)
+        std::vector<std::thread> th;
+        for (size_t d = 0; d < n_dev; d++)
+            th.emplace_back([&, d] {
+                rcs[d] = run_chunks(idx, *idx->devs[d], job, chunks, dev_cut[d], dev_cut[d + 1], &sat[d], &edge_recs);
+                if (rcs[d]) errs[d] = g_error;
+            });
+        for (auto& t : th) t.join();
+        for (size_t d = 0; d < n_dev; d++)
+            if (rcs[d]) return fail(rcs[d], "GPU " + std::to_string(idx->devs[d]->device) + ": " + errs[d]);
+    }
+    if (job.width == 0) {
+        // edge blocks, in sub-batch order: a block is assigned by the first sub-batch that touches it and OR-ed by the next
+        uint64_t* out = static_cast<uint64_t*>(job.lengths);
+        uint64_t last_blk = ~0ull;
+        for (size_t d = 0; d < n_dev; d++)
+            for (size_t ci = dev_cut[d]; ci < dev_cut[d + 1]; ci++) {
+                const EdgeRec& e = edge_recs[ci];
+                if (!e.n_blk) continue;
+                const uint64_t* src = reinterpret_cast<const uint64_t*>(idx->devs[d]->h_edges.p + (ci - dev_cut[d]) * 64);
+                for (int half = 0; half < (e.n_blk > 1 ? 2 : 1); half++) {
+                    const uint64_t g = half ? e.first_blk + e.n_blk - 1 : e.first_blk;
+                    for (int q = 0; q < 4; q++) {
+                        if (g == last_blk) out[g * 4 + q] |= src[half * 4 + q];
+                        else out[g * 4 + q] = src[half * 4 + q];
+                    }
+                    last_blk = g;
+                }
+            }
+    }
+    uint64_t total_sat = 0;
+    for (uint64_t v : sat) total_sat += v;
     if (opts && opts->saturated) *opts->saturated = total_sat;
-    if (total_sat) return fail(SPB_ERR_OVERFLOW, std::to_string(total_sat) + " value(s) exceed the narrow length / pointer output and were clamped; repeat with wider outputs");
+    // A clamped PML length loses nothing (lengths[j] != 0 iff the clamped value != 0, and the non-zero values count up from
+    // the right: spb_pml_widen_lengths rebuilds them); clamped MS lengths and 32-bit pointers cannot be rebuilt.
+    if (total_sat && job.ms)
+        return fail(SPB_ERR_OVERFLOW, std::to_string(total_sat) + " value(s) exceed the narrow length / pointer output and were clamped; repeat with wider outputs");
     return SPB_OK;
 }
 
-// buffers of the text path; grown on demand (the slot's stream is idle when this is called)
-int ensure_text_slot(Slot& s, uint64_t reads, uint64_t id_bytes, uint64_t text_bytes) {
-    if (reads > s.cap_text_reads) {
-        if (s.d_id_offsets) cudaFree(s.d_id_offsets);
-        if (s.d_starts) cudaFree(s.d_starts);
-        if (s.h_id_offsets) cudaFreeHost(s.h_id_offsets);
-        s.d_id_offsets = s.d_starts = s.h_id_offsets = nullptr;
-        const uint64_t nr = reads + reads / 4;
-        SPB_CUDA(cudaMalloc(&s.d_id_offsets, (nr + 1) * sizeof(uint64_t)));
-        SPB_CUDA(cudaMalloc(&s.d_starts, (nr + 1) * sizeof(uint64_t)));
-        SPB_CUDA(cudaMallocHost(&s.h_id_offsets, (nr + 1) * sizeof(uint64_t)));
-        s.cap_text_reads = nr;
-    }
-    if (!s.h_total) SPB_CUDA(cudaMallocHost(&s.h_total, sizeof(uint64_t)));
-    if (id_bytes > s.cap_ids) {
-        if (s.d_ids) cudaFree(s.d_ids);
-        s.d_ids = nullptr;
-        SPB_CUDA(cudaMalloc(&s.d_ids, id_bytes + id_bytes / 4 + 64));
-        s.cap_ids = id_bytes + id_bytes / 4;
-    }
-    if (text_bytes > s.cap_text) {
-        if (s.d_text) cudaFree(s.d_text);
-        s.d_text = nullptr;
-        SPB_CUDA(cudaMalloc(&s.d_text, text_bytes + text_bytes / 4 + 64));
-        s.cap_text = text_bytes + text_bytes / 4;
-    }
-    return SPB_OK;
-}
-
+// ---- PML query + on-device decimal formatting (first resident GPU) ----------------------------------------------------
 struct TextChunk { int slot; uint64_t nr, id_bytes; uint32_t elem_bytes; };
 
 int query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads, const uint8_t* ids,
@@ -334,85 +504,92 @@ int query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offset
     if (!reads || !offsets || !ids || !id_offsets || !text) return fail(SPB_ERR_ARG, "null host buffer");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
+    DeviceCtx& c = *primary(idx);
     DrainOnExit drain{idx};
     const bool want_stats = stats && opts && opts->bin_width;
     const int kSlots = idx->n_slots;
-    const uint64_t kChunkBases = idx->chunk_bases;
     spb_query_opts qo;
     std::memset(&qo, 0, sizeof(qo));
     if (opts) qo = *opts;
     qo.saturated = nullptr;
+    std::vector<spb::Chunk> chunks;
+    try {
+        chunks = spb::plan_chunks(offsets, 0, n_reads, idx->want_reads, idx->min_chunk_bases, idx->max_chunk_bases);
+    } catch (std::length_error& e) {
+        return fail(SPB_ERR_LIMIT, e.what());
+    } catch (std::exception& e) {
+        return fail(SPB_ERR_ARG, e.what());
+    }
     uint64_t text_off = 0;
     std::deque<TextChunk> inflight;
 
     // stage 2 of the oldest chunk: its sizes are known -> format on the device, copy the text to its place
     auto finish = [&]() -> int {
-        const TextChunk c = inflight.front();
+        const TextChunk t = inflight.front();
         inflight.pop_front();
-        Slot& s = idx->slots[c.slot];
+        Slot& s = c.slots[t.slot];
         SPB_CUDA(cudaStreamSynchronize(s.stream));
         const uint64_t total = *s.h_total;
         if (text_off + total > text_capacity) { *text_bytes = text_off + total; return fail(SPB_ERR_LIMIT, "text buffer too small"); }
-        int r2 = ensure_text_slot(s, c.nr, c.id_bytes, total);
+        int r2 = s.d_text.reserve((size_t)(total + total / 4), 64);
         if (r2) return r2;
         spb::TextParams tp;
-        tp.values = s.d_lengths; tp.offsets = s.d_offsets; tp.ids = s.d_ids; tp.id_offsets = s.d_id_offsets;
-        tp.n_reads = c.nr; tp.starts = s.d_starts; tp.text = s.d_text; tp.elem_bytes = c.elem_bytes;
-        SPB_CUDA(spb::launch_text_format(tp, idx->num_sms, s.stream));
+        tp.values = s.d_out.p; tp.offsets = s.d_offsets.p; tp.ids = s.d_ids.p; tp.id_offsets = s.d_id_offsets.p;
+        tp.n_reads = t.nr; tp.starts = s.d_starts.p; tp.text = s.d_text.p; tp.elem_bytes = t.elem_bytes;
+        SPB_CUDA(spb::launch_text_format(tp, c.num_sms, s.stream));
         g_launches.fetch_add(1);
-        if (total) SPB_CUDA(cudaMemcpyAsync(text + text_off, s.d_text, total, cudaMemcpyDeviceToHost, s.stream));
+        if (total) SPB_CUDA(cudaMemcpyAsync(text + text_off, s.d_text.p, total, cudaMemcpyDeviceToHost, s.stream));
         text_off += total;
         return SPB_OK;
     };
 
-    uint64_t r0 = 0;
-    int chunk = 0;
-    while (r0 < n_reads) {
-        uint64_t r1 = r0 + 1;
-        while (r1 < n_reads && offsets[r1 + 1] - offsets[r0] <= kChunkBases) r1++;
-        const uint64_t b0 = offsets[r0], nb = offsets[r1] - b0, nr = r1 - r0;
-        if (offsets[r1] < b0) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
-        const int slot = chunk % kSlots;
+    for (size_t ci = 0; ci < chunks.size(); ci++) {
+        const spb::Chunk& ch = chunks[ci];
+        const uint64_t nr = ch.r1 - ch.r0, nb = ch.nb, b0 = ch.b0;
+        const int slot = (int)(ci % (size_t)kSlots);
         while (!inflight.empty() && (int)inflight.size() >= (kSlots + 1) / 2) { rc = finish(); if (rc) return rc; }  // also frees `slot`'s previous use
-        Slot& s = idx->slots[slot];
-        rc = ensure_slot(s, nb > kChunkBases ? nb : kChunkBases, nr > (kChunkBases / 64) ? nr : (kChunkBases / 64), false, false);
-        if (rc) return rc;
+        Slot& s = c.slots[slot];
+        if ((rc = ensure_slot_base(s))) return rc;
         SPB_CUDA(cudaStreamSynchronize(s.stream));
-        const uint64_t i0 = id_offsets[r0], id_bytes = id_offsets[r1] - i0;
-        rc = ensure_text_slot(s, nr, id_bytes, 0);
-        if (rc) return rc;
-        uint64_t max_len = 0;
+        if (id_offsets[ch.r1] < id_offsets[ch.r0]) return fail(SPB_ERR_ARG, "id_offsets are not non-decreasing");
+        const uint64_t i0 = id_offsets[ch.r0], id_bytes = id_offsets[ch.r1] - i0;
+        qo.length_bytes = ch.max_len < 65536 ? 2 : 4;  // a PML never exceeds the read length: uint16 is lossless here
+        if ((rc = s.d_reads.reserve((size_t)nb + 16, 512)) || (rc = s.d_offsets.reserve((size_t)nr + 1)) || (rc = s.h_offsets.reserve((size_t)nr + 1)) ||
+            (rc = s.d_out.reserve((size_t)nb * qo.length_bytes + 64)) || (rc = s.d_stats.reserve(want_stats ? (size_t)nr : 0)) ||
+            (rc = s.d_id_offsets.reserve((size_t)nr + 1)) || (rc = s.d_starts.reserve((size_t)nr + 1)) || (rc = s.h_id_offsets.reserve((size_t)nr + 1)) ||
+            (rc = s.d_ids.reserve((size_t)id_bytes + 64)))
+            return rc;
+        if (!s.h_total) SPB_CUDA(cudaMallocHost(&s.h_total, sizeof(uint64_t)));
         for (uint64_t i = 0; i <= nr; i++) {
-            const uint64_t o = offsets[r0 + i];
-            if (o < b0 || (i && o < offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "offsets are not non-decreasing");
-            if (i && o - offsets[r0 + i - 1] > max_len) max_len = o - offsets[r0 + i - 1];
-            s.h_offsets[i] = o - b0;
-            const uint64_t io = id_offsets[r0 + i];
-            if (io < i0 || (i && io < id_offsets[r0 + i - 1])) return fail(SPB_ERR_ARG, "id_offsets are not non-decreasing");
-            s.h_id_offsets[i] = io - i0;
+            s.h_offsets.p[i] = offsets[ch.r0 + i] - b0;
+            const uint64_t io = id_offsets[ch.r0 + i];
+            if (io < i0 || (i && io < id_offsets[ch.r0 + i - 1])) return fail(SPB_ERR_ARG, "id_offsets are not non-decreasing");
+            s.h_id_offsets.p[i] = io - i0;
         }
-        if (max_len > 0xFFFFFFFFull) return fail(SPB_ERR_LIMIT, "read longer than 2^32-1 bases");
-        qo.length_bytes = max_len < 65536 ? 2 : 4;  // a PML never exceeds the read length: uint16 is lossless here
-        SPB_CUDA(cudaMemcpyAsync(s.d_offsets, s.h_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-        SPB_CUDA(cudaMemcpyAsync(s.d_id_offsets, s.h_id_offsets, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
-        if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
-        if (id_bytes) SPB_CUDA(cudaMemcpyAsync(s.d_ids, ids + i0, id_bytes, cudaMemcpyHostToDevice, s.stream));
-        rc = launch_query(idx, false, s.d_reads, s.d_offsets, nr, s.d_lengths, nullptr, nullptr, s.d_stats, &qo, nullptr, s.stream);
+        SPB_CUDA(cudaMemcpyAsync(s.d_offsets.p, s.h_offsets.p, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        SPB_CUDA(cudaMemcpyAsync(s.d_id_offsets.p, s.h_id_offsets.p, (nr + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s.stream));
+        if (nb) SPB_CUDA(cudaMemcpyAsync(s.d_reads.p, reads + b0, nb, cudaMemcpyHostToDevice, s.stream));
+        if (id_bytes) SPB_CUDA(cudaMemcpyAsync(s.d_ids.p, ids + i0, id_bytes, cudaMemcpyHostToDevice, s.stream));
+        LaunchExtras ex;
+        if ((rc = s.h_order.reserve((size_t)nr)) || (rc = s.d_order.reserve((size_t)nr))) return rc;
+        if (spb::longest_first_order(offsets, ch, s.h_order.p)) {
+            SPB_CUDA(cudaMemcpyAsync(s.d_order.p, s.h_order.p, nr * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            ex.d_order = s.d_order.p;
+        }
+        rc = launch_query(idx, c, false, s.d_reads.p, s.d_offsets.p, nr, s.d_out.p, nullptr, nullptr, want_stats ? s.d_stats.p : nullptr, &qo, nullptr, s.stream, ex);
         if (rc) return rc;
         spb::TextParams tp;
-        tp.values = s.d_lengths; tp.offsets = s.d_offsets; tp.ids = s.d_ids; tp.id_offsets = s.d_id_offsets;
-        tp.n_reads = nr; tp.starts = s.d_starts; tp.text = nullptr; tp.elem_bytes = qo.length_bytes;
-        SPB_CUDA(spb::launch_text_sizes(tp, idx->num_sms, s.stream));
+        tp.values = s.d_out.p; tp.offsets = s.d_offsets.p; tp.ids = s.d_ids.p; tp.id_offsets = s.d_id_offsets.p;
+        tp.n_reads = nr; tp.starts = s.d_starts.p; tp.text = nullptr; tp.elem_bytes = qo.length_bytes;
+        SPB_CUDA(spb::launch_text_sizes(tp, c.num_sms, s.stream));
         g_launches.fetch_add(2);
-        SPB_CUDA(cudaMemcpyAsync(s.h_total, s.d_starts + nr, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
-        if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + r0, s.d_stats, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
+        SPB_CUDA(cudaMemcpyAsync(s.h_total, s.d_starts.p + nr, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + ch.r0, s.d_stats.p, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
         inflight.push_back(TextChunk{slot, nr, id_bytes, qo.length_bytes});
-        r0 = r1;
-        chunk++;
     }
     while (!inflight.empty()) { rc = finish(); if (rc) return rc; }
     for (int i = 0; i < kMaxSlots; i++)
-        if (idx->slots[i].stream) SPB_CUDA(cudaStreamSynchronize(idx->slots[i].stream));
+        if (c.slots[i].stream) SPB_CUDA(cudaStreamSynchronize(c.slots[i].stream));
     *text_bytes = text_off;
     return SPB_OK;
 }
@@ -431,6 +608,62 @@ int guarded(F&& f) {
         return fail(SPB_ERR_FORMAT, e.what());
     }
 }
+
+// ---- replication over several GPUs -------------------------------------------------------------------------------------
+// One ncclBroadcast of the flat image from the first GPU to the others (NCCL over NVLink / NVSwitch; the library is loaded
+// at run time so that nothing links against it), or, when NCCL is not available, a binary tree of peer-to-peer copies.
+struct NcclApi {
+    void* lib = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    bool load() {
+        if (std::getenv("SPUMONI_B200_NO_NCCL")) return false;
+        lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!lib) return false;
+        CommInitAll = (int (*)(void**, int, const int*))dlsym(lib, "ncclCommInitAll");
+        CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+        GroupStart = (int (*)())dlsym(lib, "ncclGroupStart");
+        GroupEnd = (int (*)())dlsym(lib, "ncclGroupEnd");
+        Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclBroadcast");
+        return CommInitAll && CommDestroy && GroupStart && GroupEnd && Broadcast;
+    }
+};
+
+int broadcast_image(std::vector<std::unique_ptr<DeviceCtx>>& devs, size_t bytes, std::string* how) {
+    const int n = (int)devs.size();
+    NcclApi nccl;
+    if (nccl.load()) {
+        std::vector<void*> comms((size_t)n, nullptr);
+        std::vector<int> ids((size_t)n);
+        for (int i = 0; i < n; i++) ids[(size_t)i] = devs[(size_t)i]->device;
+        if (nccl.CommInitAll(comms.data(), n, ids.data()) == 0) {
+            bool ok = nccl.GroupStart() == 0;
+            for (int i = 0; ok && i < n; i++) {
+                cudaSetDevice(ids[(size_t)i]);
+                ok = nccl.Broadcast(devs[0]->dev_blob, (void*)devs[(size_t)i]->dev_blob, bytes, /*ncclChar*/ 0, 0, comms[(size_t)i], (cudaStream_t)0) == 0;
+            }
+            ok = (nccl.GroupEnd() == 0) && ok;
+            for (int i = 0; i < n; i++) { cudaSetDevice(ids[(size_t)i]); if (cudaDeviceSynchronize() != cudaSuccess) ok = false; }
+            for (int i = 0; i < n; i++) if (comms[(size_t)i]) nccl.CommDestroy(comms[(size_t)i]);
+            if (ok) { *how = "ncclBroadcast"; return SPB_OK; }
+            cudaGetLastError();
+        }
+    }
+    // peer copies: after round t the first 2^t GPUs hold the image
+    for (int have = 1; have < n; have *= 2) {
+        for (int i = 0; i < have && have + i < n; i++)
+            SPB_CUDA(cudaMemcpyPeerAsync((void*)devs[(size_t)(have + i)]->dev_blob, devs[(size_t)(have + i)]->device, devs[(size_t)i]->dev_blob, devs[(size_t)i]->device, bytes, 0));
+        for (int i = 0; i < n; i++) { SPB_CUDA(cudaSetDevice(devs[(size_t)i]->device)); SPB_CUDA(cudaDeviceSynchronize()); }
+    }
+    *how = "cudaMemcpyPeer tree";
+    return SPB_OK;
+}
+
+std::string g_replicate_how;
 
 }  // namespace
 
@@ -455,11 +688,14 @@ int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index*
         if (flags & SPB_OPEN_DOC) spb::load_doc_array(ref + ".doc", d);
         std::string text;
         if (ms) text = spb::load_reference_text(ref);
+        const double t2 = now();
+        spb::balance_runs(d, spb::default_balance_params());
         std::unique_ptr<spb_index> idx(new spb_index());
         idx->mode = mode;
-        const double t2 = now();
+        const double t3 = now();
         idx->host_blob = spb::build_flat_image(d, ms, text);
-        if (timing) std::fprintf(stderr, "[timing] index open: parse %.3f s | text/doc %.3f s | flatten %.3f s (%.1f MB)\n", t1 - t0, t2 - t1, now() - t2, idx->host_blob.size() / 1e6);
+        if (timing) std::fprintf(stderr, "[timing] index open: parse %.3f s | text/doc %.3f s | balance %.3f s (%llu runs -> %llu rows) | flatten %.3f s (%.1f MB)\n",
+                                 t1 - t0, t2 - t1, t3 - t2, (unsigned long long)d.R_file, (unsigned long long)d.R, now() - t3, idx->host_blob.size() / 1e6);
         std::memcpy(&idx->hdr, idx->host_blob.data(), sizeof(SpbFlatHeader));
         *out = idx.release();
         return SPB_OK;
@@ -469,7 +705,7 @@ int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index*
 int spb_index_stats(const spb_index* idx, uint64_t* n, uint64_t* r) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     if (n) *n = idx->hdr.n;
-    if (r) *r = idx->hdr.R;
+    if (r) *r = idx->hdr.R_file;  // the runs of the BWT as the reference counts them, not the rows of the flat image
     return SPB_OK;
 }
 
@@ -512,21 +748,45 @@ int spb_index_from_header(const void* header, uint64_t bytes, spb_index** out) {
 }
 
 int spb_index_to_device(spb_index* idx, int device) {
-    if (!idx) return fail(SPB_ERR_ARG, "null index");
+    const int devices[1] = {device};
+    return spb_index_replicate(idx, devices, 1);
+}
+
+int spb_index_replicate(spb_index* idx, const int* devices, int n_devices) {
+    if (!idx || !devices || n_devices < 1) return fail(SPB_ERR_ARG, "spb_index_replicate: bad argument");
     if (idx->host_blob.empty()) return fail(SPB_ERR_ARG, "no host image to upload");
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(SPB_ERR_NO_DEVICE, "no CUDA device available; spumoni_b200 has no CPU fallback");
-    if (device < 0 || device >= count) return fail(SPB_ERR_ARG, "device ordinal out of range");
-    SPB_CUDA(cudaSetDevice(device));
-    if (idx->own_dev && idx->dev_blob) cudaFree((void*)idx->dev_blob);
-    void* p = nullptr;
-    SPB_CUDA(cudaMalloc(&p, idx->host_blob.size()));
-    SPB_CUDA(cudaMemcpy(p, idx->host_blob.data(), idx->host_blob.size(), cudaMemcpyHostToDevice));
-    idx->dev_blob = (const uint8_t*)p;
-    idx->own_dev = true;
-    idx->device = device;
-    return ensure_device_state(idx);
+    for (int i = 0; i < n_devices; i++) {
+        if (devices[i] < 0 || devices[i] >= count) return fail(SPB_ERR_ARG, "device ordinal out of range");
+        for (int j = 0; j < i; j++) if (devices[j] == devices[i]) return fail(SPB_ERR_ARG, "device listed twice");
+    }
+    idx->devs.clear();  // a previous residency (streams, buffers, counters, image copies) goes away with its contexts
+    const size_t bytes = idx->host_blob.size();
+    std::vector<std::unique_ptr<DeviceCtx>> devs;
+    for (int i = 0; i < n_devices; i++) {
+        std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+        SPB_CUDA(cudaSetDevice(devices[i]));
+        void* p = nullptr;
+        SPB_CUDA(cudaMalloc(&p, bytes));
+        c->device = devices[i];
+        c->dev_blob = (const uint8_t*)p;
+        c->own_dev = true;
+        devs.push_back(std::move(c));
+    }
+    SPB_CUDA(cudaSetDevice(devices[0]));
+    SPB_CUDA(cudaMemcpy((void*)devs[0]->dev_blob, idx->host_blob.data(), bytes, cudaMemcpyHostToDevice));
+    if (n_devices > 1) {
+        int rc = broadcast_image(devs, bytes, &g_replicate_how);
+        if (rc) return rc;
+    }
+    idx->devs = std::move(devs);
+    for (auto& c : idx->devs) { int rc = ensure_ctx(idx, *c); if (rc) return rc; }
+    return SPB_OK;
 }
+
+int spb_index_device_count(const spb_index* idx) { return idx ? (int)idx->devs.size() : 0; }
+const char* spb_replicate_method(void) { return g_replicate_how.c_str(); }
 
 int spb_index_attach_device(spb_index* idx, int device, const void* dev_blob, uint64_t bytes) {
     if (!idx || !dev_blob) return fail(SPB_ERR_ARG, "spb_index_attach_device: bad argument");
@@ -537,42 +797,47 @@ int spb_index_attach_device(spb_index* idx, int device, const void* dev_blob, ui
     SPB_CUDA(cudaMemcpy(&chk, dev_blob, sizeof(chk), cudaMemcpyDeviceToHost));
     if (chk.magic != SPB_FLAT_MAGIC || chk.total_bytes != idx->hdr.total_bytes || chk.n != idx->hdr.n || chk.R != idx->hdr.R)
         return fail(SPB_ERR_FORMAT, "device memory does not hold this index's flat image");
-    if (idx->own_dev && idx->dev_blob) cudaFree((void*)idx->dev_blob);
-    idx->dev_blob = (const uint8_t*)dev_blob;
-    idx->own_dev = false;
-    idx->device = device;
+    idx->devs.clear();
+    std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+    c->device = device;
+    c->dev_blob = (const uint8_t*)dev_blob;
+    c->own_dev = false;
+    idx->devs.push_back(std::move(c));
     return ensure_device_state(idx);
 }
 
 void spb_index_close(spb_index* idx) {
-    if (!idx) return;
-    if (idx->device >= 0) {
-        cudaSetDevice(idx->device);
-        for (int i = 0; i < kMaxSlots; i++) {
-            if (idx->slots[i].stream) cudaStreamSynchronize(idx->slots[i].stream);
-            free_slot(idx->slots[i]);
-            if (idx->slots[i].stream) cudaStreamDestroy(idx->slots[i].stream);
-        }
-        if (idx->d_counters) cudaFree(idx->d_counters);
-        if (idx->own_dev && idx->dev_blob) cudaFree((void*)idx->dev_blob);
-    }
-    delete idx;
+    delete idx;  // contexts release their streams, buffers and image copies
 }
 
 int spb_pml_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                        void* lengths, spb_bin_stats* stats, const spb_query_opts* opts) {
-    return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, nullptr, stats, opts);
+    HostJob j;
+    j.reads = reads; j.offsets = offsets; j.lengths = lengths; j.stats = stats; j.opts = opts;
+    return query_host(idx, j, n_reads);
+}
+int spb_pml_query_host_packed(spb_index* idx, const uint8_t* packed, const uint64_t* exc_pos, const uint8_t* exc_val, uint64_t n_exc,
+                              const uint64_t* offsets, uint64_t n_reads, void* lengths, spb_bin_stats* stats, const spb_query_opts* opts) {
+    if (!packed && n_reads) return fail(SPB_ERR_ARG, "null packed reads");
+    HostJob j;
+    j.packed = packed; j.exc_pos = exc_pos; j.exc_val = exc_val; j.n_exc = n_exc;
+    j.offsets = offsets; j.lengths = lengths; j.stats = stats; j.opts = opts;
+    return query_host(idx, j, n_reads);
 }
 int spb_pml_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                            uint32_t* lengths, uint32_t* doc_nums, spb_bin_stats* stats, const spb_query_opts* opts) {
     if (!doc_nums) return fail(SPB_ERR_ARG, "null doc_nums");
-    return query_host(idx, false, reads, offsets, n_reads, lengths, nullptr, doc_nums, stats, opts);
+    HostJob j;
+    j.reads = reads; j.offsets = offsets; j.lengths = lengths; j.docs = doc_nums; j.stats = stats; j.opts = opts;
+    return query_host(idx, j, n_reads);
 }
 int spb_ms_query_host_doc(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                           uint32_t* lengths, uint64_t* pointers, uint32_t* doc_nums, spb_bin_stats* stats,
                           const spb_query_opts* opts) {
     if (!doc_nums) return fail(SPB_ERR_ARG, "null doc_nums");
-    return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, doc_nums, stats, opts);
+    HostJob j;
+    j.ms = true; j.reads = reads; j.offsets = offsets; j.lengths = lengths; j.pointers = pointers; j.docs = doc_nums; j.stats = stats; j.opts = opts;
+    return query_host(idx, j, n_reads);
 }
 uint32_t spb_index_num_docs(const spb_index* idx) { return idx ? idx->hdr.num_docs : 0; }
 int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
@@ -583,15 +848,17 @@ int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t
 }
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                       void* lengths, void* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {
-    return query_host(idx, true, reads, offsets, n_reads, lengths, pointers, nullptr, stats, opts);
+    HostJob j;
+    j.ms = true; j.reads = reads; j.offsets = offsets; j.lengths = lengths; j.pointers = pointers; j.stats = stats; j.opts = opts;
+    return query_host(idx, j, n_reads);
 }
 int spb_pml_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                          void* d_lengths, spb_bin_stats* d_stats, const spb_query_opts* opts, void* cuda_stream) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, nullptr, d_stats, opts,
-                        opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
+    return launch_query(idx, *primary(idx), false, d_reads, d_offsets, n_reads, d_lengths, nullptr, nullptr, d_stats, opts,
+                        opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream, LaunchExtras{});
 }
 int spb_pml_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                              uint32_t* d_lengths, uint32_t* d_doc_nums, spb_bin_stats* d_stats,
@@ -599,7 +866,7 @@ int spb_pml_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint6
     if (!idx || !d_doc_nums) return fail(SPB_ERR_ARG, "null index / doc_nums");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream);
+    return launch_query(idx, *primary(idx), false, d_reads, d_offsets, n_reads, d_lengths, nullptr, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream, LaunchExtras{});
 }
 int spb_ms_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                             uint32_t* d_lengths, uint64_t* d_pointers, uint32_t* d_doc_nums, spb_bin_stats* d_stats,
@@ -607,7 +874,7 @@ int spb_ms_query_device_doc(spb_index* idx, const uint8_t* d_reads, const uint64
     if (!idx || !d_doc_nums) return fail(SPB_ERR_ARG, "null index / doc_nums");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream);
+    return launch_query(idx, *primary(idx), true, d_reads, d_offsets, n_reads, d_lengths, d_pointers, d_doc_nums, d_stats, opts, nullptr, (cudaStream_t)cuda_stream, LaunchExtras{});
 }
 int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* d_offsets, uint64_t n_reads,
                         void* d_lengths, void* d_pointers, spb_bin_stats* d_stats,
@@ -615,8 +882,8 @@ int spb_ms_query_device(spb_index* idx, const uint8_t* d_reads, const uint64_t* 
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     int rc = ensure_device_state(idx);
     if (rc) return rc;
-    return launch_query(idx, true, d_reads, d_offsets, n_reads, d_lengths, (uint64_t*)d_pointers, nullptr, d_stats, opts,
-                        opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream);
+    return launch_query(idx, *primary(idx), true, d_reads, d_offsets, n_reads, d_lengths, (uint64_t*)d_pointers, nullptr, d_stats, opts,
+                        opts ? (unsigned long long*)opts->saturated : nullptr, (cudaStream_t)cuda_stream, LaunchExtras{});
 }
 
 int spb_nulldb_load(const char* path, spb_nulldb* out) {
@@ -646,12 +913,14 @@ int spb_nulldb_generate_host(spb_index* idx, const uint8_t* reads, const uint64_
         spb_query_opts o;
         std::memset(&o, 0, sizeof(o));
         o.flags = SPB_QUERY_TOUPPER;
-        int rc;
+        HostJob j;
+        j.reads = rev.data(); j.offsets = offsets; j.lengths = null_stats; j.opts = &o;
+        std::vector<uint64_t> ptrs;
         if (idx->mode == SPB_MODE_MS) {
-            std::vector<uint64_t> ptrs((size_t)total);
-            rc = query_host(idx, true, rev.data(), offsets, n_reads, null_stats, ptrs.data(), nullptr, nullptr, &o);
-        } else
-            rc = query_host(idx, false, rev.data(), offsets, n_reads, null_stats, nullptr, nullptr, nullptr, &o);
+            ptrs.resize((size_t)total);
+            j.ms = true; j.pointers = ptrs.data();
+        }
+        const int rc = query_host(idx, j, n_reads);
         if (rc) return rc;
         const spb::NullDb db = spb::summarize_null_stats(null_stats, total);
         summary->num_values = db.num_values;
@@ -684,7 +953,7 @@ uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dn
 
 int spb_host_alloc(void** p, size_t bytes) {
     if (!p) return fail(SPB_ERR_ARG, "spb_host_alloc: null");
-    SPB_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    SPB_CUDA(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));  // portable: pinned for every GPU of a replicated index
     return SPB_OK;
 }
 void spb_host_free(void* p) {
@@ -696,5 +965,32 @@ int spb_device_count(void) {
     return count;
 }
 uint64_t spb_kernel_launches(void) { return g_launches.load(); }
+
+// test hooks for the host-side planning (no GPU needed)
+int spb_plan_chunks(const uint64_t* offsets, uint64_t n_reads, uint64_t want_reads, uint64_t min_bases, uint64_t max_bases,
+                    uint64_t* chunk_first_read, uint64_t capacity, uint64_t* n_chunks) {
+    if (!offsets || !n_chunks) return fail(SPB_ERR_ARG, "spb_plan_chunks: bad argument");
+    try {
+        const std::vector<spb::Chunk> c = spb::plan_chunks(offsets, 0, n_reads, want_reads, min_bases, max_bases);
+        *n_chunks = c.size();
+        if (c.size() + 1 > capacity || !chunk_first_read) return c.empty() ? SPB_OK : fail(SPB_ERR_LIMIT, "capacity");
+        for (size_t i = 0; i < c.size(); i++) chunk_first_read[i] = c[i].r0;
+        chunk_first_read[c.size()] = n_reads;
+        return SPB_OK;
+    } catch (std::length_error& e) {
+        return fail(SPB_ERR_LIMIT, e.what());
+    } catch (std::exception& e) {
+        return fail(SPB_ERR_ARG, e.what());
+    }
+}
+int spb_plan_order(const uint64_t* offsets, uint64_t n_reads, uint32_t* order, int* sorted) {
+    if (!offsets || !order || !sorted) return fail(SPB_ERR_ARG, "spb_plan_order: bad argument");
+    spb::Chunk c;
+    c.r0 = 0; c.r1 = n_reads; c.b0 = offsets[0]; c.nb = offsets[n_reads] - offsets[0];
+    c.min_len = ~0ull; c.max_len = 0;
+    for (uint64_t i = 0; i < n_reads; i++) { const uint64_t l = offsets[i + 1] - offsets[i]; c.min_len = std::min(c.min_len, l); c.max_len = std::max(c.max_len, l); }
+    *sorted = spb::longest_first_order(offsets, c, order) ? 1 : 0;
+    return SPB_OK;
+}
 
 }  // extern "C"

@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define SPB_FLAT_MAGIC 0x3030324250535F42ULL /* "B_SPB200" */
-#define SPB_FLAT_VERSION 7u
+#define SPB_FLAT_VERSION 8u
 #define SPB_RUN_PAD 64u  /* sentinel + padding run records past R (start = 2^40-1) */
 #define SPB_POS_MAX 0xFFFFFFFFFFULL
 
@@ -125,6 +125,27 @@ struct SpbMoveRow { uint32_t x, y, z, w; };
 #define SPB_MV8_MAX_RUNS (1ull << 24)
 #define SPB_MV8_ROW_PAD 64u      /* slow-flagged padding rows past R (probing may run past the last run) */
 
+// ---- full move rows (32 bytes per run = one DRAM sector; PML without document numbers) ------------
+// Indexes whose row table does not fit the L2 (r >= 2^24: every step is a DRAM access, and the machine sustains a
+// fixed number of random DRAM accesses per second whatever their size up to a sector pair) get
+// rows that hold everything a step can need, so that a threshold jump costs no second gather: next to the 16-byte
+// row's match fields (dest, len, delta) and threshold codes, the LANDING state of the jump for each of the three other
+// fast symbols -- (dest, delta) of the next run headed by that symbol, i.e. the LF image of its first position; a
+// "down" jump lands one position before it.  "No later run of that symbol" (App. C-6) is folded into the same
+// fields: threshold code ALWAYS and a landing one position past SpbFlatHeader::mv_end.
+//   w0 = dest
+//   w1 = len   (20) | thr0 << 20
+//   w2 = delta (20) | thr1 << 20
+//   w3 = thr2 (12) | fid << 12 | slow << 15 | delta2[0] << 16
+//   w4..w6 = dest2[0..2]                 run holding the landing position of jump slot 0..2
+//   w7 = delta2[1] | delta2[2] << 16     offset of the landing position inside that run (SPB_MV32_D2_MAX at most; a
+//                                         landing that does not fit sets the slot's threshold code to SPB_MV_THR_SLOW)
+//   up   -> (dest2, delta2);   down -> (dest2, delta2 - 1), or (dest2 - 1, SPB_MV_OFF_LAST) when delta2 == 0
+#ifndef SPB_MV32_D2_MAX
+#define SPB_MV32_D2_MAX 0xFFFFu  /* the test build lowers this limit to exercise the fall-back */
+#endif
+struct SpbMoveRow32 { uint32_t w[8]; };
+
 struct SpbFlatHeader {
     uint64_t magic;
     uint32_t version;
@@ -155,7 +176,11 @@ struct SpbFlatHeader {
     uint32_t mv_end_doc[4];      // end_runs_doc of the last c-run per fast symbol
     uint32_t mrows8_stride;      // 8, or 16 (MS, n < 2^32): every compact row is followed by {u32 ss, u32 sl} -- the SpbCharSamp of
                                  // that row in 32 bits -- so that a jump gets its SA sample from the row load itself (no msamp table)
-    uint64_t pad2;               // keeps chartab 16-byte aligned (the kernels load its entries as uint4)
+    uint64_t off_mrows32;        // full 32-byte rows ((R + SPB_MV_ROW_PAD) * 32 bytes, 32-byte aligned); 0 if not built (then
+                                 // off_mrows or off_mrows8 is set).  PML images without a document array only.
+    uint64_t R_file;             // runs of the BWT as stored on disk (what the reference logs); R counts rows: >= R_file when
+                                 // long runs were cut into several rows (index_host.cpp, balance_runs)
+    uint64_t pad3;               // keeps chartab 16-byte aligned (the kernels load its entries as uint4)
     uint64_t F[256];
     SpbCharTab chartab[256];
 };

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -518,6 +519,140 @@ void load_doc_array(const std::string& path, DecodedIndex& d) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Run splitting ("balancing", Nishimoto & Tabei's move structure).  The walk normalises a state (k, off) with
+// off >= len[k] by stepping to the following rows, i.e. a match step costs one row per destination run that the LF image
+// of its run overlaps before the landing position.  On average that is < 2 rows, but a long run whose image covers many
+// short runs makes every step through it a long, divergent walk (one lane of the warp working, hundreds of rows) --
+// and long runs are where the positions are.  A run is therefore cut into sub-runs ("rows") with the same head until
+//   * the LF image of every row overlaps at most `trigger` rows (cut every `target` boundaries), and
+//   * no row is longer than `lcap` (in-run thresholds and offsets then always fit their fields).
+// A sub-run inherits threshold, SA samples and documents of its run: the query semantics do not change (the first
+// sub-run of a run is "the next run of its letter" for everything before it, the last one "the previous run" for
+// everything after it; inside a run only the match step and the signed-char quirk of App. C-1 look at the row, and
+// both read per-run values).  Cutting adds boundaries, so it is iterated to a fixed point (geometric: a fresh piece
+// overlaps `target` rows and is cut again only beyond `trigger`), eight passes at most -- the bound is a performance
+// property, the kernels' loop is correct for any walk length.
+void balance_runs(DecodedIndex& d, const BalanceParams& bp) {
+    d.R_file = d.R;
+    if (bp.trigger == 0 || d.R == 0) return;
+    const uint32_t trigger = bp.trigger, target = std::max<uint32_t>(1, std::min(bp.target, bp.trigger));
+    // the length cap is soft: it may add at most max(R / 2, 2^20) rows (an index of a few runs of 10^10 characters is not
+    // turned into millions of rows; its rows then keep the generic threshold code where an offset does not fit)
+    uint64_t lcap = bp.lcap ? bp.lcap : ~0ull;
+    if (bp.lcap) lcap = std::max<uint64_t>(lcap, d.n / std::max<uint64_t>(d.R / 2, 1ull << 20) + 1);
+    const bool ms = !d.samples_start.empty(), doc = !d.doc_start.empty();
+    for (int pass = 0; pass < 8; pass++) {
+        const uint64_t R = d.R;
+        RawVec<uint64_t> start((size_t)R + 1), lf((size_t)R);
+        {
+            std::vector<uint64_t> sliceC((size_t)(kSlices + 1) * 256, 0), slicePos((size_t)kSlices + 1, 0);
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int c = 0; c < kSlices; c++) {
+                uint64_t* cc = &sliceC[(size_t)(c + 1) * 256];
+                uint64_t tot = 0;
+                for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) { cc[d.heads[(size_t)k]] += d.lens[(size_t)k]; tot += d.lens[(size_t)k]; }
+                slicePos[(size_t)c + 1] = tot;
+            }
+            for (int c = 0; c < kSlices; c++) {
+                slicePos[(size_t)c + 1] += slicePos[(size_t)c];
+                for (int a = 0; a < 256; a++) sliceC[(size_t)(c + 1) * 256 + a] += sliceC[(size_t)c * 256 + a];
+            }
+#pragma omp parallel for schedule(dynamic, 1)
+            for (int c = 0; c < kSlices; c++) {
+                uint64_t seen[256];
+                for (int a = 0; a < 256; a++) seen[a] = d.F[a] + sliceC[(size_t)c * 256 + a];
+                uint64_t pos = slicePos[(size_t)c];
+                for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) {
+                    start[(size_t)k] = pos;
+                    lf[(size_t)k] = seen[d.heads[(size_t)k]];
+                    seen[d.heads[(size_t)k]] += d.lens[(size_t)k];
+                    pos += d.lens[(size_t)k];
+                }
+            }
+            start[(size_t)R] = d.n;
+        }
+        // cut offsets per row, slice by slice: (row, offset inside the row), ascending
+        std::vector<std::vector<std::pair<uint64_t, uint64_t>>> cuts(kSlices);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kSlices; c++) {
+            uint64_t cur[256];
+            for (int a = 0; a < 256; a++) cur[a] = ~0ull;
+            std::vector<uint64_t> offs;
+            auto& out = cuts[(size_t)c];
+            for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) {
+                const uint8_t a = d.heads[(size_t)k];
+                const uint64_t p = lf[(size_t)k], len = d.lens[(size_t)k];
+                uint64_t i = cur[a];
+                if (i == ~0ull) i = (uint64_t)(std::upper_bound(start.begin(), start.end(), p) - start.begin()) - 1;
+                else while (start[(size_t)i + 1] <= p) i++;
+                cur[a] = i;
+                if (len == 1) continue;
+                offs.clear();
+                // boundaries of the row table strictly inside the image (p, p + len)
+                uint64_t j = i + 1, inside = 0;
+                while (j <= R && start[(size_t)j] < p + len) { inside++; j++; }
+                if (inside + 1 > trigger)
+                    for (uint64_t t = target; t <= inside; t += target) offs.push_back(start[(size_t)(i + t)] - p);
+                if (len > lcap) {
+                    const uint64_t pieces = (len + lcap - 1) / lcap;
+                    for (uint64_t q = 1; q < pieces; q++) offs.push_back((uint64_t)((unsigned __int128)len * q / pieces));
+                    std::sort(offs.begin(), offs.end());
+                    offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+                }
+                for (uint64_t o : offs) if (o > 0 && o < len) out.emplace_back(k, o);
+            }
+        }
+        uint64_t total_cuts = 0;
+        std::vector<uint64_t> cut_before((size_t)kSlices + 1, 0);
+        for (int c = 0; c < kSlices; c++) { total_cuts += cuts[(size_t)c].size(); cut_before[(size_t)c + 1] = total_cuts; }
+        if (total_cuts == 0) break;
+        if (R + total_cuts >= 0xFFFFFFFFull - SPB_RUN_PAD) break;  // would leave the 32-bit row index space: keep what we have
+        const uint64_t R2 = R + total_cuts;
+        RawVec<uint8_t> heads2((size_t)R2);
+        RawVec<uint64_t> lens2((size_t)R2), thr2((size_t)R2), ss2(ms ? (size_t)R2 : 0), sl2(ms ? (size_t)R2 : 0);
+        RawVec<uint32_t> ds2(doc ? (size_t)R2 : 0), de2(doc ? (size_t)R2 : 0);
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int c = 0; c < kSlices; c++) {
+            const auto& cs = cuts[(size_t)c];
+            size_t ci = 0;
+            uint64_t w = slice_lo(R, c) + cut_before[(size_t)c];
+            for (uint64_t k = slice_lo(R, c), e = slice_lo(R, c + 1); k < e; k++) {
+                uint64_t prev = 0;
+                for (;;) {
+                    const bool more = ci < cs.size() && cs[ci].first == k;
+                    const uint64_t upto = more ? cs[ci].second : d.lens[(size_t)k];
+                    heads2[(size_t)w] = d.heads[(size_t)k];
+                    lens2[(size_t)w] = upto - prev;
+                    thr2[(size_t)w] = d.thr[(size_t)k];
+                    if (ms) { ss2[(size_t)w] = d.samples_start[(size_t)k]; sl2[(size_t)w] = d.samples_last[(size_t)k]; }
+                    if (doc) { ds2[(size_t)w] = d.doc_start[(size_t)k]; de2[(size_t)w] = d.doc_end[(size_t)k]; }
+                    w++;
+                    prev = upto;
+                    if (!more) break;
+                    ci++;
+                }
+            }
+        }
+        d.heads.swap(heads2); d.lens.swap(lens2); d.thr.swap(thr2);
+        if (ms) { d.samples_start.swap(ss2); d.samples_last.swap(sl2); }
+        if (doc) { d.doc_start.swap(ds2); d.doc_end.swap(de2); }
+        d.R = R2;
+    }
+}
+
+BalanceParams default_balance_params() {
+    BalanceParams bp;  // SPUMONI_B200_BALANCE="trigger,target,lcap" ("0" disables)
+    if (const char* e = std::getenv("SPUMONI_B200_BALANCE")) {
+        unsigned long long a = 0, b = 0, c = 0;
+        const int got = std::sscanf(e, "%llu,%llu,%llu", &a, &b, &c);
+        if (got >= 1) bp.trigger = (uint32_t)a;
+        if (got >= 2) bp.target = (uint32_t)b;
+        if (got >= 3) bp.lcap = c;
+    }
+    return bp;
+}
+
+// ------------------------------------------------------------------------------------------
 static inline uint32_t pack_hi(uint64_t a, int shift) { return (uint32_t)((a >> 32) & 0xFF) << shift; }
 
 FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& text) {
@@ -618,6 +753,7 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
     h.mode = ms ? 1 : 0;
     h.n = n;
     h.R = R;
+    h.R_file = d.R_file ? d.R_file : R;
     h.n_text = ms ? text.size() : 0;
     h.last_run_sample = ms ? (d.samples_last[(size_t)R - 1] + 1) % n : 0;
     h.sigma = sigma;
@@ -658,9 +794,16 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         if (!num_fast) for (int c = 0; c < 256; c++) fid[c] = SPB_SYM_SLOW;
     }
     h.num_fast = num_fast;
-    // row width: 8-byte rows whenever run indices fit 24 bits (SPUMONI_B200_ROWS=16 forces the wide rows, e.g. for tests)
+    // row width: 8-byte rows whenever run indices fit 24 bits (the table then has a chance to live in the L2); otherwise
+    // 32-byte full rows for PML without documents (one DRAM sector per step, jumps included) and 16-byte rows for MS / -d
+    // (their jumps read the samples / documents of the target row anyway).  SPUMONI_B200_ROWS=16|32 forces a layout (tests).
+    const bool use_doc = !d.doc_start.empty();
     bool rows8 = num_fast && R + SPB_MV8_ROW_PAD < SPB_MV8_MAX_RUNS;
-    if (const char* e = std::getenv("SPUMONI_B200_ROWS")) if (std::atoi(e) == 16) rows8 = false;
+    bool rows32 = num_fast && !rows8 && !ms && !use_doc;
+    if (const char* e = std::getenv("SPUMONI_B200_ROWS")) {
+        if (std::atoi(e) == 16) { rows8 = false; rows32 = false; }
+        if (std::atoi(e) == 32 && num_fast && !ms && !use_doc) { rows8 = false; rows32 = true; }
+    }
     if (num_fast) {
         // MS over compact rows: with 32-bit text positions the two samples of a row ride in the same 16 bytes
         bool ms_inline = ms && rows8 && n < (1ull << 32);
@@ -669,6 +812,9 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         if (rows8) {
             h.off_mrows8 = off;
             off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * h.mrows8_stride, 256);
+        } else if (rows32) {
+            h.off_mrows32 = off;
+            off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow32), 256);
         } else {
             h.off_mrows = off;
             off = align_up(off + ((size_t)R + SPB_MV_ROW_PAD) * sizeof(SpbMoveRow), 256);
@@ -678,7 +824,6 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(SpbCharSamp), 256);
         }
     }
-    const bool use_doc = !d.doc_start.empty();
     if (use_doc) {
         h.off_cdoc = off;
         off = align_up(off + ((size_t)num_crec + 1) * sizeof(SpbDocPair), 256);
@@ -817,7 +962,18 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
     }
     if (ms) std::memcpy(blob.data() + h.off_text, text.data(), text.size());
     if (num_fast) {
-        SpbMoveRow* rows = rows8 ? nullptr : reinterpret_cast<SpbMoveRow*>(blob.data() + h.off_mrows);
+        SpbMoveRow* rows = (rows8 || rows32) ? nullptr : reinterpret_cast<SpbMoveRow*>(blob.data() + h.off_mrows);
+        SpbMoveRow32* rows_f = rows32 ? reinterpret_cast<SpbMoveRow32*>(blob.data() + h.off_mrows32) : nullptr;
+        // state of the last BWT position of every fast symbol's F-interval: where a jump lands when no later run of the symbol exists
+        uint32_t end_k[4] = {0, 0, 0, 0};
+        uint64_t end_off[4] = {0, 0, 0, 0};
+        for (uint32_t s = 0; s < num_fast; s++) {
+            const int c = (int)h.fast_sym[s];
+            const uint64_t p = d.F[c] + numC[c] - 1;  // numC[c] >= 1
+            const uint64_t kp = run_of(p);
+            end_k[s] = (uint32_t)kp;
+            end_off[s] = p - start[(size_t)kp];
+        }
         uint64_t* rows_c = rows8 ? reinterpret_cast<uint64_t*>(blob.data() + h.off_mrows8) : nullptr;
         SpbCharSamp* msamp = (ms && h.off_msamp) ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
         SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
@@ -889,6 +1045,29 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
                 rows_c[k * (h.mrows8_stride / 8)] = lo | (hi << 32);
                 continue;
             }
+            if (rows32) {
+                uint32_t dest2[3] = {0, 0, 0}, delta2[3] = {0, 0, 0};
+                for (uint32_t s = 0; s < num_fast && hk < SPB_SYM_SLOW; s++) {
+                    if (s == hk) continue;
+                    const uint32_t slot = s - (s > hk ? 1u : 0u);
+                    const uint32_t k2 = nxt[s];
+                    uint64_t dk, dd;  // landing state of the "up" jump; "down" is one position before it
+                    if (k2 == 0xFFFFFFFFu) { dk = end_k[s]; dd = end_off[s] + 1; }  // always down: lands on mv_end itself
+                    else { dk = dest[k2]; dd = lf[k2] - start[(size_t)dest[k2]]; }
+                    if (dd > SPB_MV32_D2_MAX) { thr3[slot] = SPB_MV_THR_SLOW; continue; }
+                    dest2[slot] = (uint32_t)dk;
+                    delta2[slot] = (uint32_t)dd;
+                }
+                SpbMoveRow32 r;
+                r.w[0] = (uint32_t)de;
+                r.w[1] = (uint32_t)(len_k > SPB_MV_LEN_MASK ? SPB_MV_LEN_MASK : len_k) | (thr3[0] << 20);
+                r.w[2] = (uint32_t)(delta > SPB_MV_LEN_MASK ? SPB_MV_LEN_MASK : delta) | (thr3[1] << 20);
+                r.w[3] = thr3[2] | ((hk > SPB_SYM_SLOW ? SPB_SYM_SLOW : hk) << 12) | ((slow ? 1u : 0u) << 15) | (delta2[0] << 16);
+                r.w[4] = dest2[0]; r.w[5] = dest2[1]; r.w[6] = dest2[2];
+                r.w[7] = delta2[1] | (delta2[2] << 16);
+                rows_f[k] = r;
+                continue;
+            }
             SpbMoveRow r;
             r.x = (uint32_t)de;
             r.y = (uint32_t)(len_k > SPB_MV_LEN_MASK ? SPB_MV_LEN_MASK : len_k) | (thr3[0] << 20);
@@ -902,7 +1081,14 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             for (uint64_t k = R; k < R + SPB_MV8_ROW_PAD; k++)  // row R = "pos == n": generic step only
                 rows_c[k * (h.mrows8_stride / 8)] = ((uint64_t)R | (1ull << 24) | (1ull << 31)) | ((uint64_t)(SPB_SYM_SLOW << 8) << 32);
         }
-        for (uint64_t k = R; !rows8 && k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
+        for (uint64_t k = R; rows32 && k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
+            SpbMoveRow32 r;
+            std::memset(&r, 0, sizeof(r));
+            r.w[0] = (uint32_t)R; r.w[1] = 1;
+            r.w[3] = (SPB_SYM_SLOW << 12) | (1u << 15);
+            rows_f[k] = r;
+        }
+        for (uint64_t k = R; !rows8 && !rows32 && k < R + SPB_MV_ROW_PAD; k++) {  // row R = "pos == n": generic step only
             SpbMoveRow r;
             r.x = (uint32_t)R; r.y = 1; r.z = 0;
             r.w = (SPB_SYM_SLOW << 27) | (1u << 30);
@@ -962,11 +1148,8 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             for (uint32_t s = 0; s < num_fast; s++) hd->mv_end_doc[s] = d.doc_end[(size_t)last_run[h.fast_sym[s]]];
         }
         for (uint32_t s = 0; s < num_fast; s++) {
-            const int c = (int)h.fast_sym[s];
-            const uint64_t p = d.F[c] + numC[c] - 1;  // numC[c] >= 1
-            const uint64_t kp = run_of(p);
-            hd->mv_end_k[s] = (uint32_t)kp;
-            hd->mv_end_off[s] = (uint32_t)std::min<uint64_t>(p - start[(size_t)kp], 0xFFFFFFFEull);
+            hd->mv_end_k[s] = end_k[s];
+            hd->mv_end_off[s] = (uint32_t)std::min<uint64_t>(end_off[s], 0xFFFFFFFEull);
         }
     }
     return blob;

@@ -48,6 +48,7 @@ using FlatBlob = RawVec<uint8_t>;
 // pml_pointers / ms_pointers after decoding every succinct component into plain arrays
 struct DecodedIndex {
     uint64_t n = 0, R = 0, terminator_position = 0;
+    uint64_t R_file = 0;                  // runs of the BWT as stored on disk (R grows when balance_runs cuts runs into rows)
     std::vector<uint64_t> F;              // 256 entries
     RawVec<uint8_t> heads;                // R run heads (bytes <= 1 already stored as 1)
     RawVec<uint64_t> lens;                // R run lengths
@@ -63,6 +64,15 @@ struct NullDb {
 };
 
 DecodedIndex parse_index_file(const std::string& path, bool ms);
+// Cut runs into rows so that the LF image of a row overlaps few rows and no row is too long (index_host.cpp); call after
+// parse_index_file / load_doc_array and before build_flat_image.
+struct BalanceParams {
+    uint32_t trigger = 8;   // cut a row whose LF image overlaps more than this many rows ... (0 = leave the runs alone)
+    uint32_t target = 4;    // ... into pieces that overlap this many
+    uint64_t lcap = 4093;   // and any row longer than this (SPB_MV_THR_MAX: in-run thresholds stay exact); 0 = no cap
+};
+BalanceParams default_balance_params();
+void balance_runs(DecodedIndex& d, const BalanceParams& bp);
 std::string load_reference_text(const std::string& fasta_path);
 NullDb load_null_db(const std::string& path);
 // EmpNullDatabase constructor tail (/root/reference/src/emp_null_database.cpp:42-79) and serialize (:82-102)

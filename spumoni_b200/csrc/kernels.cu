@@ -1,6 +1,7 @@
 // Hand-written sm_100a kernels for SPUMONI's per-read MS/PML backward search.
 //
-//   spb_move_kernel<MS, STATS, OW, LD, ROW8, DOC, MSI>     one thread per read over the move rows (default path)
+//   spb_move_kernel<MS, STATS, OW, LD, RW, DOC, MSI>       one thread per read over the move rows (default path);
+//       RW = bytes per row (8 compact / 16 wide / 32 full), OW = bytes per length (4 / 2 / 1, or 0 = one bit per base)
 //       PML : pml_pointers::_query            /root/reference/src/compute_ms_pml.cpp:237-286 (+ doc numbers :288-340)
 //       MS  : ms_pointers::_query             /root/reference/src/compute_ms_pml.cpp:570-623 (+ doc numbers :625-682)
 //       bin-max classifier (PML, fused)       /root/reference/src/compute_ms_pml.cpp:969-995
@@ -330,6 +331,9 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
 #ifndef SPB_MV_MINB
 #define SPB_MV_MINB 9  /* 128-thread CTAs per SM: 56 registers, no spills (at 10 the 48-register cap spills inside the loop) */
 #endif
+#ifndef SPB_MV_MINB_BITS
+#define SPB_MV_MINB_BITS SPB_MV_MINB  /* PML with bit output: 4 KB of output staging instead of 8 */
+#endif
 
 template <int LD>
 __device__ __forceinline__ uint4 ld_row(const uint4* p) {
@@ -555,19 +559,27 @@ struct BinState {
     uint32_t bin_max = 0, above = 0, below = 0;
 };
 
-// A decoded move row (either layout).  raw0..2 keep the words the jump fields are extracted from.
+// A decoded move row (any layout).  raw0..2 keep the words the jump fields are extracted from.
 struct RowView {
     uint32_t dest, len, delta, hfid;
     bool slow;
     uint32_t raw0, raw1, raw2;
-    uint2 smp;  // MSI only: {ss, sl}
+    uint2 smp;      // MSI only: {ss, sl}
+    uint4 land;     // RW == 32 only: dest2[0..2], delta2[1] | delta2[2] << 16   (delta2[0] = raw2 >> 16)
 };
+__device__ __forceinline__ void ld_row32(const void* p, uint4& a, uint4& b, int ld) {  // one whole sector per instruction
+    if (ld == 0) asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                              : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+    else asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                      : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
 // MSI (MS over compact rows only): every row slot is 16 bytes, {row, u32 ss, u32 sl}: the samples come with the row load
-template <int LD, bool ROW8, bool MSI>
+template <int LD, int RW, bool MSI>
 __device__ __forceinline__ RowView load_row(const WalkParams& p, uint32_t k) {
     RowView r;
     r.smp = make_uint2(0, 0);
-    if (ROW8) {
+    r.land = make_uint4(0, 0, 0, 0);
+    if (RW == 8) {
         uint2 v;  // x = lo, y = hi (flat_index.h)
         if (MSI) {
             const uint4 q = ld_row<LD>(reinterpret_cast<const uint4*>(p.rows8) + k);
@@ -577,6 +589,13 @@ __device__ __forceinline__ RowView load_row(const WalkParams& p, uint32_t k) {
         r.dest = v.x & 0xFFFFFFu; r.len = (v.x >> 24) & 0x7Fu; r.slow = (v.x >> 31) != 0;
         r.delta = v.y & 0xFFu; r.hfid = (v.y >> 8) & 7u;
         r.raw0 = v.y; r.raw1 = 0; r.raw2 = 0;
+    } else if (RW == 32) {
+        uint4 a, b;
+        ld_row32(reinterpret_cast<const uint4*>(p.rows32) + 2 * (size_t)k, a, b, LD);
+        r.dest = a.x; r.len = a.y & SPB_MV_LEN_MASK; r.delta = a.z & SPB_MV_LEN_MASK;
+        r.hfid = (a.w >> 12) & 7u; r.slow = ((a.w >> 15) & 1u) != 0;
+        r.raw0 = a.y; r.raw1 = a.z; r.raw2 = a.w;
+        r.land = b;
     } else {
         const uint4 q = ld_row<LD>(p.rows + k);
         r.dest = q.x; r.len = q.y & SPB_MV_LEN_MASK; r.delta = q.z & SPB_MV_LEN_MASK;
@@ -586,19 +605,61 @@ __device__ __forceinline__ RowView load_row(const WalkParams& p, uint32_t k) {
     return r;
 }
 
+// ---- one bit per base (OW == 0): bit (gi + bit_shift) of the output is set iff the PML at base gi is non-zero, i.e. iff
+// the step was a match (lengths[j] = bit ? lengths[j + 1] + 1 : 0, compute_ms_pml.cpp:249-281: the bits determine every
+// length).  A lane collects 32 bits in a register and parks the word in shared memory every step (branch-free, like the
+// byte stores of the other widths); a whole 32-byte block (256 bases) is written with two 16-byte stores.  Blocks that
+// hold the first or the last bases of a read are shared with the neighbouring reads: their words go out one by one,
+// whole words as plain stores, the one or two shared words as atomicOr of the read's own bits -- the bit map must be
+// zero before the launch.
+#define SPB_BITS_WORDS 8
+__device__ __noinline__ void flush_bits_partial(uint32_t* out, const uint32_t* s_bits, uint64_t blk, uint64_t lo, uint64_t hi) {
+    for (uint32_t j = 0; j < SPB_BITS_WORDS; j++) {
+        const uint64_t wlo = blk * 256 + 32 * j, whi = wlo + 32;
+        if (whi <= lo || wlo >= hi) continue;
+        const uint32_t v = s_bits[j * SPB_MV_THREADS + threadIdx.x];
+        if (wlo >= lo && whi <= hi) { out[blk * SPB_BITS_WORDS + j] = v; continue; }
+        const uint32_t a = (uint32_t)((lo > wlo ? lo : wlo) - wlo), b = (uint32_t)((hi < whi ? hi : whi) - wlo);  // bits [a, b) of the word, b - a < 32
+        const uint32_t mask = ((1u << (b - a)) - 1u) << a;
+        if (v & mask) atomicOr(out + blk * SPB_BITS_WORDS + j, v & mask);
+    }
+}
+// bi = gi + bit_shift: position of the base in the bit map; [blo, bhi) = the read's bit range; acc = the lane's open word
+__device__ __forceinline__ void stage_bit(uint32_t* s_bits, uint32_t* out, uint64_t bi, uint32_t bit, uint64_t blo, uint64_t bhi, uint32_t& acc, bool last) {
+    acc |= bit << ((uint32_t)bi & 31u);
+    s_bits[(((uint32_t)bi >> 5) & (SPB_BITS_WORDS - 1u)) * SPB_MV_THREADS + threadIdx.x] = acc;
+    if (((uint32_t)bi & 31u) == 0) acc = 0;
+    if (((uint32_t)bi & 255u) == 0 || last) {
+        const uint64_t blk = bi >> 8, b0 = blk << 8;
+        if (b0 >= blo && b0 + 256 <= bhi) {
+            uint4 w0, w1;
+            w0.x = s_bits[0 * SPB_MV_THREADS + threadIdx.x]; w0.y = s_bits[1 * SPB_MV_THREADS + threadIdx.x];
+            w0.z = s_bits[2 * SPB_MV_THREADS + threadIdx.x]; w0.w = s_bits[3 * SPB_MV_THREADS + threadIdx.x];
+            w1.x = s_bits[4 * SPB_MV_THREADS + threadIdx.x]; w1.y = s_bits[5 * SPB_MV_THREADS + threadIdx.x];
+            w1.z = s_bits[6 * SPB_MV_THREADS + threadIdx.x]; w1.w = s_bits[7 * SPB_MV_THREADS + threadIdx.x];
+            st_stream16(out + blk * SPB_BITS_WORDS, w0);
+            st_stream16(out + blk * SPB_BITS_WORDS + 4, w1);
+        } else
+            flush_bits_partial(out, s_bits, blk, blo > b0 ? blo : b0, bhi < b0 + 256 ? bhi : b0 + 256);
+    }
+}
+
 // One thread per read, ONE BACKWARD-SEARCH STEP PER LOOP ITERATION for every lane of the warp: load row[k] (walking
 // forward while off >= len), classify the read character (match / threshold jump / generic), for a jump load the row
 // of the next run headed by that character (probing consecutive rows with the compact layout), land, emit.  The
 // jump's second load is predicated, not a separate iteration: an earlier version advanced one *load* per iteration
 // (lanes in different modes) and ran at 14 of 32 lanes per issued instruction; the step-per-iteration form keeps
 // the whole warp on the same instructions and is issue-efficient (profiles/).
-template <bool MS, bool STATS, int OW, int LD, bool ROW8, bool DOC, bool MSI = false>
-__global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB > 8) ? 8 : SPB_MV_MINB) spb_move_kernel(const __grid_constant__ WalkParams p) {
+template <bool MS, bool STATS, int OW, int LD, int RW, bool DOC, bool MSI = false>
+__global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB > 8) ? 8 : ((!MS && OW == 0) ? SPB_MV_MINB_BITS : SPB_MV_MINB)) spb_move_kernel(const __grid_constant__ WalkParams p) {
+    constexpr bool ROW8 = RW == 8;
+    constexpr bool BITS = !MS && OW == 0;
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
     __shared__ uint4 s_rd[SPB_STAGE_CH * SPB_MV_THREADS];   // staged read bytes, see stage_reads
-    __shared__ uint4 s_out[SPB_STAGE_CH * SPB_MV_THREADS];  // staged output values (lengths, or MS pointers)
+    __shared__ uint4 s_out[BITS ? 1 : SPB_STAGE_CH * SPB_MV_THREADS];  // staged output values (lengths, or MS pointers)
+    __shared__ uint32_t s_bits[BITS ? SPB_BITS_WORDS * SPB_MV_THREADS : 1];  // staged match bits (OW == 0)
     __shared__ uint4 s_doc[DOC ? SPB_STAGE_CH * SPB_MV_THREADS : 1];  // staged document numbers
     __shared__ uint32_t s_end_doc[4];
     for (int i = threadIdx.x; i < 256; i += SPB_MV_THREADS) {
@@ -622,13 +683,14 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
     uint64_t base = 0, end = 0, gi = 0;
     uint32_t k = 0, off = 0, length = 0;
     uint64_t sample = 0;
-    uint32_t nsat = 0, doc = 0;
+    uint32_t nsat = 0, doc = 0, bit_acc = 0;
     BinState bs;
 
     for (;;) {
         if (!have) {  // ---- pull the next read (rare, divergent)
             r = atomicAdd(p.work_counter, 1ULL);
             if (r >= p.n_reads) break;
+            if (p.order) r = p.order[r];  // longest reads first (the host sorts mixed-length batches): shorter tail
             base = p.offsets[r];
             const uint64_t m = p.offsets[r + 1] - base;
             if (m == 0) {
@@ -638,6 +700,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             end = base + m;
             gi = end - 1;
             k = R32 - 1; off = SPB_MV_OFF_LAST; length = 0;  // empty string: pos = n-1
+            if (BITS) bit_acc = 0;
             if (MS) sample = p.last_run_sample;
             if (DOC) doc = p.doc_init;
             stage_reads(s_rd, p.reads, gi);
@@ -653,7 +716,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         // ---- the row of the current position: walk forward while off >= len (the LF image of a run may span several runs)
         uint32_t c = rd_bytes[staged_offset((uint32_t)gi & (SPB_STAGE - 1))];
         if (upper && c >= 'a' && c <= 'z') c -= 32;
-        RowView row = load_row<LD, ROW8, MSI>(p, k);
+        RowView row = load_row<LD, RW, MSI>(p, k);
         bool slow = false;
         for (;;) {
             if (row.slow) { slow = true; break; }
@@ -661,16 +724,16 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             if (off < row.len) break;
             off -= row.len;
             k++;
-            row = load_row<LD, ROW8, MSI>(p, k);
+            row = load_row<LD, RW, MSI>(p, k);
         }
         // ---- classify: match (bwt[pos] == c, :250 / :582), threshold jump (:251-279 / :583-616), or the generic step
         const uint32_t s = s_fid[c];
         bool jump = false, endcase = false, down = false;
-        uint32_t k2 = k;
+        uint32_t k2 = k, slot = 0;
         if (!slow) {
             if (s >= SPB_SYM_SLOW) slow = true;
             else if (s != row.hfid) {
-                const uint32_t slot = s - (s > row.hfid ? 1u : 0u);
+                slot = s - (s > row.hfid ? 1u : 0u);
                 uint32_t d;
                 bool gen;
                 if (ROW8) {
@@ -680,8 +743,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
                     down = (cls == 1) || (cls == 2 && off < ((row.raw0 >> 17) & 0x3Fu));
                 } else {
                     const uint32_t v = slot == 0 ? (row.raw0 >> 20) : (slot == 1 ? (row.raw1 >> 20) : (row.raw2 & 0xFFFu));
-                    d = (row.raw2 >> (12u + 5u * slot)) & 31u;
-                    gen = v == SPB_MV_THR_SLOW || d == SPB_MV_DIST_FAR;
+                    d = RW == 32 ? 1u : ((row.raw2 >> (12u + 5u * slot)) & 31u);
+                    gen = v == SPB_MV_THR_SLOW || (RW != 32 && d == SPB_MV_DIST_FAR);
                     down = (v == SPB_MV_THR_ALWAYS) || (off < v);
                 }
                 if (gen) slow = true;
@@ -689,15 +752,16 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
                 else { jump = true; k2 = k + d; }
             }
         }
-        // ---- a jump lands through the row of the next run headed by c (compact rows: row k2 or a later one: probe)
-        if (jump) {
-            row = load_row<LD, ROW8, MSI>(p, k2);
+        // ---- a jump lands through the row of the next run headed by c (compact rows: row k2 or a later one: probe);
+        // full rows carry the landing state themselves
+        if (jump && RW != 32) {
+            row = load_row<LD, RW, MSI>(p, k2);
             if (ROW8) {
                 uint32_t probes = SPB_MV8_PROBES;
                 while (row.hfid != s) {
                     if (--probes == 0) { slow = true; break; }
                     k2++;
-                    row = load_row<LD, ROW8, MSI>(p, k2);
+                    row = load_row<LD, RW, MSI>(p, k2);
                 }
             }
             if (row.slow) slow = true;  // landing state not encodable: generic step from (k, off)
@@ -726,8 +790,13 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             }
             if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
             // first position of the c-run's LF image, or (down) one position before it
-            k = row.dest - ((down && row.delta == 0) ? 1u : 0u);
-            off = row.delta - (down ? 1u : 0u);  // down, delta == 0: 0xFFFFFFFF == SPB_MV_OFF_LAST (last position of the previous row)
+            uint32_t ldest = row.dest, ldelta = row.delta;
+            if (RW == 32) {
+                ldest = slot == 0 ? row.land.x : (slot == 1 ? row.land.y : row.land.z);
+                ldelta = slot == 0 ? (row.raw2 >> 16) : (slot == 1 ? (row.land.w & 0xFFFFu) : (row.land.w >> 16));
+            }
+            k = ldest - ((down && ldelta == 0) ? 1u : 0u);
+            off = ldelta - (down ? 1u : 0u);  // down, delta == 0: 0xFFFFFFFF == SPB_MV_OFF_LAST (last position of the previous row)
             length = 0;
         }
 
@@ -743,9 +812,12 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
                 } else stage_value<8>(s_out, p.pointers, gi, sample, end, last);
             }
             else {
-                uint32_t v = length;
-                if (OW < 4 && v > VMAX) { v = VMAX; nsat++; }
-                stage_value<OW>(s_out, p.lengths, gi, v, end, last);
+                if (BITS) stage_bit(s_bits, reinterpret_cast<uint32_t*>(p.lengths), gi + p.bit_shift, length != 0 ? 1u : 0u, base + p.bit_shift, end + p.bit_shift, bit_acc, last);
+                else {
+                    uint32_t v = length;
+                    if (OW < 4 && v > VMAX) { v = VMAX; nsat++; }
+                    stage_value<(OW ? OW : 4)>(s_out, p.lengths, gi, v, end, last);
+                }
                 if (do_stats) {
                     if (gi < bs.bound) {  // left the bin [bound, ...): close it
                         if (bs.bin_max >= p.max_value_thr) bs.above++; else bs.below++;
@@ -882,26 +954,33 @@ static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms,
     return cudaGetLastError();
 }
 
-template <bool STATS, int LD, bool ROW8>
+template <bool STATS, int LD, int RW>
 static cudaError_t launch_move_pml(const WalkParams& p, int num_sms, cudaStream_t stream) {
     switch (p.out_width) {
-        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD, ROW8, false>, p, num_sms, stream);
-        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD, ROW8, false>, p, num_sms, stream);
-        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD, ROW8, false>, p, num_sms, stream);
+        case 0: return launch_persistent(spb_move_kernel<false, STATS, 0, LD, RW, false>, p, num_sms, stream);
+        case 1: return launch_persistent(spb_move_kernel<false, STATS, 1, LD, RW, false>, p, num_sms, stream);
+        case 2: return launch_persistent(spb_move_kernel<false, STATS, 2, LD, RW, false>, p, num_sms, stream);
+        default: return launch_persistent(spb_move_kernel<false, STATS, 4, LD, RW, false>, p, num_sms, stream);
     }
 }
-template <int LD, bool ROW8>
+template <int LD, int RW>
 static cudaError_t launch_move(const WalkParams& p, bool ms, bool stats, int num_sms, cudaStream_t stream) {
-    if (p.docs) {  // document numbers: u32 lengths, L1-allocating rows only (keeps the number of kernel variants down)
-        if (p.out_width != 4) return cudaErrorInvalidValue;
-        if (ms && ROW8 && p.rows8_stride == 16) return launch_persistent(spb_move_kernel<true, false, 4, 1, ROW8, true, ROW8>, p, num_sms, stream);
-        if (ms) return launch_persistent(spb_move_kernel<true, false, 4, 1, ROW8, true>, p, num_sms, stream);
-        return stats ? launch_persistent(spb_move_kernel<false, true, 4, 1, ROW8, true>, p, num_sms, stream)
-                     : launch_persistent(spb_move_kernel<false, false, 4, 1, ROW8, true>, p, num_sms, stream);
+    constexpr bool ROW8 = RW == 8;
+    if (RW == 32) {  // full rows exist for PML without documents only
+        if (ms || p.docs) return cudaErrorInvalidValue;
+        return stats ? launch_move_pml<true, LD, 32>(p, num_sms, stream) : launch_move_pml<false, LD, 32>(p, num_sms, stream);
     }
-    if (ms && ROW8 && p.rows8_stride == 16) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8, false, ROW8>, p, num_sms, stream);
-    if (ms) return launch_persistent(spb_move_kernel<true, false, 4, LD, ROW8, false>, p, num_sms, stream);
-    return stats ? launch_move_pml<true, LD, ROW8>(p, num_sms, stream) : launch_move_pml<false, LD, ROW8>(p, num_sms, stream);
+    constexpr int RWX = RW == 32 ? 16 : RW;  // (keeps the MS / -d instantiations below out of the RW == 32 case)
+    if (p.docs) {  // document numbers: u32 lengths (keeps the number of kernel variants down)
+        if (p.out_width != 4) return cudaErrorInvalidValue;
+        if (ms && ROW8 && p.rows8_stride == 16) return launch_persistent(spb_move_kernel<true, false, 4, 1, RWX, true, ROW8>, p, num_sms, stream);
+        if (ms) return launch_persistent(spb_move_kernel<true, false, 4, 1, RWX, true>, p, num_sms, stream);
+        return stats ? launch_persistent(spb_move_kernel<false, true, 4, 1, RWX, true>, p, num_sms, stream)
+                     : launch_persistent(spb_move_kernel<false, false, 4, 1, RWX, true>, p, num_sms, stream);
+    }
+    if (ms && ROW8 && p.rows8_stride == 16) return launch_persistent(spb_move_kernel<true, false, 4, 1, RWX, false, ROW8>, p, num_sms, stream);
+    if (ms) return launch_persistent(spb_move_kernel<true, false, 4, 1, RWX, false>, p, num_sms, stream);
+    return stats ? launch_move_pml<true, 1, RWX>(p, num_sms, stream) : launch_move_pml<false, 1, RWX>(p, num_sms, stream);
 }
 template <bool STATS>
 static cudaError_t launch_ms_lengths(const WalkParams& p, int num_sms, cudaStream_t stream) {
@@ -929,10 +1008,14 @@ static cudaError_t launch_t(const WalkParams& p, int num_sms, cudaStream_t strea
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches) {
     const bool stats = p.bin_width && p.stats;
     if (lanes == 1) {
-        if ((!p.rows && !p.rows8) || (ms && !p.msamp && p.rows8_stride != 16)) return cudaErrorInvalidValue;
+        if ((!p.rows && !p.rows8 && !p.rows32) || (ms && !p.msamp && p.rows8_stride != 16)) return cudaErrorInvalidValue;
+        if (p.out_width == 0 && (ms || p.docs)) return cudaErrorInvalidValue;  // one bit per base describes PML lengths only
         cudaError_t e;
-        if (p.rows8) e = p.row_ld ? launch_move<1, true>(p, ms, stats, num_sms, stream) : launch_move<0, true>(p, ms, stats, num_sms, stream);
-        else e = p.row_ld ? launch_move<1, false>(p, ms, stats, num_sms, stream) : launch_move<0, false>(p, ms, stats, num_sms, stream);
+        // rows allocate in L1 (the neighbour rows of a normalisation walk / compact-row probe hit there: +12 % on config 2);
+        // the full rows are one sector each and may bypass it (row_ld = 0, development knob)
+        if (p.rows8) e = launch_move<1, 8>(p, ms, stats, num_sms, stream);
+        else if (p.rows32) e = p.row_ld ? launch_move<1, 32>(p, ms, stats, num_sms, stream) : launch_move<0, 32>(p, ms, stats, num_sms, stream);
+        else e = launch_move<1, 16>(p, ms, stats, num_sms, stream);
         if (launches) *launches = 1;
         if (ms && e == cudaSuccess) {
             e = stats ? launch_ms_lengths<true>(p, num_sms, stream) : launch_ms_lengths<false>(p, num_sms, stream);
@@ -940,7 +1023,7 @@ cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cu
         }
         return e;
     }
-    if (p.out_width != 4 || p.docs || p.ptr32) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths / u64 pointers only, no document numbers
+    if (p.out_width != 4 || p.docs || p.ptr32 || p.order) return cudaErrorInvalidValue;  // the cooperative kernels write u32 lengths / u64 pointers only, no document numbers
     if (launches) *launches = 1;
     switch (lanes) {
         case 4: return ms ? launch_t<4, true>(p, num_sms, stream) : launch_t<4, false>(p, num_sms, stream);
@@ -949,6 +1032,47 @@ cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cu
         case 32: return ms ? launch_t<32, true>(p, num_sms, stream) : launch_t<32, false>(p, num_sms, stream);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// ==========================================================================================
+// 2-bit packed reads (spb_pack_reads, host_util.cpp) -> one byte per base, in place of the H2D copy of the bytes:
+// a quarter of the PCIe traffic; the walk kernels then read the unpacked buffer as usual (2.25 bytes of HBM traffic
+// per base, noise next to the walk).  Base i of the sub-batch is packed base i + shift (a sub-batch starts anywhere in
+// the caller's packed array); every thread turns one 32-bit window into 16 bytes.  Bytes that are not ACGT come from
+// the caller's sorted exception list and are scattered over the unpacked buffer afterwards.
+// ==========================================================================================
+__global__ void __launch_bounds__(256) spb_unpack_kernel(const uint32_t* __restrict__ packed, uint32_t shift, uint64_t n_bases, uint4* __restrict__ reads) {
+    const uint64_t n16 = (n_bases + 15) / 16;
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n16; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w0 = packed[t], w1 = shift ? packed[t + 1] : 0u;  // bases 16 t + shift .. + 15
+        const uint32_t v = __funnelshift_r(w0, w1, 2u * shift);
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t x = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) x |= ((0x54474341u >> (8u * ((v >> (8 * q + 2 * b)) & 3u))) & 0xFFu) << (8 * b);  // "ACGT"
+            o[q] = x;
+        }
+        reads[t] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+__global__ void __launch_bounds__(256) spb_unpack_exceptions_kernel(const uint64_t* __restrict__ pos, const uint8_t* __restrict__ val, uint64_t n, uint64_t b0, uint8_t* __restrict__ reads) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (uint64_t)gridDim.x * blockDim.x) reads[pos[t] - b0] = val[t];
+}
+cudaError_t launch_unpack(const uint32_t* d_packed, uint32_t shift, uint64_t n_bases, uint8_t* d_reads, const uint64_t* d_exc_pos,
+                          const uint8_t* d_exc_val, uint64_t n_exc, uint64_t b0, int num_sms, cudaStream_t stream, int* launches) {
+    if (launches) *launches = 0;
+    if (n_bases == 0) return cudaSuccess;
+    const uint64_t need = ((n_bases + 15) / 16 + 255) / 256, cap = (uint64_t)num_sms * 8;
+    spb_unpack_kernel<<<(unsigned)(need < cap ? need : cap), 256, 0, stream>>>(d_packed, shift, n_bases, reinterpret_cast<uint4*>(d_reads));
+    if (launches) *launches = 1;
+    if (n_exc) {
+        const uint64_t need2 = (n_exc + 255) / 256;
+        spb_unpack_exceptions_kernel<<<(unsigned)(need2 < cap ? need2 : cap), 256, 0, stream>>>(d_exc_pos, d_exc_val, n_exc, b0, d_reads);
+        if (launches) *launches = 2;
+    }
+    return cudaGetLastError();
 }
 
 // ==========================================================================================

@@ -34,12 +34,16 @@ struct WalkParams {
     unsigned long long* work_counter;  // zeroed before launch
     // thread-per-read kernels over the move rows; rows == nullptr when the index has no fast symbols
     const uint4* rows;         // 16-byte move rows, or
-    const uint64_t* rows8;     // 8-byte compact rows (exactly one of rows / rows8 is set)
+    const uint64_t* rows8;     // 8-byte compact rows, or
+    const void* rows32;        // 32-byte full rows (PML without documents)   (exactly one of rows / rows8 / rows32 is set)
     uint32_t rows8_stride;     // 8, or 16 when every row carries its two 32-bit SA samples (MS; then msamp == nullptr)
     const uint4* msamp;        // MS only
     uint32_t mv_end_k[4], mv_end_off[4];
     uint64_t mv_end_sl[4];
-    uint32_t out_width;        // bytes per length value: 4, 2 or 1 (values above the maximum are clamped and counted)
+    uint32_t out_width;        // bytes per length value: 4, 2 or 1 (values above the maximum are clamped and counted), or
+                               // 0 (PML, thread-per-read kernels): one bit per base, `lengths` is a zero-initialised bit map
+    uint64_t bit_shift;        // out_width 0: base i of the batch is bit i + bit_shift of the map
+    const uint32_t* order;     // nullable: the i-th read pulled from the work counter is read order[i] (thread-per-read kernels)
     uint32_t row_ld;           // 0 = rows bypass L1, 1 = rows allocate in L1 (default)
     unsigned long long* saturated;  // nullable; += number of clamped length values
     // document numbers (-d), thread-per-read kernels only; docs == nullptr when not requested
@@ -53,6 +57,12 @@ struct WalkParams {
 // lanes: 4/8/16/32 = cooperative walk kernel (PML or MS); 1 = thread-per-read kernels over the move rows.
 // work_counter must point at two zeroed counters.  *launches (nullable) receives the number of kernels launched.
 cudaError_t launch_walk(const WalkParams& p, bool ms, int lanes, int num_sms, cudaStream_t stream, int* launches);
+
+// 2-bit packed reads -> bytes (d_packed 4-byte aligned, readable up to the word after the last base; d_reads 16-byte
+// aligned, writable up to the next multiple of 16).  Base i of the output is packed base i + shift (shift 0..3 whole bases
+// plus the caller's word alignment, 0..15).  Exceptions: d_reads[pos[i] - b0] = val[i].
+cudaError_t launch_unpack(const uint32_t* d_packed, uint32_t shift, uint64_t n_bases, uint8_t* d_reads, const uint64_t* d_exc_pos,
+                          const uint8_t* d_exc_val, uint64_t n_exc, uint64_t b0, int num_sms, cudaStream_t stream, int* launches);
 
 // K5: decimal formatting of a batch of per-base values on the device -- the text the reference writes with
 // std::copy(..., ostream_iterator<size_t>(f, " ")) (/root/reference/src/compute_ms_pml.cpp:1007-1010):

@@ -31,10 +31,11 @@ def built():
     _ensure_built()
 
 
-@pytest.fixture(params=["8", "16"])
+@pytest.fixture(params=["8", "16", "32"])
 def row_width(request, monkeypatch):
-    """Both move-row layouts of the flat image: compact 8-byte rows (the default when R < 2^24) and the wide
-    16-byte rows (larger indexes); the layout is chosen when an index is opened."""
+    """The move-row layouts of the flat image: compact 8-byte rows (the default when R < 2^24), the wide 16-byte rows
+    (larger MS / -d indexes) and the full 32-byte rows (larger PML indexes; MS / -d images ignore the request and keep
+    their default); the layout is chosen when an index is opened."""
     monkeypatch.setenv("SPUMONI_B200_ROWS", request.param)
     return request.param
 

@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQQ3I4IIQ"  # up to pad2 (then F[256], chartab[256])
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQQ3I4IIQQQ"  # up to pad3 (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -27,6 +27,8 @@ class FlatImage:
         self.num_docs, self.doc_init, self.doc_absent_ms = rest[22], rest[23], rest[24]
         self.mv_end_doc = rest[25:29]
         self.mrows8_stride = rest[29]
+        self.off_mrows32 = rest[30]
+        self.R_file = rest[31]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -43,6 +45,8 @@ class FlatImage:
                 if st == 2:  # inline 32-bit samples: {ss, sl} per row, presented like msamp
                     assert self.off_msamp == 0
                     self.msamp = np.stack([raw[:, 1] & 0xFFFFFFFF, raw[:, 1] >> 32], axis=1)
+            elif self.off_mrows32:
+                self.rows32 = np.frombuffer(b, dtype=np.uint32, count=8 * (self.R + 16), offset=self.off_mrows32).reshape(-1, 8)
             else:
                 self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
             if self.mode == 1 and self.off_msamp:
@@ -281,11 +285,13 @@ class FlatImage:
         """Whichever row table the image holds."""
         if self.off_mrows8:
             return self.walk_move8(read, **{k: v for k, v in kw.items() if k in ("probes",)})
+        if self.off_mrows32:
+            return self.walk_move32(read, **{k: v for k, v in kw.items() if k in ("len_bits",)})
         return self.walk_move(read, **{k: v for k, v in kw.items() if k in ("len_bits", "dist_far")})
 
     def walk_move(self, read: bytes, len_bits=20, dist_far=31):
         """Returns (lengths, pointers or None, stats)."""
-        assert self.num_fast and not self.off_mrows8
+        assert self.num_fast and not self.off_mrows8 and not self.off_mrows32
         ms = self.mode == 1
         LAST, lmask = 0xFFFFFFFF, (1 << len_bits) - 1
         m, R = len(read), self.R
@@ -357,3 +363,62 @@ class FlatImage:
                 stats["fast"] += 1
             out[gi], ptr[gi], self.docs[gi] = length, sample, doc
         return out, (ptr if ms else None), stats
+
+    def walk_move32(self, read: bytes, len_bits=20):
+        """Full 32-byte rows (spb_move_kernel<RW = 32>, PML without documents): a jump lands from the row itself.
+        Returns (lengths, None, stats)."""
+        assert self.num_fast and self.off_mrows32 and self.mode == 0
+        LAST, lmask = 0xFFFFFFFF, (1 << len_bits) - 1
+        m, R = len(read), self.R
+        k, off, length = R - 1, LAST, 0
+        out = [0] * m
+        self.docs = [0] * m
+        stats = {"fast": 0, "norm_iters": 0, "slow": 0, "jump2": 0, "end": 0}
+        for gi in range(m - 1, -1, -1):
+            c = read[gi]
+            slow = False
+            while True:
+                w = [int(v) for v in self.rows32[k]]
+                if (w[3] >> 15) & 1:
+                    slow = True
+                    break
+                ln = w[1] & lmask
+                if off == LAST:
+                    off = ln - 1
+                if off >= ln:
+                    off -= ln
+                    k += 1
+                    stats["norm_iters"] += 1
+                    continue
+                break
+            if not slow:
+                h, s = (w[3] >> 12) & 7, self.fid(c)
+                if s >= 4:
+                    slow = True
+                elif s == h:
+                    length += 1
+                    k, off = w[0], off + (w[2] & lmask)
+                else:
+                    slot = s - (1 if s > h else 0)
+                    v = (w[1] >> 20) if slot == 0 else ((w[2] >> 20) if slot == 1 else (w[3] & 0xFFF))
+                    if v == 0xFFE:
+                        slow = True
+                    else:
+                        down = v == 0xFFF or off < v
+                        de = w[4 + slot]
+                        d2 = (w[3] >> 16) if slot == 0 else ((w[7] & 0xFFFF) if slot == 1 else (w[7] >> 16))
+                        stats["jump2"] += 1
+                        if not down:
+                            k, off = de, d2
+                        elif d2:
+                            k, off = de, d2 - 1
+                        else:
+                            k, off = de - 1, LAST
+                        length = 0
+            if slow:
+                stats["slow"] += 1
+                k, off, length, _ = self.slow_step(k, off, c, length, 0, 0)
+            else:
+                stats["fast"] += 1
+            out[gi] = length
+        return out, None, stats

@@ -31,7 +31,7 @@ def test_header_symbols_are_exported():
 
 def test_abi_version_and_struct_sizes():
     lib = sp.load_library()
-    assert lib.spb_abi_version() == 3
+    assert lib.spb_abi_version() == 4
     assert ctypes.sizeof(sp.QueryOpts) == 32
     assert sp.BinStats.itemsize == 16
     assert sp.flat_header_bytes() % 8 == 0
@@ -76,3 +76,12 @@ def test_cli_validation_messages(small_index, tmp_path):
     assert r.returncode == 1 and "A minimizer type must be specified using -m or -a." in r.stderr
     r = subprocess.run([cli], capture_output=True, text=True)
     assert r.returncode == 1 and "SPUMONI version: 2.0.9" in r.stderr
+
+
+def test_no_gpu_replicate_fails_loudly(small_index):
+    if sp.device_count() > 0:
+        pytest.skip("GPU present")
+    idx = sp.Index.open(small_index["ref"], sp.MODE_PML)
+    with pytest.raises(sp.SpumoniError) as e:
+        idx.replicate([0, 1])
+    assert e.value.code == 5 and idx.device_count() == 0

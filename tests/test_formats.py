@@ -240,3 +240,39 @@ def test_positions_beyond_2_32(huge_periodic_index, row_width):
         assert got == want
         slow += st["slow"]
     assert slow > 0  # run lengths of ~10^8 do not fit the row fields
+
+
+@pytest.mark.parametrize("balance", ["2,1,3", "3,2,0", "0"])
+def test_balanced_rows_keep_the_semantics(tmp_path, row_width, balance, monkeypatch):
+    """balance_runs (index_host.cpp) cuts runs into rows -- here far more aggressively than the defaults: any row whose LF
+    image overlaps more than 2 rows, and any row longer than 3 -- and every table of the flat image is then built over the
+    rows.  The walk over the rows (move rows and generic tables, PML and MS incl. samples) must still equal the oracle on the
+    unmodified index, get_bwt_stats must still report the runs of the file, and the walk must get shorter."""
+    rng = random.Random(5)
+    unit = "ACGTTGCAAGGCTTAACCGGT"
+    text = "".join(unit if rng.random() < 0.9 else rng.choice("ACGT") for _ in range(150)) + "A" * 70 + "".join(rng.choice("ACGTN") for _ in range(300)) + "C" * 50
+    ref = build_index(str(tmp_path), text=text.encode())
+    po, mo = oracle.OracleIndex(ref, "pml"), oracle.OracleIndex(ref, "ms")
+    monkeypatch.setenv("SPUMONI_B200_BALANCE", balance)
+    ip, im = sp.Index.open(ref, sp.MODE_PML), sp.Index.open(ref, sp.MODE_MS)
+    fp, fm = FlatImage(ip.flat()), FlatImage(im.flat())
+    assert ip.get_bwt_stats() == (fp.n, fp.R_file) and fp.R_file == po.stats()[1]
+    assert (fp.R > fp.R_file) == (balance != "0")
+    tb = text.encode()
+    walked = 0
+    for _ in range(40):
+        ln = rng.randint(5, 250)
+        s0 = rng.randint(0, len(tb) - ln)
+        read = bytearray(tb[s0:s0 + ln])
+        for i in range(len(read)):
+            if rng.random() < 0.04:
+                read[i] = rng.choice(b"ACGTN")
+        want = po.matching_statistics(bytes(read)).tolist()
+        got, _, st = fp.walk_rows(bytes(read))
+        assert got == want and fp.walk(bytes(read))[0] == want
+        wl, wp = mo.matching_statistics(bytes(read))
+        _, ptr, _ = fm.walk_rows(bytes(read))
+        assert ptr == wp.tolist() and fm.walk(bytes(read))[1] == wp.tolist()
+        walked += st["norm_iters"]
+    if balance == "2,1,3":
+        assert walked <= 40 * 250  # at most one extra row per step

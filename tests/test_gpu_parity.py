@@ -327,8 +327,8 @@ def test_move_rows_saturation_fallbacks_on_gpu(small_index, tmp_path, row_width)
 
 @pytest.mark.parametrize("mode", ["pml", "ms"])
 def test_narrow_length_outputs(small_index, mode, row_width):
-    """uint16 / uint8 lengths are bit-identical to uint32 when nothing is clamped; a value that does not
-    fit is reported (SPB_ERR_OVERFLOW + count), never silently wrapped."""
+    """uint16 / uint8 lengths are bit-identical to uint32 when nothing is clamped; a value that does not fit is clamped and
+    counted, never silently wrapped."""
     buf, off = load_bin_reads(small_index["reads_bin"])
     idx = sp.pml_t(small_index["ref"]) if mode == "pml" else sp.ms_t(small_index["ref"])
     L4, P4, S4 = idx.query_host(buf, off, bin_width=150, max_value_thr=9)
@@ -340,19 +340,23 @@ def test_narrow_length_outputs(small_index, mode, row_width):
     if over == 0:
         L1, _, S1 = idx.query_host(buf, off, bin_width=150, max_value_thr=9, length_bytes=1)
         assert L1.dtype == np.uint8 and np.array_equal(L1, L4) and np.array_equal(S1, S4)
-    # a read that matches the reference exactly for > 255 bases must overflow uint8 loudly
+    # a read that matches the reference exactly for > 255 bases does not fit uint8: MS reports it (SPB_ERR_OVERFLOW + count,
+    # never silently wrapped); for PML a clamped array is still lossless (zero / non-zero is kept and the non-zero values count
+    # up from the right), so the call succeeds, says how many values it clamped, and spb_pml_widen_lengths rebuilds them --
+    # one long exact match in a batch no longer costs a re-run
     text = open(small_index["ref"]).read().split("\n")[1][:600].encode()
     rb, ro = sp.pack_reads([text, b"ACGT"])
     Lw, _, _ = idx.query_host(rb, ro)
     assert int(Lw.max()) > 255
-    with pytest.raises(sp.SpumoniError) as ei:
-        idx.query_host(rb, ro, length_bytes=1)
-    assert ei.value.code == sp.ERR_OVERFLOW and ei.value.saturated == int(np.count_nonzero(Lw > 255))
     out1 = np.zeros(len(rb), dtype=np.uint8)
-    try:
+    if mode == "ms":
+        with pytest.raises(sp.SpumoniError) as ei:
+            idx.query_host(rb, ro, length_bytes=1, out_lengths=out1)
+        assert ei.value.code == sp.ERR_OVERFLOW and ei.value.saturated == int(np.count_nonzero(Lw > 255))
+    else:
         idx.query_host(rb, ro, length_bytes=1, out_lengths=out1)
-    except sp.SpumoniError:
-        pass
+        assert int(idx.last_saturated.value) == int(np.count_nonzero(Lw > 255))
+        assert np.array_equal(sp.widen_lengths(out1, ro), Lw)
     assert np.array_equal(out1, np.minimum(Lw, 255).astype(np.uint8))  # clamped, otherwise complete
     # the cooperative kernels only write uint32
     with pytest.raises(sp.SpumoniError):
@@ -572,3 +576,103 @@ def test_ms_pointers32(small_index, tmp_path, row_width):
     assert ei.value.code == sp.ERR_OVERFLOW and ei.value.saturated == 3
     with pytest.raises(sp.SpumoniError):
         ms.query_host(rb, ro, pointer_bytes=4, lanes=8)
+
+
+def test_bit_output_and_packed_input(small_index, row_width):
+    """The compact transports of the PML call: one bit per base out (SPB_LENGTH_BITS), 2 bits per base in
+    (spb_pml_query_host_packed, non-ACGT bytes through the exception list) -- both lossless, alone and together, with the
+    classifier statistics unchanged; several sub-batches (edge blocks of the bit map are merged on the host)."""
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    buf = buf.copy()
+    buf[::97] = ord("N")
+    buf[5::211] = ord("a")  # lower case: verbatim without toupper, upper-cased with it
+    idx = sp.pml_t(small_index["ref"])
+    for up in (False, True):
+        L4, _, S4 = idx.query_host(buf, off, bin_width=150, max_value_thr=9, toupper=up)
+        bits, _, Sb = idx.query_host(buf, off, bin_width=150, max_value_thr=9, toupper=up, length_bytes=sp.LENGTH_BITS)
+        assert np.array_equal(sp.expand_bits(bits, off), L4) and np.array_equal(Sb, S4)
+        packed = sp.pack_reads_2bit(buf, toupper=up)
+        assert packed[1].size > 0
+        Lp, _, Sp = idx.query_host(None, off, bin_width=150, max_value_thr=9, toupper=up, packed=packed)
+        assert np.array_equal(Lp, L4) and np.array_equal(Sp, S4)
+        bp, _, _ = idx.query_host(None, off, toupper=up, packed=packed, length_bytes=sp.LENGTH_BITS)
+        assert np.array_equal(bp, bits)
+
+
+def test_bit_output_many_sub_batches(small_index, monkeypatch):
+    """Sub-batches of a few reads each: every sub-batch boundary falls inside a 32-byte block of the bit map and inside a
+    packed word; short and empty reads share words."""
+    monkeypatch.setenv("SPUMONI_B200_TEST_CHUNK_BASES", "700")  # sub-batches close after 700 bases
+    monkeypatch.setenv("SPUMONI_B200_CHUNK_READS", "3")
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    reads = [bytes(buf[int(off[i]):int(off[i + 1])]) for i in range(len(off) - 1)]
+    reads = reads[:40] + [b"", b"A", b"", b"ACG", b"T" * 31, b"G" * 33] + reads[40:120]
+    rb, ro = sp.pack_reads(reads)
+    idx = sp.pml_t(small_index["ref"])
+    L4, _, _ = idx.query_host(rb, ro)
+    Lo, _ = oracle_batch(small_index["ref"], "pml", rb, ro)
+    assert np.array_equal(L4.astype(np.uint64), Lo)
+    bits, _, _ = idx.query_host(rb, ro, length_bytes=sp.LENGTH_BITS)
+    assert np.array_equal(sp.expand_bits(bits, ro), L4)
+    bp, _, _ = idx.query_host(None, ro, packed=sp.pack_reads_2bit(rb), length_bytes=sp.LENGTH_BITS)
+    assert np.array_equal(bp, bits)
+
+
+def test_bits_device_api(small_index):
+    import torch
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    Lo, _ = oracle_batch(small_index["ref"], "pml", buf, off)
+    idx = sp.pml_t(small_index["ref"])
+    dev = torch.device("cuda", 0)
+    d_reads = torch.zeros(len(buf) + 512, dtype=torch.uint8, device=dev)
+    d_reads[: len(buf)] = torch.from_numpy(buf).to(dev)
+    d_off = torch.from_numpy(off.astype(np.int64)).to(dev)
+    d_bits = torch.zeros(sp.bits_bytes(len(buf)) // 8, dtype=torch.int64, device=dev)
+    idx.query_device(d_reads, d_off, len(off) - 1, d_bits)
+    torch.cuda.synchronize()
+    assert np.array_equal(sp.expand_bits(d_bits.cpu().numpy().view(np.uint64), off).astype(np.uint64), Lo)
+
+
+def test_mixed_lengths_longest_first(small_index):
+    """A sub-batch with very different read lengths is walked longest read first (order array); outputs stay in input order."""
+    text = open(small_index["ref"]).read().split("\n")[1].encode()
+    rng = np.random.default_rng(5)
+    reads = []
+    for i in range(300):
+        ln = int(rng.choice([30, 150, 1000, 6000]))
+        s0 = int(rng.integers(0, len(text) - ln))
+        r = bytearray(text[s0:s0 + ln])
+        for j in range(0, ln, 37):
+            r[j] = ord("ACGT"[int(rng.integers(0, 4))])
+        reads.append(bytes(r))
+    rb, ro = sp.pack_reads(reads)
+    assert sp.plan_order(ro) is not None
+    Lo, _ = oracle_batch(small_index["ref"], "pml", rb, ro)
+    for mode_idx in (sp.pml_t(small_index["ref"]),):
+        L, _, S = mode_idx.query_host(rb, ro, bin_width=150, max_value_thr=9)
+        assert np.array_equal(L.astype(np.uint64), Lo)
+    ms = sp.ms_t(small_index["ref"])
+    Lm, Pm, _ = ms.query_host(rb, ro)
+    Lmo, Pmo = oracle_batch(small_index["ref"], "ms", rb, ro)
+    assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
+
+
+def test_replicated_index_two_gpus(small_index):
+    """spb_index_replicate: the flat image is broadcast to a second GPU and host queries are sharded by bases over both;
+    results equal the single-GPU ones (lengths, statistics, bit map with its shared edge blocks)."""
+    if sp.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    buf, off = load_bin_reads(small_index["reads_bin"])
+    one = sp.pml_t(small_index["ref"])
+    two = sp.Index.open(small_index["ref"], sp.MODE_PML).replicate([0, 1])
+    assert two.device_count() == 2 and sp.load_library().spb_replicate_method().decode() in ("ncclBroadcast", "cudaMemcpyPeer tree")
+    L1, _, S1 = one.query_host(buf, off, bin_width=150, max_value_thr=9)
+    L2, _, S2 = two.query_host(buf, off, bin_width=150, max_value_thr=9)
+    assert np.array_equal(L1, L2) and np.array_equal(S1, S2)
+    b1, _, _ = one.query_host(buf, off, length_bytes=sp.LENGTH_BITS)
+    b2, _, _ = two.query_host(buf, off, length_bytes=sp.LENGTH_BITS)
+    assert np.array_equal(b1, b2)
+    ms2 = sp.Index.open(small_index["ref"], sp.MODE_MS).replicate([1, 0])
+    Lm, Pm, _ = ms2.query_host(buf, off)
+    Lmo, Pmo = oracle_batch(small_index["ref"], "ms", buf, off)
+    assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
