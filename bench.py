@@ -284,6 +284,49 @@ def run_reference(args, name):
     emit(out)
 
 
+def cli_seconds(ref, name, seed, threads, extra_env=None):
+    """`spumoni run -P -n -c -t threads` of the product CLI on the workload's reads as a FASTA file: the seconds of the phase the
+    reference times ("processing the patterns", compute_ms_pml.cpp:1324-1337; index loading is outside it) + the per-stage
+    busy times the CLI prints with SPUMONI_B200_TIMING."""
+    import spumoni_b200 as sp
+    w = WORKLOADS[name]
+    d = cache_dir(name)
+    fa = os.path.join(d, f"reads_s{seed}.fa")
+    if not os.path.exists(fa):
+        if "synth" in w:
+            return None
+        subprocess.check_call([MKINDEX, "reads", "--ref", ref, "--n", str(w["n_reads"]), "--len", str(w["read_len"]), "--seed", str(seed),
+                               "--out", fa + ".tmp"] + w["reads"], stdout=subprocess.DEVNULL)
+        os.replace(fa + ".tmp", fa)
+    db = ref + ".pmlnulldb"
+    if not os.path.exists(db):
+        stats = os.path.join(d, "null_stats.bin")
+        ((np.arange(1, 2000, dtype=np.uint64) * 7) % 23).tofile(stats)
+        subprocess.check_call([MKINDEX, "nulldb", "--stats", stats, "--out", db], stdout=subprocess.DEVNULL)
+    env = dict(os.environ, SPUMONI_B200_TIMING="1", **(extra_env or {}))
+    t0 = time.perf_counter()
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", ref[:-3], "-p", fa, "-P", "-n", "-c", "-t", str(threads)], capture_output=True, text=True, env=env)
+    wall = time.perf_counter() - t0
+    err = re.sub(r"\x1b\[[0-9;]*m", "", r.stderr)
+    m = None
+    for m in re.finditer(r"done\.\s+\(([0-9.]+) sec\)", err):  # the last one closes "processing the patterns"
+        pass
+    if r.returncode != 0 or not m:
+        log("CLI run failed:\n" + err[-1500:])
+        return None
+    out = {"phase_s": float(m.group(1)), "wall_s": wall, "threads": threads, "bytes_out": os.path.getsize(fa + ".pseudo_lengths")}
+    st = re.search(r"busy seconds per stage: (.*)", err)
+    if st:
+        out["stages"] = st.group(1).strip()
+    g = re.search(r"\[timing\] devices: (.*)", err)
+    if g:
+        out["devices"] = g.group(1).strip()
+    for ext in (".pseudo_lengths", ".report"):
+        if os.path.exists(fa + ext):
+            os.remove(fa + ext)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -292,12 +335,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per read (tuning; 0 = library default)")
     ap.add_argument("--length-bytes", type=int, default=1, choices=[1, 2, 4],
-                    help="element size of the lengths output (1/2 are checked lossless: a clamped value fails the step and it is redone wider)")
-    ap.add_argument("--mode", default="pml", choices=["pml", "ms"], help="pml = the headline metric (BASELINE configs[1]); ms = configs[2], a secondary line")
+                    help="element size of the lengths output of the headline measurement (clamped PML lengths stay lossless, see include/spumoni_b200.h)")
+    ap.add_argument("--mode", default="pml", choices=["pml", "ms"], help="pml = the headline metric (BASELINE configs[1]); ms = configs[2]")
     ap.add_argument("--pointers64", action="store_true", help="--mode ms: keep 64-bit pointers even when 32 bits are lossless")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-variants", action="store_true", help="skip the extra 4-byte-lengths measurement")
+    ap.add_argument("--no-variants", action="store_true", help="skip the secondary measurements (other output formats, MS, -c statistics, CLI)")
+    ap.add_argument("--variants", default="u16,u32,bits,packed_bits,pml_stats,ms,cli", help="which secondary measurements to run (comma-separated)")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: a fixed set of 5 x the workload's reads is sharded by bases over the ranks (BASELINE configs[3])")
     args = ap.parse_args()
+    want = set() if args.no_variants else set(v for v in args.variants.split(",") if v)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     name = os.environ.get("SPB_BENCH_WORKLOAD", "c2")
     w = WORKLOADS[name]
@@ -329,22 +375,55 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     # ---------------- untimed setup: index (rank 0 builds + parses, NCCL broadcast), reads per rank
     mode = args.mode
-    MODE = sp.MODE_PML if mode == "pml" else sp.MODE_MS
     if rank == 0:
         ref = ensure_index(name, mode)
     barrier()
     ref = os.path.join(cache_dir(name), "idx.fa")
-    t0 = time.time()
-    if world > 1:
-        idx = broadcast_index(sp.Index.open(ref, MODE) if rank == 0 else None, device=local, src=0)
-    else:
-        idx = sp.Index.open(ref, MODE).to_device(local)
+
+    def open_index(m):
+        MODE = sp.MODE_PML if m == "pml" else sp.MODE_MS
+        t0 = time.time()
+        if world > 1:
+            ix = broadcast_index(sp.Index.open(ref, MODE) if rank == 0 else None, device=local, src=0)
+        else:
+            ix = sp.Index.open(ref, MODE).to_device(local)
+        log(f"rank {rank}: {m} index resident in {time.time() - t0:.1f} s")
+        return ix
+
+    idx = open_index(mode)
     n, r = idx.get_bwt_stats()
-    log(f"rank {rank}: index resident (n={n}, r={r}) in {time.time() - t0:.1f} s")
-    buf, off = ensure_reads(name, ref, seed=4 + rank)
+    if args.strong:  # one fixed read set for any N: 5 x the workload's reads, this rank's shard by bases
+        b1, o1 = ensure_reads(name, ref, seed=4)
+        reps = 5
+        lens = np.tile(np.diff(o1.astype(np.int64)), reps)
+        goff = np.zeros(len(lens) + 1, dtype=np.uint64)
+        goff[1:] = np.cumsum(lens)
+        cuts = sp.shard_by_bases(goff, world)
+        r0, r1 = int(cuts[rank]), int(cuts[rank + 1])
+        off = (goff[r0:r1 + 1] - goff[r0]).astype(np.uint64)
+        big = np.tile(b1, reps)
+        buf = big[int(goff[r0]):int(goff[r1])].copy()
+        del big
+        total_reads_job, total_bases_job = len(lens), int(goff[-1])
+    else:
+        buf, off = ensure_reads(name, ref, seed=4 + rank)
+        total_reads_job, total_bases_job = None, None
     n_reads, n_bases = len(off) - 1, int(off[-1])
+    job_bases = sum_over_ranks(n_bases)
 
     h_reads = torch.from_numpy(buf).pin_memory()
     h_off = torch.from_numpy(off.astype(np.int64)).pin_memory()
@@ -355,78 +434,92 @@ def main():
     np_reads, np_off = h_reads.numpy(), h_off.numpy().view(np.uint64)
     TDT = {1: torch.uint8, 2: torch.int16, 4: torch.int32}
     NDT = {1: np.uint8, 2: np.uint16, 4: np.uint32}
+    packed_host = {}
 
-    def measure(width):
-        """Device-resident and end-to-end timing with `width`-byte lengths. Returns a dict + the host output."""
-        h_len = torch.empty(n_bases, dtype=TDT[width]).pin_memory()
-        d_len = torch.zeros(n_bases, dtype=TDT[width], device=dev)
+    def measure(ix, fmt, m="pml", stats=False, device_leg=True, steps=None):
+        """Device-resident and end-to-end timing of one output format.  fmt: "u8" | "u16" | "u32" | "bits" (one bit per base) |
+        "packed_bits" (2-bit packed reads in, bits out; end-to-end only).  Returns a dict + the host outputs."""
+        steps = steps or args.steps
+        bits = fmt in ("bits", "packed_bits")
+        width = {"u8": 1, "u16": 2, "u32": 4}.get(fmt, 0)
+        if bits:
+            nwords = sp.bits_bytes(n_bases) // 8
+            h_len = torch.zeros(nwords, dtype=torch.int64).pin_memory()
+            d_len = torch.zeros(nwords, dtype=torch.int64, device=dev)
+            np_len = h_len.numpy().view(np.uint64)
+            out_bytes = nwords * 8
+        else:
+            h_len = torch.empty(n_bases, dtype=TDT[width]).pin_memory()
+            d_len = torch.zeros(n_bases, dtype=TDT[width], device=dev)
+            np_len = h_len.numpy().view(NDT[width])
+            out_bytes = n_bases * width
         d_sat = torch.zeros(1, dtype=torch.int64, device=dev)
-        np_len = h_len.numpy().view(NDT[width])
         # MS pointers travel as uint32 when the text has fewer than 2^32 - 1 positions (checked lossless like the lengths)
-        pw = 4 if (mode == "ms" and n < (1 << 32) - 1 and not args.pointers64) else 8
-        d_ptr = torch.zeros(n_bases, dtype=torch.int64 if pw == 8 else torch.int32, device=dev) if mode == "ms" else None
-        h_ptr = torch.empty(n_bases, dtype=torch.int64 if pw == 8 else torch.int32).pin_memory() if mode == "ms" else None
-        np_ptr = h_ptr.numpy().view(np.uint64 if pw == 8 else np.uint32) if mode == "ms" else None
+        pw = 4 if (m == "ms" and n < (1 << 32) - 1 and not args.pointers64) else 8
+        d_ptr = torch.zeros(n_bases, dtype=torch.int64 if pw == 8 else torch.int32, device=dev) if m == "ms" else None
+        h_ptr = torch.empty(n_bases, dtype=torch.int64 if pw == 8 else torch.int32).pin_memory() if m == "ms" else None
+        np_ptr = h_ptr.numpy().view(np.uint64 if pw == 8 else np.uint32) if m == "ms" else None
+        d_stats = torch.zeros(n_reads * 2, dtype=torch.int64, device=dev) if stats else None
+        h_stats = np.zeros(n_reads, dtype=sp.BinStats) if stats else None
+        kw = dict(bin_width=150, max_value_thr=9) if stats else {}
+        packed = None
+        if fmt == "packed_bits":
+            if "p" not in packed_host:  # untimed: the caller packs while it parses; pinned like the byte reads
+                pk, ep, ev = sp.pack_reads_2bit(np_reads)
+                packed_host["p"] = (torch.from_numpy(pk).pin_memory(), torch.from_numpy(ep.astype(np.int64)).pin_memory(), torch.from_numpy(ev).pin_memory())
+            tp = packed_host["p"]
+            packed = (tp[0].numpy(), tp[1].numpy().view(np.uint64), tp[2].numpy())
+        h2d = (packed[0].nbytes + 9 * packed[1].size if packed else n_bases) + 8 * (n_reads + 1)
 
         def step_device():
-            idx.query_device(d_reads, d_off, n_reads, d_len, d_pointers=d_ptr, lanes=args.lanes, stream=stream.cuda_stream, d_saturated=d_sat)
+            if bits:
+                d_len.zero_()
+            ix.query_device(d_reads, d_off, n_reads, d_len, d_pointers=d_ptr, d_stats=d_stats, lanes=args.lanes, stream=stream.cuda_stream, d_saturated=d_sat, **kw)
 
         def step_host():
-            # the call a user makes: host buffers in, host buffers out (a clamped narrow value makes the call fail)
-            try:
-                idx.query_host(np_reads, np_off, lanes=args.lanes, out_lengths=np_len, out_pointers=np_ptr, length_bytes=width, pointer_bytes=pw)
-            except sp.SpumoniError as e:
-                raise SystemExit(f"bench.py: {e}; rerun with --length-bytes 2" if e.code == sp.ERR_OVERFLOW else f"bench.py: {e}")
+            # the call a user makes: host buffers in, host buffers out
+            ix.query_host(None if packed else np_reads, np_off, lanes=args.lanes, out_lengths=np_len, out_pointers=np_ptr, out_stats=h_stats,
+                          length_bytes=sp.LENGTH_BITS if bits else width, pointer_bytes=pw, packed=packed, **kw)
 
-        for _ in range(args.warmup):
-            step_device()
-        barrier()
-        launches0 = sp.kernel_launches()
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        evs[0].record(stream)
-        for i in range(args.steps):
-            step_device()
-            evs[i + 1].record(stream)
-        barrier()
-        launches = sp.kernel_launches() - launches0
-        kern_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
-        total_ms = evs[0].elapsed_time(evs[-1])
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms_max = float(t.item())
-        if int(d_sat.item()) != 0:
-            raise SystemExit(f"bench.py: {int(d_sat.item())} lengths were clamped at {width} byte(s); rerun with --length-bytes 2")
+        res = {"format": fmt, "d2h_bytes_per_step": out_bytes + (pw * n_bases if m == "ms" else 0) + (16 * n_reads if stats else 0), "h2d_bytes_per_step": h2d}
+        if device_leg:
+            for _ in range(args.warmup):
+                step_device()
+            barrier()
+            launches0 = sp.kernel_launches()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            evs[0].record(stream)
+            for i in range(steps):
+                step_device()
+                evs[i + 1].record(stream)
+            barrier()
+            res["launches"] = int(sp.kernel_launches() - launches0)
+            kern_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+            total_ms_max = max_over_ranks(evs[0].elapsed_time(evs[-1]))
+            res.update(value=job_bases * steps / (total_ms_max / 1e3), ms_per_step=total_ms_max / steps, kernel_ms=sum(kern_ms) / len(kern_ms),
+                       clamped=int(d_sat.item()) // (steps + args.warmup))
         for _ in range(2):
             step_host()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_host()
         barrier()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        same = bool(np.array_equal(np_len, d_len.cpu().numpy().view(NDT[width])))
-        if mode == "ms":
-            same = same and bool(np.array_equal(np_ptr, d_ptr.cpu().numpy().view(np_ptr.dtype)))
-        return {"value": n_bases * world * args.steps / (total_ms_max / 1e3), "ms_per_step": total_ms_max / args.steps,
-                "kernel_ms": sum(kern_ms) / len(kern_ms), "launches": int(launches),
-                "e2e": n_bases * world * args.steps / float(t.item()), "same": same,
-                "d2h_bytes_per_step": (width + (pw if mode == "ms" else 0)) * n_bases}, np_len, np_ptr
+        res["e2e"] = job_bases * steps / max_over_ranks(time.perf_counter() - t0)
+        if device_leg:
+            dl = d_len.cpu().numpy()
+            res["same"] = bool(np.array_equal(np_len, dl.view(np_len.dtype)))
+            if m == "ms":
+                res["same"] = res["same"] and bool(np.array_equal(np_ptr, d_ptr.cpu().numpy().view(np_ptr.dtype)))
+        return res, np_len, np_ptr
 
     # ---------------- timed region (clock sampling covers the headline measurement)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    main_m, np_len, np_ptr = measure(args.length_bytes)
+    main_fmt = {1: "u8", 2: "u16", 4: "u32"}[args.length_bytes]
+    main_m, np_len, np_ptr = measure(idx, main_fmt, mode)
     clocks = sampler.stop() if rank == 0 else None
-    other = {}
-    if args.length_bytes != 4 and not args.no_variants and world == 1:  # secondary line; N = 1 only (4 GB more pinned memory per rank)
-        other["u32"], _, _ = measure(4)
-    value, total_ms_max, kavg_ms, launches = main_m["value"], main_m["ms_per_step"] * args.steps, main_m["kernel_ms"], main_m["launches"]
-    e2e_value, same = main_m["e2e"], main_m["same"]
 
     # ---------------- parity spot check + CPU baseline (rank 0, N=1)
     cpu_baseline, parity = None, None
@@ -438,10 +531,11 @@ def main():
         o = oracle.OracleIndex(ref, mode)
         sec, Lo, Po = o.query_batch(buf[: int(off[sample_reads])], off[: sample_reads + 1], threads=cores)
         sb = int(off[sample_reads])
-        mism = int(np.count_nonzero(Lo != np_len[:sb].astype(np.uint64)))
+        got = sp.widen_lengths(np_len[:sb], off[: sample_reads + 1]) if (mode == "pml" and main_m["clamped"]) else np_len[:sb]
+        mism = int(np.count_nonzero(Lo != got.astype(np.uint64)))
         if mode == "ms":
             mism += int(np.count_nonzero(Po != np_ptr[:sb].astype(np.uint64)))
-        parity = {"reads_checked": sample_reads, "bases_checked": sb, "mismatches": mism, "host_equals_device_path": same}
+        parity = {"reads_checked": sample_reads, "bases_checked": sb, "mismatches": mism, "host_equals_device_path": main_m["same"]}
         cpu_baseline = {"value": sb / sec, "unit": "bases/s", "cores": cores, "kind": "port",
                         "sample": f"first {sample_reads} reads ({sb} bases) of the same workload, in-memory, OpenMP over reads"}
         ref_sec = reference_binary_seconds(ref, buf, off, sample_reads, mode, cores)
@@ -450,36 +544,92 @@ def main():
                             "sample": f"first {sample_reads} reads ({sb} bases) of the same workload through `spumoni run -n -t {cores}` of the "
                                       "reference's own translation units (oracle/_ref, stand-in third-party containers), its own phase timer",
                             "oracle_port": cpu_baseline["value"]}
-        if mism or not same:
+        if mism or not main_m["same"]:
             raise SystemExit(f"bench.py: PARITY FAILURE vs oracle: {parity}")
+
+    # ---------------- secondary measurements: other transports, -c statistics, MS (configs[2]), the CLI
+    variants = {}
+
+    def keep(k, v):
+        variants[k] = {q: v[q] for q in ("value", "kernel_ms", "e2e", "h2d_bytes_per_step", "d2h_bytes_per_step", "launches", "clamped", "same") if q in v}
+
+    if want and mode == "pml":
+        # every transport must give the lengths of the headline run
+        L_main = sp.widen_lengths(np_len, off) if main_m["clamped"] else np_len.astype(np.uint32)
+        fmts = [f for f in ("u16", "u32", "bits", "packed_bits") if f != main_fmt and f in want]
+        if world > 1:
+            fmts = [f for f in ("bits", "packed_bits") if f in want]
+        for f in fmts:
+            v, Lv, _ = measure(idx, f, "pml", device_leg=(f != "packed_bits"), steps=max(2, args.steps // 2))
+            Lx = sp.expand_bits(Lv, off) if f in ("bits", "packed_bits") else Lv.astype(np.uint32)
+            v["same"] = bool(v.get("same", True)) and bool(np.array_equal(Lx, L_main))
+            if not v["same"]:
+                raise SystemExit(f"bench.py: variant {f} disagrees with the headline lengths")
+            keep(f, v)
+        if world == 1 and "pml_stats" in want:
+            v, _, _ = measure(idx, main_fmt, "pml", stats=True, steps=max(2, args.steps // 2))
+            keep("pml_stats", v)
+    cli = None
+    if world == 1 and mode == "pml" and "synth" not in w and "cli" in want:
+        del idx  # the CLI opens its own copy
+        torch.cuda.empty_cache()
+        os.sched_setaffinity(0, all_cpus)
+        cores = os.cpu_count() or 1
+        cli_seconds(ref, name, 4, cores)  # page cache + first-touch warm-up
+        cli = cli_seconds(ref, name, 4, cores)
+        if cli:
+            cli["bases_per_s"] = n_bases / cli["phase_s"]
+    if world == 1 and mode == "pml" and "synth" not in w and "ms" in want:
+        try:
+            idx_ms_ref = ensure_index(name, "ms")
+            ms_idx = sp.Index.open(idx_ms_ref, sp.MODE_MS).to_device(local)
+            n_ms = ms_idx.get_bwt_stats()[0]
+            v, _, _ = measure(ms_idx, main_fmt, "ms", steps=max(2, args.steps // 2))
+            keep("ms", v)
+            variants["ms"]["roofline_frac_model"] = BYTES_PER_BASE["ms"] * n_bases / (v["kernel_ms"] / 1e3) / 1e9 / peaks()[0]
+            del ms_idx
+        except SystemExit:
+            raise
+        except Exception as e:  # the MS line is secondary: report why it is missing instead of losing the headline
+            variants["ms"] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank == 0:
         peak, peak_src = peaks()
+        kavg_ms = main_m["kernel_ms"]
         achieved = BYTES_PER_BASE[mode] * n_bases / (kavg_ms / 1e3) / 1e9
+        pw_run = 4 if (mode == "ms" and n < (1 << 32) - 1 and not args.pointers64) else 8
+        as_run = 1 + args.length_bytes + 64 + ((pw_run + 8 + 32) if mode == "ms" else 0)  # the same model with the widths this run used
+        kname = ("spb_move_kernel<PML>" if mode == "pml" else "spb_move_kernel<MS> + spb_ms_lengths_kernel") if (args.lanes or 1) == 1 else "spb_walk_kernel<G>"
         out = {
-            "metric": METRICS[mode], "value": value, "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u64", "data": "synthetic",
+            "metric": METRICS[mode], "value": main_m["value"], "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["desc"].replace("PML", mode.upper()), "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
-                       "lanes_per_read": args.lanes or 1, "length_bytes": args.length_bytes,
+                       "job_bases": job_bases, "lanes_per_read": args.lanes or 1, "length_bytes": args.length_bytes,
                        "l2": "inputs (1 GB reads per step) and outputs (1-4 GB lengths) larger than L2; no explicit flush",
-                       "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)"},
+                       "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)" +
+                                      ("; strong scaling: one fixed set of 5 x the workload's reads cut by bases" if args.strong else "")},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "bases/s", "h2d_bytes_per_step": n_bases + 8 * (n_reads + 1), "d2h_bytes_per_step": main_m["d2h_bytes_per_step"],
-                    "api": f"spb_{mode}_query_host, pinned host buffers, uint{8 * args.length_bytes} lengths (lossless on this workload: 0 clamped values)"},
-            "gpu_launches": int(launches),
+            "e2e": {"value": main_m["e2e"], "unit": "bases/s", "h2d_bytes_per_step": main_m["h2d_bytes_per_step"], "d2h_bytes_per_step": main_m["d2h_bytes_per_step"],
+                    "api": f"spb_{mode}_query_host, pinned host buffers, uint{8 * args.length_bytes} lengths ({main_m['clamped']} clamped values per step" +
+                           ("; clamped PML lengths are rebuilt exactly by spb_pml_widen_lengths)" if mode == "pml" else ")")},
+            "gpu_launches": int(main_m["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": ("spb_move_kernel<PML>" if mode == "pml" else "spb_move_kernel<MS> + spb_ms_lengths_kernel") if (args.lanes or 1) == 1 else "spb_walk_kernel<G>", "kernel_ms": kavg_ms,
-                         "bytes_per_base": BYTES_PER_BASE[mode], "peak_source": peak_src},
-            "cpu_baseline": cpu_baseline, "parity": parity,
-            "variants": {k: {"value": v["value"], "kernel_ms": v["kernel_ms"], "e2e": v["e2e"], "d2h_bytes_per_step": v["d2h_bytes_per_step"]} for k, v in other.items()},
+                         "traffic": None, "kernel": kname, "kernel_ms": kavg_ms,
+                         "bytes_per_base": BYTES_PER_BASE[mode], "bytes_per_base_as_run": as_run,
+                         "note": "achieved = SURVEY section 8(d)'s algorithmic bytes per base x bases / kernel time (a model: two index sectors per step whatever the layout); "
+                                 "traffic = DRAM bytes per launch measured by ncu (profiles/traffic.json), dram_frac = traffic / kernel time / peak",
+                         "peak_source": peak_src},
+            "cpu_baseline": cpu_baseline, "parity": parity, "variants": variants, "cli": cli,
         }
         tr = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr):
             try:
-                tj = json.load(open(tr))
-                if tj.get("kernel") == out["roofline"]["kernel"]:
+                tj = json.load(open(tr)).get(name + ":" + mode)
+                if tj and tj.get("kernel") == kname:
                     out["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+                    out["roofline"]["traffic_bases_per_launch"] = tj.get("bases_per_launch")
+                    out["roofline"]["dram_frac"] = tj["dram_bytes_per_launch"] * (n_bases / tj["bases_per_launch"]) / (kavg_ms / 1e3) / 1e9 / peak
             except Exception:
                 pass
         emit(out)

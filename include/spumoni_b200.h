@@ -190,6 +190,13 @@ int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t
                             const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
                             uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts);
 
+/* Same on the gpu_slot-th GPU of a replicated index (0 .. spb_index_device_count - 1).  Calls for DIFFERENT slots of one
+ * handle may run concurrently from different host threads (this is how `spumoni run` feeds several GPUs: batches of reads
+ * go round robin to one query thread per GPU and are written in input order); calls for the same slot may not. */
+int spb_pml_query_host_text_on(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                               const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
+                               uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts);
+
 /* Document-number variants: pml_t::matching_statistics(read, len, lengths, doc_nums) compute_ms_pml.cpp:734-737 ->
  * pml_pointers::_query :288-340, and ms_t::matching_statistics(read, len, lengths, pointers, doc_nums) :814-828 ->
  * ms_pointers::_query :625-682.  doc_nums[offsets[i] + j] is the document of position j of read i.  The index must

@@ -95,6 +95,7 @@ def load_library() -> ctypes.CDLL:
     L.spb_pml_query_device.argtypes = [vp, vp, vp, u64, vp, vp, ctypes.POINTER(QueryOpts), vp]
     L.spb_ms_query_device.argtypes = [vp, vp, vp, u64, vp, vp, vp, ctypes.POINTER(QueryOpts), vp]
     L.spb_pml_query_host_text.argtypes = [vp, vp, vp, u64, vp, vp, vp, u64, ctypes.POINTER(u64), vp, ctypes.POINTER(QueryOpts)]
+    L.spb_pml_query_host_text_on.argtypes = [vp, i32, vp, vp, u64, vp, vp, vp, u64, ctypes.POINTER(u64), vp, ctypes.POINTER(QueryOpts)]
     L.spb_nulldb_load.argtypes = [cp, ctypes.POINTER(_NullDb)]
     L.spb_nulldb_generate_host.argtypes = [vp, vp, vp, u64, vp, ctypes.POINTER(_NullDb)]
     L.spb_nulldb_save.argtypes = [cp, ctypes.POINTER(_NullDb), vp]

@@ -495,17 +495,28 @@ int query_host(spb_index* idx, HostJob job, uint64_t n_reads) {
 // ---- PML query + on-device decimal formatting (first resident GPU) ----------------------------------------------------
 struct TextChunk { int slot; uint64_t nr, id_bytes; uint32_t elem_bytes; };
 
-int query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads, const uint8_t* ids,
+struct DrainCtxOnExit {  // one GPU's streams only: other host threads may be driving the other GPUs of the handle
+    DeviceCtx* c;
+    ~DrainCtxOnExit() {
+        cudaSetDevice(c->device);
+        for (auto& s : c->slots)
+            if (s.stream) cudaStreamSynchronize(s.stream);
+    }
+};
+
+int query_host_text(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads, const uint8_t* ids,
                     const uint64_t* id_offsets, char* text, uint64_t text_capacity, uint64_t* text_bytes, spb_bin_stats* stats,
                     const spb_query_opts* opts) {
     if (!idx || !text_bytes) return fail(SPB_ERR_ARG, "null index / text_bytes");
     *text_bytes = 0;
     if (n_reads == 0) return SPB_OK;
     if (!reads || !offsets || !ids || !id_offsets || !text) return fail(SPB_ERR_ARG, "null host buffer");
-    int rc = ensure_device_state(idx);
+    if (gpu_slot < 0 || (size_t)gpu_slot >= idx->devs.size() || !idx->devs[(size_t)gpu_slot]->dev_blob)
+        return fail(SPB_ERR_NO_DEVICE, "index is not resident on that GPU (call spb_index_to_device / spb_index_replicate)");
+    DeviceCtx& c = *idx->devs[(size_t)gpu_slot];
+    int rc = ensure_ctx(idx, c);
     if (rc) return rc;
-    DeviceCtx& c = *primary(idx);
-    DrainOnExit drain{idx};
+    DrainCtxOnExit drain{&c};
     const bool want_stats = stats && opts && opts->bin_width;
     const int kSlots = idx->n_slots;
     spb_query_opts qo;
@@ -844,7 +855,13 @@ int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t
                             const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
                             uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts) {
     if (idx && idx->mode != SPB_MODE_PML) return fail(SPB_ERR_ARG, "spb_pml_query_host_text on an MS index");
-    return query_host_text(idx, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
+    return query_host_text(idx, 0, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
+}
+int spb_pml_query_host_text_on(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                               const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
+                               uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts) {
+    if (idx && idx->mode != SPB_MODE_PML) return fail(SPB_ERR_ARG, "spb_pml_query_host_text_on on an MS index");
+    return query_host_text(idx, gpu_slot, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
 }
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                       void* lengths, void* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {

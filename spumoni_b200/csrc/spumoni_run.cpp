@@ -12,10 +12,14 @@
 // libspumoni_b200.so; this file only parses FASTA, batches reads, and formats results.
 // The document array (-d) writes <reads>.doc_numbers (:859, :1003-1006).
 // Not supported (outside SURVEY section 8): minimizer digestion (-m/-a, needs bonsai).
+#include <fcntl.h>
 #include <getopt.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -28,6 +32,7 @@
 #include <memory>
 #include <mutex>
 #include <sstream>
+#include <map>
 #include <string>
 #include <thread>
 #include <vector>
@@ -153,7 +158,9 @@ struct ReadBatch {
 // std::getline semantics (lines split at '\n', a last line without terminator still counts) over 16 MiB reads
 class LineReader {
 public:
-    explicit LineReader(const std::string& path) : f_(std::fopen(path.c_str(), "rb")), buf_(16u << 20) {}
+    explicit LineReader(const std::string& path, uint64_t start = 0) : f_(std::fopen(path.c_str(), "rb")), buf_(16u << 20) {
+        if (f_ && start) fseeko(f_, (off_t)start, SEEK_SET);
+    }
     ~LineReader() { if (f_) std::fclose(f_); }
     bool good() const { return f_ != nullptr; }
     // what std::istream::good() would say after the reads so far: false once a line had to be ended by the end of the file
@@ -189,7 +196,7 @@ private:
 
 class FastaSource {  // sequential equivalent of BatchLoader::loadBatch + grabNextRead (FASTA, and FASTQ records)
 public:
-    explicit FastaSource(const std::string& path) : in_(path) {
+    explicit FastaSource(const std::string& path, uint64_t start = 0) : in_(path, start) {  // start: offset of a record's '>' (fast path hand-over)
         if (!in_.good()) return;
         int pk = in_.peek();
         if (pk == EOF) { done_ = true; return; }
@@ -511,7 +518,314 @@ static void write_batch(bool ms, const RunOptions& o, const Work& w, Outputs& ou
     lap(t_write);
 }
 
-static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
+// ---------------------------------------------------------------------------------- fast path (FASTA, PML, no -d)
+// The file is memory-mapped and cut into windows at record boundaries; a window is parsed on -t threads straight into
+// page-locked buffers (two passes over its records: sizes, then the bytes), queried on one of the GPUs the index is
+// resident on by that GPU's query thread (spb_pml_query_host_text_on: lengths are formatted on the device), and its text
+// is written with pwrite on -t threads at its final offset; windows are written in input order, which is the reference's
+// own order for -t 1 (App. C-11).  Anything the sequential parser treats specially (a header without an id, an empty
+// record) makes the fast path hand the rest of the file, from that window on, to the sequential path below, so that
+// messages and partial outputs stay those of BatchLoader.
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        if (p) spb_host_free(p);
+        p = nullptr; cap = 0;
+        const size_t want = n + n / 4;
+        if (spb_host_alloc(&p, want) != SPB_OK) fatal_error(spb_last_error());
+        cap = want;
+    }
+    ~PinnedBuf() { if (p) spb_host_free(p); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct FastBatch {
+    uint64_t seq = 0, file_lo = 0;
+    PinnedBuf bases, offsets, idcat, idoff, text, stats;
+    std::vector<uint64_t> starts;  // record starts inside the window (file offsets)
+    uint64_t n_reads = 0, n_bases = 0, id_bytes = 0, text_bytes = 0;
+    bool anomaly = false, last = false;
+};
+
+static inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }  // std::isspace, C locale
+
+// sizes (pass 0) or bytes (pass 1) of the record at [lo, hi): header line, then sequence lines with trailing blanks stripped
+static inline void parse_record(const char* d, uint64_t lo, uint64_t hi, bool copy, uint64_t& id_len, uint64_t& n_bases, uint8_t* id_out,
+                                uint8_t* base_out, bool& anomaly) {
+    const char* eol = (const char*)std::memchr(d + lo, '\n', hi - lo);
+    const uint64_t hl_end = eol ? (uint64_t)(eol - d) : hi;  // header line = [lo, hl_end)
+    const uint64_t hl = hl_end - lo;
+    if (hl <= 2) anomaly = true;  // "header line is missing an id"
+    uint64_t idl = hl;            // index of the first delimiter in the line, or its size
+    for (uint64_t i = 1; i < hl; i++) { const char c = d[lo + i]; if (c == ' ' || c == '\t' || c == '\r') { idl = i; break; } }
+    id_len = std::min(hl > 0 ? hl - 1 : 0, idl);  // substr(1, idl): keeps the delimiter (batch_loader.cpp:104-106)
+    if (copy && id_len) std::memcpy(id_out, d + lo + 1, id_len);
+    uint64_t nb = 0, p = eol ? hl_end + 1 : hi;
+    while (p < hi) {
+        const char* e2 = (const char*)std::memchr(d + p, '\n', hi - p);
+        const uint64_t le = e2 ? (uint64_t)(e2 - d) : hi;
+        uint64_t e = le;
+        while (e > p && is_space((unsigned char)d[e - 1])) e--;
+        if (copy && e > p) std::memcpy(base_out + nb, d + p, e - p);
+        nb += e - p;
+        p = e2 ? le + 1 : hi;
+    }
+    n_bases = nb;
+    if (nb == 0) anomaly = true;  // "was empty after digestion"
+}
+
+// first record start at or after p ('>' at the beginning of a line), or size
+static uint64_t next_record_start(const char* d, uint64_t size, uint64_t p) {
+    while (p < size) {
+        const char* g = (const char*)std::memchr(d + p, '>', size - p);
+        if (!g) return size;
+        const uint64_t at = (uint64_t)(g - d);
+        if (at == 0 || d[at - 1] == '\n') return at;
+        p = at + 1;
+    }
+    return size;
+}
+// record starts inside [lo, hi), found on T threads; starts[n] = hi is appended
+static void window_record_starts(const char* d, uint64_t lo, uint64_t hi, int T, std::vector<uint64_t>& starts) {
+    std::vector<std::vector<uint64_t>> part((size_t)T);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
+        const uint64_t a = lo + (hi - lo) * (uint64_t)t / (uint64_t)T, e = lo + (hi - lo) * (uint64_t)(t + 1) / (uint64_t)T;
+        uint64_t p = a;
+        while (p < e) {
+            const char* g = (const char*)std::memchr(d + p, '>', e - p);
+            if (!g) break;
+            const uint64_t at = (uint64_t)(g - d);
+            if (at == 0 || d[at - 1] == '\n') part[(size_t)t].push_back(at);
+            p = at + 1;
+        }
+    }
+    starts.clear();
+    for (auto& v : part) starts.insert(starts.end(), v.begin(), v.end());
+    starts.push_back(hi);
+}
+// pass 0: off[r + 1] / ido[r + 1] = bases / id bytes of record r, then prefix sums; false if a record needs the sequential parser
+static bool window_sizes(const char* d, const std::vector<uint64_t>& starts, int T, uint64_t* off, uint64_t* ido) {
+    const uint64_t nr = starts.size() - 1;
+    int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(T) reduction(| : bad)
+    for (int64_t r = 0; r < (int64_t)nr; r++) {
+        bool an = false;
+        parse_record(d, starts[(size_t)r], starts[(size_t)r + 1], false, ido[r + 1], off[r + 1], nullptr, nullptr, an);
+        bad |= an ? 1 : 0;
+    }
+    if (bad) return false;
+    off[0] = 0; ido[0] = 0;
+    for (uint64_t r = 0; r < nr; r++) { off[r + 1] += off[r]; ido[r + 1] += ido[r]; }
+    return true;
+}
+// pass 1: the bytes
+static void window_fill(const char* d, const std::vector<uint64_t>& starts, int T, const uint64_t* off, const uint64_t* ido, uint8_t* bases, uint8_t* ids) {
+    const uint64_t nr = starts.size() - 1;
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int64_t r = 0; r < (int64_t)nr; r++) {
+        bool an = false;
+        uint64_t il, nb;
+        parse_record(d, starts[(size_t)r], starts[(size_t)r + 1], true, il, nb, ids + ido[r], bases + off[r], an);
+    }
+}
+
+class FastRunner {
+public:
+    FastRunner(const RunOptions& o, int n_gpus) : o_(o), n_gpus_(std::max(1, n_gpus)), threads_((int)std::max<size_t>(1, o.threads)) {
+        window_ = 48ull << 20;
+        if (const char* e = std::getenv("SPUMONI_B200_BATCH_MB")) { long v = std::atol(e); if (v >= 1 && v <= 2048) window_ = (uint64_t)v << 20; }
+        batches_.resize((size_t)(2 * n_gpus_ + 3));
+    }
+    // Page-locking the batch buffers is the expensive part of setting the pipeline up: it is done while the index loads.
+    void preallocate() {
+        for (auto& b : batches_) {
+            b.bases.reserve(window_ + 64);
+            b.offsets.reserve((window_ / 64 + 2) * 8);
+            b.idoff.reserve((window_ / 64 + 2) * 8);
+            b.idcat.reserve(window_ / 8);
+            b.text.reserve(window_ * 3);
+            if (o_.write_report) b.stats.reserve((window_ / 64 + 2) * sizeof(spb_bin_stats));
+        }
+    }
+    // Returns the number of reads processed; *resume_at = file offset where the sequential path must take over (or the file size).
+    size_t run(spb_index* idx, const spb_query_opts& qo, Outputs& out, const std::string& path, const std::string& text_path, uint64_t* resume_at) {
+        idx_ = idx; qo_ = qo; out_ = &out;
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd < 0 || fstat(fd, &st) != 0) fatal_error("cannot open " + path);
+        size_ = (uint64_t)st.st_size;
+        *resume_at = size_;
+        if (size_ == 0) { ::close(fd); return 0; }
+        data_ = (const char*)mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (data_ == MAP_FAILED) fatal_error("cannot map " + path);
+        madvise((void*)data_, size_, MADV_WILLNEED);
+        out_fd_ = ::open(text_path.c_str(), O_WRONLY);
+        if (out_fd_ < 0) fatal_error("cannot open " + text_path);
+        for (auto& b : batches_) free_q_.push(&b);
+        std::thread parser([&] { parse_loop(); });
+        std::vector<std::thread> gpus;
+        for (int g = 0; g < n_gpus_; g++) gpus.emplace_back([&, g] { query_loop(g); });
+        write_loop();
+        parser.join();
+        for (auto& t : gpus) t.join();
+        ::close(out_fd_);
+        munmap((void*)data_, size_);
+        ::close(fd);
+        *resume_at = resume_;
+        text_written_ = text_off_;
+        return reads_done_;
+    }
+    uint64_t text_written() const { return text_written_; }
+    double t_parse = 0, t_gpu = 0, t_write = 0, t_report = 0;
+
+private:
+    struct Q {  // hand-off queue (FastBatch*, nullptr = end)
+        void push(FastBatch* b) { std::unique_lock<std::mutex> lk(m); q.push_back(b); cv.notify_all(); }
+        FastBatch* pop() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return !q.empty(); }); FastBatch* b = q.front(); q.pop_front(); return b; }
+        std::mutex m; std::condition_variable cv; std::deque<FastBatch*> q;
+    };
+    void parse_loop() {
+        uint64_t lo = 0, seq = 0;
+        bool stop = false;
+        while (lo < size_ && !stop) {
+            FastBatch* b = free_q_.pop();
+            const double t0 = now_s();
+            const uint64_t hi = lo + window_ >= size_ ? size_ : next_record_start(data_, size_, lo + window_);
+            b->seq = seq++; b->file_lo = lo; b->anomaly = false; b->last = false;
+            const int T = threads_;
+            window_record_starts(data_, lo, hi, T, b->starts);
+            const uint64_t nr = b->starts.size() - 1;
+            bool ok = nr > 0 && b->starts[0] == lo;  // (a file that does not start with '>' was refused before)
+            if (ok) {
+                b->offsets.reserve((nr + 1) * 8);
+                b->idoff.reserve((nr + 1) * 8);
+                if (o_.write_report) b->stats.reserve((nr + 1) * sizeof(spb_bin_stats));
+                ok = window_sizes(data_, b->starts, T, b->offsets.as<uint64_t>(), b->idoff.as<uint64_t>());
+            }
+            if (!ok) {  // hand this window and everything after it to the sequential path
+                b->anomaly = true;
+                b->n_reads = 0;
+                resume_ = lo;
+                stop = true;
+            } else {
+                const uint64_t* off = b->offsets.as<uint64_t>();
+                const uint64_t* ido = b->idoff.as<uint64_t>();
+                b->n_reads = nr; b->n_bases = off[nr]; b->id_bytes = ido[nr];
+                b->bases.reserve(b->n_bases + 64);
+                b->idcat.reserve(b->id_bytes + 64);
+                window_fill(data_, b->starts, T, off, ido, b->bases.as<uint8_t>(), b->idcat.as<uint8_t>());
+                lo = hi;
+                if (lo >= size_) resume_ = size_;
+            }
+            t_parse += now_s() - t0;
+            parsed_q_.push(b);
+        }
+        for (int g = 0; g < n_gpus_; g++) parsed_q_.push(nullptr);
+    }
+    void query_loop(int g) {
+        for (;;) {
+            FastBatch* b = parsed_q_.pop();
+            if (!b) break;
+            const double t0 = now_s();
+            if (b->n_reads) {
+                uint64_t need = b->n_bases * 3 + b->id_bytes + 3 * b->n_reads + 64;  // typical PML text is ~2 bytes per base
+                for (;;) {
+                    b->text.reserve(need);
+                    const int rc = spb_pml_query_host_text_on(idx_, g, b->bases.as<uint8_t>(), b->offsets.as<uint64_t>(), b->n_reads, b->idcat.as<uint8_t>(),
+                                                              b->idoff.as<uint64_t>(), b->text.as<char>(), b->text.cap, &b->text_bytes,
+                                                              o_.write_report ? b->stats.as<spb_bin_stats>() : nullptr, &qo_);
+                    if (rc == SPB_ERR_LIMIT && b->text_bytes > b->text.cap) { need = b->text_bytes + b->text_bytes / 2; continue; }  // rare: redo with a larger buffer
+                    spb_or_die(rc);
+                    break;
+                }
+            } else b->text_bytes = 0;
+            {
+                std::unique_lock<std::mutex> lk(gpu_m_);
+                t_gpu += now_s() - t0;
+            }
+            done_q_.push(b);
+        }
+        done_q_.push(nullptr);
+    }
+    void write_loop() {
+        std::map<uint64_t, FastBatch*> pending;  // windows finish out of order with several GPUs
+        uint64_t next_seq = 0;
+        int ended = 0;
+        while (ended < n_gpus_) {
+            FastBatch* b = done_q_.pop();
+            if (!b) { ended++; continue; }
+            pending[b->seq] = b;
+            while (!pending.empty() && pending.begin()->first == next_seq) {
+                FastBatch* w = pending.begin()->second;
+                pending.erase(pending.begin());
+                next_seq++;
+                write_batch(*w);
+                free_q_.push(w);
+            }
+        }
+    }
+    void write_batch(FastBatch& b) {
+        if (!b.n_reads) return;
+        double t0 = now_s();
+        const uint64_t piece = 8ull << 20, np = (b.text_bytes + piece - 1) / piece;
+        const char* text = b.text.as<char>();
+        const uint64_t base_off = text_off_;
+        int failed = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_) reduction(| : failed)
+        for (int64_t i = 0; i < (int64_t)np; i++) {
+            uint64_t a = (uint64_t)i * piece;
+            const uint64_t e = std::min(b.text_bytes, a + piece);
+            while (a < e) {
+                const ssize_t wr = pwrite(out_fd_, text + a, e - a, (off_t)(base_off + a));
+                if (wr <= 0) { failed = 1; break; }
+                a += (uint64_t)wr;
+            }
+        }
+        if (failed) fatal_error("write to the output file failed");
+        text_off_ += b.text_bytes;
+        reads_done_ += b.n_reads;
+        t_write += now_s() - t0;
+        if (o_.write_report) {  // rows are formatted on -t threads with the reference's manipulators, written in order
+            t0 = now_s();
+            const uint8_t* ids = b.idcat.as<uint8_t>();
+            const uint64_t* ido = b.idoff.as<uint64_t>();
+            const spb_bin_stats* S = b.stats.as<spb_bin_stats>();
+            std::vector<std::string> rows((size_t)threads_);
+            const size_t nr = b.n_reads;
+#pragma omp parallel num_threads(threads_)
+            {
+                const size_t t = (size_t)omp_get_thread_num(), nt = (size_t)omp_get_num_threads();
+                std::ostringstream os;
+                std::string id;
+                for (size_t r = nr * t / nt; r < nr * (t + 1) / nt; r++) {
+                    id.assign((const char*)ids + ido[r], ido[r + 1] - ido[r]);
+                    report_row(os, id, S[r]);
+                }
+                if (t < rows.size()) rows[t] = os.str();
+            }
+            for (const auto& r : rows) out_->report.write(r.data(), (std::streamsize)r.size());
+            t_report += now_s() - t0;
+        }
+    }
+
+    spb_index* idx_ = nullptr;
+    const RunOptions& o_;
+    spb_query_opts qo_;
+    Outputs* out_ = nullptr;
+    int n_gpus_, threads_;
+    uint64_t window_ = 0, size_ = 0, resume_ = 0, text_off_ = 0, text_written_ = 0;
+    size_t reads_done_ = 0;
+    const char* data_ = nullptr;
+    int out_fd_ = -1;
+    std::vector<FastBatch> batches_;
+    Q free_q_, parsed_q_, done_q_;
+    std::mutex gpu_m_;
+};
+
+static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o, FastRunner* fast) {
     Outputs out;
     out.lengths.open(o.pattern_file + (ms ? ".lengths" : ".pseudo_lengths"));
     if (ms) out.pointers.open(o.pattern_file + ".pointers");
@@ -537,10 +851,24 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
     constexpr int kWorks = 4;
     const bool timing = std::getenv("SPUMONI_B200_TIMING") != nullptr;  // per-stage busy time on stderr
     double t_parse = 0, t_gpu = 0, t_format = 0, t_write = 0;
+    size_t num_reads = 0;
+    uint64_t resume_at = 0;
+    if (fast) {  // FASTA, PML, no -d: memory-mapped input, parallel parse, one query thread per GPU, parallel pwrite
+        int first = EOF;
+        { std::ifstream probe(o.pattern_file, std::ifstream::binary); first = probe.peek(); }
+        if (first == '>') {
+            out.lengths.flush();
+            num_reads = fast->run(idx, qo, out, o.pattern_file, o.pattern_file + ".pseudo_lengths", &resume_at);
+            out.lengths.seekp((std::streamoff)fast->text_written());
+            if (timing) std::fprintf(stderr, "\n[timing] busy seconds per stage: parse %.3f | query (H2D + kernels + D2H) %.3f | format 0.000 | write %.3f | report %.3f\n",
+                                     fast->t_parse, fast->t_gpu, fast->t_write, fast->t_report);
+            struct stat st;
+            if (stat(o.pattern_file.c_str(), &st) == 0 && resume_at >= (uint64_t)st.st_size) return num_reads;
+        }
+    }
     std::vector<Work> works(kWorks);
     WorkQueue free_q, parsed_q, done_q;
     for (auto& w : works) free_q.push(&w);
-    size_t num_reads = 0;
 
     std::thread parser([&] {
         Work* w = free_q.pop();
@@ -555,7 +883,7 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o) {
             t0 = now_s();
         };
         if (!o.is_general_text) {
-            FastaSource src(o.pattern_file);
+            FastaSource src(o.pattern_file, resume_at);
             while (src.next(w->b)) {
                 num_reads++;
                 if (w->b.bases.size() >= kBatchBases) flush(false);
@@ -614,21 +942,48 @@ static int run_main(int argc, char** argv) {
     o.ref_file += o.use_promotions ? ".bin" : ".fa";
     const char* tag = ms ? "compute_ms" : "compute_pml";
 
+    // GPUs: SPUMONI_B200_DEVICES="0,2,3" (or the older SPUMONI_B200_DEVICE=<one ordinal>), else as many of the visible GPUs as
+    // there are threads (-t, the reference's number of parallel workers, compute_ms_pml.cpp:890-894)
+    std::vector<int> devices;
+    if (const char* e = std::getenv("SPUMONI_B200_DEVICES")) {
+        std::stringstream ss(e);
+        std::string tok;
+        while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(std::atoi(tok.c_str()));
+    } else if (const char* e1 = std::getenv("SPUMONI_B200_DEVICE")) devices.push_back(std::atoi(e1));
+    else {
+        const int visible = spb_device_count();
+        for (int d = 0; d < std::max(1, std::min<int>(visible, (int)o.threads)); d++) devices.push_back(d);
+    }
+    if (devices.empty()) devices.push_back(0);
+    const bool fast_ok = !ms && !o.use_doc && !o.is_general_text && !std::getenv("SPUMONI_B200_HOST_FORMAT") && !std::getenv("SPUMONI_B200_SEQUENTIAL");
+    std::unique_ptr<FastRunner> fast;
+    std::thread prealloc;
+    if (fast_ok && spb_device_count() > 0) {  // page-lock the pipeline's buffers while the index loads
+        fast.reset(new FastRunner(o, (int)devices.size()));
+        prealloc = std::thread([&] { fast->preallocate(); });
+    }
+
     status_log(ms ? "ms_construct" : "pml_construct", ms ? "loading the MS index" : "loading the PML index");
     double t0 = now_s();
     spb_index* idx = nullptr;
-    spb_or_die(spb_index_open_ex(o.ref_file.c_str(), ms ? SPB_MODE_MS : SPB_MODE_PML, o.use_doc ? SPB_OPEN_DOC : 0, &idx));
+    {
+        const int rc = spb_index_open_ex(o.ref_file.c_str(), ms ? SPB_MODE_MS : SPB_MODE_PML, o.use_doc ? SPB_OPEN_DOC : 0, &idx);
+        if (rc) { if (prealloc.joinable()) prealloc.join(); spb_or_die(rc); }
+    }
     if (o.use_doc) { done_log(now_s() - t0); status_log(ms ? "ms_construct" : "pml_construct", "loading the document array"); }
-    int dev = 0;
-    if (const char* e = std::getenv("SPUMONI_B200_DEVICE")) dev = std::atoi(e);
-    spb_or_die(spb_index_to_device(idx, dev));
+    {
+        const int rc = spb_index_replicate(idx, devices.data(), (int)devices.size());
+        if (prealloc.joinable()) prealloc.join();
+        spb_or_die(rc);
+    }
+    if (std::getenv("SPUMONI_B200_TIMING")) std::fprintf(stderr, "\n[timing] devices: %d %s\n", (int)devices.size(), spb_replicate_method());
     done_log(now_s() - t0);
     std::cout << std::endl;
     force_log(tag, "input reads will be used directly, no minimizer digestion");
 
     t0 = now_s();
     status_log(tag, ms ? "processing the reads" : "processing the patterns");
-    size_t num_reads = classify_reads(idx, ms, o);
+    size_t num_reads = classify_reads(idx, ms, o, fast.get());
     done_log(now_s() - t0);
     force_log(tag, "finished processing " + std::to_string(num_reads) + " reads. results are saved in *." + (ms ? "lengths" : "pseudo_lengths") + " file.");
     std::cout << std::endl;

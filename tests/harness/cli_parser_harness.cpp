@@ -5,11 +5,45 @@
 #include "../../spumoni_b200/csrc/spumoni_run.cpp"
 #undef main
 
+// argv[2] = window size in bytes, argv[3] = threads: the fast path's window parser (window_record_starts / window_sizes /
+// window_fill, the functions FastRunner::parse_loop calls) over the windows of the file, handing over to the sequential
+// parser at the first window that needs it -- exactly what `spumoni run` does, minus the GPU.
+static void fast_parse(const char* path, uint64_t window, int T, ReadBatch& b) {
+    std::ifstream f(path, std::ifstream::binary);
+    std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
+    const uint64_t size = data.size();
+    uint64_t lo = 0, resume = size;
+    if (size && data[0] != '>') { resume = 0; lo = size; }
+    while (lo < size) {
+        const uint64_t hi = lo + window >= size ? size : next_record_start(data.data(), size, lo + window);
+        std::vector<uint64_t> starts;
+        window_record_starts(data.data(), lo, hi, T, starts);
+        const uint64_t nr = starts.size() - 1;
+        std::vector<uint64_t> off(nr + 1), ido(nr + 1);
+        if (!(nr > 0 && starts[0] == lo && window_sizes(data.data(), starts, T, off.data(), ido.data()))) { resume = lo; break; }
+        std::vector<uint8_t> bases(off[nr] + 1), ids(ido[nr] + 1);
+        window_fill(data.data(), starts, T, off.data(), ido.data(), bases.data(), ids.data());
+        for (uint64_t r = 0; r < nr; r++) {
+            b.ids.emplace_back((const char*)ids.data() + ido[r], ido[r + 1] - ido[r]);
+            b.bases.insert(b.bases.end(), bases.begin() + off[r], bases.begin() + off[r + 1]);
+            b.offsets.push_back(b.bases.size());
+        }
+        lo = hi;
+    }
+    if (resume < size) {
+        FastaSource src(path, resume);
+        while (src.next(b)) {}
+    }
+}
+
 int main(int argc, char** argv) {
-    if (argc != 2) return 2;
-    FastaSource src(argv[1]);
+    if (argc != 2 && argc != 4) return 2;
     ReadBatch b;
-    while (src.next(b)) {}
+    if (argc == 4) fast_parse(argv[1], (uint64_t)std::atoll(argv[2]), std::atoi(argv[3]), b);
+    else {
+        FastaSource src(argv[1]);
+        while (src.next(b)) {}
+    }
     for (size_t r = 0; r < b.ids.size(); r++) {
         std::fputc('>', stdout);
         std::fwrite(b.ids[r].data(), 1, b.ids[r].size(), stdout);

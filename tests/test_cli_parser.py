@@ -108,3 +108,32 @@ def test_parser_equals_reference_binary_on_odd_inputs(harness, tmp_path):
         assert [(i, len(s)) for i, s in got] == want, name
         seen_drop += name.startswith("fq_") and len(want) < open(path).read().count("\n@") + 1
     assert seen_reject >= 4 and seen_drop >= 4
+
+
+def test_fast_window_parser_equals_sequential_parser(harness, tmp_path):
+    """The fast path of `spumoni run` (memory-mapped FASTA cut into windows, parsed on several threads) must produce exactly the
+    records of the sequential BatchLoader-equivalent parser -- ids with their delimiter quirk, stripped multi-line sequences,
+    CRLF, '>' inside a line -- for any window size and thread count, and must hand over to the sequential parser (same
+    records, same rejection) where a header has no id or a record is empty."""
+    d = str(tmp_path)
+    text = "".join(line.strip() for line in open(os.path.join(GOLDEN, "idx.fa")) if not line.startswith(">"))
+    files = {k: v for k, v in _nasty_files(d, text).items() if not k.startswith("fq_")}
+    files["golden"] = os.path.join(GOLDEN, "reads.fa")
+    rng = random.Random(9)
+    big = os.path.join(d, "big.fa")
+    with open(big, "w") as f:
+        for i in range(3000):
+            ln = rng.choice([1, 7, 60, 150, 400])
+            p = rng.randint(0, len(text) - ln - 1)
+            body = text[p:p + ln]
+            if i % 11 == 0:
+                body = body[: ln // 2] + "\n" + body[ln // 2:]
+            f.write(">read%d%s\n%s\n" % (i, rng.choice(["", " d", "\tq", " "]), body))
+    files["big"] = big
+    for name, path in sorted(files.items()):
+        r0 = subprocess.run([harness, path], capture_output=True)
+        for window, threads in ((1, 1), (64, 3), (300, 8), (1 << 20, 4)):
+            r1 = subprocess.run([harness, path, str(window), str(threads)], capture_output=True)
+            assert r1.returncode == r0.returncode, (name, window, threads)
+            if r0.returncode == 0:
+                assert r1.stdout == r0.stdout, (name, window, threads)
