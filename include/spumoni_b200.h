@@ -232,6 +232,28 @@ int spb_nulldb_save(const char* path, const spb_nulldb* summary, const uint32_t*
 /* max_value_thr derivation compute_ms_pml.cpp:871-875 (PML) / :1061-1063 (MS) */
 uint64_t spb_max_value_threshold(double percentile_value, int is_pml, int use_dna_letters, int use_promotions);
 
+/* ---- index construction on the GPU ----------------------------------------------------------------------- */
+/* What `spumoni build` obtains from its PFP toolchain -- Big-BWT and pfp_thresholds, run as external programs at
+ * /root/reference/src/spumoni.cpp:442-545 -- computed on the device from the text itself: per run of the BWT its head, its
+ * length, its MONI threshold (the leftmost minimum of LCP between the previous run of the character and this one; 0 for
+ * the first) and the SA values at its first and last position.  These are the contents of <ref>.bwt.heads, .bwt.len,
+ * .thr_pos, .ssa and .esa, which the reference's own constructors read (compute_ms_pml.cpp:44-82, :357-439,
+ * thresholds_ds.hpp:393-426) before serialising the index.
+ * text: n bytes = the indexed text followed by its terminator, a zero byte; every other byte must be > 0x01.
+ * n < 2^31 - 16 in this version (SPB_ERR_LIMIT otherwise).  The arrays are allocated by the library: spb_build_parts_free. */
+typedef struct {
+    uint64_t n, r;   /* BWT length, number of runs */
+    uint8_t* heads;  /* r */
+    uint64_t* lens;  /* r */
+    uint64_t* thr;   /* r */
+    uint64_t* ssa;   /* r */
+    uint64_t* esa;   /* r */
+} spb_build_parts;
+int spb_build_parts_device(const uint8_t* text, uint64_t n, int device, spb_build_parts* out);
+void spb_build_parts_free(spb_build_parts* p);
+/* writes <ref_file>.bwt.heads / .bwt.len / .thr_pos / .ssa / .esa with the 5-byte integers the reference reads */
+int spb_build_parts_write(const char* ref_file, const spb_build_parts* p);
+
 /* ---- compact transports (host side, no GPU needed) ----------------------------------------------- */
 /* bytes of the bit map for n_bases bases (whole 32-byte blocks) / of the packed array (incl. the padding the device reads) */
 uint64_t spb_bits_bytes(uint64_t n_bases);

@@ -40,6 +40,12 @@ class QueryOpts(ctypes.Structure):
                 ("saturated", ctypes.c_void_p)]
 
 
+class _BuildParts(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_uint64), ("r", ctypes.c_uint64), ("heads", ctypes.POINTER(ctypes.c_uint8)),
+                ("lens", ctypes.POINTER(ctypes.c_uint64)), ("thr", ctypes.POINTER(ctypes.c_uint64)),
+                ("ssa", ctypes.POINTER(ctypes.c_uint64)), ("esa", ctypes.POINTER(ctypes.c_uint64))]
+
+
 class _NullDb(ctypes.Structure):
     _fields_ = [("num_values", ctypes.c_uint64), ("ks_stat_threshold", ctypes.c_double),
                 ("mean_null_stat", ctypes.c_double), ("percentile_value", ctypes.c_double)]
@@ -106,6 +112,10 @@ def load_library() -> ctypes.CDLL:
     L.spb_host_free.restype = None
     L.spb_device_count.restype = i32
     L.spb_kernel_launches.restype = u64
+    L.spb_build_parts_device.argtypes = [vp, u64, i32, ctypes.POINTER(_BuildParts)]
+    L.spb_build_parts_free.argtypes = [ctypes.POINTER(_BuildParts)]
+    L.spb_build_parts_free.restype = None
+    L.spb_build_parts_write.argtypes = [cp, ctypes.POINTER(_BuildParts)]
     L.spb_index_replicate.argtypes = [vp, ctypes.POINTER(i32), i32]
     L.spb_index_device_count.argtypes = [vp]
     L.spb_replicate_method.restype = cp
@@ -183,6 +193,26 @@ def generate_null_database(index: "Index", reads: np.ndarray, offsets: np.ndarra
     out.num_values, out.ks_stat_threshold = db.num_values, db.ks_stat_threshold
     out.mean_null_stat, out.percentile_value = db.mean_null_stat, db.percentile_value
     return out, stats
+
+
+def build_parts_device(text: np.ndarray, device: int = 0, write_to: Optional[str] = None) -> dict:
+    """spb_build_parts_device: run heads / lengths / thresholds / SA samples of the BWT of `text` (uint8, ending with its
+    terminator 0), computed on the GPU -- what `spumoni build` gets from Big-BWT + pfp_thresholds.  write_to = <ref_file>:
+    also writes <ref_file>.bwt.heads / .bwt.len / .thr_pos / .ssa / .esa."""
+    text = np.ascontiguousarray(text, dtype=np.uint8)
+    lib = load_library()
+    P = _BuildParts()
+    _check(lib.spb_build_parts_device(text.ctypes.data, text.size, device, ctypes.byref(P)))
+    try:
+        r = int(P.r)
+        out = {"n": int(P.n), "r": r, "heads": np.ctypeslib.as_array(P.heads, shape=(r,)).copy()}
+        for k in ("lens", "thr", "ssa", "esa"):
+            out[k] = np.ctypeslib.as_array(getattr(P, k), shape=(r,)).copy()
+        if write_to:
+            _check(lib.spb_build_parts_write(write_to.encode(), ctypes.byref(P)))
+    finally:
+        lib.spb_build_parts_free(ctypes.byref(P))
+    return out
 
 
 def bits_bytes(n_bases: int) -> int:

@@ -19,6 +19,7 @@
 
 #include "../../include/spumoni_b200.h"
 #include "flat_index.h"
+#include "build_kernels.h"
 #include "host_util.h"
 #include "index_host.h"
 #include "kernels.h"
@@ -982,6 +983,66 @@ int spb_device_count(void) {
     return count;
 }
 uint64_t spb_kernel_launches(void) { return g_launches.load(); }
+
+// ---- index construction on the GPU -------------------------------------------------------------
+int spb_build_parts_device(const uint8_t* text, uint64_t n, int device, spb_build_parts* out) {
+    if (!text || !out) return fail(SPB_ERR_ARG, "spb_build_parts_device: bad argument");
+    std::memset(out, 0, sizeof(*out));
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return fail(SPB_ERR_NO_DEVICE, "no CUDA device available; spumoni_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(SPB_ERR_ARG, "device ordinal out of range");
+    for (uint64_t i = 0; i + 1 < n; i++) if (text[i] <= 1) return fail(SPB_ERR_ARG, "the text contains a byte <= 0x01 before its terminator");
+    return guarded([&]() -> int {
+        spb::BuildParts P;
+        std::string err;
+        if (!spb::build_rlbwt_device(text, n, device, P, err, std::getenv("SPUMONI_B200_TIMING") != nullptr))
+            return fail(err.find("length") != std::string::npos ? SPB_ERR_LIMIT : SPB_ERR_CUDA, err);
+        const size_t r = P.heads.size();
+        out->n = P.n; out->r = r;
+        out->heads = (uint8_t*)std::malloc(r ? r : 1);
+        uint64_t* block = (uint64_t*)std::malloc((r ? r : 1) * 4 * sizeof(uint64_t));
+        if (!out->heads || !block) { std::free(out->heads); std::free(block); std::memset(out, 0, sizeof(*out)); return fail(SPB_ERR_LIMIT, "out of host memory"); }
+        out->lens = block; out->thr = block + r; out->ssa = block + 2 * r; out->esa = block + 3 * r;
+        std::memcpy(out->heads, P.heads.data(), r);
+        std::memcpy(out->lens, P.lens.data(), r * 8);
+        std::memcpy(out->thr, P.thr.data(), r * 8);
+        std::memcpy(out->ssa, P.ssa.data(), r * 8);
+        std::memcpy(out->esa, P.esa.data(), r * 8);
+        return SPB_OK;
+    });
+}
+void spb_build_parts_free(spb_build_parts* p) {
+    if (!p) return;
+    std::free(p->heads);
+    std::free(p->lens);  // lens / thr / ssa / esa share one allocation
+    std::memset(p, 0, sizeof(*p));
+}
+int spb_build_parts_write(const char* ref_file, const spb_build_parts* p) {
+    if (!ref_file || !p || (p->r && (!p->heads || !p->lens))) return fail(SPB_ERR_ARG, "spb_build_parts_write: bad argument");
+    const std::string ref(ref_file);
+    auto put5 = [](std::FILE* f, uint64_t v) { std::fwrite(&v, 1, 5, f); };
+    std::FILE* h = std::fopen((ref + ".bwt.heads").c_str(), "wb");
+    std::FILE* l = std::fopen((ref + ".bwt.len").c_str(), "wb");
+    std::FILE* t = std::fopen((ref + ".thr_pos").c_str(), "wb");
+    std::FILE* s = std::fopen((ref + ".ssa").c_str(), "wb");
+    std::FILE* e = std::fopen((ref + ".esa").c_str(), "wb");
+    const bool ok = h && l && t && s && e;
+    if (ok) {
+        uint64_t pos = 0;
+        std::fwrite(p->heads, 1, p->r, h);
+        for (uint64_t k = 0; k < p->r; k++) {
+            put5(l, p->lens[k]);
+            put5(t, p->thr[k]);
+            put5(s, pos); put5(s, p->ssa[k]);
+            pos += p->lens[k];
+            put5(e, pos - 1); put5(e, p->esa[k]);
+        }
+    }
+    bool closed = true;
+    for (std::FILE* f : {h, l, t, s, e}) if (f && std::fclose(f) != 0) closed = false;
+    if (!ok || !closed) return fail(SPB_ERR_IO, "cannot write the build intermediates next to " + ref);
+    return SPB_OK;
+}
 
 // test hooks for the host-side planning (no GPU needed)
 int spb_plan_chunks(const uint64_t* offsets, uint64_t n_reads, uint64_t want_reads, uint64_t min_bases, uint64_t max_bases,

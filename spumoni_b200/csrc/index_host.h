@@ -67,8 +67,10 @@ DecodedIndex parse_index_file(const std::string& path, bool ms);
 // Cut runs into rows so that the LF image of a row overlaps few rows and no row is too long (index_host.cpp); call after
 // parse_index_file / load_doc_array and before build_flat_image.
 struct BalanceParams {
-    uint32_t trigger = 8;   // cut a row whose LF image overlaps more than this many rows ... (0 = leave the runs alone)
-    uint32_t target = 4;    // ... into pieces that overlap this many
+    uint32_t trigger = 4;   // cut a row whose LF image overlaps more than this many rows ... (0 = leave the runs alone)
+    uint32_t target = 2;    // ... into pieces that overlap this many (measured on the r = 1.5e8 stand-in of config 4: 8/4 ->
+                            // 30 Gbases/s with 1.15 x the rows, 4/2 -> 35 with 1.43 x, 3/1 and 2/1 -> 38-39 with 4.8-6.6 x: a target
+                            // of 1 does not converge, every cut makes a new boundary; profiles/r2c_*)
     uint64_t lcap = 4093;   // and any row longer than this (SPB_MV_THR_MAX: in-run thresholds stay exact); 0 = no cap
 };
 BalanceParams default_balance_params();

@@ -662,7 +662,7 @@ public:
         data_ = (const char*)mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
         if (data_ == MAP_FAILED) fatal_error("cannot map " + path);
         madvise((void*)data_, size_, MADV_WILLNEED);
-        out_fd_ = ::open(text_path.c_str(), O_WRONLY);
+        out_fd_ = ::open(text_path.c_str(), O_RDWR);
         if (out_fd_ < 0) fatal_error("cannot open " + text_path);
         for (auto& b : batches_) free_q_.push(&b);
         std::thread parser([&] { parse_loop(); });
@@ -770,18 +770,39 @@ private:
     void write_batch(FastBatch& b) {
         if (!b.n_reads) return;
         double t0 = now_s();
-        const uint64_t piece = 8ull << 20, np = (b.text_bytes + piece - 1) / piece;
         const char* text = b.text.as<char>();
         const uint64_t base_off = text_off_;
         int failed = 0;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_) reduction(| : failed)
-        for (int64_t i = 0; i < (int64_t)np; i++) {
-            uint64_t a = (uint64_t)i * piece;
-            const uint64_t e = std::min(b.text_bytes, a + piece);
-            while (a < e) {
-                const ssize_t wr = pwrite(out_fd_, text + a, e - a, (off_t)(base_off + a));
-                if (wr <= 0) { failed = 1; break; }
-                a += (uint64_t)wr;
+        // SPUMONI_B200_WRITE=pwrite (default): 8 MiB pieces on -t threads | write: one call | mmap: extend the file, map the
+        // window's range and copy on -t threads (buffered writes to ONE file serialise on its inode lock whatever the thread
+        // count -- about 5-6 GB/s on the pool's boxes, which is what bounds the phase; page faults on a shared mapping do not)
+        static const char* wm = std::getenv("SPUMONI_B200_WRITE");
+        const int mode = !wm ? 0 : (std::strcmp(wm, "write") == 0 ? 1 : (std::strcmp(wm, "mmap") == 0 ? 2 : 0));
+        if (mode == 2) {
+            const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE), lo = base_off / pg * pg, hi = base_off + b.text_bytes;
+            if (ftruncate(out_fd_, (off_t)hi) != 0) failed = 1;
+            char* m = failed ? nullptr : (char*)mmap(nullptr, hi - lo, PROT_READ | PROT_WRITE, MAP_SHARED, out_fd_, (off_t)lo);
+            if (!m || m == MAP_FAILED) failed = 1;
+            else {
+                const uint64_t piece = 2ull << 20, np = (b.text_bytes + piece - 1) / piece;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads_)
+                for (int64_t i = 0; i < (int64_t)np; i++) {
+                    const uint64_t a = (uint64_t)i * piece, e = std::min(b.text_bytes, a + piece);
+                    std::memcpy(m + (base_off - lo) + a, text + a, e - a);
+                }
+                munmap(m, hi - lo);
+            }
+        } else {
+            const uint64_t piece = mode == 1 ? b.text_bytes : (8ull << 20), np = piece ? (b.text_bytes + piece - 1) / piece : 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(mode == 1 ? 1 : threads_) reduction(| : failed)
+            for (int64_t i = 0; i < (int64_t)np; i++) {
+                uint64_t a = (uint64_t)i * piece;
+                const uint64_t e = std::min(b.text_bytes, a + piece);
+                while (a < e) {
+                    const ssize_t wr = pwrite(out_fd_, text + a, e - a, (off_t)(base_off + a));
+                    if (wr <= 0) { failed = 1; break; }
+                    a += (uint64_t)wr;
+                }
             }
         }
         if (failed) fatal_error("write to the output file failed");

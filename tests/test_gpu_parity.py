@@ -676,3 +676,78 @@ def test_replicated_index_two_gpus(small_index):
     Lm, Pm, _ = ms2.query_host(buf, off)
     Lmo, Pmo = oracle_batch(small_index["ref"], "ms", buf, off)
     assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
+
+
+def _cli_run(env_extra, prefix, reads, flags):
+    env = dict(os.environ, **env_extra)
+    r = subprocess.run([sp.CLI_PATH, "run", "-r", prefix, "-p", reads, "-n"] + flags, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    out = {}
+    for ext in (".pseudo_lengths", ".report"):
+        if os.path.exists(reads + ext):
+            out[ext] = open(reads + ext, "rb").read()
+            os.remove(reads + ext)
+    return out, r.stderr
+
+
+@pytest.fixture(scope="module")
+def many_reads(small_index, tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("many"))
+    path = os.path.join(d, "many.fa")
+    subprocess.check_call([MKINDEX, "reads", "--ref", small_index["ref"], "--n", "30000", "--len", "60", "--len-max", "400", "--sub", "0.05",
+                           "--neg-frac", "0.3", "--seed", "11", "--out", path], stdout=subprocess.DEVNULL)
+    with open(path, "a") as f:  # multi-line records, CRLF, ids with descriptions: the window parser's special cases
+        f.write(">ml one two\nACGTACGTAC\nGGTTAACC\n\n>crlf\r\nACGTTGCA\r\n>last_no_newline\nACGTAC")
+    if not os.path.exists(small_index["ref"] + ".pmlnulldb"):  # -c needs the null database of the index
+        ((np.arange(1, 200, dtype=np.uint64) * 7) % 11).tofile(os.path.join(d, "stats.bin"))
+        subprocess.check_call([MKINDEX, "nulldb", "--stats", os.path.join(d, "stats.bin"), "--out", small_index["ref"] + ".pmlnulldb"])
+    return path
+
+
+def test_cli_fast_path_equals_sequential_path(small_index, many_reads):
+    """`spumoni run -P`: the fast path (memory-mapped FASTA cut into windows, parallel parse into pinned buffers, text
+    formatted on the device, parallel writes) gives the bytes of the sequential path -- itself byte-identical to the
+    reference's files (test_cli_outputs_byte_identical_to_reference) -- for every window size and write mode."""
+    prefix = small_index["ref"][:-3]
+    want, _ = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, many_reads, ["-P", "-c"])
+    assert len(want[".pseudo_lengths"]) > 4_000_000 and ".report" in want
+    for env in ({}, {"SPUMONI_B200_BATCH_MB": "1"}, {"SPUMONI_B200_BATCH_MB": "1", "SPUMONI_B200_WRITE": "mmap"},
+                {"SPUMONI_B200_BATCH_MB": "2", "SPUMONI_B200_WRITE": "write"}):
+        for t in ("1", "5"):
+            got, err = _cli_run(env, prefix, many_reads, ["-P", "-c", "-t", t])
+            assert got == want, (env, t)
+            assert "finished processing 30003 reads" in err
+
+
+def test_cli_fast_path_hands_over_on_odd_records(small_index, tmp_path):
+    """A header without an id in a later window: the windows before it are written by the fast path, then the sequential
+    parser takes over at that window and fails exactly like BatchLoader does (same message, exit code 1)."""
+    prefix = small_index["ref"][:-3]
+    text = "".join(l.strip() for l in open(small_index["ref"]) if not l.startswith(">"))
+    path = str(tmp_path / "odd.fa")
+    with open(path, "w") as f:
+        for i in range(20000):
+            f.write(">r%d\n%s\n" % (i, text[i:i + 80]))
+        f.write(">\nACGT\n>after\nACGT\n")
+    outs = []
+    for env in ({"SPUMONI_B200_SEQUENTIAL": "1"}, {"SPUMONI_B200_BATCH_MB": "1"}):
+        r = subprocess.run([sp.CLI_PATH, "run", "-r", prefix, "-p", path, "-P", "-n"], capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 1 and "header line is missing an id" in r.stderr
+        outs.append(r.returncode)
+        os.remove(path + ".pseudo_lengths")
+
+
+def test_cli_two_gpus_byte_identical(small_index, many_reads):
+    """`spumoni run` on two GPUs (windows go round robin to one query thread per GPU, written in input order) = one GPU."""
+    if sp.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    prefix = small_index["ref"][:-3]
+    one, _ = _cli_run({"SPUMONI_B200_DEVICES": "0", "SPUMONI_B200_BATCH_MB": "1"}, prefix, many_reads, ["-P", "-c", "-t", "4"])
+    two, err = _cli_run({"SPUMONI_B200_DEVICES": "0,1", "SPUMONI_B200_BATCH_MB": "1", "SPUMONI_B200_TIMING": "1"}, prefix, many_reads, ["-P", "-c", "-t", "4"])
+    assert one == two and "devices: 2" in err
+    # the sequential path shards every batch over both GPUs inside the C ABI
+    seq, _ = _cli_run({"SPUMONI_B200_DEVICES": "1,0", "SPUMONI_B200_SEQUENTIAL": "1"}, prefix, many_reads, ["-P", "-c", "-t", "4"])
+    assert seq == one
+    # -t as the number of workers: two threads -> two GPUs
+    auto, err = _cli_run({"SPUMONI_B200_TIMING": "1"}, prefix, many_reads, ["-P", "-c", "-t", "2"])
+    assert auto == one and "devices: 2" in err
