@@ -115,6 +115,14 @@ int spb_index_open(const char* ref_file, int mode, spb_index** out);
  * -> DocumentArray::load of <ref_file>.doc (doc_array.cpp:197-201); enables the *_doc queries below. */
 int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index** out);
 
+/* Deep check of an index file (no GPU needed): parses it like spb_index_open and additionally RE-DERIVES every redundant
+ * acceleration structure stored in it -- sdsl's select_support_mcl (two per Elias-Fano vector and per wavelet tree) and
+ * rank_support_v -- from the decoded bits and compares them with the file byte for byte.  SPB_ERR_FORMAT names the field
+ * that disagrees.  This is the self-test to run on the first index written by a real `spumoni build`: the byte layout of
+ * the third-party containers (sdsl-lite, r-index) is reconstructed from their published formats, not from vendored sources
+ * (docs/FORMAT_MAP.md lists every field with the upstream function that writes it). */
+int spb_index_verify(const char* ref_file, int mode);
+
 /* get_bwt_stats() compute_ms_pml.cpp:171-173 / :484-486 */
 int spb_index_stats(const spb_index* idx, uint64_t* n, uint64_t* r);
 

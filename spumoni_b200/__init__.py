@@ -116,6 +116,7 @@ def load_library() -> ctypes.CDLL:
     L.spb_build_parts_free.argtypes = [ctypes.POINTER(_BuildParts)]
     L.spb_build_parts_free.restype = None
     L.spb_build_parts_write.argtypes = [cp, ctypes.POINTER(_BuildParts)]
+    L.spb_index_verify.argtypes = [cp, i32]
     L.spb_index_replicate.argtypes = [vp, ctypes.POINTER(i32), i32]
     L.spb_index_device_count.argtypes = [vp]
     L.spb_replicate_method.restype = cp
@@ -213,6 +214,11 @@ def build_parts_device(text: np.ndarray, device: int = 0, write_to: Optional[str
     finally:
         lib.spb_build_parts_free(ctypes.byref(P))
     return out
+
+
+def verify_index(ref_file: str, mode: int) -> None:
+    """spb_index_verify: deep self-test of an index file (re-derives the stored select / rank supports); raises with the field name."""
+    _check(load_library().spb_index_verify(ref_file.encode(), mode))
 
 
 def bits_bytes(n_bases: int) -> int:

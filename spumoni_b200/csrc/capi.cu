@@ -714,6 +714,17 @@ int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index*
     });
 }
 
+int spb_index_verify(const char* ref_file, int mode) {
+    if (!ref_file || (mode != SPB_MODE_PML && mode != SPB_MODE_MS)) return fail(SPB_ERR_ARG, "spb_index_verify: bad argument");
+    return guarded([&]() -> int {
+        setenv("SPUMONI_B200_VERIFY_INDEX", "1", 1);
+        struct Unset { ~Unset() { unsetenv("SPUMONI_B200_VERIFY_INDEX"); } } unset;
+        const bool ms = mode == SPB_MODE_MS;
+        (void)spb::parse_index_file(std::string(ref_file) + (ms ? ".thrbv.ms" : ".thrbv.spumoni"), ms);
+        return SPB_OK;
+    });
+}
+
 int spb_index_stats(const spb_index* idx, uint64_t* n, uint64_t* r) {
     if (!idx) return fail(SPB_ERR_ARG, "null index");
     if (n) *n = idx->hdr.n;

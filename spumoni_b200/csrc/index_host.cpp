@@ -46,6 +46,7 @@ public:
         return p;
     }
     bool at_end() const { return cur_ == end_; }
+    const uint8_t* pos() const { return cur_; }
     size_t remaining() const { return (size_t)(end_ - cur_); }
 private:
     template <typename T> T scalar() {
@@ -96,14 +97,146 @@ PackedInts read_packed(ByteReader& in, uint32_t fixed_width) {
 constexpr int kSlices = 64;
 inline uint64_t slice_lo(uint64_t total, int c) { return (uint64_t)((unsigned __int128)total * (unsigned)c / kSlices); }
 
-// sdsl::select_support_mcl: only its extent matters (it is an accelerator, not data)
-void skip_select_support(ByteReader& in) {
+// ---- deep verification of the redundant parts of the file (SPUMONI_B200_VERIFY_INDEX=1 / spb_index_verify) -----------
+// The succinct containers carry acceleration structures that the loader does not need: select_support_mcl (twice per
+// Elias-Fano vector, twice per wavelet tree) and rank_support_v (once per wavelet tree).  Normally only their extent is
+// parsed.  In verify mode they are RE-DERIVED from the decoded bits, following the published construction of sdsl-lite
+// (select_support_mcl<b,1>::init_slow + serialize: superblocks of 4096 arguments, 64-spaced mini blocks or, past
+// log^4 n, long superblocks; rank_support_v<1,1>: per 512 bits an absolute count and seven packed 9-bit relative counts),
+// and compared byte for byte with the file -- so an index written by a real `spumoni build` either matches this
+// loader's understanding of every field or fails with the field's name.
+bool g_verify = false;
+std::string g_field;  // the field being parsed (for error messages)
+
+inline uint32_t bits_hi(uint64_t x) { return x ? 63u - (uint32_t)__builtin_clzll(x) : 0u; }  // sdsl::bits::hi
+
+struct BitWriter {  // int_vector<0> / bit_vector image: header + words
+    std::string out;
+    void u64(uint64_t v) { out.append((const char*)&v, 8); }
+    void u8(uint8_t v) { out.push_back((char)v); }
+    // int_vector<0> of `count` entries of `width` bits
+    void packed(const std::vector<uint64_t>& vals, uint64_t count, uint8_t width, bool with_width) {
+        const uint64_t bits = count * width;
+        u64(bits);
+        if (with_width) u8(width);
+        std::vector<uint64_t> w((size_t)((bits + 63) / 64), 0);
+        for (uint64_t i = 0; i < vals.size(); i++) {
+            const uint64_t b = i * width;
+            const uint32_t sh = (uint32_t)(b & 63);
+            const uint64_t v = width >= 64 ? vals[i] : (vals[i] & ((uint64_t(1) << width) - 1));
+            w[(size_t)(b >> 6)] |= v << sh;
+            if (sh + width > 64) w[(size_t)(b >> 6) + 1] |= v >> (64 - sh);
+        }
+        out.append((const char*)w.data(), w.size() * 8);
+    }
+};
+
+// what select_support_mcl<ones,1> serialises for the bit vector bv
+std::string expected_select_support(const PackedInts& bv, bool ones) {
+    BitWriter o;
+    const uint64_t SB = 4096, nbits = bv.bits;
+    const uint64_t capacity = ((nbits + 63) >> 6) << 6;
+    const uint64_t logn = bits_hi(capacity) + 1, logn4 = logn * logn * logn * logn;
+    uint64_t arg_cnt = 0;
+    for (uint64_t w = 0; w < bv.num_words(); w++) {
+        uint64_t x = bv.word(w);
+        if (w == bv.num_words() - 1 && (nbits & 63)) x &= (uint64_t(1) << (nbits & 63)) - 1;
+        arg_cnt += (uint64_t)__builtin_popcountll(x);
+    }
+    if (!ones) arg_cnt = nbits - arg_cnt;
+    o.u64(arg_cnt);
+    if (!arg_cnt) return o.out;
+    const uint64_t sb = (arg_cnt + SB - 1) / SB;
+    std::vector<uint64_t> superblock((size_t)sb, 0);
+    struct Blk { bool is_long = false; uint8_t width = 0; std::vector<uint64_t> vals; };
+    std::vector<Blk> blk((size_t)sb);
+    bool any_long = false;
+    std::vector<uint64_t> argpos((size_t)SB);
+    uint64_t cnt = 0, sb_cnt = 0;
+    for (uint64_t i = 0; i < nbits; i++) {
+        if (bv.bit(i) != ones) continue;
+        argpos[(size_t)(cnt % SB)] = i;
+        ++cnt;
+        if (cnt % SB == 0 || cnt == arg_cnt) {
+            superblock[(size_t)sb_cnt] = argpos[0];
+            const uint64_t last = (cnt - 1) % SB, pos_diff = argpos[(size_t)last] - argpos[0];
+            Blk& b = blk[(size_t)sb_cnt];
+            if (pos_diff > logn4) {
+                any_long = true;
+                b.is_long = true;
+                b.width = (uint8_t)(bits_hi(argpos[(size_t)last]) + 1);
+                b.vals.assign((size_t)SB, 0);
+                for (uint64_t j = 0; j <= last; j++) b.vals[(size_t)j] = argpos[(size_t)j];
+            } else {
+                b.width = (uint8_t)(bits_hi(pos_diff) + 1);
+                b.vals.assign(64, 0);
+                for (uint64_t j = 0; j <= last; j += 64) b.vals[(size_t)(j / 64)] = argpos[(size_t)j] - argpos[0];
+            }
+            ++sb_cnt;
+        }
+    }
+    o.packed(superblock, sb, (uint8_t)logn, true);
+    std::vector<uint64_t> mol((size_t)(any_long ? sb : 0), 0);
+    for (uint64_t i = 0; i < mol.size(); i++) mol[(size_t)i] = blk[(size_t)i].is_long ? 0 : 1;
+    o.packed(mol, mol.size(), 1, false);
+    for (const Blk& b : blk) o.packed(b.vals, b.vals.size(), b.width, true);
+    return o.out;
+}
+
+// what rank_support_v<1,1> serialises for bv: one int_vector<64>
+std::string expected_rank_support(const PackedInts& bv) {
+    const uint64_t capacity = ((bv.bits + 63) >> 6) << 6, nblk = ((capacity >> 9) + 1) << 1, words = capacity >> 6;
+    std::vector<uint64_t> bb((size_t)nblk, 0);
+    auto pop = [&](uint64_t w) {
+        uint64_t x = bv.word(w);
+        if (w == bv.num_words() - 1 && (bv.bits & 63)) x &= (uint64_t(1) << (bv.bits & 63)) - 1;
+        return (uint64_t)__builtin_popcountll(x);
+    };
+    uint64_t j = 0, sum = words ? pop(0) : 0, second = 0, i;
+    for (i = 1; i < words; ++i) {
+        if (!(i & 7)) {
+            j += 2;
+            bb[(size_t)j - 1] = second;
+            bb[(size_t)j] = bb[(size_t)j - 2] + sum;
+            second = sum = 0;
+        } else second |= sum << (63 - 9 * (i & 7));
+        sum += pop(i);
+    }
+    if (i & 7) {
+        second |= sum << (63 - 9 * (i & 7));
+        bb[(size_t)j + 1] = second;
+    } else {
+        j += 2;
+        bb[(size_t)j - 1] = second;
+        bb[(size_t)j] = bb[(size_t)j - 2] + sum;
+        bb[(size_t)j + 1] = 0;
+    }
+    BitWriter o;
+    o.packed(bb, nblk, 64, false);
+    return o.out;
+}
+
+void compare_section(const uint8_t* from, const uint8_t* to, const std::string& want, const char* what) {
+    const size_t got = (size_t)(to - from);
+    if (got != want.size() || std::memcmp(from, want.data(), got) != 0) {
+        size_t at = 0;
+        while (at < got && at < want.size() && from[at] == (uint8_t)want[at]) at++;
+        throw FormatError(g_field + ": " + what + " in the file differs from the one derived from the decoded bits (" + std::to_string(got) +
+                          " bytes in the file, " + std::to_string(want.size()) + " expected, first difference at byte " + std::to_string(at) + ")");
+    }
+}
+
+// sdsl::select_support_mcl: only its extent matters (it is an accelerator, not data) -- unless verifying
+void skip_select_support(ByteReader& in, const PackedInts* bv = nullptr, bool ones = true) {
+    const uint8_t* from = in.pos();
     const uint64_t args = in.u64();
-    if (args == 0) return;
-    read_packed(in, 0);  // superblock
-    read_packed(in, 1);  // mini_or_long
-    const uint64_t superblocks = (args + 4095) >> 12;
-    for (uint64_t i = 0; i < superblocks; i++) read_packed(in, 0);
+    if (args != 0) {
+        read_packed(in, 0);  // superblock
+        read_packed(in, 1);  // mini_or_long
+        const uint64_t superblocks = (args + 4095) >> 12;
+        for (uint64_t i = 0; i < superblocks; i++) read_packed(in, 0);
+    }
+    if (g_verify && bv) compare_section(from, in.pos(), expected_select_support(*bv, ones), ones ? "select_support_mcl<1>" : "select_support_mcl<0>");
 }
 
 // ri::sparse_sd_vector -> sorted positions of the set bits
@@ -123,8 +256,8 @@ SparseBits read_sparse_bits(ByteReader& in) {
     const uint32_t wl = in.u8();
     PackedInts low = read_packed(in, 0);
     PackedInts high = read_packed(in, 1);
-    skip_select_support(in);
-    skip_select_support(in);
+    skip_select_support(in, &high, true);
+    skip_select_support(in, &high, false);
     if (size != s.universe) throw FormatError("sparse_sd_vector: size != universe");
     if (declared && low.width != wl) throw FormatError("sparse_sd_vector: low width != wl");
     // Elias-Fano: the i-th set bit of `high` at index b encodes bucket b - i. Slices of `high` decode independently once
@@ -174,9 +307,13 @@ RawVec<uint8_t> read_wavelet_string(ByteReader& in) {
     const uint64_t size = in.u64();
     const uint64_t sigma = in.u64();
     PackedInts bv = read_packed(in, 1);
-    read_packed(in, 64);  // rank_support_v blocks
-    skip_select_support(in);
-    skip_select_support(in);
+    {
+        const uint8_t* from = in.pos();
+        read_packed(in, 64);  // rank_support_v blocks
+        if (g_verify) compare_section(from, in.pos(), expected_rank_support(bv), "rank_support_v");
+    }
+    skip_select_support(in, &bv, true);
+    skip_select_support(in, &bv, false);
     const uint64_t nnodes = in.u64();
     if (nnodes > 1024) throw FormatError("wt_huff: implausible node count");
     struct Node { uint64_t bv_pos, bv_pos_rank; uint16_t parent, child0, child1; };
@@ -260,7 +397,10 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
     RawVec<uint8_t> buf = slurp(path);
     ByteReader in(buf.data(), buf.size());
     DecodedIndex d;
+    g_verify = std::getenv("SPUMONI_B200_VERIFY_INDEX") != nullptr;
+    auto letter = [](int c) { char b[16]; std::snprintf(b, sizeof(b), c > 32 && c < 127 ? "['%c']" : "[0x%02x]", c); return std::string(b); };
     try {
+        g_field = "terminator_position / F";
         d.terminator_position = in.u64();
         const uint64_t fsize = in.u64();
         if (fsize != 256) throw FormatError("F does not have 256 entries");
@@ -271,10 +411,13 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
         d.R = in.u64();
         const uint64_t B = in.u64();
         if (d.n == 0 || d.R == 0 || B == 0) throw FormatError("empty BWT");
+        g_field = "bwt.runs (ri::sparse_sd_vector)";
         SparseBits runs = read_sparse_bits(in);
         std::vector<SparseBits> per_letter(256);
-        for (int c = 0; c < 256; c++) per_letter[c] = read_sparse_bits(in);
+        for (int c = 0; c < 256; c++) { g_field = "bwt.runs_per_letter" + letter(c) + " (ri::sparse_sd_vector)"; per_letter[c] = read_sparse_bits(in); }
+        g_field = "bwt.run_heads (ri::huff_string = sdsl::wt_huff<>)";
         d.heads = read_wavelet_string(in);
+        g_field = "run-length BWT";
         if (d.heads.size() != d.R) throw FormatError("run_heads.size() != R");
         const uint64_t R = d.R;
         // ordinal of every run among the runs of its letter: per-slice letter counts, then an exclusive scan
@@ -344,6 +487,7 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
             for (int64_t k = 0; k < (int64_t)R; k++) out[(size_t)k] = v.at((uint64_t)k);
         };
         if (ms) {
+            g_field = "samples_last (sdsl::int_vector<>)";
             PackedInts sl = read_packed(in, 0);
             if (sl.count() != R) throw FormatError("samples_last has != R entries");
             unpack(sl, d.samples_last);
@@ -351,7 +495,8 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
         // thr_bv: thresholds of the j-th c-run (j >= 1) is the (j-1)-th bit of thresholds_per_letter[c]
         {
             std::vector<SparseBits> thr(256);
-            for (int c = 0; c < 256; c++) thr[c] = read_sparse_bits(in);
+            for (int c = 0; c < 256; c++) { g_field = "thresholds_per_letter" + letter(c) + " (ri::sparse_sd_vector)"; thr[c] = read_sparse_bits(in); }
+            g_field = "thresholds";
             for (int a = 0; a < 256; a++) {
                 const uint64_t want = runs_of[a] ? runs_of[a] - 1 : 0;
                 if (thr[a].ones.size() < want) throw FormatError("fewer thresholds than runs for a letter");
@@ -370,13 +515,15 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
             }
         }
         if (ms) {
+            g_field = "samples_start (sdsl::int_vector<>)";
             PackedInts ss = read_packed(in, 0);
             if (ss.count() != R) throw FormatError("samples_start has != R entries");
             unpack(ss, d.samples_start);
         }
         if (!in.at_end()) throw FormatError("trailing bytes after the index");
     } catch (FormatError& e) {
-        throw FormatError(path + ": " + e.what());
+        const std::string msg = e.what();
+        throw FormatError(path + ": " + (msg.compare(0, g_field.size(), g_field) == 0 ? msg : "[" + g_field + "] " + msg));
     }
     return d;
 }

@@ -773,11 +773,13 @@ private:
         const char* text = b.text.as<char>();
         const uint64_t base_off = text_off_;
         int failed = 0;
-        // SPUMONI_B200_WRITE=pwrite (default): 8 MiB pieces on -t threads | write: one call | mmap: extend the file, map the
-        // window's range and copy on -t threads (buffered writes to ONE file serialise on its inode lock whatever the thread
-        // count -- about 5-6 GB/s on the pool's boxes, which is what bounds the phase; page faults on a shared mapping do not)
+        // SPUMONI_B200_WRITE=write (default): one call per window | pwrite: 8 MiB pieces on -t threads | mmap: extend the file,
+        // map the window's range and copy on -t threads.  Buffered writes to ONE file serialise on its inode lock whatever
+        // the thread count: tools/fs_write_bench measures 5.2 GB/s for one stream, 4.6 for parallel pwrite and 4.7 through a
+        // shared mapping on the pool's boxes (profiles/r2d_fs_write_bench.txt) -- and with 2.7 bytes of text per base that
+        // write rate, not the GPU, is what bounds the phase.
         static const char* wm = std::getenv("SPUMONI_B200_WRITE");
-        const int mode = !wm ? 0 : (std::strcmp(wm, "write") == 0 ? 1 : (std::strcmp(wm, "mmap") == 0 ? 2 : 0));
+        const int mode = !wm ? 1 : (std::strcmp(wm, "pwrite") == 0 ? 0 : (std::strcmp(wm, "mmap") == 0 ? 2 : 1));
         if (mode == 2) {
             const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE), lo = base_off / pg * pg, hi = base_off + b.text_bytes;
             if (ftruncate(out_fd_, (off_t)hi) != 0) failed = 1;
