@@ -49,6 +49,16 @@ WORKLOADS = {
     "c4s": dict(synth=["--runs", "150000000", "--mean-len", "40", "--seed", "5"],
                 n_reads=1_000_000, read_len=1000, reads=["--sub", "0.55", "--neg-frac", "0.1"],
                 desc="PML, synthetic RLBWT stand-in for config 4 (n ~ 6e9 > 2^32, r = 1.5e8), 1 M x 1 kb search-driven reads per GPU"),
+    # Real-text stand-in for BASELINE configs[3]: a 500 Mb pangenome (5 haplotypes x 100 Mb, + reverse complement: n = 1e9 + 1),
+    # suffix-sorted ON THE GPU (spb_build_parts_device, build_kernels.cu), serialised by the reference's build side (mkindex
+    # from-parts).  The BWT of a real text with r ~ 1.5e8 runs: the row table (32-byte rows) is ~5 GB, far beyond the L2, like a
+    # human pangenome index -- but n < 2^31 (the 32-bit device builder); positions beyond 2^32 are covered by c4s.  SPB_BENCH_WORKLOAD=c4r
+    "c4r": dict(genome=["--kind", "pangenome", "--len", "500000000", "--haps", "5", "--snp", "0.001", "--indel", "0.0001", "--seed", "5"], gpu_build=True,
+                n_reads=1_000_000, read_len=1000, reads=["--sub", "0.06", "--ins", "0.02", "--del", "0.02", "--neg-frac", "0.1"],
+                desc="PML, 500 Mb pangenome index built on the GPU (5x100 Mb, +revcomp, n = 1e9, real BWT with r ~ 1.5e8), 1 M x 1 kb ONT-like reads per GPU"),
+    "c4r_dev": dict(genome=["--kind", "pangenome", "--len", "4000000", "--haps", "4", "--snp", "0.001", "--indel", "0.0001", "--seed", "5"], gpu_build=True,
+                    n_reads=20_000, read_len=1000, reads=["--sub", "0.06", "--ins", "0.02", "--del", "0.02", "--neg-frac", "0.1"],
+                    desc="DEV ONLY: PML, 4 Mb pangenome index built on the GPU, 20 k x 1 kb reads per GPU"),
     "c4s_dev": dict(synth=["--runs", "2000000", "--mean-len", "40", "--seed", "5"],
                     n_reads=20_000, read_len=1000, reads=["--sub", "0.55", "--neg-frac", "0.1"],
                     desc="DEV ONLY: PML, synthetic RLBWT (r = 2e6), 20 k x 1 kb search-driven reads per GPU"),
@@ -104,7 +114,19 @@ def ensure_index(name: str, mode: str = "pml") -> str:
         log(f"built synthetic index {name} in {time.time() - t0:.1f} s")
         return ref
     subprocess.check_call([MKINDEX, "genome", "--out", os.path.join(d, "raw.fa")] + WORKLOADS[name]["genome"], stdout=subprocess.DEVNULL)
-    subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--" + mode], stdout=subprocess.DEVNULL)
+    if w.get("gpu_build"):  # text -> run-length BWT / thresholds / samples on the GPU, then the reference's constructors + serialize
+        import spumoni_b200 as sp
+        txt = os.path.join(d, "idx.txt")
+        subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--text-only", "--dump-text", txt], stdout=subprocess.DEVNULL)
+        t1 = time.time()
+        P = sp.build_parts_device(np.fromfile(txt, dtype=np.uint8), int(os.environ.get("LOCAL_RANK", "0")), write_to=ref)
+        log(f"GPU build of {name}: n={P['n']} r={P['r']} in {time.time() - t1:.1f} s (incl. file I/O of the intermediates)")
+        os.remove(txt)
+        subprocess.check_call([MKINDEX, "from-parts", "--prefix", os.path.join(d, "idx"), "--" + mode], stdout=subprocess.DEVNULL)
+        for ext in (".bwt.heads", ".bwt.len", ".thr_pos", ".ssa", ".esa"):
+            os.remove(ref + ext)
+    else:
+        subprocess.check_call([MKINDEX, "build", "--input", os.path.join(d, "raw.fa"), "--prefix", os.path.join(d, "idx"), "--" + mode], stdout=subprocess.DEVNULL)
     os.remove(os.path.join(d, "raw.fa"))
     open(os.path.join(d, "ok_" + mode), "w").write("ok")
     log(f"built index {name} in {time.time() - t0:.1f} s")
@@ -334,16 +356,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per read (tuning; 0 = library default)")
-    ap.add_argument("--length-bytes", type=int, default=1, choices=[1, 2, 4],
-                    help="element size of the lengths output of the headline measurement (clamped PML lengths stay lossless, see include/spumoni_b200.h)")
+    ap.add_argument("--format", default=None, choices=["bits", "u8", "u16", "u32"],
+                    help="output transport of the headline measurement: bits = one bit per base (SPB_LENGTH_BITS: lossless for any read length, "
+                         "1/8 byte per base over PCIe; the default for PML), u8 / u16 / u32 = lengths of that width (default for --mode ms: u8)")
     ap.add_argument("--mode", default="pml", choices=["pml", "ms"], help="pml = the headline metric (BASELINE configs[1]); ms = configs[2]")
     ap.add_argument("--pointers64", action="store_true", help="--mode ms: keep 64-bit pointers even when 32 bits are lossless")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary measurements (other output formats, MS, -c statistics, CLI)")
-    ap.add_argument("--variants", default="u16,u32,bits,packed_bits,pml_stats,ms,cli", help="which secondary measurements to run (comma-separated)")
+    ap.add_argument("--variants", default="u8,u16,u32,bits,packed_bits,pml_stats,ms,cli", help="which secondary measurements to run (comma-separated)")
     ap.add_argument("--strong", action="store_true", help="strong scaling: a fixed set of 5 x the workload's reads is sharded by bases over the ranks (BASELINE configs[3])")
     args = ap.parse_args()
     want = set() if args.no_variants else set(v for v in args.variants.split(",") if v)
+    main_fmt = args.format or ("bits" if args.mode == "pml" else "u8")
+    if main_fmt == "bits" and args.mode == "ms":
+        raise SystemExit("bench.py: one bit per base describes PML lengths only")
+    args.length_bytes = {"u8": 1, "u16": 2, "u32": 4, "bits": 0}[main_fmt]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     name = os.environ.get("SPB_BENCH_WORKLOAD", "c2")
     w = WORKLOADS[name]
@@ -517,8 +544,8 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    main_fmt = {1: "u8", 2: "u16", 4: "u32"}[args.length_bytes]
     main_m, np_len, np_ptr = measure(idx, main_fmt, mode)
+    main_bits = main_fmt == "bits"
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- parity spot check + CPU baseline (rank 0, N=1)
@@ -531,7 +558,10 @@ def main():
         o = oracle.OracleIndex(ref, mode)
         sec, Lo, Po = o.query_batch(buf[: int(off[sample_reads])], off[: sample_reads + 1], threads=cores)
         sb = int(off[sample_reads])
-        got = sp.widen_lengths(np_len[:sb], off[: sample_reads + 1]) if (mode == "pml" and main_m["clamped"]) else np_len[:sb]
+        if main_bits:
+            got = sp.expand_bits(np_len, off[: sample_reads + 1])
+        else:
+            got = sp.widen_lengths(np_len[:sb], off[: sample_reads + 1]) if (mode == "pml" and main_m["clamped"]) else np_len[:sb]
         mism = int(np.count_nonzero(Lo != got.astype(np.uint64)))
         if mode == "ms":
             mism += int(np.count_nonzero(Po != np_ptr[:sb].astype(np.uint64)))
@@ -555,19 +585,19 @@ def main():
 
     if want and mode == "pml":
         # every transport must give the lengths of the headline run
-        L_main = sp.widen_lengths(np_len, off) if main_m["clamped"] else np_len.astype(np.uint32)
-        fmts = [f for f in ("u16", "u32", "bits", "packed_bits") if f != main_fmt and f in want]
+        L_main = sp.expand_bits(np_len, off) if main_bits else (sp.widen_lengths(np_len, off) if main_m["clamped"] else np_len.astype(np.uint32))
+        fmts = [f for f in ("u8", "u16", "u32", "bits", "packed_bits") if f != main_fmt and f in want]
         if world > 1:
-            fmts = [f for f in ("bits", "packed_bits") if f in want]
+            fmts = [f for f in ("u8", "bits", "packed_bits") if f != main_fmt and f in want]
         for f in fmts:
             v, Lv, _ = measure(idx, f, "pml", device_leg=(f != "packed_bits"), steps=max(2, args.steps // 2))
-            Lx = sp.expand_bits(Lv, off) if f in ("bits", "packed_bits") else Lv.astype(np.uint32)
+            Lx = sp.expand_bits(Lv, off) if f in ("bits", "packed_bits") else (sp.widen_lengths(Lv, off) if v.get("clamped") else Lv.astype(np.uint32))
             v["same"] = bool(v.get("same", True)) and bool(np.array_equal(Lx, L_main))
             if not v["same"]:
                 raise SystemExit(f"bench.py: variant {f} disagrees with the headline lengths")
             keep(f, v)
         if world == 1 and "pml_stats" in want:
-            v, _, _ = measure(idx, main_fmt, "pml", stats=True, steps=max(2, args.steps // 2))
+            v, _, _ = measure(idx, main_fmt, "pml", stats=True, steps=max(2, args.steps // 2))  # -c: per-read bin statistics ride along
             keep("pml_stats", v)
     cli = None
     if world == 1 and mode == "pml" and "synth" not in w and "cli" in want:
@@ -584,7 +614,7 @@ def main():
             idx_ms_ref = ensure_index(name, "ms")
             ms_idx = sp.Index.open(idx_ms_ref, sp.MODE_MS).to_device(local)
             n_ms = ms_idx.get_bwt_stats()[0]
-            v, _, _ = measure(ms_idx, main_fmt, "ms", steps=max(2, args.steps // 2))
+            v, _, _ = measure(ms_idx, "u8" if main_bits else main_fmt, "ms", steps=max(2, args.steps // 2))
             keep("ms", v)
             variants["ms"]["roofline_frac_model"] = BYTES_PER_BASE["ms"] * n_bases / (v["kernel_ms"] / 1e3) / 1e9 / peaks()[0]
             del ms_idx
@@ -598,21 +628,23 @@ def main():
         kavg_ms = main_m["kernel_ms"]
         achieved = BYTES_PER_BASE[mode] * n_bases / (kavg_ms / 1e3) / 1e9
         pw_run = 4 if (mode == "ms" and n < (1 << 32) - 1 and not args.pointers64) else 8
-        as_run = 1 + args.length_bytes + 64 + ((pw_run + 8 + 32) if mode == "ms" else 0)  # the same model with the widths this run used
+        as_run = 1 + (args.length_bytes or 0.125) + 64 + ((pw_run + 8 + 32) if mode == "ms" else 0)  # the same model with the widths this run used
         kname = ("spb_move_kernel<PML>" if mode == "pml" else "spb_move_kernel<MS> + spb_ms_lengths_kernel") if (args.lanes or 1) == 1 else "spb_walk_kernel<G>"
         out = {
             "metric": METRICS[mode], "value": main_m["value"], "unit": "bases/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic",
             "config": {"workload": w["desc"].replace("PML", mode.upper()), "n": n, "r": r, "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
-                       "job_bases": job_bases, "lanes_per_read": args.lanes or 1, "length_bytes": args.length_bytes,
+                       "job_bases": job_bases, "lanes_per_read": args.lanes or 1, "format": main_fmt,
                        "l2": "inputs (1 GB reads per step) and outputs (1-4 GB lengths) larger than L2; no explicit flush",
                        "parallelism": f"reads sharded over {world} GPU(s), index replicated (one NCCL broadcast at load)" +
                                       ("; strong scaling: one fixed set of 5 x the workload's reads cut by bases" if args.strong else "")},
             "clocks": clocks,
             "e2e": {"value": main_m["e2e"], "unit": "bases/s", "h2d_bytes_per_step": main_m["h2d_bytes_per_step"], "d2h_bytes_per_step": main_m["d2h_bytes_per_step"],
-                    "api": f"spb_{mode}_query_host, pinned host buffers, uint{8 * args.length_bytes} lengths ({main_m['clamped']} clamped values per step" +
-                           ("; clamped PML lengths are rebuilt exactly by spb_pml_widen_lengths)" if mode == "pml" else ")")},
+                    "api": (f"spb_{mode}_query_host, pinned host buffers, one byte per base in, " +
+                            ("one bit per base out (SPB_LENGTH_BITS: bit set iff the PML is non-zero, which determines every length; spb_pml_expand_bits)" if main_bits else
+                             f"uint{8 * args.length_bytes} lengths out ({main_m['clamped']} clamped values per step" +
+                             ("; clamped PML lengths are rebuilt exactly by spb_pml_widen_lengths)" if mode == "pml" else ")")))},
             "gpu_launches": int(main_m["launches"]),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "kernel": kname, "kernel_ms": kavg_ms,

@@ -266,6 +266,14 @@ static int cmd_build(const Args& a) {
     }
     for (auto c : T) if (c <= 1) die("input contains bytes <= 0x01");
     T.push_back(0);
+    if (has(a, "dump-text")) {  // the indexed text + terminator as raw bytes (input of the GPU builder, spb_build_parts_device)
+        std::ofstream o(get(a, "dump-text"), std::ios::binary);
+        o.write((const char*)T.data(), (std::streamsize)T.size());
+    }
+    if (has(a, "text-only")) {  // <prefix>.fa (+ the dump) only: the run-length BWT comes from somewhere else (mkindex from-parts)
+        std::printf("{\"n\": %llu}\n", (unsigned long long)T.size());
+        return 0;
+    }
     sdslw::RlbwtParts P;
     if (T.size() < (1ULL << 31)) build_rlbwt<int32_t>(T, P, verbose);
     else build_rlbwt<int64_t>(T, P, verbose);
@@ -381,6 +389,7 @@ static int cmd_synth(const Args& a) {
     const uint64_t tail_mul = std::stoull(get(a, "tail-mul", "500"));
     const uint64_t N = std::stoull(get(a, "n", "0")), L = std::stoull(get(a, "len", "1000"));
     const double sub = std::stod(get(a, "sub", "0.08")), neg = std::stod(get(a, "neg-frac", "0.1"));
+    const uint64_t read_seed = std::stoull(get(a, "read-seed", "0"));  // varies the reads without touching the index
     if (R < 8) die("synth: --runs must be at least 8");
     sdslw::RlbwtParts P;
     P.heads.resize(R);
@@ -418,7 +427,7 @@ static int cmd_synth(const Args& a) {
         }
         start[R] = pos;
     }
-    {
+    if (!has(a, "reads-only")) {  // --reads-only: the index of these parameters exists already, only (other) reads are wanted
         std::ofstream fa(prefix + ".fa");
         fa << ">synthetic_rlbwt_no_text\nN\n";
         std::ofstream o(prefix + ".fa.thrbv.spumoni", std::ios::binary);
@@ -450,7 +459,7 @@ static int cmd_synth(const Args& a) {
     std::vector<uint8_t> buf(off[N]);
 #pragma omp parallel for schedule(dynamic, 64)
     for (int64_t r = 0; r < (int64_t)N; r++) {
-        Rng q((seed << 32) ^ ((uint64_t)r + 1) * 0xD1B54A32D192ED03ULL);
+        Rng q(((seed + read_seed) << 32) ^ ((uint64_t)r + 1) * 0xD1B54A32D192ED03ULL);
         uint8_t* o = buf.data() + off[r];
         if (q.unif() < neg) {
             for (uint64_t i = 0; i < L; i++) o[i] = (uint8_t)ACGT[q.next() & 3];
