@@ -205,6 +205,20 @@ int spb_pml_query_host_text_on(spb_index* idx, int gpu_slot, const uint8_t* read
                                const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
                                uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts);
 
+/* The general form: PML or MS (the mode of the index), with or without document numbers -- every output the reference
+ * writes as text comes back formatted: <reads>.pseudo_lengths | .lengths, .pointers (MS; the reference's 64-bit values),
+ * .doc_numbers (-d, index opened with SPB_OPEN_DOC) (compute_ms_pml.cpp:1003-1010, :1184-1194).  pointers_text must be
+ * non-NULL exactly for an MS index; docs_text may be NULL.  On SPB_ERR_LIMIT every buffer's `bytes` holds the bytes needed
+ * up to the sub-batch that did not fit (grow and repeat). */
+typedef struct {
+    char* text;        /* caller buffer */
+    uint64_t capacity; /* its size */
+    uint64_t bytes;    /* out: bytes written */
+} spb_text_buf;
+int spb_query_host_text_on(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                           const uint8_t* ids, const uint64_t* id_offsets, spb_text_buf* lengths_text, spb_text_buf* pointers_text,
+                           spb_text_buf* docs_text, spb_bin_stats* stats, const spb_query_opts* opts);
+
 /* Document-number variants: pml_t::matching_statistics(read, len, lengths, doc_nums) compute_ms_pml.cpp:734-737 ->
  * pml_pointers::_query :288-340, and ms_t::matching_statistics(read, len, lengths, pointers, doc_nums) :814-828 ->
  * ms_pointers::_query :625-682.  doc_nums[offsets[i] + j] is the document of position j of read i.  The index must

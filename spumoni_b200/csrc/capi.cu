@@ -97,14 +97,18 @@ struct Slot {
     bool sat_pending = false;
     // on-device text formatting (spb_pml_query_host_text)
     DevBuf<uint8_t> d_ids;
-    DevBuf<uint64_t> d_id_offsets, d_starts;
-    DevBuf<char> d_text;
+    DevBuf<uint64_t> d_id_offsets;
     PinBuf<uint64_t> h_id_offsets;
-    uint64_t* h_total = nullptr;
+    struct TextStream {  // one formatted output: lengths, MS pointers, document numbers
+        DevBuf<uint64_t> d_starts;
+        DevBuf<char> d_text;
+    } ts[3];
+    uint64_t* h_total = nullptr;  // 3 x uint64, pinned
     void release() {
         d_reads.release(); d_out.release(); d_offsets.release(); d_pointers_raw.release(); d_docs.release(); d_order.release();
         d_packed.release(); d_stats.release(); d_exc_pos.release(); d_exc_val.release(); h_offsets.release(); h_order.release();
-        d_ids.release(); d_id_offsets.release(); d_starts.release(); d_text.release(); h_id_offsets.release();
+        d_ids.release(); d_id_offsets.release(); h_id_offsets.release();
+        for (auto& t : ts) { t.d_starts.release(); t.d_text.release(); }
         if (d_sat) cudaFree(d_sat);
         if (h_sat) cudaFreeHost(h_sat);
         if (h_total) cudaFreeHost(h_total);
@@ -494,8 +498,6 @@ int query_host(spb_index* idx, HostJob job, uint64_t n_reads) {
 }
 
 // ---- PML query + on-device decimal formatting (first resident GPU) ----------------------------------------------------
-struct TextChunk { int slot; uint64_t nr, id_bytes; uint32_t elem_bytes; };
-
 struct DrainCtxOnExit {  // one GPU's streams only: other host threads may be driving the other GPUs of the handle
     DeviceCtx* c;
     ~DrainCtxOnExit() {
@@ -504,14 +506,22 @@ struct DrainCtxOnExit {  // one GPU's streams only: other host threads may be dr
             if (s.stream) cudaStreamSynchronize(s.stream);
     }
 };
+struct TextChunk { int slot; uint64_t nr, id_bytes; uint32_t length_bytes; };
+enum { kTextLengths = 0, kTextPointers = 1, kTextDocs = 2 };
 
+// PML or MS query + on-device decimal formatting of every requested output (K5) on one GPU of the handle.
 int query_host_text(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads, const uint8_t* ids,
-                    const uint64_t* id_offsets, char* text, uint64_t text_capacity, uint64_t* text_bytes, spb_bin_stats* stats,
+                    const uint64_t* id_offsets, spb_text_buf* out_lengths, spb_text_buf* out_pointers, spb_text_buf* out_docs, spb_bin_stats* stats,
                     const spb_query_opts* opts) {
-    if (!idx || !text_bytes) return fail(SPB_ERR_ARG, "null index / text_bytes");
-    *text_bytes = 0;
+    if (!idx || !out_lengths) return fail(SPB_ERR_ARG, "null index / lengths text");
+    const bool ms = idx->mode == SPB_MODE_MS;
+    spb_text_buf* outs[3] = {out_lengths, ms ? out_pointers : nullptr, out_docs};
+    if (ms && !out_pointers) return fail(SPB_ERR_ARG, "an MS index needs a pointers text buffer");
+    if (!ms && out_pointers) return fail(SPB_ERR_ARG, "pointers text requested from a PML index");
+    for (auto* o : outs) if (o) o->bytes = 0;
     if (n_reads == 0) return SPB_OK;
-    if (!reads || !offsets || !ids || !id_offsets || !text) return fail(SPB_ERR_ARG, "null host buffer");
+    if (!reads || !offsets || !ids || !id_offsets) return fail(SPB_ERR_ARG, "null host buffer");
+    for (auto* o : outs) if (o && !o->text) return fail(SPB_ERR_ARG, "null text buffer");
     if (gpu_slot < 0 || (size_t)gpu_slot >= idx->devs.size() || !idx->devs[(size_t)gpu_slot]->dev_blob)
         return fail(SPB_ERR_NO_DEVICE, "index is not resident on that GPU (call spb_index_to_device / spb_index_replicate)");
     DeviceCtx& c = *idx->devs[(size_t)gpu_slot];
@@ -519,11 +529,13 @@ int query_host_text(spb_index* idx, int gpu_slot, const uint8_t* reads, const ui
     if (rc) return rc;
     DrainCtxOnExit drain{&c};
     const bool want_stats = stats && opts && opts->bin_width;
+    const bool want_docs = out_docs != nullptr;
     const int kSlots = idx->n_slots;
     spb_query_opts qo;
     std::memset(&qo, 0, sizeof(qo));
     if (opts) qo = *opts;
     qo.saturated = nullptr;
+    qo.flags &= ~SPB_QUERY_POINTERS32;  // the text carries the reference's 64-bit pointers (wrap-arounds included, App. C-4)
     std::vector<spb::Chunk> chunks;
     try {
         chunks = spb::plan_chunks(offsets, 0, n_reads, idx->want_reads, idx->min_chunk_bases, idx->max_chunk_bases);
@@ -532,26 +544,44 @@ int query_host_text(spb_index* idx, int gpu_slot, const uint8_t* reads, const ui
     } catch (std::exception& e) {
         return fail(SPB_ERR_ARG, e.what());
     }
-    uint64_t text_off = 0;
+    uint64_t text_off[3] = {0, 0, 0};
     std::deque<TextChunk> inflight;
 
-    // stage 2 of the oldest chunk: its sizes are known -> format on the device, copy the text to its place
+    auto stream_values = [&](Slot& s, int which, uint32_t length_bytes, const void** values, uint32_t* elem) {
+        if (which == kTextLengths) { *values = s.d_out.p; *elem = length_bytes; }
+        else if (which == kTextPointers) { *values = s.d_pointers_raw.p; *elem = 8; }
+        else { *values = s.d_docs.p; *elem = 4; }
+    };
+    // stage 2 of the oldest chunk: its sizes are known -> format on the device, copy every text to its place
     auto finish = [&]() -> int {
         const TextChunk t = inflight.front();
         inflight.pop_front();
         Slot& s = c.slots[t.slot];
         SPB_CUDA(cudaStreamSynchronize(s.stream));
-        const uint64_t total = *s.h_total;
-        if (text_off + total > text_capacity) { *text_bytes = text_off + total; return fail(SPB_ERR_LIMIT, "text buffer too small"); }
-        int r2 = s.d_text.reserve((size_t)(total + total / 4), 64);
-        if (r2) return r2;
-        spb::TextParams tp;
-        tp.values = s.d_out.p; tp.offsets = s.d_offsets.p; tp.ids = s.d_ids.p; tp.id_offsets = s.d_id_offsets.p;
-        tp.n_reads = t.nr; tp.starts = s.d_starts.p; tp.text = s.d_text.p; tp.elem_bytes = t.elem_bytes;
-        SPB_CUDA(spb::launch_text_format(tp, c.num_sms, s.stream));
-        g_launches.fetch_add(1);
-        if (total) SPB_CUDA(cudaMemcpyAsync(text + text_off, s.d_text.p, total, cudaMemcpyDeviceToHost, s.stream));
-        text_off += total;
+        bool too_small = false;
+        for (int w = 0; w < 3; w++) {
+            if (!outs[w]) continue;
+            const uint64_t total = s.h_total[w];
+            if (text_off[w] + total > outs[w]->capacity) too_small = true;
+        }
+        if (too_small) {
+            for (int w = 0; w < 3; w++) if (outs[w]) outs[w]->bytes = text_off[w] + s.h_total[w];  // bytes needed so far
+            return fail(SPB_ERR_LIMIT, "text buffer too small");
+        }
+        for (int w = 0; w < 3; w++) {
+            if (!outs[w]) continue;
+            const uint64_t total = s.h_total[w];
+            int r2 = s.ts[w].d_text.reserve((size_t)(total + total / 4), 64);
+            if (r2) return r2;
+            spb::TextParams tp;
+            stream_values(s, w, t.length_bytes, &tp.values, &tp.elem_bytes);
+            tp.offsets = s.d_offsets.p; tp.ids = s.d_ids.p; tp.id_offsets = s.d_id_offsets.p;
+            tp.n_reads = t.nr; tp.starts = s.ts[w].d_starts.p; tp.text = s.ts[w].d_text.p;
+            SPB_CUDA(spb::launch_text_format(tp, c.num_sms, s.stream));
+            g_launches.fetch_add(1);
+            if (total) SPB_CUDA(cudaMemcpyAsync(outs[w]->text + text_off[w], s.ts[w].d_text.p, total, cudaMemcpyDeviceToHost, s.stream));
+            text_off[w] += total;
+        }
         return SPB_OK;
     };
 
@@ -565,13 +595,17 @@ int query_host_text(spb_index* idx, int gpu_slot, const uint8_t* reads, const ui
         SPB_CUDA(cudaStreamSynchronize(s.stream));
         if (id_offsets[ch.r1] < id_offsets[ch.r0]) return fail(SPB_ERR_ARG, "id_offsets are not non-decreasing");
         const uint64_t i0 = id_offsets[ch.r0], id_bytes = id_offsets[ch.r1] - i0;
-        qo.length_bytes = ch.max_len < 65536 ? 2 : 4;  // a PML never exceeds the read length: uint16 is lossless here
+        // a PML / MS length never exceeds the read length: uint16 is lossless for reads < 65536 bases (document numbers need uint32 lengths)
+        qo.length_bytes = (ch.max_len < 65536 && !want_docs) ? 2 : 4;
         if ((rc = s.d_reads.reserve((size_t)nb + 16, 512)) || (rc = s.d_offsets.reserve((size_t)nr + 1)) || (rc = s.h_offsets.reserve((size_t)nr + 1)) ||
             (rc = s.d_out.reserve((size_t)nb * qo.length_bytes + 64)) || (rc = s.d_stats.reserve(want_stats ? (size_t)nr : 0)) ||
-            (rc = s.d_id_offsets.reserve((size_t)nr + 1)) || (rc = s.d_starts.reserve((size_t)nr + 1)) || (rc = s.h_id_offsets.reserve((size_t)nr + 1)) ||
-            (rc = s.d_ids.reserve((size_t)id_bytes + 64)))
+            (rc = s.d_id_offsets.reserve((size_t)nr + 1)) || (rc = s.h_id_offsets.reserve((size_t)nr + 1)) || (rc = s.d_ids.reserve((size_t)id_bytes + 64)))
             return rc;
-        if (!s.h_total) SPB_CUDA(cudaMallocHost(&s.h_total, sizeof(uint64_t)));
+        if (ms && (rc = s.d_pointers_raw.reserve((size_t)nb + 8))) return rc;
+        if (want_docs && (rc = s.d_docs.reserve((size_t)nb + 16))) return rc;
+        for (int w = 0; w < 3; w++)
+            if (outs[w] && (rc = s.ts[w].d_starts.reserve((size_t)nr + 1))) return rc;
+        if (!s.h_total) SPB_CUDA(cudaMallocHost(&s.h_total, 3 * sizeof(uint64_t)));
         for (uint64_t i = 0; i <= nr; i++) {
             s.h_offsets.p[i] = offsets[ch.r0 + i] - b0;
             const uint64_t io = id_offsets[ch.r0 + i];
@@ -588,21 +622,26 @@ int query_host_text(spb_index* idx, int gpu_slot, const uint8_t* reads, const ui
             SPB_CUDA(cudaMemcpyAsync(s.d_order.p, s.h_order.p, nr * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
             ex.d_order = s.d_order.p;
         }
-        rc = launch_query(idx, c, false, s.d_reads.p, s.d_offsets.p, nr, s.d_out.p, nullptr, nullptr, want_stats ? s.d_stats.p : nullptr, &qo, nullptr, s.stream, ex);
+        rc = launch_query(idx, c, ms, s.d_reads.p, s.d_offsets.p, nr, s.d_out.p, ms ? s.d_pointers_raw.p : nullptr, want_docs ? s.d_docs.p : nullptr,
+                          want_stats ? s.d_stats.p : nullptr, &qo, nullptr, s.stream, ex);
         if (rc) return rc;
-        spb::TextParams tp;
-        tp.values = s.d_out.p; tp.offsets = s.d_offsets.p; tp.ids = s.d_ids.p; tp.id_offsets = s.d_id_offsets.p;
-        tp.n_reads = nr; tp.starts = s.d_starts.p; tp.text = nullptr; tp.elem_bytes = qo.length_bytes;
-        SPB_CUDA(spb::launch_text_sizes(tp, c.num_sms, s.stream));
-        g_launches.fetch_add(2);
-        SPB_CUDA(cudaMemcpyAsync(s.h_total, s.d_starts.p + nr, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        for (int w = 0; w < 3; w++) {
+            if (!outs[w]) continue;
+            spb::TextParams tp;
+            stream_values(s, w, qo.length_bytes, &tp.values, &tp.elem_bytes);
+            tp.offsets = s.d_offsets.p; tp.ids = s.d_ids.p; tp.id_offsets = s.d_id_offsets.p;
+            tp.n_reads = nr; tp.starts = s.ts[w].d_starts.p; tp.text = nullptr;
+            SPB_CUDA(spb::launch_text_sizes(tp, c.num_sms, s.stream));
+            g_launches.fetch_add(2);
+            SPB_CUDA(cudaMemcpyAsync(s.h_total + w, s.ts[w].d_starts.p + nr, sizeof(uint64_t), cudaMemcpyDeviceToHost, s.stream));
+        }
         if (want_stats) SPB_CUDA(cudaMemcpyAsync(stats + ch.r0, s.d_stats.p, nr * sizeof(spb_bin_stats), cudaMemcpyDeviceToHost, s.stream));
         inflight.push_back(TextChunk{slot, nr, id_bytes, qo.length_bytes});
     }
     while (!inflight.empty()) { rc = finish(); if (rc) return rc; }
     for (int i = 0; i < kMaxSlots; i++)
         if (c.slots[i].stream) SPB_CUDA(cudaStreamSynchronize(c.slots[i].stream));
-    *text_bytes = text_off;
+    for (int w = 0; w < 3; w++) if (outs[w]) outs[w]->bytes = text_off[w];
     return SPB_OK;
 }
 
@@ -866,14 +905,23 @@ uint32_t spb_index_num_docs(const spb_index* idx) { return idx ? idx->hdr.num_do
 int spb_pml_query_host_text(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                             const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
                             uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts) {
-    if (idx && idx->mode != SPB_MODE_PML) return fail(SPB_ERR_ARG, "spb_pml_query_host_text on an MS index");
-    return query_host_text(idx, 0, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
+    return spb_pml_query_host_text_on(idx, 0, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
 }
 int spb_pml_query_host_text_on(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                                const uint8_t* ids, const uint64_t* id_offsets, char* text, uint64_t text_capacity,
                                uint64_t* text_bytes, spb_bin_stats* stats, const spb_query_opts* opts) {
-    if (idx && idx->mode != SPB_MODE_PML) return fail(SPB_ERR_ARG, "spb_pml_query_host_text_on on an MS index");
-    return query_host_text(idx, gpu_slot, reads, offsets, n_reads, ids, id_offsets, text, text_capacity, text_bytes, stats, opts);
+    if (!text_bytes) return fail(SPB_ERR_ARG, "null text_bytes");
+    *text_bytes = 0;
+    if (idx && idx->mode != SPB_MODE_PML) return fail(SPB_ERR_ARG, "spb_pml_query_host_text on an MS index");
+    spb_text_buf t{text, text_capacity, 0};
+    const int rc = query_host_text(idx, gpu_slot, reads, offsets, n_reads, ids, id_offsets, &t, nullptr, nullptr, stats, opts);
+    *text_bytes = t.bytes;
+    return rc;
+}
+int spb_query_host_text_on(spb_index* idx, int gpu_slot, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
+                           const uint8_t* ids, const uint64_t* id_offsets, spb_text_buf* lengths_text, spb_text_buf* pointers_text,
+                           spb_text_buf* docs_text, spb_bin_stats* stats, const spb_query_opts* opts) {
+    return query_host_text(idx, gpu_slot, reads, offsets, n_reads, ids, id_offsets, lengths_text, pointers_text, docs_text, stats, opts);
 }
 int spb_ms_query_host(spb_index* idx, const uint8_t* reads, const uint64_t* offsets, uint64_t n_reads,
                       void* lengths, void* pointers, spb_bin_stats* stats, const spb_query_opts* opts) {

@@ -518,12 +518,12 @@ static void write_batch(bool ms, const RunOptions& o, const Work& w, Outputs& ou
     lap(t_write);
 }
 
-// ---------------------------------------------------------------------------------- fast path (FASTA, PML, no -d)
+// ---------------------------------------------------------------------------------- fast path (FASTA input)
 // The file is memory-mapped and cut into windows at record boundaries; a window is parsed on -t threads straight into
 // page-locked buffers (two passes over its records: sizes, then the bytes), queried on one of the GPUs the index is
-// resident on by that GPU's query thread (spb_pml_query_host_text_on: lengths are formatted on the device), and its text
-// is written with pwrite on -t threads at its final offset; windows are written in input order, which is the reference's
-// own order for -t 1 (App. C-11).  Anything the sequential parser treats specially (a header without an id, an empty
+// resident on by that GPU's query thread (spb_query_host_text_on: lengths, MS pointers and document numbers come back
+// formatted by the device), and its texts are written at their final offsets; windows are written in input order, which
+// is the reference's own order for -t 1 (App. C-11).  Anything the sequential parser treats specially (a header without an id, an empty
 // record) makes the fast path hand the rest of the file, from that window on, to the sequential path below, so that
 // messages and partial outputs stay those of BatchLoader.
 struct PinnedBuf {
@@ -543,9 +543,11 @@ struct PinnedBuf {
 
 struct FastBatch {
     uint64_t seq = 0, file_lo = 0;
-    PinnedBuf bases, offsets, idcat, idoff, text, stats;
+    PinnedBuf bases, offsets, idcat, idoff, stats;
+    PinnedBuf text[3];             // lengths | MS pointers | document numbers
+    uint64_t text_bytes[3] = {0, 0, 0};
     std::vector<uint64_t> starts;  // record starts inside the window (file offsets)
-    uint64_t n_reads = 0, n_bases = 0, id_bytes = 0, text_bytes = 0;
+    uint64_t n_reads = 0, n_bases = 0, id_bytes = 0;
     bool anomaly = false, last = false;
 };
 
@@ -634,8 +636,8 @@ static void window_fill(const char* d, const std::vector<uint64_t>& starts, int 
 
 class FastRunner {
 public:
-    FastRunner(const RunOptions& o, int n_gpus) : o_(o), n_gpus_(std::max(1, n_gpus)), threads_((int)std::max<size_t>(1, o.threads)) {
-        window_ = 48ull << 20;
+    FastRunner(const RunOptions& o, bool ms, int n_gpus) : o_(o), ms_(ms), n_gpus_(std::max(1, n_gpus)), threads_((int)std::max<size_t>(1, o.threads)) {
+        window_ = ms ? (16ull << 20) : (48ull << 20);  // an MS window carries ~11 bytes of pointer text per base
         if (const char* e = std::getenv("SPUMONI_B200_BATCH_MB")) { long v = std::atol(e); if (v >= 1 && v <= 2048) window_ = (uint64_t)v << 20; }
         batches_.resize((size_t)(2 * n_gpus_ + 3));
     }
@@ -646,12 +648,15 @@ public:
             b.offsets.reserve((window_ / 64 + 2) * 8);
             b.idoff.reserve((window_ / 64 + 2) * 8);
             b.idcat.reserve(window_ / 8);
-            b.text.reserve(window_ * 3);
+            b.text[0].reserve(window_ * 3);
+            if (ms_) b.text[1].reserve(window_ * 12);
+            if (o_.use_doc) b.text[2].reserve(window_ * 3);
             if (o_.write_report) b.stats.reserve((window_ / 64 + 2) * sizeof(spb_bin_stats));
         }
     }
     // Returns the number of reads processed; *resume_at = file offset where the sequential path must take over (or the file size).
-    size_t run(spb_index* idx, const spb_query_opts& qo, Outputs& out, const std::string& path, const std::string& text_path, uint64_t* resume_at) {
+    // text_paths: lengths, pointers (MS), document numbers (-d); empty = not written
+    size_t run(spb_index* idx, const spb_query_opts& qo, Outputs& out, const std::string& path, const std::string text_paths[3], uint64_t* resume_at) {
         idx_ = idx; qo_ = qo; out_ = &out;
         const int fd = ::open(path.c_str(), O_RDONLY);
         struct stat st;
@@ -662,8 +667,12 @@ public:
         data_ = (const char*)mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
         if (data_ == MAP_FAILED) fatal_error("cannot map " + path);
         madvise((void*)data_, size_, MADV_WILLNEED);
-        out_fd_ = ::open(text_path.c_str(), O_RDWR);
-        if (out_fd_ < 0) fatal_error("cannot open " + text_path);
+        for (int w = 0; w < 3; w++) {
+            out_fd_[w] = -1;
+            if (text_paths[w].empty()) continue;
+            out_fd_[w] = ::open(text_paths[w].c_str(), O_RDWR);
+            if (out_fd_[w] < 0) fatal_error("cannot open " + text_paths[w]);
+        }
         for (auto& b : batches_) free_q_.push(&b);
         std::thread parser([&] { parse_loop(); });
         std::vector<std::thread> gpus;
@@ -671,14 +680,13 @@ public:
         write_loop();
         parser.join();
         for (auto& t : gpus) t.join();
-        ::close(out_fd_);
+        for (int w = 0; w < 3; w++) if (out_fd_[w] >= 0) ::close(out_fd_[w]);
         munmap((void*)data_, size_);
         ::close(fd);
         *resume_at = resume_;
-        text_written_ = text_off_;
         return reads_done_;
     }
-    uint64_t text_written() const { return text_written_; }
+    uint64_t text_written(int w) const { return text_off_[w]; }
     double t_parse = 0, t_gpu = 0, t_write = 0, t_report = 0;
 
 private:
@@ -731,17 +739,28 @@ private:
             if (!b) break;
             const double t0 = now_s();
             if (b->n_reads) {
-                uint64_t need = b->n_bases * 3 + b->id_bytes + 3 * b->n_reads + 64;  // typical PML text is ~2 bytes per base
+                // typical text: ~2 bytes per base of lengths, ~11 of pointers; a buffer that turns out too small is grown and the window redone
+                uint64_t need[3] = {b->n_bases * 3 + b->id_bytes + 3 * b->n_reads + 64, b->n_bases * 12 + b->id_bytes + 3 * b->n_reads + 64,
+                                    b->n_bases * 3 + b->id_bytes + 3 * b->n_reads + 64};
                 for (;;) {
-                    b->text.reserve(need);
-                    const int rc = spb_pml_query_host_text_on(idx_, g, b->bases.as<uint8_t>(), b->offsets.as<uint64_t>(), b->n_reads, b->idcat.as<uint8_t>(),
-                                                              b->idoff.as<uint64_t>(), b->text.as<char>(), b->text.cap, &b->text_bytes,
-                                                              o_.write_report ? b->stats.as<spb_bin_stats>() : nullptr, &qo_);
-                    if (rc == SPB_ERR_LIMIT && b->text_bytes > b->text.cap) { need = b->text_bytes + b->text_bytes / 2; continue; }  // rare: redo with a larger buffer
+                    spb_text_buf tb[3];
+                    for (int w = 0; w < 3; w++) {
+                        if (out_fd_[w] >= 0) b->text[w].reserve(need[w]);
+                        tb[w] = spb_text_buf{b->text[w].as<char>(), b->text[w].cap, 0};
+                    }
+                    const int rc = spb_query_host_text_on(idx_, g, b->bases.as<uint8_t>(), b->offsets.as<uint64_t>(), b->n_reads, b->idcat.as<uint8_t>(),
+                                                          b->idoff.as<uint64_t>(), &tb[0], ms_ ? &tb[1] : nullptr, out_fd_[2] >= 0 ? &tb[2] : nullptr,
+                                                          o_.write_report ? b->stats.as<spb_bin_stats>() : nullptr, &qo_);
+                    bool grow = false;
+                    for (int w = 0; w < 3; w++) {
+                        b->text_bytes[w] = tb[w].bytes;
+                        if (rc == SPB_ERR_LIMIT && out_fd_[w] >= 0 && tb[w].bytes > b->text[w].cap) { need[w] = tb[w].bytes + tb[w].bytes / 2; grow = true; }
+                    }
+                    if (grow) continue;
                     spb_or_die(rc);
                     break;
                 }
-            } else b->text_bytes = 0;
+            } else b->text_bytes[0] = b->text_bytes[1] = b->text_bytes[2] = 0;
             {
                 std::unique_lock<std::mutex> lk(gpu_m_);
                 t_gpu += now_s() - t0;
@@ -770,45 +789,50 @@ private:
     void write_batch(FastBatch& b) {
         if (!b.n_reads) return;
         double t0 = now_s();
-        const char* text = b.text.as<char>();
-        const uint64_t base_off = text_off_;
         int failed = 0;
         // SPUMONI_B200_WRITE=write (default): one call per window | pwrite: 8 MiB pieces on -t threads | mmap: extend the file,
         // map the window's range and copy on -t threads.  Buffered writes to ONE file serialise on its inode lock whatever
         // the thread count: tools/fs_write_bench measures 5.2 GB/s for one stream, 4.6 for parallel pwrite and 4.7 through a
-        // shared mapping on the pool's boxes (profiles/r2d_fs_write_bench.txt) -- and with 2.7 bytes of text per base that
-        // write rate, not the GPU, is what bounds the phase.
+        // shared mapping on the pool's boxes (profiles/r2d_fs_write_bench.txt) -- and with 2.1 bytes of text per base that
+        // write rate, not the GPU, is what bounds the phase.  The (up to three) files of a window are written concurrently.
         static const char* wm = std::getenv("SPUMONI_B200_WRITE");
         const int mode = !wm ? 1 : (std::strcmp(wm, "pwrite") == 0 ? 0 : (std::strcmp(wm, "mmap") == 0 ? 2 : 1));
-        if (mode == 2) {
-            const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE), lo = base_off / pg * pg, hi = base_off + b.text_bytes;
-            if (ftruncate(out_fd_, (off_t)hi) != 0) failed = 1;
-            char* m = failed ? nullptr : (char*)mmap(nullptr, hi - lo, PROT_READ | PROT_WRITE, MAP_SHARED, out_fd_, (off_t)lo);
-            if (!m || m == MAP_FAILED) failed = 1;
-            else {
-                const uint64_t piece = 2ull << 20, np = (b.text_bytes + piece - 1) / piece;
+#pragma omp parallel for schedule(static, 1) num_threads(3) reduction(| : failed) if (ms_ || o_.use_doc)
+        for (int w = 0; w < 3; w++) {
+            if (out_fd_[w] < 0 || !b.text_bytes[w]) continue;
+            const char* text = b.text[w].as<char>();
+            const uint64_t base_off = text_off_[w], nbytes = b.text_bytes[w];
+            const int fd = out_fd_[w];
+            if (mode == 2) {
+                const uint64_t pg = (uint64_t)sysconf(_SC_PAGESIZE), lo = base_off / pg * pg, hi = base_off + nbytes;
+                if (ftruncate(fd, (off_t)hi) != 0) { failed = 1; continue; }
+                char* m = (char*)mmap(nullptr, hi - lo, PROT_READ | PROT_WRITE, MAP_SHARED, fd, (off_t)lo);
+                if (!m || m == MAP_FAILED) { failed = 1; continue; }
+                const uint64_t piece = 2ull << 20, np = (nbytes + piece - 1) / piece;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads_)
                 for (int64_t i = 0; i < (int64_t)np; i++) {
-                    const uint64_t a = (uint64_t)i * piece, e = std::min(b.text_bytes, a + piece);
+                    const uint64_t a = (uint64_t)i * piece, e = std::min(nbytes, a + piece);
                     std::memcpy(m + (base_off - lo) + a, text + a, e - a);
                 }
                 munmap(m, hi - lo);
-            }
-        } else {
-            const uint64_t piece = mode == 1 ? b.text_bytes : (8ull << 20), np = piece ? (b.text_bytes + piece - 1) / piece : 0;
-#pragma omp parallel for schedule(dynamic, 1) num_threads(mode == 1 ? 1 : threads_) reduction(| : failed)
-            for (int64_t i = 0; i < (int64_t)np; i++) {
-                uint64_t a = (uint64_t)i * piece;
-                const uint64_t e = std::min(b.text_bytes, a + piece);
-                while (a < e) {
-                    const ssize_t wr = pwrite(out_fd_, text + a, e - a, (off_t)(base_off + a));
-                    if (wr <= 0) { failed = 1; break; }
-                    a += (uint64_t)wr;
+            } else {
+                const uint64_t piece = mode == 1 ? nbytes : (8ull << 20), np = (nbytes + piece - 1) / piece;
+                int bad = 0;
+#pragma omp parallel for schedule(dynamic, 1) num_threads(mode == 1 ? 1 : threads_) reduction(| : bad)
+                for (int64_t i = 0; i < (int64_t)np; i++) {
+                    uint64_t a = (uint64_t)i * piece;
+                    const uint64_t e = std::min(nbytes, a + piece);
+                    while (a < e) {
+                        const ssize_t wr = pwrite(fd, text + a, e - a, (off_t)(base_off + a));
+                        if (wr <= 0) { bad = 1; break; }
+                        a += (uint64_t)wr;
+                    }
                 }
+                failed |= bad;
             }
         }
         if (failed) fatal_error("write to the output file failed");
-        text_off_ += b.text_bytes;
+        for (int w = 0; w < 3; w++) text_off_[w] += b.text_bytes[w];
         reads_done_ += b.n_reads;
         t_write += now_s() - t0;
         if (o_.write_report) {  // rows are formatted on -t threads with the reference's manipulators, written in order
@@ -836,13 +860,14 @@ private:
 
     spb_index* idx_ = nullptr;
     const RunOptions& o_;
+    bool ms_ = false;
     spb_query_opts qo_;
     Outputs* out_ = nullptr;
     int n_gpus_, threads_;
-    uint64_t window_ = 0, size_ = 0, resume_ = 0, text_off_ = 0, text_written_ = 0;
+    uint64_t window_ = 0, size_ = 0, resume_ = 0, text_off_[3] = {0, 0, 0};
     size_t reads_done_ = 0;
     const char* data_ = nullptr;
-    int out_fd_ = -1;
+    int out_fd_[3] = {-1, -1, -1};
     std::vector<FastBatch> batches_;
     Q free_q_, parsed_q_, done_q_;
     std::mutex gpu_m_;
@@ -876,13 +901,17 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o, FastR
     double t_parse = 0, t_gpu = 0, t_format = 0, t_write = 0;
     size_t num_reads = 0;
     uint64_t resume_at = 0;
-    if (fast) {  // FASTA, PML, no -d: memory-mapped input, parallel parse, one query thread per GPU, parallel pwrite
+    if (fast) {  // FASTA input: memory-mapped, parsed on all threads, one query thread per GPU, texts formatted on the device
         int first = EOF;
         { std::ifstream probe(o.pattern_file, std::ifstream::binary); first = probe.peek(); }
         if (first == '>') {
             out.lengths.flush();
-            num_reads = fast->run(idx, qo, out, o.pattern_file, o.pattern_file + ".pseudo_lengths", &resume_at);
-            out.lengths.seekp((std::streamoff)fast->text_written());
+            const std::string paths[3] = {o.pattern_file + (ms ? ".lengths" : ".pseudo_lengths"), ms ? o.pattern_file + ".pointers" : std::string(),
+                                          o.use_doc ? o.pattern_file + ".doc_numbers" : std::string()};
+            num_reads = fast->run(idx, qo, out, o.pattern_file, paths, &resume_at);
+            out.lengths.seekp((std::streamoff)fast->text_written(0));
+            if (ms) out.pointers.seekp((std::streamoff)fast->text_written(1));
+            if (o.use_doc) out.docs.seekp((std::streamoff)fast->text_written(2));
             if (timing) std::fprintf(stderr, "\n[timing] busy seconds per stage: parse %.3f | query (H2D + kernels + D2H) %.3f | format 0.000 | write %.3f | report %.3f\n",
                                      fast->t_parse, fast->t_gpu, fast->t_write, fast->t_report);
             struct stat st;
@@ -978,11 +1007,11 @@ static int run_main(int argc, char** argv) {
         for (int d = 0; d < std::max(1, std::min<int>(visible, (int)o.threads)); d++) devices.push_back(d);
     }
     if (devices.empty()) devices.push_back(0);
-    const bool fast_ok = !ms && !o.use_doc && !o.is_general_text && !std::getenv("SPUMONI_B200_HOST_FORMAT") && !std::getenv("SPUMONI_B200_SEQUENTIAL");
+    const bool fast_ok = !o.is_general_text && !std::getenv("SPUMONI_B200_HOST_FORMAT") && !std::getenv("SPUMONI_B200_SEQUENTIAL");
     std::unique_ptr<FastRunner> fast;
     std::thread prealloc;
     if (fast_ok && spb_device_count() > 0) {  // page-lock the pipeline's buffers while the index loads
-        fast.reset(new FastRunner(o, (int)devices.size()));
+        fast.reset(new FastRunner(o, ms, (int)devices.size()));
         prealloc = std::thread([&] { fast->preallocate(); });
     }
 

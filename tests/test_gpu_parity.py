@@ -683,7 +683,7 @@ def _cli_run(env_extra, prefix, reads, flags):
     r = subprocess.run([sp.CLI_PATH, "run", "-r", prefix, "-p", reads, "-n"] + flags, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     out = {}
-    for ext in (".pseudo_lengths", ".report"):
+    for ext in (".pseudo_lengths", ".lengths", ".pointers", ".doc_numbers", ".report"):
         if os.path.exists(reads + ext):
             out[ext] = open(reads + ext, "rb").read()
             os.remove(reads + ext)
@@ -698,9 +698,10 @@ def many_reads(small_index, tmp_path_factory):
                            "--neg-frac", "0.3", "--seed", "11", "--out", path], stdout=subprocess.DEVNULL)
     with open(path, "a") as f:  # multi-line records, CRLF, ids with descriptions: the window parser's special cases
         f.write(">ml one two\nACGTACGTAC\nGGTTAACC\n\n>crlf\r\nACGTTGCA\r\n>last_no_newline\nACGTAC")
-    if not os.path.exists(small_index["ref"] + ".pmlnulldb"):  # -c needs the null database of the index
-        ((np.arange(1, 200, dtype=np.uint64) * 7) % 11).tofile(os.path.join(d, "stats.bin"))
-        subprocess.check_call([MKINDEX, "nulldb", "--stats", os.path.join(d, "stats.bin"), "--out", small_index["ref"] + ".pmlnulldb"])
+    for ext in (".pmlnulldb", ".msnulldb"):  # -c needs the null database of the index
+        if not os.path.exists(small_index["ref"] + ext):
+            ((np.arange(1, 200, dtype=np.uint64) * 7) % 11).tofile(os.path.join(d, "stats.bin"))
+            subprocess.check_call([MKINDEX, "nulldb", "--stats", os.path.join(d, "stats.bin"), "--out", small_index["ref"] + ext])
     return path
 
 
@@ -712,11 +713,18 @@ def test_cli_fast_path_equals_sequential_path(small_index, many_reads):
     want, _ = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, many_reads, ["-P", "-c"])
     assert len(want[".pseudo_lengths"]) > 4_000_000 and ".report" in want
     for env in ({}, {"SPUMONI_B200_BATCH_MB": "1"}, {"SPUMONI_B200_BATCH_MB": "1", "SPUMONI_B200_WRITE": "mmap"},
-                {"SPUMONI_B200_BATCH_MB": "2", "SPUMONI_B200_WRITE": "write"}):
+                {"SPUMONI_B200_BATCH_MB": "2", "SPUMONI_B200_WRITE": "pwrite"}):
         for t in ("1", "5"):
             got, err = _cli_run(env, prefix, many_reads, ["-P", "-c", "-t", t])
             assert got == want, (env, t)
             assert "finished processing 30003 reads" in err
+    # MS (lengths + pointers formatted on the device) and document numbers, same comparison
+    for flags in (["-M", "-c"], ["-P", "-d"], ["-M", "-d"]):
+        want, _ = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, many_reads, flags)
+        assert (".pointers" in want) == ("-M" in flags) and (".doc_numbers" in want) == ("-d" in flags)
+        for env in ({"SPUMONI_B200_BATCH_MB": "1"}, {"SPUMONI_B200_WRITE": "pwrite"}):
+            got, _ = _cli_run(env, prefix, many_reads, flags + ["-t", "3"])
+            assert got == want, (flags, env)
 
 
 def test_cli_fast_path_hands_over_on_odd_records(small_index, tmp_path):
