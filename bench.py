@@ -356,9 +356,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per read (tuning; 0 = library default)")
-    ap.add_argument("--format", default=None, choices=["bits", "u8", "u16", "u32"],
-                    help="output transport of the headline measurement: bits = one bit per base (SPB_LENGTH_BITS: lossless for any read length, "
-                         "1/8 byte per base over PCIe; the default for PML), u8 / u16 / u32 = lengths of that width (default for --mode ms: u8)")
+    ap.add_argument("--format", default=None, choices=["packed_bits", "bits", "u8", "u16", "u32"],
+                    help="transport of the headline measurement. packed_bits (default for PML): reads travel as 2 bits per base + an exception list "
+                         "(spb_pml_query_host_packed; the caller packs while it parses, spb_pack_reads) and the PMLs come back as one bit per base "
+                         "(SPB_LENGTH_BITS: lossless for any read length); bits: bytes in, bits out; u8 / u16 / u32: bytes in, lengths of that width out "
+                         "(default for --mode ms: u8)")
     ap.add_argument("--mode", default="pml", choices=["pml", "ms"], help="pml = the headline metric (BASELINE configs[1]); ms = configs[2]")
     ap.add_argument("--pointers64", action="store_true", help="--mode ms: keep 64-bit pointers even when 32 bits are lossless")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -367,10 +369,10 @@ def main():
     ap.add_argument("--strong", action="store_true", help="strong scaling: a fixed set of 5 x the workload's reads is sharded by bases over the ranks (BASELINE configs[3])")
     args = ap.parse_args()
     want = set() if args.no_variants else set(v for v in args.variants.split(",") if v)
-    main_fmt = args.format or ("bits" if args.mode == "pml" else "u8")
-    if main_fmt == "bits" and args.mode == "ms":
+    main_fmt = args.format or ("packed_bits" if args.mode == "pml" else "u8")
+    if main_fmt in ("bits", "packed_bits") and args.mode == "ms":
         raise SystemExit("bench.py: one bit per base describes PML lengths only")
-    args.length_bytes = {"u8": 1, "u16": 2, "u32": 4, "bits": 0}[main_fmt]
+    args.length_bytes = {"u8": 1, "u16": 2, "u32": 4, "bits": 0, "packed_bits": 0}[main_fmt]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     name = os.environ.get("SPB_BENCH_WORKLOAD", "c2")
     w = WORKLOADS[name]
@@ -464,8 +466,9 @@ def main():
     packed_host = {}
 
     def measure(ix, fmt, m="pml", stats=False, device_leg=True, steps=None):
-        """Device-resident and end-to-end timing of one output format.  fmt: "u8" | "u16" | "u32" | "bits" (one bit per base) |
-        "packed_bits" (2-bit packed reads in, bits out; end-to-end only).  Returns a dict + the host outputs."""
+        """Device-resident and end-to-end timing of one transport.  fmt: "u8" | "u16" | "u32" | "bits" (one bit per base) |
+        "packed_bits" (end to end the reads travel as 2 bits per base and are unpacked on the device; the device-resident leg is
+        the bits kernel on the unpacked resident bytes).  Returns a dict + the host outputs."""
         steps = steps or args.steps
         bits = fmt in ("bits", "packed_bits")
         width = {"u8": 1, "u16": 2, "u32": 4}.get(fmt, 0)
@@ -545,7 +548,7 @@ def main():
     if rank == 0:
         sampler.start()
     main_m, np_len, np_ptr = measure(idx, main_fmt, mode)
-    main_bits = main_fmt == "bits"
+    main_bits = main_fmt in ("bits", "packed_bits")
     clocks = sampler.stop() if rank == 0 else None
 
     # ---------------- parity spot check + CPU baseline (rank 0, N=1)
@@ -590,7 +593,7 @@ def main():
         if world > 1:
             fmts = [f for f in ("u8", "bits", "packed_bits") if f != main_fmt and f in want]
         for f in fmts:
-            v, Lv, _ = measure(idx, f, "pml", device_leg=(f != "packed_bits"), steps=max(2, args.steps // 2))
+            v, Lv, _ = measure(idx, f, "pml", steps=max(2, args.steps // 2))
             Lx = sp.expand_bits(Lv, off) if f in ("bits", "packed_bits") else (sp.widen_lengths(Lv, off) if v.get("clamped") else Lv.astype(np.uint32))
             v["same"] = bool(v.get("same", True)) and bool(np.array_equal(Lx, L_main))
             if not v["same"]:
@@ -641,7 +644,8 @@ def main():
                                       ("; strong scaling: one fixed set of 5 x the workload's reads cut by bases" if args.strong else "")},
             "clocks": clocks,
             "e2e": {"value": main_m["e2e"], "unit": "bases/s", "h2d_bytes_per_step": main_m["h2d_bytes_per_step"], "d2h_bytes_per_step": main_m["d2h_bytes_per_step"],
-                    "api": (f"spb_{mode}_query_host, pinned host buffers, one byte per base in, " +
+                    "api": ((f"spb_pml_query_host_packed, pinned host buffers, reads as 2 bits per base + exception list (packed by the caller, untimed: spb_pack_reads), "
+                             if main_fmt == "packed_bits" else f"spb_{mode}_query_host, pinned host buffers, one byte per base in, ") +
                             ("one bit per base out (SPB_LENGTH_BITS: bit set iff the PML is non-zero, which determines every length; spb_pml_expand_bits)" if main_bits else
                              f"uint{8 * args.length_bytes} lengths out ({main_m['clamped']} clamped values per step" +
                              ("; clamped PML lengths are rebuilt exactly by spb_pml_widen_lengths)" if mode == "pml" else ")")))},
