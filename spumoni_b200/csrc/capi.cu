@@ -738,7 +738,7 @@ int spb_index_open_ex(const char* ref_file, int mode, uint32_t flags, spb_index*
         const double t1 = now();
         if (flags & SPB_OPEN_DOC) spb::load_doc_array(ref + ".doc", d);
         std::string text;
-        if (ms) text = spb::load_reference_text(ref);
+        if (ms) text = spb::load_reference_text(ref, d.n - 1);
         const double t2 = now();
         spb::balance_runs(d, spb::default_balance_params());
         std::unique_ptr<spb_index> idx(new spb_index());

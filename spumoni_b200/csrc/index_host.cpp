@@ -530,8 +530,13 @@ DecodedIndex parse_index_file(const std::string& path, bool ms) {
 
 // The indexed text: every line of <prefix>.fa that is not a '>' header, trailing white space stripped, concatenated.
 // The file is cut into slices at line starts; each slice is measured, then copied to its final place.
-std::string load_reference_text(const std::string& fasta_path) {
+std::string load_reference_text(const std::string& fasta_path, uint64_t expected_length) {
     const RawVec<uint8_t> buf = slurp(fasta_path);
+    // `spumoni build -g` indexes the bytes of a general-text file as they are (/root/reference/src/spumoni.cpp:589-591: the file
+    // itself is the parse input) and `run -M -g` reads them back through the SLP; a FASTA reference is indexed without its header
+    // lines and line ends (refbuilder.cpp:349-379).  The BWT length tells the two apart.
+    auto fasta_like = [&]() { for (size_t i = 0; i < buf.size(); i++) if (buf[i] == '>' && (i == 0 || buf[i - 1] == '\n')) return true; return false; };
+    if (expected_length && buf.size() == expected_length && !fasta_like()) return std::string((const char*)buf.data(), buf.size());
     const uint8_t* b = buf.data();
     const size_t N = buf.size();
     size_t lo[kSlices + 1];
@@ -563,6 +568,8 @@ std::string load_reference_text(const std::string& fasta_path) {
         at[c + 1] = kept;
     }
     for (int c = 0; c < kSlices; c++) at[c + 1] += at[c];
+    if (expected_length && at[kSlices] != expected_length && buf.size() == expected_length)  // general text that happens to hold '>' lines
+        return std::string((const char*)buf.data(), buf.size());
     std::string text(at[kSlices], '\0');
 #pragma omp parallel for schedule(dynamic, 1)
     for (int c = 0; c < kSlices; c++) {

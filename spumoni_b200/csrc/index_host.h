@@ -75,7 +75,9 @@ struct BalanceParams {
 };
 BalanceParams default_balance_params();
 void balance_runs(DecodedIndex& d, const BalanceParams& bp);
-std::string load_reference_text(const std::string& fasta_path);
+// The indexed text for MS mode: the sequence lines of <prefix>.fa, or -- for an index built with `spumoni build -g` -- the file
+// verbatim; expected_length (n - 1, 0 = unknown) decides.
+std::string load_reference_text(const std::string& fasta_path, uint64_t expected_length = 0);
 NullDb load_null_db(const std::string& path);
 // EmpNullDatabase constructor tail (/root/reference/src/emp_null_database.cpp:42-79) and serialize (:82-102)
 NullDb summarize_null_stats(const uint32_t* stats, uint64_t n);

@@ -992,6 +992,7 @@ static int run_main(int argc, char** argv) {
     const bool ms = o.ms_requested && !o.pml_requested;
     validate(o, ms);
     o.ref_file += o.use_promotions ? ".bin" : ".fa";
+    if (o.is_general_text) o.use_doc = false;  // classify_general_reads_* never look at the document array (compute_ms_pml.cpp:1219-1297)
     const char* tag = ms ? "compute_ms" : "compute_pml";
 
     // GPUs: SPUMONI_B200_DEVICES="0,2,3" (or the older SPUMONI_B200_DEVICE=<one ordinal>), else as many of the visible GPUs as

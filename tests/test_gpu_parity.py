@@ -759,3 +759,50 @@ def test_cli_two_gpus_byte_identical(small_index, many_reads):
     # -t as the number of workers: two threads -> two GPUs
     auto, err = _cli_run({"SPUMONI_B200_TIMING": "1"}, prefix, many_reads, ["-P", "-c", "-t", "2"])
     assert auto == one and "devices: 2" in err
+
+
+def test_general_text_ms_index_against_reference_binary(tmp_path):
+    """`spumoni build -g` indexes the bytes of a general-text file as they are; `run -M -g` on such an index must read the text
+    verbatim (line ends included), not as FASTA.  The index is made from the raw bytes (tests/build_emulator.py -> the
+    reference's constructors via mkindex from-parts) and the product CLI is compared with the reference's own code."""
+    ref_bin = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "spumoni_ref")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref/spumoni_ref is not built")
+    from build_emulator import build_parts
+    rng = random.Random(8)
+    raw = "".join("".join(rng.choice("ACGT") for _ in range(rng.randint(20, 70))) + "\n" for _ in range(40)).encode()
+    d = str(tmp_path)
+    ref = os.path.join(d, "g.fa")
+    open(ref, "wb").write(raw)
+    open(ref + ".slp", "wb").write(raw)  # the reference binary's stand-in SLP reads the plain text
+    P = build_parts(np.frombuffer(raw + b"\0", dtype=np.uint8))
+
+    def put5(path, cols):
+        with open(path, "wb") as f:
+            for row in zip(*cols):
+                for v in row:
+                    f.write(int(v).to_bytes(5, "little"))
+    starts = np.concatenate([[0], np.cumsum(P["lens"])])
+    open(ref + ".bwt.heads", "wb").write(bytes(P["heads"].astype(np.uint8)))
+    put5(ref + ".bwt.len", [P["lens"]])
+    put5(ref + ".thr_pos", [P["thr"]])
+    put5(ref + ".ssa", [starts[:-1], P["ssa"]])
+    put5(ref + ".esa", [starts[1:] - 1, P["esa"]])
+    subprocess.check_call([MKINDEX, "from-parts", "--prefix", os.path.join(d, "g"), "--pml", "--ms"], stdout=subprocess.DEVNULL)
+    for ext, tool in ((".pmlnulldb", None), (".msnulldb", None)):
+        ((np.arange(1, 200, dtype=np.uint64) * 7) % 11).tofile(os.path.join(d, "stats.bin"))
+        subprocess.check_call([MKINDEX, "nulldb", "--stats", os.path.join(d, "stats.bin"), "--out", ref + ext])
+    q = os.path.join(d, "q.txt")
+    lines = raw.split(b"\n")
+    open(q, "wb").write(lines[3] + b"\n" + lines[4][:10] + b"\x01" + b"ACGTTTGA\x01" + lines[10][5:] + b"\n" + lines[11] + b"\x01")
+    outs = {}
+    for name, exe in (("ref", ref_bin), ("cli", sp.CLI_PATH)):
+        for mode, exts in (("-M", (".lengths", ".pointers")), ("-P", (".pseudo_lengths",))):
+            r = subprocess.run([exe, "run", "-r", os.path.join(d, "g"), "-p", q, mode, "-n", "-g"], capture_output=True, text=True)
+            assert r.returncode == 0, (name, mode, r.stderr)
+            for e in exts:
+                outs[(name, e)] = open(q + e, "rb").read()
+                os.remove(q + e)
+    for e in (".lengths", ".pointers", ".pseudo_lengths"):
+        assert outs[("cli", e)] == outs[("ref", e)], e
+    assert max(int(x) for x in outs[("cli", ".lengths")].split(b"\n")[1].split()) > len(lines[3])  # the match runs across the line end
