@@ -490,7 +490,7 @@ def main():
         h_ptr = torch.empty(n_bases, dtype=torch.int64 if pw == 8 else torch.int32).pin_memory() if m == "ms" else None
         np_ptr = h_ptr.numpy().view(np.uint64 if pw == 8 else np.uint32) if m == "ms" else None
         d_stats = torch.zeros(n_reads * 2, dtype=torch.int64, device=dev) if stats else None
-        h_stats = np.zeros(n_reads, dtype=sp.BinStats) if stats else None
+        h_stats = torch.zeros(n_reads * 2, dtype=torch.int64).pin_memory().numpy().view(sp.BinStats) if stats else None  # pinned like every other buffer
         kw = dict(bin_width=150, max_value_thr=9) if stats else {}
         packed = None
         if fmt == "packed_bits":

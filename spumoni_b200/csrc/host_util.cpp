@@ -37,6 +37,8 @@ std::vector<uint64_t> shard_by_bases(const uint64_t* offsets, uint64_t n_reads, 
     return cuts;
 }
 
+constexpr uint64_t kLanesPerSubBatch = 32768;
+
 std::vector<Chunk> plan_chunks(const uint64_t* offsets, uint64_t r_begin, uint64_t r_end, uint64_t want_reads,
                                uint64_t min_bases, uint64_t max_bases) {
     std::vector<Chunk> out;
@@ -54,7 +56,10 @@ std::vector<Chunk> plan_chunks(const uint64_t* offsets, uint64_t r_begin, uint64
             c.min_len = std::min(c.min_len, len); c.max_len = std::max(c.max_len, len);
             r1++;
             if (r1 == r_end) break;
-            if (r1 - r0 >= want_reads && offsets[r1] - c.b0 >= min_bases) break;
+            // enough reads, enough bases -- and enough bases for the longest read seen so far: a read of m bases holds its lane
+            // for m steps however empty the rest of the machine is, so a sub-batch must carry about that much work for each of
+            // the lanes it can count on (a share of the ~170 000 resident ones), or its kernel is all tail
+            if (r1 - r0 >= want_reads && offsets[r1] - c.b0 >= std::max<uint64_t>(min_bases, c.max_len * kLanesPerSubBatch)) break;
         }
         c.r1 = r1; c.nb = offsets[r1] - c.b0;
         out.push_back(c);

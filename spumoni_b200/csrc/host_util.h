@@ -16,8 +16,9 @@ struct Chunk {
 };
 // Cuts reads [r_begin, r_end) into sub-batches.  One read is one GPU thread, so what fills the machine is the number of
 // READS in flight, not the number of bases: a sub-batch is closed once it holds `want_reads` reads and at least
-// `min_bases` bases, or when the next read would take it past `max_bases` (device-buffer bound; a single longer read
-// still gets a sub-batch of its own).  Throws std::invalid_argument on decreasing offsets or a read of 2^32 bases or more.
+// max(`min_bases`, 32 768 x its longest read) bases -- a read of m bases occupies one lane for m steps, so a sub-batch with
+// long reads needs that much work per lane or its kernel is all tail -- or when the next read would take it past
+// `max_bases` (device-buffer bound; a single longer read still gets a sub-batch of its own).  Throws std::invalid_argument on decreasing offsets or a read of 2^32 bases or more.
 std::vector<Chunk> plan_chunks(const uint64_t* offsets, uint64_t r_begin, uint64_t r_end, uint64_t want_reads,
                                uint64_t min_bases, uint64_t max_bases);
 

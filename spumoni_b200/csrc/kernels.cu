@@ -332,7 +332,11 @@ __global__ void __launch_bounds__(SPB_CTA_THREADS) spb_walk_kernel(const WalkPar
 #define SPB_MV_MINB 9  /* 128-thread CTAs per SM: 56 registers, no spills (at 10 the 48-register cap spills inside the loop) */
 #endif
 #ifndef SPB_MV_MINB_BITS
-#define SPB_MV_MINB_BITS SPB_MV_MINB  /* PML with bit output: 4 KB of output staging instead of 8 */
+#define SPB_MV_MINB_BITS 10  /* PML with bit output: 4 KB of output staging + 4 KB of read staging, 48 registers without spills: 78.6 against
+                                76.0 Gbases/s on config 2 (profiles/r2c_experiments.json, c2_stage32_10) */
+#endif
+#ifndef SPB_STAGE_BITS_RD
+#define SPB_STAGE_BITS_RD 32
 #endif
 
 template <int LD>
@@ -465,14 +469,16 @@ __device__ __forceinline__ void ld_stream32(const void* p, uint4& a, uint4& b) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
-// (re)fill the lane's staged block of the read buffer: the SPB_STAGE-aligned block containing byte gi
+// (re)fill the lane's staged block of the read buffer: the RS-aligned block containing byte gi (RS = 64, or 32 in the
+// bit-output kernels: with their 4 KB of output staging that takes the CTA to 8.4 KB of shared memory and 10 CTAs per SM)
+template <int RS>
 __device__ __forceinline__ void stage_reads(uint4* s_rd, const uint8_t* reads, uint64_t gi) {
-    const uint8_t* src = reads + (gi & ~(uint64_t)(SPB_STAGE - 1));
-    uint4 v[SPB_STAGE_CH];
+    const uint8_t* src = reads + (gi & ~(uint64_t)(RS - 1));
+    uint4 v[RS / 16];
 #pragma unroll
-    for (int j = 0; j < SPB_STAGE_CH; j += 2) ld_stream32(src + 16 * j, v[j], v[j + 1]);
+    for (int j = 0; j < RS / 16; j += 2) ld_stream32(src + 16 * j, v[j], v[j + 1]);
 #pragma unroll
-    for (int j = 0; j < SPB_STAGE_CH; j++) s_rd[j * SPB_MV_THREADS + threadIdx.x] = v[j];
+    for (int j = 0; j < RS / 16; j++) s_rd[j * SPB_MV_THREADS + threadIdx.x] = v[j];
 }
 __device__ __forceinline__ uint32_t staged_offset(uint32_t byte_in_block) {  // byte offset inside a lane's staging area
     return (byte_in_block >> 4) * SPB_STAGE_PLANE + threadIdx.x * 16 + (byte_in_block & 15u);
@@ -657,7 +663,8 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
-    __shared__ uint4 s_rd[SPB_STAGE_CH * SPB_MV_THREADS];   // staged read bytes, see stage_reads
+    constexpr int RS = BITS ? SPB_STAGE_BITS_RD : SPB_STAGE;  // read bytes staged per lane
+    __shared__ uint4 s_rd[(RS / 16) * SPB_MV_THREADS];      // staged read bytes, see stage_reads
     __shared__ uint4 s_out[BITS ? 1 : SPB_STAGE_CH * SPB_MV_THREADS];  // staged output values (lengths, or MS pointers)
     __shared__ uint32_t s_bits[BITS ? SPB_BITS_WORDS * SPB_MV_THREADS : 1];  // staged match bits (OW == 0)
     __shared__ uint4 s_doc[DOC ? SPB_STAGE_CH * SPB_MV_THREADS : 1];  // staged document numbers
@@ -703,7 +710,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             if (BITS) bit_acc = 0;
             if (MS) sample = p.last_run_sample;
             if (DOC) doc = p.doc_init;
-            stage_reads(s_rd, p.reads, gi);
+            stage_reads<RS>(s_rd, p.reads, gi);
             have = true;
             if (do_stats) {
                 const uint64_t bw = p.bin_width;
@@ -714,7 +721,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         }
 
         // ---- the row of the current position: walk forward while off >= len (the LF image of a run may span several runs)
-        uint32_t c = rd_bytes[staged_offset((uint32_t)gi & (SPB_STAGE - 1))];
+        uint32_t c = rd_bytes[staged_offset((uint32_t)gi & (RS - 1))];
         if (upper && c >= 'a' && c <= 'z') c -= 32;
         RowView row = load_row<LD, RW, MSI>(p, k);
         bool slow = false;
@@ -838,7 +845,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
                 have = false;
             } else {
                 --gi;
-                if (((uint32_t)gi & (SPB_STAGE - 1)) == SPB_STAGE - 1) stage_reads(s_rd, p.reads, gi);
+                if (((uint32_t)gi & (RS - 1)) == RS - 1) stage_reads<RS>(s_rd, p.reads, gi);
             }
         }
     }

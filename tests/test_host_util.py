@@ -87,6 +87,14 @@ def test_plan_chunks_sizes_by_reads_not_bases():
     off = np.arange(0, 1_000_001, dtype=np.uint64) * 150
     d = np.diff(sp.plan_chunks(off, 43000, 8 << 20, 256 << 20).astype(np.int64))
     assert d[0] == -(-(8 << 20) // 150)
+    # a few long reads among short ones: the sub-batch grows to 32 768 x the longest read, so that the long chains overlap
+    # with the rest instead of being the whole kernel
+    lens = np.full(1_000_000, 150, dtype=np.int64)
+    lens[::1000] = 5000
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    c = sp.plan_chunks(off, 43000, 8 << 20, 256 << 20)
+    b = np.diff(off[c.astype(np.int64)].astype(np.int64))
+    assert np.all(b[:-1] >= 5000 * 32768) and np.all(b <= (256 << 20))
     # one read longer than max_bases gets a sub-batch of its own; zero-length reads are legal
     off = np.array([0, 10, 10, 5000, 5003], dtype=np.uint64)
     assert sp.plan_chunks(off, 2, 1, 100).tolist() == [0, 2, 3, 4]

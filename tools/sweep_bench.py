@@ -79,7 +79,7 @@ for key, (buf, off) in sets.items():
     torch.cuda.synchronize()
     dev_rate = nb * 3 / (e0.elapsed_time(e1) / 1e3)
     L16 = torch.empty(nb, dtype=torch.int16).pin_memory().numpy().view(np.uint16)
-    S = np.zeros(nr, dtype=sp.BinStats)
+    S = torch.zeros(nr * 2, dtype=torch.int64).pin_memory().numpy().view(sp.BinStats)  # pinned: a pageable output makes every D2H synchronous
     np_reads, np_off = h_reads.numpy(), h_off.numpy().view(np.uint64)
     for _ in range(2):
         idx.query_host(np_reads, np_off, bin_width=150, max_value_thr=9, out_lengths=L16, out_stats=S, length_bytes=2)
