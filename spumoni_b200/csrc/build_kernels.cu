@@ -362,11 +362,12 @@ bool build_rlbwt_device(const uint8_t* text, uint64_t n64, int device, BuildPart
     SPB_BUILD_CUDA(cudaMemcpy(ssa.data(), d_ssa.p, (size_t)runs * 4, cudaMemcpyDeviceToHost));
     SPB_BUILD_CUDA(cudaMemcpy(esa.data(), d_esa.p, (size_t)runs * 4, cudaMemcpyDeviceToHost));
     out.lens.resize(runs); out.thr.resize(runs); out.ssa.resize(runs); out.esa.resize(runs);
-    for (size_t k = 0; k < runs; k++) {
-        out.lens[k] = (uint64_t)starts[k + 1] - starts[k];
-        out.thr[k] = thr[k];
-        out.ssa[k] = ssa[k];
-        out.esa[k] = esa[k];
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < (int64_t)runs; k++) {
+        out.lens[(size_t)k] = (uint64_t)starts[(size_t)k + 1] - starts[(size_t)k];
+        out.thr[(size_t)k] = thr[(size_t)k];
+        out.ssa[(size_t)k] = ssa[(size_t)k];
+        out.esa[(size_t)k] = esa[(size_t)k];
     }
     lap("copy back");
     cudaEventDestroy(ev0);
