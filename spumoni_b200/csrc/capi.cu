@@ -128,6 +128,7 @@ struct DeviceCtx {
     std::atomic<uint32_t> counter_next{0};
     Slot slots[kMaxSlots];
     PinBuf<uint8_t> h_edges;  // bit-map transport: first / last 32-byte block of every sub-batch (merged by the host)
+    uint64_t persist_size = 0, persist_window = 0;  // SPUMONI_B200_L2_PERSIST: persisting L2 carve-out / largest access-policy window
     ~DeviceCtx() {
         if (device < 0) return;
         cudaSetDevice(device);
@@ -175,6 +176,17 @@ int ensure_ctx(spb_index* idx, DeviceCtx& c) {
         SPB_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
         // Opt-in only (it is a process-wide device setting): SPUMONI_B200_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity.
         // Measured without effect on the gathers of this path (profiles/r1_gather_bench_exp1.txt), so the default leaves it alone.
+        if (const char* e = std::getenv("SPUMONI_B200_L2_PERSIST")) {  // experiment: pin the move rows in the L2 (fraction of the maximum carve-out, in %)
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
+            const int pct = std::atoi(e);
+            if (pct > 0 && max_persist > 0 && max_window > 0) {
+                const size_t want = (size_t)((double)max_persist * std::min(pct, 100) / 100.0);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) { c.persist_size = want; c.persist_window = (uint64_t)max_window; }
+                cudaGetLastError();
+            }
+        }
         if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) {
             const size_t gran = (size_t)std::atoi(e);
             if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);  // a hint: failure is not an error
@@ -289,6 +301,14 @@ int launch_query(spb_index* idx, DeviceCtx& c, bool ms, const uint8_t* d_reads, 
         p.mdoc = reinterpret_cast<const uint2*>(c.dev_blob + h.off_mdoc);
         p.doc_init = h.doc_init; p.doc_absent_ms = h.doc_absent_ms;
         for (int i = 0; i < 4; i++) p.mv_end_doc[i] = h.mv_end_doc[i];
+    }
+    if (c.persist_size && lanes == 1) {
+        const void* tb = p.rows8 ? (const void*)p.rows8 : (p.rows32 ? p.rows32 : (const void*)p.rows);
+        const uint64_t row_bytes = p.rows8 ? h.mrows8_stride : (p.rows32 ? 32u : 16u);
+        const uint64_t tbytes = std::min<uint64_t>((h.R + SPB_MV_ROW_PAD) * row_bytes, c.persist_window);
+        p.persist_base = tb;
+        p.persist_bytes = tbytes;
+        p.persist_ratio = (float)std::min(1.0, (double)c.persist_size / (double)tbytes);
     }
     p.work_counter = c.d_counters + 2 * (c.counter_next.fetch_add(1) % (kCounters / 2));
     SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, 2 * sizeof(unsigned long long), stream));

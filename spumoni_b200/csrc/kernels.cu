@@ -22,6 +22,7 @@
 // global atomic counter, so ragged read lengths balance themselves.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstring>
 #include "flat_index.h"
 #include "kernels.h"
 
@@ -480,6 +481,25 @@ __device__ __forceinline__ void stage_reads(uint4* s_rd, const uint8_t* reads, u
 #pragma unroll
     for (int j = 0; j < RS / 16; j++) s_rd[j * SPB_MV_THREADS + threadIdx.x] = v[j];
 }
+// Asynchronous variant (SPB_ASYNC_READS): the lane's NEXT 32-byte block is copied global -> shared by the copy engine
+// (cp.async / LDGSTS, evict-first in L2) while the lane walks the current one -- two 32-byte slots per lane, the same 64
+// bytes of shared memory as the synchronous staging -- so that crossing a block boundary does not put an HBM round trip on
+// the warp's critical path (any lane of the warp that refills stalls all 32).
+#ifndef SPB_ASYNC_READS
+#define SPB_ASYNC_READS 0
+#endif
+__device__ __forceinline__ void prefetch_block32(uint4* s_rd, uint32_t slot, const uint8_t* src) {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));  // not volatile: hoisted / rematerialised by the compiler
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_rd + (slot * 2 + j) * SPB_MV_THREADS + threadIdx.x);
+        asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src + 16 * j), "l"(pol) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void prefetch_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t staged_offset(uint32_t byte_in_block) {  // byte offset inside a lane's staging area
     return (byte_in_block >> 4) * SPB_STAGE_PLANE + threadIdx.x * 16 + (byte_in_block & 15u);
 }
@@ -663,8 +683,9 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
     __shared__ uint8_t s_fid[256];  // 0..3 fast id, 4 = present but not fast, 5 = absent
     __shared__ uint32_t s_end_k[4], s_end_off[4];
     __shared__ uint64_t s_end_sl[4];
-    constexpr int RS = BITS ? SPB_STAGE_BITS_RD : SPB_STAGE;  // read bytes staged per lane
-    __shared__ uint4 s_rd[(RS / 16) * SPB_MV_THREADS];      // staged read bytes, see stage_reads
+    constexpr bool ASYNC = SPB_ASYNC_READS != 0;
+    constexpr int RS = ASYNC ? 32 : (BITS ? SPB_STAGE_BITS_RD : SPB_STAGE);  // read bytes staged per lane (and per slot)
+    __shared__ uint4 s_rd[(ASYNC ? 4 : RS / 16) * SPB_MV_THREADS];  // staged read bytes, see stage_reads (ASYNC: two slots)
     __shared__ uint4 s_out[BITS ? 1 : SPB_STAGE_CH * SPB_MV_THREADS];  // staged output values (lengths, or MS pointers)
     __shared__ uint32_t s_bits[BITS ? SPB_BITS_WORDS * SPB_MV_THREADS : 1];  // staged match bits (OW == 0)
     __shared__ uint4 s_doc[DOC ? SPB_STAGE_CH * SPB_MV_THREADS : 1];  // staged document numbers
@@ -690,7 +711,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
     uint64_t base = 0, end = 0, gi = 0;
     uint32_t k = 0, off = 0, length = 0;
     uint64_t sample = 0;
-    uint32_t nsat = 0, doc = 0, bit_acc = 0;
+    uint32_t nsat = 0, doc = 0, bit_acc = 0, rslot = 0;
     BinState bs;
 
     for (;;) {
@@ -711,6 +732,11 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
             if (MS) sample = p.last_run_sample;
             if (DOC) doc = p.doc_init;
             stage_reads<RS>(s_rd, p.reads, gi);
+            if (ASYNC) {  // slot 0 holds the block of gi; the block below it (if the read reaches into it) is on its way into slot 1
+                rslot = 0;
+                const uint64_t blk = gi & ~(uint64_t)(RS - 1);
+                if (blk > base) prefetch_block32(s_rd, 1, p.reads + blk - RS);
+            }
             have = true;
             if (do_stats) {
                 const uint64_t bw = p.bin_width;
@@ -721,7 +747,7 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         }
 
         // ---- the row of the current position: walk forward while off >= len (the LF image of a run may span several runs)
-        uint32_t c = rd_bytes[staged_offset((uint32_t)gi & (RS - 1))];
+        uint32_t c = rd_bytes[staged_offset(((uint32_t)gi & (RS - 1)) + (ASYNC ? rslot * 32u : 0u))];
         if (upper && c >= 'a' && c <= 'z') c -= 32;
         RowView row = load_row<LD, RW, MSI>(p, k);
         bool slow = false;
@@ -845,7 +871,14 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
                 have = false;
             } else {
                 --gi;
-                if (((uint32_t)gi & (RS - 1)) == RS - 1) stage_reads<RS>(s_rd, p.reads, gi);
+                if (((uint32_t)gi & (RS - 1)) == RS - 1) {
+                    if (ASYNC) {  // the block of the new gi was prefetched into the other slot; start fetching the one below it
+                        prefetch_wait();
+                        rslot ^= 1u;
+                        const uint64_t blk = gi & ~(uint64_t)(RS - 1);
+                        if (blk > base) prefetch_block32(s_rd, rslot ^ 1u, p.reads + blk - RS);
+                    } else stage_reads<RS>(s_rd, p.reads, gi);
+                }
             }
         }
     }
@@ -957,6 +990,26 @@ static cudaError_t launch_persistent(K kernel, const WalkParams& p, int num_sms,
     unsigned long long need = (p.n_reads + SPB_MV_THREADS - 1) / SPB_MV_THREADS;
     unsigned long long grid = (unsigned long long)num_sms * occ;
     if (need < grid) grid = need ? need : 1;
+    if (p.persist_bytes) {
+        // the move rows get the persisting part of the L2 for this launch (the read / output streams are evict-first already);
+        // an opt-in experiment: SPUMONI_B200_L2_PERSIST, capi.cu
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(SPB_MV_THREADS);
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        std::memset(attr, 0, sizeof(attr));
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(p.persist_base);
+        attr[0].val.accessPolicyWindow.num_bytes = (size_t)p.persist_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = p.persist_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kernel, p);
+    }
     kernel<<<(unsigned)grid, SPB_MV_THREADS, 0, stream>>>(p);
     return cudaGetLastError();
 }

@@ -44,6 +44,10 @@ struct WalkParams {
                                // 0 (PML, thread-per-read kernels): one bit per base, `lengths` is a zero-initialised bit map
     uint64_t bit_shift;        // out_width 0: base i of the batch is bit i + bit_shift of the map
     const uint32_t* order;     // nullable: the i-th read pulled from the work counter is read order[i] (thread-per-read kernels)
+    // host-only launch hint (not read by the kernels): L2 access-policy window over the move rows; persist_bytes == 0 = none
+    const void* persist_base;
+    uint64_t persist_bytes;
+    float persist_ratio;
     uint32_t row_ld;           // 0 = rows bypass L1, 1 = rows allocate in L1 (default)
     unsigned long long* saturated;  // nullable; += number of clamped length values
     // document numbers (-d), thread-per-read kernels only; docs == nullptr when not requested
