@@ -22,6 +22,10 @@
  *     (spumoni.cpp:744-747); the index is "<ref_file>.thrbv.spumoni" / "<ref_file>.thrbv.ms"
  *     (compute_ms_pml.cpp:215-217, :544-546), exactly as written by `spumoni build`;
  *   - the CUDA path is the only path: without a usable GPU the query calls fail loudly;
+ *   - device-wide settings this library touches: cudaLimitPersistingL2CacheSize is raised to its maximum on every GPU an index
+ *     becomes resident on (PML walks over row tables that nearly fit the L2 pin them there: +4-6 %); persisting lines are
+ *     reset when the index is closed, SPUMONI_B200_L2_PERSIST=0 leaves the limit alone.  cudaLimitMaxL2FetchGranularity is
+ *     only touched when SPUMONI_B200_L2_FETCH is set;
  *   - an spb_index serialises nothing: use one host thread per handle (the reference shares one index between its
  *     OpenMP threads because every call handles one read; here one call handles a whole batch, keeps several
  *     sub-batches in flight on its own streams and, for an index replicated on several GPUs, drives one host thread

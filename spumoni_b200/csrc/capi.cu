@@ -137,6 +137,7 @@ struct DeviceCtx {
             s.release();
         }
         h_edges.release();
+        if (persist_size) cudaCtxResetPersistingL2Cache();  // give the L2 back
         if (d_counters) cudaFree(d_counters);
         if (own_dev && dev_blob) cudaFree((void*)dev_blob);
     }
@@ -176,15 +177,23 @@ int ensure_ctx(spb_index* idx, DeviceCtx& c) {
         SPB_CUDA(cudaDeviceGetAttribute(&c.num_sms, cudaDevAttrMultiProcessorCount, c.device));
         // Opt-in only (it is a process-wide device setting): SPUMONI_B200_L2_FETCH=32|64|128 sets cudaLimitMaxL2FetchGranularity.
         // Measured without effect on the gathers of this path (profiles/r1_gather_bench_exp1.txt), so the default leaves it alone.
-        if (const char* e = std::getenv("SPUMONI_B200_L2_PERSIST")) {  // experiment: pin the move rows in the L2 (fraction of the maximum carve-out, in %)
+        // PML over a row table that (nearly) fits the L2: the rows get the persisting part of the L2 through an access-policy
+        // window on the walk launches (the read / output streams are evict-first already): +4-6 % on config 2
+        // (profiles/r2i_experiments.json: 84.9 against 81.3 Gbases/s; a 60 % carve-out and MS, whose 16-byte slots are twice the
+        // L2's effective size, lose).  cudaLimitPersistingL2CacheSize is a device-wide setting of this process: it is set to
+        // the maximum here and persisting lines are reset when the index is closed; SPUMONI_B200_L2_PERSIST=0 leaves it alone
+        // (=<percent of the maximum> for experiments).
+        {
+            int pct = 100;
+            if (const char* e = std::getenv("SPUMONI_B200_L2_PERSIST")) pct = std::atoi(e);
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
-            const int pct = std::atoi(e);
             if (pct > 0 && max_persist > 0 && max_window > 0) {
                 const size_t want = (size_t)((double)max_persist * std::min(pct, 100) / 100.0);
                 if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) { c.persist_size = want; c.persist_window = (uint64_t)max_window; }
                 cudaGetLastError();
+                if (std::getenv("SPUMONI_B200_TIMING")) std::fprintf(stderr, "[timing] L2 persisting carve-out %.1f MB (max %.1f), access-policy window max %.1f MB\n", want / 1e6, max_persist / 1e6, max_window / 1e6);
             }
         }
         if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) {
@@ -302,13 +311,15 @@ int launch_query(spb_index* idx, DeviceCtx& c, bool ms, const uint8_t* d_reads, 
         p.doc_init = h.doc_init; p.doc_absent_ms = h.doc_absent_ms;
         for (int i = 0; i < 4; i++) p.mv_end_doc[i] = h.mv_end_doc[i];
     }
-    if (c.persist_size && lanes == 1) {
+    if (c.persist_size && lanes == 1 && !ms) {
         const void* tb = p.rows8 ? (const void*)p.rows8 : (p.rows32 ? p.rows32 : (const void*)p.rows);
         const uint64_t row_bytes = p.rows8 ? h.mrows8_stride : (p.rows32 ? 32u : 16u);
-        const uint64_t tbytes = std::min<uint64_t>((h.R + SPB_MV_ROW_PAD) * row_bytes, c.persist_window);
-        p.persist_base = tb;
-        p.persist_bytes = tbytes;
-        p.persist_ratio = (float)std::min(1.0, (double)c.persist_size / (double)tbytes);
+        const uint64_t tbytes = (h.R + SPB_MV_ROW_PAD) * row_bytes;
+        if (tbytes <= 2 * c.persist_size && tbytes <= c.persist_window) {  // larger tables live in DRAM anyway
+            p.persist_base = tb;
+            p.persist_bytes = tbytes;
+            p.persist_ratio = (float)std::min(1.0, (double)c.persist_size / (double)tbytes);
+        }
     }
     p.work_counter = c.d_counters + 2 * (c.counter_next.fetch_add(1) % (kCounters / 2));
     SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, 2 * sizeof(unsigned long long), stream));
