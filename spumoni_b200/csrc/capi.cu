@@ -298,6 +298,7 @@ int launch_query(spb_index* idx, DeviceCtx& c, bool ms, const uint8_t* d_reads, 
     p.rows32 = (has_fast && h.off_mrows32) ? c.dev_blob + h.off_mrows32 : nullptr;
     p.msamp = (has_fast && ms && h.off_msamp) ? reinterpret_cast<const uint4*>(c.dev_blob + h.off_msamp) : nullptr;
     p.rows8_stride = h.mrows8_stride;
+    p.msamp_stride = h.msamp_stride;
     for (int i = 0; i < 4; i++) { p.mv_end_k[i] = h.mv_end_k[i]; p.mv_end_off[i] = h.mv_end_off[i]; p.mv_end_sl[i] = h.mv_end_sl[i]; }
     p.out_width = (uint32_t)width;
     p.bit_shift = ex.bit_shift;
@@ -311,7 +312,7 @@ int launch_query(spb_index* idx, DeviceCtx& c, bool ms, const uint8_t* d_reads, 
         p.doc_init = h.doc_init; p.doc_absent_ms = h.doc_absent_ms;
         for (int i = 0; i < 4; i++) p.mv_end_doc[i] = h.mv_end_doc[i];
     }
-    if (c.persist_size && lanes == 1 && !ms) {
+    if (c.persist_size && lanes == 1 && (!ms || (p.rows8 && h.mrows8_stride == 8 && std::getenv("SPUMONI_B200_MS_PERSIST")))) {
         const void* tb = p.rows8 ? (const void*)p.rows8 : (p.rows32 ? p.rows32 : (const void*)p.rows);
         const uint64_t row_bytes = p.rows8 ? h.mrows8_stride : (p.rows32 ? 32u : 16u);
         const uint64_t tbytes = (h.R + SPB_MV_ROW_PAD) * row_bytes;

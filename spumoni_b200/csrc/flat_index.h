@@ -15,7 +15,7 @@
 #include <stdint.h>
 
 #define SPB_FLAT_MAGIC 0x3030324250535F42ULL /* "B_SPB200" */
-#define SPB_FLAT_VERSION 8u
+#define SPB_FLAT_VERSION 9u
 #define SPB_RUN_PAD 64u  /* sentinel + padding run records past R (start = 2^40-1) */
 #define SPB_POS_MAX 0xFFFFFFFFFFULL
 
@@ -180,7 +180,9 @@ struct SpbFlatHeader {
                                  // off_mrows or off_mrows8 is set).  PML images without a document array only.
     uint64_t R_file;             // runs of the BWT as stored on disk (what the reference logs); R counts rows: >= R_file when
                                  // long runs were cut into several rows (index_host.cpp, balance_runs)
-    uint64_t pad3;               // keeps chartab 16-byte aligned (the kernels load its entries as uint4)
+    uint32_t msamp_stride;       // bytes per entry of the per-row sample table at off_msamp: 16 (SpbCharSamp, u64 pairs) or 8
+                                 // ({u32 ss, u32 sl}: n < 2^32, compact rows kept at 8 bytes so that the walk's own table stays in the L2)
+    uint32_t pad3;               // keeps chartab 16-byte aligned (the kernels load its entries as uint4)
     uint64_t F[256];
     SpbCharTab chartab[256];
 };

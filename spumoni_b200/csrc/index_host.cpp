@@ -960,8 +960,15 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
     }
     if (num_fast) {
         // MS over compact rows: with 32-bit text positions the two samples of a row ride in the same 16 bytes
+        // (SPUMONI_B200_MSAMP = inline (default) | split32: 8-byte rows + a separate table of {u32 ss, u32 sl} read on jumps only |
+        //  wide: 8-byte rows + the 16-byte SpbCharSamp table, what indexes with n >= 2^32 get)
         bool ms_inline = ms && rows8 && n < (1ull << 32);
-        if (const char* e = std::getenv("SPUMONI_B200_MSAMP")) if (std::string(e) == "wide") ms_inline = false;
+        bool ms_split32 = false;
+        if (const char* e = std::getenv("SPUMONI_B200_MSAMP")) {
+            if (std::string(e) == "wide") ms_inline = false;
+            if (std::string(e) == "split32" && ms_inline) { ms_inline = false; ms_split32 = true; }
+        }
+        h.msamp_stride = ms ? (ms_split32 ? 8u : 16u) : 0u;
         h.mrows8_stride = rows8 ? (ms_inline ? 16u : 8u) : 0u;
         if (rows8) {
             h.off_mrows8 = off;
@@ -975,7 +982,7 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
         }
         if (ms && !ms_inline) {
             h.off_msamp = off;
-            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * sizeof(SpbCharSamp), 256);
+            off = align_up(off + ((size_t)R + SPB_MV8_ROW_PAD) * h.msamp_stride, 256);
         }
     }
     if (use_doc) {
@@ -1129,7 +1136,8 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
             end_off[s] = p - start[(size_t)kp];
         }
         uint64_t* rows_c = rows8 ? reinterpret_cast<uint64_t*>(blob.data() + h.off_mrows8) : nullptr;
-        SpbCharSamp* msamp = (ms && h.off_msamp) ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
+        SpbCharSamp* msamp = (ms && h.off_msamp && h.msamp_stride == 16) ? reinterpret_cast<SpbCharSamp*>(blob.data() + h.off_msamp) : nullptr;
+        uint64_t* msamp32 = (ms && h.off_msamp && h.msamp_stride == 8) ? reinterpret_cast<uint64_t*>(blob.data() + h.off_msamp) : nullptr;
         SpbFlatHeader* hd = reinterpret_cast<SpbFlatHeader*>(blob.data());
         // next run (strictly after k) headed by each fast symbol: the state at every slice boundary comes from the first fast
         // runs of the slices after it, then each slice walks backwards on its own
@@ -1276,7 +1284,9 @@ FlatBlob build_flat_image(const DecodedIndex& d, bool ms, const std::string& tex
                     if (msamp) {
                         msamp[k].ss = d.samples_start[(size_t)k];
                         msamp[k].sl = prev_sl[c];
-                    } else  // inline: the second 8 bytes of the 16-byte row slot (text positions < n < 2^32)
+                    } else if (msamp32)
+                        msamp32[k] = (uint64_t)(uint32_t)d.samples_start[(size_t)k] | ((uint64_t)(uint32_t)prev_sl[c] << 32);
+                    else  // inline: the second 8 bytes of the 16-byte row slot (text positions < n < 2^32)
                         rows_c[k * 2 + 1] = (uint64_t)(uint32_t)d.samples_start[(size_t)k] | ((uint64_t)(uint32_t)prev_sl[c] << 32);
                     prev_sl[c] = d.samples_last[(size_t)k];
                 }

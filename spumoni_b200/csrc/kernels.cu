@@ -818,8 +818,13 @@ __global__ void __launch_bounds__(SPB_MV_THREADS, ((STATS || DOC) && SPB_MV_MINB
         } else {
             if (MS && MSI) sample = down ? row.smp.y : row.smp.x;
             else if (MS) {
-                const uint4 sm = ldg_nc16(p.msamp + k2);
-                sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                if (p.msamp_stride == 8) {  // uniform branch: compact sample table, read on jumps only
+                    const uint2 sm = ld_row8<0>(reinterpret_cast<const uint64_t*>(p.msamp) + k2);
+                    sample = down ? sm.y : sm.x;
+                } else {
+                    const uint4 sm = ldg_nc16(p.msamp + k2);
+                    sample = down ? ((uint64_t)sm.z | ((uint64_t)sm.w << 32)) : ((uint64_t)sm.x | ((uint64_t)sm.y << 32));
+                }
             }
             if (DOC) { const uint2 md = __ldg(p.mdoc + k2); doc = down ? md.y : md.x; }
             // first position of the c-run's LF image, or (down) one position before it

@@ -37,7 +37,8 @@ struct WalkParams {
     const uint64_t* rows8;     // 8-byte compact rows, or
     const void* rows32;        // 32-byte full rows (PML without documents)   (exactly one of rows / rows8 / rows32 is set)
     uint32_t rows8_stride;     // 8, or 16 when every row carries its two 32-bit SA samples (MS; then msamp == nullptr)
-    const uint4* msamp;        // MS only
+    const uint4* msamp;        // MS only: per-row samples, 16-byte entries (u64 ss, u64 sl) ...
+    uint32_t msamp_stride;     // ... or 8-byte entries {u32 ss, u32 sl} when msamp_stride == 8
     uint32_t mv_end_k[4], mv_end_off[4];
     uint64_t mv_end_sl[4];
     uint32_t out_width;        // bytes per length value: 4, 2 or 1 (values above the maximum are clamped and counted), or

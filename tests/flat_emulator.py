@@ -11,7 +11,7 @@ import struct
 import numpy as np
 
 U64 = (1 << 64) - 1
-HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQQ3I4IIQQQ"  # up to pad3 (then F[256], chartab[256])
+HDR_FMT = "<QIIQQQQIIIIQQQQQQQQQQI4I4I4I3I4QQQQ3I4IIQQII"  # up to pad3 (then F[256], chartab[256])
 
 
 class FlatImage:
@@ -29,6 +29,7 @@ class FlatImage:
         self.mrows8_stride = rest[29]
         self.off_mrows32 = rest[30]
         self.R_file = rest[31]
+        self.msamp_stride = rest[32]
         o = struct.calcsize(HDR_FMT)
         self.F = struct.unpack_from("<256Q", b, o)
         o += 256 * 8
@@ -49,7 +50,10 @@ class FlatImage:
                 self.rows32 = np.frombuffer(b, dtype=np.uint32, count=8 * (self.R + 16), offset=self.off_mrows32).reshape(-1, 8)
             else:
                 self.rows = np.frombuffer(b, dtype=np.uint32, count=4 * (self.R + 16), offset=self.off_mrows).reshape(-1, 4)
-            if self.mode == 1 and self.off_msamp:
+            if self.mode == 1 and self.off_msamp and self.msamp_stride == 8:  # {u32 ss, u32 sl} per row, presented like msamp
+                raw = np.frombuffer(b, dtype=np.uint64, count=self.R + 16, offset=self.off_msamp)
+                self.msamp = np.stack([raw & 0xFFFFFFFF, raw >> 32], axis=1)
+            elif self.mode == 1 and self.off_msamp:
                 self.msamp = np.frombuffer(b, dtype=np.uint64, count=2 * (self.R + 16), offset=self.off_msamp).reshape(-1, 2)
         if self.num_docs:
             self.cdoc = np.frombuffer(b, dtype=np.uint32, count=2 * (self.num_crec + 1), offset=self.off_cdoc).reshape(-1, 2)

@@ -196,15 +196,18 @@ def test_ms_sample_layouts(small_index, monkeypatch):
     mo = oracle.OracleIndex(small_index["ref"], "ms")
     monkeypatch.setenv("SPUMONI_B200_ROWS", "8")
     imgs = {}
-    for layout in ("inline", "wide"):
+    for layout in ("inline", "wide", "split32"):
         monkeypatch.setenv("SPUMONI_B200_MSAMP", layout)
         imgs[layout] = FlatImage(sp.Index.open(small_index["ref"], sp.MODE_MS).flat())
     assert imgs["inline"].mrows8_stride == 16 and imgs["inline"].off_msamp == 0
-    assert imgs["wide"].mrows8_stride == 8 and imgs["wide"].off_msamp != 0
+    assert imgs["wide"].mrows8_stride == 8 and imgs["wide"].off_msamp != 0 and imgs["wide"].msamp_stride == 16
+    assert imgs["split32"].mrows8_stride == 8 and imgs["split32"].off_msamp != 0 and imgs["split32"].msamp_stride == 8
+    assert imgs["split32"].total_bytes < imgs["wide"].total_bytes
     for i in range(40):
         r = bytes(buf[int(off[i]):int(off[i + 1])])
         want = mo.matching_statistics(r)[1].tolist()
-        assert imgs["inline"].walk_rows(r)[1] == want and imgs["wide"].walk_rows(r)[1] == want
+        for layout in imgs:
+            assert imgs[layout].walk_rows(r)[1] == want, layout
 
 
 def test_nulldb_save_matches_fixture_writer(tmp_path):

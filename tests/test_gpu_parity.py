@@ -434,7 +434,7 @@ def test_ms_sample_layouts_on_gpu(small_index, monkeypatch):
     buf, off = load_bin_reads(small_index["reads_bin"])
     Lo, Po = oracle_batch(small_index["ref"], "ms", buf, off)
     monkeypatch.setenv("SPUMONI_B200_ROWS", "8")
-    for layout in ("inline", "wide"):
+    for layout in ("inline", "wide", "split32"):
         monkeypatch.setenv("SPUMONI_B200_MSAMP", layout)
         L, P, _ = sp.ms_t(small_index["ref"]).query_host(buf, off)
         assert np.array_equal(P, Po) and np.array_equal(L.astype(np.uint64), Lo), layout
