@@ -604,7 +604,7 @@ def main():
             keep("pml_stats", v)
     cli = None
     if world == 1 and mode == "pml" and "synth" not in w and "cli" in want:
-        del idx  # the CLI opens its own copy
+        idx = None  # the CLI opens its own copy
         torch.cuda.empty_cache()
         os.sched_setaffinity(0, all_cpus)
         cores = os.cpu_count() or 1
@@ -614,6 +614,9 @@ def main():
             cli["bases_per_s"] = n_bases / cli["phase_s"]
     if world == 1 and mode == "pml" and "synth" not in w and "ms" in want:
         try:
+            idx = None  # close the PML index first (it holds the device's persisting-L2 carve-out, which MS does not want)
+            import gc
+            gc.collect()
             idx_ms_ref = ensure_index(name, "ms")
             ms_idx = sp.Index.open(idx_ms_ref, sp.MODE_MS).to_device(local)
             n_ms = ms_idx.get_bwt_stats()[0]

@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -118,6 +119,12 @@ struct Slot {
     }
 };
 
+// The persisting-L2 carve-out is a device-wide limit of the process and it costs every kernel that does not use it (MS on
+// config 2: 28.6 instead of 31.9 Gbases/s with the carve-out set): it is held only while at least one index that profits from
+// it (PML, row table up to twice the carve-out) is resident on the device, and given back with the last one.
+std::mutex g_persist_mutex;
+int g_persist_users[64] = {0};
+
 // everything one GPU needs to serve queries on a resident copy of the flat image
 struct DeviceCtx {
     int device = -1;
@@ -137,7 +144,14 @@ struct DeviceCtx {
             s.release();
         }
         h_edges.release();
-        if (persist_size) cudaCtxResetPersistingL2Cache();  // give the L2 back
+        if (persist_size && device < 64) {  // give the L2 back with the last user
+            std::lock_guard<std::mutex> lk(g_persist_mutex);
+            if (--g_persist_users[device] == 0) {
+                cudaCtxResetPersistingL2Cache();
+                cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+                cudaGetLastError();
+            }
+        }
         if (d_counters) cudaFree(d_counters);
         if (own_dev && dev_blob) cudaFree((void*)dev_blob);
     }
@@ -181,19 +195,28 @@ int ensure_ctx(spb_index* idx, DeviceCtx& c) {
         // window on the walk launches (the read / output streams are evict-first already): +4-6 % on config 2
         // (profiles/r2i_experiments.json: 84.9 against 81.3 Gbases/s; a 60 % carve-out and MS, whose 16-byte slots are twice the
         // L2's effective size, lose).  cudaLimitPersistingL2CacheSize is a device-wide setting of this process: it is set to
-        // the maximum here and persisting lines are reset when the index is closed; SPUMONI_B200_L2_PERSIST=0 leaves it alone
-        // (=<percent of the maximum> for experiments).
+        // the maximum while an index that uses it is resident and back to zero when the last one closes;
+        // SPUMONI_B200_L2_PERSIST=0 leaves it alone (=<percent of the maximum> for experiments).
         {
             int pct = 100;
             if (const char* e = std::getenv("SPUMONI_B200_L2_PERSIST")) pct = std::atoi(e);
             int max_persist = 0, max_window = 0;
             cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c.device);
             cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c.device);
-            if (pct > 0 && max_persist > 0 && max_window > 0) {
-                const size_t want = (size_t)((double)max_persist * std::min(pct, 100) / 100.0);
-                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) { c.persist_size = want; c.persist_window = (uint64_t)max_window; }
+            const SpbFlatHeader& h = idx->hdr;
+            const uint64_t row_bytes = h.off_mrows8 ? h.mrows8_stride : (h.off_mrows32 ? 32u : 16u);
+            const uint64_t tbytes = (h.R + SPB_MV_ROW_PAD) * row_bytes;
+            const size_t want = (size_t)((double)max_persist * std::min(std::max(pct, 0), 100) / 100.0);
+            const bool eligible = idx->mode == SPB_MODE_PML && h.num_fast && pct > 0 && max_persist > 0 && tbytes <= 2 * (uint64_t)want && tbytes <= (uint64_t)max_window;
+            if (eligible && c.device < 64) {
+                std::lock_guard<std::mutex> lk(g_persist_mutex);
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                    g_persist_users[c.device]++;
+                    c.persist_size = want;
+                    c.persist_window = (uint64_t)max_window;
+                }
                 cudaGetLastError();
-                if (std::getenv("SPUMONI_B200_TIMING")) std::fprintf(stderr, "[timing] L2 persisting carve-out %.1f MB (max %.1f), access-policy window max %.1f MB\n", want / 1e6, max_persist / 1e6, max_window / 1e6);
+                if (std::getenv("SPUMONI_B200_TIMING")) std::fprintf(stderr, "[timing] L2 persisting carve-out %.1f MB (max %.1f) for a %.1f MB row table\n", want / 1e6, max_persist / 1e6, tbytes / 1e6);
             }
         }
         if (const char* e = std::getenv("SPUMONI_B200_L2_FETCH")) {
@@ -312,15 +335,13 @@ int launch_query(spb_index* idx, DeviceCtx& c, bool ms, const uint8_t* d_reads, 
         p.doc_init = h.doc_init; p.doc_absent_ms = h.doc_absent_ms;
         for (int i = 0; i < 4; i++) p.mv_end_doc[i] = h.mv_end_doc[i];
     }
-    if (c.persist_size && lanes == 1 && (!ms || (p.rows8 && h.mrows8_stride == 8 && std::getenv("SPUMONI_B200_MS_PERSIST")))) {
+    if (c.persist_size && lanes == 1 && !ms) {  // (eligibility -- PML, table up to twice the carve-out -- was decided in ensure_ctx)
         const void* tb = p.rows8 ? (const void*)p.rows8 : (p.rows32 ? p.rows32 : (const void*)p.rows);
         const uint64_t row_bytes = p.rows8 ? h.mrows8_stride : (p.rows32 ? 32u : 16u);
         const uint64_t tbytes = (h.R + SPB_MV_ROW_PAD) * row_bytes;
-        if (tbytes <= 2 * c.persist_size && tbytes <= c.persist_window) {  // larger tables live in DRAM anyway
-            p.persist_base = tb;
-            p.persist_bytes = tbytes;
-            p.persist_ratio = (float)std::min(1.0, (double)c.persist_size / (double)tbytes);
-        }
+        p.persist_base = tb;
+        p.persist_bytes = tbytes;
+        p.persist_ratio = (float)std::min(1.0, (double)c.persist_size / (double)tbytes);
     }
     p.work_counter = c.d_counters + 2 * (c.counter_next.fetch_add(1) % (kCounters / 2));
     SPB_CUDA(cudaMemsetAsync(p.work_counter, 0, 2 * sizeof(unsigned long long), stream));
