@@ -113,3 +113,91 @@ def test_longest_first_order():
     # uniform lengths: no order (the kernels pull reads in input order)
     assert sp.plan_order(np.arange(0, 1001, dtype=np.uint64) * 1000) is None
     assert sp.plan_order(np.array([0, 150, 310, 452], dtype=np.uint64)) is None
+
+
+# ---- property tests (hypothesis): the planning / transport helpers on arbitrary ragged inputs
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+_lens = st.lists(st.integers(min_value=0, max_value=3000), min_size=1, max_size=300)
+
+
+def _offsets(lens):
+    off = np.zeros(len(lens) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(np.asarray(lens, dtype=np.uint64))
+    return off
+
+
+@settings(max_examples=120, deadline=None)
+@given(_lens, st.integers(1, 9))
+def test_prop_shards_tile_the_reads(lens, n_shards):
+    off = _offsets(lens)
+    cuts = sp.shard_by_bases(off, n_shards).astype(np.int64)
+    assert cuts[0] == 0 and cuts[-1] == len(lens) and np.all(np.diff(cuts) >= 0)
+    total = int(off[-1])
+    for s in range(1, n_shards):  # a cut never lands before the read that holds the s-th fraction of the bases
+        assert int(off[cuts[s]]) >= total * s // n_shards or cuts[s] == len(lens)
+
+
+@settings(max_examples=120, deadline=None)
+@given(_lens, st.integers(1, 50), st.integers(1, 5000), st.integers(1, 20000))
+def test_prop_chunks_tile_the_reads_and_respect_the_bounds(lens, want_reads, min_bases, max_extra):
+    off = _offsets(lens)
+    max_bases = min_bases + max_extra
+    c = sp.plan_chunks(off, want_reads, min_bases, max_bases).astype(np.int64)
+    assert c[0] == 0 and c[-1] == len(lens) and np.all(np.diff(c) >= 1)
+    for a, b in zip(c[:-1], c[1:]):
+        bases = int(off[b] - off[a])
+        assert bases <= max_bases or b - a == 1          # only a single over-long read may exceed the device-buffer bound
+        if b != len(lens):                                # a sub-batch that was closed early had a reason to be
+            longest = int(np.max(np.diff(off[a:b + 1].astype(np.int64))))
+            enough = (b - a) >= want_reads and bases >= max(min_bases, longest * 32768)
+            nxt = int(off[b + 1] - off[a])
+            assert enough or nxt > max_bases
+
+
+@settings(max_examples=80, deadline=None)
+@given(st.binary(min_size=0, max_size=2000), st.booleans())
+def test_prop_pack_round_trip(data, up):
+    reads = np.frombuffer(data, dtype=np.uint8)
+    packed, pos, val = sp.pack_reads_2bit(reads, toupper=up)
+    i = np.arange(reads.size)
+    un = np.frombuffer(b"ACGT", dtype=np.uint8)[(packed[i // 4] >> (2 * (i % 4))) & 3].copy() if reads.size else np.zeros(0, np.uint8)
+    un[pos.astype(np.int64)] = val
+    want = reads.copy()
+    if up:
+        low = np.isin(want, np.frombuffer(b"acgt", dtype=np.uint8))
+        want[low] -= 32
+    assert np.array_equal(un, want)
+    assert np.all(np.diff(pos.astype(np.int64)) > 0)
+
+
+@settings(max_examples=80, deadline=None)
+@given(_lens, st.randoms(use_true_random=False))
+def test_prop_bits_and_clamped_lengths_are_lossless(lens, rnd):
+    off = _offsets(lens)
+    total = int(off[-1])
+    m = np.array([rnd.random() < 0.93 for _ in range(total)], dtype=bool)
+    L = np.zeros(total, dtype=np.uint32)
+    for r in range(len(lens)):
+        l = 0
+        for j in range(int(off[r + 1]) - 1, int(off[r]) - 1, -1):
+            l = l + 1 if m[j] else 0
+            L[j] = l
+    bits = np.zeros(max(sp.bits_bytes(total) // 8, 1), dtype=np.uint64)
+    idx = np.nonzero(m)[0]
+    np.bitwise_or.at(bits, idx // 64, np.uint64(1) << (idx % 64).astype(np.uint64))
+    assert np.array_equal(sp.expand_bits(bits, off, 4), L)
+    assert np.array_equal(sp.widen_lengths(np.minimum(L, 255).astype(np.uint8), off), L)
+
+
+@settings(max_examples=80, deadline=None)
+@given(_lens)
+def test_prop_longest_first_order_is_a_permutation(lens):
+    off = _offsets(lens)
+    order = sp.plan_order(off)
+    if order is None:
+        return
+    assert sorted(order.tolist()) == list(range(len(lens)))
+    ll = np.asarray(lens)[order]
+    cls = lambda v: 0 if v < 4 else 4 * (int(v).bit_length() - 1) + ((int(v) >> (int(v).bit_length() - 3)) & 3)  # noqa: E731
+    assert all(cls(ll[i]) >= cls(ll[i + 1]) for i in range(len(ll) - 1))
