@@ -657,15 +657,20 @@ def test_mixed_lengths_longest_first(small_index):
     assert np.array_equal(Pm, Pmo) and np.array_equal(Lm.astype(np.uint64), Lmo)
 
 
-def test_replicated_index_two_gpus(small_index):
-    """spb_index_replicate: the flat image is broadcast to a second GPU and host queries are sharded by bases over both;
-    results equal the single-GPU ones (lengths, statistics, bit map with its shared edge blocks)."""
+@pytest.mark.parametrize("method", ["nccl", "peer"])
+def test_replicated_index_two_gpus(small_index, method, monkeypatch):
+    """spb_index_replicate: the flat image is broadcast to a second GPU (ncclBroadcast, or the peer-to-peer copy tree used when
+    NCCL cannot be loaded) and host queries are sharded by bases over both; results equal the single-GPU ones (lengths,
+    statistics, bit map with its shared edge blocks)."""
     if sp.device_count() < 2:
         pytest.skip("needs two GPUs")
+    if method == "peer":
+        monkeypatch.setenv("SPUMONI_B200_NO_NCCL", "1")
     buf, off = load_bin_reads(small_index["reads_bin"])
     one = sp.pml_t(small_index["ref"])
     two = sp.Index.open(small_index["ref"], sp.MODE_PML).replicate([0, 1])
-    assert two.device_count() == 2 and sp.load_library().spb_replicate_method().decode() in ("ncclBroadcast", "cudaMemcpyPeer tree")
+    assert two.device_count() == 2
+    assert sp.load_library().spb_replicate_method().decode() == ("cudaMemcpyPeer tree" if method == "peer" else "ncclBroadcast")
     L1, _, S1 = one.query_host(buf, off, bin_width=150, max_value_thr=9)
     L2, _, S2 = two.query_host(buf, off, bin_width=150, max_value_thr=9)
     assert np.array_equal(L1, L2) and np.array_equal(S1, S2)
