@@ -86,7 +86,7 @@ typedef struct {
     uint32_t length_bytes;   /* element size of the `lengths` output: 0 or 4 = uint32_t, 2 = uint16_t, 1 = uint8_t.  A PML/MS
                                 length never exceeds the read length, so 2 is lossless for reads < 65536 bases.  Values that do
                                 not fit are clamped to the maximum and counted (lanes_per_read 1 only).  For PML a clamped
-                                array is still lossless -- lengths[j] = lengths[j] != 0 ? lengths[j + 1] + 1 : 0
+                                array is still lossless -- lengths[j] = (position j matched) ? lengths[j + 1] + 1 : 0
                                 (compute_ms_pml.cpp:249-281), and clamping keeps zero / non-zero -- so the call succeeds and
                                 spb_pml_widen_lengths rebuilds the exact values where `saturated` says some were clamped.
                                 SPB_LENGTH_BITS (PML, lanes_per_read 1): `lengths` is a bit map of spb_bits_bytes(total bases)
