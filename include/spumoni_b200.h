@@ -112,8 +112,9 @@ int spb_abi_version(void);
 /* pml_t::pml_t(filename, ...) compute_ms_pml.cpp:700-721 -> pml_pointers::load :222-229
  * ms_t::ms_t(filename, ...)   compute_ms_pml.cpp:755-786 -> ms_pointers::load  :551-562
  * Parses the reference's on-disk index (host only, no GPU needed) and flattens it into the
- * device layout.  MS mode takes the text from <ref_file> itself (the FASTA written by
- * `spumoni build`) instead of <ref_file>.slp -- see DESIGN.md. */
+ * device layout.  MS mode takes the text from <ref_file> itself instead of <ref_file>.slp: the sequence lines of
+ * the FASTA written by `spumoni build`, or the file verbatim for an index built with `build -g` (the BWT length
+ * decides) -- see DESIGN.md. */
 int spb_index_open(const char* ref_file, int mode, spb_index** out);
 /* Same with flags.  SPB_OPEN_DOC: pml_t / ms_t constructed with use_doc = true (compute_ms_pml.cpp:712-720, :777-785)
  * -> DocumentArray::load of <ref_file>.doc (doc_array.cpp:197-201); enables the *_doc queries below. */
