@@ -306,19 +306,19 @@ def run_reference(args, name):
     emit(out)
 
 
-def cli_seconds(ref, name, seed, threads, extra_env=None):
+def cli_seconds(ref, name, seed, threads, extra_env=None, fastq=False):
     """`spumoni run -P -n -c -t threads` of the product CLI on the workload's reads as a FASTA file: the seconds of the phase the
     reference times ("processing the patterns", compute_ms_pml.cpp:1324-1337; index loading is outside it) + the per-stage
     busy times the CLI prints with SPUMONI_B200_TIMING."""
     import spumoni_b200 as sp
     w = WORKLOADS[name]
     d = cache_dir(name)
-    fa = os.path.join(d, f"reads_s{seed}.fa")
+    fa = os.path.join(d, f"reads_s{seed}" + ("_fq.fa" if fastq else ".fa"))  # the reference insists on a FASTA extension
     if not os.path.exists(fa):
         if "synth" in w:
             return None
         subprocess.check_call([MKINDEX, "reads", "--ref", ref, "--n", str(w["n_reads"]), "--len", str(w["read_len"]), "--seed", str(seed),
-                               "--out", fa + ".tmp"] + w["reads"], stdout=subprocess.DEVNULL)
+                               "--out", fa + ".tmp"] + (["--fastq", "1"] if fastq else []) + w["reads"], stdout=subprocess.DEVNULL)
         os.replace(fa + ".tmp", fa)
     db = ref + ".pmlnulldb"
     if not os.path.exists(db):
@@ -612,6 +612,12 @@ def main():
         cli = cli_seconds(ref, name, 4, cores)
         if cli:
             cli["bases_per_s"] = n_bases / cli["phase_s"]
+        if "cli_fastq" in want:  # the same reads as four-line FASTQ records (twice the file bytes per base)
+            cli_seconds(ref, name, 4, cores, fastq=True)
+            fq = cli_seconds(ref, name, 4, cores, fastq=True)
+            if fq and cli is not None:
+                fq["bases_per_s"] = n_bases / fq["phase_s"]
+                cli["fastq"] = fq
     if world == 1 and mode == "pml" and "synth" not in w and "ms" in want:
         try:
             idx = None  # close the PML index first (it holds the device's persisting-L2 carve-out, which MS does not want)

@@ -634,6 +634,115 @@ static void window_fill(const char* d, const std::vector<uint64_t>& starts, int 
     }
 }
 
+
+// ---- FASTQ on the fast path --------------------------------------------------------------------------------------------
+// BatchLoader takes FASTQ four lines at a time, in batches of >= 1000 estimated bases (half of the four lines' lengths,
+// compute_ms_pml.cpp:903, batch_loader.cpp:33-66), and LOSES the last batch when the file ends inside its gathering loop
+// (:51) -- which records survive depends on the line lengths from the top of the file.  The fast path therefore (1) finds
+// every line end on all threads, (2) replays the batch formation over the line lengths (a few operations per line), which
+// gives the number of lines BatchLoader processes, (3) checks on all threads that every record in them is ordinary (header
+// starts with '@' and has an id, sequence not empty); anything else -- an empty header line skips the rest of its batch, a
+// bad header is fatal -- sends the whole file to the sequential parser, which reproduces those cases line by line.
+struct FastqLines {
+    const char* d = nullptr;
+    uint64_t size = 0;
+    std::vector<uint64_t> nl;    // positions of every '\n'
+    uint64_t n_lines = 0;        // std::getline lines: a last line without terminator counts
+    bool unterminated = false;
+    uint64_t start(uint64_t i) const { return i ? nl[(size_t)i - 1] + 1 : 0; }
+    uint64_t end(uint64_t i) const { return i < nl.size() ? nl[(size_t)i] : size; }
+    uint64_t len(uint64_t i) const { return end(i) - start(i); }
+};
+static void fastq_index_lines(const char* d, uint64_t size, int T, FastqLines& L) {
+    L.d = d; L.size = size;
+    std::vector<std::vector<uint64_t>> part((size_t)T);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+    for (int t = 0; t < T; t++) {
+        const uint64_t a = size * (uint64_t)t / (uint64_t)T, e = size * (uint64_t)(t + 1) / (uint64_t)T;
+        uint64_t p = a;
+        while (p < e) {
+            const char* g = (const char*)std::memchr(d + p, '\n', e - p);
+            if (!g) break;
+            part[(size_t)t].push_back((uint64_t)(g - d));
+            p = (uint64_t)(g - d) + 1;
+        }
+    }
+    L.nl.clear();
+    for (auto& v : part) L.nl.insert(L.nl.end(), v.begin(), v.end());
+    L.unterminated = size > 0 && (L.nl.empty() || L.nl.back() + 1 < size);
+    L.n_lines = L.nl.size() + (L.unterminated ? 1 : 0);
+}
+// lines [0, result) are the ones BatchLoader hands to grabNextRead (FastaSource::load_fastq_batch, line for line)
+static uint64_t fastq_processed_lines(const FastqLines& L) {
+    uint64_t i = 0, processed = 0;
+    bool good = true;
+    while (good) {
+        uint64_t covered = 0, record = 0, cnt = 0;
+        bool lost = false;
+        while (good && covered < 1000) {
+            if (i >= L.n_lines) { lost = true; good = false; break; }  // getline fails inside the loop: the batch is dropped
+            if (L.unterminated && i + 1 == L.n_lines) good = false;   // the line was ended by the end of the file
+            record += L.len(i);
+            i++; cnt++;
+            if (cnt % 4 == 0) { covered += record / 2; record = 0; }
+        }
+        if (lost) break;
+        processed = i;
+    }
+    return processed;
+}
+// records r (lines 4r .. 4r+3) for r < processed / 4, plus the header of a trailing cut-short record: all ordinary?
+static bool fastq_all_ordinary(const FastqLines& L, uint64_t processed, int T) {
+    const uint64_t headers = (processed + 3) / 4, records = processed / 4;
+    int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(T) reduction(| : bad)
+    for (int64_t r = 0; r < (int64_t)headers; r++) {
+        const uint64_t h = 4 * (uint64_t)r, hs = L.start(h), hl = L.len(h);
+        if (hl <= 2 || L.d[hs] != '@') { bad = 1; continue; }  // empty header, not a FASTQ header, or no id
+        if ((uint64_t)r < records) {
+            const uint64_t ss = L.start(h + 1);
+            uint64_t e = L.end(h + 1);
+            while (e > ss && is_space((unsigned char)L.d[e - 1])) e--;
+            if (e == ss) bad = 1;  // "was empty after digestion"
+        }
+    }
+    return !bad;
+}
+// a window of about `window` bytes of file starting at record r: the first record boundary at or past it (line starts ascend)
+static uint64_t fastq_window_end(const FastqLines& L, uint64_t r, uint64_t records, uint64_t window) {
+    const uint64_t lo = L.start(4 * r);
+    uint64_t a = r + 1, z = records;
+    while (a < z) {
+        const uint64_t m = a + (z - a) / 2;
+        if (L.start(4 * m) - lo >= window) z = m; else a = m + 1;
+    }
+    return a;
+}
+// records [r0, r1): sizes (off[i + 1] / ido[i + 1], then prefix sums), then the bytes
+static void fastq_window_sizes(const FastqLines& L, uint64_t r0, uint64_t r1, int T, uint64_t* off, uint64_t* ido) {
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int64_t i = 0; i < (int64_t)(r1 - r0); i++) {
+        const uint64_t h = 4 * (r0 + (uint64_t)i), hs = L.start(h), hl = L.len(h);
+        uint64_t idl = hl;
+        for (uint64_t q = 1; q < hl; q++) { const char c = L.d[hs + q]; if (c == ' ' || c == '\t' || c == '\r') { idl = q; break; } }
+        ido[i + 1] = std::min(hl - 1, idl);  // substr(1, idl): keeps the delimiter (batch_loader.cpp:104-106)
+        const uint64_t ss = L.start(h + 1);
+        uint64_t e = L.end(h + 1);
+        while (e > ss && is_space((unsigned char)L.d[e - 1])) e--;
+        off[i + 1] = e - ss;
+    }
+    off[0] = 0; ido[0] = 0;
+    for (uint64_t i = 0; i < r1 - r0; i++) { off[i + 1] += off[i]; ido[i + 1] += ido[i]; }
+}
+static void fastq_window_fill(const FastqLines& L, uint64_t r0, uint64_t r1, int T, const uint64_t* off, const uint64_t* ido, uint8_t* bases, uint8_t* ids) {
+#pragma omp parallel for schedule(static) num_threads(T)
+    for (int64_t i = 0; i < (int64_t)(r1 - r0); i++) {
+        const uint64_t h = 4 * (r0 + (uint64_t)i);
+        std::memcpy(ids + ido[i], L.d + L.start(h) + 1, ido[i + 1] - ido[i]);
+        std::memcpy(bases + off[i], L.d + L.start(h + 1), off[i + 1] - off[i]);
+    }
+}
+
 class FastRunner {
 public:
     FastRunner(const RunOptions& o, bool ms, int n_gpus) : o_(o), ms_(ms), n_gpus_(std::max(1, n_gpus)), threads_((int)std::max<size_t>(1, o.threads)) {
@@ -696,6 +805,7 @@ private:
         std::mutex m; std::condition_variable cv; std::deque<FastBatch*> q;
     };
     void parse_loop() {
+        if (data_[0] == '@') return parse_loop_fastq();
         uint64_t lo = 0, seq = 0;
         bool stop = false;
         while (lo < size_ && !stop) {
@@ -728,6 +838,44 @@ private:
                 lo = hi;
                 if (lo >= size_) resume_ = size_;
             }
+            t_parse += now_s() - t0;
+            parsed_q_.push(b);
+        }
+        for (int g = 0; g < n_gpus_; g++) parsed_q_.push(nullptr);
+    }
+    void parse_loop_fastq() {
+        const int T = threads_;
+        double t0 = now_s();
+        FastqLines L;
+        fastq_index_lines(data_, size_, T, L);
+        const uint64_t processed = fastq_processed_lines(L);
+        uint64_t r = 0, seq = 0;
+        const uint64_t records = processed / 4;
+        if (!fastq_all_ordinary(L, processed, T)) {  // the sequential parser reproduces skipped batches and fatal headers line by line
+            resume_ = 0;
+            t_parse += now_s() - t0;
+            for (int g = 0; g < n_gpus_; g++) parsed_q_.push(nullptr);
+            return;
+        }
+        resume_ = size_;  // every record BatchLoader keeps is handled here
+        while (r < records) {
+            FastBatch* b = free_q_.pop();
+            if (seq) t0 = now_s();
+            // a window of about window_ bytes of file: the first record boundary at or past lo + window_ (line starts ascend)
+            const uint64_t lo = L.start(4 * r), r1 = fastq_window_end(L, r, records, window_);
+            const uint64_t nr = r1 - r;
+            b->seq = seq++; b->file_lo = lo; b->anomaly = false; b->last = false;
+            b->offsets.reserve((nr + 1) * 8);
+            b->idoff.reserve((nr + 1) * 8);
+            if (o_.write_report) b->stats.reserve((nr + 1) * sizeof(spb_bin_stats));
+            uint64_t* off = b->offsets.as<uint64_t>();
+            uint64_t* ido = b->idoff.as<uint64_t>();
+            fastq_window_sizes(L, r, r1, T, off, ido);
+            b->n_reads = nr; b->n_bases = off[nr]; b->id_bytes = ido[nr];
+            b->bases.reserve(b->n_bases + 64);
+            b->idcat.reserve(b->id_bytes + 64);
+            fastq_window_fill(L, r, r1, T, off, ido, b->bases.as<uint8_t>(), b->idcat.as<uint8_t>());
+            r = r1;
             t_parse += now_s() - t0;
             parsed_q_.push(b);
         }
@@ -904,7 +1052,7 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o, FastR
     if (fast) {  // FASTA input: memory-mapped, parsed on all threads, one query thread per GPU, texts formatted on the device
         int first = EOF;
         { std::ifstream probe(o.pattern_file, std::ifstream::binary); first = probe.peek(); }
-        if (first == '>') {
+        if (first == '>' || first == '@') {
             out.lengths.flush();
             const std::string paths[3] = {o.pattern_file + (ms ? ".lengths" : ".pseudo_lengths"), ms ? o.pattern_file + ".pointers" : std::string(),
                                           o.use_doc ? o.pattern_file + ".doc_numbers" : std::string()};

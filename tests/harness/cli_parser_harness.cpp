@@ -13,6 +13,32 @@ static void fast_parse(const char* path, uint64_t window, int T, ReadBatch& b) {
     std::string data((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     const uint64_t size = data.size();
     uint64_t lo = 0, resume = size;
+    if (size && data[0] == '@') {  // FASTQ: line index, replay of the batch formation, validation, windows of records
+        FastqLines L;
+        fastq_index_lines(data.data(), size, T, L);
+        const uint64_t processed = fastq_processed_lines(L), records = processed / 4;
+        if (fastq_all_ordinary(L, processed, T)) {
+            std::fprintf(stderr, "fastq:fast\n");
+            for (uint64_t r = 0; r < records;) {
+                const uint64_t r1 = fastq_window_end(L, r, records, window);
+                std::vector<uint64_t> off(r1 - r + 1), ido(r1 - r + 1);
+                fastq_window_sizes(L, r, r1, T, off.data(), ido.data());
+                std::vector<uint8_t> bases(off[r1 - r] + 1), ids(ido[r1 - r] + 1);
+                fastq_window_fill(L, r, r1, T, off.data(), ido.data(), bases.data(), ids.data());
+                for (uint64_t i = 0; i < r1 - r; i++) {
+                    b.ids.emplace_back((const char*)ids.data() + ido[i], ido[i + 1] - ido[i]);
+                    b.bases.insert(b.bases.end(), bases.begin() + off[i], bases.begin() + off[i + 1]);
+                    b.offsets.push_back(b.bases.size());
+                }
+                r = r1;
+            }
+            return;
+        }
+        std::fprintf(stderr, "fastq:sequential\n");
+        FastaSource src(path, 0);
+        while (src.next(b)) {}
+        return;
+    }
     if (size && data[0] != '>') { resume = 0; lo = size; }
     while (lo < size) {
         const uint64_t hi = lo + window >= size ? size : next_record_start(data.data(), size, lo + window);

@@ -76,6 +76,10 @@ def _nasty_files(d, text):
         "fq_mixed": fq(9, 150) + fq(2, 1500) + fq(5, 60), "fq_one": fq(1, 100), "fq_one_notrail": fq(1, 100, False),
         "fq_crlf": fq(12, 150).replace("\n", "\r\n"), "fq_truncated": fq(10, 400) + "@last\nACGT\n",
         "fq_blank_mid": fq(3, 600) + "\n" + fq(3, 600), "fq_plus_named": fq(4, 500).replace("\n+\n", "\n+same id\n"),
+        "fq_bad_header": fq(6, 300) + "Xnot\nACGT\n+\nIIII\n" + fq(6, 300), "fq_two_char_header": fq(6, 300) + "@a\nACGT\n+\nIIII\n" + fq(2, 300),
+        "fq_empty_seq": fq(6, 300) + "@e1 x\n\n+\n\n" + fq(6, 300), "fq_tab_ids": fq(30, 90).replace(" some", "\tsome"),
+        "fq_bare_ids": fq(30, 90).replace(" some comment", ""), "fq_cut_short_bad_header": fq(10, 400) + "Zlast\nACGT",
+        "fq_trailing_blank_lines": fq(10, 400) + "\n\n", "fq_many": fq(700, 37) + fq(40, 1001) + fq(300, 5),
     }
     paths = {}
     for name, body in cases.items():
@@ -111,13 +115,13 @@ def test_parser_equals_reference_binary_on_odd_inputs(harness, tmp_path):
 
 
 def test_fast_window_parser_equals_sequential_parser(harness, tmp_path):
-    """The fast path of `spumoni run` (memory-mapped FASTA cut into windows, parsed on several threads) must produce exactly the
+    """The fast path of `spumoni run` (memory-mapped FASTA or FASTQ cut into windows, parsed on several threads) must produce exactly the
     records of the sequential BatchLoader-equivalent parser -- ids with their delimiter quirk, stripped multi-line sequences,
     CRLF, '>' inside a line -- for any window size and thread count, and must hand over to the sequential parser (same
     records, same rejection) where a header has no id or a record is empty."""
     d = str(tmp_path)
     text = "".join(line.strip() for line in open(os.path.join(GOLDEN, "idx.fa")) if not line.startswith(">"))
-    files = {k: v for k, v in _nasty_files(d, text).items() if not k.startswith("fq_")}
+    files = _nasty_files(d, text)
     files["golden"] = os.path.join(GOLDEN, "reads.fa")
     rng = random.Random(9)
     big = os.path.join(d, "big.fa")
@@ -130,10 +134,23 @@ def test_fast_window_parser_equals_sequential_parser(harness, tmp_path):
                 body = body[: ln // 2] + "\n" + body[ln // 2:]
             f.write(">read%d%s\n%s\n" % (i, rng.choice(["", " d", "\tq", " "]), body))
     files["big"] = big
+    files["golden_fq"] = os.path.join(GOLDEN, "fastq_reads.fa")
+    bigq = os.path.join(d, "big.fq")
+    with open(bigq, "w", newline="") as f:  # ragged FASTQ: the batch replay decides which tail records BatchLoader keeps
+        for i in range(2500):
+            ln = rng.choice([1, 7, 60, 150, 400, 2100])
+            p = rng.randint(0, len(text) - ln - 1)
+            eol = rng.choice(["\n", "\n", "\r\n"])
+            f.write("@read%d%s%s%s%s+%s%s%s" % (i, rng.choice(["", " d", "\tq", " "]), eol, text[p:p + ln], eol, eol, "F" * ln,
+                                              eol if i < 2499 else ""))
+    files["big_fq"] = bigq
+    anomalous = {"fq_bad_header", "fq_two_char_header", "fq_empty_seq", "fq_cut_short_bad_header", "fq_blank_mid"}
     for name, path in sorted(files.items()):
         r0 = subprocess.run([harness, path], capture_output=True)
         for window, threads in ((1, 1), (64, 3), (300, 8), (1 << 20, 4)):
             r1 = subprocess.run([harness, path, str(window), str(threads)], capture_output=True)
             assert r1.returncode == r0.returncode, (name, window, threads)
+            if name.startswith("fq_") or name.endswith("_fq"):  # ordinary FASTQ stays on the fast path, anomalies hand over
+                assert (b"fastq:sequential" if name in anomalous else b"fastq:fast") in r1.stderr, name
             if r0.returncode == 0:
                 assert r1.stdout == r0.stdout, (name, window, threads)

@@ -732,6 +732,41 @@ def test_cli_fast_path_equals_sequential_path(small_index, many_reads):
             assert got == want, (flags, env)
 
 
+def test_cli_fastq_fast_path_equals_sequential_path(small_index, many_reads, tmp_path):
+    """FASTQ on the fast path: the line index, the replay of BatchLoader's batch formation (which tail records it loses)
+    and the windows of records give the bytes of the sequential parser's run -- itself record-identical to the reference
+    (test_zz_cli_fastq_records_equal_reference) -- with and without a final newline, CRLF, and for -P / -M / -d."""
+    prefix = small_index["ref"][:-3]
+    recs, cur = [], None
+    for line in open(many_reads, newline=""):
+        if line.startswith(">"):
+            cur = [line[1:].rstrip("\r\n"), ""]
+            recs.append(cur)
+        else:
+            cur[1] += line.strip()
+    for name, eol, trail in (("a_fq.fa", "\n", True), ("b_fq.fa", "\n", False), ("c_fq.fa", "\r\n", True)):
+        path = str(tmp_path / name)
+        with open(path, "w", newline="") as f:
+            body = "".join("@%s%s%s%s+%s%s%s" % (i, eol, q, eol, eol, "I" * len(q), eol) for i, q in recs if q)
+            f.write(body if trail else body.rstrip("\r\n"))
+        for flags in (["-P", "-c"], ["-M", "-d"]) if name == "a_fq.fa" else (["-P"],):
+            want, err0 = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, path, flags)
+            for env in ({}, {"SPUMONI_B200_BATCH_MB": "1"}, {"SPUMONI_B200_BATCH_MB": "2", "SPUMONI_B200_WRITE": "pwrite"}):
+                got, err = _cli_run(env, prefix, path, flags + ["-t", "5"])
+                assert got == want, (name, flags, env)
+                assert err.split("finished processing")[1].split()[0] == err0.split("finished processing")[1].split()[0]
+    # an empty header line skips the rest of its batch, a bad one is fatal: the sequential parser takes the whole file
+    odd = str(tmp_path / "odd_fq.fa")
+    with open(odd, "w") as f:
+        f.write("".join("@r%d\n%s\n+\n%s\n" % (i, q, "I" * len(q)) for i, (_, q) in enumerate(recs[:3000]) if q))
+        f.write("\nACGT\n+\nIIII\n")  # four lines, so the batches after this one stay aligned
+        f.write("".join("@s%d\n%s\n+\n%s\n" % (i, q, "I" * len(q)) for i, (_, q) in enumerate(recs[:3000]) if q))
+    want, _ = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, odd, ["-P"])
+    got, _ = _cli_run({"SPUMONI_B200_BATCH_MB": "1"}, prefix, odd, ["-P", "-t", "4"])
+    n_written = got[".pseudo_lengths"].count(b">")
+    assert got == want and 3000 < n_written < 2 * sum(1 for _, q in recs[:3000] if q)
+
+
 def test_cli_fast_path_hands_over_on_odd_records(small_index, tmp_path):
     """A header without an id in a later window: the windows before it are written by the fast path, then the sequential
     parser takes over at that window and fails exactly like BatchLoader does (same message, exit code 1)."""

@@ -356,12 +356,19 @@ static int cmd_reads(const Args& a) {
     }
     if (!out.empty()) {
         std::ofstream o(out, std::ios::binary);
-        std::string line;
+        const bool fastq = has(a, "fastq");  // four-line records with a constant quality string
+        std::string line, qual;
         for (uint64_t r = 0; r < N; r++) {
-            line = ">read_" + std::to_string(r) + "\n";
+            line = (fastq ? "@read_" : ">read_") + std::to_string(r) + "\n";
             o.write(line.data(), (std::streamsize)line.size());
             o.write((const char*)buf.data() + off[r], (std::streamsize)(off[r + 1] - off[r]));
             o.put('\n');
+            if (fastq) {
+                qual.assign((size_t)(off[r + 1] - off[r]), 'I');
+                o.write("+\n", 2);
+                o.write(qual.data(), (std::streamsize)qual.size());
+                o.put('\n');
+            }
         }
     }
     if (!bin.empty()) {
