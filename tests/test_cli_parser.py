@@ -154,3 +154,58 @@ def test_fast_window_parser_equals_sequential_parser(harness, tmp_path):
                 assert (b"fastq:sequential" if name in anomalous else b"fastq:fast") in r1.stderr, name
             if r0.returncode == 0:
                 assert r1.stdout == r0.stdout, (name, window, threads)
+
+
+def test_fast_fastq_parser_random_files(harness, tmp_path):
+    """Random four-line files -- ragged record lengths around the 1000-base batch limit, CRLF, a missing final newline, cut
+    short records, and now and then an empty or malformed header or an empty sequence: whatever the batch replay decides
+    (fast windows or hand-over to the sequential parser), records and exit status equal the sequential parser's."""
+    rng = random.Random(77)
+    fast = handed = rejected = pinned = 0
+    ref_prefix = None
+    if os.path.exists(REF_BIN):  # where the reference's own binary exists, the sequential parser is held to it on the same files
+        import shutil
+        for f in os.listdir(GOLDEN):
+            if f.startswith("idx.fa"):
+                shutil.copy(os.path.join(GOLDEN, f), str(tmp_path / f))
+        ref_prefix = str(tmp_path / "idx")
+    for trial in range(120):
+        n = rng.choice([1, 2, 3, 7, 40, 200])
+        eol = rng.choice(["\n", "\n", "\r\n"])
+        odd = rng.random() < 0.35
+        lines = []
+        for i in range(n):
+            ln = rng.choice([1, 5, 90, 150, 499, 500, 501, 700, 1999, 2000, 2600])
+            hdr = "@r%d%s" % (i, rng.choice(["", " x", "\ty z"]))
+            seq = "".join(rng.choice("ACGT") for _ in range(ln))
+            if odd and rng.random() < 0.08:
+                hdr = rng.choice(["", "@", "@a", "Xr%d" % i, ">r%d" % i])
+            if odd and rng.random() < 0.04:
+                seq = rng.choice(["", " "])
+            lines += [hdr, seq, "+" + rng.choice(["", hdr[1:]]), "I" * len(seq)]
+        lines = lines[: len(lines) - rng.choice([0, 0, 0, 1, 2, 3])]
+        if not lines or not lines[0].startswith("@"):
+            continue  # not recognised as FASTQ at all: the FASTA tests cover that entry
+        body = eol.join(lines) + rng.choice([eol, eol, "", eol + eol])
+        path = str(tmp_path / ("t%d.fa" % trial))
+        with open(path, "w", newline="") as f:
+            f.write(body)
+        r0 = subprocess.run([harness, path], capture_output=True)
+        window, threads = rng.choice([(1, 2), (700, 3), (5000, 8), (1 << 20, 4)])
+        r1 = subprocess.run([harness, path, str(window), str(threads)], capture_output=True)
+        assert r1.returncode == r0.returncode, (trial, body[:200])
+        if r0.returncode == 0:
+            assert r1.stdout == r0.stdout, (trial, window, threads)
+        else:
+            rejected += 1
+        if ref_prefix and trial % 2 == 0:
+            ref = subprocess.run([REF_BIN, "run", "-r", ref_prefix, "-p", path, "-P", "-n"], capture_output=True)
+            assert (ref.returncode != 0) == (r0.returncode != 0), (trial, body[:200])
+            if ref.returncode == 0:
+                out = r0.stdout.split(b"\n")
+                got = [(out[i], len(out[i + 1])) for i in range(0, len(out) - 1, 2)]
+                assert got == _reference_records(path + ".pseudo_lengths"), trial
+                pinned += 1
+        fast += b"fastq:fast" in r1.stderr
+        handed += b"fastq:sequential" in r1.stderr
+    assert fast >= 40 and handed >= 10 and rejected >= 5 and (pinned >= 30 or not ref_prefix)
