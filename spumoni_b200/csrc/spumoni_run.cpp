@@ -196,10 +196,13 @@ private:
 
 class FastaSource {  // sequential equivalent of BatchLoader::loadBatch + grabNextRead (FASTA, and FASTQ records)
 public:
-    explicit FastaSource(const std::string& path, uint64_t start = 0) : in_(path, start) {  // start: offset of a record's '>' (fast path hand-over)
+    // start: offset of a record's '>', or of the first line of a FASTQ batch (fast path hand-over; resume_fastq says which --
+    // a batch may begin with an empty line, so the first byte cannot tell)
+    explicit FastaSource(const std::string& path, uint64_t start = 0, bool resume_fastq = false) : in_(path, start) {
         if (!in_.good()) return;
         int pk = in_.peek();
         if (pk == EOF) { done_ = true; return; }
+        if (resume_fastq) { fastq_ = true; return; }
         if (pk == '@') { fastq_ = true; return; }
         if (pk != '>') fatal_error("unrecognized input query file type - expects FASTA or FASTQ.");
         if (!in_.getline(line_)) done_ = true;
@@ -638,22 +641,24 @@ static void window_fill(const char* d, const std::vector<uint64_t>& starts, int 
 // ---- FASTQ on the fast path --------------------------------------------------------------------------------------------
 // BatchLoader takes FASTQ four lines at a time, in batches of >= 1000 estimated bases (half of the four lines' lengths,
 // compute_ms_pml.cpp:903, batch_loader.cpp:33-66), and LOSES the last batch when the file ends inside its gathering loop
-// (:51) -- which records survive depends on the line lengths from the top of the file.  The fast path therefore (1) finds
-// every line end on all threads, (2) replays the batch formation over the line lengths (a few operations per line), which
-// gives the number of lines BatchLoader processes, (3) checks on all threads that every record in them is ordinary (header
-// starts with '@' and has an id, sequence not empty); anything else -- an empty header line skips the rest of its batch, a
-// bad header is fatal -- sends the whole file to the sequential parser, which reproduces those cases line by line.
+// (:51) -- which records survive depends on the line lengths from the top of the file.  The fast path therefore walks the
+// file in segments that begin at a batch boundary (fastq_walk): it (1) finds every line end of the segment on all threads,
+// (2) replays the batch formation over the line lengths (a few operations per line), which gives the lines of the complete
+// batches -- the batch the segment ends in opens the next segment, the batch the FILE ends in is lost or kept as BatchLoader
+// decides -- and (3) checks on all threads that every record in them is ordinary (header starts with '@' and has an id,
+// sequence not empty); anything else -- an empty header line skips the rest of its batch, a bad header is fatal -- hands the
+// file from that segment on to the sequential parser, which reproduces those cases line by line.
 struct FastqLines {
-    const char* d = nullptr;
+    const char* d = nullptr;     // the segment
     uint64_t size = 0;
-    std::vector<uint64_t> nl;    // positions of every '\n'
-    uint64_t n_lines = 0;        // std::getline lines: a last line without terminator counts
+    std::vector<uint64_t> nl;    // positions of every '\n' in it
+    uint64_t n_lines = 0;        // std::getline lines; at the end of the file a last line without terminator counts
     bool unterminated = false;
     uint64_t start(uint64_t i) const { return i ? nl[(size_t)i - 1] + 1 : 0; }
     uint64_t end(uint64_t i) const { return i < nl.size() ? nl[(size_t)i] : size; }
     uint64_t len(uint64_t i) const { return end(i) - start(i); }
 };
-static void fastq_index_lines(const char* d, uint64_t size, int T, FastqLines& L) {
+static void fastq_index_lines(const char* d, uint64_t size, int T, bool at_eof, FastqLines& L) {
     L.d = d; L.size = size;
     std::vector<std::vector<uint64_t>> part((size_t)T);
 #pragma omp parallel for schedule(static, 1) num_threads(T)
@@ -669,24 +674,25 @@ static void fastq_index_lines(const char* d, uint64_t size, int T, FastqLines& L
     }
     L.nl.clear();
     for (auto& v : part) L.nl.insert(L.nl.end(), v.begin(), v.end());
-    L.unterminated = size > 0 && (L.nl.empty() || L.nl.back() + 1 < size);
+    L.unterminated = at_eof && size > 0 && (L.nl.empty() || L.nl.back() + 1 < size);  // (the cut end of an inner segment is no line)
     L.n_lines = L.nl.size() + (L.unterminated ? 1 : 0);
 }
-// lines [0, result) are the ones BatchLoader hands to grabNextRead (FastaSource::load_fastq_batch, line for line)
-static uint64_t fastq_processed_lines(const FastqLines& L) {
+// lines [0, result) of the segment are the ones BatchLoader hands to grabNextRead (FastaSource::load_fastq_batch, line for
+// line); a batch the segment (not the file) ends in is left to the next segment
+static uint64_t fastq_processed_lines(const FastqLines& L, bool at_eof) {
     uint64_t i = 0, processed = 0;
     bool good = true;
     while (good) {
         uint64_t covered = 0, record = 0, cnt = 0;
-        bool lost = false;
+        bool incomplete = false;
         while (good && covered < 1000) {
-            if (i >= L.n_lines) { lost = true; good = false; break; }  // getline fails inside the loop: the batch is dropped
-            if (L.unterminated && i + 1 == L.n_lines) good = false;   // the line was ended by the end of the file
+            if (i >= L.n_lines) { incomplete = true; good = false; break; }  // at the end of the file: getline fails inside the loop, the batch is dropped
+            if (at_eof && L.unterminated && i + 1 == L.n_lines) good = false;  // the line was ended by the end of the file
             record += L.len(i);
             i++; cnt++;
             if (cnt % 4 == 0) { covered += record / 2; record = 0; }
         }
-        if (lost) break;
+        if (incomplete) break;
         processed = i;
     }
     return processed;
@@ -743,6 +749,32 @@ static void fastq_window_fill(const FastqLines& L, uint64_t r0, uint64_t r1, int
     }
 }
 
+// The whole walk: emit(L, r0, r1) gets windows of ordinary records of the current segment.  Returns the file offset where the
+// sequential parser has to take over -- the start of a batch -- or `size` when nothing is left for it.
+template <typename Emit>
+static uint64_t fastq_walk(const char* d, uint64_t size, int T, uint64_t segment, uint64_t window, Emit&& emit) {
+    FastqLines L;
+    uint64_t lo = 0;
+    segment = std::max<uint64_t>(segment, 1);
+    while (lo < size) {
+        const uint64_t len = std::min(segment, size - lo);
+        const bool at_eof = lo + len == size;
+        fastq_index_lines(d + lo, len, T, at_eof, L);
+        const uint64_t processed = fastq_processed_lines(L, at_eof);
+        if (!at_eof && processed == 0) { segment *= 2; continue; }  // not even one batch fits: a longer segment
+        if (!fastq_all_ordinary(L, processed, T)) return lo;
+        const uint64_t records = processed / 4;
+        for (uint64_t r = 0; r < records;) {
+            const uint64_t r1 = fastq_window_end(L, r, records, window);
+            emit(L, r, r1);
+            r = r1;
+        }
+        if (at_eof) return size;
+        lo += L.start(processed);
+    }
+    return size;
+}
+
 class FastRunner {
 public:
     FastRunner(const RunOptions& o, bool ms, int n_gpus) : o_(o), ms_(ms), n_gpus_(std::max(1, n_gpus)), threads_((int)std::max<size_t>(1, o.threads)) {
@@ -776,6 +808,7 @@ public:
         data_ = (const char*)mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd, 0);
         if (data_ == MAP_FAILED) fatal_error("cannot map " + path);
         madvise((void*)data_, size_, MADV_WILLNEED);
+        fastq_ = data_[0] == '@';
         for (int w = 0; w < 3; w++) {
             out_fd_[w] = -1;
             if (text_paths[w].empty()) continue;
@@ -796,6 +829,7 @@ public:
         return reads_done_;
     }
     uint64_t text_written(int w) const { return text_off_[w]; }
+    bool is_fastq() const { return fastq_; }
     double t_parse = 0, t_gpu = 0, t_write = 0, t_report = 0;
 
 private:
@@ -805,7 +839,7 @@ private:
         std::mutex m; std::condition_variable cv; std::deque<FastBatch*> q;
     };
     void parse_loop() {
-        if (data_[0] == '@') return parse_loop_fastq();
+        if (fastq_) return parse_loop_fastq();
         uint64_t lo = 0, seq = 0;
         bool stop = false;
         while (lo < size_ && !stop) {
@@ -845,26 +879,16 @@ private:
     }
     void parse_loop_fastq() {
         const int T = threads_;
+        uint64_t seq = 0;
+        uint64_t segment = 512ull << 20;  // line index: 8 bytes per line of the segment
+        if (const char* e = std::getenv("SPUMONI_B200_FASTQ_SEGMENT_MB")) { long v = std::atol(e); if (v >= 1 && v <= 65536) segment = (uint64_t)v << 20; }
         double t0 = now_s();
-        FastqLines L;
-        fastq_index_lines(data_, size_, T, L);
-        const uint64_t processed = fastq_processed_lines(L);
-        uint64_t r = 0, seq = 0;
-        const uint64_t records = processed / 4;
-        if (!fastq_all_ordinary(L, processed, T)) {  // the sequential parser reproduces skipped batches and fatal headers line by line
-            resume_ = 0;
-            t_parse += now_s() - t0;
-            for (int g = 0; g < n_gpus_; g++) parsed_q_.push(nullptr);
-            return;
-        }
-        resume_ = size_;  // every record BatchLoader keeps is handled here
-        while (r < records) {
+        resume_ = fastq_walk(data_, size_, T, segment, window_, [&](const FastqLines& L, uint64_t r, uint64_t r1) {
+            t_parse += now_s() - t0;  // (indexing, replay and checks of the segment since the last window)
             FastBatch* b = free_q_.pop();
-            if (seq) t0 = now_s();
-            // a window of about window_ bytes of file: the first record boundary at or past lo + window_ (line starts ascend)
-            const uint64_t lo = L.start(4 * r), r1 = fastq_window_end(L, r, records, window_);
+            t0 = now_s();
             const uint64_t nr = r1 - r;
-            b->seq = seq++; b->file_lo = lo; b->anomaly = false; b->last = false;
+            b->seq = seq++; b->file_lo = (uint64_t)(L.d - data_) + L.start(4 * r); b->anomaly = false; b->last = false;
             b->offsets.reserve((nr + 1) * 8);
             b->idoff.reserve((nr + 1) * 8);
             if (o_.write_report) b->stats.reserve((nr + 1) * sizeof(spb_bin_stats));
@@ -875,10 +899,11 @@ private:
             b->bases.reserve(b->n_bases + 64);
             b->idcat.reserve(b->id_bytes + 64);
             fastq_window_fill(L, r, r1, T, off, ido, b->bases.as<uint8_t>(), b->idcat.as<uint8_t>());
-            r = r1;
             t_parse += now_s() - t0;
             parsed_q_.push(b);
-        }
+            t0 = now_s();
+        });
+        t_parse += now_s() - t0;
         for (int g = 0; g < n_gpus_; g++) parsed_q_.push(nullptr);
     }
     void query_loop(int g) {
@@ -1013,6 +1038,7 @@ private:
     Outputs* out_ = nullptr;
     int n_gpus_, threads_;
     uint64_t window_ = 0, size_ = 0, resume_ = 0, text_off_[3] = {0, 0, 0};
+    bool fastq_ = false;
     size_t reads_done_ = 0;
     const char* data_ = nullptr;
     int out_fd_[3] = {-1, -1, -1};
@@ -1083,7 +1109,7 @@ static size_t classify_reads(spb_index* idx, bool ms, const RunOptions& o, FastR
             t0 = now_s();
         };
         if (!o.is_general_text) {
-            FastaSource src(o.pattern_file, resume_at);
+            FastaSource src(o.pattern_file, resume_at, fast && resume_at > 0 && fast->is_fastq());
             while (src.next(w->b)) {
                 num_reads++;
                 if (w->b.bases.size() >= kBatchBases) flush(false);

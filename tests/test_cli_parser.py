@@ -144,6 +144,7 @@ def test_fast_window_parser_equals_sequential_parser(harness, tmp_path):
             f.write("@read%d%s%s%s%s+%s%s%s" % (i, rng.choice(["", " d", "\tq", " "]), eol, text[p:p + ln], eol, eol, "F" * ln,
                                               eol if i < 2499 else ""))
     files["big_fq"] = bigq
+    late = 0
     anomalous = {"fq_bad_header", "fq_two_char_header", "fq_empty_seq", "fq_cut_short_bad_header", "fq_blank_mid"}
     for name, path in sorted(files.items()):
         r0 = subprocess.run([harness, path], capture_output=True)
@@ -154,6 +155,12 @@ def test_fast_window_parser_equals_sequential_parser(harness, tmp_path):
                 assert (b"fastq:sequential" if name in anomalous else b"fastq:fast") in r1.stderr, name
             if r0.returncode == 0:
                 assert r1.stdout == r0.stdout, (name, window, threads)
+        if name.startswith("fq_") or name.endswith("_fq"):  # FASTQ in segments: each begins at a batch boundary found by the replay
+            for segment in (1, 700, 5000, 40000):
+                r2 = subprocess.run([harness, path, "900", "3", str(segment)], capture_output=True)
+                assert r2.returncode == r0.returncode and (r0.returncode != 0 or r2.stdout == r0.stdout), (name, segment)
+                late += b"fastq:sequential from" in r2.stderr and b"from 0\n" not in r2.stderr
+    assert late >= 3  # anomalies behind the first segment: the sequential parser took over mid-file, at a batch boundary
 
 
 def test_fast_fastq_parser_random_files(harness, tmp_path):
@@ -161,7 +168,7 @@ def test_fast_fastq_parser_random_files(harness, tmp_path):
     short records, and now and then an empty or malformed header or an empty sequence: whatever the batch replay decides
     (fast windows or hand-over to the sequential parser), records and exit status equal the sequential parser's."""
     rng = random.Random(77)
-    fast = handed = rejected = pinned = 0
+    fast = handed = rejected = pinned = midfile = 0
     ref_prefix = None
     if os.path.exists(REF_BIN):  # where the reference's own binary exists, the sequential parser is held to it on the same files
         import shutil
@@ -192,10 +199,11 @@ def test_fast_fastq_parser_random_files(harness, tmp_path):
             f.write(body)
         r0 = subprocess.run([harness, path], capture_output=True)
         window, threads = rng.choice([(1, 2), (700, 3), (5000, 8), (1 << 20, 4)])
-        r1 = subprocess.run([harness, path, str(window), str(threads)], capture_output=True)
+        segment = rng.choice([1, 300, 2500, 20000, 1 << 40])
+        r1 = subprocess.run([harness, path, str(window), str(threads), str(segment)], capture_output=True)
         assert r1.returncode == r0.returncode, (trial, body[:200])
         if r0.returncode == 0:
-            assert r1.stdout == r0.stdout, (trial, window, threads)
+            assert r1.stdout == r0.stdout, (trial, window, threads, segment)
         else:
             rejected += 1
         if ref_prefix and trial % 2 == 0:
@@ -208,4 +216,6 @@ def test_fast_fastq_parser_random_files(harness, tmp_path):
                 pinned += 1
         fast += b"fastq:fast" in r1.stderr
         handed += b"fastq:sequential" in r1.stderr
+        midfile += b"fastq:sequential from" in r1.stderr and b"from 0\n" not in r1.stderr
+    assert midfile >= 5
     assert fast >= 40 and handed >= 10 and rejected >= 5 and (pinned >= 30 or not ref_prefix)

@@ -751,11 +751,13 @@ def test_cli_fastq_fast_path_equals_sequential_path(small_index, many_reads, tmp
             f.write(body if trail else body.rstrip("\r\n"))
         for flags in (["-P", "-c"], ["-M", "-d"]) if name == "a_fq.fa" else (["-P"],):
             want, err0 = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, path, flags)
-            for env in ({}, {"SPUMONI_B200_BATCH_MB": "1"}, {"SPUMONI_B200_BATCH_MB": "2", "SPUMONI_B200_WRITE": "pwrite"}):
+            for env in ({}, {"SPUMONI_B200_BATCH_MB": "1", "SPUMONI_B200_FASTQ_SEGMENT_MB": "3"},
+                        {"SPUMONI_B200_BATCH_MB": "2", "SPUMONI_B200_WRITE": "pwrite", "SPUMONI_B200_FASTQ_SEGMENT_MB": "1"}):
                 got, err = _cli_run(env, prefix, path, flags + ["-t", "5"])
                 assert got == want, (name, flags, env)
                 assert err.split("finished processing")[1].split()[0] == err0.split("finished processing")[1].split()[0]
-    # an empty header line skips the rest of its batch, a bad one is fatal: the sequential parser takes the whole file
+    # an empty header line skips the rest of its batch, a bad one is fatal: the sequential parser takes over -- from the top of
+    # the file, or from the batch boundary where the segment with the odd record begins (segments of 1 MB: mid-file)
     odd = str(tmp_path / "odd_fq.fa")
     with open(odd, "w") as f:
         f.write("".join("@r%d\n%s\n+\n%s\n" % (i, q, "I" * len(q)) for i, (_, q) in enumerate(recs[:3000]) if q))
@@ -763,6 +765,9 @@ def test_cli_fastq_fast_path_equals_sequential_path(small_index, many_reads, tmp
         f.write("".join("@s%d\n%s\n+\n%s\n" % (i, q, "I" * len(q)) for i, (_, q) in enumerate(recs[:3000]) if q))
     want, _ = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, odd, ["-P"])
     got, _ = _cli_run({"SPUMONI_B200_BATCH_MB": "1"}, prefix, odd, ["-P", "-t", "4"])
+    mid, _ = _cli_run({"SPUMONI_B200_BATCH_MB": "1", "SPUMONI_B200_FASTQ_SEGMENT_MB": "1"}, prefix, odd, ["-P", "-c", "-t", "4"])
+    want_c, _ = _cli_run({"SPUMONI_B200_SEQUENTIAL": "1"}, prefix, odd, ["-P", "-c"])
+    assert mid == want_c and os.path.getsize(odd) > (2 << 20)
     n_written = got[".pseudo_lengths"].count(b">")
     assert got == want and 3000 < n_written < 2 * sum(1 for _, q in recs[:3000] if q)
 
