@@ -116,7 +116,10 @@ def test_longest_first_order():
 
 
 # ---- property tests (hypothesis): the planning / transport helpers on arbitrary ragged inputs
-from hypothesis import given, settings, strategies as st  # noqa: E402
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+# deterministic (the driver re-runs this suite: no run-to-run variation) and no health-check verdicts on generation cost
+_PROP = dict(deadline=None, derandomize=True, suppress_health_check=list(HealthCheck))
 
 _lens = st.lists(st.integers(min_value=0, max_value=3000), min_size=1, max_size=300)
 
@@ -127,7 +130,7 @@ def _offsets(lens):
     return off
 
 
-@settings(max_examples=120, deadline=None)
+@settings(max_examples=120, **_PROP)
 @given(_lens, st.integers(1, 9))
 def test_prop_shards_tile_the_reads(lens, n_shards):
     off = _offsets(lens)
@@ -138,7 +141,7 @@ def test_prop_shards_tile_the_reads(lens, n_shards):
         assert int(off[cuts[s]]) >= total * s // n_shards or cuts[s] == len(lens)
 
 
-@settings(max_examples=120, deadline=None)
+@settings(max_examples=120, **_PROP)
 @given(_lens, st.integers(1, 50), st.integers(1, 5000), st.integers(1, 20000))
 def test_prop_chunks_tile_the_reads_and_respect_the_bounds(lens, want_reads, min_bases, max_extra):
     off = _offsets(lens)
@@ -155,7 +158,7 @@ def test_prop_chunks_tile_the_reads_and_respect_the_bounds(lens, want_reads, min
             assert enough or nxt > max_bases
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=80, **_PROP)
 @given(st.binary(min_size=0, max_size=2000), st.booleans())
 def test_prop_pack_round_trip(data, up):
     reads = np.frombuffer(data, dtype=np.uint8)
@@ -171,12 +174,12 @@ def test_prop_pack_round_trip(data, up):
     assert np.all(np.diff(pos.astype(np.int64)) > 0)
 
 
-@settings(max_examples=80, deadline=None)
-@given(_lens, st.randoms(use_true_random=False))
-def test_prop_bits_and_clamped_lengths_are_lossless(lens, rnd):
+@settings(max_examples=80, **_PROP)
+@given(_lens, st.integers(0, 2**32 - 1))
+def test_prop_bits_and_clamped_lengths_are_lossless(lens, seed):
     off = _offsets(lens)
     total = int(off[-1])
-    m = np.array([rnd.random() < 0.93 for _ in range(total)], dtype=bool)
+    m = np.random.RandomState(seed).random_sample(total) < 0.93  # (one drawn seed: a draw per base exhausts hypothesis' entropy budget)
     L = np.zeros(total, dtype=np.uint32)
     for r in range(len(lens)):
         l = 0
@@ -190,7 +193,7 @@ def test_prop_bits_and_clamped_lengths_are_lossless(lens, rnd):
     assert np.array_equal(sp.widen_lengths(np.minimum(L, 255).astype(np.uint8), off), L)
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=80, **_PROP)
 @given(_lens)
 def test_prop_longest_first_order_is_a_permutation(lens):
     off = _offsets(lens)
