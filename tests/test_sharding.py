@@ -40,7 +40,10 @@ def _worker(rank, world, ref, port, out_dir):
 
 def test_index_broadcast_gloo_world2(small_index, tmp_path):
     import torch.multiprocessing as mp
-    port = 29500 + (os.getpid() % 2000)
+    import socket
+    with socket.socket() as sk:  # a port that is free right now
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     mp.spawn(_worker, args=(2, small_index["ref"], port, str(tmp_path)), nprocs=2, join=True)
     b0, b1 = np.load(tmp_path / "blob0.npy"), np.load(tmp_path / "blob1.npy")
     assert b0.nbytes > 4096 and np.array_equal(b0, b1)
